@@ -1,0 +1,197 @@
+"""NumPy restatement of the reference's synthesis processors (the hot path).
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Each function cites the
+reference lines it follows (paths relative to ``/root/reference/ddsp_piano``).
+The dtype of the inputs selects the precision: float32 is the TF-faithful
+restatement, float64 the ground-truth variant.
+
+Pinned against ``tests/golden/*.npz`` -- vectors produced by executing the
+reference's own ``modules/inharm_synth.py`` / ``filtered_noise_synth.py`` /
+``polyphonic_dag.py`` over the NumPy ``tensorflow``/``ddsp`` stand-in of
+``oracle/tf_shim`` (generator: ``tests/golden/make_golden.py``).  The ddsp/TF
+layer underneath is restated, not imported: parity for it is unpinned.
+"""
+import numpy as np
+
+from . import ddsp_core_np as core
+
+SCALE_EXP_SIGMOID = 'exp_sigmoid'
+SCALE_EXP_TANH = 'exp_tanh'
+SCALE_NONE = None
+
+
+def exp_tanh(x, max_value=2., exponent=10., gain=1., threshold=1e-7):
+    """modules/inharm_synth.py:8-17 -- tanh flavoured exp_sigmoid."""
+    x = core.tf_float32(x)
+    dt = x.dtype.type
+    pos = dt(0.5) * (np.tanh(dt(gain) * x) + dt(1.))
+    return dt(max_value) * pos ** dt(np.log(exponent)) + dt(threshold)
+
+
+def _scale(name):
+    if name in (SCALE_EXP_SIGMOID, 'core.exp_sigmoid'):
+        return core.exp_sigmoid
+    if name == SCALE_EXP_TANH:
+        return exp_tanh
+    if name is None:
+        return None
+    if callable(name):
+        return name
+    raise ValueError(f'unknown scale_fn {name!r}')
+
+
+def inharmonic_frequencies(f0_hz, inharm_coef, n_harmonics):
+    """modules/inharm_synth.py:20-46: partial k at f0*k*sqrt(1 + B*k^2)."""
+    dt = f0_hz.dtype.type
+    k = np.linspace(1.0, float(n_harmonics), int(n_harmonics)).astype(dt)[None, None, :]
+    stretch = np.sqrt(np.power(k, dt(2)) * inharm_coef + dt(1.))
+    return f0_hz * k * stretch, stretch - dt(1.)
+
+
+def oscillator_bank(freq_env, amp_env, sample_rate, angular):
+    """modules/inharm_synth.py:49-84 (cos_oscillator_bank), sum_sinusoids=True."""
+    dt = freq_env.dtype.type
+    amp_env = core.remove_above_nyquist(freq_env, amp_env, sample_rate)     # :65-67
+    omega = freq_env * dt(2.0 * np.pi)                                        # :69
+    omega = omega / dt(float(sample_rate))                                    # :70
+    if angular:
+        phase = core.angular_cumsum(omega)                                    # :75
+    else:
+        phase = np.cumsum(omega, axis=1, dtype=dt)                            # :77
+    return np.sum(amp_env * np.cos(phase), axis=-1, dtype=dt)                 # :80-83
+
+
+def additive_controls(amplitudes, harmonic_distribution, inharm_coef, f0_hz, *,
+                      sample_rate, min_frequency=20, scale_fn=SCALE_EXP_SIGMOID,
+                      normalize_after_nyquist_cut=True, normalize_below_nyquist=True):
+    """MultiInharmonic.get_controls, modules/inharm_synth.py:254-270 on top of
+    InHarmonic.get_controls :167-219.  f0_hz is [B, F, S]."""
+    amplitudes = core.tf_float32(amplitudes)
+    harmonic_distribution = core.tf_float32(harmonic_distribution)
+    inharm_coef = core.tf_float32(inharm_coef)
+    f0_hz = core.tf_float32(f0_hz)
+    dt = f0_hz.dtype.type
+    f0_first = f0_hz[..., 0:1]                                                # :262
+    fn = _scale(scale_fn)
+    inharm_coef = np.maximum(inharm_coef, dt(0.))                             # :183
+    if fn is not None:                                                        # :184-186
+        amplitudes = fn(amplitudes)
+        harmonic_distribution = fn(harmonic_distribution)
+    n_harm = int(harmonic_distribution.shape[-1])
+    partial_hz, shifts = inharmonic_frequencies(f0_first, inharm_coef, n_harm)
+    if not normalize_after_nyquist_cut:                                       # :194-198
+        harmonic_distribution = core.safe_divide(
+            harmonic_distribution, np.sum(harmonic_distribution, -1, keepdims=True))
+    if normalize_below_nyquist:                                               # :200-208
+        harmonic_distribution = core.remove_above_nyquist(
+            partial_hz, harmonic_distribution, sample_rate)
+        amplitudes = amplitudes * (f0_first > dt(min_frequency)).astype(dt)
+    if normalize_after_nyquist_cut:                                           # :210-214
+        harmonic_distribution = core.safe_divide(
+            harmonic_distribution, np.sum(harmonic_distribution, -1, keepdims=True))
+    amplitudes = amplitudes / dt(f0_hz.shape[-1])                             # :269
+    return {'amplitudes': amplitudes,
+            'harmonic_distribution': harmonic_distribution,
+            'harmonic_shifts': shifts,
+            'f0_hz': f0_hz}
+
+
+def additive_signal(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, *,
+                    sample_rate, frame_rate=250, inference=True):
+    """MultiInharmonic.get_signal, modules/inharm_synth.py:272-293: one full
+    harmonic_synthesis (:87-127) per substring, summed."""
+    amplitudes = core.tf_float32(amplitudes)
+    harmonic_distribution = core.tf_float32(harmonic_distribution)
+    harmonic_shifts = core.tf_float32(harmonic_shifts)
+    f0_hz = core.tf_float32(f0_hz)
+    dt = f0_hz.dtype.type
+    upsampling = int(sample_rate / frame_rate)                                # :163-165
+    n_samples = upsampling * f0_hz.shape[1]                                   # :240
+    n_harm = harmonic_distribution.shape[-1]
+    audio = None
+    for s in range(f0_hz.shape[-1]):
+        partial_hz = core.get_harmonic_frequencies(f0_hz[..., s:s + 1], n_harm)   # :106
+        partial_hz = partial_hz * (dt(1.0) + harmonic_shifts)                 # :107-108
+        partial_amp = amplitudes * harmonic_distribution                      # :111-114
+        freq_env = core.resample(partial_hz, n_samples)                       # :117
+        amp_env = core.resample(partial_amp, n_samples, method='window')      # :118-119
+        y = oscillator_bank(freq_env, amp_env, sample_rate, inference)        # :122-126
+        audio = y if audio is None else audio + y                             # :286-292
+    return audio
+
+
+def noise_controls(magnitudes, *, initial_bias=-5.0, scale_fn=SCALE_EXP_SIGMOID):
+    """ddsp.synths.FilteredNoise.get_controls (inherited by
+    modules/filtered_noise_synth.py:13): scale_fn(magnitudes + initial_bias)."""
+    magnitudes = core.tf_float32(magnitudes)
+    fn = _scale(scale_fn)
+    if fn is not None:
+        magnitudes = fn(magnitudes + magnitudes.dtype.type(initial_bias))
+    return {'magnitudes': magnitudes}
+
+
+def noise_signal(magnitudes, noise, *, window_size=257):
+    """DynamicSizeFilteredNoise.get_signal, modules/filtered_noise_synth.py:27-42.
+    The reference draws ``tf.random.uniform([B, N], -1, 1)`` unseeded (:39-40);
+    the oracle takes that tensor as an argument so parity is definable."""
+    magnitudes = core.tf_float32(magnitudes)
+    noise = core.tf_float32(noise)
+    return core.frequency_filter(noise, magnitudes, window_size=window_size)    # :41-42
+
+
+def reverb_signal(audio, ir, *, add_dry=True):
+    """ddsp.effects.Reverb.get_signal (configured configs/dafx22.gin:99-100,111):
+    zero ir[:, 0], one-block FFT convolution with delay_compensation=0, plus dry."""
+    audio, ir = core.tf_float32(audio), core.tf_float32(ir)
+    if ir.ndim == 1:
+        ir = ir[None, :]
+    if ir.ndim == 3:
+        ir = ir[:, :, 0]
+    ir = np.concatenate([np.zeros([ir.shape[0], 1], ir.dtype), ir[:, 1:]], axis=1)
+    wet = core.fft_convolve(audio, ir, padding='same', delay_compensation=0)
+    return (wet + audio) if add_dry else wet
+
+
+def exponential_decay_mask(ir, decay_exponent=4., decay_start=16000):
+    """modules/sub_modules.py:339-349 (MultiInstrumentReverb, inference only)."""
+    ir = core.tf_float32(ir)
+    dt = ir.dtype.type
+    length = ir.shape[-1]
+    time = np.linspace(0.0, 1.0, length - decay_start).astype(dt)
+    mask = np.concatenate([np.ones(decay_start, dt), np.exp(-dt(decay_exponent) * time)])
+    return ir * mask[None, :]
+
+
+def polyphonic_forward(features, *, n_synths, sample_rate, frame_rate=250,
+                       inference=True, noise_by_voice=None, add_dry=True,
+                       scale_fn=SCALE_EXP_SIGMOID, noise_scale_fn=SCALE_EXP_SIGMOID,
+                       normalize_after_nyquist_cut=True, normalize_below_nyquist=True,
+                       window_size=257, initial_bias=-5.0, reverb=True):
+    """The DAG of modules/polyphonic_dag.py:21-42 as wired by configs/dafx22.gin:91-100:
+    per voice additive + noise, running sum 'add' (MultiAdd, inharm_synth.py:296-309,
+    python sum() = ((0 + a) + b) + c), then reverb on the sum.
+
+    features: dict with amplitudes_i, harmonic_distribution_i, inharm_coef_i, f0_hz_i,
+    magnitudes_i (i < n_synths) and reverb_ir.  noise_by_voice: list of [B, N] arrays.
+    Returns dict(dry=[B, N], signal=[B, N], additive=[...per voice], noise=[...])."""
+    dry = None
+    add_sigs, noise_sigs = [], []
+    for v in range(n_synths):
+        c = additive_controls(features[f'amplitudes_{v}'],
+                              features[f'harmonic_distribution_{v}'],
+                              features[f'inharm_coef_{v}'], features[f'f0_hz_{v}'],
+                              sample_rate=sample_rate, scale_fn=scale_fn,
+                              normalize_after_nyquist_cut=normalize_after_nyquist_cut,
+                              normalize_below_nyquist=normalize_below_nyquist)
+        a = additive_signal(**c, sample_rate=sample_rate, frame_rate=frame_rate,
+                            inference=inference)
+        m = noise_controls(features[f'magnitudes_{v}'], initial_bias=initial_bias,
+                           scale_fn=noise_scale_fn)
+        n = noise_signal(m['magnitudes'], noise_by_voice[v], window_size=window_size)
+        add_sigs.append(a)
+        noise_sigs.append(n)
+        dry = (n + a) if dry is None else (dry + n) + a        # polyphonic_dag.py:28-37
+    out = dry
+    if reverb:
+        out = reverb_signal(dry, features['reverb_ir'], add_dry=add_dry)
+    return {'dry': dry, 'signal': out, 'additive': add_sigs, 'noise': noise_sigs}

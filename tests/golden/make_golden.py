@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING the reference's own Python for the hot path.
+
+Runs in the build container only (needs /root/reference, which does not exist on the
+GPU box).  The reference's ``ddsp_piano/modules/{inharm_synth,filtered_noise_synth,
+polyphonic_dag}.py`` are loaded unmodified by file path; ``tensorflow``/``gin``/``ddsp``
+resolve to the NumPy stand-ins under ``oracle/tf_shim`` (TensorFlow and ddsp are not
+installable here -- see oracle/__init__.py for what that does and does not pin).
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('DDSP_PIANO_REFERENCE', '/root/reference')
+
+
+def load_reference_modules():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf_shim'))
+    sys.path.insert(0, ROOT)
+    for pkg in ('ddsp_piano', 'ddsp_piano.modules'):
+        m = types.ModuleType(pkg)
+        m.__path__ = []
+        sys.modules[pkg] = m
+    mods = {}
+    for name in ('inharm_synth', 'filtered_noise_synth', 'polyphonic_dag'):
+        full = f'ddsp_piano.modules.{name}'
+        spec = importlib.util.spec_from_file_location(
+            full, os.path.join(REF, 'ddsp_piano', 'modules', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    return mods
+
+
+def midi_hz(m):
+    return 440.0 * 2.0 ** ((np.asarray(m, np.float64) - 69.0) / 12.0)
+
+
+def make_voice_inputs(rng, B, F, H, S, M, onsets=True, silent=False):
+    """Pre-get_controls tensors for one voice (BASELINE.md section 3 distributions)."""
+    f0 = np.empty([B, F, S], np.float32)
+    for b in range(B):
+        k = 0
+        while k < F:
+            seg = int(rng.integers(4, 9)) if onsets else F
+            if silent or (onsets and rng.random() < 0.25):
+                hz = 8.1758                     # MIDI pitch 0: gated by min_frequency
+            else:
+                hz = float(midi_hz(rng.integers(21, 109)))
+            for s in range(S):
+                f0[b, k:k + seg, s] = hz * (1.0 + 1e-3 * s)
+            k += seg
+    return {
+        'amplitudes': rng.standard_normal([B, F, 1]).astype(np.float32),
+        'harmonic_distribution': rng.standard_normal([B, F, H]).astype(np.float32),
+        'inharm_coef': rng.uniform(1e-4, 1e-3, [B, F, 1]).astype(np.float32),
+        'f0_hz': f0,
+        'magnitudes': rng.standard_normal([B, F, M]).astype(np.float32),
+    }
+
+
+def main():
+    mods = load_reference_modules()
+    import tensorflow as tf_shim           # the stand-in
+    from ddsp import processors, effects   # the stand-in
+    inh, fns, dag = mods['inharm_synth'], mods['filtered_noise_synth'], mods['polyphonic_dag']
+    rng = np.random.default_rng(20221017)
+
+    def save(name, **arrays):
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, **arrays)
+        print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
+
+    # ---- additive: MultiInharmonic.get_controls + get_signal ------------------------
+    add_cases = {
+        # name: (sr, F, B, H, S, ctor kwargs)
+        'additive_24k_inference': (24000, 25, 2, 96, 2, dict(inference=True)),
+        'additive_16k_training': (16000, 20, 2, 32, 2, dict(inference=False)),
+        'additive_48k_h128': (48000, 12, 1, 128, 2, dict(inference=True)),
+        'additive_16k_exp_tanh_prenorm': (16000, 20, 1, 48, 3, dict(
+            inference=True, scale_fn=inh.exp_tanh, normalize_after_nyquist_cut=False)),
+        'additive_24k_single_string': (24000, 12, 1, 64, 1, dict(inference=True)),
+    }
+    for name, (sr, F, B, H, S, kw) in add_cases.items():
+        x = make_voice_inputs(rng, B, F, H, S, 8)
+        synth = inh.MultiInharmonic(frame_rate=250, sample_rate=sr, name='additive', **kw)
+        ctl = synth.get_controls(x['amplitudes'].copy(), x['harmonic_distribution'].copy(),
+                                 x['inharm_coef'].copy(), x['f0_hz'].copy())
+        sig = synth.get_signal(**{k: v.copy() for k, v in ctl.items()})
+        assert sig.dtype == np.float32 and sig.shape == (B, F * (sr // 250))
+        save(name, sample_rate=sr, inference=bool(kw.get('inference', False)),
+             scale_fn='exp_tanh' if 'scale_fn' in kw else 'exp_sigmoid',
+             normalize_after_nyquist_cut=kw.get('normalize_after_nyquist_cut', True),
+             in_amplitudes=x['amplitudes'], in_harmonic_distribution=x['harmonic_distribution'],
+             in_inharm_coef=x['inharm_coef'], in_f0_hz=x['f0_hz'],
+             ctl_amplitudes=ctl['amplitudes'],
+             ctl_harmonic_distribution=ctl['harmonic_distribution'],
+             ctl_harmonic_shifts=ctl['harmonic_shifts'], ctl_f0_hz=ctl['f0_hz'],
+             signal=sig)
+
+    # ---- noise: DynamicSizeFilteredNoise with injected uniform noise ----------------
+    for name, (sr, F, B, M) in {'noise_24k_m64': (24000, 25, 2, 64),
+                                'noise_48k_m96': (48000, 10, 1, 96),
+                                'noise_16k_m64': (16000, 20, 1, 64)}.items():
+        mags = rng.standard_normal([B, F, M]).astype(np.float32) * 2.0 + 3.0
+        noise = rng.uniform(-1, 1, [B, F * (sr // 250)]).astype(np.float32)
+        synth = fns.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, name='noise')
+        ctl = synth.get_controls(mags.copy())
+        tf_shim.push_noise(noise)
+        sig = synth.get_signal(**ctl)
+        assert sig.dtype == np.float32 and sig.shape == noise.shape
+        save(name, sample_rate=sr, in_magnitudes=mags, noise=noise,
+             ctl_magnitudes=ctl['magnitudes'], signal=sig)
+
+    # ---- reverb: ddsp.effects.Reverb (stand-in; no reference source exists) ---------
+    for name, (N, L, B, add_dry) in {'reverb_n2400_l1000': (2400, 1000, 2, True),
+                                     'reverb_n2400_l2400_wet': (2400, 2400, 1, False)}.items():
+        audio = rng.standard_normal([B, N]).astype(np.float32) * 0.1
+        t = np.arange(L) / L
+        ir = (rng.standard_normal([B, L]) * np.exp(-6 * t) * 1e-2).astype(np.float32)
+        rv = effects.Reverb(trainable=False, add_dry=add_dry)
+        sig = rv(audio, ir)
+        save(name, add_dry=add_dry, audio=audio, ir=ir, signal=sig)
+
+    # ---- the DAG: reference polyphonic_dag through ProcessorGroup -------------------
+    sr, F, B, H, S, M, P, L = 24000, 25, 2, 96, 2, 64, 3, 1500
+    feats, noises = {}, []
+    for v in range(P):
+        x = make_voice_inputs(rng, B, F, H, S, M, silent=(v == 2))
+        for k, a in x.items():
+            feats[f'{k}_{v}'] = a
+        noises.append(rng.uniform(-1, 1, [B, F * (sr // 250)]).astype(np.float32))
+    t = np.arange(L) / L
+    feats['reverb_ir'] = (rng.standard_normal([B, L]) * np.exp(-6 * t) * 1e-2).astype(np.float32)
+    nodes = dag.polyphonic_dag(
+        additive=inh.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True,
+                                     name='additive'),
+        additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+        noise=fns.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, name='noise'),
+        noise_controls=['magnitudes'],
+        reverb=effects.Reverb(trainable=False), reverb_controls=['reverb_ir'], n_synths=P)
+    group = processors.ProcessorGroup(dag=nodes)
+    for n in noises:
+        tf_shim.push_noise(n)
+    out = group({k: v.copy() for k, v in feats.items()}, return_outputs_dict=True)
+    arrays = {f'in_{k}': v for k, v in feats.items()}
+    for v in range(P):
+        arrays[f'noise_{v}'] = noises[v]
+    save('dag_24k_p3', sample_rate=sr, n_synths=P,
+         node_names=np.array([n[0].name for n in nodes]),
+         dry=out['controls']['add']['signal'], signal=out['signal'],
+         last_additive=out['controls']['additive']['signal'],
+         last_noise=out['controls']['noise']['signal'], **arrays)
+
+
+if __name__ == '__main__':
+    main()
