@@ -1,0 +1,276 @@
+// The inharmonic additive oscillator bank: MultiInharmonic.get_signal
+// (reference modules/inharm_synth.py:272-293 -> harmonic_synthesis :87-127 ->
+// cos_oscillator_bank :49-84, with ddsp.core.resample / angular_cumsum underneath).
+//
+// Data flow per (clip b, voice v, substring s, partial h), sample t = k*U + r:
+//   F_k[h]  = (f0[k,s] * n) * (1 + shift_k[h])                 frame-rate partial frequency
+//   A_k[h]  = amp_k * hd_k[h]                                   frame-rate partial amplitude
+//   f[t]    = F_lo + (F_hi - F_lo) * (in - lo),  in = float(t) * float(F/N)   (legacy bilinear)
+//   a[t]    = A_k * w[r+U] + A_{k+1} * w[r]                     (Hann overlap-add upsampling)
+//   omega   = (f * 2pi) / sr ;  phase = cumsum within the 1000-sample chunk (float32,
+//             sequential) ; p = floormod(phase + chunk_offset, 2pi) ; y[t] += a * cos(p)
+//
+// The float32 phase path is reproduced operation for operation (unfused mul/add, IEEE
+// division, sequential adds) because rounding noise of the reference's cumsum is part of
+// its output; everything that is not accumulated (amplitudes, cos, the sums over
+// partials/voices) only has to be accurate.
+//
+// Three launches: (1) `ends` pass = the phase chain alone, one value per (oscillator,
+// chunk); (2) a tiny scan turning chunk ends into chunk offsets; (3) the synthesis pass.
+// Work decomposition of (1) and (3): CTA = (chunk, clip, voice group); each warp takes
+// (voice, substring) pairs round-robin; lane l owns partials l, l+32, ... (HP per lane),
+// so per-sample work that does not depend on the partial (lerp weight, window weights) is
+// shared by HP oscillators and the per-frame control loads are coalesced.
+#pragma once
+#include "common.cuh"
+
+namespace b200ddsp {
+
+constexpr int kAddWarps = 8;
+constexpr int kAddThreads = kAddWarps * kWarp;
+constexpr int kMaxChunk = 1024;   // smem row length; ddsp's chunk_size is 1000
+
+struct AdditiveArgs {
+  const float* amp;     // [R, F]     R = P*B rows, row = v*B + b (voice-major, sub_modules.py:589-596)
+  const float* hd;      // [R, F, H]
+  const float* shifts;  // [R, F, H]
+  const float* f0;      // [R, F, S]
+  float* offsets;       // [R*S, n_chunks, H]: chunk end phases (pass 1), then chunk offsets (scan)
+  float* out;           // [G, B, N]
+  const float* window;  // [2U]  tf.signal.hann_window(2U, periodic)
+  int B, P, F, H, S, U, N;
+  int chunk, n_chunks;
+  int voices_per_group;
+  int accumulate;       // out += (only honoured when gridDim.z == 1)
+  float scale;          // float32(F) / float32(N)
+  float nyquist;        // float32(sr / 2)
+  float sr;             // float32(sr)
+  float inv_sr;         // float32(1 / sr)
+};
+
+// x / sr, correctly rounded.  FASTDIV: q0 = x*(1/sr), one Newton step on the exact FMA
+// remainder -- b200ddsp_create() verifies on the host, over all 2^23 mantissas, that this
+// equals IEEE division for the configured sample rate before selecting this path.
+template <bool FASTDIV>
+__device__ __forceinline__ float div_sr(float x, float sr, float inv_sr) {
+  if (FASTDIV) {
+    const float q = __fmul_rn(x, inv_sr);
+    const float e = __fmaf_rn(-q, sr, x);
+    return __fmaf_rn(e, inv_sr, q);
+  }
+  return __fdiv_rn(x, sr);
+}
+
+__device__ __forceinline__ float transpose_reduce32(float (&y)[32], int lane) {
+  // 32 lanes x 32 values -> lane l returns sum over lanes of y[l].  31 shuffles.
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? y[i] : y[i + o];
+      const float keep = up ? y[i + o] : y[i];
+      y[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return y[0];
+}
+
+template <int HP>
+struct FrameRegs {
+  float F[HP];  // partial frequencies of a control frame
+  float A[HP];  // partial amplitudes of a control frame
+};
+
+template <int HP, bool WITH_AMP>
+__device__ __forceinline__ void load_frame(const AdditiveArgs& a, int row, int s, int k, int lane,
+                                           FrameRegs<HP>& fr) {
+  const float f0 = __ldg(a.f0 + ((size_t)row * a.F + k) * a.S + s);
+  const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + k) : 0.f;
+  const size_t base = ((size_t)row * a.F + k) * a.H;
+#pragma unroll
+  for (int q = 0; q < HP; ++q) {
+    const int h = lane + 32 * q;
+    fr.F[q] = 0.f;
+    fr.A[q] = 0.f;
+    if (h < a.H) {
+      const float n = (float)(h + 1);
+      const float sh = __ldg(a.shifts + base + h);
+      // get_harmonic_frequencies (f0 * n), then *= (1.0 + shifts)   inharm_synth.py:106-108
+      fr.F[q] = __fmul_rn(__fmul_rn(f0, n), __fadd_rn(1.0f, sh));
+      if (WITH_AMP) fr.A[q] = __fmul_rn(amp, __ldg(a.hd + base + h));   // :111-114
+    }
+  }
+}
+
+// G samples per group: every group lies inside one control frame and one chunk
+// (G = 8 needs U % 8 == 0 and chunk % 8 == 0; G = 1 is the generic path).
+// FAST: floor(float(t)*scale) == t / U for every t (checked on the host) and the 3-op
+// division is exact; otherwise the lerp frame is decided per sample and __fdiv_rn is used.
+template <int HP, int G, bool FAST, bool ENDS_ONLY>
+__global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArgs a) {
+  extern __shared__ float smem[];
+  float* win = smem;                                   // [2U]
+  float* rows = smem + ((2 * a.U + 31) & ~31);         // [kAddWarps][kMaxChunk]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;   // <= kAddThreads / kAddWarps
+  const int c = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  const int t0 = c * a.chunk;
+  const int t1 = min(a.N, t0 + a.chunk);
+
+  if (!ENDS_ONLY) {
+    for (int i = threadIdx.x; i < 2 * a.U; i += n_threads) win[i] = a.window[i];
+    for (int i = threadIdx.x; i < n_warps * kMaxChunk; i += n_threads) rows[i] = 0.f;
+    __syncthreads();
+  }
+
+  const int v_begin = g * a.voices_per_group;
+  const int v_end = min(a.P, v_begin + a.voices_per_group);
+  const int n_pairs = (v_end - v_begin) * a.S;
+  const float two_pi = kTwoPi;
+
+  for (int pair = warp; pair < n_pairs; pair += n_warps) {
+    const int v = v_begin + pair / a.S;
+    const int s = pair - (pair / a.S) * a.S;
+    const int row = v * a.B + b;
+
+    int k = t0 / a.U;
+    int r = t0 - k * a.U;
+    FrameRegs<HP> cur, nxt;
+    float dF[HP], ph[HP], off[HP];
+    float Fprev[HP], dFprev[HP];   // generic path only: the frame below (lo == k-1)
+    load_frame<HP, !ENDS_ONLY>(a, row, s, k, lane, cur);
+    load_frame<HP, !ENDS_ONLY>(a, row, s, min(k + 1, a.F - 1), lane, nxt);
+    const size_t off_base = (((size_t)row * a.S + s) * a.n_chunks + c) * a.H;
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+      dF[q] = __fadd_rn(nxt.F[q], -cur.F[q]);
+      ph[q] = 0.f;
+      off[q] = 0.f;
+      Fprev[q] = cur.F[q];
+      dFprev[q] = 0.f;
+      const int h = lane + 32 * q;
+      if (!ENDS_ONLY && c > 0 && h < a.H) off[q] = a.offsets[off_base + h];
+    }
+    if (!FAST && k > 0) {
+      FrameRegs<HP> prv;
+      load_frame<HP, false>(a, row, s, k - 1, lane, prv);
+#pragma unroll
+      for (int q = 0; q < HP; ++q) {
+        Fprev[q] = prv.F[q];
+        dFprev[q] = __fadd_rn(cur.F[q], -prv.F[q]);
+      }
+    }
+
+    float tf = (float)t0;
+    int t = t0;
+    int pos = 0;
+    while (t < t1) {
+      float y[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) y[i] = 0.f;
+#pragma unroll
+      for (int gi = 0; gi < 32 / G; ++gi) {
+        if (t < t1) {
+          if (r == a.U) {   // next control frame (warp-uniform)
+            r = 0;
+            ++k;
+#pragma unroll
+            for (int q = 0; q < HP; ++q) {
+              Fprev[q] = cur.F[q];
+              dFprev[q] = dF[q];
+              cur.F[q] = nxt.F[q];
+              cur.A[q] = nxt.A[q];
+            }
+            load_frame<HP, !ENDS_ONLY>(a, row, s, min(k + 1, a.F - 1), lane, nxt);
+#pragma unroll
+            for (int q = 0; q < HP; ++q) dF[q] = __fadd_rn(nxt.F[q], -cur.F[q]);
+          }
+          const float kf = (float)k;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            // legacy ResizeBilinear coordinates: in = float(i) * scale, lerp = in - floor(in)
+            const float in = __fmul_rn(tf, a.scale);
+            float frac = __fadd_rn(in, -kf);
+            bool below = false;
+            if (!FAST) {
+              const float lo = floorf(in);
+              below = lo < kf;
+              frac = __fadd_rn(in, -lo);
+            }
+            float w0 = 0.f, w1 = 0.f;
+            if (!ENDS_ONLY) {
+              w0 = win[r + j];          // rising half: weight of frame k+1
+              w1 = win[r + j + a.U];    // falling half: weight of frame k
+            }
+#pragma unroll
+            for (int q = 0; q < HP; ++q) {
+              float f;
+              if (!FAST && below) {
+                f = __fadd_rn(Fprev[q], __fmul_rn(dFprev[q], frac));
+              } else {
+                f = __fadd_rn(cur.F[q], __fmul_rn(dF[q], frac));       // top + (bottom-top)*lerp
+              }
+              const float om = div_sr<FAST>(__fmul_rn(f, two_pi), a.sr, a.inv_sr);  // :69-70
+              ph[q] = __fadd_rn(ph[q], om);                            // in-chunk cumsum
+              if (!ENDS_ONLY) {
+                float amp = __fmaf_rn(cur.A[q], w1, __fmul_rn(nxt.A[q], w0));
+                amp = (f >= a.nyquist) ? 0.f : amp;                    // :65-67
+                const float p = wrap_to_pi(__fadd_rn(ph[q], off[q]));
+                y[gi * G + j] = __fmaf_rn(amp, __cosf(p), y[gi * G + j]);   // :80-83
+              }
+            }
+            tf += 1.0f;
+          }
+          r += G;
+          t += G;
+        }
+      }
+      if (!ENDS_ONLY) {
+        const float ysum = transpose_reduce32(y, lane);
+        rows[warp * kMaxChunk + pos + lane] += ysum;   // pos + lane < kMaxChunk always
+      }
+      pos += 32;
+    }
+
+    if (ENDS_ONLY) {
+      // chunk end phase mod 2pi (ddsp angular_cumsum: offsets = phase[:, :, -1] % 2pi)
+#pragma unroll
+      for (int q = 0; q < HP; ++q) {
+        const int h = lane + 32 * q;
+        if (h < a.H) a.offsets[off_base + h] = floormod_two_pi(ph[q]);
+      }
+    }
+  }
+
+  if (!ENDS_ONLY) {
+    __syncthreads();
+    float* out = a.out + ((size_t)g * a.B + b) * a.N + t0;
+    const int len = t1 - t0;
+    for (int i = threadIdx.x; i < len; i += n_threads) {
+      float acc = rows[i];
+      for (int w = 1; w < n_warps; ++w) acc += rows[w * kMaxChunk + i];
+      if (a.accumulate) acc += out[i];
+      out[i] = acc;
+    }
+  }
+}
+
+// Chunk end phases -> chunk offsets, in place (ddsp angular_cumsum: shift down one chunk,
+// cumsum over chunks in float32, then mod 2pi).  One thread per (row, substring, partial).
+__global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets, int n_osc_rows,
+                                                                int n_chunks, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_osc_rows * H) return;
+  const int rs = i / H, h = i - rs * H;
+  float* p = offsets + (size_t)rs * n_chunks * H + h;
+  float cum = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const float e = (c < n_chunks - 1) ? p[(size_t)c * H] : 0.f;
+    p[(size_t)c * H] = floormod_two_pi(cum);
+    cum = __fadd_rn(cum, e);
+  }
+}
+
+}  // namespace b200ddsp

@@ -1,0 +1,675 @@
+// libb200ddsp.so -- C ABI (include/b200ddsp.h) over the sm_100a kernels of this directory.
+// Host side only: argument validation, workspace carving, launch configuration.  Nothing here
+// allocates device memory after b200ddsp_create(); every launch goes to the caller's stream.
+#include "../../include/b200ddsp.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "additive.cuh"
+#include "common.cuh"
+#include "controls.cuh"
+#include "noise.cuh"
+#include "reverb.cuh"
+
+using namespace b200ddsp;
+
+struct b200ddsp_handle {
+  b200ddsp_config cfg;
+  int U = 0;
+  int device = 0;
+  float* d_window = nullptr;   // hann(2U)
+  float* d_cmat_t = nullptr;   // [M][M-1] noise IR matrix
+  bool fast_div = false;       // 3-op division == IEEE division for this sample rate
+  std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
+  unsigned long long launches = 0;
+  char err[512] = {0};
+};
+
+static thread_local char g_create_err[512] = {0};
+
+static int fail(b200ddsp_handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(h, B200DDSP_CUDA_ERROR, "%s failed: %s", #expr, cudaGetErrorString(e_));   \
+  } while (0)
+
+#define CHECK_LAUNCH(h, what)                                                                \
+  do {                                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(h, B200DDSP_CUDA_ERROR, "launch of %s failed: %s", what,                   \
+                  cudaGetErrorString(e_));                                                   \
+    (h)->launches++;                                                                         \
+  } while (0)
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// host-side tables and checks
+// ---------------------------------------------------------------------------------------------
+
+// tf.signal.hann_window(n, periodic=True) evaluated in float32 like TF does.
+static std::vector<float> hann_periodic(int n) {
+  std::vector<float> w(n);
+  for (int i = 0; i < n; ++i) {
+    const float arg = (float)(2.0 * M_PI) * (float)i / (float)n;
+    w[i] = 0.5f - 0.5f * (float)cos((double)arg);
+  }
+  return w;
+}
+
+// Noise FIR as a matrix: tap i = M-1+d (d = 0..M-2) of
+//   c[i] = hann(Lir)[i] * irfft(m)[(i + Lir/2) mod Lir]
+//        = hann[i]/Lir * ( m_0 + (-1)^(i+M-1) m_{M-1} + 2 sum_{j=1}^{M-2} (-1)^j m_j cos(2 pi j i / Lir) )
+// (ddsp.core.frequency_impulse_response + apply_window_to_impulse_response, window_size >= Lir).
+// window_size < Lir would crop the IR; the reference never configures that (window_size = 257).
+static std::vector<float> noise_ir_matrix_t(int M) {
+  const int lir = 2 * (M - 1), nd = M - 1;
+  std::vector<float> hann = hann_periodic(lir);
+  std::vector<float> c((size_t)M * nd);
+  for (int d = 0; d < nd; ++d) {
+    const int i = M - 1 + d;
+    const double wgt = (double)hann[i] / (double)lir;
+    for (int j = 0; j < M; ++j) {
+      double coef;
+      if (j == 0) {
+        coef = 1.0;
+      } else if (j == M - 1) {
+        coef = ((i + M - 1) & 1) ? -1.0 : 1.0;
+      } else {
+        const long long ji = ((long long)j * i) % lir;
+        coef = 2.0 * ((j & 1) ? -1.0 : 1.0) * cos(2.0 * M_PI * (double)ji / (double)lir);
+      }
+      c[(size_t)j * nd + d] = (float)(wgt * coef);
+    }
+  }
+  return c;
+}
+
+// Is q0 = x*r; e = fma(-q0, sr, x); q = fma(e, r, q0) equal to x / sr for every float32 mantissa?
+// (The identity is scale invariant away from underflow/overflow, so one binade suffices.)
+static bool verify_fast_division(float sr) {
+  const float r = 1.0f / sr;
+  for (uint32_t m = 0; m < (1u << 23); ++m) {
+    const uint32_t bits = (127u << 23) | m;
+    float x;
+    memcpy(&x, &bits, 4);
+    const float q0 = x * r;
+    const float e = fmaf(-q0, sr, x);
+    const float q = fmaf(e, r, q0);
+    volatile float want = x / sr;
+    if (q != want) return false;
+  }
+  return true;
+}
+
+// Legacy bilinear resize: is floor(float(t) * float(F/N)) == t / U for every output sample, so
+// that the lerp frame is the amplitude frame?  (False e.g. when float(1/U) rounds down.)
+static bool lerp_is_uniform(b200ddsp_handle* h, int F, int N, int U) {
+  auto key = std::make_pair(F, N);
+  auto it = h->uniform_lerp.find(key);
+  if (it != h->uniform_lerp.end()) return it->second;
+  volatile float scale = (float)F / (float)N;
+  bool ok = true;
+  for (int t = 0; t < N && ok; ++t) {
+    volatile float in = (float)t * scale;
+    ok = ((int)floorf(in) == t / U);
+  }
+  h->uniform_lerp[key] = ok;
+  return ok;
+}
+
+// The generic path still assumes floor(in) is the amplitude frame or the one below it.
+static bool lerp_is_supported(int F, int N, int U) {
+  volatile float scale = (float)F / (float)N;
+  for (int t = 0; t < N; ++t) {
+    volatile float in = (float)t * scale;
+    const int lo = (int)floorf(in), k = t / U;
+    if (lo != k && lo != k - 1) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int b200ddsp_version(void) { return B200DDSP_VERSION; }
+
+extern "C" const char* b200ddsp_last_error(const b200ddsp_handle* h) {
+  return h ? h->err : g_create_err;
+}
+
+extern "C" uint64_t b200ddsp_launch_count(const b200ddsp_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out) {
+  if (!cfg || !out) return fail(nullptr, B200DDSP_BAD_ARGUMENT, "cfg and out must be non-null");
+  *out = nullptr;
+  if (cfg->sample_rate <= 0 || cfg->frame_rate <= 0 || cfg->sample_rate < cfg->frame_rate)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "bad sample_rate/frame_rate %d/%d",
+                cfg->sample_rate, cfg->frame_rate);
+  if (cfg->fast_phase != 0)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "fast_phase is not implemented");
+  if (cfg->inference == 0)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG,
+                "inference=0 (plain cumsum, training mode) is not implemented yet");
+  for (int fn : {cfg->additive_scale_fn, cfg->noise_scale_fn})
+    if (fn < 0 || fn > 2) return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "bad scale_fn %d", fn);
+  const int M = cfg->n_noise_bands;
+  if (M != 0 && (M < 3 || M > 1024))
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "n_noise_bands %d out of range", M);
+  if (M != 0 && cfg->noise_window_size > 0 && cfg->noise_window_size < 2 * (M - 1))
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG,
+                "noise_window_size %d < IR length %d (cropped IR) is not implemented",
+                cfg->noise_window_size, 2 * (M - 1));
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return fail(nullptr, B200DDSP_CUDA_ERROR, "cudaGetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess)
+    return fail(nullptr, B200DDSP_CUDA_ERROR, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG,
+                "device %d is sm_%d%d; this library carries sm_100a code only", dev, prop.major,
+                prop.minor);
+
+  b200ddsp_handle* h = new (std::nothrow) b200ddsp_handle();
+  if (!h) return fail(nullptr, B200DDSP_CUDA_ERROR, "out of host memory");
+  h->cfg = *cfg;
+  h->device = dev;
+  h->U = (int)((double)cfg->sample_rate / (double)cfg->frame_rate);   // inharm_synth.py:163-165
+  h->fast_div = verify_fast_division((float)cfg->sample_rate);
+
+  std::vector<float> win = hann_periodic(2 * h->U);
+  if (cudaMalloc(&h->d_window, win.size() * sizeof(float)) != cudaSuccess ||
+      cudaMemcpy(h->d_window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice) !=
+          cudaSuccess) {
+    fail(nullptr, B200DDSP_CUDA_ERROR, "window table: %s", cudaGetErrorString(cudaGetLastError()));
+    b200ddsp_destroy(h);
+    return B200DDSP_CUDA_ERROR;
+  }
+  if (M != 0) {
+    std::vector<float> cm = noise_ir_matrix_t(M);
+    if (cudaMalloc(&h->d_cmat_t, cm.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(h->d_cmat_t, cm.data(), cm.size() * sizeof(float), cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+      fail(nullptr, B200DDSP_CUDA_ERROR, "noise matrix: %s",
+           cudaGetErrorString(cudaGetLastError()));
+      b200ddsp_destroy(h);
+      return B200DDSP_CUDA_ERROR;
+    }
+  }
+  *out = h;
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
+  if (!h) return B200DDSP_OK;
+  if (h->d_window) cudaFree(h->d_window);
+  if (h->d_cmat_t) cudaFree(h->d_cmat_t);
+  delete h;
+  return B200DDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+
+static int fft_size_for(int N, int L) {
+  int n = 2;
+  while (n < N + L - 1) n <<= 1;   // ddsp.core.get_fft_size(power_of_2=True), frame = N
+  return n;
+}
+
+static int n_chunks_for(int N) { return (N + kAngularChunk - 1) / kAngularChunk; }
+
+// Voice groups: split the voices over gridDim.z until the grid fills the GPU.
+static int voice_groups_for(int P, int B, int n_chunks) {
+  int G = 1;
+  while (G < P && (long long)n_chunks * B * G < 4 * 148) G *= 2;
+  return G < P ? G : P;
+}
+
+struct WorkspaceLayout {
+  size_t amp, hd, shifts, f0, mags, offsets, partials, tw, buf_a, buf_b, total;
+  int G, n_chunks, nfft;
+};
+
+static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, int U, bool controls) {
+  WorkspaceLayout w{};
+  const size_t R = (size_t)P * B, N = (size_t)F * U;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
+  w.n_chunks = n_chunks_for((int)N);
+  w.G = voice_groups_for(P, B, w.n_chunks);
+  if (controls) {
+    w.amp = take(R * F * 4);
+    w.hd = take(R * F * H * 4);
+    w.shifts = take(R * F * H * 4);
+    w.f0 = take(R * F * S * 4);
+    w.mags = take(R * F * (size_t)M * 4);
+  }
+  w.offsets = take(R * S * w.n_chunks * H * 4);
+  w.partials = take((size_t)w.G * B * N * 4);
+  if (L > 0) {
+    w.nfft = fft_size_for((int)N, L);
+    w.tw = take((size_t)w.nfft * 8);
+    w.buf_a = take((size_t)B * w.nfft * 8);
+    w.buf_b = take((size_t)B * w.nfft * 8);
+  }
+  w.total = o;
+  return w;
+}
+
+extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H,
+                                           int S, int M, int L) {
+  if (!h || P < 1 || B < 1 || F < 1) return 0;
+  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 0 ? M : 0, L, h->U, true).total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// additive
+// ---------------------------------------------------------------------------------------------
+
+static int check_common(b200ddsp_handle* h, int B, int F) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (B < 1 || F < 1) return fail(h, B200DDSP_BAD_SHAPE, "B=%d F=%d must be positive", B, F);
+  if ((long long)F * h->U > (1 << 24))
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "N = F*U = %lld exceeds 2^24 samples (float32 sample index of the reference's "
+                "resize is no longer exact); split the timeline", (long long)F * h->U);
+  if (B > 65535) return fail(h, B200DDSP_BAD_SHAPE, "B=%d exceeds 65535", B);
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* amplitudes,
+                                          const float* harmonic_distribution,
+                                          const float* inharm_coef, const float* f0_hz,
+                                          float* amplitudes_out, float* harmonic_distribution_out,
+                                          float* harmonic_shifts_out, int rows, int F, int H, int S,
+                                          void* stream) {
+  if (int rc = check_common(h, rows, F)) return rc;
+  if (H < 1 || H > 32 * kMaxHarmonicsPerLane)
+    return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, %d]", H, 32 * kMaxHarmonicsPerLane);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
+  if (!amplitudes || !harmonic_distribution || !inharm_coef || !f0_hz || !amplitudes_out ||
+      !harmonic_distribution_out || !harmonic_shifts_out)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  AdditiveControlsPtrs p{};
+  p.amp_in[0] = amplitudes;
+  p.hd_in[0] = harmonic_distribution;
+  p.inharm_in[0] = inharm_coef;
+  p.f0_in[0] = f0_hz;
+  AdditiveControlsArgs a{};
+  a.amp_out = amplitudes_out;
+  a.hd_out = harmonic_distribution_out;
+  a.shifts_out = harmonic_shifts_out;
+  a.f0_out = nullptr;
+  a.n_frames_voice = rows * F;
+  a.H = H;
+  a.S = S;
+  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+  a.min_frequency = h->cfg.min_frequency;
+  a.scale_fn = h->cfg.additive_scale_fn;
+  a.normalize_after = h->cfg.normalize_after_nyquist_cut;
+  a.normalize_below = h->cfg.normalize_below_nyquist;
+  dim3 grid((a.n_frames_voice + 7) / 8, 1);
+  additive_controls_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, p);
+  CHECK_LAUNCH(h, "additive_controls_kernel");
+  return B200DDSP_OK;
+}
+
+template <int HP>
+static void launch_additive_hp(const AdditiveArgs& a, bool fast, bool ends_only, dim3 grid,
+                               int threads, size_t smem, cudaStream_t st) {
+  if (fast) {
+    if (ends_only) additive_kernel<HP, 8, true, true><<<grid, threads, 0, st>>>(a);
+    else additive_kernel<HP, 8, true, false><<<grid, threads, smem, st>>>(a);
+  } else {
+    if (ends_only) additive_kernel<HP, 1, false, true><<<grid, threads, 0, st>>>(a);
+    else additive_kernel<HP, 1, false, false><<<grid, threads, smem, st>>>(a);
+  }
+}
+
+static void launch_additive(const AdditiveArgs& a, int HP, bool fast, bool ends_only, dim3 grid,
+                            int threads, size_t smem, cudaStream_t st) {
+  switch (HP) {
+    case 1: launch_additive_hp<1>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 2: launch_additive_hp<2>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 3: launch_additive_hp<3>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 4: launch_additive_hp<4>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 5:
+    case 6: launch_additive_hp<6>(a, fast, ends_only, grid, threads, smem, st); break;
+    default: launch_additive_hp<8>(a, fast, ends_only, grid, threads, smem, st); break;
+  }
+}
+
+// The three launches of the additive synth over stacked controls (R = P*B rows).
+static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, const float* shifts,
+                        const float* f0, float* offsets, float* out, int P, int B, int F, int H,
+                        int S, int G, int accumulate, cudaStream_t st) {
+  const int U = h->U, N = F * U;
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
+  bool fast = h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && lerp_is_uniform(h, F, N, U);
+  if (!fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
+                F, N);
+  AdditiveArgs a{};
+  a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
+  a.offsets = offsets;
+  a.out = out;
+  a.window = h->d_window;
+  a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
+  a.chunk = kAngularChunk;
+  a.n_chunks = n_chunks_for(N);
+  a.voices_per_group = (P + G - 1) / G;
+  a.accumulate = (G == 1) ? accumulate : 0;
+  a.scale = (float)F / (float)N;
+  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+  a.sr = (float)h->cfg.sample_rate;
+  a.inv_sr = 1.0f / a.sr;
+  const int HP = (H + 31) / 32;
+  const int n_pairs = a.voices_per_group * S;
+  const int warps = n_pairs < kAddWarps ? n_pairs : kAddWarps;
+  const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
+  if (smem > 48 * 1024)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
+  if (a.n_chunks > 1) {
+    dim3 grid(a.n_chunks - 1, B, G);
+    launch_additive(a, HP, fast, true, grid, warps * 32, 0, st);
+    CHECK_LAUNCH(h, "additive_kernel<ends>");
+    const int n = P * B * S * H;
+    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(offsets, P * B * S, a.n_chunks, H);
+    CHECK_LAUNCH(h, "additive_offsets_kernel");
+  }
+  dim3 grid(a.n_chunks, B, G);
+  launch_additive(a, HP, fast, false, grid, warps * 32, smem, st);
+  CHECK_LAUNCH(h, "additive_kernel<synth>");
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitudes,
+                                        const float* harmonic_distribution,
+                                        const float* harmonic_shifts, const float* f0_hz, float* out,
+                                        int B, int F, int H, int S, int accumulate, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (int rc = check_common(h, B, F)) return rc;
+  if (!amplitudes || !harmonic_distribution || !harmonic_shifts || !f0_hz || !out)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  const int n_chunks = n_chunks_for(F * h->U);
+  const size_t need = (size_t)B * S * n_chunks * H * 4;
+  if (n_chunks > 1 && (!workspace || workspace_bytes < need))
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "additive_signal needs %zu workspace bytes, got %zu",
+                need, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  return run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
+                      (float*)workspace, out, 1, B, F, H, S, 1, accumulate, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// noise
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitudes,
+                                       float* magnitudes_out, size_t n, void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!magnitudes || !magnitudes_out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (n == 0) return B200DDSP_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  noise_controls_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      magnitudes, magnitudes_out, n, h->cfg.noise_initial_bias, h->cfg.noise_scale_fn);
+  CHECK_LAUNCH(h, "noise_controls_kernel");
+  return B200DDSP_OK;
+}
+
+static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const float* partials,
+                     int n_partials, float* out, int B, int F, int M, int accumulate,
+                     unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
+  const int U = h->U;
+  if (M != h->cfg.n_noise_bands || !h->d_cmat_t)
+    return fail(h, B200DDSP_BAD_SHAPE, "M=%d but the handle was created for n_noise_bands=%d", M,
+                h->cfg.n_noise_bands);
+  if (U % 8 != 0)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth needs U %% 8 == 0 (U=%d)", U);
+  NoiseArgs a{};
+  a.cmat_t = h->d_cmat_t;
+  a.partials = partials;
+  a.n_partials = n_partials;
+  a.out = out;
+  a.accumulate = accumulate;
+  a.P = P; a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
+  a.halo_before = (M + U - 1) / U;
+  a.halo_after = (U + M - 5) / U;
+  a.seed = seed;
+  a.stream_id = stream_id;
+  const NoiseSmemLayout L(M, U, a.halo_before, a.halo_after);
+  const size_t smem = (size_t)L.total_floats * sizeof(float);
+  if (smem > 227 * 1024)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
+  CUDA_TRY(h, cudaFuncSetAttribute(noise_fir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B);
+  noise_fir_kernel<0><<<grid, kNoiseThreads, smem, st>>>(a, vp);
+  CHECK_LAUNCH(h, "noise_fir_kernel");
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
+                                     uint64_t seed, uint64_t stream_id, float* out, int B, int F,
+                                     int M, int accumulate, void* stream) {
+  if (int rc = check_common(h, B, F)) return rc;
+  if (!magnitudes || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  NoiseVoicePtrs vp{};
+  vp.mags[0] = magnitudes;
+  vp.noise[0] = noise;
+  return run_noise(h, vp, 1, nullptr, 0, out, B, F, M, accumulate, seed, stream_id,
+                   (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverb
+// ---------------------------------------------------------------------------------------------
+
+template <class Loader, class Storer>
+static void launch_fft_pass(int R, const Loader& ld, const Storer& st, const float2* tw, int n, int Ns,
+                            int batches, cudaStream_t s) {
+  dim3 grid((n / R + kFftThreads - 1) / kFftThreads, batches);
+  switch (R) {
+    case 2: fft_pass_kernel<2><<<grid, kFftThreads, 0, s>>>(ld, st, tw, n, Ns); break;
+    case 4: fft_pass_kernel<4><<<grid, kFftThreads, 0, s>>>(ld, st, tw, n, Ns); break;
+    case 8: fft_pass_kernel<8><<<grid, kFftThreads, 0, s>>>(ld, st, tw, n, Ns); break;
+    default: fft_pass_kernel<16><<<grid, kFftThreads, 0, s>>>(ld, st, tw, n, Ns); break;
+  }
+}
+
+static std::vector<int> fft_radices(int n) {
+  int p = 0;
+  while ((1 << p) < n) ++p;
+  std::vector<int> r;
+  if (p % 4) r.push_back(1 << (p % 4));
+  for (int i = 0; i < p / 4; ++i) r.push_back(16);
+  return r;
+}
+
+static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
+                      int N, int L, float2* tw, float2* buf_a, float2* buf_b, cudaStream_t st) {
+  const int n = fft_size_for(N, L);
+  const std::vector<int> radices = fft_radices(n);
+  const int n_pass = (int)radices.size();
+  fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
+  CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  // forward: (audio, ir) -> Z
+  float2* src = nullptr;
+  float2* dst = buf_a;
+  int Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const StoreComplex sto{dst, n};
+    if (i == 0) {
+      launch_fft_pass(radices[i], LoadAudioIr{audio, ir, N, L}, sto, tw, n, Ns, B, st);
+    } else {
+      launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, B, st);
+    }
+    CHECK_LAUNCH(h, "fft_pass_kernel<forward>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == buf_a) ? buf_b : buf_a;
+  }
+  // spectrum product, two clips per inverse transform
+  const int pairs = (B + 1) / 2;
+  {
+    dim3 grid((n / 2 + 1 + 255) / 256, pairs);
+    reverb_spectrum_kernel<<<grid, 256, 0, st>>>(src, dst, n, B);
+    CHECK_LAUNCH(h, "reverb_spectrum_kernel");
+    src = dst;
+    dst = (dst == buf_a) ? buf_b : buf_a;
+  }
+  // inverse (as a forward transform of the conjugate), last pass writes the wet+dry signal
+  Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const LoadComplex ld{src, n};
+    if (i == n_pass - 1) {
+      const StoreWetPair sto{out, audio, N, B, 1.0f / (float)n, h->cfg.reverb_add_dry};
+      launch_fft_pass(radices[i], ld, sto, tw, n, Ns, pairs, st);
+    } else {
+      launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, tw, n, Ns, pairs, st);
+    }
+    CHECK_LAUNCH(h, "fft_pass_kernel<inverse>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == buf_a) ? buf_b : buf_a;
+  }
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
+                               int B, int N, int L, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (B < 1 || N < 1 || L < 1 || B > 65535)
+    return fail(h, B200DDSP_BAD_SHAPE, "B=%d N=%d L=%d must be positive", B, N, L);
+  if ((long long)N + L - 1 > (1ll << 28))
+    return fail(h, B200DDSP_BAD_SHAPE, "N + L - 1 = %lld exceeds 2^28", (long long)N + L - 1);
+  if (!audio || !ir || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (out == audio) return fail(h, B200DDSP_BAD_ARGUMENT, "out may not alias audio");
+  const int n = fft_size_for(N, L);
+  const size_t tw_b = align_up((size_t)n * 8), buf_b = align_up((size_t)B * n * 8);
+  const size_t need = tw_b + 2 * buf_b;
+  if (!workspace || workspace_bytes < need)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "reverb needs %zu workspace bytes, got %zu", need,
+                workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  char* w = (char*)workspace;
+  return run_reverb(h, audio, ir, out, B, N, L, (float2*)w, (float2*)(w + tw_b),
+                    (float2*)(w + tw_b + buf_b), (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the whole DAG
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
+                                           const float* reverb_ir, float* dry_out, float* wet_out,
+                                           int B, int F, int H, int S, int M, int L, uint64_t seed,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_common(h, B, F)) return rc;
+  if (!voices || P < 1 || P > B200DDSP_MAX_VOICES)
+    return fail(h, B200DDSP_BAD_SHAPE, "P=%d outside [1, %d]", P, B200DDSP_MAX_VOICES);
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
+  if (!dry_out) return fail(h, B200DDSP_BAD_ARGUMENT, "dry_out is null");
+  if (reverb_ir && (!wet_out || L < 1))
+    return fail(h, B200DDSP_BAD_ARGUMENT, "reverb_ir given but wet_out is null or L < 1");
+  if (reverb_ir && wet_out == dry_out)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out may not alias dry_out");
+  const int U = h->U, N = F * U;
+  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir ? L : 0, U, true);
+  if (!workspace || workspace_bytes < w.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_polyphonic needs %zu workspace bytes, got %zu",
+                w.total, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  char* base = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* amp = (float*)(base + w.amp);
+  float* hd = (float*)(base + w.hd);
+  float* shifts = (float*)(base + w.shifts);
+  float* f0 = (float*)(base + w.f0);
+  float* mags = (float*)(base + w.mags);
+
+  // get_controls of every voice (additive: stacked [P*B, F, .]; noise: scale_fn(m + bias))
+  AdditiveControlsPtrs cp{};
+  NoiseVoicePtrs vp{};
+  for (int v = 0; v < P; ++v) {
+    const b200ddsp_voice& vc = voices[v];
+    if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
+      return fail(h, B200DDSP_BAD_ARGUMENT, "voice %d has a null control tensor", v);
+    cp.amp_in[v] = vc.amplitudes;
+    cp.hd_in[v] = vc.harmonic_distribution;
+    cp.inharm_in[v] = vc.inharm_coef;
+    cp.f0_in[v] = vc.f0_hz;
+    vp.mags[v] = mags + (size_t)v * B * F * M;
+    vp.noise[v] = vc.noise;
+  }
+  {
+    AdditiveControlsArgs a{};
+    a.amp_out = amp; a.hd_out = hd; a.shifts_out = shifts; a.f0_out = f0;
+    a.n_frames_voice = B * F;
+    a.H = H; a.S = S;
+    a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+    a.min_frequency = h->cfg.min_frequency;
+    a.scale_fn = h->cfg.additive_scale_fn;
+    a.normalize_after = h->cfg.normalize_after_nyquist_cut;
+    a.normalize_below = h->cfg.normalize_below_nyquist;
+    dim3 grid((a.n_frames_voice + 7) / 8, P);
+    additive_controls_kernel<<<grid, 256, 0, st>>>(a, cp);
+    CHECK_LAUNCH(h, "additive_controls_kernel");
+  }
+  for (int v = 0; v < P; ++v) {
+    // contiguous stacked parents ([P,B,F,M], sub_modules.py:589-596) collapse into one launch
+    int run = 1;
+    while (v + run < P && voices[v + run].magnitudes == voices[v].magnitudes + (size_t)run * B * F * M)
+      ++run;
+    if (int rc = b200ddsp_noise_controls(h, voices[v].magnitudes, mags + (size_t)v * B * F * M,
+                                         (size_t)run * B * F * M, stream))
+      return rc;
+    v += run - 1;
+  }
+  // additive oscillator bank -> G partial sums
+  if (int rc = run_additive(h, amp, hd, shifts, f0, (float*)(base + w.offsets),
+                            (float*)(base + w.partials), P, B, F, H, S, w.G, 0, st))
+    return rc;
+  // noise of every voice + mix -> dry  (outputs['add']['signal'])
+  if (int rc = run_noise(h, vp, P, (const float*)(base + w.partials), w.G, dry_out, B, F, M, 0, seed,
+                         0, st))
+    return rc;
+  // reverb -> wet
+  if (reverb_ir)
+    return run_reverb(h, dry_out, reverb_ir, wet_out, B, N, L, (float2*)(base + w.tw),
+                      (float2*)(base + w.buf_a), (float2*)(base + w.buf_b), st);
+  return B200DDSP_OK;
+}

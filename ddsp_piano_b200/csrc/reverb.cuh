@@ -1,0 +1,218 @@
+// Convolution reverb: ddsp.effects.Reverb.get_signal as configured by the reference
+// (configs/dafx22.gin:99-100,111): ir[:, 0] = 0, wet = fft_convolve(audio, ir, 'same',
+// delay_compensation=0) -- ONE block of size n = 2^ceil(log2(N + L - 1)) -- out = wet (+ audio).
+//
+// Both operands are real, so one complex transform carries both: z = audio + i*ir,
+//   X[k] = (Z[k] + conj Z[n-k]) / 2,   H[k] = (Z[k] - conj Z[n-k]) / 2i,   Y = X * H,
+// and because the wet signals are real, two clips share one inverse transform:
+//   FFT(conj Ya + i conj Yb) = n * (ya + i yb).
+// The transform is a Stockham autosort FFT: radix-16 passes (plus one radix-2/4/8 pass when
+// log2 n is not a multiple of 4) between two ping-pong buffers that stay resident in the
+// 126 MB L2 (2 MB per clip at n = 2^18).  Twiddles come from a table exp(-2 pi i q / n)
+// evaluated in double precision, so the float32 error is the butterflies' only.
+#pragma once
+#include "common.cuh"
+
+namespace b200ddsp {
+
+constexpr int kFftThreads = 256;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(__fmaf_rn(a.x, b.x, -a.y * b.y), __fmaf_rn(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }
+
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+  const float2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2);
+  const float2 t2 = cadd(v1, v3), t3 = mul_neg_i(csub(v1, v3));
+  v0 = cadd(t0, t2);
+  v1 = cadd(t1, t3);
+  v2 = csub(t0, t2);
+  v3 = csub(t1, t3);
+}
+
+// exp(-2 pi i m / 16), m = 0..15 (only m = b*c with b, c < 4 is used)
+__device__ __forceinline__ float2 w16(int m) {
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+  switch (m & 15) {
+    case 0: return make_float2(1.f, 0.f);
+    case 1: return make_float2(c1, -s1);
+    case 2: return make_float2(h, -h);
+    case 3: return make_float2(s1, -c1);
+    case 4: return make_float2(0.f, -1.f);
+    case 5: return make_float2(-s1, -c1);
+    case 6: return make_float2(-h, -h);
+    case 7: return make_float2(-c1, -s1);
+    case 8: return make_float2(-1.f, 0.f);
+    case 9: return make_float2(-c1, s1);
+    case 10: return make_float2(-h, h);
+    case 11: return make_float2(-s1, c1);
+    case 12: return make_float2(0.f, 1.f);
+    case 13: return make_float2(s1, c1);
+    case 14: return make_float2(h, h);
+    default: return make_float2(c1, s1);
+  }
+}
+
+// In-register forward DFT of R points, natural order in and out.
+template <int R>
+__device__ __forceinline__ void dft(float2 (&v)[R]);
+
+template <>
+__device__ __forceinline__ void dft<2>(float2 (&v)[2]) { dft2(v[0], v[1]); }
+
+template <>
+__device__ __forceinline__ void dft<4>(float2 (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+
+template <>
+__device__ __forceinline__ void dft<8>(float2 (&v)[8]) {
+  // r = 2a + b, q = c + 4d: DFT4 over a, twiddle W8^(bc), DFT2 over b
+  dft4(v[0], v[2], v[4], v[6]);   // b = 0: T0[c] in v[2c]
+  dft4(v[1], v[3], v[5], v[7]);   // b = 1: T1[c] in v[2c+1]
+#pragma unroll
+  for (int c = 1; c < 4; ++c) v[2 * c + 1] = cmul(v[2 * c + 1], w16(2 * c));
+  float2 o[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float2 a = v[2 * c], b = v[2 * c + 1];
+    dft2(a, b);
+    o[c] = a;
+    o[c + 4] = b;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = o[i];
+}
+
+template <>
+__device__ __forceinline__ void dft<16>(float2 (&v)[16]) {
+  // r = 4a + b, q = c + 4d: DFT4 over a, twiddle W16^(bc), DFT4 over b
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);   // T_b[c] in v[4c+b]
+#pragma unroll
+  for (int b = 1; b < 4; ++b)
+#pragma unroll
+    for (int c = 1; c < 4; ++c) v[4 * c + b] = cmul(v[4 * c + b], w16(b * c));
+  float2 o[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float2 t0 = v[4 * c], t1 = v[4 * c + 1], t2 = v[4 * c + 2], t3 = v[4 * c + 3];
+    dft4(t0, t1, t2, t3);
+    o[c] = t0;
+    o[c + 4] = t1;
+    o[c + 8] = t2;
+    o[c + 12] = t3;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+
+// ---- loaders / storers ---------------------------------------------------------------------
+struct LoadComplex {
+  const float2* src; int n;
+  __device__ __forceinline__ float2 operator()(int batch, int i) const {
+    return src[(size_t)batch * n + i];
+  }
+};
+struct StoreComplex {
+  float2* dst; int n;
+  __device__ __forceinline__ void operator()(int batch, int i, float2 v) const {
+    dst[(size_t)batch * n + i] = v;
+  }
+};
+// z = audio + i * ir with ir[0] masked (Reverb._mask_dry_ir), zero padded to n
+struct LoadAudioIr {
+  const float* audio; const float* ir; int N, L;
+  __device__ __forceinline__ float2 operator()(int batch, int i) const {
+    const float re = (i < N) ? __ldg(audio + (size_t)batch * N + i) : 0.f;
+    const float im = (i > 0 && i < L) ? __ldg(ir + (size_t)batch * L + i) : 0.f;
+    return make_float2(re, im);
+  }
+};
+// real part -> clip 2*batch, imaginary part -> clip 2*batch+1; crop to N ('same',
+// delay_compensation = 0), scale by 1/n, add the dry signal
+struct StoreWetPair {
+  float* out; const float* audio; int N, B; float inv_n; int add_dry;
+  __device__ __forceinline__ void operator()(int batch, int i, float2 v) const {
+    if (i >= N) return;
+    const int b0 = 2 * batch, b1 = b0 + 1;
+    const size_t o0 = (size_t)b0 * N + i;
+    float y0 = v.x * inv_n;
+    if (add_dry) y0 = __fadd_rn(y0, __ldg(audio + o0));
+    out[o0] = y0;
+    if (b1 < B) {
+      const size_t o1 = (size_t)b1 * N + i;
+      float y1 = v.y * inv_n;
+      if (add_dry) y1 = __fadd_rn(y1, __ldg(audio + o1));
+      out[o1] = y1;
+    }
+  }
+};
+
+// One Stockham pass of radix R: sub-transforms of length Ns -> Ns*R.
+template <int R, class Loader, class Storer>
+__global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const Loader ld, const Storer st,
+                                                              const float2* __restrict__ tw,
+                                                              int n, int Ns) {
+  const int j = blockIdx.x * kFftThreads + threadIdx.x;
+  const int batch = blockIdx.y;
+  const int stride = n / R;
+  if (j >= stride) return;
+  float2 v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = ld(batch, j + r * stride);
+  const int k = j & (Ns - 1);
+  if (Ns > 1) {
+    const int step = k * (stride / Ns);    // k * n / (Ns * R)
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(tw + r * step));
+  }
+  dft<R>(v);
+  const int base = (j - k) * R + k;
+#pragma unroll
+  for (int r = 0; r < R; ++r) st(batch, base + r * Ns, v[r]);
+}
+
+// tw[q] = exp(-2 pi i q / n)
+__global__ void __launch_bounds__(256) fft_twiddle_kernel(float2* tw, int n) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  double s, c;
+  sincospi(-2.0 * (double)q / (double)n, &s, &c);
+  tw[q] = make_float2((float)c, (float)s);
+}
+
+// Z (B clips) -> V (ceil(B/2) pairs): V[k] = conj Ya[k] + i conj Yb[k], Y = X * H.
+__global__ void __launch_bounds__(256) reverb_spectrum_kernel(const float2* __restrict__ Z,
+                                                               float2* __restrict__ V, int n,
+                                                               int B) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. n/2
+  const int pair = blockIdx.y;
+  if (k > n / 2) return;
+  const int kn = (n - k) & (n - 1);
+  float2 y[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int b = 2 * pair + e;
+    y[e] = make_float2(0.f, 0.f);
+    if (b < B) {
+      const float2 z = Z[(size_t)b * n + k], w = Z[(size_t)b * n + kn];
+      const float2 X = make_float2(0.5f * (z.x + w.x), 0.5f * (z.y - w.y));
+      const float2 H = make_float2(0.5f * (z.y + w.y), -0.5f * (z.x - w.x));
+      y[e] = cmul(X, H);
+    }
+  }
+  // V[k]   = conj(Ya) + i conj(Yb) = (ya.x + yb.y) + i (yb.x - ya.y)
+  // V[n-k] = Ya + i Yb             = (ya.x - yb.y) + i (ya.y + yb.x)      (Y is Hermitian)
+  V[(size_t)pair * n + k] = make_float2(y[0].x + y[1].y, y[1].x - y[0].y);
+  if (kn != k) V[(size_t)pair * n + kn] = make_float2(y[0].x - y[1].y, y[0].y + y[1].x);
+}
+
+}  // namespace b200ddsp

@@ -1,0 +1,168 @@
+/*
+ * b200ddsp.h -- C ABI of libb200ddsp.so: the DDSP-Piano per-sample synthesis hot path
+ * (inharmonic additive oscillator bank, filtered-noise synth, convolution reverb) as
+ * hand-written CUDA kernels for sm_100a (NVIDIA B200).
+ *
+ * The reference (lrenault/ddsp-piano) is pure Python/TensorFlow and has no FFI for this
+ * path; the "binding" it would use is a Python processor class whose get_controls /
+ * get_signal forward to these entry points through ctypes.  Each
+ * entry point cites the reference interface it replaces (paths under
+ * /root/reference/ddsp_piano/).
+ *
+ * Conventions
+ *   - plain C types only; every tensor is a DEVICE pointer to contiguous row-major
+ *     float32, 16-byte aligned, owned by the caller (allocated e.g. by torch);
+ *   - B batch (clips), F control frames (250 Hz), U = sample_rate / frame_rate,
+ *     N = F*U samples, H partials, S substrings per voice, M noise bands, L reverb taps,
+ *     P voices;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns; nothing allocates device memory after b200ddsp_create(), so calls are
+ *     CUDA-graph capturable; scratch comes from the caller's `workspace`;
+ *   - return value 0 = OK, negative = b200ddsp_status; text via b200ddsp_last_error();
+ *   - a handle may be used by one host thread at a time; handles are independent; one
+ *     handle per device (multi-GPU = one process and one handle per GPU).
+ */
+#ifndef B200DDSP_H_
+#define B200DDSP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DDSP_VERSION 100 /* 0.1.0 */
+#define B200DDSP_MAX_VOICES 64
+
+typedef enum {
+  B200DDSP_OK = 0,
+  B200DDSP_BAD_SHAPE = -1,
+  B200DDSP_BAD_ALIGN = -2,
+  B200DDSP_UNSUPPORTED_CONFIG = -3,
+  B200DDSP_CUDA_ERROR = -4,
+  B200DDSP_WORKSPACE_TOO_SMALL = -5,
+  B200DDSP_BAD_ARGUMENT = -6
+} b200ddsp_status;
+
+/* scale_fn ids: ddsp.core.exp_sigmoid (default, modules/inharm_synth.py:149),
+ * exp_tanh (modules/inharm_synth.py:13-17), or scale_fn=None. */
+typedef enum {
+  B200DDSP_SCALE_EXP_SIGMOID = 0,
+  B200DDSP_SCALE_EXP_TANH = 1,
+  B200DDSP_SCALE_NONE = 2
+} b200ddsp_scale_fn;
+
+/* Mirrors the constructor arguments of the three processors of configs/dafx22.gin:91-111:
+ * MultiInharmonic (modules/inharm_synth.py:145-153,251-252), DynamicSizeFilteredNoise
+ * (modules/filtered_noise_synth.py:18-21 + ddsp.synths.FilteredNoise) and
+ * ddsp.effects.Reverb. */
+typedef struct {
+  int sample_rate;                 /* Hz; U = sample_rate / frame_rate (inharm_synth.py:163-165) */
+  int frame_rate;                  /* Hz, 250 */
+  float min_frequency;             /* 20: voices with f0 <= this are muted (inharm_synth.py:207-208) */
+  int additive_scale_fn;           /* b200ddsp_scale_fn */
+  int normalize_after_nyquist_cut; /* inharm_synth.py:210-214 (default 1) */
+  int normalize_below_nyquist;     /* inharm_synth.py:200-208 (default 1) */
+  int inference;                   /* 1: ddsp angular_cumsum (chunks of 1000); 0: plain cumsum
+                                      (inharm_synth.py:73-77) */
+  int noise_scale_fn;              /* b200ddsp_scale_fn (FilteredNoise.scale_fn) */
+  float noise_initial_bias;        /* -5.0 */
+  int noise_window_size;           /* 257 */
+  int reverb_add_dry;              /* effects.Reverb add_dry (default 1) */
+  int n_noise_bands;               /* M: the FIR window / cosine tables are built for this M */
+  int fast_phase;                  /* 0 (default): bit-faithful float32 phase accumulation in the
+                                      reference's summation order.  1: closed-form fixed-point
+                                      phase (more accurate than the reference, but differs from it
+                                      by up to ~1e-3 rad in high partials).  Not yet implemented:
+                                      must be 0. */
+} b200ddsp_config;
+
+typedef struct b200ddsp_handle b200ddsp_handle;
+
+/* Device pointers of one voice's RAW (pre-get_controls) control tensors, i.e. the
+ * features `amplitudes_i, harmonic_distribution_i, inharm_coef_i, f0_hz_i, magnitudes_i`
+ * that Parallelizer.unparallelize produces (modules/sub_modules.py:589-596). */
+typedef struct {
+  const float* amplitudes;            /* [B, F, 1] */
+  const float* harmonic_distribution; /* [B, F, H] */
+  const float* inharm_coef;           /* [B, F, 1] */
+  const float* f0_hz;                 /* [B, F, S] */
+  const float* magnitudes;            /* [B, F, M] */
+  const float* noise;                 /* [B, N] uniform [-1,1) samples to filter, or NULL to draw
+                                         them in-kernel with Philox (filtered_noise_synth.py:39-40
+                                         draws them unseeded) */
+} b200ddsp_voice;
+
+int b200ddsp_version(void);
+
+/* Message for the last failure on this handle (or of b200ddsp_create when h == NULL). */
+const char* b200ddsp_last_error(const b200ddsp_handle* h);
+
+/* Builds the per-configuration tables (Hann tables, noise-FIR cosine table, FFT twiddles)
+ * on the current CUDA device.  The only place that allocates device memory. */
+int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out);
+int b200ddsp_destroy(b200ddsp_handle* h);
+
+/* Scratch bytes needed by the calls below for these shapes (take the max over the calls
+ * you make).  P = voices per b200ddsp_forward_polyphonic call (1 for per-voice calls). */
+size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H, int S,
+                                int M, int L);
+
+/* MultiInharmonic.get_controls -- modules/inharm_synth.py:254-270 over :167-219.
+ * rows = B (or P*B for a stacked [P,B,...] tensor).  f0_hz is passed through unchanged by
+ * the reference, so it has no output.  Outputs: amplitudes [rows,F,1],
+ * harmonic_distribution [rows,F,H], harmonic_shifts [rows,F,H]. */
+int b200ddsp_additive_controls(b200ddsp_handle* h, const float* amplitudes,
+                               const float* harmonic_distribution, const float* inharm_coef,
+                               const float* f0_hz, float* amplitudes_out,
+                               float* harmonic_distribution_out, float* harmonic_shifts_out,
+                               int rows, int F, int H, int S, void* stream);
+
+/* MultiInharmonic.get_signal -- modules/inharm_synth.py:272-293 (harmonic_synthesis :87-127,
+ * cos_oscillator_bank :49-84).  Inputs are get_controls outputs.  out [B, N]; if
+ * accumulate != 0 the result is added to `out` (the MultiAdd node, inharm_synth.py:296-309). */
+int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitudes,
+                             const float* harmonic_distribution, const float* harmonic_shifts,
+                             const float* f0_hz, float* out, int B, int F, int H, int S,
+                             int accumulate, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ddsp.synths.FilteredNoise.get_controls (base class of
+ * modules/filtered_noise_synth.py:13): scale_fn(magnitudes + initial_bias). n = element count. */
+int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitudes, float* magnitudes_out,
+                            size_t n, void* stream);
+
+/* DynamicSizeFilteredNoise.get_signal -- modules/filtered_noise_synth.py:27-42:
+ * time-varying linear-phase FIR (ddsp.core.frequency_filter) over uniform noise.
+ * magnitudes [B,F,M] are get_controls outputs.  noise [B,N] or NULL (then Philox4x32-10
+ * keyed by (seed, stream_id)).  out [B,N], added to when accumulate != 0. */
+int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
+                          uint64_t seed, uint64_t stream_id, float* out, int B, int F, int M,
+                          int accumulate, void* stream);
+
+/* ddsp.effects.Reverb.get_signal (configs/dafx22.gin:99-100,111; ir producer
+ * modules/sub_modules.py:351-365): out = conv(audio, ir with ir[:,0]=0)[:, :N] (+ audio if
+ * add_dry).  audio [B,N], ir [B,L], out [B,N]; out may not alias audio. */
+int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
+                    int N, int L, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole DAG of modules/polyphonic_dag.py:21-42 as wired by configs/dafx22.gin:91-100,
+ * entered at modules/piano_model.py:160: for every voice get_controls + get_signal of the
+ * additive and noise processors, the running MultiAdd sum, then the reverb.
+ * voices: HOST array of P structs of device pointers.  reverb_ir [B,L] or NULL (no reverb
+ * node).  dry_out [B,N] = outputs['add']['signal']; wet_out [B,N] = outputs['reverb']['signal']
+ * (ignored when reverb_ir is NULL). */
+int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
+                                const float* reverb_ir, float* dry_out, float* wet_out, int B,
+                                int F, int H, int S, int M, int L, uint64_t seed,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches enqueued by this handle since creation (bench.py's
+ * gpu_launches claim is read from here). */
+uint64_t b200ddsp_launch_count(const b200ddsp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DDSP_H_ */
