@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the DDSP-Piano synthesis hot path (BASELINE.json metric: real-time factor,
+audio seconds per wall second, 24 kHz, batch 16, poly 16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload full|dry|stress]
+    python bench.py --impl reference ...        # the CPU oracle on the host cores
+
+A step = one forward of the whole polyphonic ProcessorGroup (16 voices x (additive + noise),
+running sum, reverb) over one batch of synthetic control tensors.  `value` is timed on the
+device with inputs resident in HBM; `e2e` goes through the reference-facing ProcessorGroup
+call with pinned HOST inputs (H2D of every control tensor and D2H of the audio inside the
+timed region).  Multi-GPU: the batch of clips is sharded, one process per GPU, no collective
+on the data path -> weak scaling, value = all clips / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: batch 16 x 3 s, poly 16, 96 partials, 64 noise bands, full chain
+    # including the 3 s convolution reverb, 24 kHz
+    'full': dict(name='configs[2]: batch16 x 3s, poly16, H96, M64, additive+noise+3s reverb, 24kHz',
+                 sr=24000, B=16, P=16, S=2, H=96, M=64, F=750, L=72000),
+    # configs[1]: same without the reverb
+    'dry': dict(name='configs[1]: batch16 x 3s, poly16, H96, M64, additive+noise (no reverb), 24kHz',
+                sr=24000, B=16, P=16, S=2, H=96, M=64, F=750, L=0),
+    # configs[4]: 48 kHz / poly 32 / 128 partials stress
+    'stress': dict(name='configs[4]: batch16 x 3s, poly32, H128, M96, full chain, 48kHz',
+                   sr=48000, B=16, P=32, S=2, H=128, M=96, F=750, L=144000),
+}
+METRIC = 'real-time factor (audio-sec/wall-sec) @24kHz batch16 poly16'
+UNIT = 'x real time'
+
+
+def synthetic_inputs(w, seed, B=None):
+    """SURVEY.md 8d config 2/3 distributions, pre-get_controls, stacked [P, B, F, C] float32."""
+    B = w['B'] if B is None else B
+    P, F, H, S, M, L = w['P'], w['F'], w['H'], w['S'], w['M'], w['L']
+    rng = np.random.default_rng(seed)
+    midi = rng.integers(21, 109, size=[P, B, 1, 1])
+    f0 = 440.0 * 2.0 ** ((midi - 69) / 12.0) * (1.0 + 1e-3 * np.arange(S))[None, None, None, :]
+    x = {
+        'f0_hz': np.broadcast_to(f0, [P, B, F, S]).astype(np.float32).copy(),
+        'inharm_coef': rng.uniform(1e-4, 1e-3, [P, B, F, 1]).astype(np.float32),
+        'amplitudes': rng.standard_normal([P, B, F, 1], dtype=np.float32),
+        'harmonic_distribution': rng.standard_normal([P, B, F, H], dtype=np.float32),
+        'magnitudes': rng.standard_normal([P, B, F, M], dtype=np.float32),
+    }
+    if L:
+        t = np.arange(L) / L
+        x['reverb_ir'] = (rng.standard_normal([B, L]) * np.exp(-6 * t) * 1e-2).astype(np.float32)
+    return x
+
+
+def algorithmic_bytes(w, B, G):
+    """Bytes each stage must move once (DESIGN.md 'Algorithmic bytes')."""
+    P, F, H, S, M, L = w['P'], w['F'], w['H'], w['S'], w['M'], w['L']
+    U = w['sr'] // 250
+    N = F * U
+    n_chunks = -(-N // 1000)
+    R = P * B
+    return {
+        'forward': R * F * (1 + H + 1 + S + M) * 4 + B * L * 4 + B * N * 4 * (2 if L else 1),
+        'oscillators': R * F * (1 + 2 * H + S) * 4 + R * S * n_chunks * H * 4 + G * B * N * 4,
+        'n_samples': B * N,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the oracle as the reported baseline / reference arm
+# ------------------------------------------------------------------------------------------
+
+def _oracle_voice_clip(args):
+    """One (voice, clip) of the workload through the numpy oracle: get_controls + get_signal of
+    the additive and noise processors.  Returns seconds."""
+    (sr, F, H, S, M, seed) = args
+    from oracle import ddsp_piano_np as ref
+    rng = np.random.default_rng(seed)
+    hz = 440.0 * 2.0 ** ((int(rng.integers(21, 109)) - 69) / 12.0)
+    f0 = np.broadcast_to((hz * (1.0 + 1e-3 * np.arange(S)))[None, None, :], [1, F, S]).astype(np.float32)
+    amp = rng.standard_normal([1, F, 1], dtype=np.float32)
+    hd = rng.standard_normal([1, F, H], dtype=np.float32)
+    inh = rng.uniform(1e-4, 1e-3, [1, F, 1]).astype(np.float32)
+    mags = rng.standard_normal([1, F, M], dtype=np.float32)
+    noise = rng.uniform(-1, 1, [1, F * (sr // 250)]).astype(np.float32)
+    t0 = time.perf_counter()
+    c = ref.additive_controls(amp, hd, inh, f0, sample_rate=sr)
+    a = ref.additive_signal(**c, sample_rate=sr, inference=True)
+    n = ref.noise_signal(ref.noise_controls(mags)['magnitudes'], noise)
+    _ = a + n
+    return time.perf_counter() - t0
+
+
+def _oracle_reverb(sr, F, L, seed):
+    from oracle import ddsp_piano_np as ref
+    rng = np.random.default_rng(seed)
+    N = F * (sr // 250)
+    audio = rng.standard_normal([1, N], dtype=np.float32)
+    ir = rng.standard_normal([1, L], dtype=np.float32)
+    t0 = time.perf_counter()
+    ref.reverb_signal(audio, ir)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(w, n_voice_clips, cores, pool=None):
+    """Time `n_voice_clips` (voice, clip) units of the workload through the oracle on `cores`
+    worker processes and scale to the whole batch.  Returns (rtf, seconds, description)."""
+    sr, F, H, S, M, L, B, P = (w[k] for k in ('sr', 'F', 'H', 'S', 'M', 'L', 'B', 'P'))
+    jobs = [(sr, F, H, S, M, 1000 + i) for i in range(n_voice_clips)]
+    t0 = time.perf_counter()
+    if pool is not None:
+        pool.map(_oracle_voice_clip, jobs, chunksize=1)
+    else:
+        for j in jobs:
+            _oracle_voice_clip(j)
+    t_voices = time.perf_counter() - t0
+    t_rev = _oracle_reverb(sr, F, L, 5) if L else 0.0
+    # whole batch = P*B voice-clips (embarrassingly parallel over `cores`) + B reverbs
+    t_full = t_voices * (P * B) / n_voice_clips + t_rev * B / max(cores, 1)
+    audio_sec = B * F / 250.0
+    desc = (f'{n_voice_clips} of {P * B} (voice, clip) units (get_controls+get_signal, additive+'
+            f'noise) on {cores} worker process(es) in {t_voices:.2f}s'
+            + (f' + 1 of {B} reverbs in {t_rev:.3f}s' if L else '') + ', scaled to the whole batch')
+    return audio_sec / t_full, t_voices + t_rev, desc
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's TF2 CPU path is not installable here (tensorflow/ddsp
+    absent, no network); its CPU restatement (oracle/, numpy) is timed instead, one worker
+    process per host core, on a bounded sample of the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = 2 * cores            # two (voice, clip) units per core per step: ~1.5 s of wall
+    vals, secs, desc = [], [], ''
+    with mp.get_context('spawn').Pool(cores) as pool:
+        pool.map(_oracle_voice_clip, [(w['sr'], 25, w['H'], w['S'], w['M'], i)
+                                      for i in range(cores)])      # import numpy in the workers
+        for _ in range(min(args.warmup, 2)):
+            cpu_sample(w, cores, cores, pool)
+        for _ in range(args.steps):
+            rtf, s, desc = cpu_sample(w, per_step, cores, pool)
+            vals.append(rtf)
+            secs.append(s)
+    value = float(np.mean(vals))
+    audio_sec = w['B'] * w['F'] / 250.0
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * audio_sec / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': w['name']},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': desc},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+
+def run_gpu(args, w):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        dist.barrier()
+    import ddsp_piano_b200 as dp
+    from ddsp_piano_b200.processors import _DEFAULT_CFG
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    sr, B, P, S, H, M, F, L = (w[k] for k in ('sr', 'B', 'P', 'S', 'H', 'M', 'F', 'L'))
+    U = sr // 250
+    N = F * U
+
+    # weak scaling: every rank synthesises its own batch of B clips (independent MIDI segments)
+    x_np = synthetic_inputs(w, seed=rank)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in x_np.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    additive = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='additive')
+    noise = dp.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, name='noise', seed=1234)
+    reverb = dp.Reverb(trainable=False) if L else None
+    group = dp.ProcessorGroup(dag=dp.polyphonic_dag(
+        additive=additive, noise=noise, reverb=reverb,
+        additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+        noise_controls=['magnitudes'], reverb_controls=['reverb_ir'] if L else [], n_synths=P))
+
+    def features(parents):
+        f = {f'{k}_{v}': parents[k][v] for k in ('amplitudes', 'harmonic_distribution',
+                                                 'inharm_coef', 'f0_hz', 'magnitudes')
+             for v in range(P)}
+        if L:
+            f['reverb_ir'] = parents['reverb_ir']
+        return f
+
+    cfg = {**_DEFAULT_CFG, **additive.engine_config(), **noise.engine_config(M)}
+    if reverb is not None:
+        cfg.update(reverb.engine_config())
+    eng = dp.get_engine(dev, **cfg)
+    eng.set_profiling(True)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        return group(features(resident), return_outputs_dict=False)
+
+    h2d = sum(v.numel() * 4 for v in host.values())
+    out_host = torch.empty([B, N], dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        on_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        y = group(features(on_dev), return_outputs_dict=False)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, stages=None):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
+        steps (outside the brackets).  Returns total ms."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.zero_()
+            evs[i][0].record()
+            fn()
+            evs[i][1].record()
+            if stages is not None:
+                s = eng.last_stage_ms()
+                for k, v in s.items():
+                    stages[k] = stages.get(k, 0.0) + v
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = dp.total_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    stages = {}
+    total_ms = timed(step_resident, args.steps, stages)
+    clocks = sampler.stop()
+    launches = dp.total_launches() - launches0
+
+    for _ in range(3):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = reduce_max(total_ms)
+    e2e_ms = reduce_max(e2e_ms)
+    audio_sec = world * B * F / 250.0
+    ms_per_step = total_ms / args.steps
+    value = audio_sec / (ms_per_step * 1e-3)
+    e2e_value = audio_sec / (e2e_ms / args.steps * 1e-3)
+
+    if rank == 0:
+        peaks, peaks_src = {}, 'fallback'
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peaks, peaks_src = json.load(f), 'measured'
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        G = 1
+        while G < P and (-(-N // 1000)) * B * G < 4 * 148:
+            G *= 2
+        ab = algorithmic_bytes(w, B, min(G, P))
+        osc_ms = stages.get('oscillators', 0.0) / args.steps
+        achieved = ab['oscillators'] / (osc_ms * 1e-3) / 1e9 if osc_ms > 0 else None
+        # issue-slot view of the same kernel: counted FP32 instructions per oscillator-sample
+        osc_samples = B * P * S * H * N
+        roofline = {
+            'bound': 'hbm', 'kernel': 'additive_kernel<synth> (oscillator bank)',
+            'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': (achieved / hbm_peak) if achieved else None, 'traffic': None,
+            'peak_source': f'{peaks_src} (MEASURED_PEAKS.json hbm_gbs)' if peaks_src == 'measured'
+            else 'fallback 6650 GB/s (B200_PROFILING.md)',
+            'algorithmic_bytes_per_launch': ab['oscillators'], 'kernel_ms': osc_ms,
+            'kernel_share_of_step': osc_ms / ms_per_step if ms_per_step else None,
+            'note': 'the oscillator bank is FP32-issue bound, not HBM bound (SURVEY.md fact 5): '
+                    'see oscillator_samples_per_s and DESIGN.md',
+            'oscillator_samples_per_s': osc_samples / (osc_ms * 1e-3) if osc_ms > 0 else None,
+            'whole_step_GBps': ab['forward'] / (ms_per_step * 1e-3) / 1e9,
+            'stage_ms': {k: v / args.steps for k, v in stages.items()},
+        }
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rtf, secs, desc = cpu_sample(w, 16, 1)
+            cpu = {'value': rtf, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': desc,
+                   'host_cores_available': cores}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'clips_per_gpu': B, 'voices': P, 'substrings': S,
+                       'partials': H, 'noise_bands': M, 'frames': F, 'samples_per_clip': N,
+                       'reverb_taps': L, 'sample_rate': sr, 'noise': 'in-kernel Philox',
+                       'phase': 'bit-faithful float32 angular_cumsum',
+                       'l2': 'flushed (256 MB write) between timed steps',
+                       'sharding': 'clips over ranks, no collective'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': B * N * 4, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='full', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, w)
+    else:
+        run_gpu(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,12 @@
+"""b200-ddsp-piano: the DDSP-Piano per-sample synthesis hot path (inharmonic additive
+oscillator bank, filtered noise, convolution reverb) as hand-written sm_100a CUDA behind
+the reference's Processor / ProcessorGroup operator API.  See DESIGN.md."""
+from . import _lib
+from .engine import Engine, get_engine, total_launches
+from .processors import (DynamicSizeFilteredNoise, InHarmonic, MultiAdd, MultiInharmonic,
+                         Processor, ProcessorGroup, Reverb, exp_sigmoid, exp_tanh,
+                         nested_lookup, polyphonic_dag)
+
+__all__ = ['Engine', 'get_engine', 'total_launches', 'DynamicSizeFilteredNoise', 'InHarmonic',
+           'MultiAdd', 'MultiInharmonic', 'Processor', 'ProcessorGroup', 'Reverb',
+           'exp_sigmoid', 'exp_tanh', 'nested_lookup', 'polyphonic_dag', '_lib']

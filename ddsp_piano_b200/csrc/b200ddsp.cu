@@ -32,8 +32,32 @@ struct b200ddsp_handle {
   bool fast_div = false;       // 3-op division == IEEE division for this sample rate
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
+  cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
+  bool ev_used[B200DDSP_N_STAGES] = {};
   char err[512] = {0};
 };
+
+// Brackets one stage with events when profiling is on.
+struct StageTimer {
+  b200ddsp_handle* h;
+  int stage;
+  cudaStream_t st;
+  StageTimer(b200ddsp_handle* h_, int stage_, cudaStream_t st_) : h(h_), stage(stage_), st(st_) {
+    if (h->profiling) {
+      cudaEventRecord(h->ev_begin[stage], st);
+      h->ev_used[stage] = true;
+    }
+  }
+  ~StageTimer() {
+    if (h->profiling) cudaEventRecord(h->ev_end[stage], st);
+  }
+};
+
+static void reset_stage_flags(b200ddsp_handle* h) {
+  for (int i = 0; i < B200DDSP_N_STAGES; ++i) h->ev_used[i] = false;
+}
 
 static thread_local char g_create_err[512] = {0};
 
@@ -223,7 +247,32 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
       return B200DDSP_CUDA_ERROR;
     }
   }
+  for (int i = 0; i < B200DDSP_N_STAGES; ++i) {
+    if (cudaEventCreate(&h->ev_begin[i]) != cudaSuccess || cudaEventCreate(&h->ev_end[i]) != cudaSuccess) {
+      fail(nullptr, B200DDSP_CUDA_ERROR, "event creation: %s", cudaGetErrorString(cudaGetLastError()));
+      b200ddsp_destroy(h);
+      return B200DDSP_CUDA_ERROR;
+    }
+  }
   *out = h;
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_set_profiling(b200ddsp_handle* h, int enable) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  h->profiling = enable != 0;
+  reset_stage_flags(h);
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_last_stage_ms(b200ddsp_handle* h, float* ms) {
+  if (!h || !ms) return B200DDSP_BAD_ARGUMENT;
+  for (int i = 0; i < B200DDSP_N_STAGES; ++i) {
+    ms[i] = 0.f;
+    if (!h->ev_used[i]) continue;
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_end[i]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[i], h->ev_begin[i], h->ev_end[i]));
+  }
   return B200DDSP_OK;
 }
 
@@ -231,6 +280,10 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (!h) return B200DDSP_OK;
   if (h->d_window) cudaFree(h->d_window);
   if (h->d_cmat_t) cudaFree(h->d_cmat_t);
+  for (int i = 0; i < B200DDSP_N_STAGES; ++i) {
+    if (h->ev_begin[i]) cudaEventDestroy(h->ev_begin[i]);
+    if (h->ev_end[i]) cudaEventDestroy(h->ev_end[i]);
+  }
   delete h;
   return B200DDSP_OK;
 }
@@ -401,13 +454,18 @@ static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, c
   if (smem > 48 * 1024)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
   if (a.n_chunks > 1) {
-    dim3 grid(a.n_chunks - 1, B, G);
-    launch_additive(a, HP, fast, true, grid, warps * 32, 0, st);
-    CHECK_LAUNCH(h, "additive_kernel<ends>");
+    {
+      StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
+      dim3 grid(a.n_chunks - 1, B, G);
+      launch_additive(a, HP, fast, true, grid, warps * 32, 0, st);
+      CHECK_LAUNCH(h, "additive_kernel<ends>");
+    }
+    StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
     const int n = P * B * S * H;
     additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(offsets, P * B * S, a.n_chunks, H);
     CHECK_LAUNCH(h, "additive_offsets_kernel");
   }
+  StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
   dim3 grid(a.n_chunks, B, G);
   launch_additive(a, HP, fast, false, grid, warps * 32, smem, st);
   CHECK_LAUNCH(h, "additive_kernel<synth>");
@@ -474,6 +532,7 @@ static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const 
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
   CUDA_TRY(h, cudaFuncSetAttribute(noise_fir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
+  StageTimer tm(h, B200DDSP_STAGE_NOISE_MIX, st);
   dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B);
   noise_fir_kernel<0><<<grid, kNoiseThreads, smem, st>>>(a, vp);
   CHECK_LAUNCH(h, "noise_fir_kernel");
@@ -519,6 +578,7 @@ static std::vector<int> fft_radices(int n) {
 
 static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
                       int N, int L, float2* tw, float2* buf_a, float2* buf_b, cudaStream_t st) {
+  StageTimer tm(h, B200DDSP_STAGE_REVERB, st);
   const int n = fft_size_for(N, L);
   const std::vector<int> radices = fft_radices(n);
   const int n_pass = (int)radices.size();
@@ -635,7 +695,9 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     vp.mags[v] = mags + (size_t)v * B * F * M;
     vp.noise[v] = vc.noise;
   }
+  reset_stage_flags(h);
   {
+    StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
     AdditiveControlsArgs a{};
     a.amp_out = amp; a.hd_out = hd; a.shifts_out = shifts; a.f0_out = f0;
     a.n_frames_voice = B * F;
@@ -648,7 +710,6 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     dim3 grid((a.n_frames_voice + 7) / 8, P);
     additive_controls_kernel<<<grid, 256, 0, st>>>(a, cp);
     CHECK_LAUNCH(h, "additive_controls_kernel");
-  }
   for (int v = 0; v < P; ++v) {
     // contiguous stacked parents ([P,B,F,M], sub_modules.py:589-596) collapse into one launch
     int run = 1;
@@ -658,6 +719,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
                                          (size_t)run * B * F * M, stream))
       return rc;
     v += run - 1;
+  }
   }
   // additive oscillator bank -> G partial sums
   if (int rc = run_additive(h, amp, hd, shifts, f0, (float*)(base + w.offsets),

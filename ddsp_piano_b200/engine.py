@@ -1,0 +1,280 @@
+"""Host-side owner of a ``b200ddsp_handle``: validates tensors, owns the scratch workspace
+(a torch CUDA buffer -- PyTorch is used for device memory and streams only) and turns
+status codes into the exceptions the reference raises (``ValueError`` for shape problems,
+like ddsp; ``RuntimeError`` for CUDA failures).
+"""
+import ctypes
+import threading
+
+import torch
+
+from . import _lib
+
+_ENGINES = {}
+_LOCK = threading.Lock()
+
+
+def scale_fn_id(fn):
+    """Map the reference's ``scale_fn`` argument (``core.exp_sigmoid``, ``exp_tanh``
+    [modules/inharm_synth.py:13-17] or ``None``) to the ABI enum."""
+    if fn is None:
+        return 2
+    name = fn if isinstance(fn, str) else getattr(fn, '__name__', None)
+    if name in ('exp_sigmoid', 'core.exp_sigmoid'):
+        return 0
+    if name == 'exp_tanh':
+        return 1
+    if name in ('none', 'None'):
+        return 2
+    raise ValueError(f'unsupported scale_fn {fn!r}: the CUDA path implements exp_sigmoid, '
+                     'exp_tanh and None')
+
+
+class Engine:
+    """One handle = one processor configuration on one device."""
+
+    def __init__(self, device, **cfg):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('b200ddsp needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device(device)
+        self.cfg = _lib.Config(**cfg)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.b200ddsp_create(ctypes.byref(self.cfg), ctypes.byref(self.handle))
+        if rc != 0:
+            msg = self.lib.b200ddsp_last_error(None).decode()
+            raise (ValueError if rc in (-1, -3, -6) else RuntimeError)(
+                f'b200ddsp_create: {_lib.STATUS_NAMES.get(rc, rc)}: {msg}')
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.b200ddsp_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- helpers --------------------------------------------------------------------------
+    def check(self, rc):
+        if rc == 0:
+            return
+        msg = self.lib.b200ddsp_last_error(self.handle).decode()
+        text = f'b200ddsp {_lib.STATUS_NAMES.get(rc, rc)}: {msg}'
+        if rc in (-1, -2, -3, -6):
+            raise ValueError(text)
+        raise RuntimeError(text)
+
+    def tensor(self, x, name, ndim=None):
+        """ddsp.core.tf_float32 + device/contiguity requirements of the ABI."""
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(x, dtype=torch.float32, device=self.device)
+        if x.device != self.device:
+            raise ValueError(f'{name} is on {x.device}, engine is on {self.device}')
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        if ndim is not None and x.dim() != ndim:
+            raise ValueError(f'{name} must have {ndim} dimensions, got shape {tuple(x.shape)}')
+        return x
+
+    def workspace(self, nbytes):
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def upsampling(self):
+        return int(self.cfg.sample_rate / self.cfg.frame_rate)
+
+    def launch_count(self):
+        return int(self.lib.b200ddsp_launch_count(self.handle))
+
+    def set_profiling(self, enable):
+        self.check(self.lib.b200ddsp_set_profiling(self.handle, int(bool(enable))))
+
+    def last_stage_ms(self):
+        """Device time of each stage of the most recent call (needs set_profiling(True))."""
+        ms = (ctypes.c_float * len(_lib.STAGES))()
+        self.check(self.lib.b200ddsp_last_stage_ms(self.handle, ms))
+        return dict(zip(_lib.STAGES, [float(x) for x in ms]))
+
+    # -- entry points ---------------------------------------------------------------------
+    def additive_controls(self, amplitudes, harmonic_distribution, inharm_coef, f0_hz):
+        amplitudes = self.tensor(amplitudes, 'amplitudes', 3)
+        hd = self.tensor(harmonic_distribution, 'harmonic_distribution', 3)
+        inharm_coef = self.tensor(inharm_coef, 'inharm_coef', 3)
+        f0_hz = self.tensor(f0_hz, 'f0_hz', 3)
+        B, F, H = hd.shape
+        S = f0_hz.shape[-1]
+        for t, n, c in ((amplitudes, 'amplitudes', 1), (inharm_coef, 'inharm_coef', 1),
+                        (f0_hz, 'f0_hz', S)):
+            if tuple(t.shape) != (B, F, c):
+                raise ValueError(f'{n} has shape {tuple(t.shape)}, expected {(B, F, c)}')
+        amp_out = torch.empty_like(amplitudes)
+        hd_out = torch.empty_like(hd)
+        shifts_out = torch.empty_like(hd)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_additive_controls(
+                self.handle, amplitudes.data_ptr(), hd.data_ptr(), inharm_coef.data_ptr(),
+                f0_hz.data_ptr(), amp_out.data_ptr(), hd_out.data_ptr(), shifts_out.data_ptr(),
+                B, F, H, S, self.stream()))
+        return {'amplitudes': amp_out, 'harmonic_distribution': hd_out,
+                'harmonic_shifts': shifts_out, 'f0_hz': f0_hz}
+
+    def additive_signal(self, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz):
+        amplitudes = self.tensor(amplitudes, 'amplitudes', 3)
+        hd = self.tensor(harmonic_distribution, 'harmonic_distribution', 3)
+        shifts = self.tensor(harmonic_shifts, 'harmonic_shifts', 3)
+        f0_hz = self.tensor(f0_hz, 'f0_hz', 3)
+        B, F, H = hd.shape
+        S = f0_hz.shape[-1]
+        if tuple(amplitudes.shape) != (B, F, 1) or tuple(shifts.shape) != (B, F, H) or \
+                tuple(f0_hz.shape[:2]) != (B, F):
+            raise ValueError('additive controls have inconsistent shapes: '
+                             f'{tuple(amplitudes.shape)}, {tuple(hd.shape)}, '
+                             f'{tuple(shifts.shape)}, {tuple(f0_hz.shape)}')
+        N = F * self.upsampling
+        out = torch.empty([B, N], dtype=torch.float32, device=self.device)
+        n_chunks = -(-N // 1000)
+        ws = self.workspace(B * S * n_chunks * H * 4)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_additive_signal(
+                self.handle, amplitudes.data_ptr(), hd.data_ptr(), shifts.data_ptr(),
+                f0_hz.data_ptr(), out.data_ptr(), B, F, H, S, 0, ws.data_ptr(), ws.numel(),
+                self.stream()))
+        return out
+
+    def noise_controls(self, magnitudes):
+        magnitudes = self.tensor(magnitudes, 'magnitudes')
+        out = torch.empty_like(magnitudes)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_noise_controls(
+                self.handle, magnitudes.data_ptr(), out.data_ptr(), magnitudes.numel(),
+                self.stream()))
+        return {'magnitudes': out}
+
+    def noise_signal(self, magnitudes, noise=None, seed=0, stream_id=0):
+        magnitudes = self.tensor(magnitudes, 'magnitudes', 3)
+        B, F, M = magnitudes.shape
+        N = F * self.upsampling
+        if noise is not None:
+            noise = self.tensor(noise, 'noise', 2)
+            if tuple(noise.shape) != (B, N):
+                raise ValueError(f'noise has shape {tuple(noise.shape)}, expected {(B, N)}')
+        out = torch.empty([B, N], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_noise_signal(
+                self.handle, magnitudes.data_ptr(), noise.data_ptr() if noise is not None else None,
+                seed, stream_id, out.data_ptr(), B, F, M, 0, self.stream()))
+        return out
+
+    def reverb(self, audio, ir):
+        audio = self.tensor(audio, 'audio', 2)
+        ir = self.tensor(ir, 'ir')
+        if ir.dim() == 1:
+            ir = ir[None, :]
+        if ir.dim() == 3:
+            ir = ir[:, :, 0].contiguous()
+        B, N = audio.shape
+        if ir.shape[0] == 1 and B > 1:
+            ir = ir.expand(B, -1).contiguous()
+        if ir.shape[0] != B:
+            # ddsp.core.fft_convolve's message
+            raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
+                             'be the same.'.format(B, ir.shape[0]))
+        L = ir.shape[1]
+        n = 2
+        while n < N + L - 1:
+            n *= 2
+        al = lambda x: (x + 255) // 256 * 256
+        ws = self.workspace(al(n * 8) + 2 * al(B * n * 8))
+        out = torch.empty_like(audio)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_reverb(
+                self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L,
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return out
+
+    def forward_polyphonic(self, voices, reverb_ir=None, seed=0):
+        """voices: list of dicts with keys amplitudes, harmonic_distribution, inharm_coef,
+        f0_hz, magnitudes and optionally noise.  Returns (dry, wet or None)."""
+        P = len(voices)
+        if P < 1 or P > _lib.MAX_VOICES:
+            raise ValueError(f'n_synths={P} outside [1, {_lib.MAX_VOICES}]')
+        arr = (_lib.Voice * P)()
+        keep = []
+        B = F = H = S = M = None
+        for i, v in enumerate(voices):
+            amp = self.tensor(v['amplitudes'], f'amplitudes_{i}', 3)
+            hd = self.tensor(v['harmonic_distribution'], f'harmonic_distribution_{i}', 3)
+            inh = self.tensor(v['inharm_coef'], f'inharm_coef_{i}', 3)
+            f0 = self.tensor(v['f0_hz'], f'f0_hz_{i}', 3)
+            mag = self.tensor(v['magnitudes'], f'magnitudes_{i}', 3)
+            if i == 0:
+                B, F, H = hd.shape
+                S, M = f0.shape[-1], mag.shape[-1]
+            want = {'amplitudes': (B, F, 1), 'harmonic_distribution': (B, F, H),
+                    'inharm_coef': (B, F, 1), 'f0_hz': (B, F, S), 'magnitudes': (B, F, M)}
+            for t, k in ((amp, 'amplitudes'), (hd, 'harmonic_distribution'),
+                         (inh, 'inharm_coef'), (f0, 'f0_hz'), (mag, 'magnitudes')):
+                if tuple(t.shape) != want[k]:
+                    raise ValueError(f'{k}_{i} has shape {tuple(t.shape)}, expected {want[k]}')
+            nz = v.get('noise')
+            if nz is not None:
+                nz = self.tensor(nz, f'noise_{i}', 2)
+                if tuple(nz.shape) != (B, F * self.upsampling):
+                    raise ValueError(f'noise_{i} has shape {tuple(nz.shape)}')
+            keep += [amp, hd, inh, f0, mag, nz]
+            arr[i] = _lib.Voice(amp.data_ptr(), hd.data_ptr(), inh.data_ptr(), f0.data_ptr(),
+                                mag.data_ptr(), nz.data_ptr() if nz is not None else None)
+        N = F * self.upsampling
+        L = 0
+        ir = None
+        if reverb_ir is not None:
+            ir = self.tensor(reverb_ir, 'reverb_ir')
+            if ir.dim() == 1:
+                ir = ir[None, :]
+            if ir.dim() == 3:
+                ir = ir[:, :, 0].contiguous()
+            if ir.shape[0] == 1 and B > 1:
+                ir = ir.expand(B, -1).contiguous()
+            if ir.shape[0] != B:
+                raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
+                                 'be the same.'.format(B, ir.shape[0]))
+            L = ir.shape[1]
+        nbytes = self.lib.b200ddsp_workspace_bytes(self.handle, P, B, F, H, S, M, L)
+        ws = self.workspace(nbytes)
+        dry = torch.empty([B, N], dtype=torch.float32, device=self.device)
+        wet = torch.empty_like(dry) if ir is not None else None
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_forward_polyphonic(
+                self.handle, arr, P, ir.data_ptr() if ir is not None else None, dry.data_ptr(),
+                wet.data_ptr() if wet is not None else None, B, F, H, S, M, L, seed,
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return dry, wet
+
+
+def get_engine(device, **cfg):
+    """Engines are cached per (device, configuration)."""
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError(f'b200ddsp processors run on CUDA tensors only (got {device}); '
+                           'there is no CPU fallback')
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    key = (str(device),) + tuple(sorted(cfg.items()))
+    with _LOCK:
+        eng = _ENGINES.get(key)
+        if eng is None:
+            eng = _ENGINES[key] = Engine(device, **cfg)
+        return eng
+
+
+def total_launches():
+    return sum(e.launch_count() for e in _ENGINES.values())

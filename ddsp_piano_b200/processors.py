@@ -1,0 +1,370 @@
+"""The reference's operator API for the synthesis hot path, backed by the sm_100a kernels.
+
+Same class names, constructor arguments, method names, dictionary keys and DAG format as
+the reference, so ``configs/dafx22.gin:91-111`` can bind these in place of its own:
+
+  reference                                                      here
+  ---------------------------------------------------------------------------------------
+  ddsp.processors.Processor / ProcessorGroup (ddsp v3.7.0)        Processor / ProcessorGroup
+  modules/inharm_synth.py:130-244  InHarmonic                     InHarmonic
+  modules/inharm_synth.py:247-293  MultiInharmonic                MultiInharmonic
+  modules/inharm_synth.py:296-309  MultiAdd                       MultiAdd
+  modules/filtered_noise_synth.py:12-42 DynamicSizeFilteredNoise  DynamicSizeFilteredNoise
+  ddsp.effects.Reverb (trainable=False)                           Reverb
+  modules/polyphonic_dag.py:6-42   polyphonic_dag                 polyphonic_dag
+
+Tensors are ``torch.Tensor`` on a CUDA device (float32); every ``get_signal`` runs
+hand-written CUDA through the C ABI (``include/b200ddsp.h``).  ``ProcessorGroup`` walks the
+DAG node by node exactly like ddsp's ``DAGLayer``; when the DAG has the shape
+``polyphonic_dag`` produces it instead issues ONE ``b200ddsp_forward_polyphonic`` call
+(``fused=True``, the default).
+"""
+import os
+
+import torch
+
+from .engine import get_engine, scale_fn_id
+
+
+def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
+    """ddsp.core.exp_sigmoid.  Passed as ``scale_fn`` it only selects the in-kernel scaling;
+    called directly it is evaluated with torch ops on ``x``'s device."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    return max_value * torch.sigmoid(x) ** torch.log(torch.tensor(exponent)).item() + threshold
+
+
+def exp_tanh(x, max_value=2., exponent=10., gain=1., threshold=1e-7):
+    """modules/inharm_synth.py:13-17."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    y = max_value * (0.5 * (torch.tanh(gain * x) + 1.)) ** torch.log(torch.tensor(exponent)).item()
+    return y + threshold
+
+
+def nested_lookup(nested_key, nested_dict, delimiter='/'):
+    """ddsp.core.nested_lookup."""
+    value = nested_dict
+    for key in nested_key.split(delimiter):
+        try:
+            value = value[key]
+        except KeyError:
+            raise KeyError(f'Key \'{key}\' as a part of nested key \'{nested_key}\' '
+                           'not found during nested dictionary lookup, out of '
+                           f'available keys: {list(nested_dict.keys())}')
+    return value
+
+
+_DEFAULT_CFG = dict(sample_rate=16000, frame_rate=250, min_frequency=20.0, additive_scale_fn=0,
+                    normalize_after_nyquist_cut=1, normalize_below_nyquist=1, inference=1,
+                    noise_scale_fn=0, noise_initial_bias=-5.0, noise_window_size=257,
+                    reverb_add_dry=1, n_noise_bands=0, fast_phase=0)
+
+
+def _device_of(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor):
+            return t.device
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class Processor:
+    """ddsp.processors.Processor: ``__call__`` = ``get_signal(**get_controls(*args))``."""
+
+    def __init__(self, name, trainable=True):
+        self.name = name
+        self.trainable = trainable
+
+    def __call__(self, *args, return_outputs_dict=False, **kwargs):
+        for k in ['training', 'mask']:
+            kwargs.pop(k, None)
+        controls = self.get_controls(*args, **kwargs)
+        signal = self.get_signal(**controls)
+        if return_outputs_dict:
+            return dict(signal=signal, controls=controls)
+        return signal
+
+    def get_controls(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def get_signal(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def engine_config(self):
+        """ABI configuration fields this processor determines."""
+        return {}
+
+
+class InHarmonic(Processor):
+    """modules/inharm_synth.py:130-244: bank of inharmonic cosine oscillators."""
+
+    def __init__(self, frame_rate=250, sample_rate=16000, min_frequency=20,
+                 scale_fn=exp_sigmoid, normalize_after_nyquist_cut=True,
+                 normalize_below_nyquist=True, inference=False, name='inharmonic'):
+        self.frame_rate = frame_rate
+        self.sample_rate = sample_rate
+        self.min_frequency = min_frequency
+        self.normalize_after_nyquist_cut = normalize_after_nyquist_cut
+        self.scale_fn = scale_fn
+        self.normalize_below_nyquist = normalize_below_nyquist
+        self.inference = inference
+        super().__init__(name=name)
+
+    @property
+    def upsampling(self):
+        return int(self.sample_rate / self.frame_rate)
+
+    def engine_config(self):
+        return dict(sample_rate=int(self.sample_rate), frame_rate=int(self.frame_rate),
+                    min_frequency=float(self.min_frequency),
+                    additive_scale_fn=scale_fn_id(self.scale_fn),
+                    normalize_after_nyquist_cut=int(bool(self.normalize_after_nyquist_cut)),
+                    normalize_below_nyquist=int(bool(self.normalize_below_nyquist)),
+                    inference=int(bool(self.inference)))
+
+    def _engine(self, *tensors):
+        return get_engine(_device_of(*tensors), **{**_DEFAULT_CFG, **self.engine_config()})
+
+    def get_controls(self, amplitudes, harmonic_distribution, inharm_coef, f0_hz):
+        return self._engine(amplitudes, f0_hz).additive_controls(
+            amplitudes, harmonic_distribution, inharm_coef, f0_hz)
+
+    def get_signal(self, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz):
+        return self._engine(amplitudes, f0_hz).additive_signal(
+            amplitudes, harmonic_distribution, harmonic_shifts, f0_hz)
+
+
+class MultiInharmonic(InHarmonic):
+    """modules/inharm_synth.py:247-293: one oscillator bank per substring (f0_hz [B, F, S]),
+    sharing amplitudes (pre-divided by S) and inharmonic shifts.  The S syntheses and their
+    sum are one kernel launch here."""
+
+    def __init__(self, name='multi_inharmonic', **kwargs):
+        super().__init__(name=name, **kwargs)
+
+
+class MultiAdd(Processor):
+    """modules/inharm_synth.py:296-309: sum an arbitrary number of signals."""
+
+    def __init__(self, name='add'):
+        super().__init__(name=name)
+
+    def get_controls(self, *signals):
+        return {f'signal_{i}': s for i, s in enumerate(signals)}
+
+    def get_signal(self, **signals):
+        return sum(signals.values())
+
+
+class DynamicSizeFilteredNoise(Processor):
+    """modules/filtered_noise_synth.py:12-42 on top of ddsp.synths.FilteredNoise
+    (``n_samples`` is accepted and ignored, like in the reference: the length follows the
+    controls).  The reference draws unseeded uniform noise per call; here it comes from an
+    in-kernel Philox stream keyed by (``seed``, call counter), or -- for parity tests -- from
+    tensors queued with :meth:`push_noise`."""
+
+    def __init__(self, frame_rate=250, sample_rate=16000, n_samples=64000, window_size=257,
+                 scale_fn=exp_sigmoid, initial_bias=-5.0, name='filtered_noise', seed=None):
+        super().__init__(name=name)
+        self.frame_rate = frame_rate
+        self.sample_rate = sample_rate
+        self.n_samples = n_samples
+        self.window_size = window_size
+        self.scale_fn = scale_fn
+        self.initial_bias = initial_bias
+        self.seed = int.from_bytes(os.urandom(8), 'little') if seed is None else int(seed)
+        self._calls = 0
+        self._injected = []
+
+    @property
+    def upsampling(self):
+        return int(self.sample_rate / self.frame_rate)
+
+    def push_noise(self, noise):
+        """Queue a [B, N] tensor to be filtered by the next ``get_signal`` instead of fresh
+        noise (FIFO)."""
+        self._injected.append(noise)
+
+    def pop_noise(self):
+        return self._injected.pop(0) if self._injected else None
+
+    def next_stream_id(self, n=1):
+        sid = self._calls
+        self._calls += n
+        return sid
+
+    def engine_config(self, n_bands=0):
+        return dict(sample_rate=int(self.sample_rate), frame_rate=int(self.frame_rate),
+                    noise_scale_fn=scale_fn_id(self.scale_fn),
+                    noise_initial_bias=float(self.initial_bias),
+                    noise_window_size=int(self.window_size), n_noise_bands=int(n_bands))
+
+    def _engine(self, magnitudes):
+        cfg = {**_DEFAULT_CFG, **self.engine_config(magnitudes.shape[-1])}
+        return get_engine(_device_of(magnitudes), **cfg)
+
+    def get_controls(self, magnitudes):
+        return self._engine(magnitudes).noise_controls(magnitudes)
+
+    def get_signal(self, magnitudes):
+        return self._engine(magnitudes).noise_signal(
+            magnitudes, noise=self.pop_noise(), seed=self.seed & (2 ** 64 - 1),
+            stream_id=self.next_stream_id())
+
+
+class Reverb(Processor):
+    """ddsp.effects.Reverb with ``trainable=False`` (configs/dafx22.gin:99-100,111): the
+    impulse response is an input; ``ir[:, 0]`` is masked and the dry signal added."""
+
+    def __init__(self, trainable=False, reverb_length=48000, add_dry=True, name='reverb'):
+        super().__init__(name=name, trainable=trainable)
+        if trainable:
+            raise ValueError('Reverb(trainable=True) owns a tf.Variable in ddsp; the hot path '
+                             'implements the trainable=False form the reference configures')
+        self._reverb_length = reverb_length
+        self._add_dry = add_dry
+
+    def engine_config(self):
+        return dict(reverb_add_dry=int(bool(self._add_dry)))
+
+    def get_controls(self, audio, ir=None):
+        if ir is None:
+            raise ValueError('Must provide "ir" tensor if Reverb trainable=False.')
+        return {'audio': audio, 'ir': ir}
+
+    def get_signal(self, audio, ir):
+        eng = get_engine(_device_of(audio, ir), **{**_DEFAULT_CFG, **self.engine_config()})
+        return eng.reverb(audio, ir)
+
+
+def polyphonic_dag(additive, noise, reverb=None,
+                   additive_controls=['amps', 'harmonic_distribution', 'f0_hz'],
+                   noise_controls=['noise_magnitudes'], reverb_controls=[], n_synths=16):
+    """modules/polyphonic_dag.py:6-42: per voice additive_i, noise_i and a running sum
+    'add', then the reverb on 'add/signal'."""
+    add = MultiAdd(name='add')
+    dag = [(additive, [c + '_0' for c in additive_controls]),
+           (noise, [c + '_0' for c in noise_controls]),
+           (add, [noise.name + '/signal', additive.name + '/signal'])]
+    for i in range(1, n_synths):
+        dag.append((additive, [c + f'_{i}' for c in additive_controls]))
+        dag.append((noise, [c + f'_{i}' for c in noise_controls]))
+        dag.append((add, ['add/signal', noise.name + '/signal', additive.name + '/signal']))
+    if reverb is not None:
+        dag.append((reverb, ['add/signal'] + reverb_controls))
+    return dag
+
+
+class ProcessorGroup:
+    """ddsp.processors.ProcessorGroup (a ``DAGLayer``): runs ``(processor, [input keys])``
+    nodes in order over a growing outputs dict; ``'a/b'`` keys are nested lookups; each
+    node's ``{'signal', 'controls'}`` is stored under the processor's name and the last
+    one aliased as ``'out'``.  Call site: modules/piano_model.py:160-164.
+
+    ``fused=True`` (default): a DAG of the ``polyphonic_dag`` shape runs as one C-ABI call.
+    The outputs dict then holds ``add``, ``out`` (and ``reverb``); per-voice entries
+    (``additive``, ``noise``), which in the reference hold the LAST voice only because the
+    processor objects are shared, are produced only by the node-by-node walk
+    (``fused=False``)."""
+
+    def __init__(self, dag, name='processor_group', fused=True):
+        self.name = name
+        self.dag = []
+        self._modules = {}
+        for node in dag:
+            module, keys = node[0], node[1]
+            self._modules[module.name] = module
+            self.dag.append((module.name, list(keys)))
+        self.fused = fused
+        self._plan = self._match_polyphonic() if fused else None
+
+    @property
+    def processors(self):
+        return [self._modules[k] for k, _ in self.dag]
+
+    # -- pattern match --------------------------------------------------------------------
+    def _match_polyphonic(self):
+        dag = self.dag
+        n = len(dag)
+        has_reverb = n % 3 == 1
+        if n < 3 or n % 3 == 2:
+            return None
+        P = n // 3
+        add_name, noise_name, sum_name = dag[0][0], dag[1][0], dag[2][0]
+        additive, noise, add = (self._modules[add_name], self._modules[noise_name],
+                                self._modules[sum_name])
+        if not (isinstance(additive, InHarmonic) and isinstance(noise, DynamicSizeFilteredNoise)
+                and isinstance(add, MultiAdd)):
+            return None
+        voices = []
+        for i in range(P):
+            a, z, s = dag[3 * i], dag[3 * i + 1], dag[3 * i + 2]
+            if (a[0], z[0], s[0]) != (add_name, noise_name, sum_name):
+                return None
+            if len(a[1]) != 4 or len(z[1]) != 1:
+                return None
+            want = [noise_name + '/signal', add_name + '/signal']
+            if i > 0:
+                want = [sum_name + '/signal'] + want
+            if s[1] != want:
+                return None
+            voices.append((a[1], z[1][0]))
+        reverb, ir_key = None, None
+        if has_reverb:
+            r = dag[-1]
+            reverb = self._modules[r[0]]
+            if not isinstance(reverb, Reverb) or len(r[1]) != 2 or r[1][0] != sum_name + '/signal':
+                return None
+            ir_key = r[1][1]
+        if int(additive.sample_rate) != int(noise.sample_rate) or \
+                int(additive.frame_rate) != int(noise.frame_rate):
+            return None
+        return dict(additive=additive, noise=noise, add=add, reverb=reverb, voices=voices,
+                    ir_key=ir_key)
+
+    # -- execution ------------------------------------------------------------------------
+    def _run_fused(self, outputs):
+        plan = self._plan
+        additive, noise, reverb = plan['additive'], plan['noise'], plan['reverb']
+        voices = []
+        for add_keys, mag_key in plan['voices']:
+            amp, hd, inh, f0 = (nested_lookup(k, outputs) for k in add_keys)
+            voices.append({'amplitudes': amp, 'harmonic_distribution': hd, 'inharm_coef': inh,
+                           'f0_hz': f0, 'magnitudes': nested_lookup(mag_key, outputs),
+                           'noise': noise.pop_noise()})
+        M = voices[0]['magnitudes'].shape[-1]
+        cfg = {**_DEFAULT_CFG, **additive.engine_config(), **noise.engine_config(M)}
+        if reverb is not None:
+            cfg.update(reverb.engine_config())
+        eng = get_engine(_device_of(voices[0]['f0_hz']), **cfg)
+        ir = nested_lookup(plan['ir_key'], outputs) if reverb is not None else None
+        seed = (noise.seed + 0x9E3779B97F4A7C15 * noise.next_stream_id(len(voices))) & (2 ** 64 - 1)
+        dry, wet = eng.forward_polyphonic(voices, reverb_ir=ir, seed=seed)
+        outputs[plan['add'].name] = {'signal': dry, 'controls': {}}
+        last = outputs[plan['add'].name]
+        if reverb is not None:
+            outputs[reverb.name] = {'signal': wet, 'controls': {'audio': dry, 'ir': ir}}
+            last = outputs[reverb.name]
+        outputs['out'] = last
+        return outputs
+
+    def get_controls(self, inputs, **kwargs):
+        outputs = inputs
+        if self._plan is not None:
+            return self._run_fused(outputs)
+        module_outputs = None
+        for module_key, input_keys in self.dag:
+            module = self._modules[module_key]
+            args = [nested_lookup(key, outputs) for key in input_keys]
+            module_outputs = module(*args, return_outputs_dict=True, **kwargs)
+            outputs[module_key] = module_outputs
+        outputs['out'] = module_outputs
+        return outputs
+
+    def get_signal(self, outputs):
+        return outputs['out']['signal']
+
+    def __call__(self, inputs, return_outputs_dict=False, **kwargs):
+        controls = self.get_controls(inputs, **kwargs)
+        signal = self.get_signal(controls)
+        if return_outputs_dict:
+            return dict(signal=signal, controls=controls)
+        return signal

@@ -162,6 +162,23 @@ int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices
  * gpu_launches claim is read from here). */
 uint64_t b200ddsp_launch_count(const b200ddsp_handle* h);
 
+/* Optional per-stage device timing (bench.py's roofline figures).  When enabled, every call
+ * brackets its stages with CUDA events (created in b200ddsp_create) on the caller's stream;
+ * b200ddsp_last_stage_ms waits for the events of the most recent call and returns the
+ * duration of each stage in milliseconds (0 for stages that did not run).  Not graph
+ * capturable while enabled. */
+typedef enum {
+  B200DDSP_STAGE_CONTROLS = 0,      /* get_controls kernels */
+  B200DDSP_STAGE_PHASE_ENDS = 1,    /* additive pass 1: chunk end phases */
+  B200DDSP_STAGE_PHASE_SCAN = 2,    /* chunk ends -> chunk offsets */
+  B200DDSP_STAGE_OSCILLATORS = 3,   /* additive pass 2: the oscillator bank */
+  B200DDSP_STAGE_NOISE_MIX = 4,     /* noise FIR of every voice + mix */
+  B200DDSP_STAGE_REVERB = 5,        /* FFT convolution */
+  B200DDSP_N_STAGES = 6
+} b200ddsp_stage;
+int b200ddsp_set_profiling(b200ddsp_handle* h, int enable);
+int b200ddsp_last_stage_ms(b200ddsp_handle* h, float* ms /* [B200DDSP_N_STAGES] */);
+
 #ifdef __cplusplus
 }
 #endif
