@@ -95,6 +95,8 @@ def load():
     lib.b200ddsp_destroy.argtypes = [vp]
     lib.b200ddsp_workspace_bytes.restype = sz
     lib.b200ddsp_workspace_bytes.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci]
+    lib.b200ddsp_additive_workspace_bytes.restype = sz
+    lib.b200ddsp_additive_workspace_bytes.argtypes = [vp, ci, ci, ci, ci]
     lib.b200ddsp_additive_controls.restype = ci
     lib.b200ddsp_additive_controls.argtypes = [vp] + [vp] * 7 + [ci, ci, ci, ci, vp]
     lib.b200ddsp_additive_signal.restype = ci
@@ -119,7 +121,8 @@ def load():
 
 
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
-           'b200ddsp_workspace_bytes', 'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
+           'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
+           'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
            'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_reverb',
            'b200ddsp_forward_polyphonic', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']

@@ -1,0 +1,354 @@
+// Fast path of the additive oscillator bank (same maths and rounding as additive.cuh, which
+// stays as the generic path): used when U % 8 == 0, floor(float(t) * scale) == t / U for
+// every sample, and the 3-op division is exact for the sample rate (all checked on the host).
+//
+// What it adds over the generic kernel -- none of it changes a single output bit of the phase:
+//  * a warp owns a VOICE: lane l carries partials l, l+32, ... for SP substrings at once
+//    (NA x SP phase chains per lane), so the amplitude envelope is evaluated once per partial
+//    and shared by the substrings;
+//  * dead partial groups are not synthesised: get_controls zeroes every partial above Nyquist
+//    and mutes voices below min_frequency, so groups of 32 partials whose amplitude is zero in
+//    every frame touching a chunk are dropped for that chunk (NA = number of live groups,
+//    found by additive_alive_kernel), and the phase-only pass skips a group once no later
+//    chunk needs its offset;
+//  * per control frame the warp picks the cheapest exact variant:
+//      steady   both frame endpoints have identical partial frequencies (a held note):
+//               omega is constant over the frame -> 1 FADD per sample in the phase chain
+//      general  legacy-bilinear lerp per sample (7 FP32 ops in the chain)
+//    crossed with
+//      silent   every amplitude of the frame pair is zero: phase chain only
+//      live     amplitude cross-fade, Nyquist mask (cos_oscillator_bank, inharm_synth.py:65-67;
+//               per frame in steady frames, per sample otherwise), cos, accumulate
+//  * the unrolled body is 4 samples (not 32) so that the variants a SM executes concurrently
+//    stay inside the 32 KB instruction cache (the first version of this kernel spent its top
+//    stall reason on instruction fetch).
+#pragma once
+#include "additive.cuh"
+
+namespace b200ddsp {
+
+struct AdditiveFastArgs {
+  AdditiveArgs a;
+  const unsigned char* synth_na;   // [R, n_chunks] live partial groups per (row, chunk)
+  const unsigned char* ends_na;    // [R, n_chunks] groups whose end phase a later chunk needs
+  int sp;                          // substrings per pass (1 or 2)
+};
+
+// ---- liveness scan ---------------------------------------------------------------------------
+// na_frame[row, k] = 1 + index of the highest 32-partial group with a non-zero partial amplitude
+// in frame k (0 = silent frame).  One warp per (row, frame).
+__global__ void __launch_bounds__(256) additive_alive_frames_kernel(
+    const float* __restrict__ amp, const float* __restrict__ hd, unsigned char* __restrict__ na_frame,
+    int n_row_frames, int H) {
+  const int rf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rf >= n_row_frames) return;
+  const int lane = threadIdx.x & 31;
+  int na = 0;
+  if (__ldg(amp + rf) != 0.f) {
+    for (int q = 0; q * 32 < H; ++q) {
+      const int h = lane + 32 * q;
+      const bool live = (h < H) && (__ldg(hd + (size_t)rf * H + h) != 0.f);
+      if (__ballot_sync(0xffffffffu, live)) na = q + 1;
+    }
+  }
+  if (lane == 0) na_frame[rf] = (unsigned char)na;
+}
+
+// synth_na[row, c] = max na_frame over the frames chunk c reads (frames of its samples plus the
+// next one: the amplitude envelope cross-fades towards frame k+1); ends_na[row, c] = max
+// synth_na over chunks > c.  One thread per row (n_chunks is small).
+__global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
+    const unsigned char* __restrict__ na_frame, unsigned char* __restrict__ synth_na,
+    unsigned char* __restrict__ ends_na, int R, int F, int U, int N, int chunk, int n_chunks) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= R) return;
+  const unsigned char* nf = na_frame + (size_t)row * F;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int t0 = c * chunk, t1 = min(N, t0 + chunk) - 1;
+    const int k0 = t0 / U, k1 = min(F - 1, t1 / U + 1);
+    int m = 0;
+    for (int k = k0; k <= k1; ++k) m = max(m, (int)nf[k]);
+    synth_na[(size_t)row * n_chunks + c] = (unsigned char)m;
+  }
+  int later = 0;
+  for (int c = n_chunks - 1; c >= 0; --c) {
+    ends_na[(size_t)row * n_chunks + c] = (unsigned char)later;
+    later = max(later, (int)synth_na[(size_t)row * n_chunks + c]);
+  }
+}
+
+// ---- per-lane oscillator state ---------------------------------------------------------------
+template <int NA, int SP>
+struct OscState {
+  float ph[NA][SP];    // in-chunk float32 phase accumulator
+  float F[NA][SP];     // partial frequency of frame k
+  float Fn[NA][SP];    // ... of frame k+1
+  float dF[NA][SP];    // Fn - F (rounded once, like the resize kernel's bottom - top)
+  float om[NA][SP];    // steady frames: the constant omega
+  float off[NA][SP];   // chunk offset (synth pass)
+  float A[NA], An[NA]; // partial amplitudes of frames k, k+1
+};
+
+template <int NA, int SP, bool WITH_AMP>
+__device__ __forceinline__ void load_next_frame(const AdditiveArgs& a, int row, int s0, int kn,
+                                                int lane, OscState<NA, SP>& st) {
+  const size_t base = ((size_t)row * a.F + kn) * a.H;
+  const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + kn) : 0.f;
+  float f0[SP];
+#pragma unroll
+  for (int s = 0; s < SP; ++s) f0[s] = __ldg(a.f0 + ((size_t)row * a.F + kn) * a.S + s0 + s);
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    const int h = lane + 32 * q;
+    float sh = 0.f, hdv = 0.f;
+    if (h < a.H) {
+      sh = __ldg(a.shifts + base + h);
+      if (WITH_AMP) hdv = __ldg(a.hd + base + h);
+    }
+    const float n = (float)(h + 1);
+    const float stretch = __fadd_rn(1.0f, sh);
+#pragma unroll
+    for (int s = 0; s < SP; ++s)
+      st.Fn[q][s] = (h < a.H) ? __fmul_rn(__fmul_rn(f0[s], n), stretch) : 0.f;   // :106-108
+    st.An[q] = __fmul_rn(amp, hdv);                                               // :111-114
+  }
+}
+
+enum { kAmpSilent = 0, kAmpLive = 1 };
+constexpr int kOscUnroll = 4;   // samples per unrolled body
+
+// Shift frame k+1 into frame k, load the new k+1, derive the frame's variant.
+template <int NA, int SP, bool WITH_AMP>
+__device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, int s0, int kn, int lane,
+                                              OscState<NA, SP>& st, bool& steady, int& amp_mode) {
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    st.A[q] = st.An[q];
+#pragma unroll
+    for (int s = 0; s < SP; ++s) st.F[q][s] = st.Fn[q][s];
+  }
+  load_next_frame<NA, SP, WITH_AMP>(a, row, s0, kn, lane, st);
+  bool all_steady = true, any_live = false;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    any_live |= WITH_AMP && (st.A[q] != 0.f || st.An[q] != 0.f);
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      st.dF[q][s] = __fadd_rn(st.Fn[q][s], -st.F[q][s]);
+      all_steady &= (st.dF[q][s] == 0.f);
+      // omega of a steady frame: f = F + 0 * lerp = F
+      st.om[q][s] = div_sr<true>(__fmul_rn(st.F[q][s], kTwoPi), a.sr, a.inv_sr);
+    }
+  }
+  steady = __all_sync(0xffffffffu, all_steady);
+  amp_mode = (WITH_AMP && __any_sync(0xffffffffu, any_live)) ? kAmpLive : kAmpSilent;
+}
+
+// kOscUnroll consecutive samples (inside one control frame) of every chain of the lane.
+// win = shared Hann table positioned at the first sample's offset r inside the frame.
+template <int NA, int SP, bool STEADY, int AMP>
+__device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
+                                          const float* win, float tf, float kf,
+                                          float (&y)[kOscUnroll]) {
+  // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
+  bool cut[NA][SP];
+  if (STEADY && AMP != kAmpSilent) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+#pragma unroll
+      for (int s = 0; s < SP; ++s) cut[q][s] = st.F[q][s] >= a.nyquist;
+  }
+#pragma unroll
+  for (int j = 0; j < kOscUnroll; ++j) {
+    float frac = 0.f;
+    if (!STEADY) {
+      const float in = __fmul_rn(tf + (float)j, a.scale);   // legacy ResizeBilinear coordinate
+      frac = __fadd_rn(in, -kf);                            // lerp = in - floor(in)
+    }
+    float w0 = 0.f, w1 = 0.f;
+    if (AMP != kAmpSilent) {
+      w0 = win[j];          // rising half of hann(2U): weight of frame k+1
+      w1 = win[j + a.U];    // falling half: weight of frame k
+    }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      float amp_q = 0.f;   // Hann cross-fade of the frame amplitudes, shared by the substrings
+      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.A[q], w1, __fmul_rn(st.An[q], w0));
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        float om, f = 0.f;
+        if (STEADY) {
+          om = st.om[q][s];
+        } else {
+          f = __fadd_rn(st.F[q][s], __fmul_rn(st.dF[q][s], frac));             // top + (bottom-top)*lerp
+          om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr);            // :69-70
+        }
+        st.ph[q][s] = __fadd_rn(st.ph[q][s], om);                              // cumsum
+        if (AMP != kAmpSilent) {
+          const bool above = STEADY ? cut[q][s] : (f >= a.nyquist);            // :65-67
+          const float amp = above ? 0.f : amp_q;
+          const float p = wrap_to_pi(__fadd_rn(st.ph[q][s], st.off[q][s]));
+          y[j] = __fmaf_rn(amp, __cosf(p), y[j]);                              // :80-83
+        }
+      }
+    }
+  }
+}
+
+// 32 lanes x 4 values -> every lane returns the sum over lanes of y[lane & 3].
+__device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
+#pragma unroll
+  for (int o = 2; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? y[i] : y[i + o];
+      const float keep = up ? y[i + o] : y[i];
+      y[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float v = y[0];
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+// One (row, substring set, chunk) on one warp.  ENDS_ONLY: phase chain only, writes the chunk
+// end phases; otherwise accumulates the audio of the chunk into `row_out` (shared memory).
+template <int NA, int SP, bool ENDS_ONLY>
+__device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0, int c, int lane,
+                                          const float* win, float* row_out) {
+  const int t0 = c * a.chunk;
+  const int t1 = min(a.N, t0 + a.chunk);
+  OscState<NA, SP> st;
+  int k = t0 / a.U;
+  int r = t0 - k * a.U;
+  bool steady;
+  int amp_mode;
+  // prime: frame k lands in Fn/An, then advance shifts it down and loads k+1
+  load_next_frame<NA, SP, !ENDS_ONLY>(a, row, s0, k, lane, st);
+  advance_frame<NA, SP, !ENDS_ONLY>(a, row, s0, min(k + 1, a.F - 1), lane, st, steady, amp_mode);
+#pragma unroll
+  for (int q = 0; q < NA; ++q)
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      st.ph[q][s] = 0.f;
+      st.off[q][s] = 0.f;
+      const int h = lane + 32 * q;
+      if (!ENDS_ONLY && c > 0 && h < a.H)
+        st.off[q][s] = a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h];
+    }
+  float tf = (float)t0;
+  for (int t = t0; t < t1; t += kOscUnroll, r += kOscUnroll, tf += (float)kOscUnroll) {
+    if (r == a.U) {
+      r = 0;
+      ++k;
+      advance_frame<NA, SP, !ENDS_ONLY>(a, row, s0, min(k + 1, a.F - 1), lane, st, steady, amp_mode);
+    }
+    float y[kOscUnroll];
+#pragma unroll
+    for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
+    const float kf = (float)k;
+    const float* w = win + r;
+    if (ENDS_ONLY || amp_mode == kAmpSilent) {
+      if (steady) osc_group<NA, SP, true, kAmpSilent>(a, st, w, tf, kf, y);
+      else osc_group<NA, SP, false, kAmpSilent>(a, st, w, tf, kf, y);
+    } else {
+      if (steady) osc_group<NA, SP, true, kAmpLive>(a, st, w, tf, kf, y);
+      else osc_group<NA, SP, false, kAmpLive>(a, st, w, tf, kf, y);
+      const float v = transpose_reduce4(y, lane);
+      if (lane < kOscUnroll) row_out[t - t0 + lane] += v;
+    }
+  }
+  if (ENDS_ONLY) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        const int h = lane + 32 * q;
+        if (h < a.H)
+          a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h] =
+              floormod_two_pi(st.ph[q][s]);
+      }
+  }
+}
+
+template <int SP, bool ENDS_ONLY>
+__device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, int na, int row, int s0,
+                                                   int c, int lane, const float* win, float* row_out) {
+  switch (na) {
+    case 0: break;
+    case 1: osc_chunk<1, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
+    case 2: osc_chunk<2, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
+    case 3: osc_chunk<3, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
+    case 4: osc_chunk<4, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
+    default:
+      // more than 128 live partials: two passes over the chunk are not implemented here; the
+      // host routes H > 128 to the generic kernel
+      break;
+  }
+}
+
+// CTA = (chunk, clip, voice group).  Warps pull (voice, substring set) items from a shared
+// counter, so voices with few live partials do not leave their warp idle.
+template <int SP, bool ENDS_ONLY>
+__global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const AdditiveFastArgs fa) {
+  const AdditiveArgs& a = fa.a;
+  extern __shared__ float smem[];
+  float* win = smem;                                   // [2U]
+  float* rows = smem + ((2 * a.U + 31) & ~31);         // [n_warps][kMaxChunk]
+  __shared__ int next_item;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
+  const int c = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+
+  if (threadIdx.x == 0) next_item = n_warps;
+  if (!ENDS_ONLY) {
+    for (int i = threadIdx.x; i < 2 * a.U; i += n_threads) win[i] = a.window[i];
+    for (int i = threadIdx.x; i < n_warps * kMaxChunk; i += n_threads) rows[i] = 0.f;
+  }
+  __syncthreads();
+
+  const int v_begin = g * a.voices_per_group;
+  const int v_end = min(a.P, v_begin + a.voices_per_group);
+  const int sets = a.S / SP;
+  const int n_items = (v_end - v_begin) * sets;
+  const unsigned char* na_tab = ENDS_ONLY ? fa.ends_na : fa.synth_na;
+
+  int item = warp;
+  while (item < n_items) {
+    const int v = v_begin + item / sets;
+    const int s0 = (item - (item / sets) * sets) * SP;
+    const int row = v * a.B + b;
+    const int na = na_tab[(size_t)row * a.n_chunks + c];
+    osc_chunk_dispatch<SP, ENDS_ONLY>(a, na, row, s0, c, lane, win, rows + warp * kMaxChunk);
+    if (ENDS_ONLY) {
+      // groups that are skipped still get a defined (zero) end phase
+      for (int q = na; q * 32 < a.H; ++q) {
+        const int h = lane + 32 * q;
+        if (h < a.H)
+          for (int s = 0; s < SP; ++s)
+            a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h] = 0.f;
+      }
+    }
+    if (lane == 0) item = atomicAdd(&next_item, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+  }
+
+  if (!ENDS_ONLY) {
+    __syncthreads();
+    const int t0 = c * a.chunk;
+    const int len = min(a.N, t0 + a.chunk) - t0;
+    float* out = a.out + ((size_t)g * a.B + b) * a.N + t0;
+    for (int i = threadIdx.x; i < len; i += n_threads) {
+      float acc = rows[i];
+      for (int w = 1; w < n_warps; ++w) acc += rows[w * kMaxChunk + i];
+      if (a.accumulate) acc += out[i];
+      out[i] = acc;
+    }
+  }
+}
+
+}  // namespace b200ddsp

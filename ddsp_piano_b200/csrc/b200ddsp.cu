@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "additive.cuh"
+#include "additive_fast.cuh"
 #include "common.cuh"
 #include "controls.cuh"
 #include "noise.cuh"
@@ -307,8 +308,25 @@ static int voice_groups_for(int P, int B, int n_chunks) {
   return G < P ? G : P;
 }
 
+// Scratch of the additive synth: chunk offsets + liveness tables.
+struct AdditiveScratch {
+  size_t offsets, na_frame, synth_na, ends_na, total;
+};
+
+static AdditiveScratch carve_additive(size_t R, int F, int H, int S, int n_chunks) {
+  AdditiveScratch a{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
+  a.offsets = take(R * S * n_chunks * H * 4);
+  a.na_frame = take(R * F);
+  a.synth_na = take(R * n_chunks);
+  a.ends_na = take(R * n_chunks);
+  a.total = o;
+  return a;
+}
+
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, mags, offsets, partials, tw, buf_a, buf_b, total;
+  size_t amp, hd, shifts, f0, mags, additive, partials, tw, buf_a, buf_b, total;
   int G, n_chunks, nfft;
 };
 
@@ -326,7 +344,7 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
     w.f0 = take(R * F * S * 4);
     w.mags = take(R * F * (size_t)M * 4);
   }
-  w.offsets = take(R * S * w.n_chunks * H * 4);
+  w.additive = take(carve_additive(R, F, H, S, w.n_chunks).total);
   w.partials = take((size_t)w.G * B * N * 4);
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
@@ -342,6 +360,12 @@ extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int 
                                            int S, int M, int L) {
   if (!h || P < 1 || B < 1 || F < 1) return 0;
   return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 0 ? M : 0, L, h->U, true).total;
+}
+
+extern "C" size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H,
+                                                    int S) {
+  if (!h || B < 1 || F < 1 || H < 1 || S < 1) return 0;
+  return carve_additive((size_t)B, F, H, S, n_chunks_for(F * h->U)).total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -397,77 +421,122 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
 }
 
 template <int HP>
-static void launch_additive_hp(const AdditiveArgs& a, bool fast, bool ends_only, dim3 grid,
-                               int threads, size_t smem, cudaStream_t st) {
-  if (fast) {
-    if (ends_only) additive_kernel<HP, 8, true, true><<<grid, threads, 0, st>>>(a);
-    else additive_kernel<HP, 8, true, false><<<grid, threads, smem, st>>>(a);
-  } else {
-    if (ends_only) additive_kernel<HP, 1, false, true><<<grid, threads, 0, st>>>(a);
-    else additive_kernel<HP, 1, false, false><<<grid, threads, smem, st>>>(a);
-  }
+static void launch_additive_hp(const AdditiveArgs& a, bool ends_only, dim3 grid, int threads,
+                               size_t smem, cudaStream_t st) {
+  if (ends_only) additive_kernel<HP, 1, false, true><<<grid, threads, 0, st>>>(a);
+  else additive_kernel<HP, 1, false, false><<<grid, threads, smem, st>>>(a);
 }
 
-static void launch_additive(const AdditiveArgs& a, int HP, bool fast, bool ends_only, dim3 grid,
-                            int threads, size_t smem, cudaStream_t st) {
+// generic path (any U, per-sample lerp frame, IEEE division)
+static void launch_additive_generic(const AdditiveArgs& a, int HP, bool ends_only, dim3 grid,
+                                    int threads, size_t smem, cudaStream_t st) {
   switch (HP) {
-    case 1: launch_additive_hp<1>(a, fast, ends_only, grid, threads, smem, st); break;
-    case 2: launch_additive_hp<2>(a, fast, ends_only, grid, threads, smem, st); break;
-    case 3: launch_additive_hp<3>(a, fast, ends_only, grid, threads, smem, st); break;
-    case 4: launch_additive_hp<4>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 1: launch_additive_hp<1>(a, ends_only, grid, threads, smem, st); break;
+    case 2: launch_additive_hp<2>(a, ends_only, grid, threads, smem, st); break;
+    case 3: launch_additive_hp<3>(a, ends_only, grid, threads, smem, st); break;
+    case 4: launch_additive_hp<4>(a, ends_only, grid, threads, smem, st); break;
     case 5:
-    case 6: launch_additive_hp<6>(a, fast, ends_only, grid, threads, smem, st); break;
-    default: launch_additive_hp<8>(a, fast, ends_only, grid, threads, smem, st); break;
+    case 6: launch_additive_hp<6>(a, ends_only, grid, threads, smem, st); break;
+    default: launch_additive_hp<8>(a, ends_only, grid, threads, smem, st); break;
   }
 }
 
-// The three launches of the additive synth over stacked controls (R = P*B rows).
+static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, dim3 grid, int threads,
+                                 size_t smem, cudaStream_t st) {
+  if (fa.sp == 2) {
+    if (ends_only) additive_fast_kernel<2, true><<<grid, threads, 0, st>>>(fa);
+    else additive_fast_kernel<2, false><<<grid, threads, smem, st>>>(fa);
+  } else {
+    if (ends_only) additive_fast_kernel<1, true><<<grid, threads, 0, st>>>(fa);
+    else additive_fast_kernel<1, false><<<grid, threads, smem, st>>>(fa);
+  }
+}
+
+// The launches of the additive synth over stacked controls (R = P*B rows): [liveness scan,]
+// chunk end phases, offsets scan, oscillator bank.
 static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, const float* shifts,
-                        const float* f0, float* offsets, float* out, int P, int B, int F, int H,
+                        const float* f0, char* scratch, float* out, int P, int B, int F, int H,
                         int S, int G, int accumulate, cudaStream_t st) {
   const int U = h->U, N = F * U;
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  bool fast = h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && lerp_is_uniform(h, F, N, U);
-  if (!fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
+  const bool uniform = lerp_is_uniform(h, F, N, U);
+  const bool fast = h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && uniform && H <= 128;
+  if (!uniform && !lerp_is_supported(F, N, U))
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
                 F, N);
+  const int n_chunks = n_chunks_for(N);
+  const AdditiveScratch sc = carve_additive((size_t)P * B, F, H, S, n_chunks);
   AdditiveArgs a{};
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
-  a.offsets = offsets;
+  a.offsets = (float*)(scratch + sc.offsets);
   a.out = out;
   a.window = h->d_window;
   a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
   a.chunk = kAngularChunk;
-  a.n_chunks = n_chunks_for(N);
+  a.n_chunks = n_chunks;
   a.voices_per_group = (P + G - 1) / G;
   a.accumulate = (G == 1) ? accumulate : 0;
   a.scale = (float)F / (float)N;
   a.nyquist = (float)(h->cfg.sample_rate / 2.0);
   a.sr = (float)h->cfg.sample_rate;
   a.inv_sr = 1.0f / a.sr;
-  const int HP = (H + 31) / 32;
-  const int n_pairs = a.voices_per_group * S;
-  const int warps = n_pairs < kAddWarps ? n_pairs : kAddWarps;
   const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
   if (smem > 48 * 1024)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
-  if (a.n_chunks > 1) {
+
+  if (fast) {
+    AdditiveFastArgs fa{};
+    fa.a = a;
+    fa.synth_na = (unsigned char*)(scratch + sc.synth_na);
+    fa.ends_na = (unsigned char*)(scratch + sc.ends_na);
+    fa.sp = (S % 2 == 0) ? 2 : 1;
+    unsigned char* na_frame = (unsigned char*)(scratch + sc.na_frame);
+    const int R = P * B;
+    {
+      StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
+      additive_alive_frames_kernel<<<(R * F + 7) / 8, 256, 0, st>>>(amp, hd, na_frame, R * F, H);
+      CHECK_LAUNCH(h, "additive_alive_frames_kernel");
+      additive_alive_chunks_kernel<<<(R + 127) / 128, 128, 0, st>>>(
+          na_frame, (unsigned char*)(scratch + sc.synth_na), (unsigned char*)(scratch + sc.ends_na), R,
+          F, U, N, a.chunk, n_chunks);
+      CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
+    }
+    const int n_items = a.voices_per_group * (S / fa.sp);
+    const int warps = n_items < kAddWarps ? n_items : kAddWarps;
+    if (n_chunks > 1) {
+      {
+        StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
+        launch_additive_fast(fa, true, dim3(n_chunks - 1, B, G), warps * 32, 0, st);
+        CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
+      }
+      const int n = P * B * S * H;
+      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, P * B * S, n_chunks, H);
+      CHECK_LAUNCH(h, "additive_offsets_kernel");
+    }
+    StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
+    launch_additive_fast(fa, false, dim3(n_chunks, B, G), warps * 32, smem, st);
+    CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
+    return B200DDSP_OK;
+  }
+
+  const int HP = (H + 31) / 32;
+  const int n_pairs = a.voices_per_group * S;
+  const int warps = n_pairs < kAddWarps ? n_pairs : kAddWarps;
+  if (n_chunks > 1) {
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
-      dim3 grid(a.n_chunks - 1, B, G);
-      launch_additive(a, HP, fast, true, grid, warps * 32, 0, st);
+      launch_additive_generic(a, HP, true, dim3(n_chunks - 1, B, G), warps * 32, 0, st);
       CHECK_LAUNCH(h, "additive_kernel<ends>");
     }
     StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
     const int n = P * B * S * H;
-    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(offsets, P * B * S, a.n_chunks, H);
+    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, P * B * S, n_chunks, H);
     CHECK_LAUNCH(h, "additive_offsets_kernel");
   }
   StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
-  dim3 grid(a.n_chunks, B, G);
-  launch_additive(a, HP, fast, false, grid, warps * 32, smem, st);
+  launch_additive_generic(a, HP, false, dim3(n_chunks, B, G), warps * 32, smem, st);
   CHECK_LAUNCH(h, "additive_kernel<synth>");
   return B200DDSP_OK;
 }
@@ -480,14 +549,16 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
   if (int rc = check_common(h, B, F)) return rc;
   if (!amplitudes || !harmonic_distribution || !harmonic_shifts || !f0_hz || !out)
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
   const int n_chunks = n_chunks_for(F * h->U);
-  const size_t need = (size_t)B * S * n_chunks * H * 4;
-  if (n_chunks > 1 && (!workspace || workspace_bytes < need))
+  const size_t need = carve_additive((size_t)B, F, H, S, n_chunks).total;
+  if (!workspace || workspace_bytes < need)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "additive_signal needs %zu workspace bytes, got %zu",
                 need, workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
   return run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
-                      (float*)workspace, out, 1, B, F, H, S, 1, accumulate, (cudaStream_t)stream);
+                      (char*)workspace, out, 1, B, F, H, S, 1, accumulate, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -722,7 +793,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   }
   }
   // additive oscillator bank -> G partial sums
-  if (int rc = run_additive(h, amp, hd, shifts, f0, (float*)(base + w.offsets),
+  if (int rc = run_additive(h, amp, hd, shifts, f0, base + w.additive,
                             (float*)(base + w.partials), P, B, F, H, S, w.G, 0, st))
     return rc;
   // noise of every voice + mix -> dry  (outputs['add']['signal'])

@@ -141,8 +141,7 @@ class Engine:
                              f'{tuple(shifts.shape)}, {tuple(f0_hz.shape)}')
         N = F * self.upsampling
         out = torch.empty([B, N], dtype=torch.float32, device=self.device)
-        n_chunks = -(-N // 1000)
-        ws = self.workspace(B * S * n_chunks * H * 4)
+        ws = self.workspace(self.lib.b200ddsp_additive_workspace_bytes(self.handle, B, F, H, S))
         with torch.cuda.device(self.device):
             self.check(self.lib.b200ddsp_additive_signal(
                 self.handle, amplitudes.data_ptr(), hd.data_ptr(), shifts.data_ptr(),

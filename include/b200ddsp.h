@@ -109,6 +109,9 @@ int b200ddsp_destroy(b200ddsp_handle* h);
 size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H, int S,
                                 int M, int L);
 
+/* Scratch bytes of b200ddsp_additive_signal alone (chunk offsets + liveness tables). */
+size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H, int S);
+
 /* MultiInharmonic.get_controls -- modules/inharm_synth.py:254-270 over :167-219.
  * rows = B (or P*B for a stacked [P,B,...] tensor).  f0_hz is passed through unchanged by
  * the reference, so it has no output.  Outputs: amplitudes [rows,F,1],

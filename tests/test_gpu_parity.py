@@ -105,8 +105,13 @@ def test_additive_golden(dp, dev, golden_dir, name):
 @pytest.mark.parametrize('sr,F,B,H,S', [(24000, 250, 2, 96, 2),     # 24 chunks, BASELINE shapes
                                         (16000, 190, 1, 96, 2),     # dafx22 shapes, N % 1000 != 0
                                         (48000, 60, 1, 128, 2),
-                                        (32000, 40, 2, 192, 1),
-                                        (8000, 130, 3, 48, 3)])
+                                        (32000, 40, 2, 192, 1),     # H > 128: generic kernel
+                                        (8000, 130, 3, 48, 3),
+                                        (25000, 45, 1, 64, 2),      # U = 100: generic kernel (U % 8 != 0)
+                                        (82000, 30, 1, 40, 2),      # U = 328: float(1/U) rounds down,
+                                                                    # lerp frame != amplitude frame
+                                        (24000, 84, 2, 128, 1),     # 4 partial groups, odd S
+                                        (24000, 42, 1, 20, 4)])
 def test_additive_vs_oracle(dp, dev, sr, F, B, H, S):
     rng = np.random.default_rng(sr + F)
     x = voice_inputs(rng, B, F, H, S, 8)
