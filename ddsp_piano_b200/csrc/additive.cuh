@@ -258,18 +258,38 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
 }
 
 // Chunk end phases -> chunk offsets, in place (ddsp angular_cumsum: shift down one chunk,
-// cumsum over chunks in float32, then mod 2pi).  One thread per (row, substring, partial).
-__global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets, int n_osc_rows,
-                                                                int n_chunks, int H) {
+// cumsum over chunks in float32, then mod 2pi).  One thread per (row, substring, partial); the
+// loads of a batch of chunks are issued together so that the loop is not one L2 round trip per
+// chunk.  ends_na (optional): groups >= ends_na[row, c] were not computed for chunk c and count
+// as 0 (no later chunk reads their offset).
+__global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets,
+                                                                const unsigned char* ends_na,
+                                                                int n_osc_rows, int n_chunks, int H,
+                                                                int S) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_osc_rows * H) return;
   const int rs = i / H, h = i - rs * H;
+  const int group = h >> 5;
+  const unsigned char* na = ends_na ? ends_na + (size_t)(rs / S) * n_chunks : nullptr;
   float* p = offsets + (size_t)rs * n_chunks * H + h;
   float cum = 0.f;
-  for (int c = 0; c < n_chunks; ++c) {
-    const float e = (c < n_chunks - 1) ? p[(size_t)c * H] : 0.f;
-    p[(size_t)c * H] = floormod_two_pi(cum);
-    cum = __fadd_rn(cum, e);
+  constexpr int kBatch = 8;
+  for (int c0 = 0; c0 < n_chunks; c0 += kBatch) {
+    float e[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int c = c0 + j;
+      const bool have = (c < n_chunks - 1) && (na == nullptr || group < (int)na[c]);
+      e[j] = have ? p[(size_t)c * H] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int c = c0 + j;
+      if (c < n_chunks) {
+        p[(size_t)c * H] = floormod_two_pi(cum);
+        cum = __fadd_rn(cum, e[j]);
+      }
+    }
   }
 }
 

@@ -27,10 +27,12 @@
 
 namespace b200ddsp {
 
+struct AdditivePlan;
+
 struct AdditiveFastArgs {
-  AdditiveArgs a;
-  const unsigned char* synth_na;   // [R, n_chunks] live partial groups per (row, chunk)
-  const unsigned char* ends_na;    // [R, n_chunks] groups whose end phase a later chunk needs
+  AdditiveArgs a;                  // a.out: [P * sets, B, N] partial signals
+  AdditivePlan* plan;              // bucket counts + work counters
+  const int* lists;                // [2][kMaxGroups][R * n_chunks] units by bucket
   int sp;                          // substrings per pass (1 or 2)
 };
 
@@ -56,24 +58,36 @@ __global__ void __launch_bounds__(256) additive_alive_frames_kernel(
 
 // synth_na[row, c] = max na_frame over the frames chunk c reads (frames of its samples plus the
 // next one: the amplitude envelope cross-fades towards frame k+1); ends_na[row, c] = max
-// synth_na over chunks > c.  One thread per row (n_chunks is small).
+// synth_na over chunks > c (a group's chunk-end phase matters only if a later chunk sounds).
+// One CTA per row; shared memory holds the row's synth_na.
 __global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
     const unsigned char* __restrict__ na_frame, unsigned char* __restrict__ synth_na,
-    unsigned char* __restrict__ ends_na, int R, int F, int U, int N, int chunk, int n_chunks) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= R) return;
+    unsigned char* __restrict__ ends_na, int F, int U, int N, int chunk, int n_chunks) {
+  extern __shared__ unsigned char sna[];   // [n_chunks]
+  const int row = blockIdx.x;
   const unsigned char* nf = na_frame + (size_t)row * F;
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
     const int t0 = c * chunk, t1 = min(N, t0 + chunk) - 1;
     const int k0 = t0 / U, k1 = min(F - 1, t1 / U + 1);
     int m = 0;
     for (int k = k0; k <= k1; ++k) m = max(m, (int)nf[k]);
+    sna[c] = (unsigned char)m;
     synth_na[(size_t)row * n_chunks + c] = (unsigned char)m;
   }
+  __syncthreads();
+  // suffix maximum: each thread owns a contiguous span, spans are stitched through shared memory
+  __shared__ int span_max[128];
+  const int per = (n_chunks + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * per, hi = min(n_chunks, lo + per);
+  int m = 0;
+  for (int c = lo; c < hi; ++c) m = max(m, (int)sna[c]);
+  span_max[threadIdx.x] = m;
+  __syncthreads();
   int later = 0;
-  for (int c = n_chunks - 1; c >= 0; --c) {
+  for (int j = threadIdx.x + 1; j < (int)blockDim.x; ++j) later = max(later, span_max[j]);
+  for (int c = hi - 1; c >= lo; --c) {
     ends_na[(size_t)row * n_chunks + c] = (unsigned char)later;
-    later = max(later, (int)synth_na[(size_t)row * n_chunks + c]);
+    later = max(later, (int)sna[c]);
   }
 }
 
@@ -150,6 +164,14 @@ template <int NA, int SP, bool STEADY, int AMP>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
                                           const float* win, float tf, float kf,
                                           float (&y)[kOscUnroll]) {
+  static_assert(kOscUnroll == 4, "window loads are float4");
+  float wr[4] = {0.f, 0.f, 0.f, 0.f}, wf[4] = {0.f, 0.f, 0.f, 0.f};
+  if (AMP != kAmpSilent) {   // r and U are multiples of 8: both loads are 16-byte aligned
+    const float4 r4 = *reinterpret_cast<const float4*>(win);
+    const float4 f4 = *reinterpret_cast<const float4*>(win + a.U);
+    wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
+    wf[0] = f4.x; wf[1] = f4.y; wf[2] = f4.z; wf[3] = f4.w;
+  }
   // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
   bool cut[NA][SP];
   if (STEADY && AMP != kAmpSilent) {
@@ -167,8 +189,8 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
     }
     float w0 = 0.f, w1 = 0.f;
     if (AMP != kAmpSilent) {
-      w0 = win[j];          // rising half of hann(2U): weight of frame k+1
-      w1 = win[j + a.U];    // falling half: weight of frame k
+      w0 = wr[j];          // rising half of hann(2U): weight of frame k+1
+      w1 = wf[j];          // falling half: weight of frame k
     }
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
@@ -215,7 +237,7 @@ __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
 }
 
 // One (row, substring set, chunk) on one warp.  ENDS_ONLY: phase chain only, writes the chunk
-// end phases; otherwise accumulates the audio of the chunk into `row_out` (shared memory).
+// end phases; otherwise writes the audio of the chunk to `row_out` (global memory).
 template <int NA, int SP, bool ENDS_ONLY>
 __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0, int c, int lane,
                                           const float* win, float* row_out) {
@@ -254,11 +276,12 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
     if (ENDS_ONLY || amp_mode == kAmpSilent) {
       if (steady) osc_group<NA, SP, true, kAmpSilent>(a, st, w, tf, kf, y);
       else osc_group<NA, SP, false, kAmpSilent>(a, st, w, tf, kf, y);
+      if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
     } else {
       if (steady) osc_group<NA, SP, true, kAmpLive>(a, st, w, tf, kf, y);
       else osc_group<NA, SP, false, kAmpLive>(a, st, w, tf, kf, y);
       const float v = transpose_reduce4(y, lane);
-      if (lane < kOscUnroll) row_out[t - t0 + lane] += v;
+      if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
     }
   }
   if (ENDS_ONLY) {
@@ -290,65 +313,109 @@ __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, int na
   }
 }
 
-// CTA = (chunk, clip, voice group).  Warps pull (voice, substring set) items from a shared
-// counter, so voices with few live partials do not leave their warp idle.
+// ---- work lists ------------------------------------------------------------------------------
+// The unit of work is one (row, chunk) = 1000 samples of one voice of one clip; its cost is
+// proportional to the number of live partial groups.  additive_plan_kernel buckets the units by
+// that number so that the persistent kernels below can hand them out heaviest first (longest
+// processing time first: the tail of the launch is made of the cheapest units).
+constexpr int kMaxGroups = 4;     // H <= 128 on the fast path
+
+struct AdditivePlan {
+  int count[2][kMaxGroups];   // [synth | ends][na - 1]  number of units in the bucket
+  int next[2];                // work counters of the two persistent kernels
+  // zeroed by cudaMemsetAsync before every plan
+};
+
+__global__ void __launch_bounds__(256) additive_plan_kernel(
+    const unsigned char* __restrict__ synth_na, const unsigned char* __restrict__ ends_na,
+    AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks) {
+  // lists: [2][kMaxGroups][n_units]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  const int c = i % n_chunks;
+  const int ns = synth_na[i];
+  if (ns > 0) {
+    const int pos = atomicAdd(&plan->count[0][ns - 1], 1);
+    lists[(size_t)(0 * kMaxGroups + ns - 1) * n_units + pos] = i;
+  }
+  const int ne = ends_na[i];
+  if (ne > 0 && c < n_chunks - 1) {
+    const int pos = atomicAdd(&plan->count[1][ne - 1], 1);
+    lists[(size_t)(1 * kMaxGroups + ne - 1) * n_units + pos] = i;
+  }
+}
+
+// Persistent kernel: every warp pulls (unit, substring set) items from a global counter until
+// the lists are exhausted.  No block-level synchronisation after the Hann table is staged, so
+// a warp that drew cheap items simply draws more of them.  Each item writes its own region of
+// `out` ([P * sets, B, N] partial signals, summed in a fixed order by the mixer), which keeps the
+// result independent of the scheduling order.
 template <int SP, bool ENDS_ONLY>
 __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [2U]
-  float* rows = smem + ((2 * a.U + 31) & ~31);         // [n_warps][kMaxChunk]
-  __shared__ int next_item;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
-  const int c = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
-
-  if (threadIdx.x == 0) next_item = n_warps;
   if (!ENDS_ONLY) {
-    for (int i = threadIdx.x; i < 2 * a.U; i += n_threads) win[i] = a.window[i];
-    for (int i = threadIdx.x; i < n_warps * kMaxChunk; i += n_threads) rows[i] = 0.f;
-  }
-  __syncthreads();
-
-  const int v_begin = g * a.voices_per_group;
-  const int v_end = min(a.P, v_begin + a.voices_per_group);
-  const int sets = a.S / SP;
-  const int n_items = (v_end - v_begin) * sets;
-  const unsigned char* na_tab = ENDS_ONLY ? fa.ends_na : fa.synth_na;
-
-  int item = warp;
-  while (item < n_items) {
-    const int v = v_begin + item / sets;
-    const int s0 = (item - (item / sets) * sets) * SP;
-    const int row = v * a.B + b;
-    const int na = na_tab[(size_t)row * a.n_chunks + c];
-    osc_chunk_dispatch<SP, ENDS_ONLY>(a, na, row, s0, c, lane, win, rows + warp * kMaxChunk);
-    if (ENDS_ONLY) {
-      // groups that are skipped still get a defined (zero) end phase
-      for (int q = na; q * 32 < a.H; ++q) {
-        const int h = lane + 32 * q;
-        if (h < a.H)
-          for (int s = 0; s < SP; ++s)
-            a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h] = 0.f;
-      }
-    }
-    if (lane == 0) item = atomicAdd(&next_item, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-  }
-
-  if (!ENDS_ONLY) {
+    for (int i = threadIdx.x; i < 2 * a.U; i += blockDim.x) win[i] = a.window[i];
     __syncthreads();
-    const int t0 = c * a.chunk;
-    const int len = min(a.N, t0 + a.chunk) - t0;
-    float* out = a.out + ((size_t)g * a.B + b) * a.N + t0;
-    for (int i = threadIdx.x; i < len; i += n_threads) {
-      float acc = rows[i];
-      for (int w = 1; w < n_warps; ++w) acc += rows[w * kMaxChunk + i];
-      if (a.accumulate) acc += out[i];
-      out[i] = acc;
+  }
+  const int kind = ENDS_ONLY ? 1 : 0;
+  const int sets = a.S / SP;
+  const int n_units = a.P * a.B * a.n_chunks;
+  int bucket_end[kMaxGroups];   // cumulative item counts, heaviest bucket first
+  {
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxGroups; ++i) {
+      acc += fa.plan->count[kind][kMaxGroups - 1 - i] * sets;
+      bucket_end[i] = acc;
     }
   }
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&fa.plan->next[kind], 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= bucket_end[kMaxGroups - 1]) break;
+    int bi = 0, begin = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxGroups - 1; ++i)
+      if (item >= bucket_end[i]) { bi = i + 1; begin = bucket_end[i]; }
+    const int na = kMaxGroups - bi;
+    const int local = item - begin;
+    const int unit = fa.lists[(size_t)(kind * kMaxGroups + na - 1) * n_units + local / sets];
+    const int set = local - (local / sets) * sets;
+    const int row = unit / a.n_chunks;
+    const int c = unit - row * a.n_chunks;
+    const int v = row / a.B, b = row - v * a.B;
+    float* out = ENDS_ONLY ? nullptr
+                           : a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
+    osc_chunk_dispatch<SP, ENDS_ONLY>(a, na, row, set * SP, c, lane, win, out);
+  }
+}
+
+// out[b, t] (+)= sum over partial signals p of partials[p, b, t], skipping (voice, chunk) units
+// that were never written because nothing sounds there (live == nullptr: all written).
+struct PartialSumArgs {
+  const float* partials;          // [n_partials, B, N]
+  const unsigned char* live;      // [P * B, n_chunks] synth_na, or nullptr
+  float* out;                     // [B, N]
+  int n_partials, sets, B, N, chunk, n_chunks, accumulate;
+};
+
+__global__ void __launch_bounds__(256) additive_sum_partials_kernel(const PartialSumArgs s) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= s.N) return;
+  const int c = t / s.chunk;
+  float acc = 0.f;
+  for (int p = 0; p < s.n_partials; ++p) {
+    const int v = p / s.sets;
+    if (s.live == nullptr || s.live[((size_t)v * s.B + b) * s.n_chunks + c] != 0)
+      acc += s.partials[((size_t)p * s.B + b) * s.N + t];
+  }
+  float* o = s.out + (size_t)b * s.N + t;
+  *o = s.accumulate ? (*o + acc) : acc;
 }
 
 }  // namespace b200ddsp

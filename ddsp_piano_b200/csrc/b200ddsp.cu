@@ -28,6 +28,7 @@ struct b200ddsp_handle {
   b200ddsp_config cfg;
   int U = 0;
   int device = 0;
+  int n_sms = 148;
   float* d_window = nullptr;   // hann(2U)
   float* d_cmat_t = nullptr;   // [M][M-1] noise IR matrix
   bool fast_div = false;       // 3-op division == IEEE division for this sample rate
@@ -226,6 +227,7 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   if (!h) return fail(nullptr, B200DDSP_CUDA_ERROR, "out of host memory");
   h->cfg = *cfg;
   h->device = dev;
+  h->n_sms = prop.multiProcessorCount;
   h->U = (int)((double)cfg->sample_rate / (double)cfg->frame_rate);   // inharm_synth.py:163-165
   h->fast_div = verify_fast_division((float)cfg->sample_rate);
 
@@ -308,25 +310,38 @@ static int voice_groups_for(int P, int B, int n_chunks) {
   return G < P ? G : P;
 }
 
-// Scratch of the additive synth: chunk offsets + liveness tables.
+// Scratch of the additive synth: chunk offsets, liveness tables, work lists, partial signals.
 struct AdditiveScratch {
-  size_t offsets, na_frame, synth_na, ends_na, total;
+  size_t offsets, na_frame, synth_na, ends_na, plan, lists, partials, total;
+  int n_partials;   // partial signals [n_partials, B, N] the mixer has to sum
+  int sets;         // substring sets per voice on the fast path (1 on the generic path)
 };
 
-static AdditiveScratch carve_additive(size_t R, int F, int H, int S, int n_chunks) {
+static int substrings_per_pass(int S) { return (S % 2 == 0) ? 2 : 1; }
+
+// P voices x B clips.  `fast` selects the layout of the partial signals: one per (voice, set) on
+// the fast path, one per voice group on the generic path.
+static AdditiveScratch carve_additive(int P, int B, int F, int H, int S, int U, bool fast, int G) {
   AdditiveScratch a{};
+  const size_t R = (size_t)P * B, N = (size_t)F * U;
+  const int n_chunks = (int)((N + kAngularChunk - 1) / kAngularChunk);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
   a.offsets = take(R * S * n_chunks * H * 4);
   a.na_frame = take(R * F);
   a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
+  a.plan = take(sizeof(AdditivePlan));
+  a.lists = take((size_t)2 * kMaxGroups * R * n_chunks * 4);
+  a.sets = fast ? S / substrings_per_pass(S) : 1;
+  a.n_partials = fast ? P * a.sets : G;
+  a.partials = take((size_t)a.n_partials * B * N * 4);
   a.total = o;
   return a;
 }
 
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, mags, additive, partials, tw, buf_a, buf_b, total;
+  size_t amp, hd, shifts, f0, mags, additive, tw, buf_a, buf_b, total;
   int G, n_chunks, nfft;
 };
 
@@ -344,8 +359,13 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
     w.f0 = take(R * F * S * 4);
     w.mags = take(R * F * (size_t)M * 4);
   }
-  w.additive = take(carve_additive(R, F, H, S, w.n_chunks).total);
-  w.partials = take((size_t)w.G * B * N * 4);
+  // sized for whichever additive path the shapes select at run time (the fast path's
+  // per-voice partial signals are the larger layout)
+  {
+    const size_t fast_b = carve_additive(P, B, F, H, S, U, true, w.G).total;
+    const size_t gen_b = carve_additive(P, B, F, H, S, U, false, w.G).total;
+    w.additive = take(fast_b > gen_b ? fast_b : gen_b);
+  }
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
     w.tw = take((size_t)w.nfft * 8);
@@ -365,7 +385,9 @@ extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int 
 extern "C" size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H,
                                                     int S) {
   if (!h || B < 1 || F < 1 || H < 1 || S < 1) return 0;
-  return carve_additive((size_t)B, F, H, S, n_chunks_for(F * h->U)).total;
+  const size_t fast_b = carve_additive(1, B, F, H, S, h->U, true, 1).total;
+  const size_t gen_b = carve_additive(1, B, F, H, S, h->U, false, 1).total;
+  return fast_b > gen_b ? fast_b : gen_b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,6 +428,7 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
   a.hd_out = harmonic_distribution_out;
   a.shifts_out = harmonic_shifts_out;
   a.f0_out = nullptr;
+  a.na_frame = nullptr;
   a.n_frames_voice = rows * F;
   a.H = H;
   a.S = S;
@@ -452,75 +475,113 @@ static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, dim
   }
 }
 
-// The launches of the additive synth over stacked controls (R = P*B rows): [liveness scan,]
-// chunk end phases, offsets scan, oscillator bank.
+static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
+  const int U = h->U;
+  return h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && H <= 32 * kMaxGroups &&
+         lerp_is_uniform(h, F, F * U, U);
+}
+
+struct AdditiveResult {
+  const float* partials;        // [n_partials, B, N]
+  const unsigned char* live;    // [P*B, n_chunks] or nullptr
+  int n_partials, sets;
+};
+
+// The launches of the additive synth over stacked controls (R = P*B rows): liveness scan + work
+// lists (fast path), chunk end phases, offsets scan, oscillator bank.  The result is a set of
+// partial signals in `scratch` for the mixer to sum.  na_frame_ready: the controls kernel has
+// already written the per-frame liveness.
 static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, const float* shifts,
-                        const float* f0, char* scratch, float* out, int P, int B, int F, int H,
-                        int S, int G, int accumulate, cudaStream_t st) {
+                        const float* f0, char* scratch, int P, int B, int F, int H, int S, int G,
+                        bool na_frame_ready, AdditiveResult* res, cudaStream_t st) {
   const int U = h->U, N = F * U;
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  const bool uniform = lerp_is_uniform(h, F, N, U);
-  const bool fast = h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && uniform && H <= 128;
-  if (!uniform && !lerp_is_supported(F, N, U))
+  const bool fast = additive_fast_path(h, F, H);
+  if (!fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
                 F, N);
   const int n_chunks = n_chunks_for(N);
-  const AdditiveScratch sc = carve_additive((size_t)P * B, F, H, S, n_chunks);
+  const AdditiveScratch sc = carve_additive(P, B, F, H, S, U, fast, G);
   AdditiveArgs a{};
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
   a.offsets = (float*)(scratch + sc.offsets);
-  a.out = out;
+  a.out = (float*)(scratch + sc.partials);
   a.window = h->d_window;
   a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
   a.chunk = kAngularChunk;
   a.n_chunks = n_chunks;
   a.voices_per_group = (P + G - 1) / G;
-  a.accumulate = (G == 1) ? accumulate : 0;
+  a.accumulate = 0;
   a.scale = (float)F / (float)N;
   a.nyquist = (float)(h->cfg.sample_rate / 2.0);
   a.sr = (float)h->cfg.sample_rate;
   a.inv_sr = 1.0f / a.sr;
-  const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
-  if (smem > 48 * 1024)
-    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
+  res->partials = a.out;
+  res->n_partials = sc.n_partials;
+  res->sets = sc.sets;
+  res->live = nullptr;
 
   if (fast) {
+    const int R = P * B;
+    unsigned char* na_frame = (unsigned char*)(scratch + sc.na_frame);
+    unsigned char* synth_na = (unsigned char*)(scratch + sc.synth_na);
+    unsigned char* ends_na = (unsigned char*)(scratch + sc.ends_na);
+    AdditivePlan* plan = (AdditivePlan*)(scratch + sc.plan);
+    int* lists = (int*)(scratch + sc.lists);
+    res->live = synth_na;
     AdditiveFastArgs fa{};
     fa.a = a;
-    fa.synth_na = (unsigned char*)(scratch + sc.synth_na);
-    fa.ends_na = (unsigned char*)(scratch + sc.ends_na);
-    fa.sp = (S % 2 == 0) ? 2 : 1;
-    unsigned char* na_frame = (unsigned char*)(scratch + sc.na_frame);
-    const int R = P * B;
+    fa.plan = plan;
+    fa.lists = lists;
+    fa.sp = substrings_per_pass(S);
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
-      additive_alive_frames_kernel<<<(R * F + 7) / 8, 256, 0, st>>>(amp, hd, na_frame, R * F, H);
-      CHECK_LAUNCH(h, "additive_alive_frames_kernel");
-      additive_alive_chunks_kernel<<<(R + 127) / 128, 128, 0, st>>>(
-          na_frame, (unsigned char*)(scratch + sc.synth_na), (unsigned char*)(scratch + sc.ends_na), R,
-          F, U, N, a.chunk, n_chunks);
+      if (!na_frame_ready) {
+        additive_alive_frames_kernel<<<(R * F + 7) / 8, 256, 0, st>>>(amp, hd, na_frame, R * F, H);
+        CHECK_LAUNCH(h, "additive_alive_frames_kernel");
+      }
+      if (n_chunks > 12 * 1024)
+        return fail(h, B200DDSP_BAD_SHAPE, "timeline of %d chunks is too long for one call", n_chunks);
+      additive_alive_chunks_kernel<<<R, 128, (size_t)n_chunks, st>>>(na_frame, synth_na, ends_na, F, U,
+                                                                    N, a.chunk, n_chunks);
       CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
+      CUDA_TRY(h, cudaMemsetAsync(plan, 0, sizeof(AdditivePlan), st));
+      const int n_units = R * n_chunks;
+      additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(synth_na, ends_na, plan, lists,
+                                                                 n_units, n_chunks);
+      CHECK_LAUNCH(h, "additive_plan_kernel");
     }
-    const int n_items = a.voices_per_group * (S / fa.sp);
-    const int warps = n_items < kAddWarps ? n_items : kAddWarps;
+    // persistent grids: every warp pulls work until the lists are empty
+    const long long max_items = (long long)R * n_chunks * sc.sets;
+    const int sms = h->n_sms;
+    auto grid_for = [&](int ctas_per_sm) {
+      long long want = (max_items + kAddWarps - 1) / kAddWarps;
+      long long cap = (long long)sms * ctas_per_sm;
+      return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    };
+    const size_t smem = (size_t)(2 * U) * sizeof(float);
     if (n_chunks > 1) {
       {
         StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
-        launch_additive_fast(fa, true, dim3(n_chunks - 1, B, G), warps * 32, 0, st);
+        launch_additive_fast(fa, true, dim3(grid_for(4)), kAddThreads, 0, st);
         CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
       }
-      const int n = P * B * S * H;
-      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, P * B * S, n_chunks, H);
+      StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
+      const int n = R * S * H;
+      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, ends_na, R * S, n_chunks, H, S);
       CHECK_LAUNCH(h, "additive_offsets_kernel");
     }
     StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
-    launch_additive_fast(fa, false, dim3(n_chunks, B, G), warps * 32, smem, st);
+    launch_additive_fast(fa, false, dim3(grid_for(2)), kAddThreads, smem, st);
     CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
     return B200DDSP_OK;
   }
 
+  const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
+  if (smem > 48 * 1024)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
   const int HP = (H + 31) / 32;
   const int n_pairs = a.voices_per_group * S;
   const int warps = n_pairs < kAddWarps ? n_pairs : kAddWarps;
@@ -532,7 +593,7 @@ static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, c
     }
     StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
     const int n = P * B * S * H;
-    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, P * B * S, n_chunks, H);
+    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, nullptr, P * B * S, n_chunks, H, S);
     CHECK_LAUNCH(h, "additive_offsets_kernel");
   }
   StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
@@ -551,14 +612,31 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  const int n_chunks = n_chunks_for(F * h->U);
-  const size_t need = carve_additive((size_t)B, F, H, S, n_chunks).total;
+  const size_t need = b200ddsp_additive_workspace_bytes(h, B, F, H, S);
   if (!workspace || workspace_bytes < need)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "additive_signal needs %zu workspace bytes, got %zu",
                 need, workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
-  return run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
-                      (char*)workspace, out, 1, B, F, H, S, 1, accumulate, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  reset_stage_flags(h);
+  AdditiveResult res{};
+  if (int rc = run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
+                            (char*)workspace, 1, B, F, H, S, 1, false, &res, st))
+    return rc;
+  PartialSumArgs ps{};
+  ps.partials = res.partials;
+  ps.live = res.live;
+  ps.out = out;
+  ps.n_partials = res.n_partials;
+  ps.sets = res.sets;
+  ps.B = B;
+  ps.N = F * h->U;
+  ps.chunk = kAngularChunk;
+  ps.n_chunks = n_chunks_for(ps.N);
+  ps.accumulate = accumulate;
+  additive_sum_partials_kernel<<<dim3((ps.N + 255) / 256, B), 256, 0, st>>>(ps);
+  CHECK_LAUNCH(h, "additive_sum_partials_kernel");
+  return B200DDSP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,8 +655,8 @@ extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitud
   return B200DDSP_OK;
 }
 
-static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const float* partials,
-                     int n_partials, float* out, int B, int F, int M, int accumulate,
+static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const AdditiveResult* mix,
+                     float* out, int B, int F, int M, int accumulate,
                      unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
   const int U = h->U;
   if (M != h->cfg.n_noise_bands || !h->d_cmat_t)
@@ -588,8 +666,12 @@ static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const 
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth needs U %% 8 == 0 (U=%d)", U);
   NoiseArgs a{};
   a.cmat_t = h->d_cmat_t;
-  a.partials = partials;
-  a.n_partials = n_partials;
+  a.partials = mix ? mix->partials : nullptr;
+  a.live = mix ? mix->live : nullptr;
+  a.n_partials = mix ? mix->n_partials : 0;
+  a.sets = mix ? mix->sets : 1;
+  a.chunk = kAngularChunk;
+  a.n_chunks = n_chunks_for(F * U);
   a.out = out;
   a.accumulate = accumulate;
   a.P = P; a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
@@ -618,7 +700,7 @@ extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes
   NoiseVoicePtrs vp{};
   vp.mags[0] = magnitudes;
   vp.noise[0] = noise;
-  return run_noise(h, vp, 1, nullptr, 0, out, B, F, M, accumulate, seed, stream_id,
+  return run_noise(h, vp, 1, nullptr, out, B, F, M, accumulate, seed, stream_id,
                    (cudaStream_t)stream);
 }
 
@@ -752,6 +834,10 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   float* f0 = (float*)(base + w.f0);
   float* mags = (float*)(base + w.mags);
 
+  // per-frame liveness of the partial groups comes out of the controls kernel on the fast path
+  unsigned char* na_frame = nullptr;
+  if (additive_fast_path(h, F, H))
+    na_frame = (unsigned char*)(base + w.additive + carve_additive(P, B, F, H, S, U, true, w.G).na_frame);
   // get_controls of every voice (additive: stacked [P*B, F, .]; noise: scale_fn(m + bias))
   AdditiveControlsPtrs cp{};
   NoiseVoicePtrs vp{};
@@ -771,6 +857,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
     AdditiveControlsArgs a{};
     a.amp_out = amp; a.hd_out = hd; a.shifts_out = shifts; a.f0_out = f0;
+    a.na_frame = na_frame;
     a.n_frames_voice = B * F;
     a.H = H; a.S = S;
     a.nyquist = (float)(h->cfg.sample_rate / 2.0);
@@ -793,12 +880,12 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   }
   }
   // additive oscillator bank -> G partial sums
-  if (int rc = run_additive(h, amp, hd, shifts, f0, base + w.additive,
-                            (float*)(base + w.partials), P, B, F, H, S, w.G, 0, st))
+  AdditiveResult mix{};
+  if (int rc = run_additive(h, amp, hd, shifts, f0, base + w.additive, P, B, F, H, S, w.G,
+                            na_frame != nullptr, &mix, st))
     return rc;
   // noise of every voice + mix -> dry  (outputs['add']['signal'])
-  if (int rc = run_noise(h, vp, P, (const float*)(base + w.partials), w.G, dry_out, B, F, M, 0, seed,
-                         0, st))
+  if (int rc = run_noise(h, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, st))
     return rc;
   // reverb -> wet
   if (reverb_ir)

@@ -17,6 +17,7 @@ struct AdditiveControlsArgs {
   float* hd_out;           // [P*B, F, H]
   float* shifts_out;       // [P*B, F, H]
   float* f0_out;           // [P*B, F, S] copy (get_controls returns f0_hz unchanged), or nullptr
+  unsigned char* na_frame; // [P*B, F] 1 + highest live 32-partial group (additive_fast.cuh), or nullptr
   int n_frames_voice;      // B * F
   int H, S;
   float nyquist, min_frequency;
@@ -79,12 +80,21 @@ __global__ void __launch_bounds__(256) additive_controls_kernel(const AdditiveCo
 #pragma unroll
     for (int j = 0; j < kMaxHarmonicsPerLane; ++j) d[j] = __fdiv_rn(d[j], den);
   }
+  int na = 0;
 #pragma unroll
   for (int j = 0; j < kMaxHarmonicsPerLane; ++j) {
     const int h = lane + 32 * j;
     if (h < a.H) a.hd_out[(size_t)rf * a.H + h] = d[j];
+    if (a.na_frame != nullptr && j * 32 < a.H) {
+      const bool live = (h < a.H) && (d[j] != 0.f);
+      if (__ballot_sync(0xffffffffu, live)) na = j + 1;
+    }
   }
-  if (lane == 0) a.amp_out[rf] = __fdiv_rn(amp, (float)a.S);         // :269
+  const float amp_final = __fdiv_rn(amp, (float)a.S);                // :269
+  if (lane == 0) {
+    a.amp_out[rf] = amp_final;
+    if (a.na_frame != nullptr) a.na_frame[rf] = (unsigned char)(amp_final != 0.f ? na : 0);
+  }
 }
 
 // FilteredNoise.get_controls: scale_fn(magnitudes + initial_bias).

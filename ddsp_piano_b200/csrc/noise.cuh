@@ -34,9 +34,11 @@ struct NoiseVoicePtrs {
 
 struct NoiseArgs {
   const float* cmat_t;   // [M][M-1]: cmat_t[j*(M-1) + d] -> tap M-1+d (and its mirror M-1-d)
-  const float* partials; // [G, B, N] additive partial sums to mix in, or nullptr
+  const float* partials; // [n_partials, B, N] additive partial signals to mix in, or nullptr
+  const unsigned char* live;   // [P * B, n_chunks]: partial p = (voice p / sets) is only defined
+                               // where live != 0 (additive fast path), or nullptr
   float* out;            // [B, N]
-  int n_partials;
+  int n_partials, sets, chunk, n_chunks;
   int accumulate;        // out += result
   int P, B, F, M, U, N;
   int halo_before, halo_after;   // input halo in FRAMES either side of the tile
@@ -235,8 +237,11 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArg
   float* out = a.out + (size_t)b * a.N + t_tile;
   for (int i = threadIdx.x; i < len; i += kNoiseThreads) {
     float acc = os[(i / U) * L.pitch_o + (i % U)];
-    for (int gidx = 0; gidx < a.n_partials; ++gidx)
-      acc += a.partials[((size_t)gidx * a.B + b) * a.N + t_tile + i];
+    const int c = (t_tile + i) / a.chunk;
+    for (int p = 0; p < a.n_partials; ++p) {
+      if (a.live == nullptr || a.live[((size_t)(p / a.sets) * a.B + b) * a.n_chunks + c] != 0)
+        acc += a.partials[((size_t)p * a.B + b) * a.N + t_tile + i];
+    }
     if (a.accumulate) acc += out[i];
     out[i] = acc;
   }
