@@ -104,7 +104,9 @@ def load():
     lib.b200ddsp_noise_controls.restype = ci
     lib.b200ddsp_noise_controls.argtypes = [vp, vp, vp, sz, vp]
     lib.b200ddsp_noise_signal.restype = ci
-    lib.b200ddsp_noise_signal.argtypes = [vp, vp, vp, u64, u64, vp, ci, ci, ci, ci, vp]
+    lib.b200ddsp_noise_signal.argtypes = [vp, vp, vp, u64, u64, vp, ci, ci, ci, ci, vp, sz, vp]
+    lib.b200ddsp_noise_workspace_bytes.restype = sz
+    lib.b200ddsp_noise_workspace_bytes.argtypes = [vp, ci, ci, ci]
     lib.b200ddsp_reverb.restype = ci
     lib.b200ddsp_reverb.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_forward_polyphonic.restype = ci
@@ -123,7 +125,7 @@ def load():
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
-           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_reverb',
+           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb',
            'b200ddsp_forward_polyphonic', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
 STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise_mix', 'reverb']

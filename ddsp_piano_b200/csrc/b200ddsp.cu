@@ -301,6 +301,8 @@ static int fft_size_for(int N, int L) {
   return n;
 }
 
+static int tap_pitch_for(int M) { return (M - 1 + 3) & ~3; }
+
 static int n_chunks_for(int N) { return (N + kAngularChunk - 1) / kAngularChunk; }
 
 // Voice groups: split the voices over gridDim.z until the grid fills the GPU.
@@ -341,7 +343,7 @@ static AdditiveScratch carve_additive(int P, int B, int F, int H, int S, int U, 
 }
 
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, mags, additive, tw, buf_a, buf_b, total;
+  size_t amp, hd, shifts, f0, taps, additive, tw, buf_a, buf_b, total;
   int G, n_chunks, nfft;
 };
 
@@ -357,7 +359,7 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
     w.hd = take(R * F * H * 4);
     w.shifts = take(R * F * H * 4);
     w.f0 = take(R * F * S * 4);
-    w.mags = take(R * F * (size_t)M * 4);
+    w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
   }
   // sized for whichever additive path the shapes select at run time (the fast path's
   // per-voice partial signals are the larger layout)
@@ -655,17 +657,37 @@ extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitud
   return B200DDSP_OK;
 }
 
-static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const AdditiveResult* mix,
-                     float* out, int B, int F, int M, int accumulate,
-                     unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
+// taps GEMM (+ fused get_controls scaling when scale_fn != 2) then FIR + mix.
+static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn,
+                     const NoiseVoicePtrs& vp, int P, const AdditiveResult* mix, float* out, int B,
+                     int F, int M, int accumulate, unsigned long long seed,
+                     unsigned long long stream_id, float* taps, cudaStream_t st) {
   const int U = h->U;
   if (M != h->cfg.n_noise_bands || !h->d_cmat_t)
     return fail(h, B200DDSP_BAD_SHAPE, "M=%d but the handle was created for n_noise_bands=%d", M,
                 h->cfg.n_noise_bands);
   if (U % 8 != 0)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth needs U %% 8 == 0 (U=%d)", U);
+  if (U > 8 * 4 * 16)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth supports U <= 512 (U=%d)", U);
+  StageTimer tm(h, B200DDSP_STAGE_NOISE_MIX, st);
+  const int tap_pitch = tap_pitch_for(M);
+  {
+    NoiseTapsArgs t{};
+    t.cmat_t = h->d_cmat_t;
+    t.taps = taps;
+    t.mags_out = nullptr;
+    t.frames_per_voice = B * F;
+    t.M = M;
+    t.tap_pitch = tap_pitch;
+    t.scale_fn = scale_fn;
+    t.bias = h->cfg.noise_initial_bias;
+    dim3 grid((B * F + kTapsTileF - 1) / kTapsTileF, (M - 1 + kTapsTileD - 1) / kTapsTileD, P);
+    noise_taps_kernel<<<grid, 256, 0, st>>>(t, mags);
+    CHECK_LAUNCH(h, "noise_taps_kernel");
+  }
   NoiseArgs a{};
-  a.cmat_t = h->d_cmat_t;
+  a.taps = taps;
   a.partials = mix ? mix->partials : nullptr;
   a.live = mix ? mix->live : nullptr;
   a.n_partials = mix ? mix->n_partials : 0;
@@ -675,6 +697,7 @@ static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const 
   a.out = out;
   a.accumulate = accumulate;
   a.P = P; a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
+  a.tap_pitch = tap_pitch;
   a.halo_before = (M + U - 1) / U;
   a.halo_after = (U + M - 5) / U;
   a.seed = seed;
@@ -683,25 +706,54 @@ static int run_noise(b200ddsp_handle* h, const NoiseVoicePtrs& vp, int P, const 
   const size_t smem = (size_t)L.total_floats * sizeof(float);
   if (smem > 227 * 1024)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
-  CUDA_TRY(h, cudaFuncSetAttribute(noise_fir_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-  StageTimer tm(h, B200DDSP_STAGE_NOISE_MIX, st);
+  // warps split the U/8 blocks of a frame; NB blocks per thread
+  const int n_blocks = U / 8;
+  int warps = n_blocks <= 16 ? 4 : (n_blocks <= 32 ? 8 : 16);
+  if (warps > n_blocks) warps = n_blocks;
+  const int nb = (n_blocks + warps - 1) / warps;
   dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B);
-  noise_fir_kernel<0><<<grid, kNoiseThreads, smem, st>>>(a, vp);
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, warps * 32, smem, st>>>(a, vp);
+    return cudaSuccess;
+  };
+  cudaError_t e = cudaSuccess;
+  switch (nb) {
+    case 1: e = launch(noise_fir_kernel<1>); break;
+    case 2: e = launch(noise_fir_kernel<2>); break;
+    case 3: e = launch(noise_fir_kernel<3>); break;
+    default: e = launch(noise_fir_kernel<4>); break;
+  }
+  if (e != cudaSuccess)
+    return fail(h, B200DDSP_CUDA_ERROR, "noise_fir_kernel attribute: %s", cudaGetErrorString(e));
   CHECK_LAUNCH(h, "noise_fir_kernel");
   return B200DDSP_OK;
 }
 
+extern "C" size_t b200ddsp_noise_workspace_bytes(const b200ddsp_handle* h, int B, int F, int M) {
+  if (!h || B < 1 || F < 1 || M < 2) return 0;
+  return align_up((size_t)B * F * tap_pitch_for(M) * 4);
+}
+
 extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
                                      uint64_t seed, uint64_t stream_id, float* out, int B, int F,
-                                     int M, int accumulate, void* stream) {
+                                     int M, int accumulate, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   if (int rc = check_common(h, B, F)) return rc;
   if (!magnitudes || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  const size_t need = b200ddsp_noise_workspace_bytes(h, B, F, M);
+  if (!workspace || workspace_bytes < need)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "noise_signal needs %zu workspace bytes, got %zu", need,
+                workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  NoiseTapsPtrs mp{};
+  mp.mags[0] = magnitudes;
   NoiseVoicePtrs vp{};
-  vp.mags[0] = magnitudes;
   vp.noise[0] = noise;
-  return run_noise(h, vp, 1, nullptr, out, B, F, M, accumulate, seed, stream_id,
-                   (cudaStream_t)stream);
+  reset_stage_flags(h);
+  return run_noise(h, mp, B200DDSP_SCALE_NONE, vp, 1, nullptr, out, B, F, M, accumulate, seed, stream_id,
+                   (float*)workspace, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -832,7 +884,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   float* hd = (float*)(base + w.hd);
   float* shifts = (float*)(base + w.shifts);
   float* f0 = (float*)(base + w.f0);
-  float* mags = (float*)(base + w.mags);
+  float* taps = (float*)(base + w.taps);
 
   // per-frame liveness of the partial groups comes out of the controls kernel on the fast path
   unsigned char* na_frame = nullptr;
@@ -841,6 +893,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   // get_controls of every voice (additive: stacked [P*B, F, .]; noise: scale_fn(m + bias))
   AdditiveControlsPtrs cp{};
   NoiseVoicePtrs vp{};
+  NoiseTapsPtrs mp{};
   for (int v = 0; v < P; ++v) {
     const b200ddsp_voice& vc = voices[v];
     if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
@@ -849,7 +902,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     cp.hd_in[v] = vc.harmonic_distribution;
     cp.inharm_in[v] = vc.inharm_coef;
     cp.f0_in[v] = vc.f0_hz;
-    vp.mags[v] = mags + (size_t)v * B * F * M;
+    mp.mags[v] = vc.magnitudes;
     vp.noise[v] = vc.noise;
   }
   reset_stage_flags(h);
@@ -868,16 +921,6 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     dim3 grid((a.n_frames_voice + 7) / 8, P);
     additive_controls_kernel<<<grid, 256, 0, st>>>(a, cp);
     CHECK_LAUNCH(h, "additive_controls_kernel");
-  for (int v = 0; v < P; ++v) {
-    // contiguous stacked parents ([P,B,F,M], sub_modules.py:589-596) collapse into one launch
-    int run = 1;
-    while (v + run < P && voices[v + run].magnitudes == voices[v].magnitudes + (size_t)run * B * F * M)
-      ++run;
-    if (int rc = b200ddsp_noise_controls(h, voices[v].magnitudes, mags + (size_t)v * B * F * M,
-                                         (size_t)run * B * F * M, stream))
-      return rc;
-    v += run - 1;
-  }
   }
   // additive oscillator bank -> G partial sums
   AdditiveResult mix{};
@@ -885,7 +928,8 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
                             na_frame != nullptr, &mix, st))
     return rc;
   // noise of every voice + mix -> dry  (outputs['add']['signal'])
-  if (int rc = run_noise(h, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, st))
+  // FilteredNoise.get_controls is fused into the taps GEMM's operand load
+  if (int rc = run_noise(h, mp, h->cfg.noise_scale_fn, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, taps, st))
     return rc;
   // reverb -> wet
   if (reverb_ir)

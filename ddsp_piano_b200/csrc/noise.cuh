@@ -7,40 +7,123 @@
 // overlap-adds at hop U; the result is cropped at start = (Lir-1)/2 - 1.  In the time domain
 //   z[n] = sum_{m=1}^{Lir-1} x[n-m] * c_{frame(n-m)}[m],     noise_out[t] = z[t + start].
 // With Lir = 126 (190 at M = 96) taps the direct form costs fewer flops than three FFTs per
-// frame, needs no transposes, and is exact, so that is what runs here:
-//   stage 1  c_k = Cmat x m_k      (inverse real DFT + window as a [M-1 x M] matrix applied to
-//                                   34 frames at a time; Cmat is built once in create())
-//   stage 2  FIR, register tiled: a thread owns 8 consecutive outputs of one frame and slides
-//            an 8-tap register window over the taps: 2 shared loads per 8 FMAs.
-// CTA = (tile of 32 output frames, clip).  Lanes are FRAMES (odd shared-memory pitches make the
-// frame-strided accesses conflict free), warps split the 8-sample blocks of a frame.  The CTA
-// loops over the voices, accumulates their noise in a shared output tile and finally adds
-// the additive partial sums: it is also the MultiAdd mixer (inharm_synth.py:296-309).
+// frame, needs no transposes, and is exact, so that is what runs here, in two kernels:
+//
+//  noise_taps_kernel   c_k = Cmat x scale_fn(m_k + bias): the inverse real DFT and the window
+//                      folded into one [M x M-1] matrix (built once in create()); the filter is
+//                      symmetric about tap M-1 so only taps M-1 .. 2M-3 are computed and
+//                      stored.  A register-tiled FP32 GEMM over all frames of all voices; the
+//                      magnitudes' get_controls scaling is fused into the operand load.
+//  noise_fir_kernel    CTA = (tile of 32 output frames, clip); it loops over the voices, so the
+//                      MultiAdd node (inharm_synth.py:296-309) is register accumulation, and
+//                      finally adds the additive partial signals: it is also the mixer.  Lanes
+//                      are FRAMES (odd shared-memory pitches make the frame-strided accesses
+//                      conflict free); a thread owns 8 consecutive outputs of its frame per
+//                      block and slides a 15-tap register window over the taps:
+//                      16 shared loads per 64 FMAs.
 #pragma once
 #include "common.cuh"
 
 namespace b200ddsp {
 
+// ---- taps GEMM ------------------------------------------------------------------------------
+constexpr int kTapsTileF = 64;   // frames per CTA
+constexpr int kTapsTileD = 64;   // taps per CTA
+constexpr int kTapsTileK = 32;   // bands per shared-memory stage
+
+struct NoiseTapsPtrs {
+  const float* mags[B200DDSP_MAX_VOICES_INTERNAL];   // [B, F, M] raw or scaled magnitudes per voice
+};
+
+struct NoiseTapsArgs {
+  const float* cmat_t;   // [M][M-1]
+  float* taps;           // [P*B*F][tap_pitch]: taps M-1 .. 2M-3 of every frame
+  float* mags_out;       // [P*B*F][M] scaled magnitudes (get_controls output) or nullptr
+  int frames_per_voice;  // B * F
+  int M, tap_pitch;
+  int scale_fn;          // b200ddsp_scale_fn to apply on load; 2 = magnitudes are already scaled
+  float bias;
+};
+
+__global__ void __launch_bounds__(256) noise_taps_kernel(const NoiseTapsArgs a,
+                                                         const NoiseTapsPtrs vp) {
+  __shared__ float As[kTapsTileF][kTapsTileK + 1];
+  __shared__ __align__(16) float Cs[kTapsTileK][kTapsTileD];
+  const int v = blockIdx.z;
+  const int f0 = blockIdx.x * kTapsTileF;   // frame within the voice
+  const int d0 = blockIdx.y * kTapsTileD;
+  const int nd = a.M - 1;
+  const int tid = threadIdx.x;
+  const int tf = tid >> 4, td = tid & 15;   // 16 x 16 threads, 4 x 4 outputs each
+  const float* mags = vp.mags[v];
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < a.M; k0 += kTapsTileK) {
+    // A tile: 64 frames x 32 bands, scaled on the way in
+    for (int i = tid; i < kTapsTileF * kTapsTileK; i += 256) {
+      const int fr = i / kTapsTileK, kk = i - fr * kTapsTileK;
+      const int f = f0 + fr, k = k0 + kk;
+      float x = 0.f;
+      if (f < a.frames_per_voice && k < a.M) {
+        x = __ldg(mags + (size_t)f * a.M + k);
+        if (a.scale_fn != 2) x = apply_scale_fn(__fadd_rn(x, a.bias), a.scale_fn);
+        if (a.mags_out != nullptr && blockIdx.y == 0)
+          a.mags_out[((size_t)v * a.frames_per_voice + f) * a.M + k] = x;
+      }
+      As[fr][kk] = x;
+    }
+    for (int i = tid; i < kTapsTileK * kTapsTileD; i += 256) {
+      const int kk = i / kTapsTileD, dd = i - kk * kTapsTileD;
+      const int k = k0 + kk, d = d0 + dd;
+      Cs[kk][dd] = (k < a.M && d < nd) ? __ldg(a.cmat_t + (size_t)k * nd + d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kTapsTileK; ++kk) {
+      const float4 c4 = *reinterpret_cast<const float4*>(&Cs[kk][td * 4]);
+      const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av = As[tf * 4 + i][kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av, cv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = f0 + tf * 4 + i;
+    if (f >= a.frames_per_voice) continue;
+    float* dst = a.taps + ((size_t)v * a.frames_per_voice + f) * a.tap_pitch + d0 + td * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d0 + td * 4 + j < a.tap_pitch) dst[j] = acc[i][j];
+  }
+}
+
+// ---- FIR + mix ------------------------------------------------------------------------------
 constexpr int kNoiseFrames = 32;   // output frames per CTA (= lanes)
-constexpr int kNoiseWarps = 4;
-constexpr int kNoiseThreads = kNoiseWarps * kWarp;
 constexpr int kTapPad = 16;        // zero taps either side of c_k (8-aligned input blocks + the
                                    // 15-tap register window overhang by up to 13 taps)
 
 struct NoiseVoicePtrs {
-  const float* mags[B200DDSP_MAX_VOICES_INTERNAL];    // [B, F, M] scaled magnitudes
   const float* noise[B200DDSP_MAX_VOICES_INTERNAL];   // [B, N] or nullptr (Philox)
 };
 
 struct NoiseArgs {
-  const float* cmat_t;   // [M][M-1]: cmat_t[j*(M-1) + d] -> tap M-1+d (and its mirror M-1-d)
+  const float* taps;     // [P*B*F][tap_pitch] from noise_taps_kernel
   const float* partials; // [n_partials, B, N] additive partial signals to mix in, or nullptr
   const unsigned char* live;   // [P * B, n_chunks]: partial p = (voice p / sets) is only defined
                                // where live != 0 (additive fast path), or nullptr
   float* out;            // [B, N]
   int n_partials, sets, chunk, n_chunks;
   int accumulate;        // out += result
-  int P, B, F, M, U, N;
+  int P, B, F, M, U, N, tap_pitch;
   int halo_before, halo_after;   // input halo in FRAMES either side of the tile
   unsigned long long seed, stream_id;
 };
@@ -49,21 +132,15 @@ struct NoiseSmemLayout {
   int n_in;       // input frames held: kNoiseFrames + halo_before + halo_after
   int pitch_x;    // U | 1
   int pitch_c;    // (Lir + 2*kTapPad) | 1
-  int pitch_m;    // frames rounded up to 4, +4 (float4 broadcast loads)
-  int pitch_o;    // U | 1
-  int off_x, off_c, off_m, off_out, total_floats;
+  int off_x, off_c, total_floats;
   __host__ __device__ NoiseSmemLayout(int M, int U, int hb, int ha) {
     const int lir = 2 * (M - 1);
     n_in = kNoiseFrames + hb + ha;
     pitch_x = U | 1;
     pitch_c = (lir + 2 * kTapPad) | 1;
-    pitch_m = ((n_in + 3) & ~3) + 4;
-    pitch_o = U | 1;
     off_x = 0;
     off_c = (off_x + n_in * pitch_x + 3) & ~3;
-    off_m = (off_c + n_in * pitch_c + 3) & ~3;
-    off_out = (off_m + M * pitch_m + 3) & ~3;
-    total_floats = off_out + kNoiseFrames * pitch_o;
+    total_floats = off_c + n_in * pitch_c;
   }
 };
 
@@ -88,16 +165,15 @@ __device__ __forceinline__ float uniform_pm1(unsigned int bits) {
   return __fmaf_rn(u, 2.0f, -1.0f);
 }
 
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArgs a,
-                                                                 const NoiseVoicePtrs vp) {
+// NB = 8-sample blocks per thread: blocks warp, warp + W, ... of the thread's frame.
+template <int NB>
+__global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
   extern __shared__ __align__(16) float smem[];
   const NoiseSmemLayout L(a.M, a.U, a.halo_before, a.halo_after);
   float* xs = smem + L.off_x;     // [n_in][pitch_x]  noise samples by input frame
   float* cs = smem + L.off_c;     // [n_in][pitch_c]  zero-padded taps by input frame
-  float* ms = smem + L.off_m;     // [M][pitch_m]     magnitudes, band-major
-  float* os = smem + L.off_out;   // [kNoiseFrames][pitch_o] output tile
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
   const int b = blockIdx.y;
   const int f_tile = blockIdx.x * kNoiseFrames;        // first output frame
   const int k_first = f_tile - a.halo_before;          // first input frame held (may be < 0)
@@ -105,31 +181,38 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArg
   const int start = (lir - 1) / 2 - 1;                 // crop_and_compensate_delay
   const int n_blocks = U / 8;
 
-  for (int i = threadIdx.x; i < kNoiseFrames * L.pitch_o; i += kNoiseThreads) os[i] = 0.f;
+  float acc[NB][8];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
   // taps outside [1, Lir-1] stay zero for the whole kernel
-  for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += kNoiseThreads) cs[i] = 0.f;
+  for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += n_threads) cs[i] = 0.f;
 
   for (int v = 0; v < a.P; ++v) {
-    __syncthreads();   // previous voice's FIR is done with xs/cs/ms
-    // ---- stage 0: stage this voice's magnitudes and noise for the held input frames ------
-    const float* mags = vp.mags[v] + (size_t)b * a.F * M;
-    for (int i = threadIdx.x; i < L.n_in * M; i += kNoiseThreads) {
-      const int fi = i / M, j = i - fi * M;
+    __syncthreads();   // previous voice's FIR is done with xs/cs (and the zero fill is visible)
+    // ---- stage this voice's taps and noise for the held input frames ----------------------
+    const float* taps = a.taps + ((size_t)v * a.B + b) * a.F * a.tap_pitch;
+    for (int i = threadIdx.x; i < L.n_in * (M - 1); i += n_threads) {
+      const int fi = i / (M - 1), d = i - fi * (M - 1);
       const int k = k_first + fi;
-      ms[j * L.pitch_m + fi] = (k >= 0 && k < a.F) ? __ldg(mags + (size_t)k * M + j) : 0.f;
+      const float c = (k >= 0 && k < a.F) ? __ldg(taps + (size_t)k * a.tap_pitch + d) : 0.f;
+      float* row = cs + fi * L.pitch_c + kTapPad;
+      row[M - 1 + d] = c;
+      if (d > 0) row[M - 1 - d] = c;                   // linear phase: symmetric about tap M-1
     }
     const float* nz = vp.noise[v];
     if (nz != nullptr) {
       nz += (size_t)b * a.N;
-      for (int i = threadIdx.x; i < L.n_in * U; i += kNoiseThreads) {
+      for (int i = threadIdx.x; i < L.n_in * U; i += n_threads) {
         const int fi = i / U, j = i - fi * U;
         const int k = k_first + fi;
         xs[fi * L.pitch_x + j] = (k >= 0 && k < a.F) ? __ldg(nz + (size_t)k * U + j) : 0.f;
       }
     } else {
-      // counter = (sample index / 4, clip, voice, stream), key = seed
+      // counter = (sample index / 4, clip, voice + stream, stream >> 32), key = seed
       const uint2 key = make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32));
-      for (int i = threadIdx.x; i < L.n_in * U / 4; i += kNoiseThreads) {
+      for (int i = threadIdx.x; i < L.n_in * U / 4; i += n_threads) {
         const int fi = (i * 4) / U, j = i * 4 - fi * U;
         const int k = k_first + fi;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -147,50 +230,15 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArg
     }
     __syncthreads();
 
-    // ---- stage 1: taps c_k = Cmat x m_k for every held frame ------------------------------
-    // thread = (tap d, group of 4 frames); Cmat row read coalesced through L1, magnitudes as
-    // one float4 shared broadcast.
-    {
-      const int n_fg = (L.n_in + 3) / 4;
-      const int n_d = M - 1;
-      for (int w = threadIdx.x; w < n_d * n_fg; w += kNoiseThreads) {
-        const int fg = w / n_d, d = w - fg * n_d;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* cm = a.cmat_t + d;
-        const float* mrow = ms + fg * 4;
-#pragma unroll 4
-        for (int j = 0; j < M; ++j) {
-          const float cj = __ldg(cm + (size_t)j * n_d);
-          const float4 m4 = *reinterpret_cast<const float4*>(mrow + j * L.pitch_m);
-          acc.x = __fmaf_rn(cj, m4.x, acc.x);
-          acc.y = __fmaf_rn(cj, m4.y, acc.y);
-          acc.z = __fmaf_rn(cj, m4.z, acc.z);
-          acc.w = __fmaf_rn(cj, m4.w, acc.w);
-        }
-        const float accs[4] = {acc.x, acc.y, acc.z, acc.w};
+    // ---- FIR.  lane = output frame, warp walks its 8-sample blocks -------------------------
+    const int fo = lane;                               // output frame within the tile
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int fi = fg * 4 + e;
-          if (fi < L.n_in) {
-            float* c = cs + fi * L.pitch_c + kTapPad;
-            c[M - 1 + d] = accs[e];
-            if (d > 0) c[M - 1 - d] = accs[e];     // linear phase: symmetric about M-1
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- stage 2: FIR.  lane = output frame, warp walks 8-sample blocks -------------------
-    {
-      const int fo = lane;                               // output frame within the tile
-      for (int blk = warp; blk < n_blocks; blk += kNoiseWarps) {
+    for (int ib = 0; ib < NB; ++ib) {
+      const int blk = warp + ib * n_warps;
+      if (blk < n_blocks) {
         const int i0 = blk * 8;
-        float acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-        // z index of output q: n = (f*U + i0 + q) + start; input e = i0 + q + start - m relative
-        // to the start of output frame f, m in [1, Lir-1].
+        // z index of output q: n = (f*U + i0 + q) + start; input offset e = i0 + q + start - m
+        // relative to the start of output frame f, m in [1, Lir-1].
         const int e_hi = i0 + 7 + start - 1;             // largest input offset used
         const int e_lo = i0 + start - (lir - 1);         // smallest
         const int d_lo = (e_lo >= 0) ? e_lo / U : -((-e_lo + U - 1) / U);
@@ -212,7 +260,7 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArg
             for (int u = 0; u < 8; ++u) {
               const float xv = xrow[j + u];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] = __fmaf_rn(xv, w[7 - u + q], acc[q]);
+              for (int q = 0; q < 8; ++q) acc[ib][q] = __fmaf_rn(xv, w[7 - u + q], acc[ib][q]);
             }
             m0 -= 8;
             if (j + 8 <= j_hi) {
@@ -223,27 +271,34 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_fir_kernel(const NoiseArg
             }
           }
         }
-        float* o = os + fo * L.pitch_o + i0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] += acc[q];
       }
     }
   }
   __syncthreads();
 
-  // ---- mix: additive partial sums + noise tile -> out ------------------------------------
+  // ---- mix: noise (through shared memory, for coalescing) + additive partial signals -> out ---
+  float* os = xs;   // [kNoiseFrames][pitch_x], reuses the noise tile
+#pragma unroll
+  for (int ib = 0; ib < NB; ++ib) {
+    const int blk = warp + ib * n_warps;
+    if (blk < n_blocks) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) os[lane * L.pitch_x + blk * 8 + q] = acc[ib][q];
+    }
+  }
+  __syncthreads();
   const int t_tile = f_tile * U;
   const int len = min(kNoiseFrames * U, a.N - t_tile);
   float* out = a.out + (size_t)b * a.N + t_tile;
-  for (int i = threadIdx.x; i < len; i += kNoiseThreads) {
-    float acc = os[(i / U) * L.pitch_o + (i % U)];
+  for (int i = threadIdx.x; i < len; i += n_threads) {
+    float sum = os[(i / U) * L.pitch_x + (i % U)];
     const int c = (t_tile + i) / a.chunk;
     for (int p = 0; p < a.n_partials; ++p) {
       if (a.live == nullptr || a.live[((size_t)(p / a.sets) * a.B + b) * a.n_chunks + c] != 0)
-        acc += a.partials[((size_t)p * a.B + b) * a.N + t_tile + i];
+        sum += a.partials[((size_t)p * a.B + b) * a.N + t_tile + i];
     }
-    if (a.accumulate) acc += out[i];
-    out[i] = acc;
+    if (a.accumulate) sum += out[i];
+    out[i] = sum;
   }
 }
 

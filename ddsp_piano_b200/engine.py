@@ -167,10 +167,12 @@ class Engine:
             if tuple(noise.shape) != (B, N):
                 raise ValueError(f'noise has shape {tuple(noise.shape)}, expected {(B, N)}')
         out = torch.empty([B, N], dtype=torch.float32, device=self.device)
+        ws = self.workspace(self.lib.b200ddsp_noise_workspace_bytes(self.handle, B, F, M))
         with torch.cuda.device(self.device):
             self.check(self.lib.b200ddsp_noise_signal(
                 self.handle, magnitudes.data_ptr(), noise.data_ptr() if noise is not None else None,
-                seed, stream_id, out.data_ptr(), B, F, M, 0, self.stream()))
+                seed, stream_id, out.data_ptr(), B, F, M, 0, ws.data_ptr(), ws.numel(),
+                self.stream()))
         return out
 
     def reverb(self, audio, ir):

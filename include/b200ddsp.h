@@ -142,7 +142,9 @@ int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitudes, float* 
  * keyed by (seed, stream_id)).  out [B,N], added to when accumulate != 0. */
 int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
                           uint64_t seed, uint64_t stream_id, float* out, int B, int F, int M,
-                          int accumulate, void* stream);
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* Scratch bytes of b200ddsp_noise_signal (the per-frame FIR taps). */
+size_t b200ddsp_noise_workspace_bytes(const b200ddsp_handle* h, int B, int F, int M);
 
 /* ddsp.effects.Reverb.get_signal (configs/dafx22.gin:99-100,111; ir producer
  * modules/sub_modules.py:351-365): out = conv(audio, ir with ir[:,0]=0)[:, :N] (+ audio if
