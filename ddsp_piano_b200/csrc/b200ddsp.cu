@@ -407,6 +407,21 @@ static int check_common(b200ddsp_handle* h, int B, int F) {
   return B200DDSP_OK;
 }
 
+static void launch_additive_controls(const AdditiveControlsArgs& a, const AdditiveControlsPtrs& p,
+                                     int P, cudaStream_t st) {
+  const int warps_needed = (a.n_frames_voice + kFramesPerWarp - 1) / kFramesPerWarp;
+  dim3 grid((warps_needed + 7) / 8, P);
+  switch ((a.H + 31) / 32) {
+    case 1: additive_controls_kernel<1><<<grid, 256, 0, st>>>(a, p); break;
+    case 2: additive_controls_kernel<2><<<grid, 256, 0, st>>>(a, p); break;
+    case 3: additive_controls_kernel<3><<<grid, 256, 0, st>>>(a, p); break;
+    case 4: additive_controls_kernel<4><<<grid, 256, 0, st>>>(a, p); break;
+    case 5:
+    case 6: additive_controls_kernel<6><<<grid, 256, 0, st>>>(a, p); break;
+    default: additive_controls_kernel<8><<<grid, 256, 0, st>>>(a, p); break;
+  }
+}
+
 extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* amplitudes,
                                           const float* harmonic_distribution,
                                           const float* inharm_coef, const float* f0_hz,
@@ -439,8 +454,7 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
   a.scale_fn = h->cfg.additive_scale_fn;
   a.normalize_after = h->cfg.normalize_after_nyquist_cut;
   a.normalize_below = h->cfg.normalize_below_nyquist;
-  dim3 grid((a.n_frames_voice + 7) / 8, 1);
-  additive_controls_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, p);
+  launch_additive_controls(a, p, 1, (cudaStream_t)stream);
   CHECK_LAUNCH(h, "additive_controls_kernel");
   return B200DDSP_OK;
 }
@@ -708,9 +722,10 @@ static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
   // warps split the U/8 blocks of a frame; NB blocks per thread
   const int n_blocks = U / 8;
-  int warps = n_blocks <= 16 ? 4 : (n_blocks <= 32 ? 8 : 16);
-  if (warps > n_blocks) warps = n_blocks;
-  const int nb = (n_blocks + warps - 1) / warps;
+  // one block per thread up to 16 warps (the grid is only F/32 x B CTAs, so the CTA has to bring
+  // the parallelism), then 2..4 blocks per thread
+  int nb = (n_blocks + 15) / 16;
+  const int warps = (n_blocks + nb - 1) / nb;
   dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B);
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -918,8 +933,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
     a.scale_fn = h->cfg.additive_scale_fn;
     a.normalize_after = h->cfg.normalize_after_nyquist_cut;
     a.normalize_below = h->cfg.normalize_below_nyquist;
-    dim3 grid((a.n_frames_voice + 7) / 8, P);
-    additive_controls_kernel<<<grid, 256, 0, st>>>(a, cp);
+    launch_additive_controls(a, cp, P, st);
     CHECK_LAUNCH(h, "additive_controls_kernel");
   }
   // additive oscillator bank -> G partial sums
