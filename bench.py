@@ -279,13 +279,11 @@ def run_gpu(args, w):
         return group(features(resident), return_outputs_dict=False)
 
     h2d = sum(v.numel() * 4 for v in host.values())
-    out_host = torch.empty([B, N], dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        on_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        y = group(features(on_dev), return_outputs_dict=False)
-        out_host.copy_(y, non_blocking=True)
-        return y
+        # pinned HOST control tensors in, pinned HOST audio out: the ProcessorGroup routes CPU
+        # features to b200ddsp_forward_polyphonic_host (H2D + kernels + D2H on the timed stream)
+        return group(features(host), return_outputs_dict=False)
 
     def barrier():
         if world > 1:

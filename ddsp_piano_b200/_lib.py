@@ -112,6 +112,11 @@ def load():
     lib.b200ddsp_forward_polyphonic.restype = ci
     lib.b200ddsp_forward_polyphonic.argtypes = [vp, ctypes.POINTER(Voice), ci, vp, vp, vp,
                                                 ci, ci, ci, ci, ci, ci, u64, vp, sz, vp]
+    lib.b200ddsp_forward_polyphonic_host.restype = ci
+    lib.b200ddsp_forward_polyphonic_host.argtypes = [vp, ctypes.POINTER(Voice), ci, vp, vp, vp,
+                                                     ci, ci, ci, ci, ci, ci, u64, vp, sz, vp]
+    lib.b200ddsp_workspace_bytes_host.restype = sz
+    lib.b200ddsp_workspace_bytes_host.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci]
     lib.b200ddsp_launch_count.restype = u64
     lib.b200ddsp_launch_count.argtypes = [vp]
     lib.b200ddsp_set_profiling.restype = ci
@@ -126,6 +131,7 @@ EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200dd
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
            'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb',
-           'b200ddsp_forward_polyphonic', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
+           'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
+           'b200ddsp_workspace_bytes_host', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
 STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise_mix', 'reverb']

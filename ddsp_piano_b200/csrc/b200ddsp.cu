@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -34,6 +35,9 @@ struct b200ddsp_handle {
   bool fast_div = false;       // 3-op division == IEEE division for this sample rate
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
+  cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
+  cudaEvent_t ev_group[8] = {};
+  cudaEvent_t ev_mags = nullptr, ev_ir = nullptr, ev_enter = nullptr;
   bool profiling = false;
   cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
   cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
@@ -87,6 +91,12 @@ static int fail(b200ddsp_handle* h, int code, const char* fmt, ...) {
                   cudaGetErrorString(e_));                                                   \
     (h)->launches++;                                                                         \
   } while (0)
+
+// tuning knobs for experiments (not part of the ABI)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -257,6 +267,19 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
       return B200DDSP_CUDA_ERROR;
     }
   }
+  {
+    bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&h->ev_group[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_mags, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_ir, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      fail(nullptr, B200DDSP_CUDA_ERROR, "copy stream: %s", cudaGetErrorString(cudaGetLastError()));
+      b200ddsp_destroy(h);
+      return B200DDSP_CUDA_ERROR;
+    }
+  }
   *out = h;
   return B200DDSP_OK;
 }
@@ -283,6 +306,12 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (!h) return B200DDSP_OK;
   if (h->d_window) cudaFree(h->d_window);
   if (h->d_cmat_t) cudaFree(h->d_cmat_t);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 8; ++i)
+    if (h->ev_group[i]) cudaEventDestroy(h->ev_group[i]);
+  if (h->ev_mags) cudaEventDestroy(h->ev_mags);
+  if (h->ev_ir) cudaEventDestroy(h->ev_ir);
+  if (h->ev_enter) cudaEventDestroy(h->ev_enter);
   for (int i = 0; i < B200DDSP_N_STAGES; ++i) {
     if (h->ev_begin[i]) cudaEventDestroy(h->ev_begin[i]);
     if (h->ev_end[i]) cudaEventDestroy(h->ev_end[i]);
@@ -323,50 +352,70 @@ static int substrings_per_pass(int S) { return (S % 2 == 0) ? 2 : 1; }
 
 // P voices x B clips.  `fast` selects the layout of the partial signals: one per (voice, set) on
 // the fast path, one per voice group on the generic path.
-static AdditiveScratch carve_additive(int P, int B, int F, int H, int S, int U, bool fast, int G) {
+// with_outputs = false: the liveness tables and the partial signals live elsewhere (the
+// polyphonic forward keeps them in arrays shared by all of its voice groups).
+static AdditiveScratch carve_additive(int P, int B, int F, int H, int S, int U, bool fast, int G,
+                                      bool with_outputs = true) {
   AdditiveScratch a{};
   const size_t R = (size_t)P * B, N = (size_t)F * U;
   const int n_chunks = (int)((N + kAngularChunk - 1) / kAngularChunk);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
   a.offsets = take(R * S * n_chunks * H * 4);
-  a.na_frame = take(R * F);
-  a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
   a.plan = take(sizeof(AdditivePlan));
   a.lists = take((size_t)2 * kMaxGroups * R * n_chunks * 4);
   a.sets = fast ? S / substrings_per_pass(S) : 1;
   a.n_partials = fast ? P * a.sets : G;
-  a.partials = take((size_t)a.n_partials * B * N * 4);
+  if (with_outputs) {
+    a.na_frame = take(R * F);
+    a.synth_na = take(R * n_chunks);
+    a.partials = take((size_t)a.n_partials * B * N * 4);
+  }
   a.total = o;
   return a;
 }
 
+constexpr int kMaxCopyGroups = 8;
+
+// Voices are processed in `n_groups` consecutive groups (1 for device inputs; several for host
+// inputs, so that the H2D copies of one group overlap the kernels of the previous one).
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, taps, additive, tw, buf_a, buf_b, total;
-  int G, n_chunks, nfft;
+  size_t amp, hd, shifts, f0, taps, na_frame, synth_na, partials, tw, buf_a, buf_b, total;
+  size_t group_scratch[kMaxCopyGroups];
+  int n_groups, group_first[kMaxCopyGroups + 1];
+  int G;            // generic additive path: voice groups inside one launch (n_groups == 1 only)
+  int n_chunks, nfft;
 };
 
-static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, int U, bool controls) {
+static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, int U, int n_groups) {
   WorkspaceLayout w{};
   const size_t R = (size_t)P * B, N = (size_t)F * U;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
   w.n_chunks = n_chunks_for((int)N);
-  w.G = voice_groups_for(P, B, w.n_chunks);
-  if (controls) {
-    w.amp = take(R * F * 4);
-    w.hd = take(R * F * H * 4);
-    w.shifts = take(R * F * H * 4);
-    w.f0 = take(R * F * S * 4);
-    w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
-  }
-  // sized for whichever additive path the shapes select at run time (the fast path's
-  // per-voice partial signals are the larger layout)
-  {
-    const size_t fast_b = carve_additive(P, B, F, H, S, U, true, w.G).total;
-    const size_t gen_b = carve_additive(P, B, F, H, S, U, false, w.G).total;
-    w.additive = take(fast_b > gen_b ? fast_b : gen_b);
+  if (n_groups > P) n_groups = P;
+  if (n_groups > kMaxCopyGroups) n_groups = kMaxCopyGroups;
+  if (n_groups < 1) n_groups = 1;
+  w.n_groups = n_groups;
+  for (int g = 0; g <= n_groups; ++g) w.group_first[g] = (int)((long long)P * g / n_groups);
+  w.G = (n_groups == 1) ? voice_groups_for(P, B, w.n_chunks) : 1;
+  w.amp = take(R * F * 4);
+  w.hd = take(R * F * H * 4);
+  w.shifts = take(R * F * H * 4);
+  w.f0 = take(R * F * S * 4);
+  w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
+  w.na_frame = take(R * F);
+  w.synth_na = take(R * (size_t)w.n_chunks);
+  // partial signals: one per (voice, substring set) on the fast additive path, one per voice
+  // group on the generic one; sized for the larger layout
+  const size_t n_partials = (size_t)P * (S / substrings_per_pass(S));
+  w.partials = take((n_partials > (size_t)P ? n_partials : (size_t)P) * B * N * 4);
+  for (int g = 0; g < n_groups; ++g) {
+    const int Pg = w.group_first[g + 1] - w.group_first[g];
+    const size_t fast_b = carve_additive(Pg, B, F, H, S, U, true, w.G, false).total;
+    const size_t gen_b = carve_additive(Pg, B, F, H, S, U, false, w.G, false).total;
+    w.group_scratch[g] = take(fast_b > gen_b ? fast_b : gen_b);
   }
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
@@ -381,7 +430,7 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
 extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H,
                                            int S, int M, int L) {
   if (!h || P < 1 || B < 1 || F < 1) return 0;
-  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 0 ? M : 0, L, h->U, true).total;
+  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 1 ? M : 2, L, h->U, env_int("B200DDSP_DEV_GROUPS", 1)).total;
 }
 
 extern "C" size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H,
@@ -507,9 +556,18 @@ struct AdditiveResult {
 // lists (fast path), chunk end phases, offsets scan, oscillator bank.  The result is a set of
 // partial signals in `scratch` for the mixer to sum.  na_frame_ready: the controls kernel has
 // already written the per-frame liveness.
+// Where the liveness tables and partial signals go when they are shared between several calls
+// (null members: inside `scratch`).
+struct AdditiveOutputs {
+  unsigned char* na_frame;   // [P*B, F]
+  unsigned char* synth_na;   // [P*B, n_chunks]
+  float* partials;           // [n_partials, B, N]
+};
+
 static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, const float* shifts,
-                        const float* f0, char* scratch, int P, int B, int F, int H, int S, int G,
-                        bool na_frame_ready, AdditiveResult* res, cudaStream_t st) {
+                        const float* f0, char* scratch, const AdditiveOutputs* ext, int P, int B,
+                        int F, int H, int S, int G, bool na_frame_ready, AdditiveResult* res,
+                        cudaStream_t st) {
   const int U = h->U, N = F * U;
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
@@ -519,11 +577,11 @@ static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, c
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
                 F, N);
   const int n_chunks = n_chunks_for(N);
-  const AdditiveScratch sc = carve_additive(P, B, F, H, S, U, fast, G);
+  const AdditiveScratch sc = carve_additive(P, B, F, H, S, U, fast, G, ext == nullptr);
   AdditiveArgs a{};
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
   a.offsets = (float*)(scratch + sc.offsets);
-  a.out = (float*)(scratch + sc.partials);
+  a.out = ext ? ext->partials : (float*)(scratch + sc.partials);
   a.window = h->d_window;
   a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
   a.chunk = kAngularChunk;
@@ -541,8 +599,8 @@ static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, c
 
   if (fast) {
     const int R = P * B;
-    unsigned char* na_frame = (unsigned char*)(scratch + sc.na_frame);
-    unsigned char* synth_na = (unsigned char*)(scratch + sc.synth_na);
+    unsigned char* na_frame = ext ? ext->na_frame : (unsigned char*)(scratch + sc.na_frame);
+    unsigned char* synth_na = ext ? ext->synth_na : (unsigned char*)(scratch + sc.synth_na);
     unsigned char* ends_na = (unsigned char*)(scratch + sc.ends_na);
     AdditivePlan* plan = (AdditivePlan*)(scratch + sc.plan);
     int* lists = (int*)(scratch + sc.lists);
@@ -637,7 +695,7 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
   reset_stage_flags(h);
   AdditiveResult res{};
   if (int rc = run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
-                            (char*)workspace, 1, B, F, H, S, 1, false, &res, st))
+                            (char*)workspace, nullptr, 1, B, F, H, S, 1, false, &res, st))
     return rc;
   PartialSumArgs ps{};
   ps.partials = res.partials;
@@ -873,81 +931,266 @@ extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const flo
 // the whole DAG
 // ---------------------------------------------------------------------------------------------
 
-extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
-                                           const float* reverb_ir, float* dry_out, float* wet_out,
-                                           int B, int F, int H, int S, int M, int L, uint64_t seed,
-                                           void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = check_common(h, B, F)) return rc;
-  if (!voices || P < 1 || P > B200DDSP_MAX_VOICES)
-    return fail(h, B200DDSP_BAD_SHAPE, "P=%d outside [1, %d]", P, B200DDSP_MAX_VOICES);
-  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
-  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  if (!dry_out) return fail(h, B200DDSP_BAD_ARGUMENT, "dry_out is null");
-  if (reverb_ir && (!wet_out || L < 1))
-    return fail(h, B200DDSP_BAD_ARGUMENT, "reverb_ir given but wet_out is null or L < 1");
-  if (reverb_ir && wet_out == dry_out)
-    return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out may not alias dry_out");
+// Optional cross-stream ordering for the host-input entry point: the main stream waits for
+// `group_ready[g]` before it touches the controls of voice group g, for `mags_ready` before the
+// noise stage and for `ir_ready` before the reverb.
+struct ForwardSync {
+  cudaEvent_t group_ready[kMaxCopyGroups];
+  cudaEvent_t mags_ready, ir_ready;
+};
+
+static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, const float* reverb_ir,
+                        float* dry_out, float* wet_out, int B, int F, int H, int S, int M, int L,
+                        uint64_t seed, char* base, const WorkspaceLayout& w, const ForwardSync* sync,
+                        cudaStream_t st) {
   const int U = h->U, N = F * U;
-  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir ? L : 0, U, true);
-  if (!workspace || workspace_bytes < w.total)
-    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_polyphonic needs %zu workspace bytes, got %zu",
-                w.total, workspace_bytes);
-  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
-  char* base = (char*)workspace;
-  cudaStream_t st = (cudaStream_t)stream;
   float* amp = (float*)(base + w.amp);
   float* hd = (float*)(base + w.hd);
   float* shifts = (float*)(base + w.shifts);
   float* f0 = (float*)(base + w.f0);
   float* taps = (float*)(base + w.taps);
+  const bool fast = additive_fast_path(h, F, H);
+  const int sets = fast ? S / substrings_per_pass(S) : 1;
 
-  // per-frame liveness of the partial groups comes out of the controls kernel on the fast path
-  unsigned char* na_frame = nullptr;
-  if (additive_fast_path(h, F, H))
-    na_frame = (unsigned char*)(base + w.additive + carve_additive(P, B, F, H, S, U, true, w.G).na_frame);
-  // get_controls of every voice (additive: stacked [P*B, F, .]; noise: scale_fn(m + bias))
-  AdditiveControlsPtrs cp{};
   NoiseVoicePtrs vp{};
   NoiseTapsPtrs mp{};
   for (int v = 0; v < P; ++v) {
     const b200ddsp_voice& vc = voices[v];
     if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
       return fail(h, B200DDSP_BAD_ARGUMENT, "voice %d has a null control tensor", v);
-    cp.amp_in[v] = vc.amplitudes;
-    cp.hd_in[v] = vc.harmonic_distribution;
-    cp.inharm_in[v] = vc.inharm_coef;
-    cp.f0_in[v] = vc.f0_hz;
     mp.mags[v] = vc.magnitudes;
     vp.noise[v] = vc.noise;
   }
   reset_stage_flags(h);
-  {
-    StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
-    AdditiveControlsArgs a{};
-    a.amp_out = amp; a.hd_out = hd; a.shifts_out = shifts; a.f0_out = f0;
-    a.na_frame = na_frame;
-    a.n_frames_voice = B * F;
-    a.H = H; a.S = S;
-    a.nyquist = (float)(h->cfg.sample_rate / 2.0);
-    a.min_frequency = h->cfg.min_frequency;
-    a.scale_fn = h->cfg.additive_scale_fn;
-    a.normalize_after = h->cfg.normalize_after_nyquist_cut;
-    a.normalize_below = h->cfg.normalize_below_nyquist;
-    launch_additive_controls(a, cp, P, st);
-    CHECK_LAUNCH(h, "additive_controls_kernel");
-  }
-  // additive oscillator bank -> G partial sums
+
   AdditiveResult mix{};
-  if (int rc = run_additive(h, amp, hd, shifts, f0, base + w.additive, P, B, F, H, S, w.G,
-                            na_frame != nullptr, &mix, st))
-    return rc;
-  // noise of every voice + mix -> dry  (outputs['add']['signal'])
-  // FilteredNoise.get_controls is fused into the taps GEMM's operand load
+  mix.partials = (float*)(base + w.partials);
+  mix.live = fast ? (unsigned char*)(base + w.synth_na) : nullptr;
+  mix.sets = sets;
+  mix.n_partials = 0;
+  for (int g = 0; g < w.n_groups; ++g) {
+    const int v0 = w.group_first[g], Pg = w.group_first[g + 1] - v0;
+    const size_t row0 = (size_t)v0 * B;
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->group_ready[g], 0));
+    // get_controls of the group's voices -> stacked [P*B, F, .] rows (+ per-frame liveness of
+    // the partial groups on the fast path)
+    unsigned char* na_frame = fast ? (unsigned char*)(base + w.na_frame) + row0 * F : nullptr;
+    {
+      StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
+      AdditiveControlsPtrs cp{};
+      for (int i = 0; i < Pg; ++i) {
+        cp.amp_in[i] = voices[v0 + i].amplitudes;
+        cp.hd_in[i] = voices[v0 + i].harmonic_distribution;
+        cp.inharm_in[i] = voices[v0 + i].inharm_coef;
+        cp.f0_in[i] = voices[v0 + i].f0_hz;
+      }
+      AdditiveControlsArgs a{};
+      a.amp_out = amp + row0 * F;
+      a.hd_out = hd + row0 * F * H;
+      a.shifts_out = shifts + row0 * F * H;
+      a.f0_out = f0 + row0 * F * S;
+      a.na_frame = na_frame;
+      a.n_frames_voice = B * F;
+      a.H = H; a.S = S;
+      a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+      a.min_frequency = h->cfg.min_frequency;
+      a.scale_fn = h->cfg.additive_scale_fn;
+      a.normalize_after = h->cfg.normalize_after_nyquist_cut;
+      a.normalize_below = h->cfg.normalize_below_nyquist;
+      launch_additive_controls(a, cp, Pg, st);
+      CHECK_LAUNCH(h, "additive_controls_kernel");
+    }
+    // additive oscillator bank of the group -> partial signals
+    AdditiveOutputs ext{};
+    ext.na_frame = na_frame;
+    ext.synth_na = (unsigned char*)(base + w.synth_na) + row0 * w.n_chunks;
+    ext.partials = (float*)(base + w.partials) + (size_t)mix.n_partials * B * N;
+    AdditiveResult part{};
+    if (int rc = run_additive(h, amp + row0 * F, hd + row0 * F * H, shifts + row0 * F * H,
+                              f0 + row0 * F * S, base + w.group_scratch[g], &ext, Pg, B, F, H, S, w.G,
+                              fast, &part, st))
+      return rc;
+    mix.n_partials += part.n_partials;
+  }
+  // noise of every voice + mix -> dry  (outputs['add']['signal']); FilteredNoise.get_controls is
+  // fused into the taps GEMM's operand load
+  if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->mags_ready, 0));
   if (int rc = run_noise(h, mp, h->cfg.noise_scale_fn, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, taps, st))
     return rc;
   // reverb -> wet
-  if (reverb_ir)
+  if (reverb_ir) {
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->ir_ready, 0));
     return run_reverb(h, dry_out, reverb_ir, wet_out, B, N, L, (float2*)(base + w.tw),
                       (float2*)(base + w.buf_a), (float2*)(base + w.buf_b), st);
+  }
+  return B200DDSP_OK;
+}
+
+static int check_forward_args(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, int B, int F,
+                              int H, int S, int M, int L, bool has_ir) {
+  if (int rc = check_common(h, B, F)) return rc;
+  if (!voices || P < 1 || P > B200DDSP_MAX_VOICES)
+    return fail(h, B200DDSP_BAD_SHAPE, "P=%d outside [1, %d]", P, B200DDSP_MAX_VOICES);
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
+  if (M < 3) return fail(h, B200DDSP_BAD_SHAPE, "M=%d must be at least 3", M);
+  if (has_ir && L < 1) return fail(h, B200DDSP_BAD_SHAPE, "reverb_ir given but L < 1");
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
+                                           const float* reverb_ir, float* dry_out, float* wet_out,
+                                           int B, int F, int H, int S, int M, int L, uint64_t seed,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_forward_args(h, voices, P, B, F, H, S, M, L, reverb_ir != nullptr)) return rc;
+  if (!dry_out) return fail(h, B200DDSP_BAD_ARGUMENT, "dry_out is null");
+  if (reverb_ir && !wet_out) return fail(h, B200DDSP_BAD_ARGUMENT, "reverb_ir given but wet_out is null");
+  if (reverb_ir && wet_out == dry_out)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out may not alias dry_out");
+  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir ? L : 0, h->U, env_int("B200DDSP_DEV_GROUPS", 1));
+  if (!workspace || workspace_bytes < w.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_polyphonic needs %zu workspace bytes, got %zu",
+                w.total, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  return forward_core(h, voices, P, reverb_ir, dry_out, wet_out, B, F, H, S, M, L, seed,
+                      (char*)workspace, w, nullptr, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the whole DAG from HOST buffers
+// ---------------------------------------------------------------------------------------------
+
+struct HostStaging {
+  size_t amp, hd, inh, f0, mags, noise, ir, dry, wet, core, total;
+};
+
+static HostStaging carve_host(int P, int B, int F, int H, int S, int M, int L, int U, bool noise,
+                              const WorkspaceLayout& w) {
+  HostStaging s{};
+  const size_t R = (size_t)P * B, N = (size_t)F * U;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
+  s.amp = take(R * F * 4);
+  s.hd = take(R * F * H * 4);
+  s.inh = take(R * F * 4);
+  s.f0 = take(R * F * S * 4);
+  s.mags = take(R * F * (size_t)M * 4);
+  if (noise) s.noise = take(R * N * 4);
+  if (L > 0) s.ir = take((size_t)B * L * 4);
+  s.dry = take((size_t)B * N * 4);
+  if (L > 0) s.wet = take((size_t)B * N * 4);
+  s.core = take(w.total);
+  s.total = o;
+  return s;
+}
+
+static int host_copy_groups(int P) {
+  const int g = env_int("B200DDSP_HOST_GROUPS", 3);
+  return P >= g ? g : P;
+}
+
+extern "C" size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int F, int H,
+                                                int S, int M, int L, int with_noise) {
+  if (!h || P < 1 || B < 1 || F < 1 || H < 1 || S < 1 || M < 3) return 0;
+  const WorkspaceLayout w = carve(P, B, F, H, S, M, L, h->U, host_copy_groups(P));
+  return carve_host(P, B, F, H, S, M, L, h->U, with_noise != 0, w).total;
+}
+
+extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host,
+                                                int P, const float* reverb_ir_host,
+                                                float* dry_out_host, float* wet_out_host, int B, int F,
+                                                int H, int S, int M, int L, uint64_t seed,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_forward_args(h, voices_host, P, B, F, H, S, M, L, reverb_ir_host != nullptr))
+    return rc;
+  if (!dry_out_host && !wet_out_host)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "neither dry_out_host nor wet_out_host given");
+  if (wet_out_host && !reverb_ir_host)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out_host given without reverb_ir_host");
+  const int U = h->U, N = F * U;
+  bool any_noise = false;
+  for (int v = 0; v < P; ++v) any_noise |= voices_host[v].noise != nullptr;
+  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir_host ? L : 0, U, host_copy_groups(P));
+  const HostStaging hs = carve_host(P, B, F, H, S, M, reverb_ir_host ? L : 0, U, any_noise, w);
+  if (!workspace || workspace_bytes < hs.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL,
+                "forward_polyphonic_host needs %zu workspace bytes, got %zu", hs.total, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  for (int v = 0; v < P; ++v) {
+    const b200ddsp_voice& vc = voices_host[v];
+    if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
+      return fail(h, B200DDSP_BAD_ARGUMENT, "voice %d has a null control tensor", v);
+  }
+  char* base = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t cs = h->copy_stream;
+  const size_t BF = (size_t)B * F;
+
+  // device-side voices over the staging area
+  b200ddsp_voice dev[B200DDSP_MAX_VOICES];
+  for (int v = 0; v < P; ++v) {
+    dev[v].amplitudes = (float*)(base + hs.amp) + v * BF;
+    dev[v].harmonic_distribution = (float*)(base + hs.hd) + v * BF * H;
+    dev[v].inharm_coef = (float*)(base + hs.inh) + v * BF;
+    dev[v].f0_hz = (float*)(base + hs.f0) + v * BF * S;
+    dev[v].magnitudes = (float*)(base + hs.mags) + v * BF * M;
+    dev[v].noise = voices_host[v].noise ? (float*)(base + hs.noise) + (size_t)v * B * N : nullptr;
+  }
+  // one memcpy per run of voices whose host tensors are contiguous (stacked [P,B,F,C] parents)
+  auto copy_runs = [&](int v0, int v1, size_t elems, auto host_of, auto dev_of) -> cudaError_t {
+    int v = v0;
+    while (v < v1) {
+      int run = 1;
+      while (v + run < v1 && host_of(v + run) == host_of(v) + (size_t)run * elems) ++run;
+      cudaError_t e = cudaMemcpyAsync((void*)dev_of(v), host_of(v), (size_t)run * elems * 4,
+                                      cudaMemcpyHostToDevice, cs);
+      if (e != cudaSuccess) return e;
+      v += run;
+    }
+    return cudaSuccess;
+  };
+  // the copy stream may not overwrite the staging area before the previous call (ordered on
+  // its own stream) has consumed it, nor before work already queued on `st`
+  CUDA_TRY(h, cudaEventRecord(h->ev_enter, st));
+  CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_enter, 0));
+  ForwardSync sync{};
+  for (int g = 0; g < w.n_groups; ++g) {
+    const int v0 = w.group_first[g], v1 = w.group_first[g + 1];
+    CUDA_TRY(h, copy_runs(v0, v1, BF, [&](int v) { return voices_host[v].amplitudes; },
+                          [&](int v) { return dev[v].amplitudes; }));
+    CUDA_TRY(h, copy_runs(v0, v1, BF * H, [&](int v) { return voices_host[v].harmonic_distribution; },
+                          [&](int v) { return dev[v].harmonic_distribution; }));
+    CUDA_TRY(h, copy_runs(v0, v1, BF, [&](int v) { return voices_host[v].inharm_coef; },
+                          [&](int v) { return dev[v].inharm_coef; }));
+    CUDA_TRY(h, copy_runs(v0, v1, BF * S, [&](int v) { return voices_host[v].f0_hz; },
+                          [&](int v) { return dev[v].f0_hz; }));
+    CUDA_TRY(h, cudaEventRecord(h->ev_group[g], cs));
+    sync.group_ready[g] = h->ev_group[g];
+  }
+  CUDA_TRY(h, copy_runs(0, P, BF * M, [&](int v) { return voices_host[v].magnitudes; },
+                        [&](int v) { return dev[v].magnitudes; }));
+  for (int v = 0; v < P; ++v)
+    if (voices_host[v].noise)
+      CUDA_TRY(h, cudaMemcpyAsync((void*)dev[v].noise, voices_host[v].noise, (size_t)B * N * 4,
+                                  cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(h, cudaEventRecord(h->ev_mags, cs));
+  sync.mags_ready = h->ev_mags;
+  float* ir_dev = nullptr;
+  if (reverb_ir_host) {
+    ir_dev = (float*)(base + hs.ir);
+    CUDA_TRY(h, cudaMemcpyAsync(ir_dev, reverb_ir_host, (size_t)B * L * 4, cudaMemcpyHostToDevice, cs));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_ir, cs));
+  sync.ir_ready = h->ev_ir;
+
+  float* dry_dev = (float*)(base + hs.dry);
+  float* wet_dev = reverb_ir_host ? (float*)(base + hs.wet) : nullptr;
+  if (int rc = forward_core(h, dev, P, ir_dev, dry_dev, wet_dev, B, F, H, S, M, L, seed, base + hs.core, w,
+                            &sync, st))
+    return rc;
+  if (dry_out_host)
+    CUDA_TRY(h, cudaMemcpyAsync(dry_out_host, dry_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  if (wet_out_host)
+    CUDA_TRY(h, cudaMemcpyAsync(wet_out_host, wet_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   return B200DDSP_OK;
 }

@@ -47,6 +47,8 @@ class Engine:
             raise (ValueError if rc in (-1, -3, -6) else RuntimeError)(
                 f'b200ddsp_create: {_lib.STATUS_NAMES.get(rc, rc)}: {msg}')
         self._workspace = None
+        self._host_out = {}
+        self._keep_alive = None
 
     def __del__(self):
         try:
@@ -202,6 +204,76 @@ class Engine:
                 ws.data_ptr(), ws.numel(), self.stream()))
         return out
 
+    def forward_polyphonic_host(self, voices, reverb_ir=None, seed=0, want_dry=True):
+        """Same as forward_polyphonic for HOST tensors (pinned memory recommended): the H2D
+        copies are staged group by group and overlap the kernels; returns pinned host tensors
+        (dry or None, wet or None) that are valid once the current stream has been synchronised
+        and are REUSED by the next call on this engine."""
+        P = len(voices)
+        if P < 1 or P > _lib.MAX_VOICES:
+            raise ValueError(f'n_synths={P} outside [1, {_lib.MAX_VOICES}]')
+        arr = (_lib.Voice * P)()
+        keep = []
+        B = F = H = S = M = None
+        any_noise = False
+        for i, v in enumerate(voices):
+            amp = _host_tensor(v['amplitudes'], f'amplitudes_{i}', 3)
+            hd = _host_tensor(v['harmonic_distribution'], f'harmonic_distribution_{i}', 3)
+            inh = _host_tensor(v['inharm_coef'], f'inharm_coef_{i}', 3)
+            f0 = _host_tensor(v['f0_hz'], f'f0_hz_{i}', 3)
+            mag = _host_tensor(v['magnitudes'], f'magnitudes_{i}', 3)
+            if i == 0:
+                B, F, H = hd.shape
+                S, M = f0.shape[-1], mag.shape[-1]
+            want = {'amplitudes': (B, F, 1), 'harmonic_distribution': (B, F, H),
+                    'inharm_coef': (B, F, 1), 'f0_hz': (B, F, S), 'magnitudes': (B, F, M)}
+            for t, k in ((amp, 'amplitudes'), (hd, 'harmonic_distribution'),
+                         (inh, 'inharm_coef'), (f0, 'f0_hz'), (mag, 'magnitudes')):
+                if tuple(t.shape) != want[k]:
+                    raise ValueError(f'{k}_{i} has shape {tuple(t.shape)}, expected {want[k]}')
+            nz = v.get('noise')
+            if nz is not None:
+                nz = _host_tensor(nz, f'noise_{i}', 2)
+                if tuple(nz.shape) != (B, F * self.upsampling):
+                    raise ValueError(f'noise_{i} has shape {tuple(nz.shape)}')
+                any_noise = True
+            keep += [amp, hd, inh, f0, mag, nz]
+            arr[i] = _lib.Voice(amp.data_ptr(), hd.data_ptr(), inh.data_ptr(), f0.data_ptr(),
+                                mag.data_ptr(), nz.data_ptr() if nz is not None else None)
+        N = F * self.upsampling
+        L = 0
+        ir = None
+        if reverb_ir is not None:
+            ir = _host_tensor(reverb_ir, 'reverb_ir')
+            if ir.dim() == 1:
+                ir = ir[None, :]
+            if ir.dim() == 3:
+                ir = ir[:, :, 0].contiguous()
+            if ir.shape[0] == 1 and B > 1:
+                ir = ir.expand(B, -1).contiguous()
+            if ir.shape[0] != B:
+                raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
+                                 'be the same.'.format(B, ir.shape[0]))
+            L = ir.shape[1]
+        nbytes = self.lib.b200ddsp_workspace_bytes_host(self.handle, P, B, F, H, S, M, L,
+                                                        int(any_noise))
+        ws = self.workspace(nbytes)
+        key = (B, N)
+        bufs = self._host_out.get(key)
+        if bufs is None:
+            bufs = self._host_out[key] = (torch.empty([B, N], dtype=torch.float32).pin_memory(),
+                                          torch.empty([B, N], dtype=torch.float32).pin_memory())
+        dry = bufs[0] if (want_dry or ir is None) else None
+        wet = bufs[1] if ir is not None else None
+        self._keep_alive = keep + [ir]       # host buffers must outlive the enqueued copies
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_forward_polyphonic_host(
+                self.handle, arr, P, ir.data_ptr() if ir is not None else None,
+                dry.data_ptr() if dry is not None else None,
+                wet.data_ptr() if wet is not None else None, B, F, H, S, M, L, seed,
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return dry, wet
+
     def forward_polyphonic(self, voices, reverb_ir=None, seed=0):
         """voices: list of dicts with keys amplitudes, harmonic_distribution, inharm_coef,
         f0_hz, magnitudes and optionally noise.  Returns (dry, wet or None)."""
@@ -259,6 +331,20 @@ class Engine:
                 wet.data_ptr() if wet is not None else None, B, F, H, S, M, L, seed,
                 ws.data_ptr(), ws.numel(), self.stream()))
         return dry, wet
+
+
+def _host_tensor(x, name, ndim=None):
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x, dtype=torch.float32)
+    if x.device.type != 'cpu':
+        raise ValueError(f'{name} is on {x.device}; the host entry point takes CPU tensors')
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if ndim is not None and x.dim() != ndim:
+        raise ValueError(f'{name} must have {ndim} dimensions, got shape {tuple(x.shape)}')
+    return x
 
 
 def get_engine(device, **cfg):

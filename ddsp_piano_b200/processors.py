@@ -334,10 +334,18 @@ class ProcessorGroup:
         cfg = {**_DEFAULT_CFG, **additive.engine_config(), **noise.engine_config(M)}
         if reverb is not None:
             cfg.update(reverb.engine_config())
-        eng = get_engine(_device_of(voices[0]['f0_hz']), **cfg)
+        f0_0 = voices[0]['f0_hz']
+        on_host = not (isinstance(f0_0, torch.Tensor) and f0_0.device.type == 'cuda')
+        dev = torch.device('cuda', torch.cuda.current_device()) if on_host else f0_0.device
+        eng = get_engine(dev, **cfg)
         ir = nested_lookup(plan['ir_key'], outputs) if reverb is not None else None
         seed = (noise.seed + 0x9E3779B97F4A7C15 * noise.next_stream_id(len(voices))) & (2 ** 64 - 1)
-        dry, wet = eng.forward_polyphonic(voices, reverb_ir=ir, seed=seed)
+        if on_host:
+            # HOST features (numpy / CPU tensors): staged copies overlap the kernels; the signals
+            # come back as pinned host tensors, valid after torch.cuda.current_stream().synchronize()
+            dry, wet = eng.forward_polyphonic_host(voices, reverb_ir=ir, seed=seed)
+        else:
+            dry, wet = eng.forward_polyphonic(voices, reverb_ir=ir, seed=seed)
         outputs[plan['add'].name] = {'signal': dry, 'controls': {}}
         last = outputs[plan['add'].name]
         if reverb is not None:

@@ -163,6 +163,21 @@ int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_voice* voices
                                 int F, int H, int S, int M, int L, uint64_t seed,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same DAG fed from HOST memory -- what modules/piano_model.py:160 looks like to a caller
+ * whose control tensors live on the host.  Every pointer in `voices_host`, `reverb_ir_host`,
+ * `dry_out_host` and `wet_out_host` is a HOST pointer (page-locked memory for asynchronous,
+ * full-speed copies); either output may be NULL.  The library stages the inputs in `workspace`
+ * (device memory) on an internal copy stream, in voice groups, so that the H2D copies of one
+ * group overlap the kernels of the previous one; the result is copied back on `stream`.  The
+ * call only enqueues; the host buffers must stay valid until `stream` has drained. */
+int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host, int P,
+                                     const float* reverb_ir_host, float* dry_out_host,
+                                     float* wet_out_host, int B, int F, int H, int S, int M, int L,
+                                     uint64_t seed, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int F, int H, int S,
+                                     int M, int L, int with_noise);
+
 /* Number of kernel launches enqueued by this handle since creation (bench.py's
  * gpu_launches claim is read from here). */
 uint64_t b200ddsp_launch_count(const b200ddsp_handle* h);

@@ -355,3 +355,34 @@ def test_dag_without_reverb_and_determinism(dp, dev):
         assert out['controls']['out'] is out['controls']['add']
         runs.append(out['signal'])
     assert torch.equal(runs[0], runs[1])           # bitwise reproducible run to run
+
+
+def test_dag_host_entry_matches_device_entry(dp, dev):
+    """CPU (pinned) features go through b200ddsp_forward_polyphonic_host: staged H2D copies in
+    voice groups, same kernels, D2H of the result.  Must equal the device-resident call."""
+    sr, F, B, H, S, M, P, L = 24000, 50, 2, 96, 2, 64, 6, 3000
+    rng = np.random.default_rng(3)
+    feats = {}
+    for v in range(P):
+        for k, a in voice_inputs(rng, B, F, H, S, M).items():
+            feats[f'{k}_{v}'] = torch.from_numpy(a).pin_memory()
+    feats['reverb_ir'] = torch.from_numpy(
+        (rng.standard_normal([B, L]) * np.exp(-6 * np.arange(L) / L) * 1e-2).astype(np.float32))
+    results = []
+    for host in (True, False):
+        group, noise = _build_group(dp, sr, P, True)
+        noise.seed, noise._calls = 7, 0
+        f = dict(feats) if host else {k: v.to(dev) for k, v in feats.items()}
+        out = group(f, return_outputs_dict=True)
+        torch.cuda.synchronize()
+        assert out['signal'].device.type == ('cpu' if host else 'cuda')
+        results.append((out['signal'].cpu().clone(), out['controls']['add']['signal'].cpu().clone()))
+    assert torch.equal(results[0][0], results[1][0])
+    assert torch.equal(results[0][1], results[1][1])
+    # repeated host calls reuse the staging area: the second result must not be corrupted
+    group, noise = _build_group(dp, sr, P, True)
+    for _ in range(3):
+        noise.seed, noise._calls = 7, 0
+        out = group(dict(feats), return_outputs_dict=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out['signal'], results[0][0])
