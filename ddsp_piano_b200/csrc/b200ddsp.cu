@@ -854,8 +854,10 @@ static std::vector<int> fft_radices(int n) {
   return r;
 }
 
+// full_output: write all N + L - 1 samples of the convolution and no dry signal.
 static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
-                      int N, int L, float2* tw, float2* buf_a, float2* buf_b, cudaStream_t st) {
+                      int N, int L, float2* tw, float2* buf_a, float2* buf_b, cudaStream_t st,
+                      bool full_output = false) {
   StageTimer tm(h, B200DDSP_STAGE_REVERB, st);
   const int n = fft_size_for(N, L);
   const std::vector<int> radices = fft_radices(n);
@@ -892,7 +894,8 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   for (int i = 0; i < n_pass; ++i) {
     const LoadComplex ld{src, n};
     if (i == n_pass - 1) {
-      const StoreWetPair sto{out, audio, N, B, 1.0f / (float)n, h->cfg.reverb_add_dry};
+      const StoreWetPair sto{out, audio, N, full_output ? N + L - 1 : N, B, 1.0f / (float)n,
+                             full_output ? 0 : h->cfg.reverb_add_dry};
       launch_fft_pass(radices[i], ld, sto, tw, n, Ns, pairs, st);
     } else {
       launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, tw, n, Ns, pairs, st);
@@ -905,9 +908,9 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   return B200DDSP_OK;
 }
 
-extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
-                               int B, int N, int L, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+static int reverb_entry(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
+                        int B, int N, int L, void* workspace, size_t workspace_bytes,
+                        void* stream, bool full_output) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
   if (B < 1 || N < 1 || L < 1 || B > 65535)
     return fail(h, B200DDSP_BAD_SHAPE, "B=%d N=%d L=%d must be positive", B, N, L);
@@ -923,8 +926,21 @@ extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const flo
                 workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
   char* w = (char*)workspace;
+  reset_stage_flags(h);
   return run_reverb(h, audio, ir, out, B, N, L, (float2*)w, (float2*)(w + tw_b),
-                    (float2*)(w + tw_b + buf_b), (cudaStream_t)stream);
+                    (float2*)(w + tw_b + buf_b), (cudaStream_t)stream, full_output);
+}
+
+extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
+                               int B, int N, int L, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  return reverb_entry(h, audio, ir, out, B, N, L, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir,
+                                    float* out_full, int B, int N, int L, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return reverb_entry(h, audio, ir, out_full, B, N, L, workspace, workspace_bytes, stream, true);
 }
 
 // ---------------------------------------------------------------------------------------------

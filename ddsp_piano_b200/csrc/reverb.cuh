@@ -136,22 +136,21 @@ struct LoadAudioIr {
     return make_float2(re, im);
   }
 };
-// real part -> clip 2*batch, imaginary part -> clip 2*batch+1; crop to N ('same',
-// delay_compensation = 0), scale by 1/n, add the dry signal
+// real part -> clip 2*batch, imaginary part -> clip 2*batch+1; crop to n_out samples
+// (N for padding 'same' with delay_compensation = 0; N + L - 1 for the 'valid' form used by the
+// timeline overlap-add), scale by 1/n, add the dry signal (add_dry needs n_out <= N)
 struct StoreWetPair {
-  float* out; const float* audio; int N, B; float inv_n; int add_dry;
+  float* out; const float* audio; int N, n_out, B; float inv_n; int add_dry;
   __device__ __forceinline__ void operator()(int batch, int i, float2 v) const {
-    if (i >= N) return;
+    if (i >= n_out) return;
     const int b0 = 2 * batch, b1 = b0 + 1;
-    const size_t o0 = (size_t)b0 * N + i;
     float y0 = v.x * inv_n;
-    if (add_dry) y0 = __fadd_rn(y0, __ldg(audio + o0));
-    out[o0] = y0;
+    if (add_dry) y0 = __fadd_rn(y0, __ldg(audio + (size_t)b0 * N + i));
+    out[(size_t)b0 * n_out + i] = y0;
     if (b1 < B) {
-      const size_t o1 = (size_t)b1 * N + i;
       float y1 = v.y * inv_n;
-      if (add_dry) y1 = __fadd_rn(y1, __ldg(audio + o1));
-      out[o1] = y1;
+      if (add_dry) y1 = __fadd_rn(y1, __ldg(audio + (size_t)b1 * N + i));
+      out[(size_t)b1 * n_out + i] = y1;
     }
   }
 };

@@ -177,7 +177,11 @@ class Engine:
                 self.stream()))
         return out
 
-    def reverb(self, audio, ir):
+    def reverb_full(self, audio, ir):
+        """'valid'-padded wet signal [B, N + L - 1] (no dry), see sharding.timeline_reverb."""
+        return self.reverb(audio, ir, full=True)
+
+    def reverb(self, audio, ir, full=False):
         audio = self.tensor(audio, 'audio', 2)
         ir = self.tensor(ir, 'ir')
         if ir.dim() == 1:
@@ -197,11 +201,12 @@ class Engine:
             n *= 2
         al = lambda x: (x + 255) // 256 * 256
         ws = self.workspace(al(n * 8) + 2 * al(B * n * 8))
-        out = torch.empty_like(audio)
+        out = torch.empty([B, N + L - 1] if full else [B, N], dtype=torch.float32,
+                          device=self.device)
+        fn = self.lib.b200ddsp_reverb_full if full else self.lib.b200ddsp_reverb
         with torch.cuda.device(self.device):
-            self.check(self.lib.b200ddsp_reverb(
-                self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L,
-                ws.data_ptr(), ws.numel(), self.stream()))
+            self.check(fn(self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L,
+                          ws.data_ptr(), ws.numel(), self.stream()))
         return out
 
     def forward_polyphonic_host(self, voices, reverb_ir=None, seed=0, want_dry=True):

@@ -1,0 +1,88 @@
+"""Multi-GPU partitioning of the synthesis path.  One process per GPU.
+
+Two regimes:
+
+* independent clips (BASELINE configs 2/3/5): clips are sharded over ranks, no data-path
+  collective -- :func:`clip_shard`;
+* one long timeline cut into fixed-length segments (BASELINE config 4): segments are
+  synthesised independently (each is its own clip for the additive and noise processors,
+  exactly as the reference's segment pipeline treats them), but the reverb is a convolution of
+  the CONCATENATED dry timeline, so the last ``L-1`` wet samples of every segment spill into
+  its successors.  Inside a rank that is a local overlap-add; across ranks it is one
+  neighbour exchange (``send`` to rank+1 / ``recv`` from rank-1) of an ``L-1``-sample carry that
+  is added to the head of the receiving rank's timeline -- :func:`timeline_reverb`.
+
+The functions are backend-agnostic (``torch.distributed`` with NCCL on GPUs, gloo in the CPU
+tests); the convolution itself is injected (``conv_full``), on the GPU it is
+``Engine.reverb_full`` (hand-written FFT convolution, 'valid'-padded).
+"""
+import torch
+import torch.distributed as dist
+
+
+def clip_shard(n_clips, rank, world):
+    """Contiguous, balanced shard [start, stop) of ``n_clips`` independent clips."""
+    if not (0 <= rank < world):
+        raise ValueError(f'rank {rank} outside world of {world}')
+    base, extra = divmod(n_clips, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def overlap_add_segments(wet_full, n_samples):
+    """Local part of the timeline reverb.
+
+    wet_full: [S, N + L - 1] 'valid'-padded convolution of each of the rank's S consecutive
+    segments.  Returns (wet [S, N], carry [L - 1]) where ``wet`` already contains the spill of
+    every local segment into its local successors and ``carry`` is what spills past the end of
+    the rank's span (to be added at the start of the next rank's timeline)."""
+    S, total = wet_full.shape
+    N = n_samples
+    tail = total - N                     # L - 1
+    if tail > S * N:
+        raise ValueError(f'reverb tail ({tail} samples) is longer than the rank\'s span '
+                         f'({S} segments x {N}); use fewer ranks or longer spans')
+    span = torch.zeros(S * N + tail, dtype=wet_full.dtype, device=wet_full.device)
+    # deterministic order: segment by segment (tails may cover several successors)
+    for i in range(S):
+        span[i * N:i * N + total] += wet_full[i]
+    return span[:S * N].reshape(S, N).clone(), span[S * N:].clone()
+
+
+def exchange_carry(carry, rank, world, group=None):
+    """Send this rank's carry to rank+1 and return the carry received from rank-1 (zeros on
+    rank 0: the timeline starts there; the last rank's carry falls off the end)."""
+    recv = torch.zeros_like(carry)
+    if world == 1:
+        return recv
+    ops = []
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, carry.contiguous(), rank + 1, group))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, recv, rank - 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return recv
+
+
+def timeline_reverb(dry, ir, conv_full, rank=0, world=1, add_dry=True, group=None):
+    """Reverb of a timeline whose consecutive segments are spread over ranks.
+
+    dry: [S, N] this rank's consecutive dry segments (rank r holds segments r*S .. r*S+S-1);
+    ir: [L] (one impulse response for the whole timeline);
+    conv_full(dry [S, N], ir [S, L]) -> [S, N + L - 1]: linear convolution with ir[0] masked
+    (ddsp.effects.Reverb semantics), no dry signal added.
+    Returns wet [S, N] == reverb(concatenated timeline)[this rank's span]."""
+    S, N = dry.shape
+    if ir.dim() != 1:
+        raise ValueError('timeline_reverb takes a single impulse response [L]')
+    L = ir.shape[0]
+    wet_full = conv_full(dry, ir[None, :].expand(S, L).contiguous())
+    if tuple(wet_full.shape) != (S, N + L - 1):
+        raise ValueError(f'conv_full returned {tuple(wet_full.shape)}, expected {(S, N + L - 1)}')
+    wet, carry = overlap_add_segments(wet_full, N)
+    incoming = exchange_carry(carry, rank, world, group)
+    flat = wet.reshape(-1)
+    flat[:incoming.shape[0]] += incoming          # fused into the receive epilogue on the GPU path
+    wet = flat.reshape(S, N)
+    return wet + dry if add_dry else wet

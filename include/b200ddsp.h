@@ -152,6 +152,13 @@ size_t b200ddsp_noise_workspace_bytes(const b200ddsp_handle* h, int B, int F, in
 int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
                     int N, int L, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same convolution with padding='valid': out_full [B, N + L - 1] = conv(audio, ir with
+ * ir[:,0]=0), no dry signal.  Building block of the multi-GPU timeline reverb, where the last
+ * L-1 samples of a segment are overlap-added into its successors (ddsp.core.fft_convolve with
+ * padding='valid', delay_compensation=0). */
+int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir, float* out_full,
+                         int B, int N, int L, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole DAG of modules/polyphonic_dag.py:21-42 as wired by configs/dafx22.gin:91-100,
  * entered at modules/piano_model.py:160: for every voice get_controls + get_signal of the
  * additive and noise processors, the running MultiAdd sum, then the reverb.

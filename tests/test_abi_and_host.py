@@ -1,0 +1,198 @@
+"""CPU-side tests: the C-ABI library builds, loads and exports every symbol the header
+declares (no compute calls -- there is no GPU here), and the host-side mirror of the
+reference's operator API behaves like ddsp's (DAG format, key strings, pattern match,
+error behaviour, no silent CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    import __graft_entry__
+    __graft_entry__.build()
+    from ddsp_piano_b200 import _lib
+    return _lib.LIB_PATH
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'b200ddsp.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(b200ddsp_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_declares_the_documented_surface():
+    names = header_functions()
+    for must in ['b200ddsp_create', 'b200ddsp_destroy', 'b200ddsp_additive_controls',
+                 'b200ddsp_additive_signal', 'b200ddsp_noise_controls', 'b200ddsp_noise_signal',
+                 'b200ddsp_reverb', 'b200ddsp_forward_polyphonic',
+                 'b200ddsp_forward_polyphonic_host', 'b200ddsp_last_error']:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in header_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.b200ddsp_version.restype = ctypes.c_int
+    assert lib.b200ddsp_version() == 100
+
+
+def test_python_binding_covers_the_header(lib_path):
+    from ddsp_piano_b200 import _lib
+    assert sorted(_lib.EXPORTS) == header_functions()
+    lib = _lib.load()
+    for n in _lib.EXPORTS:
+        assert getattr(lib, n).restype is not None or n == 'never'
+
+
+def test_struct_layouts_match_the_header():
+    from ddsp_piano_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'b200ddsp.h')).read()
+    cfg = re.search(r'typedef struct \{(.*?)\} b200ddsp_config;', text, flags=re.S).group(1)
+    cfg = re.sub(r'/\*.*?\*/', '', cfg, flags=re.S)
+    fields = re.findall(r'\b(?:int|float)\s+([a-z_0-9]+)\s*;', cfg)
+    assert fields == [f[0] for f in _lib.Config._fields_]
+    voice = re.search(r'typedef struct \{(.*?)\} b200ddsp_voice;', text, flags=re.S).group(1)
+    voice = re.sub(r'/\*.*?\*/', '', voice, flags=re.S)
+    vfields = re.findall(r'const float\*\s+([a-z_0-9]+)\s*;', voice)
+    assert vfields == [f[0] for f in _lib.Voice._fields_]
+    assert ctypes.sizeof(_lib.Voice) == 6 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_create_fails_loudly_without_a_gpu(lib_path):
+    """No CPU fallback: creating a handle without a CUDA device is an error, not a detour."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from ddsp_piano_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.Config(sample_rate=24000, frame_rate=250, min_frequency=20.0, additive_scale_fn=0,
+                      normalize_after_nyquist_cut=1, normalize_below_nyquist=1, inference=1,
+                      noise_scale_fn=0, noise_initial_bias=-5.0, noise_window_size=257,
+                      reverb_add_dry=1, n_noise_bands=64, fast_phase=0)
+    h = ctypes.c_void_p()
+    rc = lib.b200ddsp_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -4 and not h.value                      # B200DDSP_CUDA_ERROR
+    assert b'cuda' in lib.b200ddsp_last_error(None).lower()
+    import ddsp_piano_b200 as dp
+    synth = dp.MultiInharmonic(sample_rate=24000, inference=True)
+    z = torch.zeros(1, 4, 1)
+    with pytest.raises(RuntimeError):
+        synth.get_signal(z, torch.zeros(1, 4, 8), torch.zeros(1, 4, 8), z)
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, 'ddsp_piano_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src, os.path.join(dirpath, f)
+                assert '/root/reference' not in src
+
+
+# ------------------------------- operator API (host logic) ------------------------------------
+
+def test_polyphonic_dag_matches_reference_structure():
+    """modules/polyphonic_dag.py:21-42: node order, key strings, shared processor objects."""
+    import ddsp_piano_b200 as dp
+    additive = dp.MultiInharmonic(sample_rate=24000, inference=True, name='additive')
+    noise = dp.DynamicSizeFilteredNoise(sample_rate=24000, name='noise')
+    reverb = dp.Reverb(trainable=False)
+    dag = dp.polyphonic_dag(additive, noise, reverb,
+                            additive_controls=['amplitudes', 'harmonic_distribution',
+                                               'inharm_coef', 'f0_hz'],
+                            noise_controls=['magnitudes'], reverb_controls=['reverb_ir'],
+                            n_synths=3)
+    assert len(dag) == 3 * 3 + 1
+    assert dag[0] == (additive, ['amplitudes_0', 'harmonic_distribution_0', 'inharm_coef_0', 'f0_hz_0'])
+    assert dag[1] == (noise, ['magnitudes_0'])
+    assert dag[2][0].name == 'add' and dag[2][1] == ['noise/signal', 'additive/signal']
+    assert dag[5][1] == ['add/signal', 'noise/signal', 'additive/signal']
+    assert dag[3][0] is additive and dag[4][0] is noise and dag[5][0] is dag[2][0]
+    assert dag[-1] == (reverb, ['add/signal', 'reverb_ir'])
+    # default key names of the reference signature
+    d2 = dp.polyphonic_dag(additive, noise, n_synths=1)
+    assert d2[0][1] == ['amps_0', 'harmonic_distribution_0', 'f0_hz_0']
+    assert d2[1][1] == ['noise_magnitudes_0'] and len(d2) == 3
+
+
+def test_processor_group_plan_and_processors_order():
+    import ddsp_piano_b200 as dp
+    additive = dp.MultiInharmonic(sample_rate=16000, inference=True, name='additive')
+    noise = dp.DynamicSizeFilteredNoise(sample_rate=16000, name='noise')
+    kw = dict(additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+              noise_controls=['magnitudes'])
+    g = dp.ProcessorGroup(dp.polyphonic_dag(additive, noise, dp.Reverb(), reverb_controls=['reverb_ir'],
+                                            n_synths=4, **kw))
+    assert g._plan is not None and len(g._plan['voices']) == 4 and g._plan['ir_key'] == 'reverb_ir'
+    # processors in DAG order, additive and noise first (synthesize_from_csv.py:99)
+    assert [p.name for p in g.processors[:3]] == ['additive', 'noise', 'add']
+    assert dp.ProcessorGroup(dp.polyphonic_dag(additive, noise, n_synths=2, **kw))._plan['reverb'] is None
+    # not the polyphonic pattern -> node-by-node walk
+    assert dp.ProcessorGroup([(additive, ['a', 'b', 'c', 'd'])])._plan is None
+    assert dp.ProcessorGroup(dp.polyphonic_dag(additive, noise, n_synths=2, **kw), fused=False)._plan is None
+    # mismatched sample rates cannot be fused
+    other = dp.DynamicSizeFilteredNoise(sample_rate=24000, name='noise')
+    assert dp.ProcessorGroup(dp.polyphonic_dag(additive, other, n_synths=2, **kw))._plan is None
+
+
+def test_dag_walk_semantics_with_stub_processors():
+    """ddsp DAGLayer semantics: nested 'a/b' lookups, outputs stored under the processor name,
+    'out' aliases the last node, input dict is extended in place, training/mask kwargs dropped."""
+    import ddsp_piano_b200 as dp
+
+    class Gain(dp.Processor):
+        def __init__(self, g, name):
+            super().__init__(name=name)
+            self.g = g
+
+        def get_controls(self, x):
+            return {'x': x}
+
+        def get_signal(self, x):
+            return x * self.g
+
+    add = dp.MultiAdd(name='add')
+    group = dp.ProcessorGroup([(Gain(2.0, 'a'), ['in']), (Gain(3.0, 'b'), ['a/signal']),
+                               (add, ['a/signal', 'b/signal'])])
+    feats = {'in': np.array([1.0, 2.0])}
+    out = group(feats, return_outputs_dict=True, training=True)
+    np.testing.assert_array_equal(out['signal'], [8.0, 16.0])
+    assert out['controls'] is feats and feats['out'] is feats['add']
+    assert list(feats['add']['controls']) == ['signal_0', 'signal_1']
+    with pytest.raises(KeyError):
+        dp.nested_lookup('a/nope', feats)
+    assert np.array_equal(group({'in': np.array([1.0])}), [8.0])
+
+
+def test_scale_fn_and_constructor_contract():
+    import ddsp_piano_b200 as dp
+    from ddsp_piano_b200.engine import scale_fn_id
+    assert scale_fn_id(dp.exp_sigmoid) == 0 and scale_fn_id('exp_sigmoid') == 0
+    assert scale_fn_id(dp.exp_tanh) == 1 and scale_fn_id(None) == 2
+    with pytest.raises(ValueError):
+        scale_fn_id(lambda x: x)
+    s = dp.MultiInharmonic(frame_rate=250, sample_rate=24000, min_frequency=20, inference=True)
+    assert s.name == 'multi_inharmonic' and s.upsampling == 96 and s.sample_rate == 24000
+    assert dp.InHarmonic().name == 'inharmonic' and dp.InHarmonic().inference is False
+    n = dp.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=16000)
+    assert (n.upsampling, n.window_size, n.initial_bias, n.name) == (64, 257, -5.0, 'filtered_noise')
+    with pytest.raises(ValueError):
+        dp.Reverb(trainable=True)
+    with pytest.raises(ValueError):
+        dp.Reverb().get_controls(np.zeros([1, 4]))
+    # exp_sigmoid / exp_tanh called directly agree with the oracle's
+    import torch
+    from oracle import ddsp_core_np as core
+    from oracle import ddsp_piano_np as ref
+    x = np.linspace(-8, 8, 33).astype(np.float32)
+    np.testing.assert_allclose(dp.exp_sigmoid(torch.from_numpy(x)).numpy(), core.exp_sigmoid(x), rtol=2e-6)
+    np.testing.assert_allclose(dp.exp_tanh(torch.from_numpy(x)).numpy(), ref.exp_tanh(x), rtol=2e-5, atol=1e-9)

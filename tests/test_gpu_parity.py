@@ -386,3 +386,40 @@ def test_dag_host_entry_matches_device_entry(dp, dev):
         out = group(dict(feats), return_outputs_dict=True)
     torch.cuda.synchronize()
     assert torch.equal(out['signal'], results[0][0])
+
+
+def test_reverb_full_and_timeline(dp, dev):
+    """'valid'-padded convolution (b200ddsp_reverb_full) and the single-rank timeline
+    overlap-add built on it vs the reverb of the concatenated timeline (float64)."""
+    from ddsp_piano_b200 import sharding
+    from ddsp_piano_b200.processors import _DEFAULT_CFG
+    eng = dp.get_engine(dev, **{**_DEFAULT_CFG, 'sample_rate': 24000})
+    rng = np.random.default_rng(8)
+    S, N, L = 6, 2400, 2400
+    dry = (rng.standard_normal([S, N]) * 0.1).astype(np.float32)
+    ir = (rng.standard_normal([L]) * np.exp(-6 * np.arange(L) / L) * 1e-2).astype(np.float32)
+    full = eng.reverb_full(cu(dry, dev), cu(np.tile(ir, [S, 1]), dev))
+    assert full.shape == (S, N + L - 1)
+    h = ir.astype(np.float64).copy()
+    h[0] = 0
+    for i in range(S):
+        assert rel_err(full[i], np.convolve(dry[i].astype(np.float64), h).astype(np.float32)) < TIGHT
+    wet = sharding.timeline_reverb(cu(dry, dev), cu(ir, dev), eng.reverb_full)
+    x = dry.astype(np.float64).reshape(-1)
+    want = (np.convolve(x, h)[:x.size] + x).astype(np.float32).reshape(S, N)
+    assert rel_err(wet, want) < TIGHT
+
+
+def test_timeline_reverb_two_gpus_nccl():
+    """BASELINE config 4's exchange step on real GPUs (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+         '--master-addr', '127.0.0.1', '--master-port', '29517',
+         os.path.join(root, 'tests', 'multi_gpu_timeline.py')],
+        capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and 'TIMELINE_OK' in proc.stdout, proc.stdout + proc.stderr
