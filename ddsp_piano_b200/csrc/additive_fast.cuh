@@ -32,7 +32,9 @@ struct AdditivePlan;
 struct AdditiveFastArgs {
   AdditiveArgs a;                  // a.out: [P * sets, B, N] partial signals
   AdditivePlan* plan;              // bucket counts + work counters
-  const int* lists;                // [2][kMaxGroups][R * n_chunks] units by bucket
+  const int* lists;                // [kPlanSlots][kMaxGroups][R * n_chunks] units by slot and bucket
+  int slot;                        // work list to drain: 0 = phase ends (all voices),
+                                   // 1 + g = synthesis of voice group g
   int sp;                          // substrings per pass (1 or 2)
 };
 
@@ -318,30 +320,42 @@ __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, int na
 // proportional to the number of live partial groups.  additive_plan_kernel buckets the units by
 // that number so that the persistent kernels below can hand them out heaviest first (longest
 // processing time first: the tail of the launch is made of the cheapest units).
-constexpr int kMaxGroups = 4;     // H <= 128 on the fast path
+constexpr int kMaxGroups = 4;        // H <= 128 on the fast path
+constexpr int kMaxVoiceGroups = 8;   // voice groups of one forward (host-input pipelining)
+constexpr int kPlanSlots = 1 + kMaxVoiceGroups;
 
 struct AdditivePlan {
-  int count[2][kMaxGroups];   // [synth | ends][na - 1]  number of units in the bucket
-  int next[2];                // work counters of the two persistent kernels
+  int count[kPlanSlots][kMaxGroups];   // [slot][na - 1]  number of units in the bucket
+  int next[kPlanSlots];                // work counter of the persistent kernel draining the slot
   // zeroed by cudaMemsetAsync before every plan
+};
+
+struct PlanGroups {
+  int n_groups;
+  int first_voice[kMaxVoiceGroups + 1];
 };
 
 __global__ void __launch_bounds__(256) additive_plan_kernel(
     const unsigned char* __restrict__ synth_na, const unsigned char* __restrict__ ends_na,
-    AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks) {
-  // lists: [2][kMaxGroups][n_units]
+    AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks, int B,
+    const PlanGroups groups) {
+  // lists: [kPlanSlots][kMaxGroups][n_units]
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_units) return;
-  const int c = i % n_chunks;
+  const int row = i / n_chunks, c = i - row * n_chunks;
   const int ns = synth_na[i];
   if (ns > 0) {
-    const int pos = atomicAdd(&plan->count[0][ns - 1], 1);
-    lists[(size_t)(0 * kMaxGroups + ns - 1) * n_units + pos] = i;
+    const int v = row / B;
+    int g = 0;
+    while (g + 1 < groups.n_groups && v >= groups.first_voice[g + 1]) ++g;
+    const int slot = 1 + g;
+    const int pos = atomicAdd(&plan->count[slot][ns - 1], 1);
+    lists[(size_t)(slot * kMaxGroups + ns - 1) * n_units + pos] = i;
   }
   const int ne = ends_na[i];
   if (ne > 0 && c < n_chunks - 1) {
-    const int pos = atomicAdd(&plan->count[1][ne - 1], 1);
-    lists[(size_t)(1 * kMaxGroups + ne - 1) * n_units + pos] = i;
+    const int pos = atomicAdd(&plan->count[0][ne - 1], 1);
+    lists[(size_t)(0 * kMaxGroups + ne - 1) * n_units + pos] = i;
   }
 }
 
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const Additi
     for (int i = threadIdx.x; i < 2 * a.U; i += blockDim.x) win[i] = a.window[i];
     __syncthreads();
   }
-  const int kind = ENDS_ONLY ? 1 : 0;
+  const int kind = fa.slot;
   const int sets = a.S / SP;
   const int n_units = a.P * a.B * a.n_chunks;
   int bucket_end[kMaxGroups];   // cumulative item counts, heaviest bucket first

@@ -37,7 +37,7 @@ struct b200ddsp_handle {
   unsigned long long launches = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
   cudaEvent_t ev_group[8] = {};
-  cudaEvent_t ev_mags = nullptr, ev_ir = nullptr, ev_enter = nullptr;
+  cudaEvent_t ev_mags = nullptr, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
   cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
   cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
@@ -274,6 +274,7 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
     ok = ok && cudaEventCreateWithFlags(&h->ev_mags, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_ir, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       fail(nullptr, B200DDSP_CUDA_ERROR, "copy stream: %s", cudaGetErrorString(cudaGetLastError()));
       b200ddsp_destroy(h);
@@ -312,6 +313,7 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->ev_mags) cudaEventDestroy(h->ev_mags);
   if (h->ev_ir) cudaEventDestroy(h->ev_ir);
   if (h->ev_enter) cudaEventDestroy(h->ev_enter);
+  if (h->ev_small) cudaEventDestroy(h->ev_small);
   for (int i = 0; i < B200DDSP_N_STAGES; ++i) {
     if (h->ev_begin[i]) cudaEventDestroy(h->ev_begin[i]);
     if (h->ev_end[i]) cudaEventDestroy(h->ev_end[i]);
@@ -341,50 +343,50 @@ static int voice_groups_for(int P, int B, int n_chunks) {
   return G < P ? G : P;
 }
 
-// Scratch of the additive synth: chunk offsets, liveness tables, work lists, partial signals.
-struct AdditiveScratch {
-  size_t offsets, na_frame, synth_na, ends_na, plan, lists, partials, total;
-  int n_partials;   // partial signals [n_partials, B, N] the mixer has to sum
-  int sets;         // substring sets per voice on the fast path (1 on the generic path)
-};
-
 static int substrings_per_pass(int S) { return (S % 2 == 0) ? 2 : 1; }
 
-// P voices x B clips.  `fast` selects the layout of the partial signals: one per (voice, set) on
-// the fast path, one per voice group on the generic path.
-// with_outputs = false: the liveness tables and the partial signals live elsewhere (the
-// polyphonic forward keeps them in arrays shared by all of its voice groups).
-static AdditiveScratch carve_additive(int P, int B, int F, int H, int S, int U, bool fast, int G,
-                                      bool with_outputs = true) {
-  AdditiveScratch a{};
-  const size_t R = (size_t)P * B, N = (size_t)F * U;
-  const int n_chunks = (int)((N + kAngularChunk - 1) / kAngularChunk);
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
-  a.offsets = take(R * S * n_chunks * H * 4);
-  a.ends_na = take(R * n_chunks);
-  a.plan = take(sizeof(AdditivePlan));
-  a.lists = take((size_t)2 * kMaxGroups * R * n_chunks * 4);
-  a.sets = fast ? S / substrings_per_pass(S) : 1;
-  a.n_partials = fast ? P * a.sets : G;
-  if (with_outputs) {
-    a.na_frame = take(R * F);
-    a.synth_na = take(R * n_chunks);
-    a.partials = take((size_t)a.n_partials * B * N * 4);
-  }
-  a.total = o;
-  return a;
+// Device buffers of the additive synth for R = P*B rows (byte offsets into a workspace).
+struct AdditiveLayout {
+  size_t offsets;    // float [R*S, n_chunks, H]   chunk end phases, then chunk offsets
+  size_t na_frame;   // u8 [R, F]                  live partial groups per frame
+  size_t synth_na;   // u8 [R, n_chunks]           live partial groups per chunk
+  size_t ends_na;    // u8 [R, n_chunks]           groups whose end phase a later chunk needs
+  size_t plan;       // AdditivePlan
+  size_t lists;      // int [kPlanSlots][kMaxGroups][R * n_chunks]
+  size_t partials;   // float [n_partials, B, N]   partial signals for the mixer
+  size_t end;
+};
+
+// Partial signals: one per (voice, substring set) on the fast path, one per voice group on the
+// generic path; sized for the larger of the two so that the choice can be made at run time.
+static size_t max_partials(int P, int S) {
+  const size_t fast = (size_t)P * (S / substrings_per_pass(S));
+  return fast > (size_t)P ? fast : (size_t)P;
 }
 
-constexpr int kMaxCopyGroups = 8;
+static AdditiveLayout carve_additive(size_t at, int P, int B, int F, int H, int S, int U) {
+  AdditiveLayout a{};
+  const size_t R = (size_t)P * B, N = (size_t)F * U;
+  const size_t n_chunks = (N + kAngularChunk - 1) / kAngularChunk;
+  size_t o = at;
+  auto take = [&](size_t bytes) { size_t p = o; o += align_up(bytes); return p; };
+  a.offsets = take(R * S * n_chunks * H * 4);
+  a.na_frame = take(R * F);
+  a.synth_na = take(R * n_chunks);
+  a.ends_na = take(R * n_chunks);
+  a.plan = take(sizeof(AdditivePlan));
+  a.lists = take((size_t)kPlanSlots * kMaxGroups * R * n_chunks * 4);
+  a.partials = take(max_partials(P, S) * B * N * 4);
+  a.end = o;
+  return a;
+}
 
 // Voices are processed in `n_groups` consecutive groups (1 for device inputs; several for host
 // inputs, so that the H2D copies of one group overlap the kernels of the previous one).
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, taps, na_frame, synth_na, partials, tw, buf_a, buf_b, total;
-  size_t group_scratch[kMaxCopyGroups];
-  int n_groups, group_first[kMaxCopyGroups + 1];
-  int G;            // generic additive path: voice groups inside one launch (n_groups == 1 only)
+  size_t amp, hd, shifts, f0, taps, tw, buf_a, buf_b, total;
+  AdditiveLayout add;
+  PlanGroups groups;
   int n_chunks, nfft;
 };
 
@@ -395,28 +397,17 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
   w.n_chunks = n_chunks_for((int)N);
   if (n_groups > P) n_groups = P;
-  if (n_groups > kMaxCopyGroups) n_groups = kMaxCopyGroups;
+  if (n_groups > kMaxVoiceGroups) n_groups = kMaxVoiceGroups;
   if (n_groups < 1) n_groups = 1;
-  w.n_groups = n_groups;
-  for (int g = 0; g <= n_groups; ++g) w.group_first[g] = (int)((long long)P * g / n_groups);
-  w.G = (n_groups == 1) ? voice_groups_for(P, B, w.n_chunks) : 1;
+  w.groups.n_groups = n_groups;
+  for (int g = 0; g <= n_groups; ++g) w.groups.first_voice[g] = (int)((long long)P * g / n_groups);
   w.amp = take(R * F * 4);
   w.hd = take(R * F * H * 4);
   w.shifts = take(R * F * H * 4);
   w.f0 = take(R * F * S * 4);
   w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
-  w.na_frame = take(R * F);
-  w.synth_na = take(R * (size_t)w.n_chunks);
-  // partial signals: one per (voice, substring set) on the fast additive path, one per voice
-  // group on the generic one; sized for the larger layout
-  const size_t n_partials = (size_t)P * (S / substrings_per_pass(S));
-  w.partials = take((n_partials > (size_t)P ? n_partials : (size_t)P) * B * N * 4);
-  for (int g = 0; g < n_groups; ++g) {
-    const int Pg = w.group_first[g + 1] - w.group_first[g];
-    const size_t fast_b = carve_additive(Pg, B, F, H, S, U, true, w.G, false).total;
-    const size_t gen_b = carve_additive(Pg, B, F, H, S, U, false, w.G, false).total;
-    w.group_scratch[g] = take(fast_b > gen_b ? fast_b : gen_b);
-  }
+  w.add = carve_additive(o, P, B, F, H, S, U);
+  o = w.add.end;
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
     w.tw = take((size_t)w.nfft * 8);
@@ -430,15 +421,14 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
 extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H,
                                            int S, int M, int L) {
   if (!h || P < 1 || B < 1 || F < 1) return 0;
-  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 1 ? M : 2, L, h->U, env_int("B200DDSP_DEV_GROUPS", 1)).total;
+  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 1 ? M : 2, L, h->U,
+               env_int("B200DDSP_DEV_GROUPS", 1)).total;
 }
 
 extern "C" size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H,
                                                     int S) {
   if (!h || B < 1 || F < 1 || H < 1 || S < 1) return 0;
-  const size_t fast_b = carve_additive(1, B, F, H, S, h->U, true, 1).total;
-  const size_t gen_b = carve_additive(1, B, F, H, S, h->U, false, 1).total;
-  return fast_b > gen_b ? fast_b : gen_b;
+  return carve_additive(0, 1, B, F, H, S, h->U).end;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -456,19 +446,49 @@ static int check_common(b200ddsp_handle* h, int B, int F) {
   return B200DDSP_OK;
 }
 
-static void launch_additive_controls(const AdditiveControlsArgs& a, const AdditiveControlsPtrs& p,
-                                     int P, cudaStream_t st) {
+// get_controls = prep (amplitudes, shifts, f0 copy, liveness) + hd (harmonic distribution)
+static void launch_additive_prep(const AdditiveControlsArgs& a, const AdditiveControlsPtrs& p, int P,
+                                 cudaStream_t st) {
   const int warps_needed = (a.n_frames_voice + kFramesPerWarp - 1) / kFramesPerWarp;
   dim3 grid((warps_needed + 7) / 8, P);
   switch ((a.H + 31) / 32) {
-    case 1: additive_controls_kernel<1><<<grid, 256, 0, st>>>(a, p); break;
-    case 2: additive_controls_kernel<2><<<grid, 256, 0, st>>>(a, p); break;
-    case 3: additive_controls_kernel<3><<<grid, 256, 0, st>>>(a, p); break;
-    case 4: additive_controls_kernel<4><<<grid, 256, 0, st>>>(a, p); break;
+    case 1: additive_prep_kernel<1><<<grid, 256, 0, st>>>(a, p); break;
+    case 2: additive_prep_kernel<2><<<grid, 256, 0, st>>>(a, p); break;
+    case 3: additive_prep_kernel<3><<<grid, 256, 0, st>>>(a, p); break;
+    case 4: additive_prep_kernel<4><<<grid, 256, 0, st>>>(a, p); break;
     case 5:
-    case 6: additive_controls_kernel<6><<<grid, 256, 0, st>>>(a, p); break;
-    default: additive_controls_kernel<8><<<grid, 256, 0, st>>>(a, p); break;
+    case 6: additive_prep_kernel<6><<<grid, 256, 0, st>>>(a, p); break;
+    default: additive_prep_kernel<8><<<grid, 256, 0, st>>>(a, p); break;
   }
+}
+
+static void launch_additive_hd(const AdditiveControlsArgs& a, const AdditiveControlsPtrs& p, int P,
+                               cudaStream_t st) {
+  const int warps_needed = (a.n_frames_voice + kFramesPerWarp - 1) / kFramesPerWarp;
+  dim3 grid((warps_needed + 7) / 8, P);
+  switch ((a.H + 31) / 32) {
+    case 1: additive_hd_kernel<1><<<grid, 256, 0, st>>>(a, p); break;
+    case 2: additive_hd_kernel<2><<<grid, 256, 0, st>>>(a, p); break;
+    case 3: additive_hd_kernel<3><<<grid, 256, 0, st>>>(a, p); break;
+    case 4: additive_hd_kernel<4><<<grid, 256, 0, st>>>(a, p); break;
+    case 5:
+    case 6: additive_hd_kernel<6><<<grid, 256, 0, st>>>(a, p); break;
+    default: additive_hd_kernel<8><<<grid, 256, 0, st>>>(a, p); break;
+  }
+}
+
+static AdditiveControlsArgs controls_args(const b200ddsp_handle* h, int rows_per_voice_frames, int H,
+                                          int S) {
+  AdditiveControlsArgs a{};
+  a.n_frames_voice = rows_per_voice_frames;
+  a.H = H;
+  a.S = S;
+  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+  a.min_frequency = h->cfg.min_frequency;
+  a.scale_fn = h->cfg.additive_scale_fn;
+  a.normalize_after = h->cfg.normalize_after_nyquist_cut;
+  a.normalize_below = h->cfg.normalize_below_nyquist;
+  return a;
 }
 
 extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* amplitudes,
@@ -489,23 +509,104 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
   p.hd_in[0] = harmonic_distribution;
   p.inharm_in[0] = inharm_coef;
   p.f0_in[0] = f0_hz;
-  AdditiveControlsArgs a{};
+  AdditiveControlsArgs a = controls_args(h, rows * F, H, S);
   a.amp_out = amplitudes_out;
   a.hd_out = harmonic_distribution_out;
   a.shifts_out = harmonic_shifts_out;
   a.f0_out = nullptr;
   a.na_frame = nullptr;
-  a.n_frames_voice = rows * F;
-  a.H = H;
-  a.S = S;
-  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
-  a.min_frequency = h->cfg.min_frequency;
-  a.scale_fn = h->cfg.additive_scale_fn;
-  a.normalize_after = h->cfg.normalize_after_nyquist_cut;
-  a.normalize_below = h->cfg.normalize_below_nyquist;
-  launch_additive_controls(a, p, 1, (cudaStream_t)stream);
-  CHECK_LAUNCH(h, "additive_controls_kernel");
+  launch_additive_prep(a, p, 1, (cudaStream_t)stream);
+  CHECK_LAUNCH(h, "additive_prep_kernel");
+  launch_additive_hd(a, p, 1, (cudaStream_t)stream);
+  CHECK_LAUNCH(h, "additive_hd_kernel");
   return B200DDSP_OK;
+}
+
+static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
+  const int U = h->U;
+  return h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && H <= 32 * kMaxGroups &&
+         lerp_is_uniform(h, F, F * U, U);
+}
+
+// What the mixer needs to know about the additive partial signals.
+struct AdditiveResult {
+  const float* partials;        // [n_partials, B, N]
+  const unsigned char* live;    // [P*B, n_chunks] or nullptr
+  int n_partials, sets;
+};
+
+// One additive synthesis over stacked controls (R = P*B rows), split in the phases the
+// polyphonic forward interleaves with its copies:
+//   additive_begin        validate, choose fast/generic path, fill the kernel arguments
+//   additive_phase_pass   liveness per chunk, work lists, chunk end phases, chunk offsets
+//                         (needs f0, shifts and na_frame only -- not hd/amp)
+//   additive_synth_group  the oscillator bank of one voice group -> partial signals
+struct AdditiveRun {
+  AdditiveArgs a;
+  AdditiveFastArgs fa;
+  bool fast;
+  int sets, n_chunks, P, B, F, H, S, G;
+  unsigned char *na_frame, *synth_na, *ends_na;
+  PlanGroups groups;
+  float* partials;
+};
+
+static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, const float* hd,
+                          const float* shifts, const float* f0, char* base, const AdditiveLayout& lay,
+                          int P, int B, int F, int H, int S, const PlanGroups& groups) {
+  const int U = h->U, N = F * U;
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
+  r->fast = additive_fast_path(h, F, H);
+  if (!r->fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
+                F, N);
+  r->n_chunks = n_chunks_for(N);
+  if (r->n_chunks > 12 * 1024)
+    return fail(h, B200DDSP_BAD_SHAPE, "timeline of %d chunks is too long for one call", r->n_chunks);
+  r->P = P; r->B = B; r->F = F; r->H = H; r->S = S;
+  r->sets = r->fast ? S / substrings_per_pass(S) : 1;
+  r->groups = groups;
+  // generic path: voice groups inside one launch (only when the forward itself is not grouped)
+  r->G = (groups.n_groups == 1) ? voice_groups_for(P, B, r->n_chunks) : 1;
+  r->na_frame = (unsigned char*)(base + lay.na_frame);
+  r->synth_na = (unsigned char*)(base + lay.synth_na);
+  r->ends_na = (unsigned char*)(base + lay.ends_na);
+  r->partials = (float*)(base + lay.partials);
+  AdditiveArgs& a = r->a;
+  a = AdditiveArgs{};
+  a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
+  a.offsets = (float*)(base + lay.offsets);
+  a.out = r->partials;
+  a.window = h->d_window;
+  a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
+  a.chunk = kAngularChunk;
+  a.n_chunks = r->n_chunks;
+  a.voices_per_group = (P + r->G - 1) / r->G;
+  a.accumulate = 0;
+  a.scale = (float)F / (float)N;
+  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
+  a.sr = (float)h->cfg.sample_rate;
+  a.inv_sr = 1.0f / a.sr;
+  r->fa = AdditiveFastArgs{};
+  r->fa.a = a;
+  r->fa.plan = (AdditivePlan*)(base + lay.plan);
+  r->fa.lists = (int*)(base + lay.lists);
+  r->fa.sp = substrings_per_pass(S);
+  const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
+  if (!r->fast && smem > 48 * 1024)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
+  return B200DDSP_OK;
+}
+
+static AdditiveResult additive_result(const AdditiveRun& r) {
+  AdditiveResult res{};
+  res.partials = r.partials;
+  res.live = r.fast ? r.synth_na : nullptr;
+  res.sets = r.sets;
+  res.n_partials = r.fast ? r.P * r.sets : (r.groups.n_groups == 1 ? r.G : r.groups.n_groups);
+  return res;
 }
 
 template <int HP>
@@ -516,9 +617,11 @@ static void launch_additive_hp(const AdditiveArgs& a, bool ends_only, dim3 grid,
 }
 
 // generic path (any U, per-sample lerp frame, IEEE division)
-static void launch_additive_generic(const AdditiveArgs& a, int HP, bool ends_only, dim3 grid,
-                                    int threads, size_t smem, cudaStream_t st) {
-  switch (HP) {
+static void launch_additive_generic(const AdditiveArgs& a, bool ends_only, dim3 grid, cudaStream_t st) {
+  const int n_pairs = a.voices_per_group * a.S;
+  const int threads = 32 * (n_pairs < kAddWarps ? n_pairs : kAddWarps);
+  const size_t smem = (size_t)(((2 * a.U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
+  switch ((a.H + 31) / 32) {
     case 1: launch_additive_hp<1>(a, ends_only, grid, threads, smem, st); break;
     case 2: launch_additive_hp<2>(a, ends_only, grid, threads, smem, st); break;
     case 3: launch_additive_hp<3>(a, ends_only, grid, threads, smem, st); break;
@@ -529,149 +632,100 @@ static void launch_additive_generic(const AdditiveArgs& a, int HP, bool ends_onl
   }
 }
 
-static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, dim3 grid, int threads,
-                                 size_t smem, cudaStream_t st) {
+static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, int grid, size_t smem,
+                                 cudaStream_t st) {
   if (fa.sp == 2) {
-    if (ends_only) additive_fast_kernel<2, true><<<grid, threads, 0, st>>>(fa);
-    else additive_fast_kernel<2, false><<<grid, threads, smem, st>>>(fa);
+    if (ends_only) additive_fast_kernel<2, true><<<grid, kAddThreads, 0, st>>>(fa);
+    else additive_fast_kernel<2, false><<<grid, kAddThreads, smem, st>>>(fa);
   } else {
-    if (ends_only) additive_fast_kernel<1, true><<<grid, threads, 0, st>>>(fa);
-    else additive_fast_kernel<1, false><<<grid, threads, smem, st>>>(fa);
+    if (ends_only) additive_fast_kernel<1, true><<<grid, kAddThreads, 0, st>>>(fa);
+    else additive_fast_kernel<1, false><<<grid, kAddThreads, smem, st>>>(fa);
   }
 }
 
-static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
-  const int U = h->U;
-  return h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && H <= 32 * kMaxGroups &&
-         lerp_is_uniform(h, F, F * U, U);
+// persistent grids: every warp pulls work until its list is empty
+static int persistent_grid(const b200ddsp_handle* h, long long max_items, int ctas_per_sm) {
+  const long long want = (max_items + kAddWarps - 1) / kAddWarps;
+  const long long cap = (long long)h->n_sms * ctas_per_sm;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-struct AdditiveResult {
-  const float* partials;        // [n_partials, B, N]
-  const unsigned char* live;    // [P*B, n_chunks] or nullptr
-  int n_partials, sets;
-};
-
-// The launches of the additive synth over stacked controls (R = P*B rows): liveness scan + work
-// lists (fast path), chunk end phases, offsets scan, oscillator bank.  The result is a set of
-// partial signals in `scratch` for the mixer to sum.  na_frame_ready: the controls kernel has
-// already written the per-frame liveness.
-// Where the liveness tables and partial signals go when they are shared between several calls
-// (null members: inside `scratch`).
-struct AdditiveOutputs {
-  unsigned char* na_frame;   // [P*B, F]
-  unsigned char* synth_na;   // [P*B, n_chunks]
-  float* partials;           // [n_partials, B, N]
-};
-
-static int run_additive(b200ddsp_handle* h, const float* amp, const float* hd, const float* shifts,
-                        const float* f0, char* scratch, const AdditiveOutputs* ext, int P, int B,
-                        int F, int H, int S, int G, bool na_frame_ready, AdditiveResult* res,
-                        cudaStream_t st) {
-  const int U = h->U, N = F * U;
-  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
-  if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  const bool fast = additive_fast_path(h, F, H);
-  if (!fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
-    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
-                "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
-                F, N);
-  const int n_chunks = n_chunks_for(N);
-  const AdditiveScratch sc = carve_additive(P, B, F, H, S, U, fast, G, ext == nullptr);
-  AdditiveArgs a{};
-  a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
-  a.offsets = (float*)(scratch + sc.offsets);
-  a.out = ext ? ext->partials : (float*)(scratch + sc.partials);
-  a.window = h->d_window;
-  a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
-  a.chunk = kAngularChunk;
-  a.n_chunks = n_chunks;
-  a.voices_per_group = (P + G - 1) / G;
-  a.accumulate = 0;
-  a.scale = (float)F / (float)N;
-  a.nyquist = (float)(h->cfg.sample_rate / 2.0);
-  a.sr = (float)h->cfg.sample_rate;
-  a.inv_sr = 1.0f / a.sr;
-  res->partials = a.out;
-  res->n_partials = sc.n_partials;
-  res->sets = sc.sets;
-  res->live = nullptr;
-
-  if (fast) {
-    const int R = P * B;
-    unsigned char* na_frame = ext ? ext->na_frame : (unsigned char*)(scratch + sc.na_frame);
-    unsigned char* synth_na = ext ? ext->synth_na : (unsigned char*)(scratch + sc.synth_na);
-    unsigned char* ends_na = (unsigned char*)(scratch + sc.ends_na);
-    AdditivePlan* plan = (AdditivePlan*)(scratch + sc.plan);
-    int* lists = (int*)(scratch + sc.lists);
-    res->live = synth_na;
-    AdditiveFastArgs fa{};
-    fa.a = a;
-    fa.plan = plan;
-    fa.lists = lists;
-    fa.sp = substrings_per_pass(S);
+static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame_ready,
+                               cudaStream_t st) {
+  const AdditiveArgs& a = r.a;
+  const int R = r.P * r.B;
+  if (r.fast) {
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
       if (!na_frame_ready) {
-        additive_alive_frames_kernel<<<(R * F + 7) / 8, 256, 0, st>>>(amp, hd, na_frame, R * F, H);
+        additive_alive_frames_kernel<<<(R * r.F + 7) / 8, 256, 0, st>>>(a.amp, a.hd, r.na_frame,
+                                                                        R * r.F, r.H);
         CHECK_LAUNCH(h, "additive_alive_frames_kernel");
       }
-      if (n_chunks > 12 * 1024)
-        return fail(h, B200DDSP_BAD_SHAPE, "timeline of %d chunks is too long for one call", n_chunks);
-      additive_alive_chunks_kernel<<<R, 128, (size_t)n_chunks, st>>>(na_frame, synth_na, ends_na, F, U,
-                                                                    N, a.chunk, n_chunks);
+      additive_alive_chunks_kernel<<<R, 128, (size_t)r.n_chunks, st>>>(
+          r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks);
       CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
-      CUDA_TRY(h, cudaMemsetAsync(plan, 0, sizeof(AdditivePlan), st));
-      const int n_units = R * n_chunks;
-      additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(synth_na, ends_na, plan, lists,
-                                                                 n_units, n_chunks);
+      CUDA_TRY(h, cudaMemsetAsync(r.fa.plan, 0, sizeof(AdditivePlan), st));
+      const int n_units = R * r.n_chunks;
+      additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(
+          r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, n_units, r.n_chunks, r.B, r.groups);
       CHECK_LAUNCH(h, "additive_plan_kernel");
     }
-    // persistent grids: every warp pulls work until the lists are empty
-    const long long max_items = (long long)R * n_chunks * sc.sets;
-    const int sms = h->n_sms;
-    auto grid_for = [&](int ctas_per_sm) {
-      long long want = (max_items + kAddWarps - 1) / kAddWarps;
-      long long cap = (long long)sms * ctas_per_sm;
-      return (int)(want < cap ? (want > 0 ? want : 1) : cap);
-    };
-    const size_t smem = (size_t)(2 * U) * sizeof(float);
-    if (n_chunks > 1) {
+    if (r.n_chunks > 1) {
       {
         StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
-        launch_additive_fast(fa, true, dim3(grid_for(4)), kAddThreads, 0, st);
+        AdditiveFastArgs fa = r.fa;
+        fa.slot = 0;
+        launch_additive_fast(fa, true, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), 0, st);
         CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
       }
-      StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
-      const int n = R * S * H;
-      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, ends_na, R * S, n_chunks, H, S);
+      const int n = R * r.S * r.H;
+      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, r.ends_na, R * r.S,
+                                                               r.n_chunks, r.H, r.S);
       CHECK_LAUNCH(h, "additive_offsets_kernel");
     }
-    StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
-    launch_additive_fast(fa, false, dim3(grid_for(2)), kAddThreads, smem, st);
-    CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
     return B200DDSP_OK;
   }
-
-  const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
-  if (smem > 48 * 1024)
-    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "upsampling factor U=%d too large", U);
-  const int HP = (H + 31) / 32;
-  const int n_pairs = a.voices_per_group * S;
-  const int warps = n_pairs < kAddWarps ? n_pairs : kAddWarps;
-  if (n_chunks > 1) {
+  if (r.n_chunks > 1) {
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
-      launch_additive_generic(a, HP, true, dim3(n_chunks - 1, B, G), warps * 32, 0, st);
+      launch_additive_generic(a, true, dim3(r.n_chunks - 1, r.B, r.G), st);
       CHECK_LAUNCH(h, "additive_kernel<ends>");
     }
     StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
-    const int n = P * B * S * H;
-    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, nullptr, P * B * S, n_chunks, H, S);
+    const int n = R * r.S * r.H;
+    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, nullptr, R * r.S, r.n_chunks,
+                                                             r.H, r.S);
     CHECK_LAUNCH(h, "additive_offsets_kernel");
   }
+  return B200DDSP_OK;
+}
+
+static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaStream_t st) {
   StageTimer tm(h, B200DDSP_STAGE_OSCILLATORS, st);
-  launch_additive_generic(a, HP, false, dim3(n_chunks, B, G), warps * 32, smem, st);
+  const int v0 = r.groups.first_voice[g], Pg = r.groups.first_voice[g + 1] - v0;
+  if (r.fast) {
+    AdditiveFastArgs fa = r.fa;
+    fa.slot = 1 + g;
+    const size_t smem = (size_t)(2 * r.a.U) * sizeof(float);
+    launch_additive_fast(fa, false, persistent_grid(h, (long long)Pg * r.B * r.n_chunks * r.sets, 2),
+                         smem, st);
+    CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
+    return B200DDSP_OK;
+  }
+  // generic kernel over the group's rows; one partial signal per launch-internal voice group
+  AdditiveArgs a = r.a;
+  const size_t row0 = (size_t)v0 * r.B;
+  a.amp += row0 * r.F;
+  a.hd += row0 * r.F * r.H;
+  a.shifts += row0 * r.F * r.H;
+  a.f0 += row0 * r.F * r.S;
+  a.offsets += row0 * r.S * r.n_chunks * r.H;
+  a.P = Pg;
+  const int G = (r.groups.n_groups == 1) ? r.G : 1;
+  a.voices_per_group = (Pg + G - 1) / G;
+  a.out = r.partials + (size_t)(r.groups.n_groups == 1 ? 0 : g) * r.B * r.a.N;
+  launch_additive_generic(a, false, dim3(r.n_chunks, r.B, G), st);
   CHECK_LAUNCH(h, "additive_kernel<synth>");
   return B200DDSP_OK;
 }
@@ -686,17 +740,24 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  const size_t need = b200ddsp_additive_workspace_bytes(h, B, F, H, S);
-  if (!workspace || workspace_bytes < need)
+  const AdditiveLayout lay = carve_additive(0, 1, B, F, H, S, h->U);
+  if (!workspace || workspace_bytes < lay.end)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "additive_signal needs %zu workspace bytes, got %zu",
-                need, workspace_bytes);
+                lay.end, workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   reset_stage_flags(h);
-  AdditiveResult res{};
-  if (int rc = run_additive(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
-                            (char*)workspace, nullptr, 1, B, F, H, S, 1, false, &res, st))
+  PlanGroups groups{};
+  groups.n_groups = 1;
+  groups.first_voice[0] = 0;
+  groups.first_voice[1] = 1;
+  AdditiveRun run;
+  if (int rc = additive_begin(h, &run, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
+                              (char*)workspace, lay, 1, B, F, H, S, groups))
     return rc;
+  if (int rc = additive_phase_pass(h, run, false, st)) return rc;
+  if (int rc = additive_synth_group(h, run, 0, st)) return rc;
+  const AdditiveResult res = additive_result(run);
   PartialSumArgs ps{};
   ps.partials = res.partials;
   ps.live = res.live;
@@ -948,10 +1009,11 @@ extern "C" int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, cons
 // ---------------------------------------------------------------------------------------------
 
 // Optional cross-stream ordering for the host-input entry point: the main stream waits for
-// `group_ready[g]` before it touches the controls of voice group g, for `mags_ready` before the
-// noise stage and for `ir_ready` before the reverb.
+// `small_ready` before the prep kernel, `group_ready[g]` before it touches the harmonic
+// distribution of voice group g, `mags_ready` before the noise stage, `ir_ready` before the reverb.
 struct ForwardSync {
-  cudaEvent_t group_ready[kMaxCopyGroups];
+  cudaEvent_t small_ready;                      // amplitudes, inharm_coef, f0_hz of all voices
+  cudaEvent_t group_ready[kMaxVoiceGroups];     // harmonic_distribution of voice group g
   cudaEvent_t mags_ready, ir_ready;
 };
 
@@ -965,75 +1027,63 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   float* shifts = (float*)(base + w.shifts);
   float* f0 = (float*)(base + w.f0);
   float* taps = (float*)(base + w.taps);
-  const bool fast = additive_fast_path(h, F, H);
-  const int sets = fast ? S / substrings_per_pass(S) : 1;
 
   NoiseVoicePtrs vp{};
   NoiseTapsPtrs mp{};
+  AdditiveControlsPtrs cp{};
   for (int v = 0; v < P; ++v) {
     const b200ddsp_voice& vc = voices[v];
     if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
       return fail(h, B200DDSP_BAD_ARGUMENT, "voice %d has a null control tensor", v);
     mp.mags[v] = vc.magnitudes;
     vp.noise[v] = vc.noise;
+    cp.amp_in[v] = vc.amplitudes;
+    cp.hd_in[v] = vc.harmonic_distribution;
+    cp.inharm_in[v] = vc.inharm_coef;
+    cp.f0_in[v] = vc.f0_hz;
   }
   reset_stage_flags(h);
+  AdditiveRun run;
+  if (int rc = additive_begin(h, &run, amp, hd, shifts, f0, base, w.add, P, B, F, H, S, w.groups))
+    return rc;
+  AdditiveControlsArgs ca = controls_args(h, B * F, H, S);
+  ca.amp_out = amp; ca.hd_out = hd; ca.shifts_out = shifts; ca.f0_out = f0;
+  ca.na_frame = run.fast ? run.na_frame : nullptr;
 
-  AdditiveResult mix{};
-  mix.partials = (float*)(base + w.partials);
-  mix.live = fast ? (unsigned char*)(base + w.synth_na) : nullptr;
-  mix.sets = sets;
-  mix.n_partials = 0;
-  for (int g = 0; g < w.n_groups; ++g) {
-    const int v0 = w.group_first[g], Pg = w.group_first[g + 1] - v0;
-    const size_t row0 = (size_t)v0 * B;
-    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->group_ready[g], 0));
-    // get_controls of the group's voices -> stacked [P*B, F, .] rows (+ per-frame liveness of
-    // the partial groups on the fast path)
-    unsigned char* na_frame = fast ? (unsigned char*)(base + w.na_frame) + row0 * F : nullptr;
-    {
-      StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
-      AdditiveControlsPtrs cp{};
-      for (int i = 0; i < Pg; ++i) {
-        cp.amp_in[i] = voices[v0 + i].amplitudes;
-        cp.hd_in[i] = voices[v0 + i].harmonic_distribution;
-        cp.inharm_in[i] = voices[v0 + i].inharm_coef;
-        cp.f0_in[i] = voices[v0 + i].f0_hz;
-      }
-      AdditiveControlsArgs a{};
-      a.amp_out = amp + row0 * F;
-      a.hd_out = hd + row0 * F * H;
-      a.shifts_out = shifts + row0 * F * H;
-      a.f0_out = f0 + row0 * F * S;
-      a.na_frame = na_frame;
-      a.n_frames_voice = B * F;
-      a.H = H; a.S = S;
-      a.nyquist = (float)(h->cfg.sample_rate / 2.0);
-      a.min_frequency = h->cfg.min_frequency;
-      a.scale_fn = h->cfg.additive_scale_fn;
-      a.normalize_after = h->cfg.normalize_after_nyquist_cut;
-      a.normalize_below = h->cfg.normalize_below_nyquist;
-      launch_additive_controls(a, cp, Pg, st);
-      CHECK_LAUNCH(h, "additive_controls_kernel");
-    }
-    // additive oscillator bank of the group -> partial signals
-    AdditiveOutputs ext{};
-    ext.na_frame = na_frame;
-    ext.synth_na = (unsigned char*)(base + w.synth_na) + row0 * w.n_chunks;
-    ext.partials = (float*)(base + w.partials) + (size_t)mix.n_partials * B * N;
-    AdditiveResult part{};
-    if (int rc = run_additive(h, amp + row0 * F, hd + row0 * F * H, shifts + row0 * F * H,
-                              f0 + row0 * F * S, base + w.group_scratch[g], &ext, Pg, B, F, H, S, w.G,
-                              fast, &part, st))
-      return rc;
-    mix.n_partials += part.n_partials;
+  // 1. everything that does not need harmonic_distribution: amplitudes, inharmonic shifts,
+  //    liveness, then the phase pass of ALL voices (chunk end phases -> chunk offsets)
+  if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->small_ready, 0));
+  {
+    StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
+    launch_additive_prep(ca, cp, P, st);
+    CHECK_LAUNCH(h, "additive_prep_kernel");
   }
-  // noise of every voice + mix -> dry  (outputs['add']['signal']); FilteredNoise.get_controls is
-  // fused into the taps GEMM's operand load
+  if (int rc = additive_phase_pass(h, run, run.fast, st)) return rc;
+
+  // 2. per voice group: harmonic distribution, then the oscillator bank -> partial signals
+  for (int g = 0; g < w.groups.n_groups; ++g) {
+    const int v0 = w.groups.first_voice[g], Pg = w.groups.first_voice[g + 1] - v0;
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->group_ready[g], 0));
+    AdditiveControlsPtrs gp{};
+    for (int i = 0; i < Pg; ++i) {
+      gp.hd_in[i] = cp.hd_in[v0 + i];
+      gp.inharm_in[i] = cp.inharm_in[v0 + i];
+      gp.f0_in[i] = cp.f0_in[v0 + i];
+    }
+    AdditiveControlsArgs ga = ca;
+    ga.hd_out = hd + (size_t)v0 * B * F * H;
+    launch_additive_hd(ga, gp, Pg, st);
+    CHECK_LAUNCH(h, "additive_hd_kernel");
+    if (int rc = additive_synth_group(h, run, g, st)) return rc;
+  }
+  const AdditiveResult mix = additive_result(run);
+
+  // 3. noise of every voice + mix -> dry  (outputs['add']['signal']); FilteredNoise.get_controls
+  //    is fused into the taps GEMM's operand load
   if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->mags_ready, 0));
   if (int rc = run_noise(h, mp, h->cfg.noise_scale_fn, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, taps, st))
     return rc;
-  // reverb -> wet
+  // 4. reverb -> wet
   if (reverb_ir) {
     if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->ir_ready, 0));
     return run_reverb(h, dry_out, reverb_ir, wet_out, B, N, L, (float2*)(base + w.tw),
@@ -1101,7 +1151,7 @@ static HostStaging carve_host(int P, int B, int F, int H, int S, int M, int L, i
 }
 
 static int host_copy_groups(int P) {
-  const int g = env_int("B200DDSP_HOST_GROUPS", 3);
+  const int g = env_int("B200DDSP_HOST_GROUPS", 2);
   return P >= g ? g : P;
 }
 
@@ -1170,16 +1220,19 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
   CUDA_TRY(h, cudaEventRecord(h->ev_enter, st));
   CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_enter, 0));
   ForwardSync sync{};
-  for (int g = 0; g < w.n_groups; ++g) {
-    const int v0 = w.group_first[g], v1 = w.group_first[g + 1];
-    CUDA_TRY(h, copy_runs(v0, v1, BF, [&](int v) { return voices_host[v].amplitudes; },
-                          [&](int v) { return dev[v].amplitudes; }));
+  // small tensors of every voice first: they are all the phase pass needs
+  CUDA_TRY(h, copy_runs(0, P, BF, [&](int v) { return voices_host[v].amplitudes; },
+                        [&](int v) { return dev[v].amplitudes; }));
+  CUDA_TRY(h, copy_runs(0, P, BF, [&](int v) { return voices_host[v].inharm_coef; },
+                        [&](int v) { return dev[v].inharm_coef; }));
+  CUDA_TRY(h, copy_runs(0, P, BF * S, [&](int v) { return voices_host[v].f0_hz; },
+                        [&](int v) { return dev[v].f0_hz; }));
+  CUDA_TRY(h, cudaEventRecord(h->ev_small, cs));
+  sync.small_ready = h->ev_small;
+  for (int g = 0; g < w.groups.n_groups; ++g) {
+    const int v0 = w.groups.first_voice[g], v1 = w.groups.first_voice[g + 1];
     CUDA_TRY(h, copy_runs(v0, v1, BF * H, [&](int v) { return voices_host[v].harmonic_distribution; },
                           [&](int v) { return dev[v].harmonic_distribution; }));
-    CUDA_TRY(h, copy_runs(v0, v1, BF, [&](int v) { return voices_host[v].inharm_coef; },
-                          [&](int v) { return dev[v].inharm_coef; }));
-    CUDA_TRY(h, copy_runs(v0, v1, BF * S, [&](int v) { return voices_host[v].f0_hz; },
-                          [&](int v) { return dev[v].f0_hz; }));
     CUDA_TRY(h, cudaEventRecord(h->ev_group[g], cs));
     sync.group_ready[g] = h->ev_group[g];
   }
