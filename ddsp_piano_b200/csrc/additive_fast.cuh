@@ -17,8 +17,9 @@
 //      general  legacy-bilinear lerp per sample (7 FP32 ops in the chain)
 //    crossed with
 //      silent   every amplitude of the frame pair is zero: phase chain only
-//      live     amplitude cross-fade, Nyquist mask (cos_oscillator_bank, inharm_synth.py:65-67;
-//               per frame in steady frames, per sample otherwise), cos, accumulate
+//      nocheck  no sounding partial can reach Nyquist inside the frame: the per-sample mask of
+//               cos_oscillator_bank (inharm_synth.py:65-67) is elided
+//      check    with the mask (per frame in steady frames, per sample otherwise)
 //  * the unrolled body is 4 samples (not 32) so that the variants a SM executes concurrently
 //    stay inside the 32 KB instruction cache (the first version of this kernel spent its top
 //    stall reason on instruction fetch).
@@ -130,8 +131,8 @@ __device__ __forceinline__ void load_next_frame(const AdditiveArgs& a, int row, 
   }
 }
 
-enum { kAmpSilent = 0, kAmpLive = 1 };
-constexpr int kOscUnroll = 4;   // samples per unrolled body
+enum { kAmpSilent = 0, kAmpNoCheck = 1, kAmpCheck = 2 };
+constexpr int kOscUnroll = 4;   // samples per unrolled body of the synthesis pass
 
 // Shift frame k+1 into frame k, load the new k+1, derive the frame's variant.
 template <int NA, int SP, bool WITH_AMP>
@@ -144,29 +145,36 @@ __device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, in
     for (int s = 0; s < SP; ++s) st.F[q][s] = st.Fn[q][s];
   }
   load_next_frame<NA, SP, WITH_AMP>(a, row, s0, kn, lane, st);
-  bool all_steady = true, any_live = false;
+  bool all_steady = true, any_live = false, any_risky = false;
+  // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
+  // bottom - top, one in the product, one in the sum), hence the margin
+  const float nyq_lo = a.nyquist * (1.0f - 1e-6f);
 #pragma unroll
   for (int q = 0; q < NA; ++q) {
-    any_live |= WITH_AMP && (st.A[q] != 0.f || st.An[q] != 0.f);
+    const bool live = WITH_AMP && (st.A[q] != 0.f || st.An[q] != 0.f);
+    any_live |= live;
 #pragma unroll
     for (int s = 0; s < SP; ++s) {
       st.dF[q][s] = __fadd_rn(st.Fn[q][s], -st.F[q][s]);
       all_steady &= (st.dF[q][s] == 0.f);
       // omega of a steady frame: f = F + 0 * lerp = F
       st.om[q][s] = div_sr<true>(__fmul_rn(st.F[q][s], kTwoPi), a.sr, a.inv_sr);
+      any_risky |= live && (fmaxf(st.F[q][s], st.Fn[q][s]) >= nyq_lo);
     }
   }
   steady = __all_sync(0xffffffffu, all_steady);
-  amp_mode = (WITH_AMP && __any_sync(0xffffffffu, any_live)) ? kAmpLive : kAmpSilent;
+  amp_mode = kAmpSilent;
+  if (WITH_AMP && __any_sync(0xffffffffu, any_live))
+    amp_mode = __any_sync(0xffffffffu, any_risky) ? kAmpCheck : kAmpNoCheck;
 }
 
 // kOscUnroll consecutive samples (inside one control frame) of every chain of the lane.
 // win = shared Hann table positioned at the first sample's offset r inside the frame.
-template <int NA, int SP, bool STEADY, int AMP>
+template <int NA, int SP, bool STEADY, int AMP, int UNROLL>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
                                           const float* win, float tf, float kf,
                                           float (&y)[kOscUnroll]) {
-  static_assert(kOscUnroll == 4, "window loads are float4");
+  static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
   float wr[4] = {0.f, 0.f, 0.f, 0.f}, wf[4] = {0.f, 0.f, 0.f, 0.f};
   if (AMP != kAmpSilent) {   // r and U are multiples of 8: both loads are 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
@@ -176,14 +184,14 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
   }
   // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
   bool cut[NA][SP];
-  if (STEADY && AMP != kAmpSilent) {
+  if (STEADY && AMP == kAmpCheck) {
 #pragma unroll
     for (int q = 0; q < NA; ++q)
 #pragma unroll
       for (int s = 0; s < SP; ++s) cut[q][s] = st.F[q][s] >= a.nyquist;
   }
 #pragma unroll
-  for (int j = 0; j < kOscUnroll; ++j) {
+  for (int j = 0; j < UNROLL; ++j) {
     float frac = 0.f;
     if (!STEADY) {
       const float in = __fmul_rn(tf + (float)j, a.scale);   // legacy ResizeBilinear coordinate
@@ -191,8 +199,8 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
     }
     float w0 = 0.f, w1 = 0.f;
     if (AMP != kAmpSilent) {
-      w0 = wr[j];          // rising half of hann(2U): weight of frame k+1
-      w1 = wf[j];          // falling half: weight of frame k
+      w0 = wr[j & 3];      // rising half of hann(2U): weight of frame k+1
+      w1 = wf[j & 3];      // falling half: weight of frame k
     }
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
@@ -209,10 +217,13 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
         }
         st.ph[q][s] = __fadd_rn(st.ph[q][s], om);                              // cumsum
         if (AMP != kAmpSilent) {
-          const bool above = STEADY ? cut[q][s] : (f >= a.nyquist);            // :65-67
-          const float amp = above ? 0.f : amp_q;
+          float amp = amp_q;
+          if (AMP == kAmpCheck) {
+            const bool above = STEADY ? cut[q][s] : (f >= a.nyquist);          // :65-67
+            amp = above ? 0.f : amp_q;
+          }
           const float p = wrap_to_pi(__fadd_rn(st.ph[q][s], st.off[q][s]));
-          y[j] = __fmaf_rn(amp, __cosf(p), y[j]);                              // :80-83
+          y[j & 3] = __fmaf_rn(amp, __cosf(p), y[j & 3]);                      // :80-83
         }
       }
     }
@@ -264,7 +275,8 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
         st.off[q][s] = a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h];
     }
   float tf = (float)t0;
-  for (int t = t0; t < t1; t += kOscUnroll, r += kOscUnroll, tf += (float)kOscUnroll) {
+  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
+  for (int t = t0; t < t1; t += STEP, r += STEP, tf += (float)STEP) {
     if (r == a.U) {
       r = 0;
       ++k;
@@ -276,12 +288,17 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
     const float kf = (float)k;
     const float* w = win + r;
     if (ENDS_ONLY || amp_mode == kAmpSilent) {
-      if (steady) osc_group<NA, SP, true, kAmpSilent>(a, st, w, tf, kf, y);
-      else osc_group<NA, SP, false, kAmpSilent>(a, st, w, tf, kf, y);
+      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, tf, kf, y);
+      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, tf, kf, y);
       if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
     } else {
-      if (steady) osc_group<NA, SP, true, kAmpLive>(a, st, w, tf, kf, y);
-      else osc_group<NA, SP, false, kAmpLive>(a, st, w, tf, kf, y);
+      if (amp_mode == kAmpNoCheck) {
+        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll>(a, st, w, tf, kf, y);
+        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll>(a, st, w, tf, kf, y);
+      } else {
+        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll>(a, st, w, tf, kf, y);
+        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll>(a, st, w, tf, kf, y);
+      }
       const float v = transpose_reduce4(y, lane);
       if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
     }

@@ -48,6 +48,7 @@ class Engine:
                 f'b200ddsp_create: {_lib.STATUS_NAMES.get(rc, rc)}: {msg}')
         self._workspace = None
         self._host_out = {}
+        self._ws_sizes = {}
         self._keep_alive = None
 
     def __del__(self):
@@ -209,68 +210,89 @@ class Engine:
                           ws.data_ptr(), ws.numel(), self.stream()))
         return out
 
-    def forward_polyphonic_host(self, voices, reverb_ir=None, seed=0, want_dry=True):
-        """Same as forward_polyphonic for HOST tensors (pinned memory recommended): the H2D
-        copies are staged group by group and overlap the kernels; returns pinned host tensors
-        (dry or None, wet or None) that are valid once the current stream has been synchronised
-        and are REUSED by the next call on this engine."""
+    def _voice_array(self, voices, host):
+        """Validate the per-voice control tensors and fill the b200ddsp_voice array.  This runs
+        on every forward, ahead of the first kernel launch, so the common case (float32,
+        contiguous, right device) is checked without conversions."""
         P = len(voices)
         if P < 1 or P > _lib.MAX_VOICES:
             raise ValueError(f'n_synths={P} outside [1, {_lib.MAX_VOICES}]')
         arr = (_lib.Voice * P)()
         keep = []
-        B = F = H = S = M = None
+        dev = torch.device('cpu') if host else self.device
+        f32 = torch.float32
+        v0 = voices[0]
+        hd0 = v0['harmonic_distribution']
+        if not isinstance(hd0, torch.Tensor) or hd0.dim() != 3:
+            hd0 = _host_tensor(hd0, 'harmonic_distribution_0', 3) if host else \
+                self.tensor(hd0, 'harmonic_distribution_0', 3)
+        B, F, H = hd0.shape
+        f00 = v0['f0_hz'] if isinstance(v0['f0_hz'], torch.Tensor) else torch.as_tensor(v0['f0_hz'])
+        m0 = v0['magnitudes'] if isinstance(v0['magnitudes'], torch.Tensor) else \
+            torch.as_tensor(v0['magnitudes'])
+        S, M = f00.shape[-1], m0.shape[-1]
+        N = F * self.upsampling
+        want = (('amplitudes', (B, F, 1)), ('harmonic_distribution', (B, F, H)),
+                ('inharm_coef', (B, F, 1)), ('f0_hz', (B, F, S)), ('magnitudes', (B, F, M)))
         any_noise = False
         for i, v in enumerate(voices):
-            amp = _host_tensor(v['amplitudes'], f'amplitudes_{i}', 3)
-            hd = _host_tensor(v['harmonic_distribution'], f'harmonic_distribution_{i}', 3)
-            inh = _host_tensor(v['inharm_coef'], f'inharm_coef_{i}', 3)
-            f0 = _host_tensor(v['f0_hz'], f'f0_hz_{i}', 3)
-            mag = _host_tensor(v['magnitudes'], f'magnitudes_{i}', 3)
-            if i == 0:
-                B, F, H = hd.shape
-                S, M = f0.shape[-1], mag.shape[-1]
-            want = {'amplitudes': (B, F, 1), 'harmonic_distribution': (B, F, H),
-                    'inharm_coef': (B, F, 1), 'f0_hz': (B, F, S), 'magnitudes': (B, F, M)}
-            for t, k in ((amp, 'amplitudes'), (hd, 'harmonic_distribution'),
-                         (inh, 'inharm_coef'), (f0, 'f0_hz'), (mag, 'magnitudes')):
-                if tuple(t.shape) != want[k]:
-                    raise ValueError(f'{k}_{i} has shape {tuple(t.shape)}, expected {want[k]}')
+            ptrs = []
+            for k, shape in want:
+                t = v[k]
+                if not (isinstance(t, torch.Tensor) and t.dtype is f32 and t.device == dev
+                        and t.is_contiguous()):
+                    t = _host_tensor(t, f'{k}_{i}') if host else self.tensor(t, f'{k}_{i}')
+                if tuple(t.shape) != shape:
+                    raise ValueError(f'{k}_{i} has shape {tuple(t.shape)}, expected {shape}')
+                keep.append(t)
+                ptrs.append(t.data_ptr())
             nz = v.get('noise')
             if nz is not None:
-                nz = _host_tensor(nz, f'noise_{i}', 2)
-                if tuple(nz.shape) != (B, F * self.upsampling):
-                    raise ValueError(f'noise_{i} has shape {tuple(nz.shape)}')
+                nz = _host_tensor(nz, f'noise_{i}', 2) if host else self.tensor(nz, f'noise_{i}', 2)
+                if tuple(nz.shape) != (B, N):
+                    raise ValueError(f'noise_{i} has shape {tuple(nz.shape)}, expected {(B, N)}')
+                keep.append(nz)
                 any_noise = True
-            keep += [amp, hd, inh, f0, mag, nz]
-            arr[i] = _lib.Voice(amp.data_ptr(), hd.data_ptr(), inh.data_ptr(), f0.data_ptr(),
-                                mag.data_ptr(), nz.data_ptr() if nz is not None else None)
-        N = F * self.upsampling
+            arr[i] = _lib.Voice(*ptrs, nz.data_ptr() if nz is not None else None)
+        return arr, keep, (P, B, F, H, S, M, N), any_noise
+
+    def _impulse_response(self, reverb_ir, B, host):
+        ir = _host_tensor(reverb_ir, 'reverb_ir') if host else self.tensor(reverb_ir, 'reverb_ir')
+        if ir.dim() == 1:
+            ir = ir[None, :]
+        if ir.dim() == 3:
+            ir = ir[:, :, 0].contiguous()
+        if ir.shape[0] == 1 and B > 1:
+            ir = ir.expand(B, -1).contiguous()
+        if ir.shape[0] != B:
+            raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
+                             'be the same.'.format(B, ir.shape[0]))
+        return ir
+
+    def forward_polyphonic_host(self, voices, reverb_ir=None, seed=0, want_dry=True):
+        """Same as forward_polyphonic for HOST tensors (pinned memory recommended): the H2D
+        copies are staged group by group and overlap the kernels; returns pinned host tensors
+        (dry or None, wet or None) that are valid once the current stream has been synchronised
+        and are REUSED by the next call on this engine."""
+        arr, keep, (P, B, F, H, S, M, N), any_noise = self._voice_array(voices, host=True)
         L = 0
         ir = None
         if reverb_ir is not None:
-            ir = _host_tensor(reverb_ir, 'reverb_ir')
-            if ir.dim() == 1:
-                ir = ir[None, :]
-            if ir.dim() == 3:
-                ir = ir[:, :, 0].contiguous()
-            if ir.shape[0] == 1 and B > 1:
-                ir = ir.expand(B, -1).contiguous()
-            if ir.shape[0] != B:
-                raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
-                                 'be the same.'.format(B, ir.shape[0]))
+            ir = self._impulse_response(reverb_ir, B, host=True)
             L = ir.shape[1]
-        nbytes = self.lib.b200ddsp_workspace_bytes_host(self.handle, P, B, F, H, S, M, L,
-                                                        int(any_noise))
+        key = ('host', P, B, F, H, S, M, L, any_noise)
+        nbytes = self._ws_sizes.get(key)
+        if nbytes is None:
+            nbytes = self._ws_sizes[key] = self.lib.b200ddsp_workspace_bytes_host(
+                self.handle, P, B, F, H, S, M, L, int(any_noise))
         ws = self.workspace(nbytes)
-        key = (B, N)
-        bufs = self._host_out.get(key)
+        bufs = self._host_out.get((B, N))
         if bufs is None:
-            bufs = self._host_out[key] = (torch.empty([B, N], dtype=torch.float32).pin_memory(),
-                                          torch.empty([B, N], dtype=torch.float32).pin_memory())
+            bufs = self._host_out[(B, N)] = (torch.empty([B, N], dtype=torch.float32).pin_memory(),
+                                             torch.empty([B, N], dtype=torch.float32).pin_memory())
         dry = bufs[0] if (want_dry or ir is None) else None
         wet = bufs[1] if ir is not None else None
-        self._keep_alive = keep + [ir]       # host buffers must outlive the enqueued copies
+        self._keep_alive = (keep, ir)        # host buffers must outlive the enqueued copies
         with torch.cuda.device(self.device):
             self.check(self.lib.b200ddsp_forward_polyphonic_host(
                 self.handle, arr, P, ir.data_ptr() if ir is not None else None,
@@ -282,51 +304,17 @@ class Engine:
     def forward_polyphonic(self, voices, reverb_ir=None, seed=0):
         """voices: list of dicts with keys amplitudes, harmonic_distribution, inharm_coef,
         f0_hz, magnitudes and optionally noise.  Returns (dry, wet or None)."""
-        P = len(voices)
-        if P < 1 or P > _lib.MAX_VOICES:
-            raise ValueError(f'n_synths={P} outside [1, {_lib.MAX_VOICES}]')
-        arr = (_lib.Voice * P)()
-        keep = []
-        B = F = H = S = M = None
-        for i, v in enumerate(voices):
-            amp = self.tensor(v['amplitudes'], f'amplitudes_{i}', 3)
-            hd = self.tensor(v['harmonic_distribution'], f'harmonic_distribution_{i}', 3)
-            inh = self.tensor(v['inharm_coef'], f'inharm_coef_{i}', 3)
-            f0 = self.tensor(v['f0_hz'], f'f0_hz_{i}', 3)
-            mag = self.tensor(v['magnitudes'], f'magnitudes_{i}', 3)
-            if i == 0:
-                B, F, H = hd.shape
-                S, M = f0.shape[-1], mag.shape[-1]
-            want = {'amplitudes': (B, F, 1), 'harmonic_distribution': (B, F, H),
-                    'inharm_coef': (B, F, 1), 'f0_hz': (B, F, S), 'magnitudes': (B, F, M)}
-            for t, k in ((amp, 'amplitudes'), (hd, 'harmonic_distribution'),
-                         (inh, 'inharm_coef'), (f0, 'f0_hz'), (mag, 'magnitudes')):
-                if tuple(t.shape) != want[k]:
-                    raise ValueError(f'{k}_{i} has shape {tuple(t.shape)}, expected {want[k]}')
-            nz = v.get('noise')
-            if nz is not None:
-                nz = self.tensor(nz, f'noise_{i}', 2)
-                if tuple(nz.shape) != (B, F * self.upsampling):
-                    raise ValueError(f'noise_{i} has shape {tuple(nz.shape)}')
-            keep += [amp, hd, inh, f0, mag, nz]
-            arr[i] = _lib.Voice(amp.data_ptr(), hd.data_ptr(), inh.data_ptr(), f0.data_ptr(),
-                                mag.data_ptr(), nz.data_ptr() if nz is not None else None)
-        N = F * self.upsampling
+        arr, keep, (P, B, F, H, S, M, N), _ = self._voice_array(voices, host=False)
         L = 0
         ir = None
         if reverb_ir is not None:
-            ir = self.tensor(reverb_ir, 'reverb_ir')
-            if ir.dim() == 1:
-                ir = ir[None, :]
-            if ir.dim() == 3:
-                ir = ir[:, :, 0].contiguous()
-            if ir.shape[0] == 1 and B > 1:
-                ir = ir.expand(B, -1).contiguous()
-            if ir.shape[0] != B:
-                raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
-                                 'be the same.'.format(B, ir.shape[0]))
+            ir = self._impulse_response(reverb_ir, B, host=False)
             L = ir.shape[1]
-        nbytes = self.lib.b200ddsp_workspace_bytes(self.handle, P, B, F, H, S, M, L)
+        key = ('dev', P, B, F, H, S, M, L)
+        nbytes = self._ws_sizes.get(key)
+        if nbytes is None:
+            nbytes = self._ws_sizes[key] = self.lib.b200ddsp_workspace_bytes(
+                self.handle, P, B, F, H, S, M, L)
         ws = self.workspace(nbytes)
         dry = torch.empty([B, N], dtype=torch.float32, device=self.device)
         wet = torch.empty_like(dry) if ir is not None else None

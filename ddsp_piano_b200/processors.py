@@ -325,11 +325,13 @@ class ProcessorGroup:
         plan = self._plan
         additive, noise, reverb = plan['additive'], plan['noise'], plan['reverb']
         voices = []
+        def get(k):
+            return outputs[k] if k in outputs else nested_lookup(k, outputs)
+
         for add_keys, mag_key in plan['voices']:
-            amp, hd, inh, f0 = (nested_lookup(k, outputs) for k in add_keys)
-            voices.append({'amplitudes': amp, 'harmonic_distribution': hd, 'inharm_coef': inh,
-                           'f0_hz': f0, 'magnitudes': nested_lookup(mag_key, outputs),
-                           'noise': noise.pop_noise()})
+            voices.append({'amplitudes': get(add_keys[0]), 'harmonic_distribution': get(add_keys[1]),
+                           'inharm_coef': get(add_keys[2]), 'f0_hz': get(add_keys[3]),
+                           'magnitudes': get(mag_key), 'noise': noise.pop_noise()})
         M = voices[0]['magnitudes'].shape[-1]
         cfg = {**_DEFAULT_CFG, **additive.engine_config(), **noise.engine_config(M)}
         if reverb is not None:
