@@ -170,7 +170,15 @@ __device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, in
 
 // kOscUnroll consecutive samples (inside one control frame) of every chain of the lane.
 // win = shared Hann table positioned at the first sample's offset r inside the frame.
-template <int NA, int SP, bool STEADY, int AMP, int UNROLL>
+// cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
+// reduce modulo the true 2 pi in double precision, then the hardware cosine.
+__device__ __forceinline__ float cos_large(float x) {
+  const double xd = (double)x;
+  const double n = rint(xd * 0.15915494309189535);
+  return __cosf((float)fma(-n, 6.283185307179586, xd));
+}
+
+template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
                                           const float* win, float tf, float kf,
                                           float (&y)[kOscUnroll]) {
@@ -222,8 +230,13 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
             const bool above = STEADY ? cut[q][s] : (f >= a.nyquist);          // :65-67
             amp = above ? 0.f : amp_q;
           }
-          const float p = wrap_to_pi(__fadd_rn(st.ph[q][s], st.off[q][s]));
-          y[j & 3] = __fmaf_rn(amp, __cosf(p), y[j & 3]);                      // :80-83
+          float c;
+          if (PLAIN) {
+            c = cos_large(st.ph[q][s]);                                        // tf.cos(tf.cumsum)
+          } else {
+            c = __cosf(wrap_to_pi(__fadd_rn(st.ph[q][s], st.off[q][s])));
+          }
+          y[j & 3] = __fmaf_rn(amp, c, y[j & 3]);                              // :80-83
         }
       }
     }
@@ -251,7 +264,7 @@ __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
 
 // One (row, substring set, chunk) on one warp.  ENDS_ONLY: phase chain only, writes the chunk
 // end phases; otherwise writes the audio of the chunk to `row_out` (global memory).
-template <int NA, int SP, bool ENDS_ONLY>
+template <int NA, int SP, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0, int c, int lane,
                                           const float* win, float* row_out) {
   const int t0 = c * a.chunk;
@@ -293,11 +306,11 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
       if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
     } else {
       if (amp_mode == kAmpNoCheck) {
-        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll>(a, st, w, tf, kf, y);
-        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll>(a, st, w, tf, kf, y);
+        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
+        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
       } else {
-        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll>(a, st, w, tf, kf, y);
-        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll>(a, st, w, tf, kf, y);
+        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
+        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
       }
       const float v = transpose_reduce4(y, lane);
       if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
@@ -316,15 +329,15 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
   }
 }
 
-template <int SP, bool ENDS_ONLY>
+template <int SP, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, int na, int row, int s0,
                                                    int c, int lane, const float* win, float* row_out) {
   switch (na) {
     case 0: break;
-    case 1: osc_chunk<1, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
-    case 2: osc_chunk<2, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
-    case 3: osc_chunk<3, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
-    case 4: osc_chunk<4, SP, ENDS_ONLY>(a, row, s0, c, lane, win, row_out); break;
+    case 1: osc_chunk<1, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
+    case 2: osc_chunk<2, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
+    case 3: osc_chunk<3, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
+    case 4: osc_chunk<4, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
     default:
       // more than 128 live partials: two passes over the chunk are not implemented here; the
       // host routes H > 128 to the generic kernel
@@ -381,7 +394,7 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
 // a warp that drew cheap items simply draws more of them.  Each item writes its own region of
 // `out` ([P * sets, B, N] partial signals, summed in a fixed order by the mixer), which keeps the
 // result independent of the scheduling order.
-template <int SP, bool ENDS_ONLY>
+template <int SP, bool ENDS_ONLY, bool PLAIN = false>
 __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const Additi
     const int v = row / a.B, b = row - v * a.B;
     float* out = ENDS_ONLY ? nullptr
                            : a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-    osc_chunk_dispatch<SP, ENDS_ONLY>(a, na, row, set * SP, c, lane, win, out);
+    osc_chunk_dispatch<SP, ENDS_ONLY, PLAIN>(a, na, row, set * SP, c, lane, win, out);
   }
 }
 

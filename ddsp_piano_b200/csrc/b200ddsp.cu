@@ -208,9 +208,6 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
                 cfg->sample_rate, cfg->frame_rate);
   if (cfg->fast_phase != 0)
     return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "fast_phase is not implemented");
-  if (cfg->inference == 0)
-    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG,
-                "inference=0 (plain cumsum, training mode) is not implemented yet");
   for (int fn : {cfg->additive_scale_fn, cfg->noise_scale_fn})
     if (fn < 0 || fn > 2) return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "bad scale_fn %d", fn);
   const int M = cfg->n_noise_bands;
@@ -334,7 +331,14 @@ static int fft_size_for(int N, int L) {
 
 static int tap_pitch_for(int M) { return (M - 1 + 3) & ~3; }
 
-static int n_chunks_for(int N) { return (N + kAngularChunk - 1) / kAngularChunk; }
+// ddsp.core.angular_cumsum wraps the phase every 1000 samples (inference=True); with
+// inference=False the reference uses one plain cumsum over the clip (inharm_synth.py:73-77):
+// a single "chunk" of N samples.
+static int chunk_for(const b200ddsp_handle* h, int N) { return h->cfg.inference ? kAngularChunk : N; }
+static int n_chunks_for(const b200ddsp_handle* h, int N) {
+  const int c = chunk_for(h, N);
+  return (N + c - 1) / c;
+}
 
 // Voice groups: split the voices over gridDim.z until the grid fills the GPU.
 static int voice_groups_for(int P, int B, int n_chunks) {
@@ -364,10 +368,12 @@ static size_t max_partials(int P, int S) {
   return fast > (size_t)P ? fast : (size_t)P;
 }
 
-static AdditiveLayout carve_additive(size_t at, int P, int B, int F, int H, int S, int U) {
+static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P, int B, int F, int H,
+                                     int S) {
   AdditiveLayout a{};
+  const int U = h->U;
   const size_t R = (size_t)P * B, N = (size_t)F * U;
-  const size_t n_chunks = (N + kAngularChunk - 1) / kAngularChunk;
+  const size_t n_chunks = (size_t)n_chunks_for(h, (int)N);
   size_t o = at;
   auto take = [&](size_t bytes) { size_t p = o; o += align_up(bytes); return p; };
   a.offsets = take(R * S * n_chunks * H * 4);
@@ -390,12 +396,14 @@ struct WorkspaceLayout {
   int n_chunks, nfft;
 };
 
-static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, int U, int n_groups) {
+static WorkspaceLayout carve(const b200ddsp_handle* h, int P, int B, int F, int H, int S, int M, int L,
+                             int n_groups) {
   WorkspaceLayout w{};
+  const int U = h->U;
   const size_t R = (size_t)P * B, N = (size_t)F * U;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
-  w.n_chunks = n_chunks_for((int)N);
+  w.n_chunks = n_chunks_for(h, (int)N);
   if (n_groups > P) n_groups = P;
   if (n_groups > kMaxVoiceGroups) n_groups = kMaxVoiceGroups;
   if (n_groups < 1) n_groups = 1;
@@ -406,7 +414,7 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
   w.shifts = take(R * F * H * 4);
   w.f0 = take(R * F * S * 4);
   w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
-  w.add = carve_additive(o, P, B, F, H, S, U);
+  w.add = carve_additive(h, o, P, B, F, H, S);
   o = w.add.end;
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
@@ -421,14 +429,14 @@ static WorkspaceLayout carve(int P, int B, int F, int H, int S, int M, int L, in
 extern "C" size_t b200ddsp_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H,
                                            int S, int M, int L) {
   if (!h || P < 1 || B < 1 || F < 1) return 0;
-  return carve(P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 1 ? M : 2, L, h->U,
+  return carve(h, P, B, F, H > 0 ? H : 1, S > 0 ? S : 1, M > 1 ? M : 2, L,
                env_int("B200DDSP_DEV_GROUPS", 1)).total;
 }
 
 extern "C" size_t b200ddsp_additive_workspace_bytes(const b200ddsp_handle* h, int B, int F, int H,
                                                     int S) {
   if (!h || B < 1 || F < 1 || H < 1 || S < 1) return 0;
-  return carve_additive(0, 1, B, F, H, S, h->U).end;
+  return carve_additive(h, 0, 1, B, F, H, S).end;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -524,7 +532,7 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
 
 static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
   const int U = h->U;
-  return h->fast_div && (U % 8 == 0) && (kAngularChunk % 8 == 0) && H <= 32 * kMaxGroups &&
+  return h->fast_div && (U % 8 == 0) && (chunk_for(h, F * U) % 8 == 0) && H <= 32 * kMaxGroups &&
          lerp_is_uniform(h, F, F * U, U);
 }
 
@@ -562,7 +570,11 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
                 F, N);
-  r->n_chunks = n_chunks_for(N);
+  r->n_chunks = n_chunks_for(h, N);
+  if (!r->fast && !h->cfg.inference)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "inference=0 (plain cumsum) is implemented on the fast additive path only "
+                "(U %% 8 == 0, H <= 128); got U=%d H=%d", U, H);
   if (r->n_chunks > 12 * 1024)
     return fail(h, B200DDSP_BAD_SHAPE, "timeline of %d chunks is too long for one call", r->n_chunks);
   r->P = P; r->B = B; r->F = F; r->H = H; r->S = S;
@@ -581,7 +593,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.out = r->partials;
   a.window = h->d_window;
   a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
-  a.chunk = kAngularChunk;
+  a.chunk = chunk_for(h, N);
   a.n_chunks = r->n_chunks;
   a.voices_per_group = (P + r->G - 1) / r->G;
   a.accumulate = 0;
@@ -633,7 +645,12 @@ static void launch_additive_generic(const AdditiveArgs& a, bool ends_only, dim3 
 }
 
 static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, int grid, size_t smem,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool plain_cumsum = false) {
+  if (plain_cumsum) {   // inference=False: one chunk per clip, no phase pass, exact cos reduction
+    if (fa.sp == 2) additive_fast_kernel<2, false, true><<<grid, kAddThreads, smem, st>>>(fa);
+    else additive_fast_kernel<1, false, true><<<grid, kAddThreads, smem, st>>>(fa);
+    return;
+  }
   if (fa.sp == 2) {
     if (ends_only) additive_fast_kernel<2, true><<<grid, kAddThreads, 0, st>>>(fa);
     else additive_fast_kernel<2, false><<<grid, kAddThreads, smem, st>>>(fa);
@@ -709,7 +726,7 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
     fa.slot = 1 + g;
     const size_t smem = (size_t)(2 * r.a.U) * sizeof(float);
     launch_additive_fast(fa, false, persistent_grid(h, (long long)Pg * r.B * r.n_chunks * r.sets, 2),
-                         smem, st);
+                         smem, st, !h->cfg.inference);
     CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
     return B200DDSP_OK;
   }
@@ -740,7 +757,7 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  const AdditiveLayout lay = carve_additive(0, 1, B, F, H, S, h->U);
+  const AdditiveLayout lay = carve_additive(h, 0, 1, B, F, H, S);
   if (!workspace || workspace_bytes < lay.end)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "additive_signal needs %zu workspace bytes, got %zu",
                 lay.end, workspace_bytes);
@@ -766,8 +783,8 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
   ps.sets = res.sets;
   ps.B = B;
   ps.N = F * h->U;
-  ps.chunk = kAngularChunk;
-  ps.n_chunks = n_chunks_for(ps.N);
+  ps.chunk = chunk_for(h, ps.N);
+  ps.n_chunks = n_chunks_for(h, ps.N);
   ps.accumulate = accumulate;
   additive_sum_partials_kernel<<<dim3((ps.N + 255) / 256, B), 256, 0, st>>>(ps);
   CHECK_LAUNCH(h, "additive_sum_partials_kernel");
@@ -825,8 +842,8 @@ static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn
   a.live = mix ? mix->live : nullptr;
   a.n_partials = mix ? mix->n_partials : 0;
   a.sets = mix ? mix->sets : 1;
-  a.chunk = kAngularChunk;
-  a.n_chunks = n_chunks_for(F * U);
+  a.chunk = chunk_for(h, F * U);
+  a.n_chunks = n_chunks_for(h, F * U);
   a.out = out;
   a.accumulate = accumulate;
   a.P = P; a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
@@ -1113,7 +1130,7 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
   if (reverb_ir && !wet_out) return fail(h, B200DDSP_BAD_ARGUMENT, "reverb_ir given but wet_out is null");
   if (reverb_ir && wet_out == dry_out)
     return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out may not alias dry_out");
-  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir ? L : 0, h->U, env_int("B200DDSP_DEV_GROUPS", 1));
+  const WorkspaceLayout w = carve(h, P, B, F, H, S, M, reverb_ir ? L : 0, env_int("B200DDSP_DEV_GROUPS", 1));
   if (!workspace || workspace_bytes < w.total)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_polyphonic needs %zu workspace bytes, got %zu",
                 w.total, workspace_bytes);
@@ -1158,7 +1175,7 @@ static int host_copy_groups(int P) {
 extern "C" size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int F, int H,
                                                 int S, int M, int L, int with_noise) {
   if (!h || P < 1 || B < 1 || F < 1 || H < 1 || S < 1 || M < 3) return 0;
-  const WorkspaceLayout w = carve(P, B, F, H, S, M, L, h->U, host_copy_groups(P));
+  const WorkspaceLayout w = carve(h, P, B, F, H, S, M, L, host_copy_groups(P));
   return carve_host(P, B, F, H, S, M, L, h->U, with_noise != 0, w).total;
 }
 
@@ -1176,7 +1193,7 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
   const int U = h->U, N = F * U;
   bool any_noise = false;
   for (int v = 0; v < P; ++v) any_noise |= voices_host[v].noise != nullptr;
-  const WorkspaceLayout w = carve(P, B, F, H, S, M, reverb_ir_host ? L : 0, U, host_copy_groups(P));
+  const WorkspaceLayout w = carve(h, P, B, F, H, S, M, reverb_ir_host ? L : 0, host_copy_groups(P));
   const HostStaging hs = carve_host(P, B, F, H, S, M, reverb_ir_host ? L : 0, U, any_noise, w);
   if (!workspace || workspace_bytes < hs.total)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL,

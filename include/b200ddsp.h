@@ -64,8 +64,9 @@ typedef struct {
   int additive_scale_fn;           /* b200ddsp_scale_fn */
   int normalize_after_nyquist_cut; /* inharm_synth.py:210-214 (default 1) */
   int normalize_below_nyquist;     /* inharm_synth.py:200-208 (default 1) */
-  int inference;                   /* 1: ddsp angular_cumsum (chunks of 1000); 0: plain cumsum
-                                      (inharm_synth.py:73-77) */
+  int inference;                   /* 1: ddsp angular_cumsum (chunks of 1000); 0: plain cumsum over the
+                                      clip (inharm_synth.py:73-77), one serial float32 chain per
+                                      oscillator -- fast additive path only (U % 8 == 0, H <= 128) */
   int noise_scale_fn;              /* b200ddsp_scale_fn (FilteredNoise.scale_fn) */
   float noise_initial_bias;        /* -5.0 */
   int noise_window_size;           /* 257 */

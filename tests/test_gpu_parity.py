@@ -423,3 +423,56 @@ def test_timeline_reverb_two_gpus_nccl():
          os.path.join(root, 'tests', 'multi_gpu_timeline.py')],
         capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and 'TIMELINE_OK' in proc.stdout, proc.stdout + proc.stderr
+
+
+def test_dag_stress_shapes_vs_oracle(dp, dev):
+    """BASELINE configs[4] shapes (48 kHz, H = 128 -> 4 partial groups, M = 96, U = 192) at a
+    size the oracle finishes in seconds; fused forward vs oracle."""
+    sr, F, B, H, S, M, P, L = 48000, 30, 1, 128, 2, 96, 5, 9000
+    U = sr // 250
+    rng = np.random.default_rng(48)
+    feats_np = {}
+    for v in range(P):
+        for k, a in voice_inputs(rng, B, F, H, S, M).items():
+            feats_np[f'{k}_{v}'] = a
+    feats_np['reverb_ir'] = (rng.standard_normal([B, L]) * np.exp(-6 * np.arange(L) / L) * 1e-2
+                             ).astype(np.float32)
+    noises = [rng.uniform(-1, 1, [B, F * U]).astype(np.float32) for _ in range(P)]
+    want = ref.polyphonic_forward(feats_np, n_synths=P, sample_rate=sr, noise_by_voice=noises)
+    group, noise = _build_group(dp, sr, P, True)
+    for n in noises:
+        noise.push_noise(cu(n, dev))
+    out = group({k: cu(v, dev) for k, v in feats_np.items()}, return_outputs_dict=True)
+    assert rel_err(out['controls']['add']['signal'], want['dry']) < TIGHT
+    assert rel_err(out['signal'], want['signal']) < TIGHT
+
+
+def test_additive_training_mode_golden(dp, dev, golden_dir):
+    """inference=False: plain float32 cumsum over the whole clip (inharm_synth.py:76-77)."""
+    g = load(golden_dir, 'additive_16k_training')
+    assert not bool(g['inference'])
+    synth = dp.MultiInharmonic(frame_rate=250, sample_rate=int(g['sample_rate']), inference=False,
+                               name='additive')
+    sig = synth(cu(g['in_amplitudes'], dev), cu(g['in_harmonic_distribution'], dev),
+                cu(g['in_inharm_coef'], dev), cu(g['in_f0_hz'], dev))
+    assert rel_err(sig, g['signal']) < TIGHT
+
+
+def test_additive_training_mode_vs_oracle_long(dp, dev):
+    """1 s at 16 kHz: phases reach 5e4 rad, so the cosine needs an exact reduction and the chain
+    the reference's summation order."""
+    sr, F, B, H, S = 16000, 250, 2, 96, 2
+    rng = np.random.default_rng(77)
+    x = voice_inputs(rng, B, F, H, S, 8)
+    ctl = ref.additive_controls(x['amplitudes'], x['harmonic_distribution'], x['inharm_coef'],
+                                x['f0_hz'], sample_rate=sr)
+    want = ref.additive_signal(**ctl, sample_rate=sr, inference=False)
+    synth = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=False, name='additive')
+    got = synth(cu(x['amplitudes'], dev), cu(x['harmonic_distribution'], dev),
+                cu(x['inharm_coef'], dev), cu(x['f0_hz'], dev))
+    assert rel_err(got, want) < TIGHT
+    # the knob really changes the algorithm
+    other = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='additive')(
+        cu(x['amplitudes'], dev), cu(x['harmonic_distribution'], dev),
+        cu(x['inharm_coef'], dev), cu(x['f0_hz'], dev))
+    assert rel_err(other, want) > 1e-3
