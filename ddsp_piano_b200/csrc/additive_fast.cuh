@@ -34,10 +34,22 @@ struct AdditiveFastArgs {
   AdditiveArgs a;                  // a.out: [P * sets, B, N] partial signals
   AdditivePlan* plan;              // bucket counts + work counters
   const int* lists;                // [kPlanSlots][kMaxGroups][R * n_chunks] units by slot and bucket
+  const float* lerp;               // [N] legacy-bilinear lerp weight of every sample (additive_lerp_kernel)
   int slot;                        // work list to drain: 0 = phase ends (all voices),
                                    // 1 + g = synthesis of voice group g
   int sp;                          // substrings per pass (1 or 2)
 };
+
+// ---- lerp table --------------------------------------------------------------------------------
+// lerp[t] = in - floor(in), in = float(t) * float(F/N): the legacy ResizeBilinear weight.  It depends
+// on the sample index only, so it is computed once per call instead of once per oscillator-sample.
+__global__ void __launch_bounds__(256) additive_lerp_kernel(float* __restrict__ lerp, int N, int U,
+                                                            float scale) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const float in = __fmul_rn((float)t, scale);
+  lerp[t] = __fadd_rn(in, -(float)(t / U));   // fast path: floor(in) == t / U (checked on the host)
+}
 
 // ---- liveness scan ---------------------------------------------------------------------------
 // na_frame[row, k] = 1 + index of the highest 32-partial group with a non-zero partial amplitude
@@ -104,6 +116,7 @@ struct OscState {
   float om[NA][SP];    // steady frames: the constant omega
   float off[NA][SP];   // chunk offset (synth pass)
   float A[NA], An[NA]; // partial amplitudes of frames k, k+1
+  float dA[NA];        // An - A: the Hann cross-fade is evaluated as A + dA * w[r]
 };
 
 template <int NA, int SP, bool WITH_AMP>
@@ -145,6 +158,8 @@ __device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, in
     for (int s = 0; s < SP; ++s) st.F[q][s] = st.Fn[q][s];
   }
   load_next_frame<NA, SP, WITH_AMP>(a, row, s0, kn, lane, st);
+#pragma unroll
+  for (int q = 0; q < NA; ++q) st.dA[q] = st.An[q] - st.A[q];
   bool all_steady = true, any_live = false, any_risky = false;
   // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
   // bottom - top, one in the product, one in the sum), hence the margin
@@ -180,15 +195,22 @@ __device__ __forceinline__ float cos_large(float x) {
 
 template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
-                                          const float* win, float tf, float kf,
+                                          const float* win, const float* lerp,
                                           float (&y)[kOscUnroll]) {
   static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-  float wr[4] = {0.f, 0.f, 0.f, 0.f}, wf[4] = {0.f, 0.f, 0.f, 0.f};
-  if (AMP != kAmpSilent) {   // r and U are multiples of 8: both loads are 16-byte aligned
+  static_assert(UNROLL == 4 || UNROLL == 8, "lerp loads are float4");
+  float wr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
-    const float4 f4 = *reinterpret_cast<const float4*>(win + a.U);
     wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
-    wf[0] = f4.x; wf[1] = f4.y; wf[2] = f4.z; wf[3] = f4.w;
+  }
+  float fr[UNROLL];
+  if (!STEADY) {             // t is a multiple of UNROLL
+#pragma unroll
+    for (int j4 = 0; j4 < UNROLL / 4; ++j4) {
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(lerp) + j4);
+      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
+    }
   }
   // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
   bool cut[NA][SP];
@@ -200,20 +222,14 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
   }
 #pragma unroll
   for (int j = 0; j < UNROLL; ++j) {
-    float frac = 0.f;
-    if (!STEADY) {
-      const float in = __fmul_rn(tf + (float)j, a.scale);   // legacy ResizeBilinear coordinate
-      frac = __fadd_rn(in, -kf);                            // lerp = in - floor(in)
-    }
-    float w0 = 0.f, w1 = 0.f;
-    if (AMP != kAmpSilent) {
-      w0 = wr[j & 3];      // rising half of hann(2U): weight of frame k+1
-      w1 = wf[j & 3];      // falling half: weight of frame k
-    }
+    const float frac = STEADY ? 0.f : fr[j];   // legacy ResizeBilinear lerp = in - floor(in)
+    const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
-      float amp_q = 0.f;   // Hann cross-fade of the frame amplitudes, shared by the substrings
-      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.A[q], w1, __fmul_rn(st.An[q], w0));
+      // Hann cross-fade of the frame amplitudes A w[r+U] + An w[r], with w[r+U] = 1 - w[r];
+      // shared by the substrings
+      float amp_q = 0.f;
+      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.dA[q], w0, st.A[q]);
 #pragma unroll
       for (int s = 0; s < SP; ++s) {
         float om, f = 0.f;
@@ -265,8 +281,8 @@ __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
 // One (row, substring set, chunk) on one warp.  ENDS_ONLY: phase chain only, writes the chunk
 // end phases; otherwise writes the audio of the chunk to `row_out` (global memory).
 template <int NA, int SP, bool ENDS_ONLY, bool PLAIN>
-__device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0, int c, int lane,
-                                          const float* win, float* row_out) {
+__device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
+                                          int c, int lane, const float* win, float* row_out) {
   const int t0 = c * a.chunk;
   const int t1 = min(a.N, t0 + a.chunk);
   OscState<NA, SP> st;
@@ -287,9 +303,8 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
       if (!ENDS_ONLY && c > 0 && h < a.H)
         st.off[q][s] = a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h];
     }
-  float tf = (float)t0;
   constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
-  for (int t = t0; t < t1; t += STEP, r += STEP, tf += (float)STEP) {
+  for (int t = t0; t < t1; t += STEP, r += STEP) {
     if (r == a.U) {
       r = 0;
       ++k;
@@ -298,19 +313,18 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
     float y[kOscUnroll];
 #pragma unroll
     for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
-    const float kf = (float)k;
     const float* w = win + r;
     if (ENDS_ONLY || amp_mode == kAmpSilent) {
-      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, tf, kf, y);
-      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, tf, kf, y);
+      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, fa_lerp + t, y);
+      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, fa_lerp + t, y);
       if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
     } else {
       if (amp_mode == kAmpNoCheck) {
-        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
-        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
+        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
+        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
       } else {
-        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
-        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, tf, kf, y);
+        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
+        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
       }
       const float v = transpose_reduce4(y, lane);
       if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
@@ -330,14 +344,15 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, int row, int s0
 }
 
 template <int SP, bool ENDS_ONLY, bool PLAIN>
-__device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, int na, int row, int s0,
-                                                   int c, int lane, const float* win, float* row_out) {
+__device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int na,
+                                                   int row, int s0, int c, int lane, const float* win,
+                                                   float* row_out) {
   switch (na) {
     case 0: break;
-    case 1: osc_chunk<1, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
-    case 2: osc_chunk<2, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
-    case 3: osc_chunk<3, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
-    case 4: osc_chunk<4, SP, ENDS_ONLY, PLAIN>(a, row, s0, c, lane, win, row_out); break;
+    case 1: osc_chunk<1, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 2: osc_chunk<2, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 3: osc_chunk<3, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 4: osc_chunk<4, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
     default:
       // more than 128 live partials: two passes over the chunk are not implemented here; the
       // host routes H > 128 to the generic kernel
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const Additi
   float* win = smem;                                   // [2U]
   const int lane = threadIdx.x & 31;
   if (!ENDS_ONLY) {
-    for (int i = threadIdx.x; i < 2 * a.U; i += blockDim.x) win[i] = a.window[i];
+    for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];   // rising half
     __syncthreads();
   }
   const int kind = fa.slot;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const Additi
     const int v = row / a.B, b = row - v * a.B;
     float* out = ENDS_ONLY ? nullptr
                            : a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-    osc_chunk_dispatch<SP, ENDS_ONLY, PLAIN>(a, na, row, set * SP, c, lane, win, out);
+    osc_chunk_dispatch<SP, ENDS_ONLY, PLAIN>(a, fa.lerp, na, row, set * SP, c, lane, win, out);
   }
 }
 
@@ -460,6 +475,36 @@ __global__ void __launch_bounds__(256) additive_sum_partials_kernel(const Partia
   }
   float* o = s.out + (size_t)b * s.N + t;
   *o = s.accumulate ? (*o + acc) : acc;
+}
+
+// Synthesis pass of ONE bucket (units with exactly NA live partial groups): a warp per (unit,
+// substring set), 4 warps per CTA, plain grid in list order.  Compiling the buckets as separate
+// kernels lets each use only the registers its NA needs (48 .. 128), i.e. 40 .. 16 resident warps
+// per SM instead of 16 for all; the host launches the four buckets on four streams so that they
+// fill each other's tails.  The grid is sized for the largest possible bucket; surplus CTAs exit.
+constexpr int kSynthWarps = 4;
+
+template <int NA, int SP, bool PLAIN>
+__global__ void __launch_bounds__(kSynthWarps * 32) additive_synth_kernel(const AdditiveFastArgs fa) {
+  const AdditiveArgs& a = fa.a;
+  extern __shared__ __align__(16) float smem[];
+  float* win = smem;                                   // [U] rising half of hann(2U)
+  const int lane = threadIdx.x & 31;
+  const int sets = a.S / SP;
+  const int n_items = fa.plan->count[fa.slot][NA - 1] * sets;
+  if ((int)blockIdx.x * kSynthWarps >= n_items) return;          // whole CTA has nothing to do
+  for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];
+  __syncthreads();
+  const int item = blockIdx.x * kSynthWarps + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int n_units = a.P * a.B * a.n_chunks;
+  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NA - 1) * n_units + item / sets];
+  const int set = item - (item / sets) * sets;
+  const int row = unit / a.n_chunks;
+  const int c = unit - row * a.n_chunks;
+  const int v = row / a.B, b = row - v * a.B;
+  float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
+  osc_chunk<NA, SP, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
 }
 
 }  // namespace b200ddsp

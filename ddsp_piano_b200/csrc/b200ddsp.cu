@@ -36,6 +36,8 @@ struct b200ddsp_handle {
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
+  cudaStream_t aux_stream[3] = {};      // the synthesis buckets run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_mags = nullptr, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
@@ -266,6 +268,11 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   }
   {
     bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i) {
+      ok = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     for (int i = 0; i < 8 && ok; ++i)
       ok = cudaEventCreateWithFlags(&h->ev_group[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_mags, cudaEventDisableTiming) == cudaSuccess;
@@ -305,6 +312,11 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->d_window) cudaFree(h->d_window);
   if (h->d_cmat_t) cudaFree(h->d_cmat_t);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 3; ++i) {
+    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
   for (int i = 0; i < 8; ++i)
     if (h->ev_group[i]) cudaEventDestroy(h->ev_group[i]);
   if (h->ev_mags) cudaEventDestroy(h->ev_mags);
@@ -355,6 +367,7 @@ struct AdditiveLayout {
   size_t na_frame;   // u8 [R, F]                  live partial groups per frame
   size_t synth_na;   // u8 [R, n_chunks]           live partial groups per chunk
   size_t ends_na;    // u8 [R, n_chunks]           groups whose end phase a later chunk needs
+  size_t lerp;       // float [N]                  legacy-bilinear lerp weight per sample
   size_t plan;       // AdditivePlan
   size_t lists;      // int [kPlanSlots][kMaxGroups][R * n_chunks]
   size_t partials;   // float [n_partials, B, N]   partial signals for the mixer
@@ -380,6 +393,7 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
   a.na_frame = take(R * F);
   a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
+  a.lerp = take(N * 4);
   a.plan = take(sizeof(AdditivePlan));
   a.lists = take((size_t)kPlanSlots * kMaxGroups * R * n_chunks * 4);
   a.partials = take(max_partials(P, S) * B * N * 4);
@@ -605,6 +619,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   r->fa.a = a;
   r->fa.plan = (AdditivePlan*)(base + lay.plan);
   r->fa.lists = (int*)(base + lay.lists);
+  r->fa.lerp = (float*)(base + lay.lerp);
   r->fa.sp = substrings_per_pass(S);
   const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
   if (!r->fast && smem > 48 * 1024)
@@ -660,6 +675,19 @@ static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, int
   }
 }
 
+template <int NA>
+static void launch_synth_bucket(const AdditiveFastArgs& fa, bool plain, int grid, size_t smem,
+                                cudaStream_t st) {
+  const int threads = kSynthWarps * 32;
+  if (fa.sp == 2) {
+    if (plain) additive_synth_kernel<NA, 2, true><<<grid, threads, smem, st>>>(fa);
+    else additive_synth_kernel<NA, 2, false><<<grid, threads, smem, st>>>(fa);
+  } else {
+    if (plain) additive_synth_kernel<NA, 1, true><<<grid, threads, smem, st>>>(fa);
+    else additive_synth_kernel<NA, 1, false><<<grid, threads, smem, st>>>(fa);
+  }
+}
+
 // persistent grids: every warp pulls work until its list is empty
 static int persistent_grid(const b200ddsp_handle* h, long long max_items, int ctas_per_sm) {
   const long long want = (max_items + kAddWarps - 1) / kAddWarps;
@@ -679,6 +707,8 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
                                                                         R * r.F, r.H);
         CHECK_LAUNCH(h, "additive_alive_frames_kernel");
       }
+      additive_lerp_kernel<<<(a.N + 255) / 256, 256, 0, st>>>((float*)r.fa.lerp, a.N, a.U, a.scale);
+      CHECK_LAUNCH(h, "additive_lerp_kernel");
       additive_alive_chunks_kernel<<<R, 128, (size_t)r.n_chunks, st>>>(
           r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks);
       CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
@@ -724,10 +754,33 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
   if (r.fast) {
     AdditiveFastArgs fa = r.fa;
     fa.slot = 1 + g;
-    const size_t smem = (size_t)(2 * r.a.U) * sizeof(float);
-    launch_additive_fast(fa, false, persistent_grid(h, (long long)Pg * r.B * r.n_chunks * r.sets, 2),
-                         smem, st, !h->cfg.inference);
-    CHECK_LAUNCH(h, "additive_fast_kernel<synth>");
+    const size_t smem = (size_t)r.a.U * sizeof(float);
+    const bool plain = !h->cfg.inference;
+    // one kernel per bucket (number of live partial groups), heaviest on the caller's stream,
+    // the others on auxiliary streams so that the buckets overlap; grids are sized for the
+    // largest possible bucket, surplus CTAs exit at once
+    const long long max_items = (long long)Pg * r.B * r.n_chunks * r.sets;
+    const int grid = (int)((max_items + kSynthWarps - 1) / kSynthWarps);
+    const int n_buckets = (r.H + 31) / 32;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    int aux = 0;
+    for (int na = n_buckets; na >= 1; --na) {
+      const bool on_main = (na == n_buckets);
+      cudaStream_t s = on_main ? st : h->aux_stream[aux];
+      if (!on_main) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_fork, 0));
+      switch (na) {
+        case 1: launch_synth_bucket<1>(fa, plain, grid, smem, s); break;
+        case 2: launch_synth_bucket<2>(fa, plain, grid, smem, s); break;
+        case 3: launch_synth_bucket<3>(fa, plain, grid, smem, s); break;
+        default: launch_synth_bucket<4>(fa, plain, grid, smem, s); break;
+      }
+      CHECK_LAUNCH(h, "additive_synth_kernel");
+      if (!on_main) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_join[aux], s));
+        ++aux;
+      }
+    }
+    for (int i = 0; i < aux; ++i) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
     return B200DDSP_OK;
   }
   // generic kernel over the group's rows; one partial signal per launch-internal voice group
