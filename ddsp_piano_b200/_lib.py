@@ -136,4 +136,4 @@ EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200dd
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
            'b200ddsp_workspace_bytes_host', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
-STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise_mix', 'reverb']
+STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise', 'reverb', 'mix']

@@ -39,7 +39,7 @@ struct b200ddsp_handle {
   cudaStream_t aux_stream[3] = {};      // the synthesis buckets run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   cudaEvent_t ev_group[8] = {};
-  cudaEvent_t ev_mags = nullptr, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
+  cudaEvent_t ev_mags[2] = {}, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
   cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
   cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
@@ -275,7 +275,8 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
     }
     for (int i = 0; i < 8 && ok; ++i)
       ok = cudaEventCreateWithFlags(&h->ev_group[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_mags, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_mags[0], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_mags[1], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_ir, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming) == cudaSuccess;
@@ -319,7 +320,8 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   }
   for (int i = 0; i < 8; ++i)
     if (h->ev_group[i]) cudaEventDestroy(h->ev_group[i]);
-  if (h->ev_mags) cudaEventDestroy(h->ev_mags);
+  if (h->ev_mags[0]) cudaEventDestroy(h->ev_mags[0]);
+  if (h->ev_mags[1]) cudaEventDestroy(h->ev_mags[1]);
   if (h->ev_ir) cudaEventDestroy(h->ev_ir);
   if (h->ev_enter) cudaEventDestroy(h->ev_enter);
   if (h->ev_small) cudaEventDestroy(h->ev_small);
@@ -340,6 +342,8 @@ static int fft_size_for(int N, int L) {
   while (n < N + L - 1) n <<= 1;   // ddsp.core.get_fft_size(power_of_2=True), frame = N
   return n;
 }
+
+constexpr int kNoiseSlices = 4;   // voice slices of the FIR stage (parallelism + overlap with copies)
 
 static int tap_pitch_for(int M) { return (M - 1 + 3) & ~3; }
 
@@ -404,7 +408,7 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
 // Voices are processed in `n_groups` consecutive groups (1 for device inputs; several for host
 // inputs, so that the H2D copies of one group overlap the kernels of the previous one).
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, taps, tw, buf_a, buf_b, total;
+  size_t amp, hd, shifts, f0, taps, noise_part, tw, buf_a, buf_b, total;
   AdditiveLayout add;
   PlanGroups groups;
   int n_chunks, nfft;
@@ -428,6 +432,7 @@ static WorkspaceLayout carve(const b200ddsp_handle* h, int P, int B, int F, int 
   w.shifts = take(R * F * H * 4);
   w.f0 = take(R * F * S * 4);
   w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
+  w.noise_part = take((size_t)kNoiseSlices * B * N * 4);
   w.add = carve_additive(h, o, P, B, F, H, S);
   o = w.add.end;
   if (L > 0) {
@@ -860,11 +865,12 @@ extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitud
   return B200DDSP_OK;
 }
 
-// taps GEMM (+ fused get_controls scaling when scale_fn != 2) then FIR + mix.
-static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn,
-                     const NoiseVoicePtrs& vp, int P, const AdditiveResult* mix, float* out, int B,
-                     int F, int M, int accumulate, unsigned long long seed,
-                     unsigned long long stream_id, float* taps, cudaStream_t st) {
+// taps GEMM (+ fused get_controls scaling when scale_fn != 2) and FIR of voices [v0, v1), written
+// as `n_slices` noise signals starting at slice index `slice0` of noise_part [*, B, N].
+static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn,
+                            const NoiseVoicePtrs& vp, int v0, int v1, int slice0, int n_slices,
+                            float* noise_part, int B, int F, int M, unsigned long long seed,
+                            unsigned long long stream_id, float* taps, cudaStream_t st) {
   const int U = h->U;
   if (M != h->cfg.n_noise_bands || !h->d_cmat_t)
     return fail(h, B200DDSP_BAD_SHAPE, "M=%d but the handle was created for n_noise_bands=%d", M,
@@ -873,33 +879,31 @@ static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth needs U %% 8 == 0 (U=%d)", U);
   if (U > 8 * 4 * 16)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth supports U <= 512 (U=%d)", U);
-  StageTimer tm(h, B200DDSP_STAGE_NOISE_MIX, st);
+  StageTimer tm(h, B200DDSP_STAGE_NOISE, st);
   const int tap_pitch = tap_pitch_for(M);
   {
     NoiseTapsArgs t{};
+    NoiseTapsPtrs sub{};
+    for (int v = v0; v < v1; ++v) sub.mags[v - v0] = mags.mags[v];
     t.cmat_t = h->d_cmat_t;
-    t.taps = taps;
+    t.taps = taps + (size_t)v0 * B * F * tap_pitch;
     t.mags_out = nullptr;
     t.frames_per_voice = B * F;
     t.M = M;
     t.tap_pitch = tap_pitch;
     t.scale_fn = scale_fn;
     t.bias = h->cfg.noise_initial_bias;
-    dim3 grid((B * F + kTapsTileF - 1) / kTapsTileF, (M - 1 + kTapsTileD - 1) / kTapsTileD, P);
-    noise_taps_kernel<<<grid, 256, 0, st>>>(t, mags);
+    dim3 grid((B * F + kTapsTileF - 1) / kTapsTileF, (M - 1 + kTapsTileD - 1) / kTapsTileD, v1 - v0);
+    noise_taps_kernel<<<grid, 256, 0, st>>>(t, sub);
     CHECK_LAUNCH(h, "noise_taps_kernel");
   }
   NoiseArgs a{};
   a.taps = taps;
-  a.partials = mix ? mix->partials : nullptr;
-  a.live = mix ? mix->live : nullptr;
-  a.n_partials = mix ? mix->n_partials : 0;
-  a.sets = mix ? mix->sets : 1;
-  a.chunk = chunk_for(h, F * U);
-  a.n_chunks = n_chunks_for(h, F * U);
-  a.out = out;
-  a.accumulate = accumulate;
-  a.P = P; a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
+  a.out = noise_part;
+  a.v_begin = v0;
+  a.v_end = v1;
+  a.slice0 = slice0;
+  a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
   a.tap_pitch = tap_pitch;
   a.halo_before = (M + U - 1) / U;
   a.halo_after = (U + M - 5) / U;
@@ -909,13 +913,11 @@ static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn
   const size_t smem = (size_t)L.total_floats * sizeof(float);
   if (smem > 227 * 1024)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
-  // warps split the U/8 blocks of a frame; NB blocks per thread
+  // warps split the U/8 blocks of a frame: one block per thread up to 16 warps, else 2..4
   const int n_blocks = U / 8;
-  // one block per thread up to 16 warps (the grid is only F/32 x B CTAs, so the CTA has to bring
-  // the parallelism), then 2..4 blocks per thread
-  int nb = (n_blocks + 15) / 16;
+  const int nb = (n_blocks + 15) / 16;
   const int warps = (n_blocks + nb - 1) / nb;
-  dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B);
+  dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B, n_slices);
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -935,9 +937,33 @@ static int run_noise(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn
   return B200DDSP_OK;
 }
 
+// dry = noise slices + additive partial signals (the MultiAdd nodes of the DAG)
+static int run_mix(b200ddsp_handle* h, const float* noise_part, int n_noise, const AdditiveResult* mix,
+                   float* out, int B, int N, int accumulate, cudaStream_t st) {
+  MixArgs m{};
+  m.noise = noise_part;
+  m.n_noise = n_noise;
+  m.partials = mix ? mix->partials : nullptr;
+  m.live = mix ? mix->live : nullptr;
+  m.n_partials = mix ? mix->n_partials : 0;
+  m.sets = mix ? mix->sets : 1;
+  m.out = out;
+  m.B = B;
+  m.N = N;
+  m.chunk = chunk_for(h, N);
+  m.n_chunks = n_chunks_for(h, N);
+  m.accumulate = accumulate;
+  if (N % 4 != 0 || m.chunk % 4 != 0)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "mixer needs N %% 4 == 0 (N=%d)", N);
+  StageTimer tm(h, B200DDSP_STAGE_MIX, st);
+  mix_kernel<<<dim3((N / 4 + 255) / 256, B), 256, 0, st>>>(m);
+  CHECK_LAUNCH(h, "mix_kernel");
+  return B200DDSP_OK;
+}
+
 extern "C" size_t b200ddsp_noise_workspace_bytes(const b200ddsp_handle* h, int B, int F, int M) {
   if (!h || B < 1 || F < 1 || M < 2) return 0;
-  return align_up((size_t)B * F * tap_pitch_for(M) * 4);
+  return align_up((size_t)B * F * tap_pitch_for(M) * 4) + align_up((size_t)B * F * h->U * 4);
 }
 
 extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
@@ -956,8 +982,12 @@ extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes
   NoiseVoicePtrs vp{};
   vp.noise[0] = noise;
   reset_stage_flags(h);
-  return run_noise(h, mp, B200DDSP_SCALE_NONE, vp, 1, nullptr, out, B, F, M, accumulate, seed, stream_id,
-                   (float*)workspace, (cudaStream_t)stream);
+  float* taps = (float*)workspace;
+  float* part = (float*)((char*)workspace + align_up((size_t)B * F * tap_pitch_for(M) * 4));
+  if (int rc = run_noise_voices(h, mp, B200DDSP_SCALE_NONE, vp, 0, 1, 0, 1, part, B, F, M, seed,
+                                stream_id, taps, (cudaStream_t)stream))
+    return rc;
+  return run_mix(h, part, 1, nullptr, out, B, F * h->U, accumulate, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1080,11 +1110,13 @@ extern "C" int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, cons
 
 // Optional cross-stream ordering for the host-input entry point: the main stream waits for
 // `small_ready` before the prep kernel, `group_ready[g]` before it touches the harmonic
-// distribution of voice group g, `mags_ready` before the noise stage, `ir_ready` before the reverb.
+// distribution of voice group g, `mags_ready[h]` before the noise stage of voice half h,
+// `ir_ready` before the reverb.
 struct ForwardSync {
   cudaEvent_t small_ready;                      // amplitudes, inharm_coef, f0_hz of all voices
   cudaEvent_t group_ready[kMaxVoiceGroups];     // harmonic_distribution of voice group g
-  cudaEvent_t mags_ready, ir_ready;
+  cudaEvent_t mags_ready[2];                    // magnitudes of the first / second half of the voices
+  cudaEvent_t ir_ready;
 };
 
 static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, const float* reverb_ir,
@@ -1150,9 +1182,20 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
 
   // 3. noise of every voice + mix -> dry  (outputs['add']['signal']); FilteredNoise.get_controls
   //    is fused into the taps GEMM's operand load
-  if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->mags_ready, 0));
-  if (int rc = run_noise(h, mp, h->cfg.noise_scale_fn, vp, P, &mix, dry_out, B, F, M, 0, seed, 0, taps, st))
-    return rc;
+  //    The voices are processed in halves (each half = its share of the noise slices), so that on
+  //    the host-input path the FIR of the first half runs while the second half is still copying.
+  float* noise_part = (float*)(base + w.noise_part);
+  const int n_slices = P < kNoiseSlices ? P : kNoiseSlices;
+  const int halves = (sync && P >= 2 && n_slices >= 2) ? 2 : 1;
+  for (int hf = 0; hf < halves; ++hf) {
+    const int v0 = P * hf / halves, v1 = P * (hf + 1) / halves;
+    const int s0 = n_slices * hf / halves, s1 = n_slices * (hf + 1) / halves;
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->mags_ready[halves == 2 ? hf : 1], 0));
+    if (int rc = run_noise_voices(h, mp, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B, F,
+                                  M, seed, 0, taps, st))
+      return rc;
+  }
+  if (int rc = run_mix(h, noise_part, n_slices, &mix, dry_out, B, N, 0, st)) return rc;
   // 4. reverb -> wet
   if (reverb_ir) {
     if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->ir_ready, 0));
@@ -1306,14 +1349,17 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaEventRecord(h->ev_group[g], cs));
     sync.group_ready[g] = h->ev_group[g];
   }
-  CUDA_TRY(h, copy_runs(0, P, BF * M, [&](int v) { return voices_host[v].magnitudes; },
-                        [&](int v) { return dev[v].magnitudes; }));
-  for (int v = 0; v < P; ++v)
-    if (voices_host[v].noise)
-      CUDA_TRY(h, cudaMemcpyAsync((void*)dev[v].noise, voices_host[v].noise, (size_t)B * N * 4,
-                                  cudaMemcpyHostToDevice, cs));
-  CUDA_TRY(h, cudaEventRecord(h->ev_mags, cs));
-  sync.mags_ready = h->ev_mags;
+  for (int hf = 0; hf < 2; ++hf) {
+    const int v0 = P * hf / 2, v1 = P * (hf + 1) / 2;
+    CUDA_TRY(h, copy_runs(v0, v1, BF * M, [&](int v) { return voices_host[v].magnitudes; },
+                          [&](int v) { return dev[v].magnitudes; }));
+    for (int v = v0; v < v1; ++v)
+      if (voices_host[v].noise)
+        CUDA_TRY(h, cudaMemcpyAsync((void*)dev[v].noise, voices_host[v].noise, (size_t)B * N * 4,
+                                    cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(h, cudaEventRecord(h->ev_mags[hf], cs));
+    sync.mags_ready[hf] = h->ev_mags[hf];
+  }
   float* ir_dev = nullptr;
   if (reverb_ir_host) {
     ir_dev = (float*)(base + hs.ir);

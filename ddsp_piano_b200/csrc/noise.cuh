@@ -14,13 +14,13 @@
 //                      symmetric about tap M-1 so only taps M-1 .. 2M-3 are computed and
 //                      stored.  A register-tiled FP32 GEMM over all frames of all voices; the
 //                      magnitudes' get_controls scaling is fused into the operand load.
-//  noise_fir_kernel    CTA = (tile of 32 output frames, clip); it loops over the voices, so the
-//                      MultiAdd node (inharm_synth.py:296-309) is register accumulation, and
-//                      finally adds the additive partial signals: it is also the mixer.  Lanes
-//                      are FRAMES (odd shared-memory pitches make the frame-strided accesses
-//                      conflict free); a thread owns 8 consecutive outputs of its frame per
-//                      block and slides a 15-tap register window over the taps:
-//                      16 shared loads per 64 FMAs.
+//  noise_fir_kernel    CTA = (tile of 32 output frames, clip, voice slice); it loops over the
+//                      voices of its slice, so most of the MultiAdd node (inharm_synth.py:296-309)
+//                      is register accumulation.  Lanes are FRAMES (shared-memory pitches = 4 mod
+//                      32 make the frame-strided 128-bit accesses conflict free); a thread owns 8
+//                      consecutive outputs of its frame and slides a 15-tap register window over
+//                      the taps: 4 LDS.128 per 64 FMAs.
+//  mix_kernel          dry = sum of the noise slices + the additive partial signals.
 #pragma once
 #include "common.cuh"
 
@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(256) noise_taps_kernel(const NoiseTapsArgs a,
   }
 }
 
-// ---- FIR + mix ------------------------------------------------------------------------------
+// ---- FIR ---------------------------------------------------------------------------------------
 constexpr int kNoiseFrames = 32;   // output frames per CTA (= lanes)
 constexpr int kTapPad = 16;        // zero taps either side of c_k (8-aligned input blocks + the
-                                   // 15-tap register window overhang by up to 13 taps)
+                                   // 16-tap register window overhang by up to 14 taps)
 
 struct NoiseVoicePtrs {
   const float* noise[B200DDSP_MAX_VOICES_INTERNAL];   // [B, N] or nullptr (Philox)
@@ -117,29 +117,33 @@ struct NoiseVoicePtrs {
 
 struct NoiseArgs {
   const float* taps;     // [P*B*F][tap_pitch] from noise_taps_kernel
-  const float* partials; // [n_partials, B, N] additive partial signals to mix in, or nullptr
-  const unsigned char* live;   // [P * B, n_chunks]: partial p = (voice p / sets) is only defined
-                               // where live != 0 (additive fast path), or nullptr
-  float* out;            // [B, N]
-  int n_partials, sets, chunk, n_chunks;
-  int accumulate;        // out += result
-  int P, B, F, M, U, N, tap_pitch;
+  float* out;            // [n_slices, B, N] noise of each voice slice
+  int v_begin, v_end;    // voices handled by this launch, split evenly over gridDim.z slices
+  int slice0;            // index of the launch's first slice in `out`
+  int B, F, M, U, N, tap_pitch;
   int halo_before, halo_after;   // input halo in FRAMES either side of the tile
   unsigned long long seed, stream_id;
 };
 
+__host__ __device__ inline int pitch_4mod32(int n) {   // smallest p >= n with p = 4 (mod 32)
+  return n + ((4 - n) % 32 + 32) % 32;
+}
+
 struct NoiseSmemLayout {
   int n_in;       // input frames held: kNoiseFrames + halo_before + halo_after
-  int pitch_x;    // U | 1
-  int pitch_c;    // (Lir + 2*kTapPad) | 1
+  int pitch_x;    // >= U,  = 4 (mod 32)
+  int pitch_c;    // >= Lir + 2*kTapPad + 4,  = 4 (mod 32)
+  int tap_shift;  // 0..3: makes the register-window loads 16-byte aligned
   int off_x, off_c, total_floats;
   __host__ __device__ NoiseSmemLayout(int M, int U, int hb, int ha) {
     const int lir = 2 * (M - 1);
+    const int start = (lir - 1) / 2 - 1;
     n_in = kNoiseFrames + hb + ha;
-    pitch_x = U | 1;
-    pitch_c = (lir + 2 * kTapPad) | 1;
+    pitch_x = pitch_4mod32(U);
+    pitch_c = pitch_4mod32(lir + 2 * kTapPad + 4);
+    tap_shift = ((7 - start) % 4 + 4) % 4;
     off_x = 0;
-    off_c = (off_x + n_in * pitch_x + 3) & ~3;
+    off_c = n_in * pitch_x;
     total_floats = off_c + n_in * pitch_c;
   }
 };
@@ -165,6 +169,11 @@ __device__ __forceinline__ float uniform_pm1(unsigned int bits) {
   return __fmaf_rn(u, 2.0f, -1.0f);
 }
 
+__device__ __forceinline__ void load4(float* dst, const float* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+}
+
 // NB = 8-sample blocks per thread: blocks warp, warp + W, ... of the thread's frame.
 template <int NB>
 __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
@@ -180,6 +189,11 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   const int U = a.U, M = a.M, lir = 2 * (M - 1);
   const int start = (lir - 1) / 2 - 1;                 // crop_and_compensate_delay
   const int n_blocks = U / 8;
+  const int tap0 = kTapPad + L.tap_shift;              // position of tap 0 inside a taps row
+  // this CTA's voices
+  const int n_v = a.v_end - a.v_begin;
+  const int v_lo = a.v_begin + (int)(((long long)n_v * blockIdx.z) / gridDim.z);
+  const int v_hi = a.v_begin + (int)(((long long)n_v * (blockIdx.z + 1)) / gridDim.z);
 
   float acc[NB][8];
 #pragma unroll
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   // taps outside [1, Lir-1] stay zero for the whole kernel
   for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += n_threads) cs[i] = 0.f;
 
-  for (int v = 0; v < a.P; ++v) {
+  for (int v = v_lo; v < v_hi; ++v) {
     __syncthreads();   // previous voice's FIR is done with xs/cs (and the zero fill is visible)
     // ---- stage this voice's taps and noise for the held input frames ----------------------
     const float* taps = a.taps + ((size_t)v * a.B + b) * a.F * a.tap_pitch;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
       const int fi = i / (M - 1), d = i - fi * (M - 1);
       const int k = k_first + fi;
       const float c = (k >= 0 && k < a.F) ? __ldg(taps + (size_t)k * a.tap_pitch + d) : 0.f;
-      float* row = cs + fi * L.pitch_c + kTapPad;
+      float* row = cs + fi * L.pitch_c + tap0;
       row[M - 1 + d] = c;
       if (d > 0) row[M - 1 - d] = c;                   // linear phase: symmetric about tap M-1
     }
@@ -224,8 +238,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
           r = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z),
                           uniform_pm1(bits.w));
         }
-        float* dst = xs + fi * L.pitch_x + j;
-        dst[0] = r.x; dst[1] = r.y; dst[2] = r.z; dst[3] = r.w;
+        *reinterpret_cast<float4*>(xs + fi * L.pitch_x + j) = r;
       }
     }
     __syncthreads();
@@ -246,28 +259,30 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
         for (int d = d_lo; d <= d_hi; ++d) {
           const int fi = fo + a.halo_before + d;         // held input frame index
           const float* xrow = xs + fi * L.pitch_x;
-          const float* crow = cs + fi * L.pitch_c + kTapPad;
+          const float* crow = cs + fi * L.pitch_c + tap0;
           // 8-aligned input range (U % 8 == 0); taps outside [1, Lir-1] read the zero padding
           const int j_lo = max(0, e_lo - d * U) & ~7;
           const int j_hi = min(U - 1, e_hi - d * U) | 7;
-          // tap of output q for input j+u: m0 - u + q with m0 = i0 + start - (d*U + j)
+          // tap of output q for input j+u: m0 - u + q with m0 = i0 + start - (d*U + j);
+          // m0 = start (mod 8), so crow + m0 - 7 is 16-byte aligned by the choice of tap_shift
           int m0 = i0 + start - (d * U + j_lo);
-          float w[15];                                   // taps m0-7 .. m0+7
+          float w[16];                                   // taps m0-7 .. m0+8 (the last is unused)
 #pragma unroll
-          for (int i = 0; i < 15; ++i) w[i] = crow[m0 - 7 + i];
+          for (int i = 0; i < 16; i += 4) load4(w + i, crow + m0 - 7 + i);
           for (int j = j_lo; j <= j_hi; j += 8) {
+            float x[8];
+            load4(x, xrow + j);
+            load4(x + 4, xrow + j + 4);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float xv = xrow[j + u];
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-              for (int q = 0; q < 8; ++q) acc[ib][q] = __fmaf_rn(xv, w[7 - u + q], acc[ib][q]);
-            }
+              for (int q = 0; q < 8; ++q) acc[ib][q] = __fmaf_rn(x[u], w[7 - u + q], acc[ib][q]);
             m0 -= 8;
             if (j + 8 <= j_hi) {
 #pragma unroll
               for (int i = 0; i < 7; ++i) w[8 + i] = w[i];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) w[i] = crow[m0 - 7 + i];
+              load4(w, crow + m0 - 7);
+              load4(w + 4, crow + m0 - 3);
             }
           }
         }
@@ -276,30 +291,57 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   }
   __syncthreads();
 
-  // ---- mix: noise (through shared memory, for coalescing) + additive partial signals -> out ---
+  // ---- through shared memory (for coalescing) to the slice's noise signal -------------------
   float* os = xs;   // [kNoiseFrames][pitch_x], reuses the noise tile
 #pragma unroll
   for (int ib = 0; ib < NB; ++ib) {
     const int blk = warp + ib * n_warps;
     if (blk < n_blocks) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) os[lane * L.pitch_x + blk * 8 + q] = acc[ib][q];
+      float* o = os + lane * L.pitch_x + blk * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[ib][0], acc[ib][1], acc[ib][2], acc[ib][3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[ib][4], acc[ib][5], acc[ib][6], acc[ib][7]);
     }
   }
   __syncthreads();
   const int t_tile = f_tile * U;
   const int len = min(kNoiseFrames * U, a.N - t_tile);
-  float* out = a.out + (size_t)b * a.N + t_tile;
-  for (int i = threadIdx.x; i < len; i += n_threads) {
-    float sum = os[(i / U) * L.pitch_x + (i % U)];
-    const int c = (t_tile + i) / a.chunk;
-    for (int p = 0; p < a.n_partials; ++p) {
-      if (a.live == nullptr || a.live[((size_t)(p / a.sets) * a.B + b) * a.n_chunks + c] != 0)
-        sum += a.partials[((size_t)p * a.B + b) * a.N + t_tile + i];
-    }
-    if (a.accumulate) sum += out[i];
-    out[i] = sum;
+  float* out = a.out + ((size_t)(a.slice0 + blockIdx.z) * a.B + b) * a.N + t_tile;
+  for (int i = threadIdx.x; i < len; i += n_threads) out[i] = os[(i / U) * L.pitch_x + (i % U)];
+}
+
+// ---- mix ---------------------------------------------------------------------------------------
+// out[b, t] (+)= sum of the noise slices + sum of the additive partial signals (skipping (voice,
+// chunk) units that were never written because nothing sounds there).  Fixed summation order.
+struct MixArgs {
+  const float* noise;          // [n_noise, B, N] or nullptr
+  const float* partials;       // [n_partials, B, N] or nullptr
+  const unsigned char* live;   // [P * B, n_chunks] synth_na (partial p belongs to voice p / sets), or nullptr
+  float* out;                  // [B, N]
+  int n_noise, n_partials, sets, B, N, chunk, n_chunks, accumulate;
+};
+
+__global__ void __launch_bounds__(256) mix_kernel(const MixArgs m) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4;   // N and chunk are multiples of 4
+  const int b = blockIdx.y;
+  if (t >= m.N) return;
+  const int c = t / m.chunk;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < m.n_noise; ++z) {
+    const float4 v = *reinterpret_cast<const float4*>(m.noise + ((size_t)z * m.B + b) * m.N + t);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
+  for (int p = 0; p < m.n_partials; ++p) {
+    if (m.live == nullptr || m.live[((size_t)(p / m.sets) * m.B + b) * m.n_chunks + c] != 0) {
+      const float4 v = *reinterpret_cast<const float4*>(m.partials + ((size_t)p * m.B + b) * m.N + t);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(m.out + (size_t)b * m.N + t);
+  if (m.accumulate) {
+    const float4 v = *o;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *o = acc;
 }
 
 }  // namespace b200ddsp

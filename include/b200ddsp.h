@@ -200,9 +200,10 @@ typedef enum {
   B200DDSP_STAGE_PHASE_ENDS = 1,    /* additive pass 1: chunk end phases */
   B200DDSP_STAGE_PHASE_SCAN = 2,    /* chunk ends -> chunk offsets */
   B200DDSP_STAGE_OSCILLATORS = 3,   /* additive pass 2: the oscillator bank */
-  B200DDSP_STAGE_NOISE_MIX = 4,     /* noise FIR of every voice + mix */
+  B200DDSP_STAGE_NOISE = 4,         /* noise taps GEMM + FIR of every voice */
   B200DDSP_STAGE_REVERB = 5,        /* FFT convolution */
-  B200DDSP_N_STAGES = 6
+  B200DDSP_STAGE_MIX = 6,           /* dry = noise slices + additive partial signals */
+  B200DDSP_N_STAGES = 7
 } b200ddsp_stage;
 int b200ddsp_set_profiling(b200ddsp_handle* h, int enable);
 int b200ddsp_last_stage_ms(b200ddsp_handle* h, float* ms /* [B200DDSP_N_STAGES] */);
