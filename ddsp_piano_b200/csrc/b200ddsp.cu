@@ -997,6 +997,12 @@ extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes
 template <class Loader, class Storer>
 static void launch_fft_pass(int R, const Loader& ld, const Storer& st, const float2* tw, int n, int Ns,
                             int batches, cudaStream_t s) {
+  if (R == 64) {
+    dim3 grid64(n / 64 / kFft64J, batches);
+    if (Ns < 16) fft_pass64_kernel<Loader, Storer, true><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
+    else fft_pass64_kernel<Loader, Storer, false><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
+    return;
+  }
   dim3 grid((n / R + kFftThreads - 1) / kFftThreads, batches);
   switch (R) {
     case 2: fft_pass_kernel<2><<<grid, kFftThreads, 0, s>>>(ld, st, tw, n, Ns); break;
@@ -1006,12 +1012,21 @@ static void launch_fft_pass(int R, const Loader& ld, const Storer& st, const flo
   }
 }
 
+// Radix plan: as many radix-64 passes (shared-memory kernel) as possible, the remaining bits as
+// small register-radix passes in front.  n < 1024 keeps the plain radix-16 plan.
 static std::vector<int> fft_radices(int n) {
   int p = 0;
   while ((1 << p) < n) ++p;
   std::vector<int> r;
-  if (p % 4) r.push_back(1 << (p % 4));
-  for (int i = 0; i < p / 4; ++i) r.push_back(16);
+  if (n < 1024 || env_int("B200DDSP_FFT_RADIX16", 0)) {
+    if (p % 4) r.push_back(1 << (p % 4));
+    for (int i = 0; i < p / 4; ++i) r.push_back(16);
+    return r;
+  }
+  const int rem = p % 6;
+  if (rem == 5) { r.push_back(8); r.push_back(4); }
+  else if (rem > 0) r.push_back(1 << rem);
+  for (int i = 0; i < p / 6; ++i) r.push_back(64);
   return r;
 }
 

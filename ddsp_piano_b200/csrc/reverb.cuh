@@ -179,6 +179,74 @@ __global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const Loader ld, 
   for (int r = 0; r < R; ++r) st(batch, base + r * Ns, v[r]);
 }
 
+// One Stockham pass of radix 64 = 8 x 8 through shared memory: a CTA of 128 threads takes 16
+// consecutive butterflies (1024 points).  Stage 1: thread (jj, a) loads points r = a + 8m with
+// the inter-pass twiddle, does the 8-point DFT over m, applies W64^(a c); stage 2, after a
+// shared-memory exchange: thread (jj, c) does the 8-point DFT over a and owns outputs q = c + 8d.
+// Global loads are 128-byte runs (16 consecutive j); stores are 128-byte runs when Ns >= 16 and
+// go through shared memory (SMALL_NS) when the output runs are shorter.
+constexpr int kFft64J = 16;
+constexpr int kFft64Threads = kFft64J * 8;
+
+template <class Loader, class Storer, bool SMALL_NS>
+__global__ void __launch_bounds__(kFft64Threads) fft_pass64_kernel(const Loader ld, const Storer st,
+                                                                  const float2* __restrict__ tw,
+                                                                  int n, int Ns) {
+  __shared__ float2 S[kFft64J * 65];
+  const int jj = threadIdx.x & (kFft64J - 1);
+  const int a = threadIdx.x >> 4;                 // stage 1: residue of r mod 8; stage 2: c
+  const int batch = blockIdx.y;
+  const int stride = n >> 6;                      // n / 64
+  const int j = blockIdx.x * kFft64J + jj;        // n >= 1024: every j is valid
+  const int k = j & (Ns - 1);
+  float2 v[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = ld(batch, j + (a + 8 * m) * stride);
+  if (Ns > 1) {
+    const int step = k * (stride / Ns);           // k * n / (Ns * 64)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int r = a + 8 * m;
+      if (r > 0) v[m] = cmul(v[m], __ldg(tw + r * step));
+    }
+  }
+  dft<8>(v);                                      // over m -> index c
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float2 x = v[c];
+    if (a * c > 0) x = cmul(x, __ldg(tw + (a * c) * stride));   // W64^(a c)
+    S[jj * 65 + c * 8 + a] = x;
+  }
+  __syncthreads();
+  const int c = a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = S[jj * 65 + c * 8 + i];
+  dft<8>(v);                                      // over a -> index d, output q = c + 8 d
+  if (!SMALL_NS) {
+    const int base = (j - k) * 64 + k;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) st(batch, base + (c + 8 * d) * Ns, v[d]);
+  } else {
+    // outputs of the CTA's 16 butterflies: q-major inside a butterfly when Ns == 1; gather them in
+    // shared memory and let consecutive threads store consecutive addresses as far as they go
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < 8; ++d) S[jj * 65 + c + 8 * d] = v[d];
+    __syncthreads();
+    // output address of (j, q) = (j - k) * 64 + k + q * Ns: for fixed q-block the run over k is
+    // contiguous; enumerate (jblock, q, k) so that k is fastest
+    const int j0 = blockIdx.x * kFft64J;          // multiple of 16 >= Ns (Ns in {1,2,4,8})
+    for (int e = threadIdx.x; e < kFft64J * 64; e += kFft64Threads) {
+      const int kk = e & (Ns - 1);
+      const int q = (e / Ns) & 63;
+      const int jb = e / (Ns * 64);               // which Ns-block of the CTA's 16 j's
+      const int jl = jb * Ns + kk;                // local j
+      const int jg = j0 + jl;
+      st(batch, (jg - kk) * 64 + kk + q * Ns, S[jl * 65 + q]);
+    }
+  }
+}
+
 // tw[q] = exp(-2 pi i q / n)
 __global__ void __launch_bounds__(256) fft_twiddle_kernel(float2* tw, int n) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
