@@ -367,16 +367,22 @@ def run_gpu(args, w):
         achieved = ab['oscillators'] / (osc_ms * 1e-3) / 1e9 if osc_ms > 0 else None
         # issue-slot view of the same kernel: counted FP32 instructions per oscillator-sample
         osc_samples = B * P * S * H * N
+        # dram__bytes_read+write of the three bucket launches of one step, from the ncu --set full
+        # capture of this same command (profiles/r01_prof6_summary.txt); config 3 at N=1 only
+        traffic = 103.7e6 if (args.workload == 'full' and world == 1) else None
         roofline = {
-            'bound': 'hbm', 'kernel': 'additive_kernel<synth> (oscillator bank)',
+            'bound': 'hbm',
+            'kernel': 'additive_synth_kernel<NA,2> x 3 buckets, concurrent (the oscillator bank)',
             'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': (achieved / hbm_peak) if achieved else None, 'traffic': None,
+            'frac': (achieved / hbm_peak) if achieved else None, 'traffic': traffic,
+            'traffic_source': 'profiles/r01_prof6_summary.txt (sum over the 3 bucket launches; below '
+                              'the algorithmic bytes because silent partial groups are never read)',
             'peak_source': f'{peaks_src} (MEASURED_PEAKS.json hbm_gbs)' if peaks_src == 'measured'
             else 'fallback 6650 GB/s (B200_PROFILING.md)',
             'algorithmic_bytes_per_launch': ab['oscillators'], 'kernel_ms': osc_ms,
             'kernel_share_of_step': osc_ms / ms_per_step if ms_per_step else None,
-            'note': 'the oscillator bank is FP32-issue bound, not HBM bound (SURVEY.md fact 5): '
-                    'see oscillator_samples_per_s and DESIGN.md',
+            'note': 'the oscillator bank is FP32-issue bound, not HBM bound (SURVEY.md fact 5): 83 % '
+                    'issue-slot utilisation in ncu; see oscillator_samples_per_s and DESIGN.md section 4',
             'oscillator_samples_per_s': osc_samples / (osc_ms * 1e-3) if osc_ms > 0 else None,
             'whole_step_GBps': ab['forward'] / (ms_per_step * 1e-3) / 1e9,
             'stage_ms': {k: v / args.steps for k, v in stages.items()},
