@@ -384,6 +384,15 @@ def run_gpu(args, w):
             'note': 'the oscillator bank is FP32-issue bound, not HBM bound (SURVEY.md fact 5): 83 % '
                     'issue-slot utilisation in ncu; see oscillator_samples_per_s and DESIGN.md section 4',
             'oscillator_samples_per_s': osc_samples / (osc_ms * 1e-3) if osc_ms > 0 else None,
+            # what actually bounds the stage: warp instructions issued (smsp__inst_executed.sum of
+            # the three bucket launches in profiles/r01_prof6_summary.txt, config 3) over the issue
+            # slots available in the measured time (SMs x 4 schedulers x SM clock under load)
+            'fp32_issue': ({'warp_instructions_per_launch_set': 1.3137e9,
+                            'achieved_per_s': 1.3137e9 / (osc_ms * 1e-3),
+                            'peak_per_s': 148 * 4 * (clocks.get('sm_mhz') or 1965.0) * 1e6,
+                            'frac': 1.3137e9 / (osc_ms * 1e-3) /
+                                    (148 * 4 * (clocks.get('sm_mhz') or 1965.0) * 1e6)}
+                           if (args.workload == 'full' and world == 1 and osc_ms > 0) else None),
             'whole_step_GBps': ab['forward'] / (ms_per_step * 1e-3) / 1e9,
             'stage_ms': {k: v / args.steps for k, v in stages.items()},
         }

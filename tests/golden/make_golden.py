@@ -163,3 +163,21 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def make_ir_fixture():
+    """Row 0 of the reverb impulse-response embedding of the SHIPPED dafx22 checkpoint
+    (ddsp_piano/model_weights/dafx22/ckpt-0.data-00000-of-00001: tensor
+    model/reverb_model/reverb_dict/layer_with_weights-0/embeddings [10, 24000] float32 LE at byte
+    offset 308892) -- a real IR for the reverb parity tests.
+
+        python -c "import sys; sys.path.insert(0, 'tests/golden'); import make_golden as m; m.make_ir_fixture()"
+    """
+    path = os.path.join(REF, 'ddsp_piano', 'model_weights', 'dafx22', 'ckpt-0.data-00000-of-00001')
+    with open(path, 'rb') as f:
+        f.seek(308892)
+        ir = np.frombuffer(f.read(10 * 24000 * 4), dtype='<f4').reshape(10, 24000)
+    assert np.isfinite(ir).all() and abs(float(ir[0, 1]) - 3.1801593) < 1e-6
+    out = os.path.join(HERE, 'dafx22_reverb_ir_row0.npz')
+    np.savez_compressed(out, ir=ir[0].astype(np.float32), sample_rate=16000, piano_model=0)
+    print(f'dafx22_reverb_ir_row0: {os.path.getsize(out) / 1024:.1f} KiB')

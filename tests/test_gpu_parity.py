@@ -476,3 +476,38 @@ def test_additive_training_mode_vs_oracle_long(dp, dev):
         cu(x['amplitudes'], dev), cu(x['harmonic_distribution'], dev),
         cu(x['inharm_coef'], dev), cu(x['f0_hz'], dev))
     assert rel_err(other, want) > 1e-3
+
+
+def test_config1_shapes_four_notes_real_ir(dp, dev, golden_dir):
+    """BASELINE configs[0] at the processor-group level with the shipped dafx22 shapes: one 3.5 s
+    clip at 16 kHz, 16 channels of which 4 sound (MIDI 48/60/64/67 held for 625 frames, then
+    released), 96 partials, 64 noise bands, the shipped 24 000-tap impulse response with the
+    inference-time decay mask.  Controls are synthetic (the control-rate networks are out of scope)."""
+    sr, F, B, H, S, M, P = 16000, 875, 1, 96, 2, 64, 16
+    U = sr // 250
+    rng = np.random.default_rng(1)
+    ir = load(golden_dir, 'dafx22_reverb_ir_row0')['ir']
+    ir = ref.exponential_decay_mask(ir[None, :]).astype(np.float32)
+    feats_np = {}
+    for v in range(P):
+        f0 = np.full([B, F, S], 8.1758, np.float32)                  # MIDI pitch 0: gated voice
+        if v < 4:
+            hz = midi_hz([48, 60, 64, 67][v])
+            f0[:, :625, :] = (hz * (1.0 + 1e-3 * np.arange(S)))[None, None, :]
+        feats_np[f'f0_hz_{v}'] = f0
+        feats_np[f'amplitudes_{v}'] = rng.standard_normal([B, F, 1]).astype(np.float32)
+        feats_np[f'harmonic_distribution_{v}'] = rng.standard_normal([B, F, H]).astype(np.float32)
+        feats_np[f'inharm_coef_{v}'] = np.full([B, F, 1], 2e-4 * (1 + v % 4), np.float32)
+        feats_np[f'magnitudes_{v}'] = rng.standard_normal([B, F, M]).astype(np.float32)
+    feats_np['reverb_ir'] = ir
+    noises = [rng.uniform(-1, 1, [B, F * U]).astype(np.float32) for _ in range(P)]
+    want = ref.polyphonic_forward(feats_np, n_synths=P, sample_rate=sr, noise_by_voice=noises)
+    group, noise = _build_group(dp, sr, P, True)
+    for n in noises:
+        noise.push_noise(cu(n, dev))
+    out = group({k: cu(v, dev) for k, v in feats_np.items()}, return_outputs_dict=True)
+    assert rel_err(out['controls']['add']['signal'], want['dry']) < TIGHT
+    assert rel_err(out['signal'], want['signal']) < TIGHT
+    # the 12 silent channels and the released tails contribute noise only: additive part of the
+    # last channel is exactly zero in the oracle
+    assert not np.any(want['additive'][-1])

@@ -223,3 +223,20 @@ def test_exponential_decay_mask():
     ir = np.ones([1, 24000], np.float32)
     m = ref.exponential_decay_mask(ir)
     assert np.all(m[0, :16000] == 1) and abs(m[0, -1] - np.exp(-4)) < 1e-6
+
+
+def test_reverb_real_ir_fixture(golden_dir):
+    """SURVEY 8c KAT 12: the shipped dafx22 impulse response (row 0 of reverb_dict, with the
+    inference-time decay mask of sub_modules.py:339-349) against float64 direct convolution."""
+    ir = load(golden_dir, 'dafx22_reverb_ir_row0')['ir']
+    assert ir.shape == (24000,) and ir.dtype == np.float32
+    masked = ref.exponential_decay_mask(ir[None, :])
+    assert np.array_equal(masked[0, :16000], ir[:16000])            # decay starts at sample 16000
+    assert abs(masked[0, -1] / ir[-1] - np.exp(-4.0)) < 1e-6
+    rng = np.random.default_rng(12)
+    audio = (rng.standard_normal([1, 8000]) * 0.1).astype(np.float32)
+    got = ref.reverb_signal(audio, masked)
+    h = masked[0].astype(np.float64).copy()
+    h[0] = 0.0
+    want = np.convolve(audio[0].astype(np.float64), h)[:8000] + audio[0]
+    assert np.max(np.abs(got[0] - want)) <= 2e-6 * np.max(np.abs(want))
