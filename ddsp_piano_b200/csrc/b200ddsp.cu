@@ -437,7 +437,7 @@ static WorkspaceLayout carve(const b200ddsp_handle* h, int P, int B, int F, int 
   o = w.add.end;
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
-    w.tw = take((size_t)w.nfft * 8);
+    w.tw = take((size_t)w.nfft * 8 + (size_t)B * 32);   // twiddles + per-clip scales + maxima
     w.buf_a = take((size_t)B * w.nfft * 8);
     w.buf_b = take((size_t)B * w.nfft * 8);
   }
@@ -1040,6 +1040,13 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   const int n_pass = (int)radices.size();
   fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
   CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  float4* scales = reinterpret_cast<float4*>(tw + n);   // [B], right behind the twiddle table
+  unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);   // [B][2]
+  CUDA_TRY(h, cudaMemsetAsync(maxima, 0, (size_t)B * 8, st));
+  reverb_maxima_kernel<<<dim3(32, B), 256, 0, st>>>(audio, ir, maxima, N, L);
+  CHECK_LAUNCH(h, "reverb_maxima_kernel");
+  reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);
+  CHECK_LAUNCH(h, "reverb_scales_kernel");
   // forward: (audio, ir) -> Z
   float2* src = nullptr;
   float2* dst = buf_a;
@@ -1047,7 +1054,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   for (int i = 0; i < n_pass; ++i) {
     const StoreComplex sto{dst, n};
     if (i == 0) {
-      launch_fft_pass(radices[i], LoadAudioIr{audio, ir, N, L}, sto, tw, n, Ns, B, st);
+      launch_fft_pass(radices[i], LoadAudioIr{audio, ir, scales, N, L}, sto, tw, n, Ns, B, st);
     } else {
       launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, B, st);
     }
@@ -1070,7 +1077,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   for (int i = 0; i < n_pass; ++i) {
     const LoadComplex ld{src, n};
     if (i == n_pass - 1) {
-      const StoreWetPair sto{out, audio, N, full_output ? N + L - 1 : N, B, 1.0f / (float)n,
+      const StoreWetPair sto{out, audio, scales, N, full_output ? N + L - 1 : N, B, 1.0f / (float)n,
                              full_output ? 0 : h->cfg.reverb_add_dry};
       launch_fft_pass(radices[i], ld, sto, tw, n, Ns, pairs, st);
     } else {
@@ -1095,7 +1102,7 @@ static int reverb_entry(b200ddsp_handle* h, const float* audio, const float* ir,
   if (!audio || !ir || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
   if (out == audio) return fail(h, B200DDSP_BAD_ARGUMENT, "out may not alias audio");
   const int n = fft_size_for(N, L);
-  const size_t tw_b = align_up((size_t)n * 8), buf_b = align_up((size_t)B * n * 8);
+  const size_t tw_b = align_up((size_t)n * 8 + (size_t)B * 32), buf_b = align_up((size_t)B * n * 8);
   const size_t need = tw_b + 2 * buf_b;
   if (!workspace || workspace_bytes < need)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "reverb needs %zu workspace bytes, got %zu", need,

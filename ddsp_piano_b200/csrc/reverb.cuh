@@ -127,12 +127,57 @@ struct StoreComplex {
     dst[(size_t)batch * n + i] = v;
   }
 };
-// z = audio + i * ir with ir[0] masked (Reverb._mask_dry_ir), zero padded to n
+// Per-clip power-of-two normalisation.  Audio and IR travel through ONE complex transform and are
+// separated afterwards as (Z[k] +- conj Z[n-k]) / 2, so rounding noise of the larger operand leaks
+// into the smaller one: without normalisation the error of the wet signal grows like
+// |audio| / |ir| (quadratically with the input level).  Scaling both to [0.5, 1) by exact powers
+// of two (undone exactly in the final store) makes the error independent of the levels.
+// scales[b] = (2^-ea, 2^-ei, 2^(ea+ei)) with 2^ea >= max|audio[b]|, 2^ei >= max|ir[b, 1:]|.
+// Step 1: per-clip maxima (bit patterns of non-negative floats order like unsigned ints), many
+// CTAs per clip; maxima must be zeroed beforehand.  Step 2: one thread per clip -> scales.
+__global__ void __launch_bounds__(256) reverb_maxima_kernel(const float* __restrict__ audio,
+                                                            const float* __restrict__ ir,
+                                                            unsigned int* __restrict__ maxima, int N,
+                                                            int L) {
+  const int b = blockIdx.y;
+  const int stride = gridDim.x * blockDim.x;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  float ma = 0.f, mi = 0.f;
+  for (int i = i0; i < N; i += stride) ma = fmaxf(ma, fabsf(__ldg(audio + (size_t)b * N + i)));
+  for (int i = 1 + i0; i < L; i += stride) mi = fmaxf(mi, fabsf(__ldg(ir + (size_t)b * L + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // NaN compares false everywhere above and is dropped; +inf survives and disables scaling
+    atomicMax(maxima + 2 * b, __float_as_uint(ma));
+    atomicMax(maxima + 2 * b + 1, __float_as_uint(mi));
+  }
+}
+
+__global__ void reverb_scales_kernel(const unsigned int* __restrict__ maxima,
+                                     float4* __restrict__ scales, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float ma = __uint_as_float(maxima[2 * b]), mi = __uint_as_float(maxima[2 * b + 1]);
+  // exponent e with 2^e > m (finite); m == 0 or non-finite -> no scaling
+  int ea = 0, ei = 0;
+  if (ma > 0.f && ma < 3.0e38f) frexpf(ma, &ea);
+  if (mi > 0.f && mi < 3.0e38f) frexpf(mi, &ei);
+  ea = max(-60, min(60, ea));
+  ei = max(-60, min(60, ei));
+  scales[b] = make_float4(ldexpf(1.f, -ea), ldexpf(1.f, -ei), ldexpf(1.f, ea + ei), 0.f);
+}
+
+// z = audio / 2^ea + i * ir / 2^ei with ir[0] masked (Reverb._mask_dry_ir), zero padded to n
 struct LoadAudioIr {
-  const float* audio; const float* ir; int N, L;
+  const float* audio; const float* ir; const float4* scales; int N, L;
   __device__ __forceinline__ float2 operator()(int batch, int i) const {
-    const float re = (i < N) ? __ldg(audio + (size_t)batch * N + i) : 0.f;
-    const float im = (i > 0 && i < L) ? __ldg(ir + (size_t)batch * L + i) : 0.f;
+    const float4 sc = __ldg(scales + batch);
+    const float re = (i < N) ? __ldg(audio + (size_t)batch * N + i) * sc.x : 0.f;
+    const float im = (i > 0 && i < L) ? __ldg(ir + (size_t)batch * L + i) * sc.y : 0.f;
     return make_float2(re, im);
   }
 };
@@ -140,15 +185,15 @@ struct LoadAudioIr {
 // (N for padding 'same' with delay_compensation = 0; N + L - 1 for the 'valid' form used by the
 // timeline overlap-add), scale by 1/n, add the dry signal (add_dry needs n_out <= N)
 struct StoreWetPair {
-  float* out; const float* audio; int N, n_out, B; float inv_n; int add_dry;
+  float* out; const float* audio; const float4* scales; int N, n_out, B; float inv_n; int add_dry;
   __device__ __forceinline__ void operator()(int batch, int i, float2 v) const {
     if (i >= n_out) return;
     const int b0 = 2 * batch, b1 = b0 + 1;
-    float y0 = v.x * inv_n;
+    float y0 = v.x * inv_n * __ldg(scales + b0).z;
     if (add_dry) y0 = __fadd_rn(y0, __ldg(audio + (size_t)b0 * N + i));
     out[(size_t)b0 * n_out + i] = y0;
     if (b1 < B) {
-      float y1 = v.y * inv_n;
+      float y1 = v.y * inv_n * __ldg(scales + b1).z;
       if (add_dry) y1 = __fadd_rn(y1, __ldg(audio + (size_t)b1 * N + i));
       out[(size_t)b1 * n_out + i] = y1;
     }

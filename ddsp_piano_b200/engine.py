@@ -201,7 +201,7 @@ class Engine:
         while n < N + L - 1:
             n *= 2
         al = lambda x: (x + 255) // 256 * 256
-        ws = self.workspace(al(n * 8) + 2 * al(B * n * 8))
+        ws = self.workspace(al(n * 8 + B * 32) + 2 * al(B * n * 8))
         out = torch.empty([B, N + L - 1] if full else [B, N], dtype=torch.float32,
                           device=self.device)
         fn = self.lib.b200ddsp_reverb_full if full else self.lib.b200ddsp_reverb

@@ -511,3 +511,123 @@ def test_config1_shapes_four_notes_real_ir(dp, dev, golden_dir):
     # the 12 silent channels and the released tails contribute noise only: additive part of the
     # last channel is exactly zero in the oracle
     assert not np.any(want['additive'][-1])
+
+
+# ------------------- BASELINE.json full sizes (configs[2]: B16 P16 S2 H96 M64 F750 L72000) ------
+
+@pytest.fixture(scope='module')
+def full_size(dp, dev):
+    import bench
+    w = bench.WORKLOADS['full']
+    x = bench.synthetic_inputs(w, seed=0)
+    rng = np.random.default_rng(2024)
+    U = w['sr'] // 250
+    noises = [rng.uniform(-1, 1, [w['B'], w['F'] * U]).astype(np.float32) for _ in range(w['P'])]
+    return w, x, noises
+
+
+def _forward_full(dp, dev, w, x, noises, voices=None, reverb=True):
+    voices = list(range(w['P'])) if voices is None else voices
+    group, noise = _build_group(dp, w['sr'], len(voices), True, reverb=reverb)
+    feats = {}
+    for i, v in enumerate(voices):
+        for k in ('amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz', 'magnitudes'):
+            feats[f'{k}_{i}'] = cu(x[k][v], dev)
+        noise.push_noise(cu(noises[v], dev))
+    if reverb:
+        feats['reverb_ir'] = cu(x['reverb_ir'], dev)
+    out = group(feats, return_outputs_dict=True)
+    return out['controls']['add']['signal'], out['signal']
+
+
+def test_full_size_parity_on_one_clip(dp, dev, full_size):
+    """The whole batch runs on the GPU at full size; clip 5 is checked against the oracle (clips
+    are independent, so the oracle only needs that clip's controls: ~15 s of CPU)."""
+    w, x, noises = full_size
+    dry, wet = _forward_full(dp, dev, w, x, noises)
+    assert dry.shape == (16, 72000) and wet.shape == (16, 72000)
+    assert bool(torch.isfinite(wet).all())
+    b = 5
+    feats_np = {f'{k}_{v}': x[k][v][b:b + 1] for k in ('amplitudes', 'harmonic_distribution',
+                                                        'inharm_coef', 'f0_hz', 'magnitudes')
+                for v in range(w['P'])}
+    feats_np['reverb_ir'] = x['reverb_ir'][b:b + 1]
+    want = ref.polyphonic_forward(feats_np, n_synths=w['P'], sample_rate=w['sr'],
+                                  noise_by_voice=[n[b:b + 1] for n in noises])
+    assert rel_err(dry[b:b + 1], want['dry']) < TIGHT
+    assert rel_err(wet[b:b + 1], want['signal']) < TIGHT
+
+
+def test_full_size_properties(dp, dev, full_size):
+    """Size-independent properties at BASELINE's full size: run-to-run bitwise determinism,
+    superposition over voices (the DAG is a sum), linearity and identity of the reverb."""
+    w, x, noises = full_size
+    dry, wet = _forward_full(dp, dev, w, x, noises)
+    dry2, wet2 = _forward_full(dp, dev, w, x, noises)
+    assert torch.equal(dry, dry2) and torch.equal(wet, wet2)
+    lo, _ = _forward_full(dp, dev, w, x, noises, voices=list(range(0, 8)), reverb=False)
+    hi, _ = _forward_full(dp, dev, w, x, noises, voices=list(range(8, 16)), reverb=False)
+    scale = float(dry.abs().max())
+    assert float((lo + hi - dry).abs().max()) < 2e-6 * scale
+    rv = dp.Reverb(trainable=False)
+    ir = cu(x['reverb_ir'], dev)
+    assert torch.equal(rv(dry, ir), wet)                                  # same kernel, same bits
+    a = rv(2.0 * dry, ir)
+    # homogeneity (not bit exact: audio and IR share one complex transform, so scaling the audio
+    # changes the rounding of the packed butterflies)
+    assert float((a - 2.0 * wet).abs().max()) < TIGHT * float(wet.abs().max())
+    delta = torch.zeros_like(ir)
+    delta[:, 0] = 1.0                                                     # masked tap: wet part is 0
+    assert float((rv(dry, delta) - dry).abs().max()) < TIGHT * scale
+    shift = torch.zeros_like(ir)
+    shift[:, 7] = 0.5
+    want = dry.clone()
+    want[:, 7:] += 0.5 * dry[:, :-7]
+    assert float((rv(dry, shift) - want).abs().max()) < TIGHT * scale
+
+
+@pytest.mark.parametrize('P,B,F,host', [(1, 1, 1, False), (1, 2, 7, True), (3, 1, 40, True),
+                                        (5, 2, 33, False), (16, 1, 11, True)])
+def test_dag_edge_shapes(dp, dev, P, B, F, host):
+    """Smallest and ragged shapes (one voice, one frame, F not a multiple of the 32-frame noise tile,
+    P not a multiple of the voice groups / noise slices), device and host entry points vs oracle."""
+    sr, H, S, M, L = 24000, 96, 2, 64, 500
+    U = sr // 250
+    rng = np.random.default_rng(P * 100 + F)
+    feats_np = {}
+    for v in range(P):
+        for k, a in voice_inputs(rng, B, F, H, S, M).items():
+            feats_np[f'{k}_{v}'] = a
+    feats_np['reverb_ir'] = (rng.standard_normal([B, L]) * 1e-2).astype(np.float32)
+    noises = [rng.uniform(-1, 1, [B, F * U]).astype(np.float32) for _ in range(P)]
+    want = ref.polyphonic_forward(feats_np, n_synths=P, sample_rate=sr, noise_by_voice=noises)
+    group, noise = _build_group(dp, sr, P, True)
+    for n in noises:
+        noise.push_noise(torch.from_numpy(n) if host else cu(n, dev))
+    feats = {k: (torch.from_numpy(v) if host else cu(v, dev)) for k, v in feats_np.items()}
+    out = group(feats, return_outputs_dict=True)
+    torch.cuda.synchronize()
+    assert rel_err(out['controls']['add']['signal'], want['dry']) < TIGHT
+    assert rel_err(out['signal'], want['signal']) < TIGHT
+
+
+@pytest.mark.parametrize('audio_gain,ir_gain', [(1e3, 1.0), (1.0, 1e-4), (1e-3, 1e2), (0.0, 1.0)])
+def test_reverb_error_is_level_independent(dp, dev, audio_gain, ir_gain):
+    """Audio and IR share one complex FFT; per-clip power-of-two normalisation keeps the error of the
+    wet signal independent of their relative levels (without it it grows like |audio| / |ir|)."""
+    rng = np.random.default_rng(5)
+    N, L, B = 24000, 24000, 3
+    audio = (rng.standard_normal([B, N]) * audio_gain).astype(np.float32)
+    audio[1] *= 1e-3                                            # clips of very different loudness
+    ir = (rng.standard_normal([B, L]) * np.exp(-6 * np.arange(L) / L) * 1e-2 * ir_gain).astype(np.float32)
+    wet = dp.Reverb(trainable=False, add_dry=False)(cu(audio, dev), cu(ir, dev)).cpu().numpy()
+    from scipy.signal import fftconvolve
+    for b in range(B):
+        h = ir[b].astype(np.float64).copy()
+        h[0] = 0
+        want = fftconvolve(audio[b].astype(np.float64), h)[:N]
+        scale = np.max(np.abs(want))
+        if scale == 0:      # silence in: rounding noise of the packed transform only
+            assert np.max(np.abs(wet[b])) < 1e-6 * np.max(np.abs(ir[b]))
+        else:
+            assert np.max(np.abs(wet[b] - want)) < 5e-6 * scale
