@@ -38,7 +38,7 @@ WORKLOADS = {
     'stress': dict(name='configs[4]: batch16 x 3s, poly32, H128, M96, full chain, 48kHz',
                    sr=48000, B=16, P=32, S=2, H=128, M=96, F=750, L=144000),
 }
-METRIC = 'real-time factor (audio-sec/wall-sec) @24kHz batch16 poly16'
+METRIC = 'real-time factor (audio-sec/wall-sec) @24kHz batch16 poly16; HBM GB/s %peak'   # BASELINE.json
 UNIT = 'x real time'
 
 
@@ -313,14 +313,15 @@ def run_gpu(args, w):
         barrier()
         return sum(a.elapsed_time(b) for a, b in evs)
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the last timed loop
+    # (the resident loop alone lasts ~60 ms, shorter than nvidia-smi's start-up)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     launches0 = dp.total_launches()
-    sampler = ClockSampler(local)
-    sampler.start()
     stages = {}
     total_ms = timed(step_resident, args.steps, stages)
-    clocks = sampler.stop()
     launches = dp.total_launches() - launches0
 
     for _ in range(3):
@@ -335,6 +336,7 @@ def run_gpu(args, w):
         group(dict(feats_held), return_outputs_dict=False)
     held_stages = {}
     held_ms = timed(lambda: group(dict(feats_held), return_outputs_dict=False), args.steps, held_stages)
+    clocks = sampler.stop()
 
     def reduce_max(v):
         if world == 1:

@@ -111,6 +111,12 @@ def load():
     lib.b200ddsp_reverb.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_reverb_full.restype = ci
     lib.b200ddsp_reverb_full.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp]
+    lib.b200ddsp_fft_convolve.restype = ci
+    lib.b200ddsp_fft_convolve.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, sz, vp]
+    lib.b200ddsp_fdn_ir.restype = ci
+    lib.b200ddsp_fdn_ir.argtypes = [vp] + [vp] * 7 + [ci, c_float_p, ctypes.c_float, vp, ci, vp, sz, vp]
+    lib.b200ddsp_fdn_workspace_bytes.restype = sz
+    lib.b200ddsp_fdn_workspace_bytes.argtypes = [vp, ctypes.c_float, ci]
     lib.b200ddsp_forward_polyphonic.restype = ci
     lib.b200ddsp_forward_polyphonic.argtypes = [vp, ctypes.POINTER(Voice), ci, vp, vp, vp,
                                                 ci, ci, ci, ci, ci, ci, u64, vp, sz, vp]
@@ -132,8 +138,10 @@ def load():
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
-           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full',
+           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_fdn_ir',
+           'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
            'b200ddsp_workspace_bytes_host', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
+CONV_MASK_IR0, CONV_ADD_DRY, CONV_FULL = 1, 2, 4
 STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise', 'reverb', 'mix']

@@ -20,6 +20,7 @@
 #include "additive_fast.cuh"
 #include "common.cuh"
 #include "controls.cuh"
+#include "fdn.cuh"
 #include "noise.cuh"
 #include "reverb.cuh"
 
@@ -1030,10 +1031,14 @@ static std::vector<int> fft_radices(int n) {
   return r;
 }
 
-// full_output: write all N + L - 1 samples of the convolution and no dry signal.
+// flags: B200DDSP_CONV_*; -1 = the handle's effects.Reverb configuration (mask ir[0], add_dry).
 static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
                       int N, int L, float2* tw, float2* buf_a, float2* buf_b, cudaStream_t st,
-                      bool full_output = false) {
+                      int flags = -1) {
+  if (flags < 0) flags = B200DDSP_CONV_MASK_IR0 | (h->cfg.reverb_add_dry ? B200DDSP_CONV_ADD_DRY : 0);
+  const bool full_output = (flags & B200DDSP_CONV_FULL) != 0;
+  const int add_dry = (!full_output && (flags & B200DDSP_CONV_ADD_DRY)) ? 1 : 0;
+  const int first_tap = (flags & B200DDSP_CONV_MASK_IR0) ? 1 : 0;
   StageTimer tm(h, B200DDSP_STAGE_REVERB, st);
   const int n = fft_size_for(N, L);
   const std::vector<int> radices = fft_radices(n);
@@ -1043,7 +1048,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   float4* scales = reinterpret_cast<float4*>(tw + n);   // [B], right behind the twiddle table
   unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);   // [B][2]
   CUDA_TRY(h, cudaMemsetAsync(maxima, 0, (size_t)B * 8, st));
-  reverb_maxima_kernel<<<dim3(32, B), 256, 0, st>>>(audio, ir, maxima, N, L);
+  reverb_maxima_kernel<<<dim3(32, B), 256, 0, st>>>(audio, ir, maxima, N, L, first_tap);
   CHECK_LAUNCH(h, "reverb_maxima_kernel");
   reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);
   CHECK_LAUNCH(h, "reverb_scales_kernel");
@@ -1054,7 +1059,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   for (int i = 0; i < n_pass; ++i) {
     const StoreComplex sto{dst, n};
     if (i == 0) {
-      launch_fft_pass(radices[i], LoadAudioIr{audio, ir, scales, N, L}, sto, tw, n, Ns, B, st);
+      launch_fft_pass(radices[i], LoadAudioIr{audio, ir, scales, N, L, first_tap}, sto, tw, n, Ns, B, st);
     } else {
       launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, B, st);
     }
@@ -1078,7 +1083,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
     const LoadComplex ld{src, n};
     if (i == n_pass - 1) {
       const StoreWetPair sto{out, audio, scales, N, full_output ? N + L - 1 : N, B, 1.0f / (float)n,
-                             full_output ? 0 : h->cfg.reverb_add_dry};
+                             add_dry};
       launch_fft_pass(radices[i], ld, sto, tw, n, Ns, pairs, st);
     } else {
       launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, tw, n, Ns, pairs, st);
@@ -1093,7 +1098,7 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
 
 static int reverb_entry(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
                         int B, int N, int L, void* workspace, size_t workspace_bytes,
-                        void* stream, bool full_output) {
+                        void* stream, int flags) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
   if (B < 1 || N < 1 || L < 1 || B > 65535)
     return fail(h, B200DDSP_BAD_SHAPE, "B=%d N=%d L=%d must be positive", B, N, L);
@@ -1111,19 +1116,76 @@ static int reverb_entry(b200ddsp_handle* h, const float* audio, const float* ir,
   char* w = (char*)workspace;
   reset_stage_flags(h);
   return run_reverb(h, audio, ir, out, B, N, L, (float2*)w, (float2*)(w + tw_b),
-                    (float2*)(w + tw_b + buf_b), (cudaStream_t)stream, full_output);
+                    (float2*)(w + tw_b + buf_b), (cudaStream_t)stream, flags);
 }
 
 extern "C" int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
                                int B, int N, int L, void* workspace, size_t workspace_bytes,
                                void* stream) {
-  return reverb_entry(h, audio, ir, out, B, N, L, workspace, workspace_bytes, stream, false);
+  return reverb_entry(h, audio, ir, out, B, N, L, workspace, workspace_bytes, stream, -1);
 }
 
 extern "C" int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir,
                                     float* out_full, int B, int N, int L, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  return reverb_entry(h, audio, ir, out_full, B, N, L, workspace, workspace_bytes, stream, true);
+  return reverb_entry(h, audio, ir, out_full, B, N, L, workspace, workspace_bytes, stream,
+                      B200DDSP_CONV_MASK_IR0 | B200DDSP_CONV_FULL);
+}
+
+extern "C" int b200ddsp_fft_convolve(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
+                                     int B, int N, int L, int flags, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (flags < 0 || flags > 7) return fail(h, B200DDSP_BAD_ARGUMENT, "bad convolution flags %d", flags);
+  return reverb_entry(h, audio, ir, out, B, N, L, workspace, workspace_bytes, stream, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// feedback-delay-network impulse response
+// ---------------------------------------------------------------------------------------------
+
+extern "C" size_t b200ddsp_fdn_workspace_bytes(const b200ddsp_handle* h, float sampling_rate, int B) {
+  if (!h || B < 1 || !(sampling_rate >= 1.0f)) return 0;
+  const int n = (int)(2.0f * sampling_rate);
+  return align_up((size_t)B * (n / 2 + 1) * sizeof(float2));
+}
+
+extern "C" int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, const float* output_gain,
+                               const float* gain_allpass, const float* delays_allpass,
+                               const float* time_rev_0_sec, const float* alpha_tone,
+                               const float* early_ir, int E, const float* delay_values,
+                               float sampling_rate, float* ir_out, int B, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!input_gain || !output_gain || !gain_allpass || !delays_allpass || !time_rev_0_sec || !alpha_tone ||
+      !ir_out || (E > 0 && !early_ir))
+    return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (B < 1 || B > 65535 || E < 0) return fail(h, B200DDSP_BAD_SHAPE, "B=%d E=%d", B, E);
+  if (!(sampling_rate >= 1.0f) || sampling_rate > 4.0e6f)
+    return fail(h, B200DDSP_BAD_SHAPE, "sampling_rate %g out of range", (double)sampling_rate);
+  const int n = (int)(2.0f * sampling_rate);            // freq_points = int(2 * sampling_rate), :83
+  if (n < 2 || (n & 1)) return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "freq_points=%d must be even", n);
+  const size_t need = b200ddsp_fdn_workspace_bytes(h, sampling_rate, B);
+  if (!workspace || workspace_bytes < need)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "fdn_ir needs %zu workspace bytes, got %zu", need,
+                workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  static const float kDefaultDelays[kFdnLines] = {233, 311, 421, 461, 587, 613, 789, 891};
+  FdnArgs a{};
+  a.input_gain = input_gain; a.output_gain = output_gain;
+  a.gain_allpass = gain_allpass; a.delays_allpass = delays_allpass;
+  a.time_rev_0_sec = time_rev_0_sec; a.alpha_tone = alpha_tone;
+  a.early_ir = early_ir;
+  a.H = (float2*)workspace;
+  a.ir = ir_out;
+  for (int d = 0; d < kFdnLines; ++d) a.delay_values[d] = delay_values ? delay_values[d] : kDefaultDelays[d];
+  a.sampling_rate = sampling_rate;
+  a.n = n; a.E = E < n ? E : n; a.B = B;
+  cudaStream_t st = (cudaStream_t)stream;
+  fdn_transfer_kernel<<<dim3((n / 2 + 1 + 127) / 128, B), 128, 0, st>>>(a);
+  CHECK_LAUNCH(h, "fdn_transfer_kernel");
+  fdn_irfft_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(a);
+  CHECK_LAUNCH(h, "fdn_irfft_kernel");
+  return B200DDSP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -138,13 +138,13 @@ struct StoreComplex {
 __global__ void __launch_bounds__(256) reverb_maxima_kernel(const float* __restrict__ audio,
                                                             const float* __restrict__ ir,
                                                             unsigned int* __restrict__ maxima, int N,
-                                                            int L) {
+                                                            int L, int first_tap) {
   const int b = blockIdx.y;
   const int stride = gridDim.x * blockDim.x;
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   float ma = 0.f, mi = 0.f;
   for (int i = i0; i < N; i += stride) ma = fmaxf(ma, fabsf(__ldg(audio + (size_t)b * N + i)));
-  for (int i = 1 + i0; i < L; i += stride) mi = fmaxf(mi, fabsf(__ldg(ir + (size_t)b * L + i)));
+  for (int i = first_tap + i0; i < L; i += stride) mi = fmaxf(mi, fabsf(__ldg(ir + (size_t)b * L + i)));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
@@ -171,13 +171,14 @@ __global__ void reverb_scales_kernel(const unsigned int* __restrict__ maxima,
   scales[b] = make_float4(ldexpf(1.f, -ea), ldexpf(1.f, -ei), ldexpf(1.f, ea + ei), 0.f);
 }
 
-// z = audio / 2^ea + i * ir / 2^ei with ir[0] masked (Reverb._mask_dry_ir), zero padded to n
+// z = audio / 2^ea + i * ir / 2^ei, zero padded to n; first_tap = 1 masks ir[0]
+// (Reverb._mask_dry_ir)
 struct LoadAudioIr {
-  const float* audio; const float* ir; const float4* scales; int N, L;
+  const float* audio; const float* ir; const float4* scales; int N, L, first_tap;
   __device__ __forceinline__ float2 operator()(int batch, int i) const {
     const float4 sc = __ldg(scales + batch);
     const float re = (i < N) ? __ldg(audio + (size_t)batch * N + i) * sc.x : 0.f;
-    const float im = (i > 0 && i < L) ? __ldg(ir + (size_t)batch * L + i) * sc.y : 0.f;
+    const float im = (i >= first_tap && i < L) ? __ldg(ir + (size_t)batch * L + i) * sc.y : 0.f;
     return make_float2(re, im);
   }
 };

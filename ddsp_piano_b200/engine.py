@@ -182,7 +182,47 @@ class Engine:
         """'valid'-padded wet signal [B, N + L - 1] (no dry), see sharding.timeline_reverb."""
         return self.reverb(audio, ir, full=True)
 
-    def reverb(self, audio, ir, full=False):
+    def fft_convolve(self, audio, ir, mask_ir0=False, add_dry=False, full=False):
+        """ddsp.core.fft_convolve(audio, ir, delay_compensation=0) + the reverbs' options."""
+        flags = (_lib.CONV_MASK_IR0 if mask_ir0 else 0) | (_lib.CONV_ADD_DRY if add_dry else 0) | \
+            (_lib.CONV_FULL if full else 0)
+        return self.reverb(audio, ir, full=full, flags=flags)
+
+    def fdn_ir(self, input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
+               alpha_tone, early_ir, sampling_rate, delay_values=None):
+        """FeedbackDelayNetwork.get_ir for a batch of parameter rows -> [B, int(2 * sampling_rate)]."""
+        ig = self.tensor(input_gain, 'input_gain')
+        batched = ig.dim() == 2
+        B = ig.shape[0] if batched else 1
+        def prep(x, name, shape):
+            x = self.tensor(x, name).reshape(shape)
+            return x if x.is_contiguous() else x.contiguous()
+        ig = prep(ig, 'input_gain', [B, 8])
+        og = prep(output_gain, 'output_gain', [B, 8])
+        ga = prep(gain_allpass, 'gain_allpass', [B, 8, 4])
+        da = prep(delays_allpass, 'delays_allpass', [B, 8, 4])
+        t0 = prep(time_rev_0_sec, 'time_rev_0_sec', [B])
+        al = prep(alpha_tone, 'alpha_tone', [B])
+        er = self.tensor(early_ir, 'early_ir')
+        er = prep(er, 'early_ir', [B, er.numel() // B])
+        E = er.shape[1]
+        n = int(2 * float(sampling_rate))
+        dv = None
+        if delay_values is not None:
+            vals = [float(v) for v in torch.as_tensor(delay_values).reshape(-1).tolist()]
+            if len(vals) != 8:
+                raise ValueError('the CUDA path implements the reference\'s fixed 8 delay lines')
+            dv = (ctypes.c_float * 8)(*vals)
+        ws = self.workspace(self.lib.b200ddsp_fdn_workspace_bytes(self.handle, float(sampling_rate), B))
+        out = torch.empty([B, n], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_fdn_ir(
+                self.handle, ig.data_ptr(), og.data_ptr(), ga.data_ptr(), da.data_ptr(), t0.data_ptr(),
+                al.data_ptr(), er.data_ptr(), E, dv, float(sampling_rate), out.data_ptr(), B,
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return out if batched else out[0]
+
+    def reverb(self, audio, ir, full=False, flags=None):
         audio = self.tensor(audio, 'audio', 2)
         ir = self.tensor(ir, 'ir')
         if ir.dim() == 1:
@@ -204,10 +244,15 @@ class Engine:
         ws = self.workspace(al(n * 8 + B * 32) + 2 * al(B * n * 8))
         out = torch.empty([B, N + L - 1] if full else [B, N], dtype=torch.float32,
                           device=self.device)
-        fn = self.lib.b200ddsp_reverb_full if full else self.lib.b200ddsp_reverb
         with torch.cuda.device(self.device):
-            self.check(fn(self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L,
-                          ws.data_ptr(), ws.numel(), self.stream()))
+            if flags is not None:
+                self.check(self.lib.b200ddsp_fft_convolve(
+                    self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L, flags,
+                    ws.data_ptr(), ws.numel(), self.stream()))
+            else:
+                fn = self.lib.b200ddsp_reverb_full if full else self.lib.b200ddsp_reverb
+                self.check(fn(self.handle, audio.data_ptr(), ir.data_ptr(), out.data_ptr(), B, N, L,
+                              ws.data_ptr(), ws.numel(), self.stream()))
         return out
 
     def _voice_array(self, voices, host):

@@ -235,6 +235,58 @@ class Reverb(Processor):
         return eng.reverb(audio, ir)
 
 
+class FeedbackDelayNetwork(Processor):
+    """modules/fdn_reverb.py:20-410 with ``trainable=False``: frequency-sampled feedback delay
+    network (8 delay lines, Householder mixing, one-pole reverberation-time control, 4 allpasses
+    per line, FIR early reflections).  ``get_ir`` is what
+    ``MultiInstrumentFeedbackDelayReverb`` (modules/sub_modules.py:368-446, the reverb model of
+    configs/maestro-v2.gin) calls to produce ``reverb_ir``; as a DAG processor
+    (configs/ENSTDkCl-*.gin) ``get_signal`` convolves the dry audio with that IR."""
+
+    def __init__(self, trainable=False, name='DelayNetwork', sampling_rate=16000.0, delay_lines=8,
+                 delay_values=None, delays_allpass=None, early_ir_length=200, early_reflections=6,
+                 time_control_bands=6, delay_trainable=False):
+        super().__init__(name=name, trainable=trainable)
+        if trainable:
+            raise ValueError('FeedbackDelayNetwork(trainable=True) owns tf.Variables in the reference; '
+                             'the hot path implements the trainable=False form (parameters are inputs)')
+        if delay_lines != 8:
+            raise ValueError('the reference fixes the network to 8 delay lines')
+        self.sampling_rate = float(sampling_rate)
+        self.freq_points = int(2 * self.sampling_rate)
+        self.delay_values = delay_values
+        self.delays_allpass = delays_allpass
+        self.early_ir_length = early_ir_length
+        self.delay_lines = delay_lines
+
+    def __len__(self):
+        return self.delay_lines
+
+    def build(self, input_shape=None):
+        """The reference fills in its fixed delay values here (fdn_reverb.py:93-97)."""
+        if self.delay_values is None:
+            self.delay_values = [233., 311., 421., 461., 587., 613., 789., 891.]
+
+    def _engine(self, *tensors):
+        return get_engine(_device_of(*tensors), **_DEFAULT_CFG)
+
+    def get_ir(self, input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
+               alpha_tone, early_ir):
+        return self._engine(input_gain, early_ir).fdn_ir(
+            input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec, alpha_tone,
+            early_ir, self.sampling_rate, self.delay_values)
+
+    def get_controls(self, audio_dry=None, input_gain=None, output_gain=None, gain_allpass=None,
+                     delays_allpass=None, time_rev_0_sec=None, alpha_tone=None, early_ir=None):
+        ir = self.get_ir(input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
+                         alpha_tone, early_ir)
+        return {'audio': audio_dry, 'ir': ir}
+
+    def get_signal(self, audio, ir):
+        # fft_convolve(audio, ir[None], delay_compensation=0): no dry path, ir[0] kept
+        return self._engine(audio, ir).fft_convolve(audio, ir)
+
+
 def polyphonic_dag(additive, noise, reverb=None,
                    additive_controls=['amps', 'harmonic_distribution', 'f0_hz'],
                    noise_controls=['noise_magnitudes'], reverb_controls=[], n_synths=16):

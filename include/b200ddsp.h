@@ -160,6 +160,33 @@ int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, flo
 int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir, float* out_full,
                          int B, int N, int L, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ddsp.core.fft_convolve(audio, ir, padding, delay_compensation=0) with the options the reverbs
+ * of the reference use.  flags: B200DDSP_CONV_MASK_IR0 zeroes ir[:,0] (effects.Reverb masks the dry
+ * tap), B200DDSP_CONV_ADD_DRY adds the input (effects.Reverb add_dry), B200DDSP_CONV_FULL writes
+ * N + L - 1 samples (padding='valid') instead of N.  flags = 0 is FeedbackDelayNetwork.get_signal
+ * (modules/fdn_reverb.py:406-410). */
+#define B200DDSP_CONV_MASK_IR0 1
+#define B200DDSP_CONV_ADD_DRY 2
+#define B200DDSP_CONV_FULL 4
+int b200ddsp_fft_convolve(b200ddsp_handle* h, const float* audio, const float* ir, float* out, int B,
+                          int N, int L, int flags, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* FeedbackDelayNetwork.get_ir -- modules/fdn_reverb.py:339-360 over get_late_ir :178-337: the
+ * impulse response of the 8-line feedback delay network that modules/sub_modules.py:368-446
+ * (MultiInstrumentFeedbackDelayReverb, configs/maestro-v2.gin:118-122) feeds to effects.Reverb.
+ * All parameters are device tensors, one row per batch element: input_gain, output_gain [B,8],
+ * gain_allpass, delays_allpass [B,8,4], time_rev_0_sec, alpha_tone [B], early_ir [B,E].
+ * delay_values: HOST array of 8 delay-line lengths, or NULL for the reference's fixed values
+ * (fdn_reverb.py:96).  ir_out [B, n], n = (int)(2 * sampling_rate).  workspace >=
+ * b200ddsp_fdn_workspace_bytes(). */
+int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, const float* output_gain,
+                    const float* gain_allpass, const float* delays_allpass,
+                    const float* time_rev_0_sec, const float* alpha_tone, const float* early_ir, int E,
+                    const float* delay_values, float sampling_rate, float* ir_out, int B,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t b200ddsp_fdn_workspace_bytes(const b200ddsp_handle* h, float sampling_rate, int B);
+
 /* The whole DAG of modules/polyphonic_dag.py:21-42 as wired by configs/dafx22.gin:91-100,
  * entered at modules/piano_model.py:160: for every voice get_controls + get_signal of the
  * additive and noise processors, the running MultiAdd sum, then the reverb.

@@ -23,6 +23,9 @@ class Processor:
     def get_signal(self, *args, **kwargs):
         raise NotImplementedError
 
+    def build(self, input_shape=None):     # keras Layer.build: nothing to do in the stand-in
+        self.built = True
+
 
 class ProcessorGroup:
     """DAG of (processor, [input keys]) nodes run in order over a growing outputs dict."""

@@ -82,3 +82,103 @@ class _Layer:
 
 
 keras = types.SimpleNamespace(layers=types.SimpleNamespace(Layer=_Layer))
+
+
+# ---- symbols used by modules/fdn_reverb.py (executed for tests/golden/fdn_*.npz) ---------------
+complex64 = np.complex64
+
+
+class Tensor(np.ndarray):
+    """isinstance(x, tf.Tensor) is False for plain ndarrays, so fdn_reverb.tf_complex64 takes its
+    convert_to_tensor branch -- same values."""
+
+
+def cast(x, dtype=None):
+    return np.asarray(x).astype(dtype)
+
+
+def convert_to_tensor(x, dtype=None):
+    return np.asarray(x).astype(dtype) if dtype is not None else np.asarray(x)
+
+
+def complex(real, imag):  # noqa: A001  (tf.complex)
+    real = np.asarray(real, dtype=np.float32)
+    return (real + 1j * np.asarray(imag, dtype=np.float32)).astype(np.complex64)
+
+
+def exp(x):
+    return np.exp(x)
+
+
+def floor(x):
+    return np.floor(x)
+
+
+def pow(x, y):  # noqa: A001
+    y = np.asarray(y)
+    return np.power(np.asarray(x, dtype=y.dtype) if np.isscalar(x) else x, y)
+
+
+def stack(values, axis=0):
+    return np.stack(values, axis=axis)
+
+
+def range(n, dtype=np.int32):  # noqa: A001
+    return np.arange(n).astype(dtype)
+
+
+def eye(n, batch_shape=None, dtype=np.float32):
+    e = np.eye(n, dtype=dtype)
+    if batch_shape:
+        e = np.broadcast_to(e, list(batch_shape) + [n, n]).copy()
+    return e
+
+
+def ones(shape, dtype=np.float32):
+    return np.ones(shape, dtype=dtype)
+
+
+def expand_dims(x, axis):
+    return np.expand_dims(x, axis)
+
+
+def squeeze(x, axis=None):
+    return np.squeeze(x, axis=axis)
+
+
+def tile(x, multiples):
+    return np.tile(x, multiples)
+
+
+def repeat(x, repeats, axis=None):
+    return np.repeat(x, repeats, axis=axis)
+
+
+def transpose(x, perm=None):
+    return np.transpose(x, perm)
+
+
+def pad(x, paddings):
+    return np.pad(x, paddings)
+
+
+def matmul(a, b):
+    return np.matmul(a, b)
+
+
+def reduce_prod(x, axis=None):
+    x = np.asarray(x)
+    return np.prod(x, axis=axis, dtype=x.dtype)
+
+
+def _batch_diag(x):
+    x = np.asarray(x)
+    out = np.zeros(x.shape + (x.shape[-1],), dtype=x.dtype)
+    idx = np.arange(x.shape[-1])
+    out[..., idx, idx] = x
+    return out
+
+
+linalg = types.SimpleNamespace(diag=_batch_diag, inv=np.linalg.inv)
+signal = types.SimpleNamespace(irfft=lambda x: np.fft.irfft(x).astype(np.float32))
+keras.activations = types.SimpleNamespace(sigmoid=lambda x: 1.0 / (1.0 + np.exp(-x)))

@@ -181,3 +181,38 @@ def make_ir_fixture():
     out = os.path.join(HERE, 'dafx22_reverb_ir_row0.npz')
     np.savez_compressed(out, ir=ir[0].astype(np.float32), sample_rate=16000, piano_model=0)
     print(f'dafx22_reverb_ir_row0: {os.path.getsize(out) / 1024:.1f} KiB')
+
+
+def make_fdn():
+    """tests/golden/fdn_*.npz: the reference's modules/fdn_reverb.py executed over the stand-in.
+
+        python -c "import sys; sys.path.insert(0, 'tests/golden'); import make_golden as m; m.make_fdn()"
+    """
+    load_reference_modules()
+    spec = importlib.util.spec_from_file_location(
+        'ddsp_piano.modules.fdn_reverb', os.path.join(REF, 'ddsp_piano', 'modules', 'fdn_reverb.py'))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['ddsp_piano.modules.fdn_reverb'] = mod
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(20230928)
+    for name, sr, n_audio in (('fdn_sr2000', 2000.0, 1500), ('fdn_sr8000', 8000.0, 5000)):
+        fdn = mod.FeedbackDelayNetwork(trainable=False, sampling_rate=sr)
+        fdn.build(None)
+        # the initialisers of MultiInstrumentFeedbackDelayReverb (sub_modules.py:384-411) and the
+        # activations of its call (:431-438)
+        p = dict(
+            input_gain=rng.normal(0.25, 0.1, 8).astype(np.float32),
+            output_gain=rng.normal(0.25, 0.1, 8).astype(np.float32),
+            gain_allpass=rng.normal(0.25, 0.1, [8, 4]).astype(np.float32),
+            delays_allpass=rng.normal(400, 60, [8, 4]).astype(np.float32),
+            time_rev_0_sec=np.maximum(rng.normal(2, 0.5, [1]), 0).astype(np.float32),
+            alpha_tone=(1 / (1 + np.exp(-rng.normal(0, 0.1, [1])))).astype(np.float32),
+            early_ir=rng.normal(0, 0.1, [200]).astype(np.float32))
+        audio = (rng.standard_normal([2, n_audio]) * 0.1).astype(np.float32)
+        ctl = fdn.get_controls(audio_dry=audio, **{k: v.copy() for k, v in p.items()})
+        ir = ctl['ir']
+        assert ir.dtype == np.float32 and ir.shape == (int(2 * sr),)
+        sig = fdn.get_signal(ctl['audio'], ir)
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, sampling_rate=sr, audio=audio, ir=ir, signal=sig, **p)
+        print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')

@@ -631,3 +631,48 @@ def test_reverb_error_is_level_independent(dp, dev, audio_gain, ir_gain):
             assert np.max(np.abs(wet[b])) < 1e-6 * np.max(np.abs(ir[b]))
         else:
             assert np.max(np.abs(wet[b] - want)) < 5e-6 * scale
+
+
+# ------------------- feedback-delay-network reverb IR generator ----------------
+
+FDN_KEYS = ('input_gain', 'output_gain', 'gain_allpass', 'delays_allpass', 'time_rev_0_sec',
+            'alpha_tone', 'early_ir')
+
+
+@pytest.mark.parametrize('name', ['fdn_sr2000', 'fdn_sr8000'])
+def test_fdn_golden(dp, dev, golden_dir, name):
+    g = load(golden_dir, name)
+    fdn = dp.FeedbackDelayNetwork(trainable=False, sampling_rate=float(g['sampling_rate']))
+    fdn.build(None)
+    out = fdn(cu(g['audio'], dev), *[cu(g[k], dev) for k in FDN_KEYS], return_outputs_dict=True)
+    assert out['controls']['ir'].shape == g['ir'].shape
+    assert rel_err(out['controls']['ir'], g['ir']) < TIGHT
+    assert rel_err(out['signal'], g['signal']) < TIGHT
+    # get_signal alone on the golden IR: plain convolution, ir[0] kept, no dry signal
+    assert rel_err(fdn.get_signal(cu(g['audio'], dev), cu(g['ir'], dev)), g['signal']) < TIGHT
+
+
+def test_fdn_full_size_vs_oracle_and_into_reverb(dp, dev):
+    """24 kHz (48 000-tap IR, 24 001 frequency bins), batch of 3 parameter rows vs the oracle; the
+    IR then feeds effects.Reverb like in configs/maestro-v2.gin."""
+    from oracle import fdn_np
+    sr, B = 24000.0, 3
+    rng = np.random.default_rng(404)
+    p = dict(input_gain=rng.normal(0.25, 0.1, [B, 8]), output_gain=rng.normal(0.25, 0.1, [B, 8]),
+             gain_allpass=rng.normal(0.25, 0.1, [B, 8, 4]), delays_allpass=rng.normal(400, 60, [B, 8, 4]),
+             time_rev_0_sec=np.maximum(rng.normal(2, 0.5, [B, 1]), 0.1),
+             alpha_tone=1 / (1 + np.exp(-rng.normal(0, 0.1, [B, 1]))), early_ir=rng.normal(0, 0.1, [B, 200]))
+    p = {k: v.astype(np.float32) for k, v in p.items()}
+    fdn = dp.FeedbackDelayNetwork(trainable=False, sampling_rate=sr)
+    fdn.build(None)
+    ir = fdn.get_ir(*[cu(p[k], dev) for k in FDN_KEYS])
+    assert ir.shape == (B, 48000)
+    for b in range(B):
+        want = fdn_np.fdn_ir(*[p[k][b] for k in FDN_KEYS], sampling_rate=sr)
+        assert rel_err(ir[b], want) < TIGHT
+    audio = cu((rng.standard_normal([B, 24000]) * 0.1).astype(np.float32), dev)
+    wet = dp.Reverb(trainable=False)(audio, ir)
+    want = ref.reverb_signal(audio.cpu().numpy(), ir.cpu().numpy())
+    assert rel_err(wet, want) < TIGHT
+    with pytest.raises(ValueError):
+        dp.FeedbackDelayNetwork(trainable=True)
