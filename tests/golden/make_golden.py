@@ -216,3 +216,23 @@ def make_fdn():
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, sampling_rate=sr, audio=audio, ir=ir, signal=sig, **p)
         print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
+def make_checkpoint_fixtures():
+    """Small fixtures cut from the SHIPPED checkpoints with ddsp_piano_b200/checkpoint.py (no TF):
+    * dafx22_ckpt-0.index         -- verbatim copy of model_weights/dafx22/ckpt-0.index (2.5 KB), for
+                                     the parser test;
+    * v2_fdn_params_piano0.npz    -- the feedback-delay-network parameters of instrument 0 in
+                                     model_weights/v2/ckpt-225000 (activations applied as in
+                                     sub_modules.py:431-438), for the FDN kernels.
+
+        python -c "import sys; sys.path.insert(0, 'tests/golden'); import make_golden as m; m.make_checkpoint_fixtures()"
+    """
+    import shutil
+    sys.path.insert(0, ROOT)
+    from ddsp_piano_b200.checkpoint import Checkpoint
+    weights = os.path.join(REF, 'ddsp_piano', 'model_weights')
+    shutil.copyfile(os.path.join(weights, 'dafx22', 'ckpt-0.index'),
+                    os.path.join(HERE, 'dafx22_ckpt-0.index'))
+    p = Checkpoint(os.path.join(weights, 'v2', 'ckpt-225000')).fdn_parameters(0)
+    np.savez_compressed(os.path.join(HERE, 'v2_fdn_params_piano0.npz'), sampling_rate=24000.0, **p)

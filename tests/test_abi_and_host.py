@@ -196,3 +196,48 @@ def test_scale_fn_and_constructor_contract():
     x = np.linspace(-8, 8, 33).astype(np.float32)
     np.testing.assert_allclose(dp.exp_sigmoid(torch.from_numpy(x)).numpy(), core.exp_sigmoid(x), rtol=2e-6)
     np.testing.assert_allclose(dp.exp_tanh(torch.from_numpy(x)).numpy(), ref.exp_tanh(x), rtol=2e-5, atol=1e-9)
+
+
+# ------------------------------- TF checkpoint reader (no TensorFlow) --------------------------
+
+def test_checkpoint_index_parser_matches_survey_appendix_b():
+    """ddsp_piano_b200/checkpoint.py on the shipped dafx22 index (fixture = verbatim copy of
+    model_weights/dafx22/ckpt-0.index): tensor names, shapes and byte offsets of SURVEY appendix B."""
+    import shutil
+    import tempfile
+    from ddsp_piano_b200.checkpoint import Checkpoint
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copyfile(os.path.join(ROOT, 'tests', 'golden', 'dafx22_ckpt-0.index'),
+                        os.path.join(d, 'ckpt-0.index'))
+        ck = Checkpoint(os.path.join(d, 'ckpt-0'))
+    suffix = '/.ATTRIBUTES/VARIABLE_VALUE'
+    want = {
+        'model/reverb_model/reverb_dict/layer_with_weights-0/embeddings': ([10, 24000], 308892),
+        'model/monophonic_network/dense_out/kernel': ([192, 161], 9092),
+        'model/context_network/dense_out/kernel': ([64, 32], 772),
+        'model/detuner/layer/kernel': ([1, 2], 133384),
+        'model/note_release/layer/cell/release_duration': ([], 133400),
+        'model/z_encoder/embedding/embeddings': ([10, 16], 52),
+    }
+    for key, (shape, offset) in want.items():
+        e = ck.entries[key + suffix]
+        assert e['shape'] == shape and e['offset'] == offset and e['dtype'] == 1
+        assert e['size'] == 4 * int(np.prod(shape, dtype=np.int64))
+    assert ck.n_shards == 1 and len(ck.keys()) == 35
+    with pytest.raises(KeyError):
+        ck.tensor('no/such/variable')
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/ddsp_piano/model_weights'),
+                    reason='shipped checkpoints only exist in the build container')
+def test_checkpoint_tensors_from_shipped_weights(golden_dir):
+    from ddsp_piano_b200.checkpoint import Checkpoint
+    weights = '/root/reference/ddsp_piano/model_weights'
+    ir = Checkpoint(os.path.join(weights, 'dafx22', 'ckpt-0')).reverb_ir(0)
+    fixture = np.load(os.path.join(golden_dir, 'dafx22_reverb_ir_row0.npz'))['ir']
+    np.testing.assert_array_equal(ir, fixture)
+    p = Checkpoint(os.path.join(weights, 'v2', 'ckpt-225000')).fdn_parameters(0)
+    g = np.load(os.path.join(golden_dir, 'v2_fdn_params_piano0.npz'))
+    for k, v in p.items():
+        np.testing.assert_array_equal(v, g[k])
+    assert p['gain_allpass'].shape == (8, 4) and p['early_ir'].shape == (200,)

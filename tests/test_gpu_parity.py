@@ -676,3 +676,17 @@ def test_fdn_full_size_vs_oracle_and_into_reverb(dp, dev):
     assert rel_err(wet, want) < TIGHT
     with pytest.raises(ValueError):
         dp.FeedbackDelayNetwork(trainable=True)
+
+
+def test_fdn_shipped_v2_parameters(dp, dev, golden_dir):
+    """The FDN parameters of instrument 0 in the shipped v2 checkpoint (24 kHz) -> 48 000-tap IR, vs
+    the oracle; this is the reverb_ir the maestro-v2 model feeds to effects.Reverb."""
+    from oracle import fdn_np
+    g = load(golden_dir, 'v2_fdn_params_piano0')
+    sr = float(g['sampling_rate'])
+    fdn = dp.FeedbackDelayNetwork(trainable=False, sampling_rate=sr)
+    fdn.build(None)
+    ir = fdn.get_ir(*[cu(g[k], dev) for k in FDN_KEYS])
+    want = fdn_np.fdn_ir(*[g[k] for k in FDN_KEYS], sampling_rate=sr)
+    assert ir.shape == (48000,) and rel_err(ir, want) < TIGHT
+    assert float(ir.abs().max()) > 0.5 and float(ir[-1000:].abs().max()) < 0.01    # a decaying room response
