@@ -1132,6 +1132,21 @@ extern "C" int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, cons
                       B200DDSP_CONV_MASK_IR0 | B200DDSP_CONV_FULL);
 }
 
+extern "C" int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int B, int L,
+                                      float decay_exponent, int decay_start, void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!ir || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (B < 1 || L < 1 || B > 65535) return fail(h, B200DDSP_BAD_SHAPE, "B=%d L=%d", B, L);
+  if (decay_start < 0 || decay_start >= L)
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "decay_start=%d must lie inside the impulse response (L=%d): the reference's "
+                "tf.linspace(0, 1, L - decay_start) is empty otherwise", decay_start, L);
+  ir_decay_mask_kernel<<<dim3((L + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(ir, out, L, decay_start,
+                                                                                 decay_exponent);
+  CHECK_LAUNCH(h, "ir_decay_mask_kernel");
+  return B200DDSP_OK;
+}
+
 extern "C" int b200ddsp_fft_convolve(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
                                      int B, int N, int L, int flags, void* workspace,
                                      size_t workspace_bytes, void* stream) {

@@ -293,6 +293,25 @@ __global__ void __launch_bounds__(kFft64Threads) fft_pass64_kernel(const Loader 
   }
 }
 
+// MultiInstrumentReverb.exponential_decay_mask (modules/sub_modules.py:339-349, inference only):
+// out = ir * concat(ones(start), exp(-e * linspace(0, 1, L - start))), tf.linspace evaluated in
+// float32 (start + i * step, last element exactly 1).
+__global__ void __launch_bounds__(256) ir_decay_mask_kernel(const float* __restrict__ ir,
+                                                            float* __restrict__ out, int L, int start,
+                                                            float exponent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const size_t o = (size_t)blockIdx.y * L + i;
+  float m = 1.0f;
+  if (i >= start) {
+    const int n = L - start, j = i - start;
+    const float step = (n > 1) ? __fdiv_rn(1.0f, (float)(n - 1)) : 0.f;
+    const float t = (j == n - 1 && n > 1) ? 1.0f : __fmul_rn((float)j, step);
+    m = expf(-exponent * t);
+  }
+  out[o] = ir[o] * m;
+}
+
 // tw[q] = exp(-2 pi i q / n)
 __global__ void __launch_bounds__(256) fft_twiddle_kernel(float2* tw, int n) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;

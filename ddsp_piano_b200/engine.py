@@ -182,6 +182,15 @@ class Engine:
         """'valid'-padded wet signal [B, N + L - 1] (no dry), see sharding.timeline_reverb."""
         return self.reverb(audio, ir, full=True)
 
+    def ir_decay_mask(self, ir, decay_exponent=4.0, decay_start=16000):
+        ir = self.tensor(ir, 'ir', 2)
+        out = torch.empty_like(ir)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_ir_decay_mask(
+                self.handle, ir.data_ptr(), out.data_ptr(), ir.shape[0], ir.shape[1],
+                float(decay_exponent), int(decay_start), self.stream()))
+        return out
+
     def fft_convolve(self, audio, ir, mask_ir0=False, add_dry=False, full=False):
         """ddsp.core.fft_convolve(audio, ir, delay_compensation=0) + the reverbs' options."""
         flags = (_lib.CONV_MASK_IR0 if mask_ir0 else 0) | (_lib.CONV_ADD_DRY if add_dry else 0) | \

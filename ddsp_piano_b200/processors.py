@@ -235,6 +235,45 @@ class Reverb(Processor):
         return eng.reverb(audio, ir)
 
 
+class MultiInstrumentReverb:
+    """modules/sub_modules.py:300-365: one learnt impulse response per instrument (an embedding
+    table [n_instruments, reverb_length], e.g. ``Checkpoint.tensor('reverb_model/reverb_dict')``);
+    ``__call__(piano_model [B, 1])`` returns ``reverb_ir [B, L]``, with the exponential decay mask
+    (:339-349) when ``inference=True``.  The lookup is an index; the mask is a CUDA kernel."""
+
+    def __init__(self, embeddings, n_instruments=None, reverb_duration=None, sample_rate=16000,
+                 inference=False, name='reverb_model'):
+        self.name = name
+        self.embeddings = embeddings
+        self.sample_rate = sample_rate
+        self.inference = inference
+        self.n_instruments = embeddings.shape[0] if n_instruments is None else n_instruments
+        self.reverb_duration = (embeddings.shape[1] / sample_rate if reverb_duration is None
+                                else reverb_duration)
+
+    @property
+    def reverb_length(self):
+        return int(self.reverb_duration * self.sample_rate)
+
+    def exponential_decay_mask(self, ir, decay_exponent=4., decay_start=16000):
+        eng = get_engine(_device_of(ir), **_DEFAULT_CFG)
+        return eng.ir_decay_mask(ir, decay_exponent, decay_start)
+
+    def __call__(self, piano_model):
+        idx = torch.as_tensor(piano_model, device=self.embeddings.device).long()
+        if self.n_instruments == 1:
+            idx = torch.zeros_like(idx)
+        ir = self.embeddings[idx]                       # [B, 1, L] for piano_model [B, 1]
+        if ir.dim() == 3:
+            ir = ir[:, 0]
+        ir = ir.contiguous()
+        if self.inference:
+            ir = self.exponential_decay_mask(ir)
+        return ir
+
+    call = __call__
+
+
 class FeedbackDelayNetwork(Processor):
     """modules/fdn_reverb.py:20-410 with ``trainable=False``: frequency-sampled feedback delay
     network (8 delay lines, Householder mixing, one-pole reverberation-time control, 4 allpasses

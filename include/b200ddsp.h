@@ -160,6 +160,13 @@ int b200ddsp_reverb(b200ddsp_handle* h, const float* audio, const float* ir, flo
 int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir, float* out_full,
                          int B, int N, int L, void* workspace, size_t workspace_bytes, void* stream);
 
+/* MultiInstrumentReverb.exponential_decay_mask -- modules/sub_modules.py:339-349 (applied to the
+ * impulse response when the model is built with inference=True, :361-363): out[b, i] = ir[b, i] for
+ * i < decay_start, ir[b, i] * exp(-decay_exponent * t) after, t = linspace(0, 1, L - decay_start).
+ * The reference hard-codes decay_exponent = 4, decay_start = 16000.  out may alias ir. */
+int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int B, int L,
+                           float decay_exponent, int decay_start, void* stream);
+
 /* ddsp.core.fft_convolve(audio, ir, padding, delay_compensation=0) with the options the reverbs
  * of the reference use.  flags: B200DDSP_CONV_MASK_IR0 zeroes ir[:,0] (effects.Reverb masks the dry
  * tap), B200DDSP_CONV_ADD_DRY adds the input (effects.Reverb add_dry), B200DDSP_CONV_FULL writes

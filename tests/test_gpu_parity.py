@@ -690,3 +690,23 @@ def test_fdn_shipped_v2_parameters(dp, dev, golden_dir):
     want = fdn_np.fdn_ir(*[g[k] for k in FDN_KEYS], sampling_rate=sr)
     assert ir.shape == (48000,) and rel_err(ir, want) < TIGHT
     assert float(ir.abs().max()) > 0.5 and float(ir[-1000:].abs().max()) < 0.01    # a decaying room response
+
+
+def test_ir_decay_mask_and_instrument_lookup(dp, dev, golden_dir):
+    """MultiInstrumentReverb -- embedding lookup + the inference-time
+    exponential decay mask (sub_modules.py:339-365), on the shipped dafx22 impulse response."""
+    ir0 = load(golden_dir, 'dafx22_reverb_ir_row0')['ir']
+    rng = np.random.default_rng(0)
+    table = np.stack([ir0, ir0[::-1].copy(), rng.standard_normal(24000).astype(np.float32)])
+    model = dp.MultiInstrumentReverb(cu(table, dev), sample_rate=16000, inference=True)
+    assert model.reverb_length == 24000 and model.n_instruments == 3
+    got = model(torch.tensor([[0], [2], [1], [0]], device=dev))
+    want = ref.exponential_decay_mask(table[[0, 2, 1, 0]])
+    assert got.shape == (4, 24000)
+    np.testing.assert_array_equal(got[:, :16000].cpu().numpy(), want[:, :16000])   # untouched head
+    assert rel_err(got, want) < 2e-6
+    raw = dp.MultiInstrumentReverb(cu(table, dev), sample_rate=16000, inference=False)(
+        torch.tensor([[1]], device=dev))
+    np.testing.assert_array_equal(raw.cpu().numpy(), table[[1]])
+    with pytest.raises(ValueError):
+        model.exponential_decay_mask(cu(table[:, :1000], dev))       # shorter than decay_start
