@@ -42,7 +42,7 @@ class Voice(ctypes.Structure):
 
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
-                  if f.endswith(('.cu', '.cuh'))) + [HEADER]
+                  if f.endswith(('.cu', '.cuh', '.inl'))) + [HEADER]
 
 
 def needs_build():
@@ -127,6 +127,8 @@ def load():
                                                      ci, ci, ci, ci, ci, ci, u64, vp, sz, vp]
     lib.b200ddsp_workspace_bytes_host.restype = sz
     lib.b200ddsp_workspace_bytes_host.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci]
+    lib.b200ddsp_midi_roll_to_conditioning.restype = ci
+    lib.b200ddsp_midi_roll_to_conditioning.argtypes = [vp, ci, ci, ci, ctypes.c_float, vp, vp]
     lib.b200ddsp_launch_count.restype = u64
     lib.b200ddsp_launch_count.argtypes = [vp]
     lib.b200ddsp_set_profiling.restype = ci
@@ -143,7 +145,8 @@ EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200dd
            'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_fdn_ir',
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
-           'b200ddsp_workspace_bytes_host', 'b200ddsp_launch_count', 'b200ddsp_set_profiling',
+           'b200ddsp_workspace_bytes_host', 'b200ddsp_midi_roll_to_conditioning',
+           'b200ddsp_launch_count', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
 CONV_MASK_IR0, CONV_ADD_DRY, CONV_FULL = 1, 2, 4
 STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise', 'reverb', 'mix']

@@ -1478,3 +1478,8 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaMemcpyAsync(wet_out_host, wet_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   return B200DDSP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// host-side front end
+// ---------------------------------------------------------------------------------------------
+#include "midi_host.inl"

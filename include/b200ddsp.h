@@ -220,6 +220,15 @@ int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200ddsp_voice* v
 size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int F, int H, int S,
                                      int M, int L, int with_noise);
 
+/* HOST function (no GPU work): MIDIRoll2Conditioning.__call__ of a fresh object --
+ * utils/midi_encoders.py:33-104, called from utils/io_utils.py:115-116.  roll [n_frames, n_pitches,
+ * 2] = stacked (activity, onset velocity) pianorolls at the control rate (n_pitches = 88,
+ * first_pitch = 21 in the reference); conditioning [n_frames, n_synths, 2] = (pitch, velocity) per
+ * polyphonic channel, a sounding note keeping its channel; polyphony [n_frames] (may be NULL) =
+ * number of active notes before the reduction to n_synths.  All pointers are HOST pointers. */
+int b200ddsp_midi_roll_to_conditioning(const float* roll, int n_frames, int n_pitches, int n_synths,
+                                       float first_pitch, float* conditioning, float* polyphony);
+
 /* Number of kernel launches enqueued by this handle since creation (bench.py's
  * gpu_launches claim is read from here). */
 uint64_t b200ddsp_launch_count(const b200ddsp_handle* h);

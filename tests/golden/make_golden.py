@@ -236,3 +236,48 @@ def make_checkpoint_fixtures():
                     os.path.join(HERE, 'dafx22_ckpt-0.index'))
     p = Checkpoint(os.path.join(weights, 'v2', 'ckpt-225000')).fdn_parameters(0)
     np.savez_compressed(os.path.join(HERE, 'v2_fdn_params_piano0.npz'), sampling_rate=24000.0, **p)
+
+
+def make_midi_conditioning():
+    """tests/golden/midi_conditioning.npz: the reference's OWN utils/midi_encoders.py (pure NumPy,
+    imported unmodified -- no stand-in involved) run on synthetic pianorolls.
+
+        python -c "import sys; sys.path.insert(0, 'tests/golden'); import make_golden as m; m.make_midi_conditioning()"
+    """
+    spec = importlib.util.spec_from_file_location(
+        'ref_midi_encoders', os.path.join(REF, 'ddsp_piano', 'utils', 'midi_encoders.py'))
+    enc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(enc)
+    rng = np.random.default_rng(88)
+
+    def random_roll(n_frames, n_notes, max_len):
+        roll = np.zeros([n_frames, 88, 2], np.float32)
+        for _ in range(n_notes):
+            p = int(rng.integers(0, 88))
+            t0 = int(rng.integers(0, n_frames - 2))
+            t1 = min(n_frames, t0 + int(rng.integers(2, max_len)))
+            if roll[max(t0 - 1, 0):t1 + 1, p, 0].any():
+                continue                                   # keep notes of one pitch apart
+            roll[t0:t1, p, 0] = 1.0
+            roll[t0, p, 1] = float(rng.integers(1, 128)) / 127.0    # onset velocity, onset frame only
+        return roll
+
+    cases = {'sparse': random_roll(500, 60, 80), 'dense': random_roll(400, 400, 120),
+             'chords': random_roll(300, 150, 200)}
+    # more simultaneous notes than channels for a while
+    over = np.zeros([120, 88, 2], np.float32)
+    over[10:90, 20:44, 0] = 1.0
+    over[10, 20:44, 1] = 0.5
+    over[50:110, 60:64, 0] = 1.0
+    over[50, 60:64, 1] = 0.8
+    cases['overflow'] = over
+    arrays = {}
+    for name, roll in cases.items():
+        for n_synths in (16, 4):
+            cond, poly = enc.MIDIRoll2Conditioning(n_synths)(roll.copy())
+            arrays[f'{name}_cond{n_synths}'] = cond.astype(np.float32)
+            arrays[f'{name}_poly'] = poly.astype(np.float32)
+        arrays[f'{name}_roll'] = roll
+    path = os.path.join(HERE, 'midi_conditioning.npz')
+    np.savez_compressed(path, **arrays)
+    print(f'midi_conditioning: {os.path.getsize(path) / 1024:.1f} KiB')

@@ -241,3 +241,36 @@ def test_checkpoint_tensors_from_shipped_weights(golden_dir):
     for k, v in p.items():
         np.testing.assert_array_equal(v, g[k])
     assert p['gain_allpass'].shape == (8, 4) and p['early_ir'].shape == (200,)
+
+
+# ------------------------------- MIDI front end: voice allocation ------------------------------
+
+@pytest.mark.parametrize('case', ['sparse', 'dense', 'chords', 'overflow'])
+@pytest.mark.parametrize('n_synths', [16, 4])
+def test_midi_roll_to_conditioning_matches_reference(lib_path, case, n_synths):
+    """SURVEY 8f row 3 (voice allocation): the C++ port inside libb200ddsp.so vs outputs of the
+    reference's own utils/midi_encoders.py (imported unmodified by tests/golden/make_golden.py).
+    Integer/index work: bit exact."""
+    from ddsp_piano_b200.midi import MIDIRoll2Conditioning
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'midi_conditioning.npz'))
+    roll = g[f'{case}_roll']
+    cond, poly = MIDIRoll2Conditioning(n_synths)(roll)
+    np.testing.assert_array_equal(poly, g[f'{case}_poly'])
+    np.testing.assert_array_equal(cond, g[f'{case}_cond{n_synths}'])
+    # properties: every channel holds an active pitch of the frame or 0; a held note never moves
+    pitches = cond[..., 0]
+    for t in range(1, len(pitches)):
+        for ch in range(n_synths):
+            p = pitches[t, ch]
+            if p != 0 and p in pitches[t - 1]:
+                assert pitches[t - 1, ch] == p
+
+
+def test_midi_roll_shape_errors(lib_path):
+    from ddsp_piano_b200.midi import MIDIRoll2Conditioning
+    with pytest.raises(ValueError):
+        MIDIRoll2Conditioning(16)(np.zeros([10, 88], np.float32))
+    with pytest.raises(ValueError):
+        MIDIRoll2Conditioning(16)(np.zeros([10, 8, 2], np.float32))
+    cond, poly = MIDIRoll2Conditioning(16)(np.zeros([0, 88, 2], np.float32))
+    assert cond.shape == (0, 16, 2) and poly.shape == (0,)

@@ -710,3 +710,31 @@ def test_ir_decay_mask_and_instrument_lookup(dp, dev, golden_dir):
     np.testing.assert_array_equal(raw.cpu().numpy(), table[[1]])
     with pytest.raises(ValueError):
         model.exponential_decay_mask(cu(table[:, :1000], dev))       # shorter than decay_start
+
+
+def test_forward_is_cuda_graph_capturable(dp, dev):
+    """Every launch goes to the caller's stream (plus forked auxiliary streams that rejoin it) and
+    nothing allocates after the engine exists, so a forward can be captured in a CUDA graph and
+    replayed; the replay must reproduce the eager result bit for bit (same seed baked in)."""
+    sr, F, B, H, S, M, P, L = 24000, 60, 2, 96, 2, 64, 4, 2000
+    rng = np.random.default_rng(21)
+    feats = {}
+    for v in range(P):
+        for k, a in voice_inputs(rng, B, F, H, S, M).items():
+            feats[f'{k}_{v}'] = cu(a, dev)
+    feats['reverb_ir'] = cu((rng.standard_normal([B, L]) * 1e-2).astype(np.float32), dev)
+    group, noise = _build_group(dp, sr, P, True)
+    noise.seed, noise._calls = 5, 0
+    eager = group(dict(feats)).clone()            # also creates the engine and its workspace
+    torch.cuda.synchronize()
+    noise._calls = 0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = group(dict(feats))
+    captured.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
