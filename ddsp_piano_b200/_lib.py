@@ -10,7 +10,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
-LIB_PATH = os.path.join(HERE, 'libb200ddsp.so')
+# B200DDSP_LIB: developer switch for A/B timing of an alternative in-tree build of the same sources
+LIB_PATH = os.environ.get('B200DDSP_LIB') or os.path.join(HERE, 'libb200ddsp.so')
 HEADER = os.path.join(ROOT, 'include', 'b200ddsp.h')
 
 OK = 0
@@ -60,6 +61,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-o', LIB_PATH, os.path.join(CSRC, 'b200ddsp.cu')]
+    cmd[1:1] = os.environ.get('B200DDSP_NVCC_FLAGS', '').split()
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -46,18 +46,18 @@ struct AdditiveArgs {
   float nyquist;        // float32(sr / 2)
   float sr;             // float32(sr)
   float inv_sr;         // float32(1 / sr)
+  float inv_sr_lo;      // float32(1 / sr - inv_sr): second word of the reciprocal
 };
 
-// x / sr, correctly rounded.  FASTDIV: q0 = x*(1/sr), one Newton step on the exact FMA
-// remainder -- b200ddsp_create() verifies on the host, over all 2^23 mantissas, that this
-// equals IEEE division for the configured sample rate before selecting this path.
+// x / sr, correctly rounded.  FASTDIV: the reciprocal is held as two float32 words r + r_lo
+// (relative error 2^-48), so fma(x, r, fl(x * r_lo)) is the quotient to 2^-47 before its single
+// rounding -- and a float32 quotient by an integer sample rate can only come that close to a
+// rounding boundary when it lies on it.  b200ddsp_create() verifies on the host, over all 2^23
+// mantissas, that this equals IEEE division for the configured sample rate before selecting
+// this path.  Two FMA-pipe operations instead of the classic three (x*r, remainder, correction).
 template <bool FASTDIV>
-__device__ __forceinline__ float div_sr(float x, float sr, float inv_sr) {
-  if (FASTDIV) {
-    const float q = __fmul_rn(x, inv_sr);
-    const float e = __fmaf_rn(-q, sr, x);
-    return __fmaf_rn(e, inv_sr, q);
-  }
+__device__ __forceinline__ float div_sr(float x, float sr, float inv_sr, float inv_sr_lo) {
+  if (FASTDIV) return __fmaf_rn(x, inv_sr, __fmul_rn(x, inv_sr_lo));
   return __fdiv_rn(x, sr);
 }
 
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
               } else {
                 f = __fadd_rn(cur.F[q], __fmul_rn(dF[q], frac));       // top + (bottom-top)*lerp
               }
-              const float om = div_sr<FAST>(__fmul_rn(f, two_pi), a.sr, a.inv_sr);  // :69-70
+              const float om = div_sr<FAST>(__fmul_rn(f, two_pi), a.sr, a.inv_sr, a.inv_sr_lo);  // :69-70
               ph[q] = __fadd_rn(ph[q], om);                            // in-chunk cumsum
               if (!ENDS_ONLY) {
                 float amp = __fmaf_rn(cur.A[q], w1, __fmul_rn(nxt.A[q], w0));

@@ -173,7 +173,7 @@ __device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, in
       st.dF[q][s] = __fadd_rn(st.Fn[q][s], -st.F[q][s]);
       all_steady &= (st.dF[q][s] == 0.f);
       // omega of a steady frame: f = F + 0 * lerp = F
-      st.om[q][s] = div_sr<true>(__fmul_rn(st.F[q][s], kTwoPi), a.sr, a.inv_sr);
+      st.om[q][s] = div_sr<true>(__fmul_rn(st.F[q][s], kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);
       any_risky |= live && (fmaxf(st.F[q][s], st.Fn[q][s]) >= nyq_lo);
     }
   }
@@ -193,12 +193,109 @@ __device__ __forceinline__ float cos_large(float x) {
   return __cosf((float)fma(-n, 6.283185307179586, xd));
 }
 
+// ---- packed float32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) -------------------------------
+// The two substrings of a partial go through identical operations, so they ride in the two
+// halves of one 64-bit register: a packed operation takes ONE issue slot for two oscillators
+// (it still occupies the FMA pipe for two cycles), which frees issue slots for the MUFU, the
+// shuffles and the address arithmetic that used to compete with the FP32 work.  Every packed
+// operation rounds each half exactly like its scalar form (.rn), so the phase stays bit-identical.
+// One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only on
+// the scalar forms), so the one product that must stay unfused -- (bottom - top) * lerp of the
+// legacy bilinear resize -- is computed with two scalar __fmul_rn.
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+template <int NA, bool STEADY, int AMP, int UNROLL, bool PLAIN>
+__device__ __forceinline__ void osc_group_x2(const AdditiveArgs& a, OscState<NA, 2>& st,
+                                             const float* win, const float* lerp,
+                                             float (&y)[kOscUnroll]) {
+  static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
+  static_assert(UNROLL == 4 || UNROLL == 8, "lerp loads are float4");
+  float wr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
+    const float4 r4 = *reinterpret_cast<const float4*>(win);
+    wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
+  }
+  float fr[UNROLL];
+  if (!STEADY) {             // t is a multiple of UNROLL
+#pragma unroll
+    for (int j4 = 0; j4 < UNROLL / 4; ++j4) {
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(lerp) + j4);
+      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
+    }
+  }
+  const float2 two_pi2 = splat2(kTwoPi), neg_two_pi2 = splat2(-kTwoPi);
+  const float2 inv_sr2 = splat2(a.inv_sr), inv_sr_lo2 = splat2(a.inv_sr_lo);
+  const float2 inv_two_pi2 = splat2(kInvTwoPi);
+  const float2 magic2 = splat2(kRoundMagic), neg_magic2 = splat2(-kRoundMagic);
+  float2 ph[NA], acc[4];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) ph[q] = make_float2(st.ph[q][0], st.ph[q][1]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+  bool cut[NA][2];
+  if (STEADY && AMP == kAmpCheck) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) cut[q][s] = st.F[q][s] >= a.nyquist;
+  }
+#pragma unroll
+  for (int j = 0; j < UNROLL; ++j) {
+    const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      float amp_q = 0.f;
+      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.dA[q], w0, st.A[q]);
+      float2 om, f = make_float2(0.f, 0.f);
+      if (STEADY) {
+        om = make_float2(st.om[q][0], st.om[q][1]);
+      } else {
+        // top + (bottom - top) * lerp, product and sum rounded separately (scalar products: see above)
+        const float2 m = make_float2(__fmul_rn(st.dF[q][0], fr[j]), __fmul_rn(st.dF[q][1], fr[j]));
+        f = __fadd2_rn(make_float2(st.F[q][0], st.F[q][1]), m);
+        const float2 x = __fmul2_rn(f, two_pi2);                               // :69
+        om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));                // :70, see div_sr
+      }
+      ph[q] = __fadd2_rn(ph[q], om);                                           // cumsum
+      if (AMP != kAmpSilent) {
+        float2 amp = splat2(amp_q);
+        if (AMP == kAmpCheck) {                                                // :65-67
+          amp.x = (STEADY ? cut[q][0] : (f.x >= a.nyquist)) ? 0.f : amp_q;
+          amp.y = (STEADY ? cut[q][1] : (f.y >= a.nyquist)) ? 0.f : amp_q;
+        }
+        float2 c;
+        if (PLAIN) {
+          c = make_float2(cos_large(ph[q].x), cos_large(ph[q].y));             // tf.cos(tf.cumsum)
+        } else {
+          const float2 x = __fadd2_rn(ph[q], make_float2(st.off[q][0], st.off[q][1]));
+          const float2 n = __fadd2_rn(__ffma2_rn(x, inv_two_pi2, magic2), neg_magic2);
+          const float2 r = __ffma2_rn(n, neg_two_pi2, x);                      // wrap_to_pi
+          c = make_float2(__cosf(r.x), __cosf(r.y));
+        }
+        acc[j & 3] = __ffma2_rn(amp, c, acc[j & 3]);                           // :80-83
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NA; ++q) { st.ph[q][0] = ph[q].x; st.ph[q][1] = ph[q].y; }
+  if (AMP != kAmpSilent) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] += acc[i].x + acc[i].y;
+  }
+}
+
 template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
                                           const float* win, const float* lerp,
                                           float (&y)[kOscUnroll]) {
   static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
   static_assert(UNROLL == 4 || UNROLL == 8, "lerp loads are float4");
+#ifndef B200DDSP_NO_F32X2
+  if constexpr (SP == 2) {   // substring pairs in packed float32x2 registers
+    osc_group_x2<NA, STEADY, AMP, UNROLL, PLAIN>(a, st, win, lerp, y);
+    return;
+  }
+#endif
   float wr[4] = {0.f, 0.f, 0.f, 0.f};
   if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
@@ -237,7 +334,7 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
           om = st.om[q][s];
         } else {
           f = __fadd_rn(st.F[q][s], __fmul_rn(st.dF[q][s], frac));             // top + (bottom-top)*lerp
-          om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr);            // :69-70
+          om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);            // :69-70
         }
         st.ph[q][s] = __fadd_rn(st.ph[q][s], om);                              // cumsum
         if (AMP != kAmpSilent) {

@@ -33,14 +33,16 @@ struct b200ddsp_handle {
   int n_sms = 148;
   float* d_window = nullptr;   // hann(2U)
   float* d_cmat_t = nullptr;   // [M][M-1] noise IR matrix
-  bool fast_div = false;       // 3-op division == IEEE division for this sample rate
+  bool fast_div = false;       // two-word-reciprocal division == IEEE division for this sample rate
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
   cudaStream_t aux_stream[3] = {};      // the synthesis buckets run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+  cudaStream_t noise_stream = nullptr;  // the noise synth runs beside the oscillator bank
+  cudaEvent_t ev_noise_fork = nullptr, ev_noise_join = nullptr;
   cudaEvent_t ev_group[8] = {};
-  cudaEvent_t ev_mags[2] = {}, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
+  cudaEvent_t ev_mags[4] = {}, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
   cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
   cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
@@ -147,17 +149,18 @@ static std::vector<float> noise_ir_matrix_t(int M) {
   return c;
 }
 
-// Is q0 = x*r; e = fma(-q0, sr, x); q = fma(e, r, q0) equal to x / sr for every float32 mantissa?
-// (The identity is scale invariant away from underflow/overflow, so one binade suffices.)
+// Is fma(x, r, fl(x * r_lo)), with r + r_lo the two-word float32 reciprocal of sr, equal to x / sr
+// for every float32 mantissa?  (The identity is scale invariant away from underflow/overflow,
+// so one binade suffices.)
 static bool verify_fast_division(float sr) {
   const float r = 1.0f / sr;
+  const float r_lo = (float)(1.0 / (double)sr - (double)r);
   for (uint32_t m = 0; m < (1u << 23); ++m) {
     const uint32_t bits = (127u << 23) | m;
     float x;
     memcpy(&x, &bits, 4);
-    const float q0 = x * r;
-    const float e = fmaf(-q0, sr, x);
-    const float q = fmaf(e, r, q0);
+    volatile float lo = x * r_lo;
+    const float q = fmaf(x, r, lo);
     volatile float want = x / sr;
     if (q != want) return false;
   }
@@ -276,8 +279,11 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
     }
     for (int i = 0; i < 8 && ok; ++i)
       ok = cudaEventCreateWithFlags(&h->ev_group[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_mags[0], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_mags[1], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->noise_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_noise_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_noise_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&h->ev_mags[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_ir, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming) == cudaSuccess;
@@ -315,14 +321,17 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->d_cmat_t) cudaFree(h->d_cmat_t);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->noise_stream) cudaStreamDestroy(h->noise_stream);
+  if (h->ev_noise_fork) cudaEventDestroy(h->ev_noise_fork);
+  if (h->ev_noise_join) cudaEventDestroy(h->ev_noise_join);
   for (int i = 0; i < 3; ++i) {
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   for (int i = 0; i < 8; ++i)
     if (h->ev_group[i]) cudaEventDestroy(h->ev_group[i]);
-  if (h->ev_mags[0]) cudaEventDestroy(h->ev_mags[0]);
-  if (h->ev_mags[1]) cudaEventDestroy(h->ev_mags[1]);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_mags[i]) cudaEventDestroy(h->ev_mags[i]);
   if (h->ev_ir) cudaEventDestroy(h->ev_ir);
   if (h->ev_enter) cudaEventDestroy(h->ev_enter);
   if (h->ev_small) cudaEventDestroy(h->ev_small);
@@ -621,6 +630,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.nyquist = (float)(h->cfg.sample_rate / 2.0);
   a.sr = (float)h->cfg.sample_rate;
   a.inv_sr = 1.0f / a.sr;
+  a.inv_sr_lo = (float)(1.0 / (double)a.sr - (double)a.inv_sr);
   r->fa = AdditiveFastArgs{};
   r->fa.a = a;
   r->fa.plan = (AdditivePlan*)(base + lay.plan);
@@ -1211,10 +1221,13 @@ extern "C" int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, cons
 // `small_ready` before the prep kernel, `group_ready[g]` before it touches the harmonic
 // distribution of voice group g, `mags_ready[h]` before the noise stage of voice half h,
 // `ir_ready` before the reverb.
+// host-input path: the magnitudes arrive in this many voice parts (one noise slice each)
+static int noise_parts(int P) { return P < kNoiseSlices ? 1 : kNoiseSlices; }
+
 struct ForwardSync {
   cudaEvent_t small_ready;                      // amplitudes, inharm_coef, f0_hz of all voices
   cudaEvent_t group_ready[kMaxVoiceGroups];     // harmonic_distribution of voice group g
-  cudaEvent_t mags_ready[2];                    // magnitudes of the first / second half of the voices
+  cudaEvent_t mags_ready[4];                    // magnitudes of voice part p (noise_parts(P) parts)
   cudaEvent_t ir_ready;
 };
 
@@ -1251,6 +1264,34 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   ca.amp_out = amp; ca.hd_out = hd; ca.shifts_out = shifts; ca.f0_out = f0;
   ca.na_frame = run.fast ? run.na_frame : nullptr;
 
+  // 3. noise of every voice -> noise slices; FilteredNoise.get_controls is fused into the taps
+  //    GEMM's operand load.  It depends on the magnitudes only, so it is enqueued on its own stream
+  //    and shares the SMs with the phase pass and the oscillator bank (neither fills every issue
+  //    slot); the mixer joins the two.  The voices are processed in halves (each half = its share of
+  //    the noise slices), so that on the host-input path the FIR of the first half runs while the
+  //    second half is still copying.
+  float* noise_part = (float*)(base + w.noise_part);
+  const int n_slices = P < kNoiseSlices ? P : kNoiseSlices;
+  auto enqueue_noise = [&](cudaStream_t ns) -> int {
+    const int halves = sync ? noise_parts(P) : 1;
+    for (int hf = 0; hf < halves; ++hf) {
+      const int v0 = P * hf / halves, v1 = P * (hf + 1) / halves;
+      const int s0 = n_slices * hf / halves, s1 = n_slices * (hf + 1) / halves;
+      if (sync) CUDA_TRY(h, cudaStreamWaitEvent(ns, sync->mags_ready[hf], 0));
+      if (int rc = run_noise_voices(h, mp, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B,
+                                    F, M, seed, 0, taps, ns))
+        return rc;
+    }
+    return B200DDSP_OK;
+  };
+  static const bool noise_beside = env_int("B200DDSP_NOISE_STREAM", 1) != 0;
+  if (noise_beside) {
+    CUDA_TRY(h, cudaEventRecord(h->ev_noise_fork, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->noise_stream, h->ev_noise_fork, 0));
+    if (int rc = enqueue_noise(h->noise_stream)) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_noise_join, h->noise_stream));
+  }
+
   // 1. everything that does not need harmonic_distribution: amplitudes, inharmonic shifts,
   //    liveness, then the phase pass of ALL voices (chunk end phases -> chunk offsets)
   if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->small_ready, 0));
@@ -1279,20 +1320,10 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   }
   const AdditiveResult mix = additive_result(run);
 
-  // 3. noise of every voice + mix -> dry  (outputs['add']['signal']); FilteredNoise.get_controls
-  //    is fused into the taps GEMM's operand load
-  //    The voices are processed in halves (each half = its share of the noise slices), so that on
-  //    the host-input path the FIR of the first half runs while the second half is still copying.
-  float* noise_part = (float*)(base + w.noise_part);
-  const int n_slices = P < kNoiseSlices ? P : kNoiseSlices;
-  const int halves = (sync && P >= 2 && n_slices >= 2) ? 2 : 1;
-  for (int hf = 0; hf < halves; ++hf) {
-    const int v0 = P * hf / halves, v1 = P * (hf + 1) / halves;
-    const int s0 = n_slices * hf / halves, s1 = n_slices * (hf + 1) / halves;
-    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->mags_ready[halves == 2 ? hf : 1], 0));
-    if (int rc = run_noise_voices(h, mp, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B, F,
-                                  M, seed, 0, taps, st))
-      return rc;
+  if (!noise_beside) {
+    if (int rc = enqueue_noise(st)) return rc;
+  } else {
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_noise_join, 0));
   }
   if (int rc = run_mix(h, noise_part, n_slices, &mix, dry_out, B, N, 0, st)) return rc;
   // 4. reverb -> wet
@@ -1448,8 +1479,18 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaEventRecord(h->ev_group[g], cs));
     sync.group_ready[g] = h->ev_group[g];
   }
-  for (int hf = 0; hf < 2; ++hf) {
-    const int v0 = P * hf / 2, v1 = P * (hf + 1) / 2;
+  // the impulse responses are small and nothing waits for them until the very end: sending them
+  // now keeps them out of the tail after the last large copy
+  float* ir_dev = nullptr;
+  if (reverb_ir_host) {
+    ir_dev = (float*)(base + hs.ir);
+    CUDA_TRY(h, cudaMemcpyAsync(ir_dev, reverb_ir_host, (size_t)B * L * 4, cudaMemcpyHostToDevice, cs));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_ir, cs));
+  sync.ir_ready = h->ev_ir;
+  const int n_parts = noise_parts(P);
+  for (int hf = 0; hf < n_parts; ++hf) {
+    const int v0 = P * hf / n_parts, v1 = P * (hf + 1) / n_parts;
     CUDA_TRY(h, copy_runs(v0, v1, BF * M, [&](int v) { return voices_host[v].magnitudes; },
                           [&](int v) { return dev[v].magnitudes; }));
     for (int v = v0; v < v1; ++v)
@@ -1459,13 +1500,6 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaEventRecord(h->ev_mags[hf], cs));
     sync.mags_ready[hf] = h->ev_mags[hf];
   }
-  float* ir_dev = nullptr;
-  if (reverb_ir_host) {
-    ir_dev = (float*)(base + hs.ir);
-    CUDA_TRY(h, cudaMemcpyAsync(ir_dev, reverb_ir_host, (size_t)B * L * 4, cudaMemcpyHostToDevice, cs));
-  }
-  CUDA_TRY(h, cudaEventRecord(h->ev_ir, cs));
-  sync.ir_ready = h->ev_ir;
 
   float* dry_dev = (float*)(base + hs.dry);
   float* wet_dev = reverb_ir_host ? (float*)(base + hs.wet) : nullptr;
