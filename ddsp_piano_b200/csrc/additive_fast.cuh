@@ -26,6 +26,7 @@
 #pragma once
 #include "additive.cuh"
 
+
 namespace b200ddsp {
 
 struct AdditivePlan;
@@ -206,22 +207,13 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 template <int NA, bool STEADY, int AMP, int UNROLL, bool PLAIN>
 __device__ __forceinline__ void osc_group_x2(const AdditiveArgs& a, OscState<NA, 2>& st,
-                                             const float* win, const float* lerp,
+                                             const float* win, const float (&fr)[UNROLL],
                                              float (&y)[kOscUnroll]) {
   static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-  static_assert(UNROLL == 4 || UNROLL == 8, "lerp loads are float4");
   float wr[4] = {0.f, 0.f, 0.f, 0.f};
   if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
     wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
-  }
-  float fr[UNROLL];
-  if (!STEADY) {             // t is a multiple of UNROLL
-#pragma unroll
-    for (int j4 = 0; j4 < UNROLL / 4; ++j4) {
-      const float4 l4 = __ldg(reinterpret_cast<const float4*>(lerp) + j4);
-      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
-    }
   }
   const float2 two_pi2 = splat2(kTwoPi), neg_two_pi2 = splat2(-kTwoPi);
   const float2 inv_sr2 = splat2(a.inv_sr), inv_sr_lo2 = splat2(a.inv_sr_lo);
@@ -286,13 +278,12 @@ __device__ __forceinline__ void osc_group_x2(const AdditiveArgs& a, OscState<NA,
 
 template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
-                                          const float* win, const float* lerp,
+                                          const float* win, const float (&fr)[UNROLL],
                                           float (&y)[kOscUnroll]) {
   static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-  static_assert(UNROLL == 4 || UNROLL == 8, "lerp loads are float4");
 #ifndef B200DDSP_NO_F32X2
   if constexpr (SP == 2) {   // substring pairs in packed float32x2 registers
-    osc_group_x2<NA, STEADY, AMP, UNROLL, PLAIN>(a, st, win, lerp, y);
+    osc_group_x2<NA, STEADY, AMP, UNROLL, PLAIN>(a, st, win, fr, y);
     return;
   }
 #endif
@@ -300,14 +291,6 @@ __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP
   if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
     wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
-  }
-  float fr[UNROLL];
-  if (!STEADY) {             // t is a multiple of UNROLL
-#pragma unroll
-    for (int j4 = 0; j4 < UNROLL / 4; ++j4) {
-      const float4 l4 = __ldg(reinterpret_cast<const float4*>(lerp) + j4);
-      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
-    }
   }
   // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
   bool cut[NA][SP];
@@ -401,27 +384,39 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, const float* fa
         st.off[q][s] = a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h];
     }
   constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
+  // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel),
+  // fetched one group ahead: the first consumer is the first instruction of the phase chain
   for (int t = t0; t < t1; t += STEP, r += STEP) {
     if (r == a.U) {
       r = 0;
       ++k;
       advance_frame<NA, SP, !ENDS_ONLY>(a, row, s0, min(k + 1, a.F - 1), lane, st, steady, amp_mode);
     }
+    // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
+    // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
+    // and does not pay: the other resident warps already cover the L1 latency.
+    float fr[STEP];
+#pragma unroll
+    for (int j4 = 0; j4 < STEP / 4; ++j4) {
+      float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!steady) l4 = __ldg(reinterpret_cast<const float4*>(fa_lerp + t) + j4);
+      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
+    }
     float y[kOscUnroll];
 #pragma unroll
     for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
     const float* w = win + r;
     if (ENDS_ONLY || amp_mode == kAmpSilent) {
-      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, fa_lerp + t, y);
-      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, fa_lerp + t, y);
+      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, fr, y);
+      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, fr, y);
       if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
-    } else {
+    } else if constexpr (!ENDS_ONLY) {
       if (amp_mode == kAmpNoCheck) {
-        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
-        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
+        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
       } else {
-        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
-        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fa_lerp + t, y);
+        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
       }
       const float v = transpose_reduce4(y, lane);
       if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
@@ -507,7 +502,7 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
 // `out` ([P * sets, B, N] partial signals, summed in a fixed order by the mixer), which keeps the
 // result independent of the scheduling order.
 template <int SP, bool ENDS_ONLY, bool PLAIN = false>
-__global__ void __launch_bounds__(kAddThreads) additive_fast_kernel(const AdditiveFastArgs fa) {
+__global__ void __launch_bounds__(kAddThreads, 3) additive_fast_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [2U]
@@ -580,9 +575,13 @@ __global__ void __launch_bounds__(256) additive_sum_partials_kernel(const Partia
 // per SM instead of 16 for all; the host launches the four buckets on four streams so that they
 // fill each other's tails.  The grid is sized for the largest possible bucket; surplus CTAs exit.
 constexpr int kSynthWarps = 4;
+// resident CTAs per SM the compiler must allow (= register budget) per bucket: 9 x 128 threads at
+// 56 registers, 8 at 64, 7 at 72, 5 at 96.  Measured on config 3: the higher occupancy is worth
+// 4 % of the stage over leaving the choice to ptxas (80 registers for NA = 3).
+__host__ __device__ constexpr int synth_min_ctas(int na) { return na == 1 ? 9 : na == 2 ? 8 : na == 3 ? 7 : 5; }
 
 template <int NA, int SP, bool PLAIN>
-__global__ void __launch_bounds__(kSynthWarps * 32) additive_synth_kernel(const AdditiveFastArgs fa) {
+__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(NA)) additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [U] rising half of hann(2U)
