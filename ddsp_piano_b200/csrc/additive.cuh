@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
 // Chunk end phases -> chunk offsets, in place (ddsp angular_cumsum: shift down one chunk,
 // cumsum over chunks in float32, then mod 2pi).  One thread per (row, substring, partial); the
 // loads of a batch of chunks are issued together so that the loop is not one L2 round trip per
-// chunk.  ends_na (optional): groups >= ends_na[row, c] were not computed for chunk c and count
+// chunk.  ends_na (optional): 16-partial half-groups >= ends_na[row, c] were not computed for chunk c and count
 // as 0 (no later chunk reads their offset).
 __global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets,
                                                                 const unsigned char* ends_na,
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_osc_rows * H) return;
   const int rs = i / H, h = i - rs * H;
-  const int group = h >> 5;
+  const int group = h >> 4;   // liveness is counted in 16-partial half-groups
   const unsigned char* na = ends_na ? ends_na + (size_t)(rs / S) * n_chunks : nullptr;
   float* p = offsets + (size_t)rs * n_chunks * H + h;
   float cum = 0.f;

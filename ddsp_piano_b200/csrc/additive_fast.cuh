@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) additive_lerp_kernel(float* __restrict__ 
 }
 
 // ---- liveness scan ---------------------------------------------------------------------------
-// na_frame[row, k] = 1 + index of the highest 32-partial group with a non-zero partial amplitude
-// in frame k (0 = silent frame).  One warp per (row, frame).
+// na_frame[row, k] = 1 + index of the highest 16-partial half-group with a non-zero partial
+// amplitude in frame k (0 = silent frame).  One warp per (row, frame).
 __global__ void __launch_bounds__(256) additive_alive_frames_kernel(
     const float* __restrict__ amp, const float* __restrict__ hd, unsigned char* __restrict__ na_frame,
     int n_row_frames, int H) {
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) additive_alive_frames_kernel(
     for (int q = 0; q * 32 < H; ++q) {
       const int h = lane + 32 * q;
       const bool live = (h < H) && (__ldg(hd + (size_t)rf * H + h) != 0.f);
-      if (__ballot_sync(0xffffffffu, live)) na = q + 1;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (m) na = (m >> 16) ? 2 * q + 2 : 2 * q + 1;
     }
   }
   if (lane == 0) na_frame[rf] = (unsigned char)na;
@@ -194,99 +195,11 @@ __device__ __forceinline__ float cos_large(float x) {
   return __cosf((float)fma(-n, 6.283185307179586, xd));
 }
 
-// ---- packed float32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) -------------------------------
-// The two substrings of a partial go through identical operations, so they ride in the two
-// halves of one 64-bit register: a packed operation takes ONE issue slot for two oscillators
-// (it still occupies the FMA pipe for two cycles), which frees issue slots for the MUFU, the
-// shuffles and the address arithmetic that used to compete with the FP32 work.  Every packed
-// operation rounds each half exactly like its scalar form (.rn), so the phase stays bit-identical.
-// One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only on
-// the scalar forms), so the one product that must stay unfused -- (bottom - top) * lerp of the
-// legacy bilinear resize -- is computed with two scalar __fmul_rn.
-__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-
-template <int NA, bool STEADY, int AMP, int UNROLL, bool PLAIN>
-__device__ __forceinline__ void osc_group_x2(const AdditiveArgs& a, OscState<NA, 2>& st,
-                                             const float* win, const float (&fr)[UNROLL],
-                                             float (&y)[kOscUnroll]) {
-  static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-  float wr[4] = {0.f, 0.f, 0.f, 0.f};
-  if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
-    const float4 r4 = *reinterpret_cast<const float4*>(win);
-    wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
-  }
-  const float2 two_pi2 = splat2(kTwoPi), neg_two_pi2 = splat2(-kTwoPi);
-  const float2 inv_sr2 = splat2(a.inv_sr), inv_sr_lo2 = splat2(a.inv_sr_lo);
-  const float2 inv_two_pi2 = splat2(kInvTwoPi);
-  const float2 magic2 = splat2(kRoundMagic), neg_magic2 = splat2(-kRoundMagic);
-  float2 ph[NA], acc[4];
-#pragma unroll
-  for (int q = 0; q < NA; ++q) ph[q] = make_float2(st.ph[q][0], st.ph[q][1]);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
-  bool cut[NA][2];
-  if (STEADY && AMP == kAmpCheck) {
-#pragma unroll
-    for (int q = 0; q < NA; ++q)
-#pragma unroll
-      for (int s = 0; s < 2; ++s) cut[q][s] = st.F[q][s] >= a.nyquist;
-  }
-#pragma unroll
-  for (int j = 0; j < UNROLL; ++j) {
-    const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
-#pragma unroll
-    for (int q = 0; q < NA; ++q) {
-      float amp_q = 0.f;
-      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.dA[q], w0, st.A[q]);
-      float2 om, f = make_float2(0.f, 0.f);
-      if (STEADY) {
-        om = make_float2(st.om[q][0], st.om[q][1]);
-      } else {
-        // top + (bottom - top) * lerp, product and sum rounded separately (scalar products: see above)
-        const float2 m = make_float2(__fmul_rn(st.dF[q][0], fr[j]), __fmul_rn(st.dF[q][1], fr[j]));
-        f = __fadd2_rn(make_float2(st.F[q][0], st.F[q][1]), m);
-        const float2 x = __fmul2_rn(f, two_pi2);                               // :69
-        om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));                // :70, see div_sr
-      }
-      ph[q] = __fadd2_rn(ph[q], om);                                           // cumsum
-      if (AMP != kAmpSilent) {
-        float2 amp = splat2(amp_q);
-        if (AMP == kAmpCheck) {                                                // :65-67
-          amp.x = (STEADY ? cut[q][0] : (f.x >= a.nyquist)) ? 0.f : amp_q;
-          amp.y = (STEADY ? cut[q][1] : (f.y >= a.nyquist)) ? 0.f : amp_q;
-        }
-        float2 c;
-        if (PLAIN) {
-          c = make_float2(cos_large(ph[q].x), cos_large(ph[q].y));             // tf.cos(tf.cumsum)
-        } else {
-          const float2 x = __fadd2_rn(ph[q], make_float2(st.off[q][0], st.off[q][1]));
-          const float2 n = __fadd2_rn(__ffma2_rn(x, inv_two_pi2, magic2), neg_magic2);
-          const float2 r = __ffma2_rn(n, neg_two_pi2, x);                      // wrap_to_pi
-          c = make_float2(__cosf(r.x), __cosf(r.y));
-        }
-        acc[j & 3] = __ffma2_rn(amp, c, acc[j & 3]);                           // :80-83
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < NA; ++q) { st.ph[q][0] = ph[q].x; st.ph[q][1] = ph[q].y; }
-  if (AMP != kAmpSilent) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] += acc[i].x + acc[i].y;
-  }
-}
-
 template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
 __device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
                                           const float* win, const float (&fr)[UNROLL],
                                           float (&y)[kOscUnroll]) {
   static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-#ifndef B200DDSP_NO_F32X2
-  if constexpr (SP == 2) {   // substring pairs in packed float32x2 registers
-    osc_group_x2<NA, STEADY, AMP, UNROLL, PLAIN>(a, st, win, fr, y);
-    return;
-  }
-#endif
   float wr[4] = {0.f, 0.f, 0.f, 0.f};
   if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
     const float4 r4 = *reinterpret_cast<const float4*>(win);
@@ -435,20 +348,266 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, const float* fa
   }
 }
 
+// ---- half-warp layout for substring pairs (S even) ---------------------------------------------
+// Lanes 0-15 carry substring s0, lanes 16-31 substring s0 + 1; chain j of a lane is partial
+// 16 j + (lane & 15).  A unit with nh live 16-partial half-groups therefore runs nh chains per
+// lane with no idle lanes beyond the last half-group (with 32-partial groups and the substrings
+// in the two halves of a register, 29 % of the lanes of the benchmark distribution computed
+// partials above Nyquist).  Chains are processed two at a time in packed float32x2 registers
+// (sm_100: FFMA2 / FADD2 / FMUL2): a packed operation takes ONE issue slot for two oscillators
+// (it still occupies the FMA pipe for two cycles), which frees issue slots for the MUFU, the
+// shuffles and the address arithmetic; an odd last chain uses the scalar forms.  Every packed
+// operation rounds each half exactly like its scalar form (.rn), so the phase stays bit-identical.
+// One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only on
+// the scalar forms), so the one product that must stay unfused -- (bottom - top) * lerp of the
+// legacy bilinear resize -- is computed with two scalar __fmul_rn.
+template <int NC>
+struct OscStateH {
+  float ph[NC];    // in-chunk float32 phase accumulator
+  float F[NC];     // partial frequency of frame k
+  float g[NC];     // general frames: F(k+1) - F(k), rounded once like the resize kernel's
+                   // bottom - top; steady frames: the constant omega
+  float off[NC];   // chunk offset (synthesis pass)
+  float A[NC];     // partial amplitude of frame k
+  float dA[NC];    // A(k+1) - A(k): the Hann cross-fade is evaluated as A + dA * w[r]
+};
+
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+template <int NC, bool WITH_AMP>
+__device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
+                                             float (&F)[NC], float (&A)[NC]) {
+  const size_t base = ((size_t)row * a.F + k) * a.H;
+  const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + k) : 0.f;
+  const float f0 = __ldg(a.f0 + ((size_t)row * a.F + k) * a.S + s);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int h = l16 + 16 * j;
+    float sh = 0.f, hdv = 0.f;
+    if (h < a.H) {
+      sh = __ldg(a.shifts + base + h);
+      if (WITH_AMP) hdv = __ldg(a.hd + base + h);
+    }
+    F[j] = (h < a.H) ? __fmul_rn(__fmul_rn(f0, (float)(h + 1)), __fadd_rn(1.0f, sh)) : 0.f;   // :106-108
+    A[j] = __fmul_rn(amp, hdv);                                                                // :111-114
+  }
+}
+
+// Load frames k and min(k + 1, F - 1) and derive the frame's variant (both frames are re-read at
+// every frame boundary: one extra L1 hit per 96 samples buys 3 NC registers of carried state).
+template <int NC, bool WITH_AMP>
+__device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
+                                              OscStateH<NC>& st, bool& steady, int& amp_mode) {
+  float Fn[NC], An[NC];
+  load_frame_h<NC, WITH_AMP>(a, row, s, k, l16, st.F, st.A);
+  load_frame_h<NC, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l16, Fn, An);
+  bool all_steady = true, any_live = false, any_risky = false;
+  // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
+  // bottom - top, one in the product, one in the sum), hence the margin
+  const float nyq_lo = a.nyquist * (1.0f - 1e-6f);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const bool live = WITH_AMP && (st.A[j] != 0.f || An[j] != 0.f);
+    any_live |= live;
+    st.dA[j] = An[j] - st.A[j];
+    st.g[j] = __fadd_rn(Fn[j], -st.F[j]);
+    all_steady &= (st.g[j] == 0.f);
+    any_risky |= live && (fmaxf(st.F[j], Fn[j]) >= nyq_lo);
+  }
+  steady = __all_sync(0xffffffffu, all_steady);
+  if (steady) {   // omega of a steady frame: f = F + 0 * lerp = F
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      st.g[j] = div_sr<true>(__fmul_rn(st.F[j], kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);
+  }
+  amp_mode = kAmpSilent;
+  if (WITH_AMP && __any_sync(0xffffffffu, any_live))
+    amp_mode = __any_sync(0xffffffffu, any_risky) ? kAmpCheck : kAmpNoCheck;
+}
+
+// UNROLL consecutive samples (inside one control frame) of every chain of the lane.
+// win = shared Hann table positioned at the first sample's offset r inside the frame.
+template <int NC, bool STEADY, int AMP, int UNROLL, bool PLAIN>
+__device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>& st, const float* win,
+                                            const float (&fr)[UNROLL], float (&y)[kOscUnroll]) {
+  static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
+  constexpr int NP = NC / 2;          // packed pairs of chains
+  constexpr bool ODD = (NC & 1) != 0; // plus one scalar chain
+  float wr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
+    const float4 r4 = *reinterpret_cast<const float4*>(win);
+    wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
+  }
+  const float2 two_pi2 = splat2(kTwoPi), neg_two_pi2 = splat2(-kTwoPi);
+  const float2 inv_sr2 = splat2(a.inv_sr), inv_sr_lo2 = splat2(a.inv_sr_lo);
+  const float2 inv_two_pi2 = splat2(kInvTwoPi);
+  const float2 magic2 = splat2(kRoundMagic), neg_magic2 = splat2(-kRoundMagic);
+  float2 ph[NP > 0 ? NP : 1], acc[4];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) ph[i] = make_float2(st.ph[2 * i], st.ph[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+  constexpr int L = NC - 1;   // the scalar chain when ODD
+#pragma unroll
+  for (int j = 0; j < UNROLL; ++j) {
+    const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int c0 = 2 * i, c1 = 2 * i + 1;
+      float2 om, f = make_float2(0.f, 0.f);
+      if (STEADY) {
+        om = make_float2(st.g[c0], st.g[c1]);
+      } else {
+        // top + (bottom - top) * lerp, product and sum rounded separately (scalar products: see above)
+        const float2 m = make_float2(__fmul_rn(st.g[c0], fr[j]), __fmul_rn(st.g[c1], fr[j]));
+        f = __fadd2_rn(make_float2(st.F[c0], st.F[c1]), m);
+        const float2 x = __fmul2_rn(f, two_pi2);                               // :69
+        om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));                // :70, see div_sr
+      }
+      ph[i] = __fadd2_rn(ph[i], om);                                           // cumsum
+      if (AMP != kAmpSilent) {
+        // Hann cross-fade of the frame amplitudes A w[r+U] + An w[r], with w[r+U] = 1 - w[r]
+        float2 amp = __ffma2_rn(make_float2(st.dA[c0], st.dA[c1]), splat2(w0),
+                                make_float2(st.A[c0], st.A[c1]));
+        if (AMP == kAmpCheck) {                                                // :65-67
+          const float2 fc = STEADY ? make_float2(st.F[c0], st.F[c1]) : f;
+          amp.x = (fc.x >= a.nyquist) ? 0.f : amp.x;
+          amp.y = (fc.y >= a.nyquist) ? 0.f : amp.y;
+        }
+        float2 c;
+        if (PLAIN) {
+          c = make_float2(cos_large(ph[i].x), cos_large(ph[i].y));             // tf.cos(tf.cumsum)
+        } else {
+          const float2 x = __fadd2_rn(ph[i], make_float2(st.off[c0], st.off[c1]));
+          const float2 n = __fadd2_rn(__ffma2_rn(x, inv_two_pi2, magic2), neg_magic2);
+          const float2 r = __ffma2_rn(n, neg_two_pi2, x);                      // wrap_to_pi
+          c = make_float2(__cosf(r.x), __cosf(r.y));
+        }
+        acc[j & 3] = __ffma2_rn(amp, c, acc[j & 3]);                           // :80-83
+      }
+    }
+    if (ODD) {
+      float om, f = 0.f;
+      if (STEADY) {
+        om = st.g[L];
+      } else {
+        f = __fadd_rn(st.F[L], __fmul_rn(st.g[L], fr[j]));
+        om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);
+      }
+      st.ph[L] = __fadd_rn(st.ph[L], om);
+      if (AMP != kAmpSilent) {
+        float amp = __fmaf_rn(st.dA[L], w0, st.A[L]);
+        if (AMP == kAmpCheck) amp = ((STEADY ? st.F[L] : f) >= a.nyquist) ? 0.f : amp;
+        const float c = PLAIN ? cos_large(st.ph[L])
+                              : __cosf(wrap_to_pi(__fadd_rn(st.ph[L], st.off[L])));
+        y[j & 3] = __fmaf_rn(amp, c, y[j & 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { st.ph[2 * i] = ph[i].x; st.ph[2 * i + 1] = ph[i].y; }
+  if (AMP != kAmpSilent && NP > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] += acc[i].x + acc[i].y;
+  }
+}
+
+// One (row, substring pair, chunk) on one warp, half-warp layout.  ENDS_ONLY: phase chain only,
+// writes the chunk end phases; otherwise writes the audio of the chunk to `row_out`.
+template <int NC, bool ENDS_ONLY, bool PLAIN>
+__device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
+                                            int c, int lane, const float* win, float* row_out) {
+  const int t0 = c * a.chunk;
+  const int t1 = min(a.N, t0 + a.chunk);
+  const int l16 = lane & 15, s = s0 + (lane >> 4);
+  OscStateH<NC> st;
+  int k = t0 / a.U;
+  int r = t0 - k * a.U;
+  bool steady;
+  int amp_mode;
+  enter_frame_h<NC, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    st.ph[j] = 0.f;
+    st.off[j] = 0.f;
+    const int h = l16 + 16 * j;
+    if (!ENDS_ONLY && c > 0 && h < a.H)
+      st.off[j] = a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h];
+  }
+  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
+  for (int t = t0; t < t1; t += STEP, r += STEP) {
+    if (r == a.U) {
+      r = 0;
+      ++k;
+      enter_frame_h<NC, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+    }
+    // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
+    // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
+    // and does not pay: the other resident warps already cover the L1 latency.
+    float fr[STEP];
+#pragma unroll
+    for (int j4 = 0; j4 < STEP / 4; ++j4) {
+      float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!steady) l4 = __ldg(reinterpret_cast<const float4*>(fa_lerp + t) + j4);
+      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
+    }
+    float y[kOscUnroll];
+#pragma unroll
+    for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
+    const float* w = win + r;
+    if (ENDS_ONLY || amp_mode == kAmpSilent) {
+      if (steady) osc_group_h<NC, true, kAmpSilent, STEP, false>(a, st, w, fr, y);
+      else osc_group_h<NC, false, kAmpSilent, STEP, false>(a, st, w, fr, y);
+      if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
+    } else if constexpr (!ENDS_ONLY) {
+      if (amp_mode == kAmpNoCheck) {
+        if (steady) osc_group_h<NC, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+        else osc_group_h<NC, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+      } else {
+        if (steady) osc_group_h<NC, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+        else osc_group_h<NC, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+      }
+      const float v = transpose_reduce4(y, lane);
+      if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
+    }
+  }
+  if (ENDS_ONLY) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int h = l16 + 16 * j;
+      if (h < a.H)
+        a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h] = floormod_two_pi(st.ph[j]);
+    }
+  }
+}
+
+// nh = live 16-partial half-groups of the unit.  S even: half-warp layout, nh chains per lane;
+// S odd: one substring per pass, lanes own partials lane + 32 q, (nh + 1) / 2 groups of 32.
 template <int SP, bool ENDS_ONLY, bool PLAIN>
-__device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int na,
+__device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int nh,
                                                    int row, int s0, int c, int lane, const float* win,
                                                    float* row_out) {
-  switch (na) {
-    case 0: break;
-    case 1: osc_chunk<1, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 2: osc_chunk<2, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 3: osc_chunk<3, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 4: osc_chunk<4, SP, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    default:
-      // more than 128 live partials: two passes over the chunk are not implemented here; the
-      // host routes H > 128 to the generic kernel
-      break;
+  if constexpr (SP == 2) {
+    switch (nh) {
+      case 0: break;
+      case 1: osc_chunk_h<1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 2: osc_chunk_h<2, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 3: osc_chunk_h<3, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 4: osc_chunk_h<4, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 5: osc_chunk_h<5, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 6: osc_chunk_h<6, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 7: osc_chunk_h<7, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      default: osc_chunk_h<8, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    }
+  } else {
+    switch ((nh + 1) / 2) {
+      case 0: break;
+      case 1: osc_chunk<1, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 2: osc_chunk<2, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      case 3: osc_chunk<3, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      default: osc_chunk<4, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+      // more than 128 live partials: the host routes H > 128 to the generic kernel
+    }
   }
 }
 
@@ -457,7 +616,7 @@ __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const 
 // proportional to the number of live partial groups.  additive_plan_kernel buckets the units by
 // that number so that the persistent kernels below can hand them out heaviest first (longest
 // processing time first: the tail of the launch is made of the cheapest units).
-constexpr int kMaxGroups = 4;        // H <= 128 on the fast path
+constexpr int kMaxGroups = 8;        // buckets = live 16-partial half-groups; H <= 128 on the fast path
 constexpr int kMaxVoiceGroups = 8;   // voice groups of one forward (host-input pipelining)
 constexpr int kPlanSlots = 1 + kMaxVoiceGroups;
 
@@ -532,7 +691,7 @@ __global__ void __launch_bounds__(kAddThreads, 3) additive_fast_kernel(const Add
 #pragma unroll
     for (int i = 0; i < kMaxGroups - 1; ++i)
       if (item >= bucket_end[i]) { bi = i + 1; begin = bucket_end[i]; }
-    const int na = kMaxGroups - bi;
+    const int na = kMaxGroups - bi;   // live half-groups of the bucket
     const int local = item - begin;
     const int unit = fa.lists[(size_t)(kind * kMaxGroups + na - 1) * n_units + local / sets];
     const int set = local - (local / sets) * sets;
@@ -575,32 +734,36 @@ __global__ void __launch_bounds__(256) additive_sum_partials_kernel(const Partia
 // per SM instead of 16 for all; the host launches the four buckets on four streams so that they
 // fill each other's tails.  The grid is sized for the largest possible bucket; surplus CTAs exit.
 constexpr int kSynthWarps = 4;
-// resident CTAs per SM the compiler must allow (= register budget) per bucket: 9 x 128 threads at
-// 56 registers, 8 at 64, 7 at 72, 5 at 96.  Measured on config 3: the higher occupancy is worth
-// 4 % of the stage over leaving the choice to ptxas (80 registers for NA = 3).
-__host__ __device__ constexpr int synth_min_ctas(int na) { return na == 1 ? 9 : na == 2 ? 8 : na == 3 ? 7 : 5; }
+// resident CTAs per SM the compiler must allow (= register budget) by chains per lane: 9 x 128
+// threads at 56 registers, 8 at 64, 7 at 72, 5 at 96.  Measured on config 3: the higher occupancy
+// is worth 4 % of the stage over leaving the choice to ptxas.
+__host__ __device__ constexpr int synth_min_ctas(int chains) {
+  return chains <= 2 ? 9 : chains <= 4 ? 8 : chains <= 6 ? 7 : 5;
+}
 
-template <int NA, int SP, bool PLAIN>
-__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(NA)) additive_synth_kernel(const AdditiveFastArgs fa) {
+template <int NH, int SP, bool PLAIN>
+__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : 2 * ((NH + 1) / 2)))
+additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [U] rising half of hann(2U)
   const int lane = threadIdx.x & 31;
   const int sets = a.S / SP;
-  const int n_items = fa.plan->count[fa.slot][NA - 1] * sets;
+  const int n_items = fa.plan->count[fa.slot][NH - 1] * sets;
   if ((int)blockIdx.x * kSynthWarps >= n_items) return;          // whole CTA has nothing to do
   for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];
   __syncthreads();
   const int item = blockIdx.x * kSynthWarps + (threadIdx.x >> 5);
   if (item >= n_items) return;
   const int n_units = a.P * a.B * a.n_chunks;
-  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NA - 1) * n_units + item / sets];
+  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NH - 1) * n_units + item / sets];
   const int set = item - (item / sets) * sets;
   const int row = unit / a.n_chunks;
   const int c = unit - row * a.n_chunks;
   const int v = row / a.B, b = row - v * a.B;
   float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-  osc_chunk<NA, SP, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
+  if constexpr (SP == 2) osc_chunk_h<NH, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
+  else osc_chunk<(NH + 1) / 2, 1, false, PLAIN>(a, fa.lerp, row, set, c, lane, win, out);
 }
 
 }  // namespace b200ddsp

@@ -37,8 +37,8 @@ struct b200ddsp_handle {
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
-  cudaStream_t aux_stream[3] = {};      // the synthesis buckets run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+  cudaStream_t aux_stream[kMaxGroups - 1] = {};   // the synthesis buckets run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {};
   cudaStream_t noise_stream = nullptr;  // the noise synth runs beside the oscillator bank
   cudaEvent_t ev_noise_fork = nullptr, ev_noise_join = nullptr;
   cudaEvent_t ev_group[8] = {};
@@ -273,7 +273,7 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   {
     bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 3 && ok; ++i) {
+    for (int i = 0; i < kMaxGroups - 1 && ok; ++i) {
       ok = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -324,7 +324,7 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->noise_stream) cudaStreamDestroy(h->noise_stream);
   if (h->ev_noise_fork) cudaEventDestroy(h->ev_noise_fork);
   if (h->ev_noise_join) cudaEventDestroy(h->ev_noise_join);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < kMaxGroups - 1; ++i) {
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
@@ -561,7 +561,7 @@ extern "C" int b200ddsp_additive_controls(b200ddsp_handle* h, const float* ampli
 
 static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
   const int U = h->U;
-  return h->fast_div && (U % 8 == 0) && (chunk_for(h, F * U) % 8 == 0) && H <= 32 * kMaxGroups &&
+  return h->fast_div && (U % 8 == 0) && (chunk_for(h, F * U) % 8 == 0) && H <= 16 * kMaxGroups &&
          lerp_is_uniform(h, F, F * U, U);
 }
 
@@ -691,16 +691,16 @@ static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, int
   }
 }
 
-template <int NA>
+template <int NH>
 static void launch_synth_bucket(const AdditiveFastArgs& fa, bool plain, int grid, size_t smem,
                                 cudaStream_t st) {
   const int threads = kSynthWarps * 32;
   if (fa.sp == 2) {
-    if (plain) additive_synth_kernel<NA, 2, true><<<grid, threads, smem, st>>>(fa);
-    else additive_synth_kernel<NA, 2, false><<<grid, threads, smem, st>>>(fa);
+    if (plain) additive_synth_kernel<NH, 2, true><<<grid, threads, smem, st>>>(fa);
+    else additive_synth_kernel<NH, 2, false><<<grid, threads, smem, st>>>(fa);
   } else {
-    if (plain) additive_synth_kernel<NA, 1, true><<<grid, threads, smem, st>>>(fa);
-    else additive_synth_kernel<NA, 1, false><<<grid, threads, smem, st>>>(fa);
+    if (plain) additive_synth_kernel<NH, 1, true><<<grid, threads, smem, st>>>(fa);
+    else additive_synth_kernel<NH, 1, false><<<grid, threads, smem, st>>>(fa);
   }
 }
 
@@ -772,23 +772,27 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
     fa.slot = 1 + g;
     const size_t smem = (size_t)r.a.U * sizeof(float);
     const bool plain = !h->cfg.inference;
-    // one kernel per bucket (number of live partial groups), heaviest on the caller's stream,
-    // the others on auxiliary streams so that the buckets overlap; grids are sized for the
+    // one kernel per bucket (number of live 16-partial half-groups), heaviest on the caller's
+    // stream, the others on auxiliary streams so that the buckets overlap; grids are sized for the
     // largest possible bucket, surplus CTAs exit at once
     const long long max_items = (long long)Pg * r.B * r.n_chunks * r.sets;
     const int grid = (int)((max_items + kSynthWarps - 1) / kSynthWarps);
-    const int n_buckets = (r.H + 31) / 32;
+    const int n_buckets = (r.H + 15) / 16;
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     int aux = 0;
-    for (int na = n_buckets; na >= 1; --na) {
-      const bool on_main = (na == n_buckets);
+    for (int nh = n_buckets; nh >= 1; --nh) {
+      const bool on_main = (nh == n_buckets);
       cudaStream_t s = on_main ? st : h->aux_stream[aux];
       if (!on_main) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_fork, 0));
-      switch (na) {
+      switch (nh) {
         case 1: launch_synth_bucket<1>(fa, plain, grid, smem, s); break;
         case 2: launch_synth_bucket<2>(fa, plain, grid, smem, s); break;
         case 3: launch_synth_bucket<3>(fa, plain, grid, smem, s); break;
-        default: launch_synth_bucket<4>(fa, plain, grid, smem, s); break;
+        case 4: launch_synth_bucket<4>(fa, plain, grid, smem, s); break;
+        case 5: launch_synth_bucket<5>(fa, plain, grid, smem, s); break;
+        case 6: launch_synth_bucket<6>(fa, plain, grid, smem, s); break;
+        case 7: launch_synth_bucket<7>(fa, plain, grid, smem, s); break;
+        default: launch_synth_bucket<8>(fa, plain, grid, smem, s); break;
       }
       CHECK_LAUNCH(h, "additive_synth_kernel");
       if (!on_main) {

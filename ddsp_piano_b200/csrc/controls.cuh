@@ -17,7 +17,7 @@ struct AdditiveControlsArgs {
   float* hd_out;           // [P*B, F, H]
   float* shifts_out;       // [P*B, F, H]
   float* f0_out;           // [P*B, F, S] copy (get_controls returns f0_hz unchanged), or nullptr
-  unsigned char* na_frame; // [P*B, F] number of leading 32-partial groups that can sound
+  unsigned char* na_frame; // [P*B, F] number of leading 16-partial half-groups that can sound
                            // (additive_fast.cuh), or nullptr
   int n_frames_voice;      // B * F
   int H, S;
@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) additive_prep_kernel(const AdditiveContro
         // the Nyquist cut of get_controls (:200-205) zeroes this partial in this frame
         can_sound = !a.normalize_below || !(fi >= a.nyquist);
       }
-      if (__ballot_sync(0xffffffffu, can_sound)) na = j + 1;
+      const unsigned m = __ballot_sync(0xffffffffu, can_sound);
+      if (m) na = (m >> 16) ? 2 * j + 2 : 2 * j + 1;
     }
     if (lane == 0) {
       a.amp_out[rf] = amp_final;
