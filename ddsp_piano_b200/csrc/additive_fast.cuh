@@ -356,7 +356,7 @@ __device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, const float* fa
 // partials above Nyquist).  Chains are processed two at a time in packed float32x2 registers
 // (sm_100: FFMA2 / FADD2 / FMUL2): a packed operation takes ONE issue slot for two oscillators
 // (it still occupies the FMA pipe for two cycles), which frees issue slots for the MUFU, the
-// shuffles and the address arithmetic; an odd last chain uses the scalar forms.  Every packed
+// shuffles and the address arithmetic; an odd last chain is packed over pairs of consecutive samples.  Every packed
 // operation rounds each half exactly like its scalar form (.rn), so the phase stays bit-identical.
 // One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only on
 // the scalar forms), so the one product that must stay unfused -- (bottom - top) * lerp of the
@@ -447,7 +447,8 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
   for (int i = 0; i < NP; ++i) ph[i] = make_float2(st.ph[2 * i], st.ph[2 * i + 1]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
-  constexpr int L = NC - 1;   // the scalar chain when ODD
+  float2 acct[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // odd chain: {y0, y1}, {y2, y3}
+  constexpr int L = NC - 1;   // the odd last chain
 #pragma unroll
   for (int j = 0; j < UNROLL; ++j) {
     const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
@@ -486,21 +487,38 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
         acc[j & 3] = __ffma2_rn(amp, c, acc[j & 3]);                           // :80-83
       }
     }
-    if (ODD) {
-      float om, f = 0.f;
+    if (ODD && (j & 1) == 0) {
+      // the odd last chain is packed over TIME instead: samples j and j + 1 share every operation
+      // except the two sequential adds of the phase accumulator
+      float2 om, f = make_float2(0.f, 0.f);
       if (STEADY) {
-        om = st.g[L];
+        om = splat2(st.g[L]);
       } else {
-        f = __fadd_rn(st.F[L], __fmul_rn(st.g[L], fr[j]));
-        om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);
+        const float2 m = make_float2(__fmul_rn(st.g[L], fr[j]), __fmul_rn(st.g[L], fr[j + 1]));
+        f = __fadd2_rn(splat2(st.F[L]), m);
+        const float2 x = __fmul2_rn(f, two_pi2);
+        om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));
       }
-      st.ph[L] = __fadd_rn(st.ph[L], om);
+      const float pa = __fadd_rn(st.ph[L], om.x);
+      const float pb = __fadd_rn(pa, om.y);
+      st.ph[L] = pb;
       if (AMP != kAmpSilent) {
-        float amp = __fmaf_rn(st.dA[L], w0, st.A[L]);
-        if (AMP == kAmpCheck) amp = ((STEADY ? st.F[L] : f) >= a.nyquist) ? 0.f : amp;
-        const float c = PLAIN ? cos_large(st.ph[L])
-                              : __cosf(wrap_to_pi(__fadd_rn(st.ph[L], st.off[L])));
-        y[j & 3] = __fmaf_rn(amp, c, y[j & 3]);
+        float2 amp = __ffma2_rn(splat2(st.dA[L]), make_float2(w0, wr[(j + 1) & 3]), splat2(st.A[L]));
+        if (AMP == kAmpCheck) {
+          const float2 fc = STEADY ? splat2(st.F[L]) : f;
+          amp.x = (fc.x >= a.nyquist) ? 0.f : amp.x;
+          amp.y = (fc.y >= a.nyquist) ? 0.f : amp.y;
+        }
+        float2 c;
+        if (PLAIN) {
+          c = make_float2(cos_large(pa), cos_large(pb));
+        } else {
+          const float2 x = __fadd2_rn(make_float2(pa, pb), splat2(st.off[L]));
+          const float2 n = __fadd2_rn(__ffma2_rn(x, inv_two_pi2, magic2), neg_magic2);
+          const float2 r = __ffma2_rn(n, neg_two_pi2, x);
+          c = make_float2(__cosf(r.x), __cosf(r.y));
+        }
+        acct[(j & 3) >> 1] = __ffma2_rn(amp, c, acct[(j & 3) >> 1]);
       }
     }
   }
@@ -509,6 +527,9 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
   if (AMP != kAmpSilent && NP > 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) y[i] += acc[i].x + acc[i].y;
+  }
+  if (AMP != kAmpSilent && ODD) {
+    y[0] += acct[0].x; y[1] += acct[0].y; y[2] += acct[1].x; y[3] += acct[1].y;
   }
 }
 
