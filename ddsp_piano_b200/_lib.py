@@ -115,6 +115,8 @@ def load():
     lib.b200ddsp_reverb_full.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_ir_decay_mask.restype = ci
     lib.b200ddsp_ir_decay_mask.argtypes = [vp, vp, vp, ci, ci, ctypes.c_float, ci, vp]
+    lib.b200ddsp_note_release.restype = ci
+    lib.b200ddsp_note_release.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.b200ddsp_fft_convolve.restype = ci
     lib.b200ddsp_fft_convolve.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_fdn_ir.restype = ci
@@ -144,7 +146,7 @@ def load():
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
-           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_fdn_ir',
+           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_fdn_ir',
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
            'b200ddsp_workspace_bytes_host', 'b200ddsp_midi_roll_to_conditioning',

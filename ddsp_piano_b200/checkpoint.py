@@ -155,3 +155,28 @@ class Checkpoint:
                     time_rev_0_sec=np.maximum(emb('_time_rev_0_sec'), 0.0),
                     alpha_tone=(1.0 / (1.0 + np.exp(-emb('_alpha_tone')))).astype(np.float32),
                     early_ir=emb('_early_ir'))
+
+
+class NpzWeights:
+    """The same ``tensor(key)`` lookup over an ``.npz`` export of a checkpoint (keys = the
+    checkpoint's variable keys, see ``tests/golden/make_dafx22_weights.py``): lets the model be
+    restored where the TensorFlow bundle itself is not available."""
+
+    def __init__(self, path):
+        self.path = path
+        with np.load(path) as z:
+            self.arrays = {k: z[k] for k in z.files}
+
+    def keys(self):
+        return sorted(self.arrays)
+
+    def find(self, fragment):
+        return [k for k in self.keys() if fragment in k]
+
+    def tensor(self, key):
+        if key not in self.arrays:
+            hits = [k for k in self.find(key) if k.endswith('/.ATTRIBUTES/VARIABLE_VALUE')]
+            if len(hits) != 1:
+                raise KeyError(f'{key!r} matches {len(hits)} variables: {hits[:5]}')
+            key = hits[0]
+        return self.arrays[key]

@@ -754,7 +754,10 @@ __global__ void __launch_bounds__(256) additive_sum_partials_kernel(const Partia
 // kernels lets each use only the registers its NA needs (48 .. 128), i.e. 40 .. 16 resident warps
 // per SM instead of 16 for all; the host launches the four buckets on four streams so that they
 // fill each other's tails.  The grid is sized for the largest possible bucket; surplus CTAs exit.
-constexpr int kSynthWarps = 4;
+#ifndef B200DDSP_SYNTH_WARPS
+#define B200DDSP_SYNTH_WARPS 4
+#endif
+constexpr int kSynthWarps = B200DDSP_SYNTH_WARPS;
 // resident CTAs per SM the compiler must allow (= register budget) by chains per lane: 9 x 128
 // threads at 56 registers, 8 at 64, 7 at 72, 5 at 96.  Measured on config 3: the higher occupancy
 // is worth 4 % of the stage over leaving the choice to ptxas.
@@ -763,7 +766,7 @@ __host__ __device__ constexpr int synth_min_ctas(int chains) {
 }
 
 template <int NH, int SP, bool PLAIN>
-__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : 2 * ((NH + 1) / 2)))
+__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : 2 * ((NH + 1) / 2)) * 4 / kSynthWarps)
 additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];

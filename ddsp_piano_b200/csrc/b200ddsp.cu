@@ -23,6 +23,7 @@
 #include "fdn.cuh"
 #include "noise.cuh"
 #include "reverb.cuh"
+#include "control_rate.cuh"
 
 using namespace b200ddsp;
 
@@ -1529,6 +1530,24 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaMemcpyAsync(dry_out_host, dry_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   if (wet_out_host)
     CUDA_TRY(h, cudaMemcpyAsync(wet_out_host, wet_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  return B200DDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// control-rate helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200ddsp_note_release(b200ddsp_handle* h, const float* active_pitch, float* extended_pitch,
+                                     int rows, int F, int in_stride, float release_frames,
+                                     void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!active_pitch || !extended_pitch) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (rows < 1 || F < 1 || in_stride < 1)
+    return fail(h, B200DDSP_BAD_SHAPE, "rows=%d F=%d in_stride=%d", rows, F, in_stride);
+  if (!(release_frames >= 0.f))
+    return fail(h, B200DDSP_BAD_ARGUMENT, "release_frames=%g must be >= 0", (double)release_frames);
+  note_release_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      active_pitch, extended_pitch, rows, F, in_stride, release_frames);
+  CHECK_LAUNCH(h, "note_release_kernel");
   return B200DDSP_OK;
 }
 

@@ -191,6 +191,17 @@ class Engine:
                 float(decay_exponent), int(decay_start), self.stream()))
         return out
 
+    def note_release(self, conditioning, release_frames):
+        """NoteRelease over conditioning [rows, F, 2] (pitch column) or active pitch [rows, F, 1]
+        -> extended_pitch [rows, F, 1]."""
+        c = self.tensor(conditioning, 'conditioning', 3)
+        out = torch.empty(c.shape[0], c.shape[1], 1, dtype=torch.float32, device=c.device)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_note_release(
+                self.handle, c.data_ptr(), out.data_ptr(), c.shape[0], c.shape[1], c.shape[2],
+                float(release_frames), self.stream()))
+        return out
+
     def fft_convolve(self, audio, ir, mask_ir0=False, add_dry=False, full=False):
         """ddsp.core.fft_convolve(audio, ir, delay_compensation=0) + the reverbs' options."""
         flags = (_lib.CONV_MASK_IR0 if mask_ir0 else 0) | (_lib.CONV_ADD_DRY if add_dry else 0) | \

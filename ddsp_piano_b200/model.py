@@ -1,0 +1,311 @@
+"""The control-rate graph of ``configs/dafx22.gin`` in front of the synthesis
+kernels: MIDI conditioning -> 250 Hz control tensors -> ``ProcessorGroup`` -> audio.
+
+Mirrors the reference's module structure (``ddsp_piano/modules/piano_model.py:146-169`` and the
+sub-modules of ``modules/sub_modules.py`` named below) so that a ``PianoModel`` here is called
+like the reference's: ``model({'conditioning': [B, F, P, 2], 'pedal': [B, F, 4],
+'piano_model': [B, 1]})`` returns the processor group's controls plus ``'audio_synth'``.
+
+This is caller-side plumbing at 1/96 of the audio rate, not the hot path: the dense layers and
+the two GRUs are torch library calls (cuBLAS / cuDNN with TF32 disabled); the note-release
+recurrence, which has no library form, is a small CUDA kernel behind the C ABI
+(``b200ddsp_note_release``).  Weights come from the reference's shipped TensorFlow checkpoint
+through the TF-free reader in ``checkpoint.py``.
+
+Parity status: checked in ``tests/test_model.py`` against a numpy restatement of the same graph on
+the shipped weights; the Keras / ddsp layer semantics underneath are restated, not pinned
+(TensorFlow is not in the container) -- see DESIGN.md section 8.
+"""
+import numpy as np
+import torch
+
+from .checkpoint import Checkpoint, NpzWeights
+from .engine import get_engine
+from .processors import (_DEFAULT_CFG, DynamicSizeFilteredNoise, MultiInharmonic,
+                         MultiInstrumentReverb, ProcessorGroup, Reverb, polyphonic_dag)
+
+MIDI_NORM = 128.0
+
+
+def _t(x, device):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=device)
+
+
+class Dense:
+    """tf.keras.layers.Dense: ``act(x @ kernel + bias)``."""
+
+    def __init__(self, kernel, bias, activation=None):
+        self.kernel, self.bias, self.activation = kernel, bias, activation
+
+    def __call__(self, x):
+        y = torch.matmul(x, self.kernel) + self.bias
+        return self.activation(y) if self.activation is not None else y
+
+
+def leaky_relu(x):
+    return torch.nn.functional.leaky_relu(x, 0.2)          # tf.nn.leaky_relu default alpha
+
+
+class GRU:
+    """tf.keras.layers.GRU(units, return_sequences=True) with TF2's ``reset_after=True``: the same
+    recurrence as torch.nn.GRU once the gates are reordered from Keras' (z, r, h) to torch's
+    (r, z, n) and the [2, 3u] bias is split into input and recurrent halves."""
+
+    def __init__(self, kernel, recurrent_kernel, bias, device):
+        u = recurrent_kernel.shape[0]
+        order = np.concatenate([np.arange(u, 2 * u), np.arange(0, u), np.arange(2 * u, 3 * u)])
+        self.gru = torch.nn.GRU(kernel.shape[0], u, batch_first=True).to(device)
+        with torch.no_grad():
+            self.gru.weight_ih_l0.copy_(_t(kernel[:, order].T, device))
+            self.gru.weight_hh_l0.copy_(_t(recurrent_kernel[:, order].T, device))
+            self.gru.bias_ih_l0.copy_(_t(bias[0][order], device))
+            self.gru.bias_hh_l0.copy_(_t(bias[1][order], device))
+        self.gru.requires_grad_(False)
+        self.gru.flatten_parameters()
+
+    def __call__(self, x):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), torch.no_grad():
+            return self.gru(x.contiguous())[0]
+
+
+class Normalize:
+    """ddsp.training.nn.Normalize('layer'): moments over time and channels (every axis but the
+    batch), learnt scale/shift [1, 1, 1, C]; ``norm_axes='channels'`` = per-frame moments."""
+
+    def __init__(self, scale, shift, norm_axes='time_channels', eps=1e-5):
+        self.scale, self.shift = scale.reshape(1, 1, -1), shift.reshape(1, 1, -1)
+        self.dims = (1, 2) if norm_axes == 'time_channels' else (2,)
+        self.eps = eps
+
+    def __call__(self, x):
+        mean = x.mean(dim=self.dims, keepdim=True)
+        var = x.var(dim=self.dims, unbiased=False, keepdim=True)
+        return (x - mean) / torch.sqrt(var + self.eps) * self.scale + self.shift
+
+
+class OneHotZEncoder:
+    """sub_modules.py:183-251: instrument id -> z, global_inharm, global_detuning, held over the
+    clip (``resample`` of a one-frame embedding is a broadcast)."""
+
+    def __init__(self, embedding, inharm_embedding, detune_embedding):
+        self.embedding, self.inharm_embedding, self.detune_embedding = \
+            embedding, inharm_embedding, detune_embedding
+        self.n_instruments = embedding.shape[0]
+
+    def __call__(self, piano_model, n_frames):
+        idx = torch.as_tensor(piano_model, device=self.embedding.device).long().reshape(-1)
+        if self.n_instruments == 1:
+            idx = torch.zeros_like(idx)
+        hold = lambda e: e[idx][:, None, :].expand(-1, n_frames, -1)
+        return hold(self.embedding), hold(self.inharm_embedding), hold(self.detune_embedding)
+
+
+class ContextNetwork:
+    """sub_modules.py:18-65 with the layers of dafx22.gin:60-71: Dense 32 (leaky_relu), GRU 64,
+    Normalize, then OutputSplitsLayer's dense_out -> context [B, F, 32]."""
+
+    def __init__(self, dense, gru, norm, dense_out, normalize_pitch=False):
+        self.dense, self.gru, self.norm, self.dense_out = dense, gru, norm, dense_out
+        self.normalize_pitch = normalize_pitch
+
+    def __call__(self, conditioning, pedal, z):
+        B, F = conditioning.shape[:2]
+        if self.normalize_pitch:
+            conditioning = conditioning / torch.tensor([MIDI_NORM, 1.0], device=conditioning.device)
+        x = torch.cat([conditioning.reshape(B, F, -1), pedal, z], dim=-1)   # collapse_last_axis :41-48
+        return self.dense_out(self.norm(self.gru(self.dense(x))))
+
+
+class NoteRelease:
+    """sub_modules.py:1174-1188 over F0ProcessorCell (:1114-1171): CUDA kernel, one thread per row."""
+
+    def __init__(self, release_duration, frame_rate=250):
+        self.release_duration, self.frame_rate = float(release_duration), frame_rate
+
+    def __call__(self, conditioning):
+        eng = get_engine(conditioning.device, **_DEFAULT_CFG)
+        return eng.note_release(conditioning, np.float32(self.release_duration) * np.float32(self.frame_rate))
+
+
+class InharmonicityNetwork:
+    """sub_modules.py:611-701."""
+
+    def __init__(self, model_specific_weight, slopes, offsets, slopes_modifier, offsets_modifier):
+        self.model_specific_weight = model_specific_weight
+        self.slopes, self.offsets = slopes + slopes_modifier, offsets + offsets_modifier
+
+    def __call__(self, extended_pitch, global_inharm=None):
+        asym = self.slopes * (extended_pitch / MIDI_NORM + self.offsets)
+        if global_inharm is not None:
+            g = global_inharm * 10.0
+            asym = asym + self.model_specific_weight * torch.cat([torch.zeros_like(g), g], dim=-1)
+        return torch.exp(asym).sum(dim=-1, keepdim=True)
+
+
+class Detuner:
+    """sub_modules.py:903-943."""
+
+    def __init__(self, layer, n_substrings=2, use_detune=True):
+        self.layer, self.n_substrings, self.use_detune = layer, n_substrings, use_detune
+
+    def __call__(self, extended_pitch, global_detuning=None):
+        pitch = extended_pitch
+        if self.use_detune:
+            detuning = torch.tanh(self.layer(extended_pitch / MIDI_NORM))
+            if global_detuning is not None:
+                detuning = detuning + torch.tanh(global_detuning)
+            pitch = extended_pitch + detuning
+        return 440.0 * torch.exp2((pitch - 69.0) / 12.0)                     # ddsp.core.midi_to_hz
+
+
+class MonophonicNetwork:
+    """sub_modules.py:455-496 with the layers of dafx22.gin:73-88: Dense 128, GRU 192, Dense 192,
+    Normalize, dense_out -> (amplitudes 1, harmonic_distribution H, magnitudes M)."""
+
+    def __init__(self, dense1, gru, dense2, norm, dense_out, output_splits):
+        self.dense1, self.gru, self.dense2, self.norm, self.dense_out = dense1, gru, dense2, norm, dense_out
+        self.output_splits = output_splits
+
+    def __call__(self, conditioning, extended_pitch, context):
+        scale = torch.tensor([MIDI_NORM, 1.0], device=conditioning.device)
+        x = torch.cat([extended_pitch / MIDI_NORM, conditioning / scale, context], dim=-1)
+        y = self.dense_out(self.norm(self.dense2(self.gru(self.dense1(x)))))
+        out, at = {}, 0
+        for key, dim in self.output_splits:
+            out[key] = y[..., at:at + dim]
+            at += dim
+        return out
+
+
+class Parallelizer:
+    """sub_modules.py:528-602: merges the polyphony axis into the batch (voice-major rows
+    v * B + b) for the monophonic modules and hands the results back as stacked [P, B, F, C]
+    tensors plus per-voice views ``key_i`` -- the layout the fused forward takes zero-copy."""
+
+    def __init__(self, n_synths=16,
+                 global_keys=('conditioning', 'context', 'global_inharm', 'global_detuning'),
+                 mono_keys=('f0_hz', 'inharm_coef', 'amplitudes', 'harmonic_distribution', 'magnitudes')):
+        self.n_synths, self.global_keys, self.mono_keys = n_synths, global_keys, mono_keys
+
+    def parallelize(self, features):
+        P = self.n_synths
+        for k in self.global_keys:
+            x = features[k]
+            if x.dim() == 4:                                                 # [B, F, P, C] -> [P, B, F, C]
+                x = x.permute(2, 0, 1, 3)
+            else:
+                x = x.unsqueeze(0).expand(P, *x.shape)
+            self.batch_size = x.shape[1]
+            features[k] = x.reshape(P * x.shape[1], *x.shape[2:])
+        return features
+
+    def unparallelize(self, features):
+        P = self.n_synths
+        for k in self.mono_keys:
+            x = features[k].contiguous()
+            x = x.reshape(P, self.batch_size, *x.shape[1:])
+            features[k] = x
+            for i in range(P):
+                features[f'{k}_{i}'] = x[i]
+        return features
+
+    def __call__(self, features, parallelize=True):
+        return self.parallelize(features) if parallelize else self.unparallelize(features)
+
+
+class PianoModel:
+    """piano_model.py:12-169, inference only: global features -> parallelize -> monophonic
+    features -> unparallelize -> processor group."""
+
+    def __init__(self, z_encoder, note_release, context_network, parallelizer, monophonic_network,
+                 inharm_model, detuner, reverb_model, processor_group):
+        self.z_encoder, self.note_release, self.context_network = z_encoder, note_release, context_network
+        self.parallelizer, self.monophonic_network = parallelizer, monophonic_network
+        self.inharm_model, self.detuner, self.reverb_model = inharm_model, detuner, reverb_model
+        self.processor_group = processor_group
+
+    @property
+    def n_synths(self):
+        return self.parallelizer.n_synths
+
+    @property
+    def sample_rate(self):
+        return self.processor_group.processors[0].sample_rate
+
+    def compute_controls(self, features):
+        """Everything before the processor group (piano_model.py:146-158)."""
+        f = dict(features)
+        dev = self.z_encoder.embedding.device
+        f['conditioning'] = torch.as_tensor(f['conditioning'], dtype=torch.float32, device=dev)
+        f['pedal'] = torch.as_tensor(f['pedal'], dtype=torch.float32, device=dev)
+        n_frames = f['conditioning'].shape[1]
+        # compute_global_features :118-128
+        f['z'], f['global_inharm'], f['global_detuning'] = self.z_encoder(f['piano_model'], n_frames)
+        f['context'] = self.context_network(f['conditioning'], f['pedal'], f['z'])
+        f['reverb_ir'] = self.reverb_model(f['piano_model'])
+        f = self.parallelizer(f, parallelize=True)
+        # compute_monophonic_features :130-142
+        f['extended_pitch'] = self.note_release(f['conditioning'])
+        f['inharm_coef'] = self.inharm_model(f['extended_pitch'], f['global_inharm'])
+        f['f0_hz'] = self.detuner(f['extended_pitch'], f['global_detuning'])
+        f.update(self.monophonic_network(f['conditioning'], f['extended_pitch'], f['context']))
+        return self.parallelizer(f, parallelize=False)
+
+    def __call__(self, features, training=False):
+        if training:
+            raise ValueError('the B200 path is inference only (no losses, no gradients)')
+        f = self.compute_controls(features)
+        pg_out = self.processor_group(f, return_outputs_dict=True)          # piano_model.py:160
+        outputs = pg_out['controls']
+        outputs['audio_synth'] = pg_out['signal']
+        return outputs
+
+    def get_audio_from_outputs(self, outputs):
+        return outputs['audio_synth']
+
+
+def dafx22_model(checkpoint_prefix, device='cuda', sample_rate=16000, frame_rate=250, n_synths=16,
+                 inference=True, norm_axes='time_channels', seed=0):
+    """The model ``configs/dafx22.gin`` builds, restored from the shipped weights
+    (``model_weights/dafx22/ckpt-0``; 16 kHz, 96 partials, 64 noise bands, 1.5 s reverb)."""
+    device = torch.device(device)
+    if isinstance(checkpoint_prefix, (Checkpoint, NpzWeights)):
+        ck = checkpoint_prefix
+    elif str(checkpoint_prefix).endswith('.npz'):
+        ck = NpzWeights(checkpoint_prefix)
+    else:
+        ck = Checkpoint(checkpoint_prefix)
+    t = lambda name: _t(ck.tensor(f'model/{name}/.ATTRIBUTES/VARIABLE_VALUE'), device)
+    raw = lambda name: ck.tensor(f'model/{name}/.ATTRIBUTES/VARIABLE_VALUE')
+    dense = lambda p, act=None: Dense(t(f'{p}/kernel'), t(f'{p}/bias'), act)
+    gru = lambda p: GRU(raw(f'{p}/cell/kernel'), raw(f'{p}/cell/recurrent_kernel'), raw(f'{p}/cell/bias'), device)
+    norm = lambda p: Normalize(t(f'{p}/scale'), t(f'{p}/shift'), norm_axes)
+    cn, mn = 'context_network/model/layer_with_weights-', 'monophonic_network/model/layer_with_weights-'
+    out_dim = raw('monophonic_network/dense_out/bias').shape[0]
+    n_mags = 64
+    splits = (('amplitudes', 1), ('harmonic_distribution', out_dim - 1 - n_mags), ('magnitudes', n_mags))
+    additive = MultiInharmonic(frame_rate=frame_rate, sample_rate=sample_rate, inference=inference,
+                               name='additive')
+    noise = DynamicSizeFilteredNoise(frame_rate=frame_rate, sample_rate=sample_rate, name='noise',
+                                     seed=seed)
+    dag = polyphonic_dag(additive=additive, noise=noise, reverb=Reverb(trainable=False),
+                         additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+                         noise_controls=['magnitudes'], reverb_controls=['reverb_ir'], n_synths=n_synths)
+    return PianoModel(
+        z_encoder=OneHotZEncoder(t('z_encoder/embedding/embeddings'),
+                                 t('z_encoder/inharm_embedding/embeddings'),
+                                 t('z_encoder/detune_embedding/embeddings')),
+        note_release=NoteRelease(float(raw('note_release/layer/cell/release_duration')), frame_rate),
+        context_network=ContextNetwork(dense(cn + '0', leaky_relu), gru(cn + '1'), norm(cn + '2'),
+                                       dense('context_network/dense_out')),
+        parallelizer=Parallelizer(n_synths),
+        monophonic_network=MonophonicNetwork(dense(mn + '0', leaky_relu), gru(mn + '1'),
+                                             dense(mn + '2', leaky_relu), norm(mn + '3'),
+                                             dense('monophonic_network/dense_out'), splits),
+        inharm_model=InharmonicityNetwork(*(t(f'inharm_model/{k}') for k in
+                                            ('model_specific_weight', 'slopes', 'offsets',
+                                             'slopes_modifier', 'offsets_modifier'))),
+        detuner=Detuner(dense('detuner/layer')),
+        reverb_model=MultiInstrumentReverb(t('reverb_model/reverb_dict/layer_with_weights-0/embeddings'),
+                                           sample_rate=sample_rate, inference=inference),
+        processor_group=ProcessorGroup(dag=dag))

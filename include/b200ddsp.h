@@ -167,6 +167,15 @@ int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir
 int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int B, int L,
                            float decay_exponent, int decay_start, void* stream);
 
+/* NoteRelease -- modules/sub_modules.py:1174-1188 (tfkl.RNN over F0ProcessorCell, :1114-1171): holds
+ * each voice's last played MIDI note for `release_frames` (= release_duration * frame_rate; the
+ * shipped dafx22 weights have release_duration = 1 s) frames after its note-off, so that the partial
+ * frequencies stay defined while the note rings out.  active_pitch is read with a stride of
+ * in_stride floats between frames (2 for the pitch column of conditioning [rows, F, 2], :1184);
+ * extended_pitch is [rows, F].  Control-rate helper of the caller row SURVEY 8f-1. */
+int b200ddsp_note_release(b200ddsp_handle* h, const float* active_pitch, float* extended_pitch,
+                          int rows, int F, int in_stride, float release_frames, void* stream);
+
 /* ddsp.core.fft_convolve(audio, ir, padding, delay_compensation=0) with the options the reverbs
  * of the reference use.  flags: B200DDSP_CONV_MASK_IR0 zeroes ir[:,0] (effects.Reverb masks the dry
  * tap), B200DDSP_CONV_ADD_DRY adds the input (effects.Reverb add_dry), B200DDSP_CONV_FULL writes

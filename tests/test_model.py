@@ -1,0 +1,172 @@
+"""Control-rate graph of dafx22.gin: ddsp_piano_b200/model.py against the numpy
+restatement oracle/piano_model_np.py on the shipped weights (tests/golden/dafx22_weights.npz,
+exported by tests/golden/make_dafx22_weights.py).  The Keras/ddsp layer semantics underneath both
+are restated, not pinned (see the oracle's header)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import piano_model_np as ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WEIGHTS = os.path.join(HERE, 'golden', 'dafx22_weights.npz')
+
+
+@pytest.fixture(scope='module')
+def weights():
+    from ddsp_piano_b200.checkpoint import NpzWeights
+    return NpzWeights(WEIGHTS)
+
+
+def midi_clip(B=2, T=300, P=16, seed=0):
+    """A few notes per clip on the first voices, the rest silent (pitch 0), pedal ramps."""
+    rng = np.random.default_rng(seed)
+    cond = np.zeros([B, T, P, 2], np.float32)
+    for b in range(B):
+        for v in range(4):
+            t = int(rng.integers(0, T // 4))
+            while t < T - 20:
+                dur = int(rng.integers(20, 120))
+                cond[b, t:t + dur, v, 0] = rng.integers(30, 100)
+                cond[b, t, v, 1] = rng.uniform(0.2, 1.0)
+                t += dur + int(rng.integers(5, 60))
+    pedal = np.zeros([B, T, 4], np.float32)
+    pedal[:, T // 3:2 * T // 3, 0] = 0.8
+    return cond, pedal, np.arange(B).reshape(B, 1) % 2
+
+
+# ---- oracle known answers -------------------------------------------------------------------
+
+def test_note_release_holds_the_note_for_the_release_time():
+    T, rel = 400, 0.4                                   # 100 frames at 250 Hz
+    pitch = np.zeros([1, T, 1], np.float32)
+    pitch[0, 10:30, 0] = 60
+    out = ref.note_release(pitch, rel, 250)[0, :, 0]
+    assert np.all(out[:10] == 0) and np.all(out[10:30] == 60)
+    # the counter starts at the first silent frame: held while steps <= 100, i.e. 101 more frames
+    assert np.all(out[30:131] == 60) and np.all(out[131:] == 0)
+
+
+def test_note_release_new_note_replaces_the_held_one():
+    pitch = np.zeros([1, 200, 1], np.float32)
+    pitch[0, 5:10, 0] = 50
+    pitch[0, 40:45, 0] = 72
+    out = ref.note_release(pitch, 1.0, 250)[0, :, 0]
+    assert np.all(out[10:40] == 50) and np.all(out[40:] == 72)
+
+
+def test_inharmonicity_and_detuner_known_answers(weights):
+    w = ref.load_weights(weights)
+    pitch = np.array([[[21.0], [60.0], [108.0]]], np.float32)
+    b = ref.inharmonicity(pitch, None, w['inharm'])[0, :, 0]
+    # Rigaud et al. tessitura model: a valley between the bass and treble bridges
+    assert b[1] < b[0] and b[1] < b[2] and 1e-5 < b[1] < 1e-3
+    f0 = ref.detuner(pitch, None, np.zeros([1, 2], np.float32), np.zeros(2, np.float32))
+    np.testing.assert_allclose(f0[0, 1], 440.0 * 2 ** ((60 - 69) / 12), rtol=1e-6)
+    # silent voices (pitch 0) land at 8.18 Hz, below min_frequency: the synth mutes them
+    assert ref.detuner(np.zeros([1, 1, 1], np.float32), None, *w['detuner'])[0, 0, 0] < 20.0
+
+
+def test_gru_restatement_matches_torch_gru():
+    from ddsp_piano_b200.model import GRU
+    rng = np.random.default_rng(1)
+    i, u = 7, 12
+    k, r, b = (rng.standard_normal(s).astype(np.float32) * 0.4 for s in ([i, 3 * u], [u, 3 * u], [2, 3 * u]))
+    x = rng.standard_normal([3, 40, i]).astype(np.float32)
+    want = ref.gru(x, k, r, b)
+    got = GRU(k, r, b, torch.device('cpu'))(torch.from_numpy(x)).numpy()
+    np.testing.assert_allclose(got, want, atol=2e-6)
+
+
+def test_controls_on_cpu_match_the_oracle(weights, monkeypatch):
+    """The torch graph (on CPU, with the note-release kernel replaced by the oracle's recurrence)
+    against the numpy restatement, shipped weights."""
+    from ddsp_piano_b200 import model as M
+    cond, pedal, pm = midi_clip()
+    w = ref.load_weights(weights)
+    want = ref.control_graph(cond, pedal, pm, w)
+
+    class CpuRelease:
+        def __init__(self, dur, fr):
+            self.dur, self.fr = dur, fr
+
+        def __call__(self, conditioning):
+            return torch.from_numpy(ref.note_release(conditioning[..., 0:1].numpy(), self.dur, self.fr))
+
+    class CpuReverb:
+        def __init__(self, emb, **kw):
+            self.emb = emb
+
+        def __call__(self, pm_):
+            return self.emb[torch.as_tensor(pm_).long().reshape(-1)]
+
+    monkeypatch.setattr(M, 'NoteRelease', CpuRelease)
+    monkeypatch.setattr(M, 'MultiInstrumentReverb', CpuReverb)
+    model = M.dafx22_model(weights, device='cpu')
+    got = model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': pm})
+    for key in ('f0_hz', 'inharm_coef', 'amplitudes', 'harmonic_distribution', 'magnitudes'):
+        g, r_ = got[key].numpy(), want[key]
+        assert g.shape == r_.shape, key
+        err = np.max(np.abs(g - r_)) / np.max(np.abs(r_))
+        assert err < 1e-4, (key, err)
+        assert got[f'{key}_3'].data_ptr() == got[key][3].data_ptr()          # per-voice views
+    assert got['reverb_ir'].shape == (2, 24000)
+
+
+# ---- GPU -------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_note_release_kernel_is_bit_exact():
+    import ddsp_piano_b200 as dp
+    dev = torch.device('cuda:0')
+    cond, _, _ = midi_clip(B=3, T=700, seed=3)
+    rows = cond.transpose(2, 0, 1, 3).reshape(-1, 700, 2)
+    want = ref.note_release(rows[..., 0:1], 1.0, 250)
+    eng = dp.get_engine(dev, **dp.processors._DEFAULT_CFG)
+    got = eng.note_release(torch.from_numpy(rows).to(dev), 250.0).cpu().numpy()
+    assert np.array_equal(got, want)
+    got1 = eng.note_release(torch.from_numpy(rows[..., 0:1].copy()).to(dev), 250.0).cpu().numpy()
+    assert np.array_equal(got1, want)
+
+
+@pytest.mark.gpu
+def test_dafx22_controls_match_the_oracle_on_gpu(weights):
+    import ddsp_piano_b200 as dp
+    cond, pedal, pm = midi_clip(B=2, T=300)
+    want = ref.control_graph(cond, pedal, pm, ref.load_weights(weights))
+    model = dp.dafx22_model(weights, device='cuda:0')
+    got = model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': pm})
+    assert np.array_equal(got['extended_pitch'].cpu().numpy().reshape(want['extended_pitch'].shape),
+                          want['extended_pitch'])
+    for key in ('f0_hz', 'inharm_coef', 'amplitudes', 'harmonic_distribution', 'magnitudes'):
+        g, r_ = got[key].cpu().numpy(), want[key]
+        err = np.max(np.abs(g - r_)) / np.max(np.abs(r_))
+        assert err < 1e-4, (key, err)
+
+
+@pytest.mark.gpu
+def test_dafx22_midi_to_audio(weights):
+    """MIDI conditioning -> audio with the shipped weights: one sustained A4 sounds at 440 Hz during
+    the note, decays after the note-off, and the clip is silent before the onset."""
+    import ddsp_piano_b200 as dp
+    B, T, P, sr = 1, 750, 16, 16000
+    cond = np.zeros([B, T, P, 2], np.float32)
+    cond[0, 250:500, 0, 0] = 69
+    cond[0, 250, 0, 1] = 0.8
+    model = dp.dafx22_model(weights, device='cuda:0', sample_rate=sr, inference=True)
+    out = model({'conditioning': cond, 'pedal': np.zeros([B, T, 4], np.float32),
+                 'piano_model': np.zeros([B, 1], np.int64)})
+    audio = model.get_audio_from_outputs(out).cpu().numpy()
+    U = sr // 250
+    assert audio.shape == (B, T * U) and np.all(np.isfinite(audio))
+    dry = out['add']['signal'].cpu().numpy()[0]
+    before, during, after = dry[100 * U:240 * U], dry[260 * U:500 * U], dry[700 * U:]
+    rms = lambda x: float(np.sqrt(np.mean(x.astype(np.float64) ** 2)))
+    # (the 16 noise synths hiss at a low level whether or not a note sounds)
+    assert rms(during) > 5 * rms(before) and rms(during) > 5 * rms(after)
+    n = 8192
+    spec = np.abs(np.fft.rfft(during[2048:2048 + n] * np.hanning(n), 4 * n))
+    peak_hz = np.argmax(spec) * sr / (4 * n)
+    assert abs(peak_hz - 440.0) < 3.0, peak_hz
