@@ -159,7 +159,7 @@ class Checkpoint:
 
 class NpzWeights:
     """The same ``tensor(key)`` lookup over an ``.npz`` export of a checkpoint (keys = the
-    checkpoint's variable keys, see ``tests/golden/make_dafx22_weights.py``): lets the model be
+    checkpoint's variable keys, see ``tests/golden/make_model_weights.py``): lets the model be
     restored where the TensorFlow bundle itself is not available."""
 
     def __init__(self, path):

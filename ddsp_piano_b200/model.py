@@ -218,7 +218,8 @@ class PianoModel:
     features -> unparallelize -> processor group."""
 
     def __init__(self, z_encoder, note_release, context_network, parallelizer, monophonic_network,
-                 inharm_model, detuner, reverb_model, processor_group):
+                 inharm_model, detuner, reverb_model, processor_group, device='cuda'):
+        self.device = torch.device(device)
         self.z_encoder, self.note_release, self.context_network = z_encoder, note_release, context_network
         self.parallelizer, self.monophonic_network = parallelizer, monophonic_network
         self.inharm_model, self.detuner, self.reverb_model = inharm_model, detuner, reverb_model
@@ -235,19 +236,26 @@ class PianoModel:
     def compute_controls(self, features):
         """Everything before the processor group (piano_model.py:146-158)."""
         f = dict(features)
-        dev = self.z_encoder.embedding.device
+        dev = self.device
         f['conditioning'] = torch.as_tensor(f['conditioning'], dtype=torch.float32, device=dev)
         f['pedal'] = torch.as_tensor(f['pedal'], dtype=torch.float32, device=dev)
+        f['piano_model'] = torch.as_tensor(f['piano_model'], device=dev).long().reshape(-1, 1)
         n_frames = f['conditioning'].shape[1]
         # compute_global_features :118-128
-        f['z'], f['global_inharm'], f['global_detuning'] = self.z_encoder(f['piano_model'], n_frames)
-        f['context'] = self.context_network(f['conditioning'], f['pedal'], f['z'])
+        if self.z_encoder is not None:
+            f['z'], f['global_inharm'], f['global_detuning'] = self.z_encoder(f['piano_model'], n_frames)
+            f['context'] = self.context_network(f['conditioning'], f['pedal'], f['z'])
+        else:
+            f['context'] = self.context_network(f['conditioning'], f['pedal'], f['piano_model'])
         f['reverb_ir'] = self.reverb_model(f['piano_model'])
         f = self.parallelizer(f, parallelize=True)
         # compute_monophonic_features :130-142
         f['extended_pitch'] = self.note_release(f['conditioning'])
-        f['inharm_coef'] = self.inharm_model(f['extended_pitch'], f['global_inharm'])
-        f['f0_hz'] = self.detuner(f['extended_pitch'], f['global_detuning'])
+        if self.detuner is not None:
+            f['inharm_coef'] = self.inharm_model(f['extended_pitch'], f['global_inharm'])
+            f['f0_hz'] = self.detuner(f['extended_pitch'], f['global_detuning'])
+        else:
+            f['f0_hz'], f['inharm_coef'] = self.inharm_model(f['extended_pitch'], f['piano_model'])
         f.update(self.monophonic_network(f['conditioning'], f['extended_pitch'], f['context']))
         return self.parallelizer(f, parallelize=False)
 
@@ -308,4 +316,180 @@ def dafx22_model(checkpoint_prefix, device='cuda', sample_rate=16000, frame_rate
         detuner=Detuner(dense('detuner/layer')),
         reverb_model=MultiInstrumentReverb(t('reverb_model/reverb_dict/layer_with_weights-0/embeddings'),
                                            sample_rate=sample_rate, inference=inference),
-        processor_group=ProcessorGroup(dag=dag))
+        processor_group=ProcessorGroup(dag=dag), device=device)
+
+
+# ---- configs/maestro-v2.gin: the script default (synthesize_midi_file.py:14-17) ----------------
+
+class LayerNormalization:
+    """tf.keras.layers.LayerNormalization(): last axis, epsilon 1e-3."""
+
+    def __init__(self, gamma, beta, eps=1e-3):
+        self.gamma, self.beta, self.eps = gamma, beta, eps
+
+    def __call__(self, x):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), self.gamma, self.beta, self.eps)
+
+
+class FcStack:
+    """ddsp.training.nn.FcStack(ch, layers): [Dense, LayerNormalization, leaky_relu] x layers."""
+
+    def __init__(self, layers):
+        self.layers = layers                       # [(Dense, LayerNormalization)]
+
+    def __call__(self, x):
+        for dense, norm in self.layers:
+            x = leaky_relu(norm(dense(x)))
+        return x
+
+
+class FiLMContextNetwork:
+    """sub_modules.py:97-180."""
+
+    def __init__(self, conditioning_head, pedal_head, piano_id_head, main_dense0, main_gru, main_dense2,
+                 main_norm, film_input_reshape, output_layer):
+        self.conditioning_head, self.pedal_head, self.piano_id_head = conditioning_head, pedal_head, piano_id_head
+        self.main_dense0, self.main_gru, self.main_dense2, self.main_norm = \
+            main_dense0, main_gru, main_dense2, main_norm
+        self.film_input_reshape, self.output_layer = film_input_reshape, output_layer
+
+    def apply_film(self, features, piano_feat):
+        film_coef, film_bias = self.film_input_reshape(piano_feat).chunk(2, dim=-1)
+        return features * film_coef + film_bias
+
+    def __call__(self, conditioning, pedal, piano_model):
+        B, F = conditioning.shape[:2]
+        scale = torch.tensor([MIDI_NORM, 1.0], device=conditioning.device)
+        conditioning_feat = self.conditioning_head((conditioning / scale).reshape(B, F, -1))
+        pedal_feat = self.pedal_head(pedal)
+        piano_feat = self.piano_id_head[piano_model.reshape(-1)][:, None, :]
+        x = torch.cat([conditioning_feat, pedal_feat], dim=-1)
+        x = leaky_relu(self.main_norm(self.main_dense2(self.main_gru(self.main_dense0(x)))))
+        return self.output_layer(self.apply_film(x, piano_feat))
+
+
+class MonophonicDeepNetwork:
+    """sub_modules.py:499-525."""
+
+    def __init__(self, input_stacks, rnn, out_stack, dense_out, output_splits):
+        self.input_stacks, self.rnn, self.out_stack, self.dense_out = input_stacks, rnn, out_stack, dense_out
+        self.output_splits = output_splits
+
+    def __call__(self, conditioning, extended_pitch, context):
+        scale = torch.tensor([MIDI_NORM, 1.0], device=conditioning.device)
+        a = self.input_stacks[0](extended_pitch / MIDI_NORM)
+        b = self.input_stacks[1](conditioning / scale)
+        c = self.input_stacks[2](context)
+        x = self.rnn(torch.cat([a, b, c], dim=-1))
+        y = self.dense_out(self.out_stack(torch.cat([a, b, c, x], dim=-1)))
+        out, at = {}, 0
+        for key, dim in self.output_splits:
+            out[key] = y[..., at:at + dim]
+            at += dim
+        return out
+
+
+class JointParametricInharmTuning:
+    """sub_modules.py:763-876 (Rigaud et al., DAFx-11): inharmonicity and octave-stretched tuning
+    along the tessitura from seven per-instrument parameters."""
+
+    def __init__(self, **embeddings):
+        self.e = embeddings                        # alpha_b, beta_b, alpha_t, beta_t, pitch_ref, K, alpha
+
+    def _p(self, name, piano_model):
+        return self.e[name][piano_model.reshape(-1)][:, None, :]
+
+    def get_inharm(self, pitch, pm):
+        return torch.exp(self._p('alpha_b', pm) * pitch + self._p('beta_b', pm)) + \
+            torch.exp(self._p('alpha_t', pm) * pitch + self._p('beta_t', pm))
+
+    def get_deviation_from_ET(self, pitch, pm):
+        hz = lambda n: 440.0 * torch.exp2((n - 69.0) / 12.0)
+        ref = self._p('pitch_ref', pm)
+        ratio = hz(pitch) / hz(ref)
+        rho = 1.0 + self._p('K', pm) * (1.0 - torch.tanh((pitch - ref) / self._p('alpha', pm))) / 2.0
+        detuning = 1.0 + self.get_inharm(ref, pm) * (ratio * rho) ** 2
+        detuning = detuning / (1.0 + self.get_inharm(pitch, pm) * rho ** 2)
+        return torch.sqrt(detuning)
+
+    def __call__(self, extended_pitch, piano_model):
+        inharm_coef = self.get_inharm(extended_pitch, piano_model)
+        f0_hz = 440.0 * torch.exp2((extended_pitch - 69.0) / 12.0) * \
+            self.get_deviation_from_ET(extended_pitch, piano_model)
+        return f0_hz, inharm_coef
+
+
+class MultiInstrumentFeedbackDelayReverb:
+    """sub_modules.py:368-446: per-instrument FDN parameters (embeddings) -> ``reverb_ir`` through
+    ``FeedbackDelayNetwork.get_ir`` (the CUDA IR generator of csrc/fdn.cuh)."""
+
+    def __init__(self, embeddings, sample_rate=24000):
+        from .processors import FeedbackDelayNetwork
+        self.e = embeddings
+        self.n_instruments = embeddings['_input_gain'].shape[0]
+        self.reverb_model = FeedbackDelayNetwork(trainable=False, sampling_rate=float(sample_rate))
+        self.reverb_model.build(None)
+
+    def __call__(self, piano_model):
+        idx = piano_model.reshape(-1)
+        if self.n_instruments == 1:
+            idx = torch.zeros_like(idx)
+        split = lambda x: torch.stack(x.chunk(4, dim=-1), dim=-1)            # reshape_embedding :427-429
+        g = lambda name: self.e[name][idx]
+        return self.reverb_model.get_ir(
+            g('_input_gain'), g('_output_gain'), split(g('_gain_allpass')).contiguous(),
+            split(g('_delays_allpass')).contiguous(), torch.relu(g('_time_rev_0_sec')),
+            torch.sigmoid(g('_alpha_tone')), g('_early_ir'))
+
+
+def maestro_v2_model(checkpoint_prefix, device='cuda', sample_rate=24000, frame_rate=250, n_synths=16,
+                     inference=True, seed=0):
+    """The model ``configs/maestro-v2.gin`` builds, restored from the shipped weights
+    (``model_weights/v2/ckpt-225000``; 24 kHz, 128 partials, 96 noise bands, one string per note,
+    2 s feedback-delay-network reverb)."""
+    device = torch.device(device)
+    if isinstance(checkpoint_prefix, (Checkpoint, NpzWeights)):
+        ck = checkpoint_prefix
+    elif str(checkpoint_prefix).endswith('.npz'):
+        ck = NpzWeights(checkpoint_prefix)
+    else:
+        ck = Checkpoint(checkpoint_prefix)
+    raw = lambda name: ck.tensor(f'model/{name}/.ATTRIBUTES/VARIABLE_VALUE')
+    t = lambda name: _t(raw(name), device)
+    dense = lambda p, act=None: Dense(t(f'{p}/kernel'), t(f'{p}/bias'), act)
+    gru = lambda p: GRU(raw(f'{p}/cell/kernel'), raw(f'{p}/cell/recurrent_kernel'), raw(f'{p}/cell/bias'), device)
+    ln = lambda p: LayerNormalization(t(f'{p}/gamma'), t(f'{p}/beta'))
+    lw = 'layer_with_weights-'
+    stack = lambda p, n: FcStack([(dense(f'{p}/{lw}{i}/{lw}0'), ln(f'{p}/{lw}{i}/{lw}1')) for i in range(n)])
+    cn, mn = 'context_network', 'monophonic_network'
+    out_dim = raw(f'{mn}/dense_out/bias').shape[0]
+    n_mags = 96
+    splits = (('amplitudes', 1), ('harmonic_distribution', out_dim - 1 - n_mags), ('magnitudes', n_mags))
+    additive = MultiInharmonic(frame_rate=frame_rate, sample_rate=sample_rate, inference=inference,
+                               name='additive')
+    noise = DynamicSizeFilteredNoise(frame_rate=frame_rate, sample_rate=sample_rate, name='noise',
+                                     seed=seed)
+    dag = polyphonic_dag(additive=additive, noise=noise, reverb=Reverb(trainable=False),
+                         additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+                         noise_controls=['magnitudes'], reverb_controls=['reverb_ir'], n_synths=n_synths)
+    return PianoModel(
+        z_encoder=None,
+        note_release=NoteRelease(float(raw('note_release/layer/cell/release_duration')), frame_rate),
+        context_network=FiLMContextNetwork(
+            stack(f'{cn}/conditioning_head', 2), stack(f'{cn}/pedal_head', 2),
+            t(f'{cn}/piano_id_head/embeddings'), dense(f'{cn}/main_model/{lw}0', leaky_relu),
+            gru(f'{cn}/main_model/{lw}1'), dense(f'{cn}/main_model/{lw}2'), ln(f'{cn}/main_model/{lw}3'),
+            dense(f'{cn}/film_input_reshape'), stack(f'{cn}/output_layer', 2)),
+        parallelizer=Parallelizer(n_synths, global_keys=('conditioning', 'context', 'piano_model')),
+        monophonic_network=MonophonicDeepNetwork(
+            [stack(f'{mn}/input_stacks/{i}', 3) for i in range(3)], gru(f'{mn}/model/{lw}0/rnn'),
+            stack(f'{mn}/out_stack', 3), dense(f'{mn}/dense_out'), splits),
+        inharm_model=JointParametricInharmTuning(
+            **{k: t(f'inharm_model/{k}/embeddings') for k in
+               ('alpha_b', 'beta_b', 'alpha_t', 'beta_t', 'pitch_ref', 'K', 'alpha')}),
+        detuner=None,
+        reverb_model=MultiInstrumentFeedbackDelayReverb(
+            {k: t(f'reverb_model/{k}/embeddings') for k in
+             ('_input_gain', '_output_gain', '_gain_allpass', '_delays_allpass', '_time_rev_0_sec',
+              '_alpha_tone', '_early_ir')}, sample_rate=sample_rate),
+        processor_group=ProcessorGroup(dag=dag), device=device)

@@ -189,3 +189,120 @@ def load_weights(ckpt, n_harmonics=96, n_magnitudes=64):
                 ('model_specific_weight', 'slopes', 'offsets', 'slopes_modifier', 'offsets_modifier')},
         release_duration=float(t('note_release/layer/cell/release_duration')),
         n_harmonics=n_harmonics, n_magnitudes=n_magnitudes)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs/maestro-v2.gin (the script default, synthesize_midi_file.py:14-17): FiLM context network,
+# deep monophonic network, joint parametric inharmonicity/tuning.  Additional third-party layers,
+# restated and unpinned like the ones above:
+# * ``ddsp.training.nn.FcStack(ch, layers)``: ``layers`` x [Dense(ch), LayerNormalization(),
+#   leaky_relu] (checkpoint: kernel/bias + gamma/beta per layer).
+# * ``tf.keras.layers.LayerNormalization``: moments over the last axis, epsilon 1e-3, gamma/beta.
+# * ``nn.Rnn(ch, 'gru')`` = GRU(ch, return_sequences=True); ``nn.get_embedding`` = Embedding.
+# ------------------------------------------------------------------------------------------------
+
+def layer_norm(x, gamma, beta, eps=1e-3):
+    x64 = x.astype(np.float64)
+    mean = x64.mean(axis=-1, keepdims=True)
+    var = x64.var(axis=-1, keepdims=True)
+    return (((x64 - mean) / np.sqrt(var + eps)).astype(F32) * gamma.astype(F32) + beta.astype(F32)).astype(F32)
+
+
+def fc_stack(x, layers):
+    for kernel, bias, gamma, beta in layers:
+        x = leaky_relu(layer_norm(dense(x, kernel, bias), gamma, beta))
+    return x
+
+
+def joint_inharm_tuning(extended_pitch, piano_model, w):
+    """JointParametricInharmTuning.call, sub_modules.py:833-876.  extended_pitch [R, T, 1],
+    piano_model [R] -> f0_hz [R, T, 1], inharm_coef [R, T, 1]."""
+    e = lambda name: w[name][piano_model][:, None, :].astype(F32)             # [R, 1, 1]
+    pitch = extended_pitch.astype(F32)
+
+    def inharm(p):                                                            # :833-837
+        return (np.exp(e('alpha_b') * p + e('beta_b')) + np.exp(e('alpha_t') * p + e('beta_t'))).astype(F32)
+
+    ref_pitch = e('pitch_ref')
+    ratio = (midi_to_hz(pitch) / midi_to_hz(ref_pitch)).astype(F32)           # :842
+    rst = ((F32(1) - np.tanh((pitch - ref_pitch) / e('alpha'))) / F32(2)).astype(F32)   # :830-831
+    rho = (F32(1) + e('K') * rst).astype(F32)                                 # :845-847
+    det = (F32(1) + inharm(ref_pitch) * (ratio * rho) ** 2).astype(F32)       # :849
+    det = (det / (F32(1) + inharm(pitch) * rho ** 2)).astype(F32)             # :850
+    det = np.sqrt(det).astype(F32)
+    return (midi_to_hz(pitch) * det).astype(F32), inharm(pitch)
+
+
+def control_graph_v2(conditioning, pedal, piano_model, w, frame_rate=250):
+    """maestro-v2: conditioning [B, T, P, 2], pedal [B, T, 4], piano_model [B] -> stacked controls
+    (f0_hz has ONE string: [P, B, T, 1])."""
+    conditioning = conditioning.astype(F32)
+    pedal = pedal.astype(F32)
+    B, T, P, _ = conditioning.shape
+    pm = np.asarray(piano_model).reshape(B).astype(np.int64)
+    scale = np.array([MIDI_NORM, 1.0], F32)
+    # FiLMContextNetwork.call, sub_modules.py:153-180
+    cond_feat = fc_stack((conditioning / scale).reshape(B, T, 2 * P), w['ctx_conditioning_head'])
+    pedal_feat = fc_stack(pedal, w['ctx_pedal_head'])
+    piano_feat = w['ctx_piano_id'][pm][:, None, :].astype(F32)                # [B, 1, 32]
+    x = np.concatenate([cond_feat, pedal_feat], axis=-1)
+    x = dense(x, *w['ctx_main_dense0'], activation=leaky_relu)
+    x = gru(x, *w['ctx_main_gru'])
+    x = leaky_relu(layer_norm(dense(x, *w['ctx_main_dense2']), *w['ctx_main_ln']))
+    film = dense(piano_feat, *w['ctx_film'])                                  # :140-151
+    half = film.shape[-1] // 2
+    x = (x * film[..., :half] + film[..., half:]).astype(F32)
+    context = fc_stack(x, w['ctx_output'])
+    # Parallelizer, global_keys = (conditioning, context, piano_model)  (maestro-v2.gin:36-38)
+    cond_p = conditioning.transpose(2, 0, 1, 3).reshape(P * B, T, 2)
+    context_p = np.repeat(context[None], P, axis=0).reshape(P * B, T, -1)
+    pm_p = np.tile(pm, P)
+    ext = note_release(cond_p[..., 0:1], w['release_duration'], frame_rate)
+    f0, inharm = joint_inharm_tuning(ext, pm_p, w['tuning'])
+    # MonophonicDeepNetwork.compute_output, sub_modules.py:510-525
+    a = fc_stack(ext / MIDI_NORM, w['mono_in0'])
+    b = fc_stack(cond_p / scale, w['mono_in1'])
+    c = fc_stack(context_p, w['mono_in2'])
+    x = np.concatenate([a, b, c], axis=-1)
+    x = gru(x, *w['mono_gru'])
+    x = np.concatenate([a, b, c, x], axis=-1)
+    y = dense(fc_stack(x, w['mono_out_stack']), *w['mono_out'])
+    H, M = w['n_harmonics'], w['n_magnitudes']
+    un = lambda t_: t_.reshape(P, B, T, t_.shape[-1])
+    return dict(amplitudes=un(y[..., 0:1]), harmonic_distribution=un(y[..., 1:1 + H]),
+                magnitudes=un(y[..., 1 + H:1 + H + M]), f0_hz=un(f0), inharm_coef=un(inharm),
+                extended_pitch=un(ext), context=context)
+
+
+def load_weights_v2(ckpt, n_harmonics=128, n_magnitudes=96):
+    t = lambda name: ckpt.tensor(f'model/{name}/.ATTRIBUTES/VARIABLE_VALUE')
+    pair = lambda prefix, a='kernel', b='bias': (t(f'{prefix}/{a}'), t(f'{prefix}/{b}'))
+
+    def stack(prefix, n):
+        return [(t(f'{prefix}/layer_with_weights-{i}/layer_with_weights-0/kernel'),
+                 t(f'{prefix}/layer_with_weights-{i}/layer_with_weights-0/bias'),
+                 t(f'{prefix}/layer_with_weights-{i}/layer_with_weights-1/gamma'),
+                 t(f'{prefix}/layer_with_weights-{i}/layer_with_weights-1/beta')) for i in range(n)]
+
+    gru_w = lambda prefix: (t(f'{prefix}/cell/kernel'), t(f'{prefix}/cell/recurrent_kernel'),
+                            t(f'{prefix}/cell/bias'))
+    cn, mn = 'context_network', 'monophonic_network'
+    return dict(
+        ctx_conditioning_head=stack(f'{cn}/conditioning_head', 2),
+        ctx_pedal_head=stack(f'{cn}/pedal_head', 2),
+        ctx_piano_id=t(f'{cn}/piano_id_head/embeddings'),
+        ctx_main_dense0=pair(f'{cn}/main_model/layer_with_weights-0'),
+        ctx_main_gru=gru_w(f'{cn}/main_model/layer_with_weights-1'),
+        ctx_main_dense2=pair(f'{cn}/main_model/layer_with_weights-2'),
+        ctx_main_ln=pair(f'{cn}/main_model/layer_with_weights-3', 'gamma', 'beta'),
+        ctx_film=pair(f'{cn}/film_input_reshape'),
+        ctx_output=stack(f'{cn}/output_layer', 2),
+        mono_in0=stack(f'{mn}/input_stacks/0', 3), mono_in1=stack(f'{mn}/input_stacks/1', 3),
+        mono_in2=stack(f'{mn}/input_stacks/2', 3),
+        mono_gru=gru_w(f'{mn}/model/layer_with_weights-0/rnn'),
+        mono_out_stack=stack(f'{mn}/out_stack', 3),
+        mono_out=pair(f'{mn}/dense_out'),
+        tuning={k: t(f'inharm_model/{k}/embeddings') for k in
+                ('alpha_b', 'beta_b', 'alpha_t', 'beta_t', 'pitch_ref', 'K', 'alpha')},
+        release_duration=float(t('note_release/layer/cell/release_duration')),
+        n_harmonics=n_harmonics, n_magnitudes=n_magnitudes)

@@ -1,6 +1,6 @@
 """Control-rate graph of dafx22.gin: ddsp_piano_b200/model.py against the numpy
 restatement oracle/piano_model_np.py on the shipped weights (tests/golden/dafx22_weights.npz,
-exported by tests/golden/make_dafx22_weights.py).  The Keras/ddsp layer semantics underneath both
+exported by tests/golden/make_model_weights.py).  The Keras/ddsp layer semantics underneath both
 are restated, not pinned (see the oracle's header)."""
 import os
 
@@ -170,3 +170,98 @@ def test_dafx22_midi_to_audio(weights):
     spec = np.abs(np.fft.rfft(during[2048:2048 + n] * np.hanning(n), 4 * n))
     peak_hz = np.argmax(spec) * sr / (4 * n)
     assert abs(peak_hz - 440.0) < 3.0, peak_hz
+
+
+# ---- maestro-v2.gin (the script default) --------------------------------------------------------
+
+V2_WEIGHTS = os.path.join(HERE, 'golden', 'v2_weights.npz')
+
+
+@pytest.fixture(scope='module')
+def v2_weights():
+    from ddsp_piano_b200.checkpoint import NpzWeights
+    return NpzWeights(V2_WEIGHTS)
+
+
+def test_joint_tuning_known_answers(v2_weights):
+    """Rigaud's model: no detuning at the reference pitch, octaves stretched away from it."""
+    w = ref.load_weights_v2(v2_weights)['tuning']
+    pm = np.array([5])                                  # pitch_ref = 64.0, K = 4.51, alpha = 24 (maestro-v2.gin)
+    pitch = np.array([[[64.0], [40.0], [88.0]]], np.float32)
+    f0, inharm = ref.joint_inharm_tuning(pitch, pm, w)
+    et = 440.0 * 2.0 ** ((pitch[0, :, 0] - 69.0) / 12.0)
+    assert abs(f0[0, 0, 0] / et[0] - 1.0) < 1e-6        # at pitch_ref: ratio = 1, detuning = 1
+    assert f0[0, 1, 0] < et[1] and f0[0, 2, 0] > et[2]  # Railsback curve: flat bass, sharp treble
+    assert np.all(inharm > 0) and inharm[0, 2, 0] > inharm[0, 0, 0] > inharm[0, 1, 0]   # treble bridge dominates
+
+
+def test_v2_controls_on_cpu_match_the_oracle(v2_weights, monkeypatch):
+    from ddsp_piano_b200 import model as M
+    cond, pedal, pm = midi_clip(B=2, T=200, seed=5)
+    want = ref.control_graph_v2(cond, pedal, pm, ref.load_weights_v2(v2_weights))
+
+    class CpuRelease:
+        def __init__(self, dur, fr):
+            self.dur, self.fr = dur, fr
+
+        def __call__(self, conditioning):
+            return torch.from_numpy(ref.note_release(conditioning[..., 0:1].numpy(), self.dur, self.fr))
+
+    class NoReverb:
+        def __init__(self, *a, **kw):
+            pass
+
+        def __call__(self, pm_):
+            return torch.zeros(pm_.shape[0], 8)
+
+    monkeypatch.setattr(M, 'NoteRelease', CpuRelease)
+    monkeypatch.setattr(M, 'MultiInstrumentFeedbackDelayReverb', NoReverb)
+    model = M.maestro_v2_model(v2_weights, device='cpu')
+    got = model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': pm})
+    for key in ('f0_hz', 'inharm_coef', 'amplitudes', 'harmonic_distribution', 'magnitudes'):
+        g, r_ = got[key].numpy(), want[key]
+        assert g.shape == r_.shape, (key, g.shape, r_.shape)
+        err = np.max(np.abs(g - r_)) / np.max(np.abs(r_))
+        assert err < 1e-4, (key, err)
+    assert got['f0_hz'].shape[-1] == 1 and got['harmonic_distribution'].shape[-1] == 128
+
+
+@pytest.mark.gpu
+def test_v2_controls_match_the_oracle_on_gpu(v2_weights):
+    import ddsp_piano_b200 as dp
+    cond, pedal, pm = midi_clip(B=2, T=200, seed=5)
+    want = ref.control_graph_v2(cond, pedal, pm, ref.load_weights_v2(v2_weights))
+    model = dp.maestro_v2_model(v2_weights, device='cuda:0')
+    got = model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': pm})
+    for key in ('f0_hz', 'inharm_coef', 'amplitudes', 'harmonic_distribution', 'magnitudes'):
+        g, r_ = got[key].cpu().numpy(), want[key]
+        err = np.max(np.abs(g - r_)) / np.max(np.abs(r_))
+        assert err < 1e-4, (key, err)
+    assert got['reverb_ir'].shape == (2, 48000)
+
+
+@pytest.mark.gpu
+def test_v2_midi_to_audio(v2_weights):
+    """The reference's default model (maestro-v2.gin, 24 kHz, one string per note, FDN reverb) from
+    MIDI conditioning to audio: a sustained A4 peaks at its (slightly stretched) 440 Hz."""
+    import ddsp_piano_b200 as dp
+    B, T, P, sr = 1, 750, 16, 24000
+    cond = np.zeros([B, T, P, 2], np.float32)
+    cond[0, 250:500, 0, 0] = 69
+    cond[0, 250, 0, 1] = 0.8
+    model = dp.maestro_v2_model(v2_weights, device='cuda:0')
+    out = model({'conditioning': cond, 'pedal': np.zeros([B, T, 4], np.float32),
+                 'piano_model': np.zeros([B, 1], np.int64)})
+    audio = model.get_audio_from_outputs(out).cpu().numpy()
+    U = sr // 250
+    assert audio.shape == (B, T * U) and np.all(np.isfinite(audio))
+    dry = out['add']['signal'].cpu().numpy()[0]
+    before, during, after = dry[100 * U:240 * U], dry[260 * U:500 * U], dry[700 * U:]
+    rms = lambda x: float(np.sqrt(np.mean(x.astype(np.float64) ** 2)))
+    assert rms(during) > 5 * rms(before) and rms(during) > 5 * rms(after)
+    n = 16384
+    spec = np.abs(np.fft.rfft(during[2048:2048 + n] * np.hanning(n), 4 * n))
+    peak_hz = np.argmax(spec) * sr / (4 * n)
+    assert abs(peak_hz - 440.0) < 4.0, peak_hz
+    wet_tail = audio[0, 700 * U:]
+    assert rms(wet_tail) > rms(after)                   # the reverb rings on after the dry decay
