@@ -127,6 +127,35 @@ def test_additive_vs_oracle(dp, dev, sr, F, B, H, S):
     assert rel_err(out['signal'], want) < TIGHT
 
 
+@pytest.mark.parametrize('H,inference,held', [(128, True, False), (128, True, True), (120, True, False),
+                                             (72, False, False), (40, True, False), (8, True, True)])
+def test_additive_every_half_group_bucket(dp, dev, H, inference, held):
+    """The half-warp layout runs nh = 1..8 chains per lane (16-partial half-groups, packed in pairs,
+    an odd last chain packed over time): one clip per bucket, fundamentals chosen so that exactly
+    5, 17, 33, ... partials lie below Nyquist, with (held) and without steady frames."""
+    sr, F, S = 24000, 45, 2
+    live = [k for k in (5, 17, 33, 49, 65, 81, 97, 113) if k <= H] + [H]
+    B = len(live)
+    rng = np.random.default_rng(H + 7 * inference + held)
+    x = voice_inputs(rng, B, F, H, S, 8, onsets=False)
+    for b, k in enumerate(live):
+        f0 = 12000.0 / ((k + 0.5) * np.sqrt(1.0 + 1e-4 * (k + 0.5) ** 2))
+        x['f0_hz'][b] = (f0 * (1.0 + 1e-3 * np.arange(S))).astype(np.float32)
+    x['inharm_coef'][:] = 1e-4 if held else rng.uniform(0.9e-4, 1.1e-4, x['inharm_coef'].shape)
+    x['f0_hz'][0, 30:] = 8.1758                       # a note-off: silent frames, then a silent chunk
+    ctl = ref.additive_controls(x['amplitudes'], x['harmonic_distribution'], x['inharm_coef'],
+                                x['f0_hz'], sample_rate=sr)
+    n_live = (ctl['harmonic_distribution'][:, 0] != 0).sum(-1)
+    assert len(set(-(-n_live // 16))) >= min(B, (H + 15) // 16) - 1      # the buckets really differ
+    want = ref.additive_signal(**ctl, sample_rate=sr, inference=inference)
+    synth = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=inference, name='additive')
+    got = synth(cu(x['amplitudes'], dev), cu(x['harmonic_distribution'], dev),
+                cu(x['inharm_coef'], dev), cu(x['f0_hz'], dev))
+    assert rel_err(got, want) < TIGHT
+    for b in range(B):                                 # per clip: small buckets are not drowned out
+        assert rel_err(got[b], want[b]) < 5 * TIGHT, (b, live[b])
+
+
 def test_additive_known_answers(dp, dev):
     """SURVEY 8c KATs 2-4, 6 on the CUDA path."""
     sr, F, H = 24000, 30, 8
