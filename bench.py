@@ -370,34 +370,34 @@ def run_gpu(args, w):
         # issue-slot view of the same kernel: counted FP32 instructions per oscillator-sample
         osc_samples = B * P * S * H * N
         # dram__bytes_read+write of the six bucket launches of one step, from the ncu --set full
-        # capture of this same command (profiles/r01_prof9_summary.txt); config 3 at N=1 only
-        traffic = 102.3e6 if (args.workload == 'full' and world == 1) else None
+        # capture of this same command (profiles/r01_prof10_summary.txt); config 3 at N=1 only
+        traffic = 101.7e6 if (args.workload == 'full' and world == 1) else None
         sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
         roofline = {
             'bound': 'hbm',
             'kernel': 'additive_synth_kernel<NH,2> x 6 buckets, concurrent (the oscillator bank)',
             'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': (achieved / hbm_peak) if achieved else None, 'traffic': traffic,
-            'traffic_source': 'profiles/r01_prof9_summary.txt (sum over the 6 bucket launches; below '
+            'traffic_source': 'profiles/r01_prof10_summary.txt (sum over the 6 bucket launches; below '
                               'the algorithmic bytes because silent partial groups are never read)',
             'peak_source': f'{peaks_src} (MEASURED_PEAKS.json hbm_gbs)' if peaks_src == 'measured'
             else 'fallback 6650 GB/s (B200_PROFILING.md)',
             'algorithmic_bytes_per_launch': ab['oscillators'], 'kernel_ms': osc_ms,
             'kernel_share_of_step': osc_ms / ms_per_step if ms_per_step else None,
             'note': 'the oscillator bank is bound by the FP32 (FMA) pipe, not by HBM (SURVEY.md fact 5): '
-                    'the bit-faithful phase chain needs 13 FMA-pipe cycles per oscillator-sample; see '
+                    'the bit-faithful phase chain needs 11.5 FMA-pipe cycles per oscillator-sample (+6 in the phase pass); see '
                     'fma_pipe, oscillator_samples_per_s and DESIGN.md section 4',
             'oscillator_samples_per_s': osc_samples / (osc_ms * 1e-3) if osc_ms > 0 else None,
             # what actually bounds the stage.  Static facts from the ncu capture of this command
-            # (profiles/r01_prof9_summary.txt, config 3): warp instructions of the six bucket
+            # (profiles/r01_prof10_summary.txt, config 3): warp instructions of the six bucket
             # launches and the FMA-pipe activity of the two dominant kernels; live: the share of
             # the issue slots of the measured time those instructions fill
-            'fma_pipe': ({'ncu_pipe_fma_cycles_active_pct': {'additive_synth_kernel<6,2> (largest bucket)': 65.4,
-                                                             'additive_fast_kernel<2,ends> (phase pass)': 76.9},
-                          'warp_instructions_per_launch_set': 8.943e8,
+            'fma_pipe': ({'ncu_pipe_fma_cycles_active_pct': {'additive_synth_kernel<6,2> (largest bucket)': 61.0,
+                                                             'additive_fast_kernel<2,ends> (phase pass)': 77.0},
+                          'warp_instructions_per_launch_set': 8.560e8,
                           'issue_slots_per_s': 148 * 4 * sm_hz,
-                          'issue_frac': 8.943e8 / (osc_ms * 1e-3) / (148 * 4 * sm_hz),
-                          'source': 'profiles/r01_prof9_summary.txt'}
+                          'issue_frac': 8.560e8 / (osc_ms * 1e-3) / (148 * 4 * sm_hz),
+                          'source': 'profiles/r01_prof10_summary.txt'}
                          if (args.workload == 'full' and world == 1 and osc_ms > 0) else None),
             'whole_step_GBps': ab['forward'] / (ms_per_step * 1e-3) / 1e9,
             'stage_ms': {k: v / args.steps for k, v in stages.items()},
