@@ -1,25 +1,28 @@
 // Fast path of the additive oscillator bank (same maths and rounding as additive.cuh, which
 // stays as the generic path): used when U % 8 == 0, floor(float(t) * scale) == t / U for
-// every sample, and the 3-op division is exact for the sample rate (all checked on the host).
+// every sample, and the two-word-reciprocal division is exact for the sample rate (all checked
+// on the host).
 //
 // What it adds over the generic kernel -- none of it changes a single output bit of the phase:
-//  * a warp owns a VOICE: lane l carries partials l, l+32, ... for SP substrings at once
-//    (NA x SP phase chains per lane), so the amplitude envelope is evaluated once per partial
-//    and shared by the substrings;
-//  * dead partial groups are not synthesised: get_controls zeroes every partial above Nyquist
-//    and mutes voices below min_frequency, so groups of 32 partials whose amplitude is zero in
-//    every frame touching a chunk are dropped for that chunk (NA = number of live groups,
-//    found by additive_alive_kernel), and the phase-only pass skips a group once no later
-//    chunk needs its offset;
+//  * a warp owns one (voice, clip, 1000-sample chunk).  S even: the two substrings of a pair ride
+//    on the two half-warps and chain j of a lane is partial 16 j + (lane & 15); S odd: one
+//    substring on the whole warp, chain j = partial 32 j + lane.  Chains are processed two at a
+//    time in packed float32x2 registers (FFMA2 / FADD2 / FMUL2), an odd last chain is packed over
+//    pairs of consecutive samples;
+//  * dead partials are not synthesised: get_controls zeroes every partial above Nyquist and mutes
+//    voices below min_frequency, so 16-partial half-groups whose amplitude is zero in every frame
+//    touching a chunk are dropped for that chunk (nh = number of live half-groups, from the
+//    controls kernel / additive_alive_frames_kernel), and the phase-only pass skips a half-group
+//    once no later chunk needs its offset;
 //  * per control frame the warp picks the cheapest exact variant:
 //      steady   both frame endpoints have identical partial frequencies (a held note):
 //               omega is constant over the frame -> 1 FADD per sample in the phase chain
-//      general  legacy-bilinear lerp per sample (7 FP32 ops in the chain)
+//      general  legacy-bilinear lerp per sample (6 FMA-pipe cycles in the chain)
 //    crossed with
 //      silent   every amplitude of the frame pair is zero: phase chain only
 //      nocheck  no sounding partial can reach Nyquist inside the frame: the per-sample mask of
 //               cos_oscillator_bank (inharm_synth.py:65-67) is elided
-//      check    with the mask (per frame in steady frames, per sample otherwise)
+//      check    with the mask
 //  * the unrolled body is 4 samples (not 32) so that the variants a SM executes concurrently
 //    stay inside the 32 KB instruction cache (the first version of this kernel spent its top
 //    stall reason on instruction fetch).
@@ -108,148 +111,15 @@ __global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
   }
 }
 
-// ---- per-lane oscillator state ---------------------------------------------------------------
-template <int NA, int SP>
-struct OscState {
-  float ph[NA][SP];    // in-chunk float32 phase accumulator
-  float F[NA][SP];     // partial frequency of frame k
-  float Fn[NA][SP];    // ... of frame k+1
-  float dF[NA][SP];    // Fn - F (rounded once, like the resize kernel's bottom - top)
-  float om[NA][SP];    // steady frames: the constant omega
-  float off[NA][SP];   // chunk offset (synth pass)
-  float A[NA], An[NA]; // partial amplitudes of frames k, k+1
-  float dA[NA];        // An - A: the Hann cross-fade is evaluated as A + dA * w[r]
-};
-
-template <int NA, int SP, bool WITH_AMP>
-__device__ __forceinline__ void load_next_frame(const AdditiveArgs& a, int row, int s0, int kn,
-                                                int lane, OscState<NA, SP>& st) {
-  const size_t base = ((size_t)row * a.F + kn) * a.H;
-  const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + kn) : 0.f;
-  float f0[SP];
-#pragma unroll
-  for (int s = 0; s < SP; ++s) f0[s] = __ldg(a.f0 + ((size_t)row * a.F + kn) * a.S + s0 + s);
-#pragma unroll
-  for (int q = 0; q < NA; ++q) {
-    const int h = lane + 32 * q;
-    float sh = 0.f, hdv = 0.f;
-    if (h < a.H) {
-      sh = __ldg(a.shifts + base + h);
-      if (WITH_AMP) hdv = __ldg(a.hd + base + h);
-    }
-    const float n = (float)(h + 1);
-    const float stretch = __fadd_rn(1.0f, sh);
-#pragma unroll
-    for (int s = 0; s < SP; ++s)
-      st.Fn[q][s] = (h < a.H) ? __fmul_rn(__fmul_rn(f0[s], n), stretch) : 0.f;   // :106-108
-    st.An[q] = __fmul_rn(amp, hdv);                                               // :111-114
-  }
-}
-
 enum { kAmpSilent = 0, kAmpNoCheck = 1, kAmpCheck = 2 };
 constexpr int kOscUnroll = 4;   // samples per unrolled body of the synthesis pass
 
-// Shift frame k+1 into frame k, load the new k+1, derive the frame's variant.
-template <int NA, int SP, bool WITH_AMP>
-__device__ __forceinline__ void advance_frame(const AdditiveArgs& a, int row, int s0, int kn, int lane,
-                                              OscState<NA, SP>& st, bool& steady, int& amp_mode) {
-#pragma unroll
-  for (int q = 0; q < NA; ++q) {
-    st.A[q] = st.An[q];
-#pragma unroll
-    for (int s = 0; s < SP; ++s) st.F[q][s] = st.Fn[q][s];
-  }
-  load_next_frame<NA, SP, WITH_AMP>(a, row, s0, kn, lane, st);
-#pragma unroll
-  for (int q = 0; q < NA; ++q) st.dA[q] = st.An[q] - st.A[q];
-  bool all_steady = true, any_live = false, any_risky = false;
-  // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
-  // bottom - top, one in the product, one in the sum), hence the margin
-  const float nyq_lo = a.nyquist * (1.0f - 1e-6f);
-#pragma unroll
-  for (int q = 0; q < NA; ++q) {
-    const bool live = WITH_AMP && (st.A[q] != 0.f || st.An[q] != 0.f);
-    any_live |= live;
-#pragma unroll
-    for (int s = 0; s < SP; ++s) {
-      st.dF[q][s] = __fadd_rn(st.Fn[q][s], -st.F[q][s]);
-      all_steady &= (st.dF[q][s] == 0.f);
-      // omega of a steady frame: f = F + 0 * lerp = F
-      st.om[q][s] = div_sr<true>(__fmul_rn(st.F[q][s], kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);
-      any_risky |= live && (fmaxf(st.F[q][s], st.Fn[q][s]) >= nyq_lo);
-    }
-  }
-  steady = __all_sync(0xffffffffu, all_steady);
-  amp_mode = kAmpSilent;
-  if (WITH_AMP && __any_sync(0xffffffffu, any_live))
-    amp_mode = __any_sync(0xffffffffu, any_risky) ? kAmpCheck : kAmpNoCheck;
-}
-
-// kOscUnroll consecutive samples (inside one control frame) of every chain of the lane.
-// win = shared Hann table positioned at the first sample's offset r inside the frame.
 // cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
 // reduce modulo the true 2 pi in double precision, then the hardware cosine.
 __device__ __forceinline__ float cos_large(float x) {
   const double xd = (double)x;
   const double n = rint(xd * 0.15915494309189535);
   return __cosf((float)fma(-n, 6.283185307179586, xd));
-}
-
-template <int NA, int SP, bool STEADY, int AMP, int UNROLL, bool PLAIN = false>
-__device__ __forceinline__ void osc_group(const AdditiveArgs& a, OscState<NA, SP>& st,
-                                          const float* win, const float (&fr)[UNROLL],
-                                          float (&y)[kOscUnroll]) {
-  static_assert(AMP == kAmpSilent || UNROLL == 4, "window loads are float4");
-  float wr[4] = {0.f, 0.f, 0.f, 0.f};
-  if (AMP != kAmpSilent) {   // r is a multiple of 4: the load is 16-byte aligned
-    const float4 r4 = *reinterpret_cast<const float4*>(win);
-    wr[0] = r4.x; wr[1] = r4.y; wr[2] = r4.z; wr[3] = r4.w;
-  }
-  // steady frames: f = F for the whole frame, so the Nyquist mask is a per-frame predicate
-  bool cut[NA][SP];
-  if (STEADY && AMP == kAmpCheck) {
-#pragma unroll
-    for (int q = 0; q < NA; ++q)
-#pragma unroll
-      for (int s = 0; s < SP; ++s) cut[q][s] = st.F[q][s] >= a.nyquist;
-  }
-#pragma unroll
-  for (int j = 0; j < UNROLL; ++j) {
-    const float frac = STEADY ? 0.f : fr[j];   // legacy ResizeBilinear lerp = in - floor(in)
-    const float w0 = wr[j & 3];                // rising half of hann(2U): weight of frame k+1
-#pragma unroll
-    for (int q = 0; q < NA; ++q) {
-      // Hann cross-fade of the frame amplitudes A w[r+U] + An w[r], with w[r+U] = 1 - w[r];
-      // shared by the substrings
-      float amp_q = 0.f;
-      if (AMP != kAmpSilent) amp_q = __fmaf_rn(st.dA[q], w0, st.A[q]);
-#pragma unroll
-      for (int s = 0; s < SP; ++s) {
-        float om, f = 0.f;
-        if (STEADY) {
-          om = st.om[q][s];
-        } else {
-          f = __fadd_rn(st.F[q][s], __fmul_rn(st.dF[q][s], frac));             // top + (bottom-top)*lerp
-          om = div_sr<true>(__fmul_rn(f, kTwoPi), a.sr, a.inv_sr, a.inv_sr_lo);            // :69-70
-        }
-        st.ph[q][s] = __fadd_rn(st.ph[q][s], om);                              // cumsum
-        if (AMP != kAmpSilent) {
-          float amp = amp_q;
-          if (AMP == kAmpCheck) {
-            const bool above = STEADY ? cut[q][s] : (f >= a.nyquist);          // :65-67
-            amp = above ? 0.f : amp_q;
-          }
-          float c;
-          if (PLAIN) {
-            c = cos_large(st.ph[q][s]);                                        // tf.cos(tf.cumsum)
-          } else {
-            c = __cosf(wrap_to_pi(__fadd_rn(st.ph[q][s], st.off[q][s])));
-          }
-          y[j & 3] = __fmaf_rn(amp, c, y[j & 3]);                              // :80-83
-        }
-      }
-    }
-  }
 }
 
 // 32 lanes x 4 values -> every lane returns the sum over lanes of y[lane & 3].
@@ -271,86 +141,10 @@ __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
   return v;
 }
 
-// One (row, substring set, chunk) on one warp.  ENDS_ONLY: phase chain only, writes the chunk
-// end phases; otherwise writes the audio of the chunk to `row_out` (global memory).
-template <int NA, int SP, bool ENDS_ONLY, bool PLAIN>
-__device__ __forceinline__ void osc_chunk(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
-                                          int c, int lane, const float* win, float* row_out) {
-  const int t0 = c * a.chunk;
-  const int t1 = min(a.N, t0 + a.chunk);
-  OscState<NA, SP> st;
-  int k = t0 / a.U;
-  int r = t0 - k * a.U;
-  bool steady;
-  int amp_mode;
-  // prime: frame k lands in Fn/An, then advance shifts it down and loads k+1
-  load_next_frame<NA, SP, !ENDS_ONLY>(a, row, s0, k, lane, st);
-  advance_frame<NA, SP, !ENDS_ONLY>(a, row, s0, min(k + 1, a.F - 1), lane, st, steady, amp_mode);
-#pragma unroll
-  for (int q = 0; q < NA; ++q)
-#pragma unroll
-    for (int s = 0; s < SP; ++s) {
-      st.ph[q][s] = 0.f;
-      st.off[q][s] = 0.f;
-      const int h = lane + 32 * q;
-      if (!ENDS_ONLY && c > 0 && h < a.H)
-        st.off[q][s] = a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h];
-    }
-  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
-  // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel),
-  // fetched one group ahead: the first consumer is the first instruction of the phase chain
-  for (int t = t0; t < t1; t += STEP, r += STEP) {
-    if (r == a.U) {
-      r = 0;
-      ++k;
-      advance_frame<NA, SP, !ENDS_ONLY>(a, row, s0, min(k + 1, a.F - 1), lane, st, steady, amp_mode);
-    }
-    // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
-    // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
-    // and does not pay: the other resident warps already cover the L1 latency.
-    float fr[STEP];
-#pragma unroll
-    for (int j4 = 0; j4 < STEP / 4; ++j4) {
-      float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!steady) l4 = __ldg(reinterpret_cast<const float4*>(fa_lerp + t) + j4);
-      fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
-    }
-    float y[kOscUnroll];
-#pragma unroll
-    for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
-    const float* w = win + r;
-    if (ENDS_ONLY || amp_mode == kAmpSilent) {
-      if (steady) osc_group<NA, SP, true, kAmpSilent, STEP>(a, st, w, fr, y);
-      else osc_group<NA, SP, false, kAmpSilent, STEP>(a, st, w, fr, y);
-      if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
-    } else if constexpr (!ENDS_ONLY) {
-      if (amp_mode == kAmpNoCheck) {
-        if (steady) osc_group<NA, SP, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-        else osc_group<NA, SP, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-      } else {
-        if (steady) osc_group<NA, SP, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-        else osc_group<NA, SP, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-      }
-      const float v = transpose_reduce4(y, lane);
-      if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
-    }
-  }
-  if (ENDS_ONLY) {
-#pragma unroll
-    for (int q = 0; q < NA; ++q)
-#pragma unroll
-      for (int s = 0; s < SP; ++s) {
-        const int h = lane + 32 * q;
-        if (h < a.H)
-          a.offsets[(((size_t)row * a.S + s0 + s) * a.n_chunks + c) * a.H + h] =
-              floormod_two_pi(st.ph[q][s]);
-      }
-  }
-}
-
-// ---- half-warp layout for substring pairs (S even) ---------------------------------------------
-// Lanes 0-15 carry substring s0, lanes 16-31 substring s0 + 1; chain j of a lane is partial
-// 16 j + (lane & 15).  A unit with nh live 16-partial half-groups therefore runs nh chains per
+// ---- lane layout and packed arithmetic ----------------------------------------------------------
+// LW = 16 (S even): lanes 0-15 carry substring s0, lanes 16-31 substring s0 + 1; chain j of a lane
+// is partial 16 j + (lane & 15).  LW = 32 (S odd): one substring, chain j = partial 32 j + lane.
+// With LW = 16,  A unit with nh live 16-partial half-groups therefore runs nh chains per
 // lane with no idle lanes beyond the last half-group (with 32-partial groups and the substrings
 // in the two halves of a register, 29 % of the lanes of the benchmark distribution computed
 // partials above Nyquist).  Chains are processed two at a time in packed float32x2 registers
@@ -374,7 +168,7 @@ struct OscStateH {
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-template <int NC, bool WITH_AMP>
+template <int NC, int LW, bool WITH_AMP>
 __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
                                              float (&F)[NC], float (&A)[NC]) {
   const size_t base = ((size_t)row * a.F + k) * a.H;
@@ -382,7 +176,7 @@ __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int
   const float f0 = __ldg(a.f0 + ((size_t)row * a.F + k) * a.S + s);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
-    const int h = l16 + 16 * j;
+    const int h = l16 + LW * j;
     float sh = 0.f, hdv = 0.f;
     if (h < a.H) {
       sh = __ldg(a.shifts + base + h);
@@ -395,12 +189,12 @@ __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int
 
 // Load frames k and min(k + 1, F - 1) and derive the frame's variant (both frames are re-read at
 // every frame boundary: one extra L1 hit per 96 samples buys 3 NC registers of carried state).
-template <int NC, bool WITH_AMP>
+template <int NC, int LW, bool WITH_AMP>
 __device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
                                               OscStateH<NC>& st, bool& steady, int& amp_mode) {
   float Fn[NC], An[NC];
-  load_frame_h<NC, WITH_AMP>(a, row, s, k, l16, st.F, st.A);
-  load_frame_h<NC, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l16, Fn, An);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, k, l16, st.F, st.A);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l16, Fn, An);
   bool all_steady = true, any_live = false, any_risky = false;
   // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
   // bottom - top, one in the product, one in the sum), hence the margin
@@ -547,23 +341,23 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
 
 // One (row, substring pair, chunk) on one warp, half-warp layout.  ENDS_ONLY: phase chain only,
 // writes the chunk end phases; otherwise writes the audio of the chunk to `row_out`.
-template <int NC, bool ENDS_ONLY, bool PLAIN>
+template <int NC, int LW, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
                                             int c, int lane, const float* win, float* row_out) {
   const int t0 = c * a.chunk;
   const int t1 = min(a.N, t0 + a.chunk);
-  const int l16 = lane & 15, s = s0 + (lane >> 4);
+  const int l16 = lane & (LW - 1), s = s0 + lane / LW;   // LW = 16: two substrings on the half-warps
   OscStateH<NC> st;
   int k = t0 / a.U;
   int r = t0 - k * a.U;
   bool steady;
   int amp_mode;
-  enter_frame_h<NC, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+  enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     st.ph[j] = 0.f;
     st.off[j] = 0.f;
-    const int h = l16 + 16 * j;
+    const int h = l16 + LW * j;
     if (!ENDS_ONLY && c > 0 && h < a.H)
       st.off[j] = a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h];
   }
@@ -572,7 +366,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     if (r == a.U) {
       r = 0;
       ++k;
-      enter_frame_h<NC, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+      enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
     }
     // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
     // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
@@ -607,40 +401,39 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
   if (ENDS_ONLY) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      const int h = l16 + 16 * j;
+      const int h = l16 + LW * j;
       if (h < a.H)
         a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h] = floormod_two_pi(st.ph[j]);
     }
   }
 }
 
-// nh = live 16-partial half-groups of the unit.  S even: half-warp layout, nh chains per lane;
-// S odd: one substring per pass, lanes own partials lane + 32 q, (nh + 1) / 2 groups of 32.
+// nh = live 16-partial half-groups of the unit.  S even: substring pairs on the half-warps, nh chains
+// per lane; S odd: one substring per pass on the whole warp, lanes own partials lane + 32 j,
+// (nh + 1) / 2 chains per lane.
 template <int SP, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int nh,
                                                    int row, int s0, int c, int lane, const float* win,
                                                    float* row_out) {
-  if constexpr (SP == 2) {
-    switch (nh) {
-      case 0: break;
-      case 1: osc_chunk_h<1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 2: osc_chunk_h<2, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 3: osc_chunk_h<3, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 4: osc_chunk_h<4, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 5: osc_chunk_h<5, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 6: osc_chunk_h<6, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 7: osc_chunk_h<7, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      default: osc_chunk_h<8, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    }
-  } else {
-    switch ((nh + 1) / 2) {
-      case 0: break;
-      case 1: osc_chunk<1, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 2: osc_chunk<2, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      case 3: osc_chunk<3, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      default: osc_chunk<4, 1, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-      // more than 128 live partials: the host routes H > 128 to the generic kernel
-    }
+  constexpr int LW = (SP == 2) ? 16 : 32;
+  switch ((SP == 2) ? nh : (nh + 1) / 2) {
+    case 0: break;
+    case 1: osc_chunk_h<1, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 2: osc_chunk_h<2, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 3: osc_chunk_h<3, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    case 4: osc_chunk_h<4, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+    default:
+      if constexpr (SP == 2) {
+        switch (nh) {
+          case 5: osc_chunk_h<5, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+          case 6: osc_chunk_h<6, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+          case 7: osc_chunk_h<7, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+          default: osc_chunk_h<8, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
+        }
+      }
+      // S odd: more than 128 live partials never reach here (the host routes H > 128 to the
+      // generic kernel)
+      break;
   }
 }
 
@@ -778,7 +571,7 @@ __host__ __device__ constexpr int synth_min_ctas(int chains) {
 }
 
 template <int NH, int SP, bool PLAIN>
-__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : 2 * ((NH + 1) / 2)) * 4 / kSynthWarps)
+__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : (NH + 1) / 2) * 4 / kSynthWarps)
 additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
@@ -798,8 +591,8 @@ additive_synth_kernel(const AdditiveFastArgs fa) {
   const int c = unit - row * a.n_chunks;
   const int v = row / a.B, b = row - v * a.B;
   float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-  if constexpr (SP == 2) osc_chunk_h<NH, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
-  else osc_chunk<(NH + 1) / 2, 1, false, PLAIN>(a, fa.lerp, row, set, c, lane, win, out);
+  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
+  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, lane, win, out);
 }
 
 }  // namespace b200ddsp
