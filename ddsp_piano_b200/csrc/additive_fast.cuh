@@ -411,30 +411,24 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
 // nh = live 16-partial half-groups of the unit.  S even: substring pairs on the half-warps, nh chains
 // per lane; S odd: one substring per pass on the whole warp, lanes own partials lane + 32 j,
 // (nh + 1) / 2 chains per lane.
-template <int SP, bool ENDS_ONLY, bool PLAIN>
+// CMAX = largest number of chains per lane that can occur (prunes the switch, and with it the
+// register budget of the kernel, to what the configured H needs).
+template <int SP, bool ENDS_ONLY, bool PLAIN, int CMAX = 8>
 __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int nh,
                                                    int row, int s0, int c, int lane, const float* win,
                                                    float* row_out) {
   constexpr int LW = (SP == 2) ? 16 : 32;
-  switch ((SP == 2) ? nh : (nh + 1) / 2) {
-    case 0: break;
-    case 1: osc_chunk_h<1, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 2: osc_chunk_h<2, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 3: osc_chunk_h<3, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    case 4: osc_chunk_h<4, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-    default:
-      if constexpr (SP == 2) {
-        switch (nh) {
-          case 5: osc_chunk_h<5, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-          case 6: osc_chunk_h<6, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-          case 7: osc_chunk_h<7, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-          default: osc_chunk_h<8, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out); break;
-        }
-      }
-      // S odd: more than 128 live partials never reach here (the host routes H > 128 to the
-      // generic kernel)
-      break;
+  const int chains = (SP == 2) ? nh : (nh + 1) / 2;
+#define B200DDSP_CHAIN_CASE(N)                                                                   \
+  if constexpr (CMAX >= N) {                                                                     \
+    if (chains == N || (N == CMAX && chains > N)) {                                              \
+      osc_chunk_h<N, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out);          \
+      return;                                                                                    \
+    }                                                                                            \
   }
+  B200DDSP_CHAIN_CASE(1) B200DDSP_CHAIN_CASE(2) B200DDSP_CHAIN_CASE(3) B200DDSP_CHAIN_CASE(4)
+  B200DDSP_CHAIN_CASE(5) B200DDSP_CHAIN_CASE(6) B200DDSP_CHAIN_CASE(7) B200DDSP_CHAIN_CASE(8)
+#undef B200DDSP_CHAIN_CASE
 }
 
 // ---- work lists ------------------------------------------------------------------------------
