@@ -144,17 +144,18 @@ __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
 // ---- lane layout and packed arithmetic ----------------------------------------------------------
 // LW = 16 (S even): lanes 0-15 carry substring s0, lanes 16-31 substring s0 + 1; chain j of a lane
 // is partial 16 j + (lane & 15).  LW = 32 (S odd): one substring, chain j = partial 32 j + lane.
-// With LW = 16,  A unit with nh live 16-partial half-groups therefore runs nh chains per
-// lane with no idle lanes beyond the last half-group (with 32-partial groups and the substrings
-// in the two halves of a register, 29 % of the lanes of the benchmark distribution computed
-// partials above Nyquist).  Chains are processed two at a time in packed float32x2 registers
-// (sm_100: FFMA2 / FADD2 / FMUL2): a packed operation takes ONE issue slot for two oscillators
-// (it still occupies the FMA pipe for two cycles), which frees issue slots for the MUFU, the
-// shuffles and the address arithmetic; an odd last chain is packed over pairs of consecutive samples.  Every packed
-// operation rounds each half exactly like its scalar form (.rn), so the phase stays bit-identical.
-// One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it honours .rn only on
-// the scalar forms), so the one product that must stay unfused -- (bottom - top) * lerp of the
-// legacy bilinear resize -- is computed with two scalar __fmul_rn.
+// A unit with nh live 16-partial half-groups therefore runs nh chains per lane (LW = 16) with no
+// idle lanes beyond the last half-group: with 32-partial groups and the substrings in the two
+// halves of a register, 29 % of the lanes of the benchmark's pitch distribution computed partials
+// above Nyquist; at 16-partial granularity it is 15 %.
+// Chains are processed two at a time in packed float32x2 registers (sm_100: FFMA2 / FADD2 /
+// FMUL2): a packed operation takes ONE issue slot for two oscillators (it still occupies the FMA
+// pipe for two cycles), which frees issue slots for the MUFU, the shuffles and the address
+// arithmetic; an odd last chain is packed over pairs of consecutive samples instead.  Every
+// packed operation rounds each half exactly like its scalar form (.rn), so the phase stays
+// bit-identical.  One trap: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it
+// honours .rn only on the scalar forms), so the one product that must stay unfused --
+// (bottom - top) * lerp of the legacy bilinear resize -- is computed with two scalar __fmul_rn.
 template <int NC>
 struct OscStateH {
   float ph[NC];    // in-chunk float32 phase accumulator
@@ -169,14 +170,14 @@ struct OscStateH {
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 template <int NC, int LW, bool WITH_AMP>
-__device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
+__device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int s, int k, int l,
                                              float (&F)[NC], float (&A)[NC]) {
   const size_t base = ((size_t)row * a.F + k) * a.H;
   const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + k) : 0.f;
   const float f0 = __ldg(a.f0 + ((size_t)row * a.F + k) * a.S + s);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
-    const int h = l16 + LW * j;
+    const int h = l + LW * j;
     float sh = 0.f, hdv = 0.f;
     if (h < a.H) {
       sh = __ldg(a.shifts + base + h);
@@ -190,11 +191,11 @@ __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int
 // Load frames k and min(k + 1, F - 1) and derive the frame's variant (both frames are re-read at
 // every frame boundary: one extra L1 hit per 96 samples buys 3 NC registers of carried state).
 template <int NC, int LW, bool WITH_AMP>
-__device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, int s, int k, int l16,
+__device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, int s, int k, int l,
                                               OscStateH<NC>& st, bool& steady, int& amp_mode) {
   float Fn[NC], An[NC];
-  load_frame_h<NC, LW, WITH_AMP>(a, row, s, k, l16, st.F, st.A);
-  load_frame_h<NC, LW, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l16, Fn, An);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, k, l, st.F, st.A);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l, Fn, An);
   bool all_steady = true, any_live = false, any_risky = false;
   // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
   // bottom - top, one in the product, one in the sum), hence the margin
@@ -346,18 +347,18 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
                                             int c, int lane, const float* win, float* row_out) {
   const int t0 = c * a.chunk;
   const int t1 = min(a.N, t0 + a.chunk);
-  const int l16 = lane & (LW - 1), s = s0 + lane / LW;   // LW = 16: two substrings on the half-warps
+  const int l = lane & (LW - 1), s = s0 + lane / LW;   // LW = 16: two substrings on the half-warps
   OscStateH<NC> st;
   int k = t0 / a.U;
   int r = t0 - k * a.U;
   bool steady;
   int amp_mode;
-  enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+  enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     st.ph[j] = 0.f;
     st.off[j] = 0.f;
-    const int h = l16 + LW * j;
+    const int h = l + LW * j;
     if (!ENDS_ONLY && c > 0 && h < a.H)
       st.off[j] = a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h];
   }
@@ -366,7 +367,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     if (r == a.U) {
       r = 0;
       ++k;
-      enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l16, st, steady, amp_mode);
+      enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
     }
     // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
     // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
@@ -401,7 +402,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
   if (ENDS_ONLY) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      const int h = l16 + LW * j;
+      const int h = l + LW * j;
       if (h < a.H)
         a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h] = floormod_two_pi(st.ph[j]);
     }
