@@ -82,6 +82,34 @@ def algorithmic_bytes(w, B, G):
     }
 
 
+def live_chain_samples(w, x):
+    """Oscillator-samples the synthesis kernels actually run for these inputs: the kernels drop
+    16-partial half-groups that lie above Nyquist (or belong to a muted voice) in every frame a
+    1000-sample chunk touches, and a unit with nh live half-groups runs nh chains
+    on each of the warp's 32 lanes.  Host-side restatement of that bookkeeping (the liveness rule
+    of the controls kernel: a partial can sound if f0 n sqrt(1 + B n^2) < sr / 2 and f0 > 20 Hz)."""
+    P, F, H, S = w['P'], w['F'], w['H'], w['S']
+    sr = w['sr']
+    U = sr // 250
+    N = F * U
+    f0 = x['f0_hz'][..., 0].astype(np.float64)                           # [P, B, F]
+    binh = np.maximum(x['inharm_coef'][..., 0].astype(np.float64), 0.0)
+    n = np.arange(1, H + 1, dtype=np.float64)
+    freq = f0[..., None] * n * np.sqrt(1.0 + binh[..., None] * n * n)    # [P, B, F, H]
+    can = (freq < sr / 2.0) & (f0[..., None] > 20.0)
+    top = np.where(can.any(-1), H - np.argmax(can[..., ::-1], axis=-1), 0)   # 1 + highest live partial
+    nh_frame = -(-top // 16)                                             # [P, B, F]
+    total = 0
+    for t0 in range(0, N, 1000):
+        t1 = min(N, t0 + 1000) - 1
+        k0, k1 = t0 // U, min(F - 1, t1 // U + 1)
+        nh = nh_frame[..., k0:k1 + 1].max(-1)                            # [P, B]
+        lanes_per_string = 16 if S % 2 == 0 else 32
+        chains = nh if S % 2 == 0 else -(-nh // 2)
+        total += int(chains.sum()) * lanes_per_string * S * (t1 + 1 - t0)
+    return total
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -372,6 +400,8 @@ def run_gpu(args, w):
         # dram__bytes_read+write of the six bucket launches of one step, from the ncu --set full
         # capture of this same command (profiles/r01_prof10_summary.txt); config 3 at N=1 only
         traffic = 101.7e6 if (args.workload == 'full' and world == 1) else None
+        live = live_chain_samples(w, synthetic_inputs(w, seed=rank))
+        ends_ms = stages.get('phase_ends', 0.0) / args.steps
         sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
         roofline = {
             'bound': 'hbm',
@@ -388,6 +418,19 @@ def run_gpu(args, w):
                     'the bit-faithful phase chain needs 11.5 FMA-pipe cycles per oscillator-sample (+6 in the phase pass); see '
                     'fma_pipe, oscillator_samples_per_s and DESIGN.md section 4',
             'oscillator_samples_per_s': osc_samples / (osc_ms * 1e-3) if osc_ms > 0 else None,
+            # the bound that matters, measured live: FMA-pipe cycles the bit-faithful algorithm needs
+            # for the oscillator-samples on live lanes (11.5 per sample in the synthesis pass, 6 in
+            # the phase pass) over the pipe cycles available in the measured time
+            # (148 SMs x 4 schedulers x 32 lanes at the SM clock under load)
+            'fp32_pipe': ({'live_oscillator_samples': live,
+                           'synthesis': {'needed_lane_cycles': live * 11.5,
+                                         'frac': live * 11.5 / (osc_ms * 1e-3 * 148 * 128 * sm_hz)},
+                           'phase_pass': ({'needed_lane_cycles': live * 6.0 * (1 - 1000.0 / N),
+                                           'frac': live * 6.0 * (1 - 1000.0 / N) /
+                                                   (ends_ms * 1e-3 * 148 * 128 * sm_hz)}
+                                          if ends_ms > 0 else None),
+                           'peak_lane_cycles_per_s': 148 * 128 * sm_hz}
+                          if osc_ms > 0 else None),
             # what actually bounds the stage.  Static facts from the ncu capture of this command
             # (profiles/r01_prof10_summary.txt, config 3): warp instructions of the six bucket
             # launches and the FMA-pipe activity of the two dominant kernels; live: the share of
