@@ -254,6 +254,35 @@ def run_reference(args, w):
 # GPU side
 # ------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers
+    are allocated (first touch places them on that node): with several ranks per host the
+    host-to-device copies otherwise cross the socket interconnect.  Returns the node or None."""
+    try:
+        import subprocess
+        bus = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i',
+                              str(index)], capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = bus.lower()
+        if bus.count(':') == 2 and len(bus.split(':')[0]) == 8:      # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_gpu(args, w):
     import torch
     import torch.distributed as dist
@@ -270,6 +299,7 @@ def run_gpu(args, w):
     from ddsp_piano_b200.processors import _DEFAULT_CFG
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     sr, B, P, S, H, M, F, L = (w[k] for k in ('sr', 'B', 'P', 'S', 'H', 'M', 'F', 'L'))
     U = sr // 250
     N = F * U
@@ -460,7 +490,8 @@ def run_gpu(args, w):
                        'reverb_taps': L, 'sample_rate': sr, 'noise': 'in-kernel Philox',
                        'phase': 'bit-faithful float32 angular_cumsum',
                        'l2': 'flushed (256 MB write) between timed steps',
-                       'sharding': 'clips over ranks, no collective'},
+                       'sharding': 'clips over ranks, no collective',
+                       'host_numa_binding': numa_node},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': B * N * 4, 'ms_per_step': e2e_ms / args.steps,
                     'h2d_GBps_if_copy_bound': h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
