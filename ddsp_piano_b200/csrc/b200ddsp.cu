@@ -24,6 +24,7 @@
 #include "noise.cuh"
 #include "reverb.cuh"
 #include "control_rate.cuh"
+#include "timeline.cuh"
 
 using namespace b200ddsp;
 
@@ -1563,6 +1564,65 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     CUDA_TRY(h, cudaMemcpyAsync(dry_out_host, dry_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   if (wet_out_host)
     CUDA_TRY(h, cudaMemcpyAsync(wet_out_host, wet_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  return B200DDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// timeline reverb across GPUs: peer-visible buffers + the fused overlap-add / carry kernel
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200ddsp_peer_alloc(b200ddsp_handle* h, size_t bytes, void** dev_ptr,
+                                   unsigned char* ipc_handle64) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!dev_ptr || !ipc_handle64 || bytes == 0)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "peer_alloc: null output or zero size");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 bytes");
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t ipc;
+  cudaError_t e = cudaIpcGetMemHandle(&ipc, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(h, B200DDSP_CUDA_ERROR, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle64, &ipc, 64);
+  *dev_ptr = p;
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_peer_free(b200ddsp_handle* h, void* dev_ptr) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (dev_ptr) CUDA_TRY(h, cudaFree(dev_ptr));
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_peer_open(b200ddsp_handle* h, const unsigned char* ipc_handle64, void** peer_ptr) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!ipc_handle64 || !peer_ptr) return fail(h, B200DDSP_BAD_ARGUMENT, "peer_open: null argument");
+  cudaIpcMemHandle_t ipc;
+  memcpy(&ipc, ipc_handle64, 64);
+  CUDA_TRY(h, cudaIpcOpenMemHandle(peer_ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_peer_close(b200ddsp_handle* h, void* peer_ptr) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (peer_ptr) CUDA_TRY(h, cudaIpcCloseMemHandle(peer_ptr));
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_timeline_overlap_add(b200ddsp_handle* h, const float* wet_full, const float* dry,
+                                             float* out, float* peer_head, int S, int N, int L,
+                                             void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!wet_full || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (S < 1 || N < 1 || L < 1) return fail(h, B200DDSP_BAD_SHAPE, "S=%d N=%d L=%d", S, N, L);
+  if ((long long)(L - 1) > (long long)S * N)
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "the reverb tail (%d samples) is longer than a rank's span (%d segments x %d)", L - 1, S, N);
+  const long long n = (long long)S * N + (peer_head ? L - 1 : 0);
+  timeline_overlap_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      wet_full, dry, out, peer_head, S, N, N + L - 1);
+  CHECK_LAUNCH(h, "timeline_overlap_add_kernel");
   return B200DDSP_OK;
 }
 

@@ -191,6 +191,44 @@ class Engine:
                 float(decay_exponent), int(decay_start), self.stream()))
         return out
 
+    # -- peer-visible buffers and the fused timeline overlap-add (sharding.PeerTimeline) ----------
+    def peer_alloc(self, nbytes):
+        """cudaMalloc + CUDA IPC handle: (device pointer, 64-byte handle)."""
+        import ctypes
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_peer_alloc(self.handle, nbytes, ctypes.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def peer_open(self, handle):
+        import ctypes
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_peer_open(self.handle, handle, ctypes.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr):
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_peer_close(self.handle, ptr))
+
+    def peer_free(self, ptr):
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_peer_free(self.handle, ptr))
+
+    def timeline_overlap_add(self, wet_full, dry, out_ptr, peer_head_ptr, S, N, L):
+        wet_full = self.tensor(wet_full, 'wet_full', 2)
+        if tuple(wet_full.shape) != (S, N + L - 1):
+            raise ValueError(f'wet_full is {tuple(wet_full.shape)}, expected {(S, N + L - 1)}')
+        dry_ptr = 0
+        if dry is not None:
+            dry = self.tensor(dry, 'dry', 2)
+            dry_ptr = dry.data_ptr()
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_timeline_overlap_add(
+                self.handle, wet_full.data_ptr(), dry_ptr, out_ptr, peer_head_ptr or 0, S, N, L,
+                self.stream()))
+
     def note_release(self, conditioning, release_frames):
         """NoteRelease over conditioning [rows, F, 2] (pitch column) or active pitch [rows, F, 1]
         -> extended_pitch [rows, F, 1]."""

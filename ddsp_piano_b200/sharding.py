@@ -83,6 +83,65 @@ def timeline_reverb(dry, ir, conv_full, rank=0, world=1, add_dry=True, group=Non
     wet, carry = overlap_add_segments(wet_full, N)
     incoming = exchange_carry(carry, rank, world, group)
     flat = wet.reshape(-1)
-    flat[:incoming.shape[0]] += incoming          # fused into the receive epilogue on the GPU path
+    flat[:incoming.shape[0]] += incoming          # PeerTimeline fuses this into the overlap-add kernel
     wet = flat.reshape(S, N)
     return wet + dry if add_dry else wet
+
+
+class _DeviceBuffer:
+    """A raw device allocation as a ``__cuda_array_interface__`` object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {'shape': (n_floats,), 'typestr': '<f4', 'data': (ptr, False),
+                                         'version': 2}
+
+
+class PeerTimeline:
+    """The GPU form of :func:`timeline_reverb`: ONE kernel does the local overlap-add and adds the
+    carry straight into the successor's output buffer over NVLink peer memory
+    (``csrc/timeline.cuh``) -- no send/recv, no staging buffer, no separate add.
+
+    Every rank owns a peer-visible output buffer [S * N] (``b200ddsp_peer_alloc``); the CUDA IPC
+    handles are exchanged once, here, through ``torch.distributed`` and rank r maps the buffer of
+    rank r + 1.  Per call: zero the head of the own buffer, barrier, launch, barrier."""
+
+    def __init__(self, engine, n_segments, n_samples, ir_length, rank, world, group=None):
+        self.eng, self.S, self.N, self.L = engine, n_segments, n_samples, ir_length
+        self.rank, self.world, self.group = rank, world, group
+        if ir_length - 1 > n_segments * n_samples:
+            raise ValueError(f'reverb tail ({ir_length - 1} samples) is longer than the rank\'s span '
+                             f'({n_segments} segments x {n_samples})')
+        self.ptr, handle = engine.peer_alloc(n_segments * n_samples * 4)
+        self.out = torch.as_tensor(_DeviceBuffer(self.ptr, n_segments * n_samples), device=engine.device)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, handle, group=group)
+        self.peer_head = engine.peer_open(handles[rank + 1]) if rank + 1 < world else 0
+
+    def reverb(self, dry, ir, add_dry=True):
+        """dry [S, N] (this rank's consecutive segments), ir [L] -> wet [S, N], a view of the
+        peer-visible buffer (valid until the next call)."""
+        S, N, L = self.S, self.N, self.L
+        if tuple(dry.shape) != (S, N) or tuple(ir.shape) != (L,):
+            raise ValueError(f'expected dry {(S, N)} and ir {(L,)}, got {tuple(dry.shape)}, {tuple(ir.shape)}')
+        wet_full = self.eng.reverb_full(dry, ir[None, :].expand(S, L).contiguous())
+        self.out[:L - 1].zero_()
+        if self.world > 1:
+            dist.barrier(group=self.group)           # every head is zero before anyone adds into it
+        self.eng.timeline_overlap_add(wet_full, dry if add_dry else None, self.ptr, self.peer_head, S, N, L)
+        if self.world > 1:
+            dist.barrier(group=self.group)           # every carry has landed
+        return self.out.view(S, N)
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.peer_head:
+            self.eng.peer_close(self.peer_head)
+            self.peer_head = 0
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.ptr:
+            self.out = None
+            self.eng.peer_free(self.ptr)
+            self.ptr = 0

@@ -167,6 +167,21 @@ int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir
 int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int B, int L,
                            float decay_exponent, int decay_start, void* stream);
 
+/* Timeline reverb across GPUs (the reference has no multi-GPU synthesis, its segment
+ * pipeline -- synthesize_midi_file.py / data_pipeline.py -- treats every segment alone).  A rank holds S
+ * consecutive segments of N samples; wet_full [S, N + L - 1] is b200ddsp_reverb_full of them.  One
+ * launch overlap-adds them into out [S * N] (+ dry when given) and adds the L - 1 samples that spill past
+ * the span directly into the head of the NEXT rank's out buffer through peer memory (peer_head = that
+ * buffer mapped with b200ddsp_peer_open; NULL on the last rank).  Protocol: every rank zeroes
+ * out[0 .. L-1), all ranks synchronise, every rank launches, all ranks synchronise.  Buffers that a
+ * peer writes must come from b200ddsp_peer_alloc (plain cudaMalloc + CUDA IPC handle, 64 bytes). */
+int b200ddsp_peer_alloc(b200ddsp_handle* h, size_t bytes, void** dev_ptr, unsigned char* ipc_handle64);
+int b200ddsp_peer_free(b200ddsp_handle* h, void* dev_ptr);
+int b200ddsp_peer_open(b200ddsp_handle* h, const unsigned char* ipc_handle64, void** peer_ptr);
+int b200ddsp_peer_close(b200ddsp_handle* h, void* peer_ptr);
+int b200ddsp_timeline_overlap_add(b200ddsp_handle* h, const float* wet_full, const float* dry, float* out,
+                                  float* peer_head, int S, int N, int L, void* stream);
+
 /* NoteRelease -- modules/sub_modules.py:1174-1188 (tfkl.RNN over F0ProcessorCell, :1114-1171): holds
  * each voice's last played MIDI note for `release_frames` (= release_duration * frame_rate; the
  * shipped dafx22 weights have release_duration = 1 s) frames after its note-off, so that the partial

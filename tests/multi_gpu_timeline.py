@@ -38,6 +38,18 @@ def main():
     x = dry_all.astype(np.float64).reshape(-1)
     want = (np.convolve(x, h)[:x.size] + x).reshape(world * S, N)[lo:hi]
     err = float(np.max(np.abs(wet.cpu().numpy() - want)) / np.max(np.abs(want)))
+    # the same through the fused kernel: overlap-add + carry into the successor's buffer over peer memory
+    peer = sharding.PeerTimeline(eng, hi - lo, N, L, rank, world)
+    errs = []
+    for _ in range(3):                                   # the buffers are reused call after call
+        wet2 = peer.reverb(torch.from_numpy(dry_all[lo:hi]).to(dev), torch.from_numpy(ir).to(dev))
+        torch.cuda.synchronize()
+        errs.append(float(np.max(np.abs(wet2.cpu().numpy() - want)) / np.max(np.abs(want))))
+    same = bool(torch.equal(wet2, peer.reverb(torch.from_numpy(dry_all[lo:hi]).to(dev),
+                                              torch.from_numpy(ir).to(dev))))
+    peer.close()
+    print(f'rank {rank}: peer-memory timeline rel err {max(errs):.3e}, repeatable {same}', flush=True)
+    err = max(err, max(errs)) if same else 1.0
     ok = torch.tensor([1.0 if err < 2e-5 else 0.0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     print(f'rank {rank}: timeline reverb rel err {err:.3e}', flush=True)
