@@ -115,6 +115,10 @@ def load():
     lib.b200ddsp_reverb_full.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_ir_decay_mask.restype = ci
     lib.b200ddsp_ir_decay_mask.argtypes = [vp, vp, vp, ci, ci, ctypes.c_float, ci, vp]
+    lib.b200ddsp_surrogate_decays.restype = ci
+    lib.b200ddsp_surrogate_decays.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
+    lib.b200ddsp_surrogate_signal.restype = ci
+    lib.b200ddsp_surrogate_signal.argtypes = [vp] + [vp] * 7 + [ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_peer_alloc.restype = ci
     lib.b200ddsp_peer_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
     lib.b200ddsp_peer_free.restype = ci
@@ -156,7 +160,7 @@ def load():
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
-           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_peer_alloc', 'b200ddsp_peer_free',
+           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_surrogate_decays', 'b200ddsp_surrogate_signal', 'b200ddsp_peer_alloc', 'b200ddsp_peer_free',
            'b200ddsp_peer_open', 'b200ddsp_peer_close', 'b200ddsp_timeline_overlap_add', 'b200ddsp_fdn_ir',
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',

@@ -36,6 +36,8 @@ struct AdditiveArgs {
   const float* shifts;  // [R, F, H]
   const float* f0;      // [R, F, S]
   float* offsets;       // [R*S, n_chunks, H]: chunk end phases (pass 1), then chunk offsets (scan)
+  const float* decays;      // [R, F, H] or nullptr: SurrogateAdditive (surrogate_synth.py:78-97), generic
+  const float* decay_time;  // [R, F]                kernel only: amplitude *= |decay|^(decay_time U + r)
   float* out;           // [G, B, N]
   const float* window;  // [2U]  tf.signal.hann_window(2U, periodic)
   int B, P, F, H, S, U, N;
@@ -140,6 +142,17 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
     FrameRegs<HP> cur, nxt;
     float dF[HP], ph[HP], off[HP];
     float Fprev[HP], dFprev[HP];   // generic path only: the frame below (lo == k-1)
+    float D[HP], T0 = 0.f;         // surrogate: |decay| of frame k per partial, decay_time * U
+    const bool surrogate = !ENDS_ONLY && a.decays != nullptr;
+    auto load_decays = [&](int kk) {
+      T0 = __fmul_rn(__ldg(a.decay_time + (size_t)row * a.F + kk), (float)a.U);
+#pragma unroll
+      for (int q = 0; q < HP; ++q) {
+        const int h = lane + 32 * q;
+        D[q] = (h < a.H) ? fabsf(__ldg(a.decays + ((size_t)row * a.F + kk) * a.H + h)) : 1.f;
+      }
+    };
+    if (surrogate) load_decays(k);
     load_frame<HP, !ENDS_ONLY>(a, row, s, k, lane, cur);
     load_frame<HP, !ENDS_ONLY>(a, row, s, min(k + 1, a.F - 1), lane, nxt);
     const size_t off_base = (((size_t)row * a.S + s) * a.n_chunks + c) * a.H;
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
             load_frame<HP, !ENDS_ONLY>(a, row, s, min(k + 1, a.F - 1), lane, nxt);
 #pragma unroll
             for (int q = 0; q < HP; ++q) dF[q] = __fadd_rn(nxt.F[q], -cur.F[q]);
+            if (surrogate) load_decays(k);
           }
           const float kf = (float)k;
 #pragma unroll
@@ -216,6 +230,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
               ph[q] = __fadd_rn(ph[q], om);                            // in-chunk cumsum
               if (!ENDS_ONLY) {
                 float amp = __fmaf_rn(cur.A[q], w1, __fmul_rn(nxt.A[q], w0));
+                if (surrogate) amp = __fmul_rn(amp, powf(D[q], __fadd_rn(T0, (float)(r + j))));
                 amp = (f >= a.nyquist) ? 0.f : amp;                    // :65-67
                 const float p = wrap_to_pi(__fadd_rn(ph[q], off[q]));
                 y[gi * G + j] = __fmaf_rn(amp, __cosf(p), y[gi * G + j]);   // :80-83

@@ -602,11 +602,12 @@ struct AdditiveRun {
 
 static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, const float* hd,
                           const float* shifts, const float* f0, char* base, const AdditiveLayout& lay,
-                          int P, int B, int F, int H, int S, const PlanGroups& groups) {
+                          int P, int B, int F, int H, int S, const PlanGroups& groups,
+                          const float* decays = nullptr, const float* decay_time = nullptr) {
   const int U = h->U, N = F * U;
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  r->fast = additive_fast_path(h, F, H);
+  r->fast = additive_fast_path(h, F, H) && decays == nullptr;   // the surrogate runs on the generic kernel
   if (!r->fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
@@ -630,6 +631,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   AdditiveArgs& a = r->a;
   a = AdditiveArgs{};
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
+  a.decays = decays; a.decay_time = decay_time;
   a.offsets = (float*)(base + lay.offsets);
   a.out = r->partials;
   a.window = h->d_window;
@@ -849,11 +851,11 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
   return B200DDSP_OK;
 }
 
-extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitudes,
-                                        const float* harmonic_distribution,
-                                        const float* harmonic_shifts, const float* f0_hz, float* out,
-                                        int B, int F, int H, int S, int accumulate, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+static int additive_signal_impl(b200ddsp_handle* h, const float* amplitudes,
+                                const float* harmonic_distribution, const float* harmonic_shifts,
+                                const float* f0_hz, const float* decays, const float* decay_time,
+                                float* out, int B, int F, int H, int S, int accumulate, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   if (int rc = check_common(h, B, F)) return rc;
   if (!amplitudes || !harmonic_distribution || !harmonic_shifts || !f0_hz || !out)
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
@@ -872,7 +874,7 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
   groups.first_voice[1] = 1;
   AdditiveRun run;
   if (int rc = additive_begin(h, &run, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz,
-                              (char*)workspace, lay, 1, B, F, H, S, groups))
+                              (char*)workspace, lay, 1, B, F, H, S, groups, decays, decay_time))
     return rc;
   if (int rc = additive_phase_pass(h, run, false, st)) return rc;
   if (int rc = additive_synth_group(h, run, 0, st)) return rc;
@@ -896,6 +898,42 @@ extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitu
 // ---------------------------------------------------------------------------------------------
 // noise
 // ---------------------------------------------------------------------------------------------
+
+extern "C" int b200ddsp_additive_signal(b200ddsp_handle* h, const float* amplitudes,
+                                        const float* harmonic_distribution,
+                                        const float* harmonic_shifts, const float* f0_hz, float* out,
+                                        int B, int F, int H, int S, int accumulate, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return additive_signal_impl(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, nullptr, nullptr,
+                              out, B, F, H, S, accumulate, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200ddsp_surrogate_signal(b200ddsp_handle* h, const float* amplitudes, const float* decays,
+                                         const float* decay_time, const float* harmonic_distribution,
+                                         const float* harmonic_shifts, const float* f0_hz, float* out,
+                                         int B, int F, int H, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!decays || !decay_time) return fail(h, B200DDSP_BAD_ARGUMENT, "null decay tensor");
+  if (!h->cfg.inference)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "SurrogateAdditive is implemented for inference=1 (angular cumsum) only");
+  return additive_signal_impl(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, decays,
+                              decay_time, out, B, F, H, 1, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200ddsp_surrogate_decays(b200ddsp_handle* h, const float* decays, const float* inharm_coef,
+                                         const float* f0_hz, float* out, int B, int F, int H,
+                                         void* stream) {
+  if (int rc = check_common(h, B, F)) return rc;
+  if (!decays || !inharm_coef || !f0_hz || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
+  const size_t n = (size_t)B * F * H;
+  surrogate_decays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      decays, inharm_coef, f0_hz, out, B * F, H, (float)(h->cfg.sample_rate / 2.0));
+  CHECK_LAUNCH(h, "surrogate_decays_kernel");
+  return B200DDSP_OK;
+}
 
 extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitudes,
                                        float* magnitudes_out, size_t n, void* stream) {

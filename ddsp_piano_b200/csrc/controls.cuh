@@ -172,4 +172,20 @@ __global__ void __launch_bounds__(256) noise_controls_kernel(const float* __rest
   }
 }
 
+// SurrogateAdditive.get_controls, decay part (surrogate_synth.py:163-171): clip to [1e-5, 1], and
+// 1 (no decay) for partials whose inharmonic frequency is at or above Nyquist.
+__global__ void __launch_bounds__(256) surrogate_decays_kernel(const float* __restrict__ decays,
+                                                               const float* __restrict__ inharm_coef,
+                                                               const float* __restrict__ f0_hz,
+                                                               float* __restrict__ out, int n_frames,
+                                                               int H, float nyquist) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n_frames * H) return;
+  const int fr = (int)(i / H), h = (int)(i - (size_t)fr * H);
+  const float binh = fmaxf(__ldg(inharm_coef + fr), 0.f);
+  const float fi = __fmul_rn(__fmul_rn(__ldg(f0_hz + fr), (float)(h + 1)), inharm_factor(h, binh));
+  const float d = fmaxf(fminf(__ldg(decays + i), 1.f), 1e-5f);
+  out[i] = (fi >= nyquist) ? 1.f : d;
+}
+
 }  // namespace b200ddsp

@@ -152,6 +152,44 @@ class Engine:
                 self.stream()))
         return out
 
+    def surrogate_decays(self, decays, inharm_coef, f0_hz):
+        """SurrogateAdditive.get_controls, decay clipping (surrogate_synth.py:163-171)."""
+        decays = self.tensor(decays, 'decays', 3)
+        inharm_coef = self.tensor(inharm_coef, 'inharm_coef', 3)
+        f0_hz = self.tensor(f0_hz, 'f0_hz', 3)
+        B, F, H = decays.shape
+        if tuple(inharm_coef.shape) != (B, F, 1) or tuple(f0_hz.shape) != (B, F, 1):
+            raise ValueError(f'inharm_coef {tuple(inharm_coef.shape)} / f0_hz {tuple(f0_hz.shape)} '
+                             f'must be {(B, F, 1)}')
+        out = torch.empty_like(decays)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_surrogate_decays(
+                self.handle, decays.data_ptr(), inharm_coef.data_ptr(), f0_hz.data_ptr(),
+                out.data_ptr(), B, F, H, self.stream()))
+        return out
+
+    def surrogate_signal(self, amplitudes, decays, decay_time, harmonic_distribution, harmonic_shifts,
+                         f0_hz):
+        amplitudes = self.tensor(amplitudes, 'amplitudes', 3)
+        decays = self.tensor(decays, 'decays', 3)
+        decay_time = self.tensor(decay_time, 'decay_time', 3)
+        hd = self.tensor(harmonic_distribution, 'harmonic_distribution', 3)
+        shifts = self.tensor(harmonic_shifts, 'harmonic_shifts', 3)
+        f0_hz = self.tensor(f0_hz, 'f0_hz', 3)
+        B, F, H = hd.shape
+        for t, n, c in ((amplitudes, 'amplitudes', 1), (decays, 'decays', H), (decay_time, 'decay_time', 1),
+                        (shifts, 'harmonic_shifts', H), (f0_hz, 'f0_hz', 1)):
+            if tuple(t.shape) != (B, F, c):
+                raise ValueError(f'{n} has shape {tuple(t.shape)}, expected {(B, F, c)}')
+        out = torch.empty([B, F * self.upsampling], dtype=torch.float32, device=self.device)
+        ws = self.workspace(self.lib.b200ddsp_additive_workspace_bytes(self.handle, B, F, H, 1))
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_surrogate_signal(
+                self.handle, amplitudes.data_ptr(), decays.data_ptr(), decay_time.data_ptr(),
+                hd.data_ptr(), shifts.data_ptr(), f0_hz.data_ptr(), out.data_ptr(), B, F, H,
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return out
+
     def noise_controls(self, magnitudes):
         magnitudes = self.tensor(magnitudes, 'magnitudes')
         out = torch.empty_like(magnitudes)

@@ -132,6 +132,38 @@ class InHarmonic(Processor):
             amplitudes, harmonic_distribution, harmonic_shifts, f0_hz)
 
 
+class SurrogateAdditive(InHarmonic):
+    """modules/surrogate_synth.py:107-214 (configs/surrogate.gin): the inharmonic bank of one string
+    with exponentially decaying partial amplitudes, ``|decays| ** (decay_time * U + r)`` per sample
+    (B. Hayes, sinusoidal frequency estimation by gradient descent).  Forward only, ``inference=True``
+    (angular cumsum); it runs on the generic oscillator kernel."""
+
+    def __init__(self, frame_rate=250, sample_rate=16000, min_frequency=20,
+                 normalize_harm_distribution=True, scale_fn=exp_sigmoid, normalize_below_nyquist=True,
+                 inference=False, name='inharmonic'):
+        super().__init__(frame_rate=frame_rate, sample_rate=sample_rate, min_frequency=min_frequency,
+                         scale_fn=scale_fn, normalize_after_nyquist_cut=True,
+                         normalize_below_nyquist=normalize_below_nyquist, inference=inference, name=name)
+        if not normalize_harm_distribution:
+            raise ValueError('SurrogateAdditive(normalize_harm_distribution=False) is not implemented')
+        self.normalize_harm_distribution = normalize_harm_distribution
+
+    def get_controls(self, amplitudes, decays, decay_time, harmonic_distribution, inharm_coef, f0_hz):
+        eng = self._engine(amplitudes, f0_hz)
+        ctl = eng.additive_controls(amplitudes, harmonic_distribution, inharm_coef, f0_hz)
+        return {'amplitudes': ctl['amplitudes'],
+                'decays': None if decays is None else eng.surrogate_decays(decays, inharm_coef, f0_hz),
+                'decay_time': decay_time, 'harmonic_distribution': ctl['harmonic_distribution'],
+                'harmonic_shifts': ctl['harmonic_shifts'], 'f0_hz': ctl['f0_hz']}
+
+    def get_signal(self, amplitudes, decays, decay_time, harmonic_distribution, harmonic_shifts, f0_hz):
+        eng = self._engine(amplitudes, f0_hz)
+        if decays is None or decay_time is None:                               # surrogate_synth.py:78
+            return eng.additive_signal(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz)
+        return eng.surrogate_signal(amplitudes, decays, decay_time, harmonic_distribution,
+                                    harmonic_shifts, f0_hz)
+
+
 class MultiInharmonic(InHarmonic):
     """modules/inharm_synth.py:247-293: one oscillator bank per substring (f0_hz [B, F, S]),
     sharing amplitudes (pre-divided by S) and inharmonic shifts.  The S syntheses and their

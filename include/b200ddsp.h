@@ -167,6 +167,20 @@ int b200ddsp_reverb_full(b200ddsp_handle* h, const float* audio, const float* ir
 int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int B, int L,
                            float decay_exponent, int decay_start, void* stream);
 
+/* SurrogateAdditive -- modules/surrogate_synth.py:107-214 (configs/surrogate.gin:106): the inharmonic
+ * bank of ONE string (f0_hz [B, F, 1]) whose partial amplitudes are multiplied by |decay|^t, t = samples
+ * since the frame-rate decay_time origin (surrogate_harmonic_synthesis :78-97).  get_controls =
+ * b200ddsp_additive_controls with S = 1 (no pre-normalisation) for amplitudes / harmonic_distribution /
+ * harmonic_shifts, plus b200ddsp_surrogate_decays (clip to [1e-5, 1], 1 above Nyquist, :163-171);
+ * get_signal = b200ddsp_surrogate_signal (decays [B, F, H], decay_time [B, F, 1]; workspace of
+ * b200ddsp_additive_workspace_bytes(h, B, F, H, 1)).  inference = 1 only. */
+int b200ddsp_surrogate_decays(b200ddsp_handle* h, const float* decays, const float* inharm_coef,
+                              const float* f0_hz, float* decays_out, int B, int F, int H, void* stream);
+int b200ddsp_surrogate_signal(b200ddsp_handle* h, const float* amplitudes, const float* decays,
+                              const float* decay_time, const float* harmonic_distribution,
+                              const float* harmonic_shifts, const float* f0_hz, float* out, int B, int F,
+                              int H, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Timeline reverb across GPUs (the reference has no multi-GPU synthesis, its segment
  * pipeline -- synthesize_midi_file.py / data_pipeline.py -- treats every segment alone).  A rank holds S
  * consecutive segments of N samples; wet_full [S, N + L - 1] is b200ddsp_reverb_full of them.  One

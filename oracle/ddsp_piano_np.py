@@ -120,6 +120,61 @@ def additive_signal(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, *
     return audio
 
 
+def surrogate_controls(amplitudes, decays, decay_time, harmonic_distribution, inharm_coef, f0_hz, *,
+                       sample_rate, min_frequency=20, scale_fn=SCALE_EXP_SIGMOID,
+                       normalize_harm_distribution=True, normalize_below_nyquist=True):
+    """SurrogateAdditive.get_controls, modules/surrogate_synth.py:132-189.  f0_hz is [B, F, 1]."""
+    amplitudes = core.tf_float32(amplitudes)
+    harmonic_distribution = core.tf_float32(harmonic_distribution)
+    inharm_coef = core.tf_float32(inharm_coef)
+    f0_hz = core.tf_float32(f0_hz)
+    dt = f0_hz.dtype.type
+    fn = _scale(scale_fn)
+    if fn is not None:                                                        # :152-154
+        amplitudes = fn(amplitudes)
+        harmonic_distribution = fn(harmonic_distribution)
+    inharm_coef = np.maximum(inharm_coef, dt(0.))                             # :157
+    n_harm = int(harmonic_distribution.shape[-1])
+    partial_hz, shifts = inharmonic_frequencies(f0_hz, inharm_coef, n_harm)   # :159-161
+    if decays is not None:                                                    # :163-171
+        decays = np.maximum(np.minimum(core.tf_float32(decays), dt(1.)), dt(1e-5))
+        decays = np.where(partial_hz >= dt(sample_rate / 2.), np.ones_like(decays), decays)
+    if normalize_below_nyquist:                                               # :172-181
+        harmonic_distribution = core.remove_above_nyquist(partial_hz, harmonic_distribution, sample_rate)
+        amplitudes = amplitudes * (f0_hz > dt(min_frequency)).astype(dt)
+    if normalize_harm_distribution:                                           # :183-187
+        harmonic_distribution = core.safe_divide(
+            harmonic_distribution, np.sum(harmonic_distribution, -1, keepdims=True))
+    return {'amplitudes': amplitudes, 'decays': decays, 'decay_time': decay_time,
+            'harmonic_distribution': harmonic_distribution, 'harmonic_shifts': shifts, 'f0_hz': f0_hz}
+
+
+def surrogate_signal(amplitudes, decays, decay_time, harmonic_distribution, harmonic_shifts, f0_hz, *,
+                     sample_rate, frame_rate=250, inference=True):
+    """SurrogateAdditive.get_signal -> surrogate_harmonic_synthesis, modules/surrogate_synth.py:11-104:
+    the additive bank with every partial's amplitude envelope multiplied by |decay|^t, t = samples
+    since the (frame-rate) decay_time origin, both held over each control frame (tf.repeat)."""
+    amplitudes = core.tf_float32(amplitudes)
+    harmonic_distribution = core.tf_float32(harmonic_distribution)
+    harmonic_shifts = core.tf_float32(harmonic_shifts)
+    f0_hz = core.tf_float32(f0_hz)
+    dt = f0_hz.dtype.type
+    upsampling = int(sample_rate / frame_rate)
+    n_frames = f0_hz.shape[1]
+    n_samples = upsampling * n_frames                                         # :49
+    n_harm = harmonic_distribution.shape[-1]
+    partial_hz = core.get_harmonic_frequencies(f0_hz, n_harm) * (dt(1.0) + harmonic_shifts)   # :61-64
+    partial_amp = amplitudes * harmonic_distribution                          # :67-70
+    freq_env = core.resample(partial_hz, n_samples)                           # :73
+    amp_env = core.resample(partial_amp, n_samples, method='window')          # :74-75
+    if decays is not None and decay_time is not None:                         # :78-97
+        decay_env = np.repeat(core.tf_float32(decays), upsampling, axis=1)
+        t = np.repeat(core.tf_float32(decay_time), upsampling, axis=1) * dt(upsampling)
+        t = t + np.tile(np.arange(upsampling, dtype=dt), n_frames)[None, :, None]
+        amp_env = amp_env * np.power(np.abs(decay_env), t.astype(dt))
+    return oscillator_bank(freq_env, amp_env, sample_rate, inference)         # :100-103
+
+
 def noise_controls(magnitudes, *, initial_bias=-5.0, scale_fn=SCALE_EXP_SIGMOID):
     """ddsp.synths.FilteredNoise.get_controls (inherited by
     modules/filtered_noise_synth.py:13): scale_fn(magnitudes + initial_bias)."""

@@ -56,9 +56,20 @@ def _maximum(a, b):
     return np.maximum(a, a.dtype.type(b) if np.isscalar(b) else b)
 
 
+def _pow(x, y):
+    x = np.asarray(x)
+    y = x.dtype.type(y) if np.isscalar(y) else np.asarray(y, x.dtype)
+    return np.power(x, y)
+
+
+def _minimum(a, b):
+    a = np.asarray(a)
+    return np.minimum(a, a.dtype.type(b) if np.isscalar(b) else b)
+
+
 math = types.SimpleNamespace(
-    tanh=np.tanh, log=_log, pow=lambda x, y: np.power(x, np.asarray(x).dtype.type(y)),
-    sqrt=np.sqrt, maximum=_maximum, exp=np.exp)
+    tanh=np.tanh, log=_log, pow=_pow, sqrt=np.sqrt, maximum=_maximum, minimum=_minimum, exp=np.exp,
+    abs=np.abs)
 
 
 def _uniform(shape, minval=0., maxval=1., dtype=np.float32, seed=None):
@@ -150,8 +161,19 @@ def tile(x, multiples):
     return np.tile(x, multiples)
 
 
+class _Immutable(np.ndarray):
+    """TF tensors are immutable: ``x += y`` rebinds x to a new (broadcast) tensor, it never writes
+    in place (surrogate_synth.py:91 relies on it: [B, N, 1] += [B, N, H])."""
+
+    def __iadd__(self, other):
+        return np.add(self, other)
+
+    def __imul__(self, other):
+        return np.multiply(self, other)
+
+
 def repeat(x, repeats, axis=None):
-    return np.repeat(x, repeats, axis=axis)
+    return np.repeat(x, repeats, axis=axis).view(_Immutable)
 
 
 def transpose(x, perm=None):
@@ -182,3 +204,20 @@ def _batch_diag(x):
 linalg = types.SimpleNamespace(diag=_batch_diag, inv=np.linalg.inv)
 signal = types.SimpleNamespace(irfft=lambda x: np.fft.irfft(x).astype(np.float32))
 keras.activations = types.SimpleNamespace(sigmoid=lambda x: 1.0 / (1.0 + np.exp(-x)))
+
+
+# ---- symbols used by modules/surrogate_synth.py (executed for tests/golden/surrogate_*.npz) ------
+newaxis = None
+
+
+def where(cond, x, y):
+    return np.where(cond, x, y)
+
+
+def greater_equal(a, b):
+    a = np.asarray(a)
+    return a >= (a.dtype.type(b) if np.isscalar(b) else b)
+
+
+def ones_like(x, dtype=None):
+    return np.ones_like(x, dtype=dtype)

@@ -161,6 +161,32 @@ def test_additive_every_half_group_bucket(dp, dev, H, inference, held):
         assert rel_err(got[b], want[b]) < 5 * TIGHT, (b, live[b])
 
 
+@pytest.mark.parametrize('name', ['surrogate_16k', 'surrogate_24k_h40'])
+def test_surrogate_additive_golden(dp, dev, golden_dir, name):
+    """SurrogateAdditive (modules/surrogate_synth.py) against the vectors produced by executing the
+    reference's own module (tests/golden/make_golden_surrogate.py): decays clipped to [1e-5, 1] and
+    forced to 1 above Nyquist, amplitudes multiplied by |decay|^(decay_time U + r)."""
+    g = load(golden_dir, name)
+    synth = dp.SurrogateAdditive(frame_rate=250, sample_rate=int(g['sample_rate']), inference=True,
+                                 name='inharmonic')
+    args = [cu(g['in_' + k], dev) for k in ('amplitudes', 'decays', 'decay_time', 'harmonic_distribution',
+                                             'inharm_coef', 'f0_hz')]
+    out = synth(*args, return_outputs_dict=True)
+    np.testing.assert_array_equal(out['controls']['decays'].cpu().numpy(), g['ctl_decays'])
+    assert rel_err(out['controls']['harmonic_distribution'], g['ctl_harmonic_distribution']) < 2e-6
+    assert rel_err(out['signal'], g['signal']) < TIGHT
+    # without decays it is the plain inharmonic bank
+    plain = synth.get_signal(out['controls']['amplitudes'], None, None,
+                             out['controls']['harmonic_distribution'],
+                             out['controls']['harmonic_shifts'], out['controls']['f0_hz'])
+    want = ref.additive_signal(g['ctl_amplitudes'], g['ctl_harmonic_distribution'],
+                               g['ctl_harmonic_shifts'], g['ctl_f0_hz'],
+                               sample_rate=int(g['sample_rate']), inference=True)
+    assert rel_err(plain, want) < TIGHT
+    with pytest.raises(ValueError):
+        dp.SurrogateAdditive(sample_rate=int(g['sample_rate']), inference=False)(*args)
+
+
 def test_additive_known_answers(dp, dev):
     """SURVEY 8c KATs 2-4, 6 on the CUDA path."""
     sr, F, H = 24000, 30, 8

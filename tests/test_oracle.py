@@ -257,3 +257,19 @@ def test_fdn_restatement_matches_reference_python(golden_dir, name):
     np.testing.assert_array_equal(sig, g['signal'])
     # the early FIR is the head of the response; the late part decays
     assert np.max(np.abs(ir[-200:])) < 0.2 * np.max(np.abs(ir))
+
+
+@pytest.mark.parametrize('name', ['surrogate_16k', 'surrogate_24k_h40'])
+def test_surrogate_restatement_matches_reference_execution(golden_dir, name):
+    """SurrogateAdditive (surrogate_synth.py), goldens from tests/golden/make_golden_surrogate.py:
+    the restatement reproduces the reference-executed controls and signal bit for bit."""
+    g = load(golden_dir, name)
+    sr = int(g['sample_rate'])
+    ctl = ref.surrogate_controls(g['in_amplitudes'], g['in_decays'], g['in_decay_time'],
+                                 g['in_harmonic_distribution'], g['in_inharm_coef'], g['in_f0_hz'],
+                                 sample_rate=sr)
+    for k, v in ctl.items():
+        np.testing.assert_array_equal(np.asarray(v, np.float32), g['ctl_' + k], err_msg=k)
+    assert np.all((g['ctl_decays'] >= 1e-5) & (g['ctl_decays'] <= 1.0))
+    sig = ref.surrogate_signal(**ctl, sample_rate=sr, inference=True)
+    np.testing.assert_array_equal(sig, g['signal'])
