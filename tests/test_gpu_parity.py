@@ -680,7 +680,8 @@ def test_full_size_properties(dp, dev, full_size):
 
 
 @pytest.mark.parametrize('P,B,F,host', [(1, 1, 1, False), (1, 2, 7, True), (3, 1, 40, True),
-                                        (5, 2, 33, False), (16, 1, 11, True)])
+                                        (5, 2, 33, False), (16, 1, 11, True), (5, 1, 20, True),
+                                        (7, 2, 9, True)])
 def test_dag_edge_shapes(dp, dev, P, B, F, host):
     """Smallest and ragged shapes (one voice, one frame, F not a multiple of the 32-frame noise tile,
     P not a multiple of the voice groups / noise slices), device and host entry points vs oracle."""
