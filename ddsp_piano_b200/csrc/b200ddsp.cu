@@ -44,7 +44,7 @@ struct b200ddsp_handle {
   cudaStream_t noise_stream = nullptr;  // the noise synth runs beside the oscillator bank
   cudaEvent_t ev_noise_fork = nullptr, ev_noise_join = nullptr;
   cudaStream_t hd_stream = nullptr;     // harmonic_distribution controls run beside the phase pass
-  cudaEvent_t ev_hd_fork = nullptr, ev_hd_done[8] = {};
+  cudaEvent_t ev_hd_fork = nullptr, ev_hd_done[8] = {}, ev_ir_spectra = nullptr;
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_mags[4] = {}, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
@@ -288,6 +288,7 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
     ok = ok && cudaEventCreateWithFlags(&h->ev_noise_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->hd_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_hd_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_ir_spectra, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i)
       ok = cudaEventCreateWithFlags(&h->ev_hd_done[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4 && ok; ++i)
@@ -334,6 +335,7 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->ev_noise_join) cudaEventDestroy(h->ev_noise_join);
   if (h->hd_stream) cudaStreamDestroy(h->hd_stream);
   if (h->ev_hd_fork) cudaEventDestroy(h->ev_hd_fork);
+  if (h->ev_ir_spectra) cudaEventDestroy(h->ev_ir_spectra);
   for (int i = 0; i < 8; ++i)
     if (h->ev_hd_done[i]) cudaEventDestroy(h->ev_hd_done[i]);
   for (int i = 0; i < kMaxGroups - 1; ++i) {
@@ -460,8 +462,10 @@ static WorkspaceLayout carve(const b200ddsp_handle* h, int P, int B, int F, int 
   if (L > 0) {
     w.nfft = fft_size_for((int)N, L);
     w.tw = take((size_t)w.nfft * 8 + (size_t)B * 32);   // twiddles + per-clip scales + maxima
-    w.buf_a = take((size_t)B * w.nfft * 8);
-    w.buf_b = take((size_t)B * w.nfft * 8);
+    // B + 1 rows: the split reverb keeps the IR spectra in the first ceil(B/2) rows and works on the
+    // dry signal in the next ceil(B/2)
+    w.buf_a = take((size_t)(B + 1) * w.nfft * 8);
+    w.buf_b = take((size_t)(B + 1) * w.nfft * 8);
   }
   w.total = o;
   return w;
@@ -1177,6 +1181,93 @@ static int run_reverb(b200ddsp_handle* h, const float* audio, const float* ir, f
   return B200DDSP_OK;
 }
 
+// The same convolution in two phases for the polyphonic forward (reverb.cuh, "split form").
+// Phase 1 (needs the impulse responses only): twiddles, IR scales, forward transforms of IR pairs
+// into rows [0, pairs) of the ping-pong buffers; returns where the spectra ended up.
+static int run_reverb_ir_phase(b200ddsp_handle* h, const float* ir, int B, int N, int L, float2* tw,
+                               float2* buf_a, float2* buf_b, const float2** ir_spectra,
+                               cudaStream_t st) {
+  const int n = fft_size_for(N, L);
+  const std::vector<int> radices = fft_radices(n);
+  const int pairs = (B + 1) / 2;
+  fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
+  CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  float4* scales = reinterpret_cast<float4*>(tw + n);
+  unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);
+  CUDA_TRY(h, cudaMemsetAsync(maxima, 0, (size_t)B * 8, st));
+  reverb_maxima1_kernel<<<dim3(32, B), 256, 0, st>>>(ir, maxima, L, 1, 1);
+  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);   // audio part still 1
+  CHECK_LAUNCH(h, "reverb_scales_kernel");
+  float2* src = nullptr;
+  float2* dst = buf_a;
+  int Ns = 1;
+  for (size_t i = 0; i < radices.size(); ++i) {
+    const StoreComplex sto{dst, n};
+    if (i == 0) launch_fft_pass(radices[i], LoadRealPair{ir, scales, L, 1, B, 1}, sto, tw, n, Ns, pairs, st);
+    else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, pairs, st);
+    CHECK_LAUNCH(h, "fft_pass_kernel<ir>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == buf_a) ? buf_b : buf_a;
+  }
+  *ir_spectra = src;
+  return B200DDSP_OK;
+}
+
+// Phase 2 (the tail of the forward): dry pairs -> spectra, product with the IR spectra, inverse.
+static int run_reverb_audio_phase(b200ddsp_handle* h, const float* audio, const float2* ir_spectra,
+                                  float* out, int B, int N, int L, float2* tw, float2* buf_a,
+                                  float2* buf_b, cudaStream_t st) {
+  StageTimer tm(h, B200DDSP_STAGE_REVERB, st);
+  const int n = fft_size_for(N, L);
+  const std::vector<int> radices = fft_radices(n);
+  const int n_pass = (int)radices.size();
+  const int pairs = (B + 1) / 2;
+  float4* scales = reinterpret_cast<float4*>(tw + n);
+  unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);
+  reverb_maxima1_kernel<<<dim3(32, B), 256, 0, st>>>(audio, maxima, N, 0, 0);
+  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);
+  CHECK_LAUNCH(h, "reverb_scales_kernel");
+  float2* wa = buf_a + (size_t)pairs * n;   // rows [pairs, 2 pairs) of both buffers
+  float2* wb = buf_b + (size_t)pairs * n;
+  float2* src = nullptr;
+  float2* dst = wa;
+  int Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const StoreComplex sto{dst, n};
+    if (i == 0) launch_fft_pass(radices[i], LoadRealPair{audio, scales, N, 0, B, 0}, sto, tw, n, Ns, pairs, st);
+    else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, pairs, st);
+    CHECK_LAUNCH(h, "fft_pass_kernel<forward>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  {
+    dim3 grid((n / 2 + 1 + 255) / 256, pairs);
+    reverb_spectrum_split_kernel<<<grid, 256, 0, st>>>(src, ir_spectra, dst, n);
+    CHECK_LAUNCH(h, "reverb_spectrum_split_kernel");
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const LoadComplex ld{src, n};
+    if (i == n_pass - 1) {
+      const StoreWetPair sto{out, audio, scales, N, N, B, 1.0f / (float)n, h->cfg.reverb_add_dry ? 1 : 0};
+      launch_fft_pass(radices[i], ld, sto, tw, n, Ns, pairs, st);
+    } else {
+      launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, tw, n, Ns, pairs, st);
+    }
+    CHECK_LAUNCH(h, "fft_pass_kernel<inverse>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  return B200DDSP_OK;
+}
+
 static int reverb_entry(b200ddsp_handle* h, const float* audio, const float* ir, float* out,
                         int B, int N, int L, void* workspace, size_t workspace_bytes,
                         void* stream, int flags) {
@@ -1387,6 +1478,17 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     CHECK_LAUNCH(h, "additive_hd_kernel");
     CUDA_TRY(h, cudaEventRecord(h->ev_hd_done[g], h->hd_stream));
   }
+  // the impulse responses are known now, the dry signal only at the very end: their spectra are
+  // prepared on the same side stream, which leaves the tail with 8 + 8 transforms instead of 16 + 8
+  static const int reverb_split = env_int("B200DDSP_REVERB_SPLIT", 1);
+  const float2* ir_spectra = nullptr;
+  if (reverb_ir && reverb_split) {
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(h->hd_stream, sync->ir_ready, 0));
+    if (int rc = run_reverb_ir_phase(h, reverb_ir, B, N, L, (float2*)(base + w.tw), (float2*)(base + w.buf_a),
+                                     (float2*)(base + w.buf_b), &ir_spectra, h->hd_stream))
+      return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_ir_spectra, h->hd_stream));
+  }
 
   // 1. everything that does not need harmonic_distribution: amplitudes, inharmonic shifts,
   //    liveness, then the phase pass of ALL voices (chunk end phases -> chunk offsets)
@@ -1419,6 +1521,11 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   }
   if (int rc = run_mix(h, noise_part, n_slices, &mix, dry_out, B, N, 0, st)) return rc;
   // 4. reverb -> wet
+  if (reverb_ir && ir_spectra) {
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ir_spectra, 0));
+    return run_reverb_audio_phase(h, dry_out, ir_spectra, wet_out, B, N, L, (float2*)(base + w.tw),
+                                  (float2*)(base + w.buf_a), (float2*)(base + w.buf_b), st);
+  }
   if (reverb_ir) {
     if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->ir_ready, 0));
     return run_reverb(h, dry_out, reverb_ir, wet_out, B, N, L, (float2*)(base + w.tw),

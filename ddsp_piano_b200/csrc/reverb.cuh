@@ -201,6 +201,64 @@ struct StoreWetPair {
   }
 };
 
+// ---- split form: impulse responses first, audio later ---------------------------------------------
+// Inside the polyphonic forward the impulse responses are known from the start while the dry signal
+// exists only at the very end, so the forward transforms of the IRs (two real IRs per complex
+// transform) run early on a side stream and the tail of the forward is left with 8 + 8 transforms
+// (two dry clips per forward transform, two wet clips per inverse) instead of 16 + 8.
+// maxima[2 b + which]: which = 0 audio, 1 impulse response (entries zeroed beforehand).
+__global__ void __launch_bounds__(256) reverb_maxima1_kernel(const float* __restrict__ x,
+                                                             unsigned int* __restrict__ maxima, int len,
+                                                             int first, int which) {
+  const int b = blockIdx.y;
+  const int stride = gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+    m = fmaxf(m, fabsf(__ldg(x + (size_t)b * len + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxima + 2 * b + which, __float_as_uint(m));
+}
+
+// z = x[2 pair] * s + i * x[2 pair + 1] * s', zero padded; which selects the audio (.x) or the
+// impulse-response (.y) scale of each clip; first = 1 masks tap 0 (Reverb._mask_dry_ir)
+struct LoadRealPair {
+  const float* x; const float4* scales; int len, first, B, which;
+  __device__ __forceinline__ float2 operator()(int pair, int i) const {
+    const int b0 = 2 * pair, b1 = b0 + 1;
+    if (i < first || i >= len) return make_float2(0.f, 0.f);
+    const float4 s0 = __ldg(scales + b0);
+    const float re = __ldg(x + (size_t)b0 * len + i) * (which ? s0.y : s0.x);
+    float im = 0.f;
+    if (b1 < B) {
+      const float4 s1 = __ldg(scales + b1);
+      im = __ldg(x + (size_t)b1 * len + i) * (which ? s1.y : s1.x);
+    }
+    return make_float2(re, im);
+  }
+};
+
+// Za = FFT(a0 + i a1), Zh = FFT(h0 + i h1) of one pair of clips -> V[k] = conj Y0[k] + i conj Y1[k],
+// Y0 = A0 H0, Y1 = A1 H1 (the real signals separated by Hermitian symmetry).
+__global__ void __launch_bounds__(256) reverb_spectrum_split_kernel(const float2* __restrict__ Za,
+                                                                     const float2* __restrict__ Zh,
+                                                                     float2* __restrict__ V, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. n/2
+  const int pair = blockIdx.y;
+  if (k > n / 2) return;
+  const int kn = (n - k) & (n - 1);
+  const float2 za = Za[(size_t)pair * n + k], wa = Za[(size_t)pair * n + kn];
+  const float2 zh = Zh[(size_t)pair * n + k], wh = Zh[(size_t)pair * n + kn];
+  // even part -> first signal, odd part / i -> second signal
+  const float2 A0 = make_float2(0.5f * (za.x + wa.x), 0.5f * (za.y - wa.y));
+  const float2 A1 = make_float2(0.5f * (za.y + wa.y), -0.5f * (za.x - wa.x));
+  const float2 H0 = make_float2(0.5f * (zh.x + wh.x), 0.5f * (zh.y - wh.y));
+  const float2 H1 = make_float2(0.5f * (zh.y + wh.y), -0.5f * (zh.x - wh.x));
+  const float2 y0 = cmul(A0, H0), y1 = cmul(A1, H1);
+  V[(size_t)pair * n + k] = make_float2(y0.x + y1.y, y1.x - y0.y);
+  if (kn != k) V[(size_t)pair * n + kn] = make_float2(y0.x - y1.y, y0.y + y1.x);
+}
+
 // One Stockham pass of radix R: sub-transforms of length Ns -> Ns*R.
 template <int R, class Loader, class Storer>
 __global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const Loader ld, const Storer st,
