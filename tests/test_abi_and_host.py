@@ -274,3 +274,34 @@ def test_midi_roll_shape_errors(lib_path):
         MIDIRoll2Conditioning(16)(np.zeros([10, 8, 2], np.float32))
     cond, poly = MIDIRoll2Conditioning(16)(np.zeros([0, 88, 2], np.float32))
     assert cond.shape == (0, 16, 2) and poly.shape == (0,)
+
+
+# ------------------------------- bench helpers (host logic) -------------------------------------
+
+def test_bench_live_chain_samples_matches_brute_force():
+    """bench.live_chain_samples restates the kernels' liveness bookkeeping (16-partial half-groups,
+    maximum over the frames a 1000-sample chunk touches, both substrings on every lane)."""
+    import bench
+    w = dict(P=2, B=2, F=30, H=40, S=2, sr=24000)
+    rng = np.random.default_rng(3)
+    f0 = np.empty([2, 2, 30, 2], np.float32)
+    f0[..., 0] = np.array([[110.0, 8.1758], [1500.0, 440.0]], np.float32)[:, :, None]
+    f0[1, 1, 15:, 0] = 3000.0                            # a pitch change inside the clip
+    f0[..., 1] = f0[..., 0] * 1.001
+    x = {'f0_hz': f0, 'inharm_coef': rng.uniform(1e-4, 1e-3, [2, 2, 30, 1]).astype(np.float32)}
+    U, N = 96, 30 * 96
+    n = np.arange(1, 41)
+    total = 0
+    for v in range(2):
+        for b in range(2):
+            live = np.zeros(30, int)
+            for k in range(30):
+                fk, bk = float(f0[v, b, k, 0]), float(x['inharm_coef'][v, b, k, 0])
+                ok = (fk * n * np.sqrt(1 + bk * n * n) < 12000.0) & (fk > 20.0)
+                live[k] = 0 if not ok.any() else -(-(int(np.max(np.nonzero(ok)[0])) + 1) // 16)
+            for t0 in range(0, N, 1000):
+                t1 = min(N, t0 + 1000) - 1
+                nh = live[t0 // U:min(29, t1 // U + 1) + 1].max()
+                total += int(nh) * 32 * (t1 + 1 - t0)
+    assert bench.live_chain_samples(w, x) == total
+    assert bench.bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3)   # never raises without a GPU
