@@ -1,0 +1,102 @@
+"""MIDI file front end (ddsp_piano_b200/midi.py, reference utils/io_utils.py:77-137) on files written
+by the test itself.  note_seq / pretty_midi are absent: the conventions are restated (parity
+unpinned) and what is tested here is the file format, the tempo map and the stated conventions."""
+import struct
+
+import numpy as np
+import pytest
+
+from ddsp_piano_b200 import midi
+
+
+def vlq(n):
+    out = [n & 0x7f]
+    n >>= 7
+    while n:
+        out.append((n & 0x7f) | 0x80)
+        n >>= 7
+    return bytes(reversed(out))
+
+
+def write_smf(path, tracks, division=480, fmt=1):
+    """tracks: lists of (absolute tick, bytes of the event without delta time)."""
+    chunks = b''
+    for tr in tracks:
+        body, last = b'', 0
+        for tick, ev in sorted(tr, key=lambda e: e[0]):
+            body += vlq(tick - last) + ev
+            last = tick
+        body += vlq(0) + b'\xff\x2f\x00'
+        chunks += b'MTrk' + struct.pack('>I', len(body)) + body
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, fmt, len(tracks), division) + chunks)
+
+
+def on(p, v, ch=0): return bytes([0x90 | ch, p, v])
+def off(p, ch=0): return bytes([0x80 | ch, p, 0])
+def cc(n, v, ch=0): return bytes([0xb0 | ch, n, v])
+def tempo(us): return b'\xff\x51\x03' + us.to_bytes(3, 'big')
+
+
+def test_read_midi_tempo_map_and_note_pairing(tmp_path):
+    path = str(tmp_path / 'a.mid')
+    # 480 ticks per quarter; 120 bpm for one quarter (0.5 s), then 60 bpm (1 s per quarter)
+    write_smf(path, [[(0, tempo(500000)), (480, tempo(1000000))],
+                     [(0, on(60, 100)), (480, off(60)), (480, on(64, 80)), (960, on(64, 0)),   # vel 0 = off
+                      (240, cc(64, 127)), (1200, cc(64, 0))]])
+    notes, ccs, end = midi.read_midi(path)
+    assert [[round(x, 6) for x in n[:2]] + n[2:] for n in notes] == [[0.0, 0.5, 60, 100], [0.5, 1.5, 64, 80]]
+    assert [[round(c[0], 6)] + c[1:] for c in ccs] == [[0.25, 64, 127], [2.0, 64, 0]]
+    assert abs(end - 2.0) < 1e-9
+
+
+def test_running_status_and_format_0(tmp_path):
+    path = str(tmp_path / 'b.mid')
+    body = vlq(0) + on(60, 90) + vlq(240) + bytes([62, 70]) + vlq(240) + off(60) + vlq(0) + off(62) + \
+        vlq(0) + b'\xff\x2f\x00'
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 0, 1, 480) + b'MTrk' + struct.pack('>I', len(body)) + body)
+    notes, _, _ = midi.read_midi(path)
+    assert [(n[2], n[3], round(n[0], 6), round(n[1], 6)) for n in notes] == [(60, 90, 0.0, 0.5), (62, 70, 0.25, 0.5)]
+
+
+def test_sustain_pedal_extends_notes():
+    notes = [[0.0, 0.2, 60, 100], [0.5, 0.6, 60, 90], [0.1, 0.3, 64, 80]]
+    ccs = [[0.05, 64, 127], [1.0, 64, 0]]
+    out, total = midi.apply_sustain_control_changes(notes, ccs)
+    by = {(n[2], n[0]): n[1] for n in out}
+    assert by[(60, 0.0)] == 0.5            # rings on the pedal until the same pitch is struck again
+    assert by[(60, 0.5)] == 1.0            # ... or until the pedal comes up
+    assert by[(64, 0.1)] == 1.0
+    assert total == 1.0
+    out2, _ = midi.apply_sustain_control_changes(notes, [])
+    assert sorted(n[1] for n in out2) == [0.2, 0.3, 0.6]
+
+
+def test_pianoroll_conventions():
+    notes = [[0.1, 0.2, 60, 127], [0.1004, 0.1008, 21, 64], [0.0, 1.0, 20, 100]]   # pitch 20 is out of range
+    active, onset, ccs = midi.sequence_to_pianoroll(notes, [[0.3, 64, 127], [0.3, 67, 0]], 1.0, 250)
+    assert active.shape == (251, 88) and ccs.shape == (251, 128)
+    assert active[:, 60 - 21].nonzero()[0].tolist() == list(range(25, 50))
+    assert active[:, 0].nonzero()[0].tolist() == [25]                              # at least one frame
+    assert onset[:, 60 - 21].nonzero()[0].tolist() == [24, 25, 26] and onset[25, 39] == 1.0
+    assert abs(onset[25, 0] - 64 / 127) < 1e-7
+    assert ccs[75, 64] == 128 and ccs[75, 67] == 1 and ccs.sum() == 129            # value + 1 on the event frame
+
+
+def test_load_midi_as_conditioning_shapes(tmp_path):
+    path = str(tmp_path / 'c.mid')
+    write_smf(path, [[(0, tempo(500000)), (0, on(60, 100)), (0, on(64, 100)), (960, off(60)), (960, off(64)),
+                      (480, cc(64, 100)), (1440, cc(64, 0))]])
+    x = midi.load_midi_as_conditioning(path, n_synths=16, frame_rate=250, warm_up_duration=0.5)
+    assert x['conditioning'].shape == (1, 2 * 250 + 125, 16, 2) and x['pedal'].shape == (1, 625, 4)
+    assert x['duration'] == 2.5
+    pitches = x['conditioning'][0, 125 + 10, :, 0]
+    assert sorted(pitches[pitches > 0].tolist()) == [60.0, 64.0]
+    assert np.all(x['conditioning'][0, :125] == 0)                                  # warm-up padding
+    held = x['conditioning'][0, 125 + 300, :, 0]                                    # 1.2 s: pedal still down
+    assert sorted(held[held > 0].tolist()) == [60.0, 64.0]
+    assert np.all(x['conditioning'][0, 125 + 380:, :, 0] == 0)                      # pedal up at 1.5 s
+    assert x['pedal'][0, 125 + 125, 0] == pytest.approx(101 / 128)
+    fixed = midi.load_midi_as_conditioning(path, duration=1.0)
+    assert fixed['conditioning'].shape == (1, 250, 16, 2)

@@ -265,3 +265,48 @@ def test_v2_midi_to_audio(v2_weights):
     assert abs(peak_hz - 440.0) < 4.0, peak_hz
     wet_tail = audio[0, 700 * U:]
     assert rms(wet_tail) > rms(after)                   # the reverb rings on after the dry decay
+
+
+@pytest.mark.gpu
+def test_midi_file_to_audio(weights, tmp_path):
+    """The reference's synthesize_midi_file.py path without note_seq / TensorFlow: a MIDI file
+    written here (A4 held for 1 s with the sustain pedal down) -> load_midi_as_conditioning ->
+    PianoModel (shipped dafx22 weights) -> audio; the spectrum peaks at 440 Hz and the note keeps
+    ringing on the pedal after its note-off."""
+    import struct
+    import ddsp_piano_b200 as dp
+    from ddsp_piano_b200 import midi
+
+    def vlq(n):
+        out = [n & 0x7f]
+        n >>= 7
+        while n:
+            out.append((n & 0x7f) | 0x80)
+            n >>= 7
+        return bytes(reversed(out))
+
+    events = [(0, b'\xff\x51\x03' + (500000).to_bytes(3, 'big')), (0, bytes([0xb0, 64, 127])),
+              (480, bytes([0x90, 69, 100])), (1440, bytes([0x80, 69, 0])), (2400, bytes([0xb0, 64, 0]))]
+    body, last = b'', 0
+    for tick, ev in events:
+        body += vlq(tick - last) + ev
+        last = tick
+    body += vlq(0) + b'\xff\x2f\x00'
+    path = str(tmp_path / 'a4.mid')
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 0, 1, 480) + b'MTrk' + struct.pack('>I', len(body)) + body)
+    x = midi.load_midi_as_conditioning(path, n_synths=16, frame_rate=250, warm_up_duration=0.5)
+    assert x['conditioning'].shape[1] == int(3 * 250 + 125)
+    model = dp.dafx22_model(weights, device='cuda:0', sample_rate=16000, inference=True)
+    out = model({'conditioning': x['conditioning'], 'pedal': x['pedal'],
+                 'piano_model': np.zeros([1, 1], np.int64)})
+    dry = out['add']['signal'].cpu().numpy()[0]
+    U = 64
+    note = dry[(125 + 130) * U:(125 + 370) * U]          # 0.5 s + note-on at 0.5 s
+    n = 8192
+    spec = np.abs(np.fft.rfft(note[1024:1024 + n] * np.hanning(n), 4 * n))
+    assert abs(np.argmax(spec) * 16000 / (4 * n) - 440.0) < 3.0
+    rms = lambda v: float(np.sqrt(np.mean(v.astype(np.float64) ** 2)))
+    pedal_tail = dry[(125 + 400) * U:(125 + 600) * U]    # after the note-off (1.5 s), pedal down until 2.5 s
+    after = dry[(125 + 700) * U:]
+    assert rms(pedal_tail) > 3 * rms(after)
