@@ -100,3 +100,53 @@ def test_load_midi_as_conditioning_shapes(tmp_path):
     assert x['pedal'][0, 125 + 125, 0] == pytest.approx(101 / 128)
     fixed = midi.load_midi_as_conditioning(path, duration=1.0)
     assert fixed['conditioning'].shape == (1, 250, 16, 2)
+
+
+def _script():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts', 'synthesize_midi_file.py')
+    spec = importlib.util.spec_from_file_location('synthesize_midi_file', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_script_arguments_wav_and_normalisation(tmp_path):
+    """scripts/synthesize_midi_file.py: the reference's argument list (synthesize_midi_file.py:12-36),
+    the 16-bit wav writer and the dBFS normalisation (io_utils.py:245-253)."""
+    import wave
+    s = _script()
+    a = s.process_args(['in.mid', 'out.wav'])
+    assert (a.model, a.piano_type, a.warm_up, a.duration, a.normalize, a.unreverbed) == ('v2', 9, 0.5, None, None, False)
+    a = s.process_args(['-m', 'dafx22', '-wu', '0', '-d', '3', '-n', '-20', '-u', '--piano_type', '2', 'in.mid', 'out.wav'])
+    assert (a.model, a.piano_type, a.warm_up, a.duration, a.normalize, a.unreverbed) == ('dafx22', 2, 0.0, 3.0, -20.0, True)
+    t = np.arange(2400, dtype=np.float32) / 24000
+    x = (0.25 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    y = s.normalize_dbfs(x, -20.0)
+    assert abs(20 * np.log10(np.sqrt(np.mean(y.astype(np.float64) ** 2))) + 20.0) < 1e-4
+    assert s.normalize_dbfs(np.zeros(8, np.float32), -20.0).tolist() == [0.0] * 8
+    path = str(tmp_path / 'o.wav')
+    s.write_wav(path, np.array([0.0, 0.5, -0.5, 2.0, -2.0], np.float32), 24000)
+    with wave.open(path, 'rb') as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 24000, 5)
+        assert np.frombuffer(f.readframes(5), '<i2').tolist() == [0, 16384, -16384, 32767, -32768]
+
+
+@pytest.mark.gpu
+def test_script_midi_file_to_wav(tmp_path):
+    """The whole config-1 path as a user runs it: MIDI file -> wav (reverberated and dry) with the shipped
+    v2 weights, piano 9, 0.5 s warm-up cut from the output."""
+    import wave
+    s = _script()
+    mid, out = str(tmp_path / 'a4.mid'), str(tmp_path / 'a4.wav')
+    write_smf(mid, [[(0, tempo(500000)), (0, on(69, 100)), (960, off(69))]])
+    s.main(s.process_args(['-u', '-n', '-20', mid, out]))
+    for path in (out, out + '_unreverbed.wav'):
+        with wave.open(path, 'rb') as f:
+            assert (f.getframerate(), f.getnframes()) == (24000, 24000)
+            x = np.frombuffer(f.readframes(24000), '<i2').astype(np.float64) / 32768
+        assert abs(20 * np.log10(np.sqrt(np.mean(x ** 2))) + 20.0) < 0.5
+        n = 8192
+        spec = np.abs(np.fft.rfft(x[2048:2048 + n] * np.hanning(n), 4 * n))
+        assert abs(np.argmax(spec) * 24000 / (4 * n) - 440.0) < 4.0
