@@ -43,8 +43,14 @@ class MIDIRoll2Conditioning:
 # extends notes over the sustain pedal (note_seq.apply_sustain_control_changes) and rasterises with
 # note_seq.sequences_lib.sequence_to_pianoroll.  note_seq / pretty_midi are not in the container, so
 # their behaviour is RESTATED here from the published sources and is parity unpinned (DESIGN.md
-# section 7): Standard MIDI File parsing and the tempo map are fixed by the file format; the
-# restated conventions that matter for the model input are spelled out where they are applied.
+# section 7): Standard MIDI File parsing is fixed by the file format; the restated conventions that
+# matter for the model input (which track carries the tempo map, the float64 operation order of the
+# tick -> seconds table, how notes are paired and grouped into instruments, the order in which equal-time
+# events are processed, frame rounding) are spelled out where they are applied.
+#
+# A note is [start_s, end_s, pitch, velocity, instrument]; a control change is
+# [time_s, number, value, instrument]; both lists are in note_seq's sequence order (instrument by
+# instrument, each in file order).
 
 def _vlq(data, pos):
     value = 0
@@ -56,27 +62,24 @@ def _vlq(data, pos):
             return value, pos
 
 
-def read_midi(path):
-    """Standard MIDI File (format 0/1, metrical time) -> (notes, control_changes, end_time):
-    notes = [[start_s, end_s, pitch, velocity]], control_changes = [[time_s, number, value]].
-    pretty_midi conventions: note-on with velocity 0 is a note-off; a note-off closes every open
-    note-on of its (channel, pitch) that started on an earlier tick; tempo events of any track
-    apply to all tracks; end_time = the last note end / control change."""
+def _parse_tracks(data, path):
+    """Standard MIDI File chunks -> (division, [[(absolute tick, kind, channel, d1, d2)] per track]);
+    kind in 'on' / 'off' / 'cc' / 'program' / 'tempo' (tempo: d1 = microseconds per quarter)."""
     import struct
-    with open(path, 'rb') as f:
-        data = f.read()
     if data[:4] != b'MThd':
         raise ValueError(f'{path}: not a Standard MIDI File')
-    hlen, fmt, n_tracks, division = struct.unpack('>IHHH', data[4:14])
+    hlen, _, n_tracks, division = struct.unpack('>IHHH', data[4:14])
     if division & 0x8000:
-        raise ValueError('SMPTE time division is not supported')
-    pos = 8 + hlen
-    events, tempi = [], [(0, 500000)]                  # (tick, kind, a, b, c); default 120 bpm
+        raise ValueError(f'{path}: SMPTE time division is not supported')
+    pos, tracks = 8 + hlen, []
+    data_bytes = {0x80: 2, 0x90: 2, 0xa0: 2, 0xb0: 2, 0xc0: 1, 0xd0: 1, 0xe0: 2}
     for _ in range(n_tracks):
         if data[pos:pos + 4] != b'MTrk':
-            raise ValueError('corrupt track chunk')
+            raise ValueError(f'{path}: corrupt track chunk')
         tlen = struct.unpack('>I', data[pos + 4:pos + 8])[0]
-        p, end, tick, status = pos + 8, pos + 8 + tlen, 0, 0
+        p, end, tick, status, events = pos + 8, pos + 8 + tlen, 0, 0, []
+        if end > len(data):
+            raise ValueError(f'{path}: truncated track chunk')
         while p < end:
             delta, p = _vlq(data, p)
             tick += delta
@@ -85,122 +88,176 @@ def read_midi(path):
                 kind = data[p + 1]
                 n, p = _vlq(data, p + 2)
                 if kind == 0x51 and n == 3:
-                    tempi.append((tick, int.from_bytes(data[p:p + 3], 'big')))
+                    events.append((tick, 'tempo', 0, int.from_bytes(data[p:p + 3], 'big'), 0))
                 p += n
             elif b in (0xf0, 0xf7):                    # sysex
                 n, p = _vlq(data, p + 1)
                 p += n
+            elif b >= 0xf1:                            # system common / real time (not valid in files)
+                p += 1 + {0xf1: 1, 0xf2: 2, 0xf3: 1}.get(b, 0)
             else:
                 if b & 0x80:
                     status = b
                     p += 1
                 kind, channel = status & 0xf0, status & 0x0f
-                if kind in (0xc0, 0xd0):
-                    p += 1
-                else:
-                    d1, d2 = data[p], data[p + 1]
-                    p += 2
-                    if kind == 0x90 and d2 > 0:
-                        events.append((tick, 'on', channel, d1, d2))
-                    elif kind == 0x80 or kind == 0x90:
-                        events.append((tick, 'off', channel, d1, 0))
-                    elif kind == 0xb0:
-                        events.append((tick, 'cc', channel, d1, d2))
+                if kind not in data_bytes:
+                    raise ValueError(f'{path}: data byte without a running status')
+                d1 = data[p]
+                d2 = data[p + 1] if data_bytes[kind] == 2 else 0
+                p += data_bytes[kind]
+                if kind == 0x90 and d2 > 0:
+                    events.append((tick, 'on', channel, d1, d2))
+                elif kind == 0x80 or kind == 0x90:     # note-on with velocity 0 is a note-off
+                    events.append((tick, 'off', channel, d1, 0))
+                elif kind == 0xb0:
+                    events.append((tick, 'cc', channel, d1, d2))
+                elif kind == 0xc0:
+                    events.append((tick, 'program', channel, d1, 0))
+        tracks.append(events)
         pos = end
-    # tempo map: seconds at each tempo change
-    tempi = sorted(set(tempi))
-    marks, t = [], 0.0
-    for i, (tk, us) in enumerate(tempi):
+    return division, tracks
+
+
+def read_midi(path):
+    """Standard MIDI File (format 0/1, metrical time) -> (notes, control_changes, total_time), what
+    note_seq.midi_file_to_note_sequence holds after pretty_midi.PrettyMIDI(file).  Conventions:
+
+    * the tempo map is read from track 0 only; a tempo event at tick 0 replaces the 120 bpm default, a later
+      one opens a new interval unless its scale repeats the last one; seconds(tick) =
+      seconds(interval start) + scale * (tick - interval start) with scale = 60 / ((6e7 / us) * division),
+      in float64 in that order (frame rounding downstream depends on the last bit);
+    * a note-off closes every open note-on of its (channel, pitch) in its track that started on an earlier
+      tick; notes struck on the very tick of the note-off stay open;
+    * an instrument is a (program, channel, track) triple in order of first note END; control changes
+      seen on a (channel, track) before its first note join that instrument, those of (channel, track)
+      pairs without any note are dropped;
+    * total_time = the latest note end (control changes do not extend it)."""
+    with open(path, 'rb') as f:
+        data = f.read()
+    division, tracks = _parse_tracks(data, path)
+    scales = [(0, 60.0 / (120.0 * division))]
+    for tick, kind, _, us, _ in (tracks[0] if tracks else []):
+        if kind != 'tempo':
+            continue
+        scale = 60.0 / ((6e7 / us) * division)
+        if tick == 0:
+            scales = [(0, scale)]
+        elif scale != scales[-1][1]:
+            scales.append((tick, scale))
+    starts, t = [], 0.0
+    for i, (tk, scale) in enumerate(scales):
         if i:
-            t += (tk - tempi[i - 1][0]) * tempi[i - 1][1] * 1e-6 / division
-        marks.append((tk, t, us))
+            t = t + scales[i - 1][1] * (tk - scales[i - 1][0])
+        starts.append(t)
+    ticks_of = [tk for tk, _ in scales]
 
     def seconds(tick):
-        k = 0
-        for i, m in enumerate(marks):
-            if m[0] <= tick:
-                k = i
-        tk, t0, us = marks[k]
-        return t0 + (tick - tk) * us * 1e-6 / division
+        import bisect
+        k = bisect.bisect_right(ticks_of, tick) - 1
+        return starts[k] + scales[k][1] * (tick - ticks_of[k])
 
-    notes, ccs, open_notes = [], [], {}
-    for tick, kind, channel, d1, d2 in sorted(events, key=lambda e: e[0]):   # stable: file order per tick
-        if kind == 'on':
-            open_notes.setdefault((channel, d1), []).append((tick, d2))
-        elif kind == 'off':
-            key = (channel, d1)
-            if key in open_notes:
-                close = [(s, v) for s, v in open_notes[key] if s != tick]
-                keep = [(s, v) for s, v in open_notes[key] if s == tick]
-                for s, v in close:
-                    notes.append([seconds(s), seconds(tick), d1, v])
-                if close and keep:
-                    open_notes[key] = keep
-                else:
-                    del open_notes[key]
-        else:
-            ccs.append([seconds(tick), d1, d2])
-    notes.sort(key=lambda n_: n_[0])
-    end_time = max([n_[1] for n_ in notes] + [c[0] for c in ccs] + [0.0])
-    return notes, ccs, end_time
+    instruments, stragglers = {}, {}                    # (program, channel, track) -> [notes, ccs]
+
+    def instrument(program, channel, track, create):
+        key = (program, channel, track)
+        if key in instruments:
+            return instruments[key]
+        if not create and (channel, track) in stragglers:
+            return stragglers[(channel, track)]
+        if create:
+            instruments[key] = stragglers.pop((channel, track), None) or [[], []]
+            return instruments[key]
+        stragglers[(channel, track)] = [[], []]
+        return stragglers[(channel, track)]
+
+    for track, events in enumerate(tracks):
+        open_notes, program = {}, [0] * 16
+        for tick, kind, channel, d1, d2 in events:
+            if kind == 'program':
+                program[channel] = d1
+            elif kind == 'on':
+                open_notes.setdefault((channel, d1), []).append((tick, d2))
+            elif kind == 'off':
+                key = (channel, d1)
+                if key in open_notes:
+                    close = [(s, v) for s, v in open_notes[key] if s != tick]
+                    keep = [(s, v) for s, v in open_notes[key] if s == tick]
+                    dest = instrument(program[channel], channel, track, True)[0]
+                    for s, v in close:
+                        dest.append([seconds(s), seconds(tick), d1, v])
+                    if close and keep:
+                        open_notes[key] = keep
+                    else:
+                        del open_notes[key]
+            elif kind == 'cc':
+                instrument(program[channel], channel, track, False)[1].append([seconds(tick), d1, d2])
+    notes, ccs = [], []
+    for index, (ns, cs) in enumerate(instruments.values()):
+        notes += [n_ + [index] for n_ in ns]
+        ccs += [c + [index] for c in cs]
+    total_time = max([n_[1] for n_ in notes] + [0.0])
+    return notes, ccs, total_time
 
 
-def apply_sustain_control_changes(notes, control_changes, sustain_control_number=64):
-    """note_seq.apply_sustain_control_changes: while the sustain pedal (value >= 64) is down a note
-    rings until the pedal is released or the same pitch is struck again, whichever comes first.
-    Events at equal times are processed in the order sustain-on, sustain-off, note-on, note-off.
-    Returns (notes, total_time)."""
+def apply_sustain_control_changes(notes, control_changes, total_time=None, sustain_control_number=64):
+    """note_seq.apply_sustain_control_changes: while the sustain pedal of its instrument (value >= 64) is
+    down a note rings until the pedal is released or the same pitch is struck again on that instrument,
+    whichever comes first.  Events at equal times are processed in the order sustain-on, sustain-off,
+    note-on, note-off.  total_time grows with the notes ended by a pedal release; notes still ringing after
+    the last event end there, and that time becomes total_time.  Returns (notes, total_time)."""
     ON, OFF, NOTE_ON, NOTE_OFF = 0, 1, 2, 3
+    inst = lambda x, at: x[at] if len(x) > at else 0
     notes = [list(n_) for n_ in notes]
-    events = []
-    for n_ in notes:
-        events.append((n_[0], NOTE_ON, n_))
-        events.append((n_[1], NOTE_OFF, n_))
-    for t, number, value in control_changes:
-        if number == sustain_control_number:
-            events.append((t, ON if value >= 64 else OFF, None))
+    if total_time is None:
+        total_time = max([n_[1] for n_ in notes] + [0.0])
+    events = [(n_[0], NOTE_ON, n_, inst(n_, 4)) for n_ in notes] + [(n_[1], NOTE_OFF, n_, inst(n_, 4)) for n_ in notes]
+    for c in control_changes:
+        if c[1] == sustain_control_number:
+            events.append((c[0], ON if c[2] >= 64 else OFF, None, inst(c, 3)))
     events.sort(key=lambda e: (e[0], e[1]))
-    active, sustain, removed, time = [], False, set(), 0.0
-    for time, kind, note in events:
+    active, sustain, removed, time = {}, {}, set(), 0
+    for time, kind, note, i in events:
+        held = active.setdefault(i, [])
         if kind == ON:
-            sustain = True
+            sustain[i] = True
         elif kind == OFF:
-            sustain = False
+            sustain[i] = False
             still = []
-            for a in active:
+            for a in held:
                 if a[1] < time:
                     a[1] = time                         # it was ringing on the pedal: ends now
+                    total_time = max(total_time, time)
                 else:
                     still.append(a)
-            active = still
+            active[i] = still
         elif kind == NOTE_ON:
-            if sustain:
+            if sustain.get(i, False):
                 still = []
-                for a in active:
+                for a in held:
                     if a[2] == note[2]:
                         a[1] = time                     # same pitch struck again
                         if a[0] == a[1]:
                             removed.add(id(a))
                     else:
                         still.append(a)
-                active = still
-            active.append(note)
-        else:
-            if not sustain and any(a is note for a in active):
-                active = [a for a in active if a is not note]
-    for a in active:                                    # still ringing at the end of the piece
-        a[1] = max(a[1], time)
-    notes = [n_ for n_ in notes if id(n_) not in removed]
-    total = max([n_[1] for n_ in notes] + [c[0] for c in control_changes] + [0.0])
-    return notes, total
+                active[i] = held = still
+            held.append(note)
+        elif not sustain.get(i, False):
+            active[i] = [a for a in held if a is not note]
+    for held in active.values():                        # still ringing after the last event
+        for a in held:
+            a[1] = time
+            total_time = time
+    return [n_ for n_ in notes if id(n_) not in removed], total_time
 
 
 def sequence_to_pianoroll(notes, control_changes, total_time, frames_per_second=250, min_pitch=21,
                           max_pitch=108, onset_window=1, max_velocity=127.0):
     """note_seq.sequences_lib.sequence_to_pianoroll with its defaults (onset_mode='window'):
-    a note is active from floor(start * fps) to ceil(end * fps) (at least one frame); its onset
-    velocity, velocity / max_velocity, is written on the onset frame +- onset_window frames;
-    control_changes[frame, number] = value + 1 on the frame of the event (0 = no event).
+    a note is active from floor(start * fps) to ceil(end * fps); its onset velocity,
+    velocity / max_velocity, is written on the onset frame +- onset_window frames, notes taken by
+    start time (stable), later ones overwriting; control_changes[frame, number] = value + 1 on the
+    frame of the event (0 = no event), in sequence order.
     Returns (active [T, 88], onset_velocities [T, 88], control_changes [T, 128])."""
     import math
     n_frames = int(total_time * frames_per_second + 1)
@@ -208,18 +265,19 @@ def sequence_to_pianoroll(notes, control_changes, total_time, frames_per_second=
     active = np.zeros([n_frames, n_pitches], np.float32)
     onset_vel = np.zeros([n_frames, n_pitches], np.float32)
     ccs = np.zeros([n_frames, 128], np.int32)
-    for start, end, pitch, velocity in sorted(notes, key=lambda n_: n_[0]):
+    for n_ in sorted(notes, key=lambda n_: n_[0]):
+        start, end, pitch, velocity = n_[:4]
         if pitch < min_pitch or pitch > max_pitch:
             continue
         s = int(start * frames_per_second)
-        e = max(s + 1, int(math.ceil(end * frames_per_second)))
+        e = max(s, int(math.ceil(end * frames_per_second)))
         active[s:e, pitch - min_pitch] = 1.0
         o0, o1 = max(0, s - onset_window), min(n_frames, s + onset_window + 1)
         onset_vel[o0:o1, pitch - min_pitch] = velocity / max_velocity
-    for t, number, value in sorted(control_changes, key=lambda c: c[0]):
-        frame = int(t * frames_per_second)
+    for c in control_changes:
+        frame = int(c[0] * frames_per_second)
         if frame < n_frames:
-            ccs[frame, number] = value + 1
+            ccs[frame, c[1]] = c[2] + 1
     return active, onset_vel, ccs
 
 
@@ -238,8 +296,8 @@ def load_midi_as_conditioning(mid_path, n_synths=16, frame_rate=250, duration=No
                               onset_window=1):
     """utils/io_utils.py:85-137: MIDI file -> {'conditioning' [1, F, n_synths, 2], 'pedal' [1, F, 4],
     'duration'}; the dict a PianoModel takes (plus 'piano_model')."""
-    notes, ccs, _ = read_midi(mid_path)
-    notes, total_time = apply_sustain_control_changes(notes, ccs)          # :77-82
+    notes, ccs, total_time = read_midi(mid_path)
+    notes, total_time = apply_sustain_control_changes(notes, ccs, total_time)   # :77-82
     active, onset_vel, cc_roll = sequence_to_pianoroll(notes, ccs, total_time, frame_rate, 21, 108,
                                                        onset_window)       # :104-107
     midi_roll = np.stack((active, onset_vel), axis=-1)                     # :109

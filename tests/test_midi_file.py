@@ -45,9 +45,44 @@ def test_read_midi_tempo_map_and_note_pairing(tmp_path):
                      [(0, on(60, 100)), (480, off(60)), (480, on(64, 80)), (960, on(64, 0)),   # vel 0 = off
                       (240, cc(64, 127)), (1200, cc(64, 0))]])
     notes, ccs, end = midi.read_midi(path)
-    assert [[round(x, 6) for x in n[:2]] + n[2:] for n in notes] == [[0.0, 0.5, 60, 100], [0.5, 1.5, 64, 80]]
-    assert [[round(c[0], 6)] + c[1:] for c in ccs] == [[0.25, 64, 127], [2.0, 64, 0]]
-    assert abs(end - 2.0) < 1e-9
+    assert [[round(x, 6) for x in n[:2]] + n[2:] for n in notes] == [[0.0, 0.5, 60, 100, 0], [0.5, 1.5, 64, 80, 0]]
+    assert [[round(c[0], 6)] + c[1:] for c in ccs] == [[0.25, 64, 127, 0], [2.0, 64, 0, 0]]
+    assert abs(end - 1.5) < 1e-9                       # total_time = the latest note end
+
+
+def test_read_midi_pretty_midi_conventions(tmp_path):
+    path = str(tmp_path / 'p.mid')
+    # tempo events outside track 0 are ignored; a repeated tempo opens no new interval; a program change
+    # makes a new instrument; control changes of a channel without notes are dropped
+    write_smf(path, [[(0, tempo(500000)), (480, tempo(500000)), (960, tempo(250000))],
+                     [(0, tempo(1000000)), (0, cc(64, 127)), (0, on(60, 100)), (480, off(60)),
+                      (480, bytes([0xc0, 5])), (480, on(62, 90)), (1440, off(62)), (0, cc(64, 10, ch=3))],
+                     [(0, on(60, 70, ch=1)), (960, off(60, ch=1))]])
+    notes, ccs, end = midi.read_midi(path)
+    assert notes == [[0.0, 0.5, 60, 100, 0], [0.5, 1.25, 62, 90, 1], [0.0, 1.0, 60, 70, 2]]
+    assert ccs == [[0.0, 64, 127, 0]] and end == 1.25
+    # seconds(tick) = start of the interval + scale * ticks, with pretty_midi's scale arithmetic
+    scale = 60.0 / ((6e7 / 500000) * 480)
+    assert notes[1][1] == scale * 960 + (60.0 / ((6e7 / 250000) * 480)) * 480
+    # the pedal of instrument 0 holds only its own notes (note_seq keeps one pedal state per instrument)
+    out, total = midi.apply_sustain_control_changes(notes, ccs, end)
+    assert [n[1] for n in out] == [1.25, 1.25, 1.0] and total == 1.25
+
+
+def test_read_midi_rejects_garbage(tmp_path):
+    path = str(tmp_path / 'x.mid')
+    with open(path, 'wb') as f:
+        f.write(b'RIFF....')
+    with pytest.raises(ValueError):
+        midi.read_midi(path)
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 1, 1, 0x8000 | 25) + b'MTrk' + struct.pack('>I', 0))
+    with pytest.raises(ValueError, match='SMPTE'):
+        midi.read_midi(path)
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 1, 1, 480) + b'MTrk' + struct.pack('>I', 400) + b'\x00')
+    with pytest.raises(ValueError, match='truncated'):
+        midi.read_midi(path)
 
 
 def test_running_status_and_format_0(tmp_path):
