@@ -233,10 +233,26 @@ class PianoModel:
     def sample_rate(self):
         return self.processor_group.processors[0].sample_rate
 
+    @property
+    def n_instruments(self):
+        """Rows of the smallest per-instrument table (tables with one row serve every instrument)."""
+        rows = [getattr(m, 'n_instruments', None) for m in (self.z_encoder, self.reverb_model)]
+        if isinstance(self.context_network, FiLMContextNetwork):
+            rows.append(self.context_network.piano_id_head.shape[0])
+        if isinstance(self.inharm_model, JointParametricInharmTuning):
+            rows += [e.shape[0] for e in self.inharm_model.e.values()]
+        rows = [r for r in rows if r is not None and r > 1]
+        return min(rows) if rows else None
+
     def compute_controls(self, features):
         """Everything before the processor group (piano_model.py:146-158)."""
         f = dict(features)
         dev = self.device
+        ids, n = torch.as_tensor(f['piano_model']).reshape(-1), self.n_instruments
+        if n is not None and ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= n):
+            # an embedding lookup out of range is an InvalidArgumentError in the reference; on the
+            # device it would be an assert that takes the CUDA context with it
+            raise ValueError(f'piano_model ids must lie in [0, {n}), got {ids.tolist()}')
         f['conditioning'] = torch.as_tensor(f['conditioning'], dtype=torch.float32, device=dev)
         f['pedal'] = torch.as_tensor(f['pedal'], dtype=torch.float32, device=dev)
         f['piano_model'] = torch.as_tensor(f['piano_model'], device=dev).long().reshape(-1, 1)

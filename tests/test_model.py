@@ -310,3 +310,16 @@ def test_midi_file_to_audio(weights, tmp_path):
     pedal_tail = dry[(125 + 400) * U:(125 + 600) * U]    # after the note-off (1.5 s), pedal down until 2.5 s
     after = dry[(125 + 700) * U:]
     assert rms(pedal_tail) > 3 * rms(after)
+
+
+def test_piano_model_id_out_of_range_is_a_value_error(weights, v2_weights):
+    """An instrument id beyond the smallest per-instrument table is refused on the host (the reference's
+    embedding lookup raises InvalidArgumentError); nothing reaches the device."""
+    from ddsp_piano_b200 import model as M
+    cond, pedal = np.zeros([1, 4, 16, 2], np.float32), np.zeros([1, 4, 4], np.float32)
+    for factory, path, n in ((M.dafx22_model, weights, 2), (M.maestro_v2_model, v2_weights, 10)):
+        model = factory(path, device='cpu')
+        assert model.n_instruments == n                 # the dafx22 fixture keeps 2 of the 10 shipped IRs
+        for bad in ([[n]], [[-1]]):
+            with pytest.raises(ValueError, match='piano_model ids'):
+                model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': bad})
