@@ -131,6 +131,8 @@ def load():
     lib.b200ddsp_timeline_overlap_add.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     lib.b200ddsp_note_release.restype = ci
     lib.b200ddsp_note_release.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
+    lib.b200ddsp_gru_recurrence.restype = ci
+    lib.b200ddsp_gru_recurrence.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     lib.b200ddsp_fft_convolve.restype = ci
     lib.b200ddsp_fft_convolve.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_fdn_ir.restype = ci
@@ -160,7 +162,7 @@ def load():
 EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200ddsp_destroy',
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
-           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_surrogate_decays', 'b200ddsp_surrogate_signal', 'b200ddsp_peer_alloc', 'b200ddsp_peer_free',
+           'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_gru_recurrence', 'b200ddsp_surrogate_decays', 'b200ddsp_surrogate_signal', 'b200ddsp_peer_alloc', 'b200ddsp_peer_free',
            'b200ddsp_peer_open', 'b200ddsp_peer_close', 'b200ddsp_timeline_overlap_add', 'b200ddsp_fdn_ir',
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',

@@ -1789,6 +1789,55 @@ extern "C" int b200ddsp_note_release(b200ddsp_handle* h, const float* active_pit
   return B200DDSP_OK;
 }
 
+template <int UC, int CL>
+static int launch_gru(b200ddsp_handle* h, const float* x_proj, const float* w_hh, const float* b_hh,
+                      float* out, int rows, int F, cudaStream_t st) {
+  constexpr int u = UC * CL;
+  // rows per cluster: as few as keeps every cluster resident at once (the frame loop is latency-bound,
+  // so small groups on many SMs win), at most what 1024 threads hold (4 lanes per unit and row pair)
+  const int rb_max = 2 * (1024 / (4 * UC)) < 16 ? 2 * (1024 / (4 * UC)) : 16;
+  int RB = 2;
+  while (RB < rb_max && (int64_t)((rows + RB - 1) / RB) * CL > h->n_sms) RB *= 2;
+  const int groups = (rows + RB - 1) / RB;
+  const size_t smem = (size_t)(3 * UC * (u + 16) + 2 * RB * u) * sizeof(float);
+  auto kernel = gru_recurrence_kernel<UC, CL>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CL));
+  cfg.blockDim = dim3((unsigned)(UC * (RB / 2) * 4));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kernel, x_proj, w_hh, b_hh, out, rows, F, RB));
+  CHECK_LAUNCH(h, "gru_recurrence_kernel");
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_gru_recurrence(b200ddsp_handle* h, const float* x_proj, const float* w_hh,
+                                       const float* b_hh, float* out, int rows, int F, int units,
+                                       void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!x_proj || !w_hh || !b_hh || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (rows < 1 || F < 1) return fail(h, B200DDSP_BAD_SHAPE, "rows=%d F=%d", rows, F);
+  if ((((uintptr_t)x_proj | (uintptr_t)w_hh | (uintptr_t)b_hh | (uintptr_t)out) & 3) != 0)
+    return fail(h, B200DDSP_BAD_ALIGN, "tensors must be float32-aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (units) {
+    case 64: return launch_gru<64, 1>(h, x_proj, w_hh, b_hh, out, rows, F, st);
+    case 128: return launch_gru<32, 4>(h, x_proj, w_hh, b_hh, out, rows, F, st);
+    case 192: return launch_gru<24, 8>(h, x_proj, w_hh, b_hh, out, rows, F, st);
+    case 256: return launch_gru<32, 8>(h, x_proj, w_hh, b_hh, out, rows, F, st);
+    default:
+      return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "GRU of %d units (supported: 64, 128, 192, 256)", units);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side front end
 // ---------------------------------------------------------------------------------------------

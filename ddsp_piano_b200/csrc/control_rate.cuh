@@ -1,5 +1,7 @@
 // Control-rate (250 Hz) helpers that feed the synthesis path.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace b200ddsp {
@@ -32,6 +34,122 @@ __global__ void __launch_bounds__(128) note_release_kernel(const float* __restri
                       __fadd_rn(1.f, -release_end));
     previous = y;
     o[k] = y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GRU recurrence (tf.keras.layers.GRU(units, return_sequences=True), TF2 default reset_after=True:
+// ContextNetwork / MonophonicNetwork, reference modules/sub_modules.py:18-65, 455-496, 97-180, 499-525).
+// ---------------------------------------------------------------------------------------------
+// The input projections x W_i + b_i of all frames are one library GEMM upstream; what is left is the
+// part that is sequential in time:
+//   r = sigmoid(xr + h Wr + br)   z = sigmoid(xz + h Wz + bz)   n = tanh(xn + r * (h Wn + bn))
+//   h' = (1 - z) * n + z * h
+// A frame is a [rows, u] x [u, 3u] product with rows = voices x clips (16 for one clip): far too small
+// for a launch per frame, which is what a library GRU costs (6.5 us per frame measured, 100 ms for a
+// 60 s piece).  Here ONE launch walks all frames: a cluster of CL CTAs owns a group of RB rows for the
+// whole sequence, CTA c keeps the recurrent weights of its UC = u / CL units in shared memory
+// (3 * UC * u floats: 55 KB for u = 192 on 8 CTAs) and the hidden state of the group in two shared
+// buffers; after each frame every CTA writes its UC new state values into the next buffer of ALL CTAs
+// of the cluster (distributed shared memory) and one cluster barrier ends the frame.
+// Thread = (row pair p, unit j, quarter q of the k range): 4 adjacent lanes split the dot products
+// (float4 reads, k interleaved by 16 so that a quarter-warp reads 2 x 64 contiguous bytes on disjoint
+// banks: row stride u + 16 floats), reduce with two shuffles, lanes q = 0, 1 finish rows 2p, 2p + 1.
+template <int UC, int CL>
+__global__ void __launch_bounds__(UC * 32 > 1024 ? 1024 : UC * 32, 1)
+gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gates (r, z, n), bias b_i included
+                      const float* __restrict__ w_hh,     // [3u, u]        torch weight_hh layout
+                      const float* __restrict__ b_hh,     // [3u]
+                      float* __restrict__ out,            // [rows, F, u]
+                      int rows, int F, int RB) {
+  constexpr int u = UC * CL;
+  constexpr int WS = u + 16;                              // padded row of the weight tile
+  extern __shared__ __align__(16) float gru_smem[];
+  float* Ws = gru_smem;                                   // [3][UC][WS]
+  float* hs = gru_smem + 3 * UC * WS;                     // [2][RB][u]
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
+  const int group = blockIdx.x / CL;
+  const int tid = threadIdx.x;
+  const int q = tid & 3, jl = (tid >> 2) % UC, p = (tid >> 2) / UC;
+  const int j = rank * UC + jl;                           // unit of this thread
+  const int row0 = group * RB;
+
+  for (int i = tid; i < 3 * UC * u; i += blockDim.x) {    // recurrent weights of the own units
+    const int g = i / (UC * u), r = i % (UC * u), jj = r / u, k = r % u;
+    Ws[(g * UC + jj) * WS + k] = w_hh[(size_t)(g * u + rank * UC + jj) * u + k];
+  }
+  for (int i = tid; i < 2 * RB * u; i += blockDim.x) hs[i] = 0.f;
+
+  // lanes q = 0, 1 own the state of (row 2p + q, unit j)
+  const int lrow = 2 * p + q;                             // meaningful for q < 2
+  const int row = row0 + lrow;
+  const bool owner = q < 2 && row < rows;
+  float b_r = 0.f, b_z = 0.f, b_n = 0.f, h_own = 0.f;
+  if (owner) { b_r = b_hh[j]; b_z = b_hh[u + j]; b_n = b_hh[2 * u + j]; }
+  const float* xp = x_proj + ((size_t)row * F) * (3 * u) + j;
+  float* op = out + ((size_t)row * F) * u + j;
+
+  // lane q writes the new state into the buffers of CTAs q, q + 4, ... of the cluster
+  constexpr int NR = (CL + 3) / 4;
+  float* remote[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int c = q + 4 * i;
+    remote[i] = c >= CL ? nullptr : (CL > 1 ? cluster.map_shared_rank(hs, c) : hs);
+  }
+  if (CL > 1) cluster.sync(); else __syncthreads();       // weights and zero state in place everywhere
+
+  const float4* wr = reinterpret_cast<const float4*>(Ws + (0 * UC + jl) * WS) + q;
+  const float4* wz = reinterpret_cast<const float4*>(Ws + (1 * UC + jl) * WS) + q;
+  const float4* wn = reinterpret_cast<const float4*>(Ws + (2 * UC + jl) * WS) + q;
+  const unsigned base_lane = (tid & 31) & ~3u;
+
+  for (int t = 0; t < F; ++t) {
+    const int cur = t & 1;
+    float xr = 0.f, xz = 0.f, xn = 0.f;
+    if (owner) {                                          // in flight under the dot products
+      xr = __ldg(xp + (size_t)t * 3 * u);
+      xz = __ldg(xp + (size_t)t * 3 * u + u);
+      xn = __ldg(xp + (size_t)t * 3 * u + 2 * u);
+    }
+    const float4* ha = reinterpret_cast<const float4*>(hs + (cur * RB + 2 * p) * u) + q;
+    const float4* hb = ha + u / 4;
+    float ar0 = 0.f, az0 = 0.f, an0 = 0.f, ar1 = 0.f, az1 = 0.f, an1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < u / 16; ++i) {
+      const float4 a = ha[4 * i], b = hb[4 * i];
+      const float4 r4 = wr[4 * i], z4 = wz[4 * i], n4 = wn[4 * i];
+      ar0 = fmaf(r4.x, a.x, ar0); az0 = fmaf(z4.x, a.x, az0); an0 = fmaf(n4.x, a.x, an0);
+      ar1 = fmaf(r4.x, b.x, ar1); az1 = fmaf(z4.x, b.x, az1); an1 = fmaf(n4.x, b.x, an1);
+      ar0 = fmaf(r4.y, a.y, ar0); az0 = fmaf(z4.y, a.y, az0); an0 = fmaf(n4.y, a.y, an0);
+      ar1 = fmaf(r4.y, b.y, ar1); az1 = fmaf(z4.y, b.y, az1); an1 = fmaf(n4.y, b.y, an1);
+      ar0 = fmaf(r4.z, a.z, ar0); az0 = fmaf(z4.z, a.z, az0); an0 = fmaf(n4.z, a.z, an0);
+      ar1 = fmaf(r4.z, b.z, ar1); az1 = fmaf(z4.z, b.z, az1); an1 = fmaf(n4.z, b.z, an1);
+      ar0 = fmaf(r4.w, a.w, ar0); az0 = fmaf(z4.w, a.w, az0); an0 = fmaf(n4.w, a.w, an0);
+      ar1 = fmaf(r4.w, b.w, ar1); az1 = fmaf(z4.w, b.w, az1); an1 = fmaf(n4.w, b.w, an1);
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      ar0 += __shfl_xor_sync(0xffffffffu, ar0, o); az0 += __shfl_xor_sync(0xffffffffu, az0, o);
+      an0 += __shfl_xor_sync(0xffffffffu, an0, o); ar1 += __shfl_xor_sync(0xffffffffu, ar1, o);
+      az1 += __shfl_xor_sync(0xffffffffu, az1, o); an1 += __shfl_xor_sync(0xffffffffu, an1, o);
+    }
+    const float sr = q == 0 ? ar0 : ar1, sz = q == 0 ? az0 : az1, sn = q == 0 ? an0 : an1;
+    const float r = 1.f / (1.f + expf(-(xr + sr + b_r)));
+    const float z = 1.f / (1.f + expf(-(xz + sz + b_z)));
+    const float n = tanhf(xn + r * (sn + b_n));
+    const float h_new = owner ? (1.f - z) * n + z * h_own : 0.f;
+    h_own = h_new;
+    if (owner) op[(size_t)t * u] = h_new;
+    // both rows of the pair to all four lanes, then out to the cluster
+    const float va = __shfl_sync(0xffffffffu, h_new, base_lane), vb = __shfl_sync(0xffffffffu, h_new, base_lane + 1);
+    const int at = ((cur ^ 1) * RB + 2 * p) * u + j;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (remote[i] != nullptr) { remote[i][at] = va; remote[i][at + u] = vb; }
+    if (CL > 1) cluster.sync(); else __syncthreads();
   }
 }
 

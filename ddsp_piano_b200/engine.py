@@ -278,6 +278,20 @@ class Engine:
                 float(release_frames), self.stream()))
         return out
 
+    def gru_recurrence(self, x_proj, w_hh, b_hh):
+        """GRU recurrence over x_proj [rows, F, 3u] (input projections, gates r, z, n) -> [rows, F, u]."""
+        x = self.tensor(x_proj, 'x_proj', 3)
+        w, b = self.tensor(w_hh, 'w_hh', 2), self.tensor(b_hh, 'b_hh', 1)
+        u = w.shape[1]
+        if w.shape[0] != 3 * u or b.shape[0] != 3 * u or x.shape[2] != 3 * u:
+            raise ValueError(f'GRU shapes disagree: x_proj {tuple(x.shape)}, w_hh {tuple(w.shape)}, b_hh {tuple(b.shape)}')
+        out = torch.empty(x.shape[0], x.shape[1], u, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_gru_recurrence(
+                self.handle, x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                u, self.stream()))
+        return out
+
     def fft_convolve(self, audio, ir, mask_ir0=False, add_dry=False, full=False):
         """ddsp.core.fft_convolve(audio, ir, delay_compensation=0) + the reverbs' options."""
         flags = (_lib.CONV_MASK_IR0 if mask_ir0 else 0) | (_lib.CONV_ADD_DRY if add_dry else 0) | \

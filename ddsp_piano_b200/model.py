@@ -16,6 +16,8 @@ Parity status: checked in ``tests/test_model.py`` against a numpy restatement of
 the shipped weights; the Keras / ddsp layer semantics underneath are restated, not pinned
 (TensorFlow is not in the container) -- see DESIGN.md section 8.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -42,6 +44,10 @@ class Dense:
         return self.activation(y) if self.activation is not None else y
 
 
+# 'cluster': the persistent cluster kernel of this library; 'cudnn': torch.nn.GRU (A/B timing only)
+GRU_IMPL = os.environ.get('B200DDSP_GRU', 'cluster')
+
+
 def leaky_relu(x):
     return torch.nn.functional.leaky_relu(x, 0.2)          # tf.nn.leaky_relu default alpha
 
@@ -64,6 +70,15 @@ class GRU:
         self.gru.flatten_parameters()
 
     def __call__(self, x):
+        u = self.gru.hidden_size
+        if x.is_cuda and GRU_IMPL == 'cluster' and u in (64, 128, 192, 256):
+            # input projections of all frames as one GEMM, then the recurrence as ONE launch
+            # (csrc/control_rate.cuh::gru_recurrence_kernel) instead of a library step per frame
+            with torch.no_grad():
+                R, F, C = x.shape
+                xp = torch.addmm(self.gru.bias_ih_l0, x.reshape(R * F, C), self.gru.weight_ih_l0.t())
+                return get_engine(x.device, **_DEFAULT_CFG).gru_recurrence(
+                    xp.reshape(R, F, 3 * u), self.gru.weight_hh_l0, self.gru.bias_hh_l0)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), torch.no_grad():
             return self.gru(x.contiguous())[0]
 

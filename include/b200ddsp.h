@@ -205,6 +205,16 @@ int b200ddsp_timeline_overlap_add(b200ddsp_handle* h, const float* wet_full, con
 int b200ddsp_note_release(b200ddsp_handle* h, const float* active_pitch, float* extended_pitch,
                           int rows, int F, int in_stride, float release_frames, void* stream);
 
+/* The time-sequential part of tf.keras.layers.GRU(units, return_sequences=True) with TF2's default
+ * reset_after=True, zero initial state (ContextNetwork / MonophonicNetwork and their v2 forms, reference
+ * modules/sub_modules.py:32-38, 122-131, 471-478, 510-513), all F frames in ONE launch: clusters of
+ * CTAs hold the recurrent weights in shared memory and exchange the hidden state through distributed
+ * shared memory.  x_proj [rows, F, 3 * units] = x W_i + b_i (the caller's GEMM); w_hh [3 * units, units];
+ * b_hh [3 * units]; gates in the order (r, z, n), i.e. Keras' (z, r, h) columns swapped as for
+ * torch.nn.GRU; out [rows, F, units].  units in {64, 128, 192, 256}. */
+int b200ddsp_gru_recurrence(b200ddsp_handle* h, const float* x_proj, const float* w_hh,
+                            const float* b_hh, float* out, int rows, int F, int units, void* stream);
+
 /* ddsp.core.fft_convolve(audio, ir, padding, delay_compensation=0) with the options the reverbs
  * of the reference use.  flags: B200DDSP_CONV_MASK_IR0 zeroes ir[:,0] (effects.Reverb masks the dry
  * tap), B200DDSP_CONV_ADD_DRY adds the input (effects.Reverb add_dry), B200DDSP_CONV_FULL writes

@@ -323,3 +323,31 @@ def test_piano_model_id_out_of_range_is_a_value_error(weights, v2_weights):
         for bad in ([[n]], [[-1]]):
             with pytest.raises(ValueError, match='piano_model ids'):
                 model.compute_controls({'conditioning': cond, 'pedal': pedal, 'piano_model': bad})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rows,F,units,inputs', [(1, 300, 64, 32), (16, 300, 192, 52), (37, 65, 192, 35),
+                                                 (256, 40, 192, 52), (3, 50, 128, 8), (20, 50, 256, 8)])
+def test_gru_recurrence_kernel(rows, F, units, inputs):
+    """b200ddsp_gru_recurrence (one launch for all frames, clusters sharing the state over distributed
+    shared memory) against torch.nn.GRU in float64 on the CPU: same recurrence (Keras reset_after=True),
+    tolerance 2e-5 on a state bounded by 1."""
+    from ddsp_piano_b200.engine import get_engine
+    from ddsp_piano_b200.processors import _DEFAULT_CFG
+    g = torch.Generator().manual_seed(rows * 1000 + units)
+    gru = torch.nn.GRU(inputs, units, batch_first=True).double()
+    with torch.no_grad():
+        for p_ in gru.parameters():
+            # +-2/sqrt(u): a contracting recurrence (with N(0, 0.3) weights at u >= 192 it is chaotic and
+            # torch's own float32 and float64 runs part by O(1) within 300 frames)
+            p_.copy_((torch.rand(p_.shape, generator=g, dtype=torch.float64) * 2 - 1) * (2.0 / units ** 0.5))
+    x = torch.randn(rows, F, inputs, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        want = gru(x)[0].numpy()
+        xp = (x @ gru.weight_ih_l0.t() + gru.bias_ih_l0).float()
+    eng = get_engine(torch.device('cuda:0'), **_DEFAULT_CFG)
+    got = eng.gru_recurrence(xp.cuda(), gru.weight_hh_l0.detach().float().cuda(), gru.bias_hh_l0.detach().float().cuda())
+    torch.cuda.synchronize()
+    assert got.shape == (rows, F, units)
+    err = np.max(np.abs(got.cpu().numpy() - want))
+    assert err < 2e-5, err
