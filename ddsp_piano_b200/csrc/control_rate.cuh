@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128) note_release_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------
 // GRU recurrence (tf.keras.layers.GRU(units, return_sequences=True), TF2 default reset_after=True:
-// ContextNetwork / MonophonicNetwork, reference modules/sub_modules.py:18-65, 455-496, 97-180, 499-525).
+// the GRUs of ContextNetwork / MonophonicNetwork, reference configs/dafx22.gin:64-72, 77-86, and of
+// FiLMContextNetwork / MonophonicDeepNetwork, modules/sub_modules.py:121, 503).
 // ---------------------------------------------------------------------------------------------
 // The input projections x W_i + b_i of all frames are one library GEMM upstream; what is left is the
 // part that is sequential in time:

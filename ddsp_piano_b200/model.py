@@ -6,10 +6,10 @@ sub-modules of ``modules/sub_modules.py`` named below) so that a ``PianoModel`` 
 like the reference's: ``model({'conditioning': [B, F, P, 2], 'pedal': [B, F, 4],
 'piano_model': [B, 1]})`` returns the processor group's controls plus ``'audio_synth'``.
 
-This is caller-side plumbing at 1/96 of the audio rate, not the hot path: the dense layers and
-the two GRUs are torch library calls (cuBLAS / cuDNN with TF32 disabled); the note-release
-recurrence, which has no library form, is a small CUDA kernel behind the C ABI
-(``b200ddsp_note_release``).  Weights come from the reference's shipped TensorFlow checkpoint
+This is caller-side plumbing at 1/96 of the audio rate, not the hot path: the dense layers are
+torch library calls (cuBLAS, TF32 disabled); the two parts that are sequential in time, the
+note-release recurrence and the recurrence of the two GRUs, are CUDA kernels behind the C ABI
+(``b200ddsp_note_release``, ``b200ddsp_gru_recurrence``: one launch for all frames).  Weights come from the reference's shipped TensorFlow checkpoint
 through the TF-free reader in ``checkpoint.py``.
 
 Parity status: checked in ``tests/test_model.py`` against a numpy restatement of the same graph on

@@ -206,8 +206,8 @@ int b200ddsp_note_release(b200ddsp_handle* h, const float* active_pitch, float* 
                           int rows, int F, int in_stride, float release_frames, void* stream);
 
 /* The time-sequential part of tf.keras.layers.GRU(units, return_sequences=True) with TF2's default
- * reset_after=True, zero initial state (ContextNetwork / MonophonicNetwork and their v2 forms, reference
- * modules/sub_modules.py:32-38, 122-131, 471-478, 510-513), all F frames in ONE launch: clusters of
+ * reset_after=True, zero initial state (the GRUs of ContextNetwork / MonophonicNetwork, reference
+ * configs/dafx22.gin:64-72, 77-86, and of their v2 forms, modules/sub_modules.py:121, 503), all F frames in ONE launch: clusters of
  * CTAs hold the recurrent weights in shared memory and exchange the hidden state through distributed
  * shared memory.  x_proj [rows, F, 3 * units] = x W_i + b_i (the caller's GEMM); w_hh [3 * units, units];
  * b_hh [3 * units]; gates in the order (r, z, n), i.e. Keras' (z, r, h) columns swapped as for
