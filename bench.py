@@ -507,10 +507,30 @@ def run_gpu(args, w):
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if world == 1 and args.workload == 'full':
+            line['config1'] = config1_line()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config1_line():
+    """BASELINE configs[0] beside the headline (after the timed region, never part of it): one 3 s clip from
+    MIDI conditioning to audio through the control-rate graph and the kernels with the shipped weights
+    (scripts/config1_timing.py).  A failure here is reported in the line, it does not take the bench with it."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            'config1_timing', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'scripts', 'config1_timing.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out = mod.measure()
+        out['what'] = ('configs[0]: single 3 s MIDI clip (+0.5 s warm-up), 4 notes on 16 channels, shipped weights, '
+                       'MIDI conditioning -> audio; wall clock, median of 10')
+        return out
+    except Exception as e:                               # noqa: BLE001 (informational key)
+        return {'error': f'{type(e).__name__}: {e}'}
 
 
 def main():

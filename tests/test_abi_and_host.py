@@ -305,3 +305,15 @@ def test_bench_live_chain_samples_matches_brute_force():
                 total += int(nh) * 32 * (t1 + 1 - t0)
     assert bench.live_chain_samples(w, x) == total
     assert bench.bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3)   # never raises without a GPU
+
+
+def test_bench_config1_key_never_raises():
+    """The informational "config1" key of the bench line (configs[0] beside the headline) reports a failure
+    instead of raising: without a GPU it is an error entry, on a GPU the two shipped models."""
+    import torch
+    import bench
+    out = bench.config1_line()
+    if torch.cuda.is_available():
+        assert {'dafx22', 'maestro_v2', 'what'} <= set(out) and out['dafx22']['rtf'] > 50
+    else:
+        assert set(out) == {'error'}
