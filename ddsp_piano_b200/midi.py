@@ -8,6 +8,7 @@ called with NumPy arrays.  Like the reference, one object = one allocation state
 ``__call__`` starts from a fresh state.
 """
 import ctypes
+import struct
 
 import numpy as np
 
@@ -65,7 +66,6 @@ def _vlq(data, pos):
 def _parse_tracks(data, path):
     """Standard MIDI File chunks -> (division, [[(absolute tick, kind, channel, d1, d2)] per track]);
     kind in 'on' / 'off' / 'cc' / 'program' / 'tempo' (tempo: d1 = microseconds per quarter)."""
-    import struct
     if data[:4] != b'MThd':
         raise ValueError(f'{path}: not a Standard MIDI File')
     hlen, _, n_tracks, division = struct.unpack('>IHHH', data[4:14])
@@ -134,7 +134,12 @@ def read_midi(path):
     * total_time = the latest note end (control changes do not extend it)."""
     with open(path, 'rb') as f:
         data = f.read()
-    division, tracks = _parse_tracks(data, path)
+    try:
+        division, tracks = _parse_tracks(data, path)
+    except (IndexError, struct.error) as e:            # an event or chunk header cut short
+        raise ValueError(f'{path}: truncated MIDI data') from e
+    if division == 0:
+        raise ValueError(f'{path}: zero ticks per quarter note')
     scales = [(0, 60.0 / (120.0 * division))]
     for tick, kind, _, us, _ in (tracks[0] if tracks else []):
         if kind != 'tempo':

@@ -83,6 +83,46 @@ def test_read_midi_rejects_garbage(tmp_path):
         f.write(b'MThd' + struct.pack('>IHHH', 6, 1, 1, 480) + b'MTrk' + struct.pack('>I', 400) + b'\x00')
     with pytest.raises(ValueError, match='truncated'):
         midi.read_midi(path)
+    with open(path, 'wb') as f:                          # an event cut short inside a well-formed chunk
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 1, 1, 480) + b'MTrk' + struct.pack('>I', 2) + b'\x00\x90')
+    with pytest.raises(ValueError, match='truncated'):
+        midi.read_midi(path)
+    with open(path, 'wb') as f:
+        f.write(b'MThd' + struct.pack('>IHHH', 6, 1, 1, 0) + b'MTrk' + struct.pack('>I', 0))
+    with pytest.raises(ValueError, match='zero ticks'):
+        midi.read_midi(path)
+
+
+def test_written_notes_come_back(tmp_path):
+    """Property: any set of notes without same-pitch overlaps, written as note-on / note-off pairs at any
+    constant tempo, is read back with its ticks * scale times, pitches and velocities."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 5000), st.integers(1, 2000), st.integers(0, 127), st.integers(1, 127)),
+                    min_size=1, max_size=30),
+           st.integers(200000, 1500000), st.sampled_from([96, 240, 480, 960]))
+    def check(raw, us, division):
+        busy, kept = {}, []
+        for start, length, pitch, vel in raw:
+            if all(start + length <= s0 or start >= e0 for s0, e0 in busy.get(pitch, [])):
+                busy.setdefault(pitch, []).append((start, start + length))
+                kept.append((start, start + length, pitch, vel))
+        path = str(tmp_path / 'h.mid')
+        events = [(0, tempo(us))]
+        for s0, e0, pitch, vel in kept:
+            events += [(s0, on(pitch, vel)), (e0, off(pitch))]
+        # write_smf sorts by tick (stable): a note-off on the tick of the next note-on of its pitch must come
+        # first, as in a real file
+        events.sort(key=lambda e: (e[0], 0 if e[1][0] & 0xf0 == 0x80 else 1))
+        write_smf(path, [events], division=division)
+        notes, ccs, total = midi.read_midi(path)
+        scale = 60.0 / ((6e7 / us) * division)
+        want = sorted((scale * s0, scale * e0, pitch, vel, 0) for s0, e0, pitch, vel in kept)
+        assert sorted(tuple(n) for n in notes) == want
+        assert ccs == [] and total == max(n[1] for n in want)
+
+    check()
 
 
 def test_running_status_and_format_0(tmp_path):
