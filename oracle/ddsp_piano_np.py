@@ -250,3 +250,76 @@ def polyphonic_forward(features, *, n_synths, sample_rate, frame_rate=250,
     if reverb:
         out = reverb_signal(dry, features['reverb_ir'], add_dry=add_dry)
     return {'dry': dry, 'signal': out, 'additive': add_sigs, 'noise': noise_sigs}
+
+
+# ---------------------------------------------------------------------------------------------
+# Timeline segments: the additive synth of frames [f0, f1) of a long clip, bit for
+# bit what additive_signal gives for those samples on the whole clip.  This is the SPECIFICATION of
+# the carried state for a segment-sharded oscillator bank (no kernel implements it yet, DESIGN.md
+# section 6): what has to cross a segment boundary is
+#   * one frame of halo on each side for the two resamplers: the window resampler reads frame k + 1,
+#     and the legacy bilinear coordinate float32(i) * float32(F / N) of the GLOBAL sample index i can
+#     round below the frame of sample i, so the first samples of a segment may read frame f0 - 1 (it
+#     does not at U = 64, 96, 192, where float32(1 / U) is exact or rounds up; the assert keeps watch);
+#   * per (clip, substring, partial) the float32 running sum of the chunk-end phases mod 2 pi that
+#     angular_cumsum (ddsp.core, chunk_size 1000) accumulates UNWRAPPED over the chunks before the
+#     segment, so f0 * U must be a multiple of 1000 (72 000 samples per 3 s segment at 24 kHz is).
+# ---------------------------------------------------------------------------------------------
+def additive_signal_segment(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, *, frames,
+                            carry=None, sample_rate, frame_rate=250, chunk_size=1000):
+    """Controls of the WHOLE clip ([B, F, ...], the output of additive_controls) + frames = (f0, f1)
+    + carry [S, B, H] from the previous segment (None at f0 = 0) -> (audio [B, (f1 - f0) * U],
+    carry for the next segment).  Only frames f0 - 1 .. f1 of the controls are read.  inference=True
+    (angular_cumsum) only: the plain cumsum of training mode carries its unbounded float32 phase."""
+    amplitudes = core.tf_float32(amplitudes)
+    harmonic_distribution = core.tf_float32(harmonic_distribution)
+    harmonic_shifts = core.tf_float32(harmonic_shifts)
+    f0_hz = core.tf_float32(f0_hz)
+    dt = f0_hz.dtype.type
+    two_pi = dt(2.0 * np.pi)
+    f_lo, f_hi = frames
+    n_frames = f0_hz.shape[1]
+    U = int(sample_rate / frame_rate)
+    n_total = U * n_frames
+    i_lo, i_hi = f_lo * U, f_hi * U
+    if i_lo % chunk_size or (i_hi % chunk_size and f_hi != n_frames):
+        raise ValueError('segment boundaries must fall on angular_cumsum chunk boundaries')
+    n_harm = harmonic_distribution.shape[-1]
+    S = f0_hz.shape[-1]
+    # legacy bilinear coordinates of the global sample indices (core._resize_bilinear_legacy)
+    scale = dt(n_frames) / dt(n_total)
+    pos = np.arange(i_lo, i_hi).astype(dt) * scale
+    pos_floor = np.floor(pos)
+    lower = np.maximum(pos_floor.astype(np.int64), 0)
+    upper = np.minimum(np.ceil(pos).astype(np.int64), n_frames - 1)
+    lerp = (pos - pos_floor).astype(dt)
+    assert lower.min() >= max(f_lo - 1, 0) and upper.max() <= min(f_hi, n_frames - 1)      # the halo
+    # window resampler in closed form (core.upsample_with_windows): y[kU + r] = x[k] w[r + U] + x[k + 1] w[r]
+    window = core.hann_window(2 * U, dt)
+    k = np.arange(i_lo, i_hi) // U
+    r = np.arange(i_lo, i_hi) % U
+    k_next = np.minimum(k + 1, n_frames - 1)                                  # add_endpoint: last frame held
+    partial_amp = amplitudes * harmonic_distribution                          # :111-114
+    amp_env = partial_amp[:, k_next, :] * window[r][None, :, None] + partial_amp[:, k, :] * window[r + U][None, :, None]
+    audio, carry_out = None, []
+    for s in range(S):
+        partial_hz = core.get_harmonic_frequencies(f0_hz[..., s:s + 1], n_harm) * (dt(1.0) + harmonic_shifts)
+        top, bottom = partial_hz[:, lower, :], partial_hz[:, upper, :]
+        freq_env = top + (bottom - top) * lerp[None, :, None]                 # :117
+        amp = core.remove_above_nyquist(freq_env, amp_env, sample_rate)       # :65-67
+        omega = freq_env * two_pi / dt(float(sample_rate))                    # :69-70
+        B, n = omega.shape[:2]
+        pad = (-n) % chunk_size
+        if pad:
+            omega = np.pad(omega, [(0, 0), (0, pad), (0, 0)])
+        chunks = omega.reshape(B, -1, chunk_size, n_harm)
+        phase = np.cumsum(chunks, axis=2, dtype=dt)
+        ends = np.mod(phase[:, :, -1, :], two_pi)                             # [B, chunks, H]
+        start = np.zeros([B, 1, n_harm], dt) if carry is None else np.asarray(carry[s], dt)[:, None, :]
+        running = np.cumsum(np.concatenate([start, ends], axis=1), axis=1, dtype=dt)      # unwrapped, sequential
+        phase = np.mod(phase + np.mod(running[:, :-1], two_pi)[:, :, None, :], two_pi)
+        phase = phase.reshape(B, -1, n_harm)[:, :n]
+        carry_out.append(running[:, -1])
+        y = np.sum(amp * np.cos(phase), axis=-1, dtype=dt)                    # :80-83
+        audio = y if audio is None else audio + y
+    return audio, np.stack(carry_out)

@@ -273,3 +273,28 @@ def test_surrogate_restatement_matches_reference_execution(golden_dir, name):
     assert np.all((g['ctl_decays'] >= 1e-5) & (g['ctl_decays'] <= 1.0))
     sig = ref.surrogate_signal(**ctl, sample_rate=sr, inference=True)
     np.testing.assert_array_equal(sig, g['signal'])
+
+
+def test_additive_segments_with_carried_state_equal_the_whole_clip():
+    """SURVEY 8e-i/ii as a specification (oracle only; no kernel does this yet): frames [f0, f1) of a long
+    clip synthesised from one frame of halo on each side and the carried float32 chunk-offset sum are BIT
+    identical to the same samples of the whole-clip synthesis; restarting the phase per segment is not."""
+    rng = np.random.default_rng(3)
+    sr, B, F, H, S = 24000, 2, 375, 24, 2                 # three segments of 125 frames = 12 000 samples
+    f0 = (110.0 * 2 ** rng.uniform(0, 3, [B, 1, 1]) * (1 + 1e-3 * np.arange(S))[None, None, :])
+    f0 = np.broadcast_to(f0, [B, F, S]).astype(np.float32).copy()
+    f0[:, 200:, :] *= np.float32(1.122)                   # a pitch change inside the second segment
+    ctl = ref.additive_controls(rng.standard_normal([B, F, 1]).astype(np.float32),
+                                rng.standard_normal([B, F, H]).astype(np.float32),
+                                rng.uniform(1e-4, 1e-3, [B, F, 1]).astype(np.float32), f0, sample_rate=sr)
+    whole = ref.additive_signal(**ctl, sample_rate=sr, inference=True)
+    carry, parts = None, []
+    for lo in (0, 125, 250):
+        y, carry = ref.additive_signal_segment(**ctl, frames=(lo, lo + 125), carry=carry, sample_rate=sr)
+        parts.append(y)
+        assert carry.shape == (S, B, H) and carry.dtype == np.float32
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
+    restarted, _ = ref.additive_signal_segment(**ctl, frames=(125, 250), carry=None, sample_rate=sr)
+    assert not np.array_equal(restarted, whole[:, 12000:24000])
+    with pytest.raises(ValueError):
+        ref.additive_signal_segment(**ctl, frames=(1, 126), carry=None, sample_rate=sr)
