@@ -225,3 +225,31 @@ def test_script_midi_file_to_wav(tmp_path):
         n = 8192
         spec = np.abs(np.fft.rfft(x[2048:2048 + n] * np.hanning(n), 4 * n))
         assert abs(np.argmax(spec) * 24000 / (4 * n) - 440.0) < 4.0
+
+
+def test_script_main_with_a_stub_model(tmp_path, monkeypatch):
+    """The script's own logic (warm-up cut, the two output files, the piano id) around a stub model:
+    no GPU needed."""
+    import wave
+    import torch
+    import ddsp_piano_b200 as dp
+    s = _script()
+    seen = {}
+
+    class Stub:
+        def __call__(self, inputs):
+            seen.update(inputs)
+            n = inputs['conditioning'].shape[1] * 96
+            wet = torch.full([1, n], 0.25)
+            wet[0, :12000] = 1.0                         # the warm-up part must not reach the file
+            return {'audio_synth': wet, 'add': {'signal': wet * 0.5}}
+
+    monkeypatch.setattr(dp, 'maestro_v2_model', lambda *a, **k: Stub())
+    mid, out = str(tmp_path / 'n.mid'), str(tmp_path / 'n.wav')
+    write_smf(mid, [[(0, tempo(500000)), (0, on(60, 100)), (960, off(60))]])
+    s.main(s.process_args(['-u', '--piano_type', '3', mid, out]))
+    assert seen['piano_model'].tolist() == [[3]] and seen['conditioning'].shape == (1, 375, 16, 2)
+    for path, level in ((out, 8192), (out + '_unreverbed.wav', 4096)):
+        with wave.open(path, 'rb') as f:
+            assert (f.getframerate(), f.getnframes()) == (24000, 24000)
+            assert set(np.frombuffer(f.readframes(24000), '<i2').tolist()) == {level}
