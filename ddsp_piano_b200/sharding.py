@@ -12,6 +12,10 @@ Two regimes:
   neighbour exchange (``send`` to rank+1 / ``recv`` from rank-1) of an ``L-1``-sample carry that
   is added to the head of the receiving rank's timeline -- :func:`timeline_reverb`.
 
+A third piece, :func:`chain_carry`, is the rank-to-rank protocol for oscillator phase continuity
+across segments (specified by ``oracle/ddsp_piano_np.py::additive_signal_segment``; the kernels do
+not take a phase seed yet).
+
 The functions are backend-agnostic (``torch.distributed`` with NCCL on GPUs, gloo in the CPU
 tests); the convolution itself is injected (``conv_full``), on the GPU it is
 ``Engine.reverb_full`` (hand-written FFT convolution, 'valid'-padded).
@@ -86,6 +90,27 @@ def timeline_reverb(dry, ir, conv_full, rank=0, world=1, add_dry=True, group=Non
     flat[:incoming.shape[0]] += incoming          # PeerTimeline fuses this into the overlap-add kernel
     wet = flat.reshape(S, N)
     return wet + dry if add_dry else wet
+
+
+def chain_carry(finish, carry_like, rank, world, group=None):
+    """Order-preserving chain over ranks for state that must be accumulated in timeline order (the
+    oscillators' float32 chunk-offset sums across timeline segments, SURVEY 8e-i: float32 addition is
+    not associative, so a tree scan would not reproduce the whole-clip phases bit for bit).
+
+    ``finish(carry_in) -> (result, carry_out)`` completes this rank's span from the state at its start;
+    everything that does not depend on the carry (the in-chunk phase sums, the bulk of the work) belongs
+    BEFORE this call so that ranks only serialise on the seed.  Rank 0 starts from zeros; the carry is
+    ``carry_like``-shaped (12 KB per clip at config 2).  Returns ``result``."""
+    carry_in = torch.zeros_like(carry_like)
+    if rank > 0:
+        dist.recv(carry_in, src=rank - 1, group=group)
+    result, carry_out = finish(carry_in)
+    if rank + 1 < world:
+        if carry_out.shape != carry_like.shape or carry_out.dtype != carry_like.dtype:
+            raise ValueError(f'carry changed from {tuple(carry_like.shape)} {carry_like.dtype} to '
+                             f'{tuple(carry_out.shape)} {carry_out.dtype}')
+        dist.send(carry_out.contiguous(), dst=rank + 1, group=group)
+    return result
 
 
 class _DeviceBuffer:

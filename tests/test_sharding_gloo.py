@@ -95,3 +95,48 @@ def test_timeline_reverb_across_ranks(world, S, N, L, add_dry):
     assert sorted(r[0] for r in results) == list(range(world))
     for _, err, scale in results:
         assert err <= 2e-6 * max(scale, 1.0)
+
+
+def _phase_worker(rank, world, port, q):
+    """Each rank synthesises its third of a clip with the oracle's segment form; the chunk-offset carry
+    travels down the ranks through sharding.chain_carry."""
+    from oracle import ddsp_piano_np as ref
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)                         # same clip on every rank
+        sr, B, H, S, seg = 24000, 1, 16, 2, 125
+        F = world * seg
+        f0 = 220.0 * 2 ** rng.uniform(0, 2, [B, 1, 1]) * (1 + 1e-3 * np.arange(S))[None, None, :]
+        f0 = np.broadcast_to(f0, [B, F, S]).astype(np.float32).copy()
+        ctl = ref.additive_controls(rng.standard_normal([B, F, 1]).astype(np.float32),
+                                    rng.standard_normal([B, F, H]).astype(np.float32),
+                                    rng.uniform(1e-4, 1e-3, [B, F, 1]).astype(np.float32), f0, sample_rate=sr)
+
+        def finish(carry_in):
+            y, carry = ref.additive_signal_segment(**ctl, frames=(rank * seg, (rank + 1) * seg),
+                                                   carry=carry_in.numpy(), sample_rate=sr)
+            return y, torch.from_numpy(carry)
+
+        got = sharding.chain_carry(finish, torch.zeros(S, B, H), rank, world)
+        whole = ref.additive_signal(**ctl, sample_rate=sr, inference=True)
+        n = seg * 96
+        q.put((rank, bool(np.array_equal(got, whole[:, rank * n:(rank + 1) * n]))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_phase_carry_chain_across_ranks_is_bit_exact(world):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_phase_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
