@@ -13,8 +13,8 @@ Two regimes:
   is added to the head of the receiving rank's timeline -- :func:`timeline_reverb`.
 
 A third piece, :func:`chain_carry`, is the rank-to-rank protocol for oscillator phase continuity
-across segments (specified by ``oracle/ddsp_piano_np.py::additive_signal_segment``; the kernels do
-not take a phase seed yet).
+across segments (the carried state is specified in DESIGN.md section 6; the kernels do not take a
+phase seed yet).
 
 The functions are backend-agnostic (``torch.distributed`` with NCCL on GPUs, gloo in the CPU
 tests); the convolution itself is injected (``conv_full``), on the GPU it is
