@@ -323,3 +323,44 @@ def additive_signal_segment(amplitudes, harmonic_distribution, harmonic_shifts, 
         y = np.sum(amp * np.cos(phase), axis=-1, dtype=dt)                    # :80-83
         audio = y if audio is None else audio + y
     return audio, np.stack(carry_out)
+
+
+def noise_signal_segment(magnitudes, noise, *, frames, sample_rate, frame_rate=250, window_size=257):
+    """SURVEY 8e-iii as a specification: samples [f0 * U, f1 * U) of noise_signal on the whole clip,
+    bit for bit, from the frames that reach into them.  Frame f of the noise is filtered by its own
+    impulse response and laid down at f * U with a tail of fft_size - U samples, and the output is read
+    (Lir - 1) // 2 - 1 samples late (ddsp.core.fft_convolve, delay_compensation = -1), so a segment
+    needs ceil(fft_size / U) - 1 frames of halo before it (2 frames for M = 64, 5 for M = 96 at 24 kHz:
+    the zero-padded end of each transform is rounding noise, not zeros, and the whole-clip sum includes
+    it) and one frame after it; the per-sample sums run from the newest frame to the oldest, as
+    tf.signal.overlap_and_add (restated in core.fft_convolve) orders them.
+    magnitudes [B, F, M] (after noise_controls) and noise [B, N] are those of the WHOLE clip; only the
+    halo-extended range is read."""
+    magnitudes = core.tf_float32(magnitudes)
+    noise = core.tf_float32(noise)
+    dt = noise.dtype.type
+    B, F = magnitudes.shape[:2]
+    U = int(sample_rate / frame_rate)
+    f_lo, f_hi = frames
+    ir_size = 2 * (magnitudes.shape[-1] - 1)
+    if 1 <= window_size < ir_size:                              # a shorter window crops the response
+        ir_size = window_size
+    fft_size = core.get_fft_size(U, ir_size, power_of_2=True)
+    n_seg = -(-fft_size // U)
+    start = (ir_size - 1) // 2 - 1
+    fa, fb = max(0, f_lo - (n_seg - 1)), min(F, f_hi + 1)
+    ir = core.frequency_impulse_response(magnitudes[:, fa:fb], window_size=window_size)
+    assert ir.shape[-1] == ir_size
+    audio_frames = noise[:, fa * U:fb * U].reshape(B, fb - fa, U)
+    fr = np.fft.irfft(np.fft.rfft(audio_frames, fft_size) * np.fft.rfft(ir, fft_size), fft_size).astype(dt)
+    fr = np.pad(fr, [(0, 0), (0, 0), (0, n_seg * U - fft_size)]).reshape(B, fb - fa, n_seg, U)
+    i_lo, i_hi = f_lo * U + start, f_hi * U + start            # positions in the un-cropped overlap-add
+    j_lo, j_hi = i_lo // U, (i_hi - 1) // U
+    blocks = np.zeros([B, j_hi - j_lo + 1, U], dt)
+    for s in range(n_seg):                                      # newest frame first
+        for j in range(j_lo, j_hi + 1):
+            f = j - s
+            if fa <= f < fb:
+                blocks[:, j - j_lo] += fr[:, f - fa, s]
+    flat = blocks.reshape(B, -1)
+    return flat[:, i_lo - j_lo * U:i_hi - j_lo * U]

@@ -298,3 +298,20 @@ def test_additive_segments_with_carried_state_equal_the_whole_clip():
     assert not np.array_equal(restarted, whole[:, 12000:24000])
     with pytest.raises(ValueError):
         ref.additive_signal_segment(**ctl, frames=(1, 126), carry=None, sample_rate=sr)
+
+
+@pytest.mark.parametrize('M', [64, 96])
+def test_noise_segments_with_frame_halo_equal_the_whole_clip(M):
+    """SURVEY 8e-iii as a specification (oracle only): a segment of the filtered noise from its frames plus
+    ceil(fft / U) - 1 frames of halo before and one after is BIT identical to the whole-clip synthesis."""
+    rng = np.random.default_rng(5)
+    sr, B, F, U = 24000, 2, 60, 96
+    mags = ref.noise_controls(rng.standard_normal([B, F, M]).astype(np.float32) * 2 + 3)['magnitudes']
+    noise = rng.uniform(-1, 1, [B, F * U]).astype(np.float32)
+    whole = ref.noise_signal(mags, noise)
+    parts = [ref.noise_signal_segment(mags, noise, frames=(lo, hi), sample_rate=sr)
+             for lo, hi in ((0, 20), (20, 27), (27, 60))]
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
+    # without the halo (the segment treated as its own clip, as the kernels do today) the head differs
+    alone = ref.noise_signal(mags[:, 20:27], noise[:, 20 * U:27 * U])
+    assert not np.array_equal(alone, whole[:, 20 * U:27 * U])
