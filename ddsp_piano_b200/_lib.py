@@ -41,6 +41,19 @@ class Voice(ctypes.Structure):
                 ('magnitudes', ctypes.c_void_p), ('noise', ctypes.c_void_p)]
 
 
+class Link(ctypes.Structure):
+    """``b200ddsp_link``: one rank's end of a stream-ordered hand-off through peer memory."""
+    _fields_ = [('seed', ctypes.c_void_p), ('seed_ready', ctypes.c_void_p), ('seed_ack', ctypes.c_void_p),
+                ('carry', ctypes.c_void_p), ('carry_ready', ctypes.c_void_p), ('carry_ack', ctypes.c_void_p),
+                ('epoch', ctypes.c_ulonglong), ('scratch', ctypes.c_void_p)]
+
+
+class Span(ctypes.Structure):
+    """``b200ddsp_span``: which frames of a timeline a call reads and synthesises."""
+    _fields_ = [('in_first_frame', ctypes.c_longlong), ('out_first_frame', ctypes.c_longlong),
+                ('n_out_frames', ctypes.c_int), ('total_frames', ctypes.c_longlong), ('phase', Link)]
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
                   if f.endswith(('.cu', '.cuh', '.inl'))) + [HEADER]
@@ -127,8 +140,21 @@ def load():
     lib.b200ddsp_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     lib.b200ddsp_peer_close.restype = ci
     lib.b200ddsp_peer_close.argtypes = [vp, vp]
-    lib.b200ddsp_timeline_overlap_add.restype = ci
-    lib.b200ddsp_timeline_overlap_add.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
+    span_p, link_p = ctypes.POINTER(Span), ctypes.POINTER(Link)
+    lib.b200ddsp_forward_span.restype = ci
+    lib.b200ddsp_forward_span.argtypes = [vp, ctypes.POINTER(Voice), ci, vp, ci, ci, ci, ci, ci, u64,
+                                          span_p, vp, sz, vp]
+    lib.b200ddsp_forward_timeline.restype = ci
+    lib.b200ddsp_forward_timeline.argtypes = [vp, ctypes.POINTER(Voice), ci, vp, vp, vp, ci, ci, ci, ci, ci,
+                                              ci, ci, u64, span_p, link_p, vp, sz, vp]
+    lib.b200ddsp_forward_timeline_host.restype = ci
+    lib.b200ddsp_forward_timeline_host.argtypes = lib.b200ddsp_forward_timeline.argtypes
+    lib.b200ddsp_timeline_workspace_bytes.restype = sz
+    lib.b200ddsp_timeline_workspace_bytes.argtypes = [vp] + [ci] * 11
+    lib.b200ddsp_timeline_reverb.restype = ci
+    lib.b200ddsp_timeline_reverb.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, link_p, vp, sz, vp]
+    lib.b200ddsp_timeline_reverb_workspace_bytes.restype = sz
+    lib.b200ddsp_timeline_reverb_workspace_bytes.argtypes = [vp, ci, ci, ci, ci]
     lib.b200ddsp_note_release.restype = ci
     lib.b200ddsp_note_release.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.b200ddsp_gru_recurrence.restype = ci
@@ -163,7 +189,9 @@ EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200dd
            'b200ddsp_workspace_bytes', 'b200ddsp_additive_workspace_bytes',
            'b200ddsp_additive_controls', 'b200ddsp_additive_signal',
            'b200ddsp_noise_controls', 'b200ddsp_noise_signal', 'b200ddsp_noise_workspace_bytes', 'b200ddsp_reverb', 'b200ddsp_reverb_full', 'b200ddsp_fft_convolve', 'b200ddsp_ir_decay_mask', 'b200ddsp_note_release', 'b200ddsp_gru_recurrence', 'b200ddsp_surrogate_decays', 'b200ddsp_surrogate_signal', 'b200ddsp_peer_alloc', 'b200ddsp_peer_free',
-           'b200ddsp_peer_open', 'b200ddsp_peer_close', 'b200ddsp_timeline_overlap_add', 'b200ddsp_fdn_ir',
+           'b200ddsp_peer_open', 'b200ddsp_peer_close', 'b200ddsp_forward_span', 'b200ddsp_forward_timeline',
+           'b200ddsp_forward_timeline_host', 'b200ddsp_timeline_workspace_bytes', 'b200ddsp_timeline_reverb',
+           'b200ddsp_timeline_reverb_workspace_bytes', 'b200ddsp_fdn_ir',
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
            'b200ddsp_workspace_bytes_host', 'b200ddsp_midi_roll_to_conditioning',

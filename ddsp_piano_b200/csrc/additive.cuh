@@ -23,6 +23,7 @@
 // shared by HP oscillators and the per-frame control loads are coalesced.
 #pragma once
 #include "common.cuh"
+#include "link.cuh"
 
 namespace b200ddsp {
 
@@ -43,6 +44,8 @@ struct AdditiveArgs {
   int B, P, F, H, S, U, N;
   int chunk, n_chunks;
   int voices_per_group;
+  int koff;             // input frame of output sample 0 (spans: halo frames in front; else 0)
+  int seeded;           // chunk 0 has an offset too (a span that continues a timeline)
   int accumulate;       // out += (only honoured when gridDim.z == 1)
   float scale;          // float32(F) / float32(N)
   float nyquist;        // float32(sr / 2)
@@ -272,40 +275,72 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
   }
 }
 
-// Chunk end phases -> chunk offsets, in place (ddsp angular_cumsum: shift down one chunk,
-// cumsum over chunks in float32, then mod 2pi).  One thread per (row, substring, partial); the
-// loads of a batch of chunks are issued together so that the loop is not one L2 round trip per
-// chunk.  ends_na (optional): 16-partial half-groups >= ends_na[row, c] were not computed for chunk c and count
+// Chunk end phases -> chunk offsets, in place (ddsp angular_cumsum: shift down one chunk, cumsum over
+// chunks in float32, then mod 2pi).  The running sum is sequential per oscillator (float32 addition is
+// not associative and the reference's order is part of its output), so: one CTA per (row, substring,
+// block of 32 partials); all threads stage a tile of chunk ends in shared memory (coalesced: 32
+// consecutive partials per chunk), ONE warp walks the tile adding sequentially, all threads store the
+// wrapped offsets.  A 1152-chunk span costs the same few microseconds as a 72-chunk clip.
+// ends_na (optional): 16-partial half-groups >= ends_na[row, c] were not computed for chunk c and count
 // as 0 (no later chunk reads their offset).
-__global__ void __launch_bounds__(256) additive_offsets_kernel(float* offsets,
-                                                                const unsigned char* ends_na,
-                                                                int n_osc_rows, int n_chunks, int H,
-                                                                int S) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_osc_rows * H) return;
-  const int rs = i / H, h = i - rs * H;
+// Spans of a timeline (b200ddsp_span): the sum starts from the predecessor's state `link.seed` instead
+// of 0 and its final value (including the LAST chunk's end, carry_all) goes to `link.carry` -- which
+// may be the successor GPU's inbox; see link.cuh for the hand-off.
+constexpr int kOffTile = 128;   // chunks per shared-memory tile
+
+struct OffsetsArgs {
+  float* offsets;                 // [n_osc_rows, n_chunks, H]
+  const unsigned char* ends_na;   // [n_osc_rows / S, n_chunks] or nullptr
+  int n_osc_rows, n_chunks, H, S;
+  int carry_all;                  // the last chunk's end phase is part of the sum (a carry is wanted)
+  Link link;                      // payload [n_osc_rows, H]
+};
+
+__global__ void __launch_bounds__(256) additive_offsets_kernel(const OffsetsArgs a) {
+  __shared__ float tile[kOffTile][33];
+  const int hb = (a.H + 31) / 32;
+  const int rs = blockIdx.x / hb, h0 = (blockIdx.x - rs * hb) * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = h0 + lane;
   const int group = h >> 4;   // liveness is counted in 16-partial half-groups
-  const unsigned char* na = ends_na ? ends_na + (size_t)(rs / S) * n_chunks : nullptr;
-  float* p = offsets + (size_t)rs * n_chunks * H + h;
+  const unsigned char* na = a.ends_na ? a.ends_na + (size_t)(rs / a.S) * a.n_chunks : nullptr;
+  float* p = a.offsets + (size_t)rs * a.n_chunks * a.H + h;
+  const Link& lk = a.link;
   float cum = 0.f;
-  constexpr int kBatch = 8;
-  for (int c0 = 0; c0 < n_chunks; c0 += kBatch) {
-    float e[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
+  if (lk.seed != nullptr) {
+    if (threadIdx.x == 0) link_wait(lk.seed_ready, lk.epoch, lk.scratch);
+    __syncthreads();
+    if (warp == 0 && h < a.H) cum = ld_inbox(lk.seed + (size_t)rs * a.H + h);
+  }
+  const int last_end = a.carry_all ? a.n_chunks : a.n_chunks - 1;   // chunks whose end phase counts
+  for (int c0 = 0; c0 < a.n_chunks; c0 += kOffTile) {
+    const int nc = min(kOffTile, a.n_chunks - c0);
+    for (int j = warp; j < nc; j += 8) {
       const int c = c0 + j;
-      const bool have = (c < n_chunks - 1) && (na == nullptr || group < (int)na[c]);
-      e[j] = have ? p[(size_t)c * H] : 0.f;
+      const bool have = (h < a.H) && (c < last_end) && (na == nullptr || group < (int)na[c]);
+      tile[j][lane] = have ? p[(size_t)c * a.H] : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const int c = c0 + j;
-      if (c < n_chunks) {
-        p[(size_t)c * H] = floormod_two_pi(cum);
-        cum = __fadd_rn(cum, e[j]);
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 8
+      for (int j = 0; j < nc; ++j) {
+        const float e = tile[j][lane];
+        tile[j][lane] = cum;             // offset of chunk c0 + j, unwrapped
+        cum = __fadd_rn(cum, e);
       }
     }
+    __syncthreads();
+    for (int j = warp; j < nc; j += 8)
+      if (h < a.H) p[(size_t)(c0 + j) * a.H] = floormod_two_pi(tile[j][lane]);
+    __syncthreads();
   }
+  if (lk.carry != nullptr) {
+    if (threadIdx.x == 0 && lk.carry_ack != nullptr && lk.epoch > 2)
+      link_wait(lk.carry_ack, lk.epoch - 2, lk.scratch);
+    __syncthreads();
+    if (warp == 0 && h < a.H) lk.carry[(size_t)rs * a.H + h] = cum;
+  }
+  link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr);
 }
 
 }  // namespace b200ddsp

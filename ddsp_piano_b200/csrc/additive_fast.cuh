@@ -47,12 +47,15 @@ struct AdditiveFastArgs {
 // ---- lerp table --------------------------------------------------------------------------------
 // lerp[t] = in - floor(in), in = float(t) * float(F/N): the legacy ResizeBilinear weight.  It depends
 // on the sample index only, so it is computed once per call instead of once per oscillator-sample.
+// Spans of a timeline: the coordinate is taken on the GLOBAL sample index tg0 + t and `scale` is that
+// of the whole timeline (the reference resizes the whole piece in one call).
 __global__ void __launch_bounds__(256) additive_lerp_kernel(float* __restrict__ lerp, int N, int U,
-                                                            float scale) {
+                                                            float scale, int tg0) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
-  const float in = __fmul_rn((float)t, scale);
-  lerp[t] = __fadd_rn(in, -(float)(t / U));   // fast path: floor(in) == t / U (checked on the host)
+  const int tg = tg0 + t;
+  const float in = __fmul_rn((float)tg, scale);
+  lerp[t] = __fadd_rn(in, -(float)(tg / U));   // fast path: floor(in) == tg / U (checked on the host)
 }
 
 // ---- liveness scan ---------------------------------------------------------------------------
@@ -82,13 +85,14 @@ __global__ void __launch_bounds__(256) additive_alive_frames_kernel(
 // One CTA per row; shared memory holds the row's synth_na.
 __global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
     const unsigned char* __restrict__ na_frame, unsigned char* __restrict__ synth_na,
-    unsigned char* __restrict__ ends_na, int F, int U, int N, int chunk, int n_chunks) {
+    unsigned char* __restrict__ ends_na, int F, int U, int N, int chunk, int n_chunks, int koff,
+    int carry_na) {
   extern __shared__ unsigned char sna[];   // [n_chunks]
   const int row = blockIdx.x;
   const unsigned char* nf = na_frame + (size_t)row * F;
   for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
     const int t0 = c * chunk, t1 = min(N, t0 + chunk) - 1;
-    const int k0 = t0 / U, k1 = min(F - 1, t1 / U + 1);
+    const int k0 = koff + t0 / U, k1 = min(F - 1, koff + t1 / U + 1);
     int m = 0;
     for (int k = k0; k <= k1; ++k) m = max(m, (int)nf[k]);
     sna[c] = (unsigned char)m;
@@ -105,8 +109,10 @@ __global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
   __syncthreads();
   int later = 0;
   for (int j = threadIdx.x + 1; j < (int)blockDim.x; ++j) later = max(later, span_max[j]);
+  // carry_na > 0 (a span whose phase state is handed on): what sounds after the span is not known
+  // here, so every half-group's chain is followed through every chunk
   for (int c = hi - 1; c >= lo; --c) {
-    ends_na[(size_t)row * n_chunks + c] = (unsigned char)later;
+    ends_na[(size_t)row * n_chunks + c] = (unsigned char)(carry_na > 0 ? carry_na : later);
     later = max(later, (int)sna[c]);
   }
 }
@@ -351,6 +357,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
   OscStateH<NC> st;
   int k = t0 / a.U;
   int r = t0 - k * a.U;
+  k += a.koff;                                         // input frame (spans carry halo frames in front)
   bool steady;
   int amp_mode;
   enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
@@ -359,7 +366,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     st.ph[j] = 0.f;
     st.off[j] = 0.f;
     const int h = l + LW * j;
-    if (!ENDS_ONLY && c > 0 && h < a.H)
+    if (!ENDS_ONLY && (c > 0 || a.seeded) && h < a.H)
       st.off[j] = a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h];
   }
   constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
@@ -471,7 +478,7 @@ __device__ __forceinline__ int list_append_slot(int* counter, bool active, int k
 __global__ void __launch_bounds__(256) additive_plan_kernel(
     const unsigned char* __restrict__ synth_na, const unsigned char* __restrict__ ends_na,
     AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks, int B,
-    const PlanGroups groups) {
+    const PlanGroups groups, int carry_all) {
   // lists: [kPlanSlots][kMaxGroups][n_units]
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = i < n_units;
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
     if (ns > 0) lists[(size_t)key * n_units + pos] = i;
   }
   const int ne = in_range ? ends_na[i] : 0;
-  const bool ends = ne > 0 && c < n_chunks - 1;
+  const bool ends = ne > 0 && (c < n_chunks - 1 || carry_all);
   {
     const int key = ne - 1;
     const int pos = list_append_slot(ends ? &plan->count[0][ne - 1] : nullptr, ends, key);

@@ -581,6 +581,26 @@ static bool additive_fast_path(b200ddsp_handle* h, int F, int H) {
          lerp_is_uniform(h, F, F * U, U);
 }
 
+// A span of a timeline as the kernels see it (b200ddsp_span validated and reduced; null = the call
+// covers whole clips).
+struct SpanInfo {
+  int koff;            // input frame of output frame 0
+  int F_out;           // frames synthesised
+  int tg0;             // global sample index of output sample 0
+  int total_frames;    // frames of the whole timeline
+  bool seeded;         // not the start of the timeline: chunk 0 has an offset
+  bool carry;          // the phase state at the span's end is wanted
+  Link phase;
+};
+
+static Link to_link(const b200ddsp_link& l) {
+  Link k{};
+  k.seed = l.seed; k.seed_ready = l.seed_ready; k.seed_ack = l.seed_ack;
+  k.carry = l.carry; k.carry_ready = l.carry_ready; k.carry_ack = l.carry_ack;
+  k.epoch = l.epoch; k.scratch = l.scratch;
+  return k;
+}
+
 // What the mixer needs to know about the additive partial signals.
 struct AdditiveResult {
   const float* partials;        // [n_partials, B, N]
@@ -602,16 +622,29 @@ struct AdditiveRun {
   unsigned char *na_frame, *synth_na, *ends_na;
   PlanGroups groups;
   float* partials;
+  const SpanInfo* span;
 };
 
 static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, const float* hd,
                           const float* shifts, const float* f0, char* base, const AdditiveLayout& lay,
                           int P, int B, int F, int H, int S, const PlanGroups& groups,
-                          const float* decays = nullptr, const float* decay_time = nullptr) {
-  const int U = h->U, N = F * U;
+                          const float* decays = nullptr, const float* decay_time = nullptr,
+                          const SpanInfo* span = nullptr) {
+  const int U = h->U, N = (span ? span->F_out : F) * U;
+  // legacy-bilinear coordinates are those of the whole timeline
+  const int F_all = span ? span->total_frames : F, N_all = F_all * U;
+  r->span = span;
   if (H < 1 || H > 256) return fail(h, B200DDSP_BAD_SHAPE, "H=%d outside [1, 256]", H);
   if (S < 1 || S > 32) return fail(h, B200DDSP_BAD_SHAPE, "S=%d outside [1, 32]", S);
-  r->fast = additive_fast_path(h, F, H) && decays == nullptr;   // the surrogate runs on the generic kernel
+  r->fast = additive_fast_path(h, F_all, H) && decays == nullptr;   // the surrogate runs on the generic kernel
+  if (span && !r->fast)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "spans of a timeline are implemented on the fast additive path only (U %% 8 == 0, "
+                "H <= 128, uniform resize coordinates); got U=%d H=%d", U, H);
+  if (span && !h->cfg.inference)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "spans of a timeline need inference=1: the plain cumsum of training mode carries an "
+                "unbounded float32 phase");
   if (!r->fast && !lerp_is_uniform(h, F, N, U) && !lerp_is_supported(F, N, U))
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
@@ -643,8 +676,10 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.chunk = chunk_for(h, N);
   a.n_chunks = r->n_chunks;
   a.voices_per_group = (P + r->G - 1) / r->G;
+  a.koff = span ? span->koff : 0;
+  a.seeded = (span && span->seeded) ? 1 : 0;
   a.accumulate = 0;
-  a.scale = (float)F / (float)N;
+  a.scale = (float)F_all / (float)N_all;
   a.nyquist = (float)(h->cfg.sample_rate / 2.0);
   a.sr = (float)h->cfg.sample_rate;
   a.inv_sr = 1.0f / a.sr;
@@ -733,6 +768,7 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
                                cudaStream_t st, cudaEvent_t small_kernels_done = nullptr) {
   const AdditiveArgs& a = r.a;
   const int R = r.P * r.B;
+  const bool carry = r.span && r.span->carry;
   if (r.fast) {
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
@@ -741,32 +777,39 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
                                                                         R * r.F, r.H);
         CHECK_LAUNCH(h, "additive_alive_frames_kernel");
       }
-      additive_lerp_kernel<<<(a.N + 255) / 256, 256, 0, st>>>((float*)r.fa.lerp, a.N, a.U, a.scale);
+      additive_lerp_kernel<<<(a.N + 255) / 256, 256, 0, st>>>((float*)r.fa.lerp, a.N, a.U, a.scale,
+                                                               r.span ? r.span->tg0 : 0);
       CHECK_LAUNCH(h, "additive_lerp_kernel");
       additive_alive_chunks_kernel<<<R, 128, (size_t)r.n_chunks, st>>>(
-          r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks);
+          r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks, a.koff,
+          carry ? (r.H + 15) / 16 : 0);
       CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
       CUDA_TRY(h, cudaMemsetAsync(r.fa.plan, 0, sizeof(AdditivePlan), st));
       const int n_units = R * r.n_chunks;
       additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(
-          r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, n_units, r.n_chunks, r.B, r.groups);
+          r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, n_units, r.n_chunks, r.B, r.groups,
+          carry ? 1 : 0);
       CHECK_LAUNCH(h, "additive_plan_kernel");
     }
     if (small_kernels_done) {
       CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
       small_kernels_done = nullptr;
     }
-    if (r.n_chunks > 1) {
-      {
-        StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
-        AdditiveFastArgs fa = r.fa;
-        fa.slot = 0;
-        launch_additive_fast(fa, true, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), 0, st);
-        CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
-      }
-      const int n = R * r.S * r.H;
-      additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, r.ends_na, R * r.S,
-                                                               r.n_chunks, r.H, r.S);
+    if (r.n_chunks > 1 || carry) {
+      StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
+      AdditiveFastArgs fa = r.fa;
+      fa.slot = 0;
+      launch_additive_fast(fa, true, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), 0, st);
+      CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
+    }
+    if (r.n_chunks > 1 || carry || (r.span && r.span->seeded)) {
+      OffsetsArgs oa{};
+      oa.offsets = a.offsets;
+      oa.ends_na = r.ends_na;
+      oa.n_osc_rows = R * r.S; oa.n_chunks = r.n_chunks; oa.H = r.H; oa.S = r.S;
+      oa.carry_all = carry ? 1 : 0;
+      if (r.span) oa.link = r.span->phase;
+      additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
       CHECK_LAUNCH(h, "additive_offsets_kernel");
     }
     return B200DDSP_OK;
@@ -778,9 +821,10 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       CHECK_LAUNCH(h, "additive_kernel<ends>");
     }
     StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
-    const int n = R * r.S * r.H;
-    additive_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.offsets, nullptr, R * r.S, r.n_chunks,
-                                                             r.H, r.S);
+    OffsetsArgs oa{};
+    oa.offsets = a.offsets;
+    oa.n_osc_rows = R * r.S; oa.n_chunks = r.n_chunks; oa.H = r.H; oa.S = r.S;
+    additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
     CHECK_LAUNCH(h, "additive_offsets_kernel");
   }
   if (small_kernels_done) CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
@@ -956,8 +1000,10 @@ extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitud
 static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn,
                             const NoiseVoicePtrs& vp, int v0, int v1, int slice0, int n_slices,
                             float* noise_part, int B, int F, int M, unsigned long long seed,
-                            unsigned long long stream_id, float* taps, cudaStream_t st) {
+                            unsigned long long stream_id, float* taps, cudaStream_t st,
+                            const SpanInfo* span = nullptr, long long in_first_frame = 0) {
   const int U = h->U;
+  const int F_out = span ? span->F_out : F;
   if (M != h->cfg.n_noise_bands || !h->d_cmat_t)
     return fail(h, B200DDSP_BAD_SHAPE, "M=%d but the handle was created for n_noise_bands=%d", M,
                 h->cfg.n_noise_bands);
@@ -989,7 +1035,9 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   a.v_begin = v0;
   a.v_end = v1;
   a.slice0 = slice0;
-  a.B = B; a.F = F; a.M = M; a.U = U; a.N = F * U;
+  a.B = B; a.F = F; a.M = M; a.U = U; a.N = F_out * U;
+  a.koff = span ? span->koff : 0;
+  a.sample0 = (unsigned long long)in_first_frame * (unsigned long long)U;
   a.tap_pitch = tap_pitch;
   a.halo_before = (M + U - 1) / U;
   a.halo_after = (U + M - 5) / U;
@@ -1003,7 +1051,7 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   const int n_blocks = U / 8;
   const int nb = (n_blocks + 15) / 16;
   const int warps = (n_blocks + nb - 1) / nb;
-  dim3 grid((F + kNoiseFrames - 1) / kNoiseFrames, B, n_slices);
+  dim3 grid((F_out + kNoiseFrames - 1) / kNoiseFrames, B, n_slices);
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1327,6 +1375,181 @@ extern "C" int b200ddsp_fft_convolve(b200ddsp_handle* h, const float* audio, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// reverb of a span of a timeline (timeline.cuh): per-segment 'valid' convolution with the timeline's
+// impulse response, then ONE kernel for the overlap-add and both ends of the tail hand-off
+// ---------------------------------------------------------------------------------------------
+struct TimelineReverbPlan {
+  const float* ir;            // [B, L] device
+  int B, n_seg, N, L, nfft, add_dry;
+  float2 *tw, *buf_a, *buf_b; // twiddles; ping-pong buffers of B + ceil(rows / 2) transforms each
+  float4 *scales, *ir_scales; // [rows], [B]
+  unsigned int* maxima;       // [rows + B][2]
+  float* wet_full;            // [rows, N + L - 1]
+  mutable const float2* ir_spectra;
+  Link tail;
+};
+
+struct TimelineReverbLayout { size_t tw, buf_a, buf_b, wet_full, total; int nfft; };
+
+static TimelineReverbLayout carve_timeline_reverb(size_t at, int B, int n_seg, int N, int L) {
+  TimelineReverbLayout t{};
+  const size_t rows = (size_t)B * n_seg, pairs = (rows + 1) / 2;
+  t.nfft = fft_size_for(N, L);
+  size_t o = at;
+  auto take = [&](size_t bytes) { size_t p = o; o += align_up(bytes); return p; };
+  t.tw = take((size_t)t.nfft * 8 + (rows + B) * 16 + (rows + B) * 8);
+  t.buf_a = take((B + pairs) * (size_t)t.nfft * 8);
+  t.buf_b = take((B + pairs) * (size_t)t.nfft * 8);
+  t.wet_full = take(rows * (size_t)(N + L - 1) * 4);
+  t.total = o;
+  return t;
+}
+
+static TimelineReverbPlan timeline_plan(const b200ddsp_handle* h, char* base, const TimelineReverbLayout& lay,
+                                        const float* ir, int B, int n_seg, int N, int L, const Link& tail) {
+  TimelineReverbPlan p{};
+  const size_t rows = (size_t)B * n_seg;
+  p.ir = ir; p.B = B; p.n_seg = n_seg; p.N = N; p.L = L; p.nfft = lay.nfft;
+  p.add_dry = h->cfg.reverb_add_dry ? 1 : 0;
+  p.tw = (float2*)(base + lay.tw);
+  p.scales = reinterpret_cast<float4*>(p.tw + lay.nfft);
+  p.ir_scales = p.scales + rows;
+  p.maxima = reinterpret_cast<unsigned int*>(p.ir_scales + B);
+  p.buf_a = (float2*)(base + lay.buf_a);
+  p.buf_b = (float2*)(base + lay.buf_b);
+  p.wet_full = (float*)(base + lay.wet_full);
+  p.tail = tail;
+  return p;
+}
+
+static int timeline_reverb_ir_phase(b200ddsp_handle* h, const TimelineReverbPlan& p, cudaStream_t st) {
+  const int n = p.nfft, rows = p.B * p.n_seg;
+  const std::vector<int> radices = fft_radices(n);
+  fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.tw, n);
+  CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  CUDA_TRY(h, cudaMemsetAsync(p.maxima, 0, (size_t)(rows + p.B) * 8, st));
+  unsigned int* max_ir = p.maxima + 2 * rows;
+  reverb_maxima1_kernel<<<dim3(32, p.B), 256, 0, st>>>(p.ir, max_ir, p.L, 1, 1);
+  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  timeline_scales_kernel<<<(rows + 63) / 64, 64, 0, st>>>(nullptr, max_ir, p.scales, p.ir_scales, rows, p.n_seg);
+  CHECK_LAUNCH(h, "timeline_scales_kernel");
+  float2* src = nullptr;
+  float2* dst = p.buf_a;
+  int Ns = 1;
+  for (size_t i = 0; i < radices.size(); ++i) {
+    const StoreComplex sto{dst, n};
+    if (i == 0) launch_fft_pass(radices[i], LoadRealSingle{p.ir, p.ir_scales, p.L, 1}, sto, p.tw, n, Ns, p.B, st);
+    else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, p.tw, n, Ns, p.B, st);
+    CHECK_LAUNCH(h, "fft_pass_kernel<ir>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == p.buf_a) ? p.buf_b : p.buf_a;
+  }
+  p.ir_spectra = src;
+  return B200DDSP_OK;
+}
+
+static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbPlan& p, const float* dry,
+                                       float* out, cudaStream_t st) {
+  StageTimer tm(h, B200DDSP_STAGE_REVERB, st);
+  const int n = p.nfft, rows = p.B * p.n_seg, pairs = (rows + 1) / 2;
+  const std::vector<int> radices = fft_radices(n);
+  const int n_pass = (int)radices.size();
+  reverb_maxima1_kernel<<<dim3(32, rows), 256, 0, st>>>(dry, p.maxima, p.N, 0, 0);
+  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  timeline_scales_kernel<<<(rows + 63) / 64, 64, 0, st>>>(p.maxima, p.maxima + 2 * rows, p.scales, nullptr, rows,
+                                                          p.n_seg);
+  CHECK_LAUNCH(h, "timeline_scales_kernel");
+  float2* wa = p.buf_a + (size_t)p.B * n;
+  float2* wb = p.buf_b + (size_t)p.B * n;
+  float2* src = nullptr;
+  float2* dst = wa;
+  int Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const StoreComplex sto{dst, n};
+    if (i == 0) launch_fft_pass(radices[i], LoadRealPair{dry, p.scales, p.N, 0, rows, 0}, sto, p.tw, n, Ns, pairs, st);
+    else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, p.tw, n, Ns, pairs, st);
+    CHECK_LAUNCH(h, "fft_pass_kernel<forward>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  {
+    dim3 grid((n / 2 + 1 + 255) / 256, pairs);
+    timeline_spectrum_kernel<<<grid, 256, 0, st>>>(src, p.ir_spectra, dst, n, rows, p.n_seg);
+    CHECK_LAUNCH(h, "timeline_spectrum_kernel");
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  const int total = p.N + p.L - 1;
+  Ns = 1;
+  for (int i = 0; i < n_pass; ++i) {
+    const LoadComplex ld{src, n};
+    if (i == n_pass - 1) {
+      const StoreWetPair sto{p.wet_full, dry, p.scales, p.N, total, rows, 1.0f / (float)n, 0};
+      launch_fft_pass(radices[i], ld, sto, p.tw, n, Ns, pairs, st);
+    } else {
+      launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, p.tw, n, Ns, pairs, st);
+    }
+    CHECK_LAUNCH(h, "fft_pass_kernel<inverse>");
+    Ns *= radices[i];
+    src = dst;
+    dst = (dst == wa) ? wb : wa;
+  }
+  TimelineTailArgs ta{};
+  ta.wet_full = p.wet_full;
+  ta.dry = p.add_dry ? dry : nullptr;
+  ta.out = out;
+  ta.B = p.B; ta.n_seg = p.n_seg; ta.N = p.N; ta.total = total;
+  const long long span = (long long)p.n_seg * p.N;
+  const int tail = p.L - 1;
+  ta.tail_ctas = p.tail.carry ? (tail + 255) / 256 : 0;
+  ta.body_ctas = (int)((span - tail + 255) / 256);
+  ta.head_ctas = (tail + 255) / 256;
+  ta.link = p.tail;
+  timeline_tail_kernel<<<dim3(ta.tail_ctas + ta.body_ctas + ta.head_ctas, p.B), 256, 0, st>>>(ta);
+  CHECK_LAUNCH(h, "timeline_tail_kernel");
+  return B200DDSP_OK;
+}
+
+static int check_timeline_reverb(b200ddsp_handle* h, int B, int n_seg, int N, int L) {
+  if (B < 1 || n_seg < 1 || N < 1 || L < 1 || B > 65535 || (long long)B * n_seg > 65535)
+    return fail(h, B200DDSP_BAD_SHAPE, "B=%d n_seg=%d N=%d L=%d", B, n_seg, N, L);
+  if ((long long)(L - 1) > (long long)n_seg * N)
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "the reverb tail (%d samples) is longer than the span (%d segments x %d)", L - 1, n_seg, N);
+  if ((long long)N + L - 1 > (1ll << 28))
+    return fail(h, B200DDSP_BAD_SHAPE, "N + L - 1 = %lld exceeds 2^28", (long long)N + L - 1);
+  return B200DDSP_OK;
+}
+
+extern "C" size_t b200ddsp_timeline_reverb_workspace_bytes(const b200ddsp_handle* h, int B, int n_seg, int N,
+                                                           int L) {
+  if (!h || B < 1 || n_seg < 1 || N < 1 || L < 1) return 0;
+  return carve_timeline_reverb(0, B, n_seg, N, L).total;
+}
+
+extern "C" int b200ddsp_timeline_reverb(b200ddsp_handle* h, const float* dry, const float* reverb_ir,
+                                        float* out, int B, int n_seg, int N, int L, const b200ddsp_link* tail,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!dry || !reverb_ir || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
+  if (out == dry) return fail(h, B200DDSP_BAD_ARGUMENT, "out may not alias dry");
+  if (int rc = check_timeline_reverb(h, B, n_seg, N, L)) return rc;
+  const TimelineReverbLayout lay = carve_timeline_reverb(0, B, n_seg, N, L);
+  if (!workspace || workspace_bytes < lay.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "timeline_reverb needs %zu workspace bytes, got %zu",
+                lay.total, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  reset_stage_flags(h);
+  const TimelineReverbPlan p = timeline_plan(h, (char*)workspace, lay, reverb_ir, B, n_seg, N, L,
+                                             tail ? to_link(*tail) : Link{});
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = timeline_reverb_ir_phase(h, p, st)) return rc;
+  return timeline_reverb_audio_phase(h, p, dry, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // feedback-delay-network impulse response
 // ---------------------------------------------------------------------------------------------
 
@@ -1396,8 +1619,9 @@ struct ForwardSync {
 static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, const float* reverb_ir,
                         float* dry_out, float* wet_out, int B, int F, int H, int S, int M, int L,
                         uint64_t seed, char* base, const WorkspaceLayout& w, const ForwardSync* sync,
-                        cudaStream_t st) {
-  const int U = h->U, N = F * U;
+                        cudaStream_t st, const SpanInfo* span = nullptr, long long in_first_frame = 0,
+                        const TimelineReverbPlan* tl = nullptr) {
+  const int U = h->U, N = (span ? span->F_out : F) * U;
   float* amp = (float*)(base + w.amp);
   float* hd = (float*)(base + w.hd);
   float* shifts = (float*)(base + w.shifts);
@@ -1420,7 +1644,8 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   }
   reset_stage_flags(h);
   AdditiveRun run;
-  if (int rc = additive_begin(h, &run, amp, hd, shifts, f0, base, w.add, P, B, F, H, S, w.groups))
+  if (int rc = additive_begin(h, &run, amp, hd, shifts, f0, base, w.add, P, B, F, H, S, w.groups, nullptr,
+                              nullptr, span))
     return rc;
   AdditiveControlsArgs ca = controls_args(h, B * F, H, S);
   ca.amp_out = amp; ca.hd_out = hd; ca.shifts_out = shifts; ca.f0_out = f0;
@@ -1441,7 +1666,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
       const int s0 = n_slices * hf / halves, s1 = n_slices * (hf + 1) / halves;
       if (sync) CUDA_TRY(h, cudaStreamWaitEvent(ns, sync->mags_ready[hf], 0));
       if (int rc = run_noise_voices(h, mp, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B,
-                                    F, M, seed, 0, taps, ns))
+                                    F, M, seed, 0, taps, ns, span, in_first_frame))
         return rc;
     }
     return B200DDSP_OK;
@@ -1482,7 +1707,11 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   // prepared on the same side stream, which leaves the tail with 8 + 8 transforms instead of 16 + 8
   static const int reverb_split = env_int("B200DDSP_REVERB_SPLIT", 1);
   const float2* ir_spectra = nullptr;
-  if (reverb_ir && reverb_split) {
+  if (tl) {   // timeline reverb: the impulse responses' spectra, early and off the critical path
+    if (sync) CUDA_TRY(h, cudaStreamWaitEvent(h->hd_stream, sync->ir_ready, 0));
+    if (int rc = timeline_reverb_ir_phase(h, *tl, h->hd_stream)) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_ir_spectra, h->hd_stream));
+  } else if (reverb_ir && reverb_split) {
     if (sync) CUDA_TRY(h, cudaStreamWaitEvent(h->hd_stream, sync->ir_ready, 0));
     if (int rc = run_reverb_ir_phase(h, reverb_ir, B, N, L, (float2*)(base + w.tw), (float2*)(base + w.buf_a),
                                      (float2*)(base + w.buf_b), &ir_spectra, h->hd_stream))
@@ -1520,6 +1749,10 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_noise_join, 0));
   }
   if (int rc = run_mix(h, noise_part, n_slices, &mix, dry_out, B, N, 0, st)) return rc;
+  if (tl) {
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ir_spectra, 0));
+    return timeline_reverb_audio_phase(h, *tl, dry_out, wet_out, st);
+  }
   // 4. reverb -> wet
   if (reverb_ir && ir_spectra) {
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ir_spectra, 0));
@@ -1565,17 +1798,17 @@ extern "C" int b200ddsp_forward_polyphonic(b200ddsp_handle* h, const b200ddsp_vo
 }
 
 // ---------------------------------------------------------------------------------------------
-// the whole DAG from HOST buffers
+// staging of HOST inputs
 // ---------------------------------------------------------------------------------------------
-
 struct HostStaging {
   size_t amp, hd, inh, f0, mags, noise, ir, dry, wet, core, total;
 };
 
-static HostStaging carve_host(int P, int B, int F, int H, int S, int M, int L, int U, bool noise,
-                              const WorkspaceLayout& w) {
+// F = input frames, F_out = frames synthesised (== F for whole clips); `core_bytes` of scratch follow.
+static HostStaging carve_host(int P, int B, int F, int F_out, int H, int S, int M, int L, int U, bool noise,
+                              size_t core_bytes) {
   HostStaging s{};
-  const size_t R = (size_t)P * B, N = (size_t)F * U;
+  const size_t R = (size_t)P * B, N_in = (size_t)F * U, N = (size_t)F_out * U;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
   s.amp = take(R * F * 4);
@@ -1583,11 +1816,11 @@ static HostStaging carve_host(int P, int B, int F, int H, int S, int M, int L, i
   s.inh = take(R * F * 4);
   s.f0 = take(R * F * S * 4);
   s.mags = take(R * F * (size_t)M * 4);
-  if (noise) s.noise = take(R * N * 4);
+  if (noise) s.noise = take(R * N_in * 4);
   if (L > 0) s.ir = take((size_t)B * L * 4);
   s.dry = take((size_t)B * N * 4);
   if (L > 0) s.wet = take((size_t)B * N * 4);
-  s.core = take(w.total);
+  s.core = take(core_bytes);
   s.total = o;
   return s;
 }
@@ -1597,32 +1830,166 @@ static int host_copy_groups(int P) {
   return P >= g ? g : P;
 }
 
+// ---------------------------------------------------------------------------------------------
+// spans of a timeline (device inputs)
+// ---------------------------------------------------------------------------------------------
+static int make_span(b200ddsp_handle* h, const b200ddsp_span* sp, int F, SpanInfo* out) {
+  if (!sp) return fail(h, B200DDSP_BAD_ARGUMENT, "span is null");
+  const int U = h->U;
+  const long long in0 = sp->in_first_frame, out0 = sp->out_first_frame, total = sp->total_frames;
+  const long long Fo = sp->n_out_frames;
+  if (in0 < 0 || out0 < in0 || Fo < 1 || total < 1 || out0 + Fo > total || in0 + F > total)
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "span: input frames [%lld, %lld), output frames [%lld, %lld) of a timeline of %lld", in0,
+                in0 + F, out0, out0 + Fo, total);
+  if (total * U > (1ll << 24))
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "timeline of %lld samples exceeds 2^24 (the float32 sample index of the reference's "
+                "resize is no longer exact)", total * U);
+  if (out0 > 0 && out0 == in0)
+    return fail(h, B200DDSP_BAD_SHAPE, "span: one frame of halo is needed before output frame %lld", out0);
+  if (out0 + Fo < total && in0 + F < out0 + Fo + 1)
+    return fail(h, B200DDSP_BAD_SHAPE, "span: one frame of halo is needed after output frame %lld",
+                out0 + Fo - 1);
+  if ((out0 * U) % kAngularChunk != 0)
+    return fail(h, B200DDSP_BAD_SHAPE,
+                "span: the first output sample (%lld) must lie on a multiple of the %d-sample chunk of "
+                "angular_cumsum", out0 * U, kAngularChunk);
+  if (sp->phase.carry && ((out0 + Fo) * U) % kAngularChunk != 0 && out0 + Fo != total)
+    return fail(h, B200DDSP_BAD_SHAPE, "span: a phase carry needs the span to end on a chunk boundary");
+  if (out0 > 0 && !sp->phase.seed)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "span: output frame %lld > 0 needs a phase seed", out0);
+  out->koff = (int)(out0 - in0);
+  out->F_out = (int)Fo;
+  out->tg0 = (int)(out0 * U);
+  out->total_frames = (int)total;
+  out->seeded = out0 > 0;
+  out->carry = sp->phase.carry != nullptr;
+  out->phase = to_link(sp->phase);
+  if (out0 == 0) { out->phase.seed = nullptr; out->phase.seed_ready = nullptr; out->phase.seed_ack = nullptr; }
+  return B200DDSP_OK;
+}
+
+extern "C" int b200ddsp_forward_span(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, float* dry_out,
+                                     int B, int F, int H, int S, int M, uint64_t seed,
+                                     const b200ddsp_span* span, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (int rc = check_forward_args(h, voices, P, B, F, H, S, M, 0, false)) return rc;
+  if (!dry_out) return fail(h, B200DDSP_BAD_ARGUMENT, "dry_out is null");
+  SpanInfo si{};
+  if (int rc = make_span(h, span, F, &si)) return rc;
+  const WorkspaceLayout w = carve(h, P, B, F, H, S, M, 0, 1);
+  if (!workspace || workspace_bytes < w.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_span needs %zu workspace bytes, got %zu", w.total,
+                workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  return forward_core(h, voices, P, nullptr, dry_out, nullptr, B, F, H, S, M, 0, seed, (char*)workspace, w,
+                      nullptr, (cudaStream_t)stream, &si, span->in_first_frame);
+}
+
+static int check_timeline_args(b200ddsp_handle* h, const b200ddsp_span* span, int B, int L, int seg_frames) {
+  if (!span) return fail(h, B200DDSP_BAD_ARGUMENT, "span is null");
+  if (seg_frames < 1 || span->n_out_frames % seg_frames != 0)
+    return fail(h, B200DDSP_BAD_SHAPE, "n_out_frames=%d is not a multiple of seg_frames=%d",
+                span->n_out_frames, seg_frames);
+  return check_timeline_reverb(h, B, span->n_out_frames / seg_frames, seg_frames * h->U, L);
+}
+
+struct TimelineLayout { WorkspaceLayout core; TimelineReverbLayout rev; size_t dry, total; };
+
+static TimelineLayout carve_timeline(const b200ddsp_handle* h, int P, int B, int F, int H, int S, int M, int L,
+                                     int n_out_frames, int seg_frames, int n_groups) {
+  TimelineLayout t{};
+  t.core = carve(h, P, B, F, H, S, M, 0, n_groups);
+  t.rev = carve_timeline_reverb(t.core.total, B, n_out_frames / seg_frames, seg_frames * h->U, L);
+  t.dry = t.rev.total;                                   // dry span when the caller does not want it
+  t.total = t.dry + align_up((size_t)B * n_out_frames * h->U * 4);
+  return t;
+}
+
+extern "C" int b200ddsp_forward_timeline(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
+                                         const float* reverb_ir, float* dry_out, float* wet_out, int B,
+                                         int F, int H, int S, int M, int L, int seg_frames, uint64_t seed,
+                                         const b200ddsp_span* span, const b200ddsp_link* tail,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_forward_args(h, voices, P, B, F, H, S, M, L, true)) return rc;
+  if (!reverb_ir || !wet_out) return fail(h, B200DDSP_BAD_ARGUMENT, "reverb_ir / wet_out is null");
+  if (wet_out == dry_out) return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out may not alias dry_out");
+  if (int rc = check_timeline_args(h, span, B, L, seg_frames)) return rc;
+  SpanInfo si{};
+  if (int rc = make_span(h, span, F, &si)) return rc;
+  const TimelineLayout t = carve_timeline(h, P, B, F, H, S, M, L, si.F_out, seg_frames, 1);
+  if (!workspace || workspace_bytes < t.total)
+    return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "forward_timeline needs %zu workspace bytes, got %zu",
+                t.total, workspace_bytes);
+  if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
+  char* base = (char*)workspace;
+  const TimelineReverbPlan tl = timeline_plan(h, base, t.rev, reverb_ir, B, si.F_out / seg_frames,
+                                              seg_frames * h->U, L, tail ? to_link(*tail) : Link{});
+  float* dry = dry_out ? dry_out : (float*)(base + t.dry);
+  return forward_core(h, voices, P, nullptr, dry, wet_out, B, F, H, S, M, L, seed, base, t.core, nullptr,
+                      (cudaStream_t)stream, &si, span->in_first_frame, &tl);
+}
+
+extern "C" size_t b200ddsp_timeline_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H, int S,
+                                                    int M, int L, int n_out_frames, int seg_frames,
+                                                    int host_inputs, int with_noise) {
+  if (!h || P < 1 || B < 1 || F < 1 || H < 1 || S < 1 || M < 3 || L < 1 || seg_frames < 1 ||
+      n_out_frames < seg_frames)
+    return 0;
+  const TimelineLayout t = carve_timeline(h, P, B, F, H, S, M, L, n_out_frames, seg_frames,
+                                          host_inputs ? host_copy_groups(P) : 1);
+  if (!host_inputs) return t.total;
+  return carve_host(P, B, F, n_out_frames, H, S, M, L, h->U, with_noise != 0, t.total).total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the whole DAG from HOST buffers
+// ---------------------------------------------------------------------------------------------
 extern "C" size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int F, int H,
                                                 int S, int M, int L, int with_noise) {
   if (!h || P < 1 || B < 1 || F < 1 || H < 1 || S < 1 || M < 3) return 0;
   const WorkspaceLayout w = carve(h, P, B, F, H, S, M, L, host_copy_groups(P));
-  return carve_host(P, B, F, H, S, M, L, h->U, with_noise != 0, w).total;
+  return carve_host(P, B, F, F, H, S, M, L, h->U, with_noise != 0, w.total).total;
 }
 
-extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host,
-                                                int P, const float* reverb_ir_host,
-                                                float* dry_out_host, float* wet_out_host, int B, int F,
-                                                int H, int S, int M, int L, uint64_t seed,
-                                                void* workspace, size_t workspace_bytes, void* stream) {
+// Shared by b200ddsp_forward_polyphonic_host (span == nullptr: whole clips, one-block reverb) and
+// b200ddsp_forward_timeline_host (a span of a timeline, segment reverb + tail hand-off).
+static int forward_host_impl(b200ddsp_handle* h, const b200ddsp_voice* voices_host, int P,
+                             const float* reverb_ir_host, float* dry_out_host, float* wet_out_host, int B,
+                             int F, int H, int S, int M, int L, uint64_t seed, const b200ddsp_span* span,
+                             int seg_frames, const b200ddsp_link* tail, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (int rc = check_forward_args(h, voices_host, P, B, F, H, S, M, L, reverb_ir_host != nullptr))
     return rc;
   if (!dry_out_host && !wet_out_host)
     return fail(h, B200DDSP_BAD_ARGUMENT, "neither dry_out_host nor wet_out_host given");
   if (wet_out_host && !reverb_ir_host)
     return fail(h, B200DDSP_BAD_ARGUMENT, "wet_out_host given without reverb_ir_host");
-  const int U = h->U, N = F * U;
+  const int U = h->U;
+  SpanInfo si{};
+  if (span) {
+    if (!reverb_ir_host || !wet_out_host)
+      return fail(h, B200DDSP_BAD_ARGUMENT, "forward_timeline_host needs reverb_ir_host and wet_out_host");
+    if (int rc = check_timeline_args(h, span, B, L, seg_frames)) return rc;
+    if (int rc = make_span(h, span, F, &si)) return rc;
+  }
+  const int F_out = span ? si.F_out : F, N = F_out * U, N_in = F * U;
   bool any_noise = false;
   for (int v = 0; v < P; ++v) any_noise |= voices_host[v].noise != nullptr;
-  const WorkspaceLayout w = carve(h, P, B, F, H, S, M, reverb_ir_host ? L : 0, host_copy_groups(P));
-  const HostStaging hs = carve_host(P, B, F, H, S, M, reverb_ir_host ? L : 0, U, any_noise, w);
+  const int Lr = reverb_ir_host ? L : 0;
+  WorkspaceLayout w{};
+  TimelineLayout tlay{};
+  if (span) {
+    tlay = carve_timeline(h, P, B, F, H, S, M, L, F_out, seg_frames, host_copy_groups(P));
+    w = tlay.core;
+  } else {
+    w = carve(h, P, B, F, H, S, M, Lr, host_copy_groups(P));
+  }
+  const HostStaging hs = carve_host(P, B, F, F_out, H, S, M, Lr, U, any_noise, span ? tlay.total : w.total);
   if (!workspace || workspace_bytes < hs.total)
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL,
-                "forward_polyphonic_host needs %zu workspace bytes, got %zu", hs.total, workspace_bytes);
+                "forward from host inputs needs %zu workspace bytes, got %zu", hs.total, workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
   for (int v = 0; v < P; ++v) {
     const b200ddsp_voice& vc = voices_host[v];
@@ -1642,7 +2009,7 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
     dev[v].inharm_coef = (float*)(base + hs.inh) + v * BF;
     dev[v].f0_hz = (float*)(base + hs.f0) + v * BF * S;
     dev[v].magnitudes = (float*)(base + hs.mags) + v * BF * M;
-    dev[v].noise = voices_host[v].noise ? (float*)(base + hs.noise) + (size_t)v * B * N : nullptr;
+    dev[v].noise = voices_host[v].noise ? (float*)(base + hs.noise) + (size_t)v * B * N_in : nullptr;
   }
   // one memcpy per run of voices whose host tensors are contiguous (stacked [P,B,F,C] parents)
   auto copy_runs = [&](int v0, int v1, size_t elems, auto host_of, auto dev_of) -> cudaError_t {
@@ -1694,7 +2061,7 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
                           [&](int v) { return dev[v].magnitudes; }));
     for (int v = v0; v < v1; ++v)
       if (voices_host[v].noise)
-        CUDA_TRY(h, cudaMemcpyAsync((void*)dev[v].noise, voices_host[v].noise, (size_t)B * N * 4,
+        CUDA_TRY(h, cudaMemcpyAsync((void*)dev[v].noise, voices_host[v].noise, (size_t)B * N_in * 4,
                                     cudaMemcpyHostToDevice, cs));
     CUDA_TRY(h, cudaEventRecord(h->ev_mags[hf], cs));
     sync.mags_ready[hf] = h->ev_mags[hf];
@@ -1702,9 +2069,16 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
 
   float* dry_dev = (float*)(base + hs.dry);
   float* wet_dev = reverb_ir_host ? (float*)(base + hs.wet) : nullptr;
-  if (int rc = forward_core(h, dev, P, ir_dev, dry_dev, wet_dev, B, F, H, S, M, L, seed, base + hs.core, w,
-                            &sync, st))
+  if (span) {
+    const TimelineReverbPlan tl = timeline_plan(h, base + hs.core, tlay.rev, ir_dev, B, F_out / seg_frames,
+                                                seg_frames * U, L, tail ? to_link(*tail) : Link{});
+    if (int rc = forward_core(h, dev, P, nullptr, dry_dev, wet_dev, B, F, H, S, M, L, seed, base + hs.core, w,
+                              &sync, st, &si, span->in_first_frame, &tl))
+      return rc;
+  } else if (int rc = forward_core(h, dev, P, ir_dev, dry_dev, wet_dev, B, F, H, S, M, L, seed, base + hs.core,
+                                   w, &sync, st)) {
     return rc;
+  }
   if (dry_out_host)
     CUDA_TRY(h, cudaMemcpyAsync(dry_out_host, dry_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   if (wet_out_host)
@@ -1712,8 +2086,28 @@ extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200dd
   return B200DDSP_OK;
 }
 
+extern "C" int b200ddsp_forward_polyphonic_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host,
+                                                int P, const float* reverb_ir_host,
+                                                float* dry_out_host, float* wet_out_host, int B, int F,
+                                                int H, int S, int M, int L, uint64_t seed,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_host_impl(h, voices_host, P, reverb_ir_host, dry_out_host, wet_out_host, B, F, H, S, M, L,
+                           seed, nullptr, 0, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200ddsp_forward_timeline_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host, int P,
+                                              const float* reverb_ir_host, float* dry_out_host,
+                                              float* wet_out_host, int B, int F, int H, int S, int M, int L,
+                                              int seg_frames, uint64_t seed, const b200ddsp_span* span,
+                                              const b200ddsp_link* tail, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  if (!span) return fail(h, B200DDSP_BAD_ARGUMENT, "span is null");
+  return forward_host_impl(h, voices_host, P, reverb_ir_host, dry_out_host, wet_out_host, B, F, H, S, M, L,
+                           seed, span, seg_frames, tail, workspace, workspace_bytes, stream);
+}
+
 // ---------------------------------------------------------------------------------------------
-// timeline reverb across GPUs: peer-visible buffers + the fused overlap-add / carry kernel
+// peer-visible buffers (the inboxes of the span hand-off, link.cuh)
 // ---------------------------------------------------------------------------------------------
 extern "C" int b200ddsp_peer_alloc(b200ddsp_handle* h, size_t bytes, void** dev_ptr,
                                    unsigned char* ipc_handle64) {
@@ -1723,6 +2117,10 @@ extern "C" int b200ddsp_peer_alloc(b200ddsp_handle* h, size_t bytes, void** dev_
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 bytes");
   void* p = nullptr;
   CUDA_TRY(h, cudaMalloc(&p, bytes));
+  if (cudaMemset(p, 0, bytes) != cudaSuccess) {   // counters of a link start at zero
+    cudaFree(p);
+    return fail(h, B200DDSP_CUDA_ERROR, "cudaMemset of a peer buffer failed");
+  }
   cudaIpcMemHandle_t ipc;
   cudaError_t e = cudaIpcGetMemHandle(&ipc, p);
   if (e != cudaSuccess) {
@@ -1752,22 +2150,6 @@ extern "C" int b200ddsp_peer_open(b200ddsp_handle* h, const unsigned char* ipc_h
 extern "C" int b200ddsp_peer_close(b200ddsp_handle* h, void* peer_ptr) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
   if (peer_ptr) CUDA_TRY(h, cudaIpcCloseMemHandle(peer_ptr));
-  return B200DDSP_OK;
-}
-
-extern "C" int b200ddsp_timeline_overlap_add(b200ddsp_handle* h, const float* wet_full, const float* dry,
-                                             float* out, float* peer_head, int S, int N, int L,
-                                             void* stream) {
-  if (!h) return B200DDSP_BAD_ARGUMENT;
-  if (!wet_full || !out) return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
-  if (S < 1 || N < 1 || L < 1) return fail(h, B200DDSP_BAD_SHAPE, "S=%d N=%d L=%d", S, N, L);
-  if ((long long)(L - 1) > (long long)S * N)
-    return fail(h, B200DDSP_BAD_SHAPE,
-                "the reverb tail (%d samples) is longer than a rank's span (%d segments x %d)", L - 1, S, N);
-  const long long n = (long long)S * N + (peer_head ? L - 1 : 0);
-  timeline_overlap_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      wet_full, dry, out, peer_head, S, N, N + L - 1);
-  CHECK_LAUNCH(h, "timeline_overlap_add_kernel");
   return B200DDSP_OK;
 }
 

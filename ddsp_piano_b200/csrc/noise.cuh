@@ -120,7 +120,10 @@ struct NoiseArgs {
   float* out;            // [n_slices, B, N] noise of each voice slice
   int v_begin, v_end;    // voices handled by this launch, split evenly over gridDim.z slices
   int slice0;            // index of the launch's first slice in `out`
-  int B, F, M, U, N, tap_pitch;
+  int B, F, M, U, N, tap_pitch;  // F = input frames (rows of `taps`, frames of an injected noise tensor),
+                                 // N = output samples
+  int koff;                      // input frame of output frame 0 (spans of a timeline: halo in front)
+  unsigned long long sample0;    // global sample index of input frame 0 (Philox counter base)
   int halo_before, halo_after;   // input halo in FRAMES either side of the tile
   unsigned long long seed, stream_id;
 };
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
   const int b = blockIdx.y;
   const int f_tile = blockIdx.x * kNoiseFrames;        // first output frame
-  const int k_first = f_tile - a.halo_before;          // first input frame held (may be < 0)
+  const int k_first = f_tile + a.koff - a.halo_before; // first input frame held (may be < 0)
   const int U = a.U, M = a.M, lir = 2 * (M - 1);
   const int start = (lir - 1) / 2 - 1;                 // crop_and_compensate_delay
   const int n_blocks = U / 8;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
     }
     const float* nz = vp.noise[v];
     if (nz != nullptr) {
-      nz += (size_t)b * a.N;
+      nz += (size_t)b * a.F * U;
       for (int i = threadIdx.x; i < L.n_in * U; i += n_threads) {
         const int fi = i / U, j = i - fi * U;
         const int k = k_first + fi;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
         const int k = k_first + fi;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k >= 0 && k < a.F) {
-          const unsigned int blk = (unsigned int)(((size_t)k * U + j) >> 2);
+          const unsigned int blk = (unsigned int)((a.sample0 + (size_t)k * U + j) >> 2);
           const uint4 bits = philox4x32_10(
               make_uint4(blk, (unsigned int)b, (unsigned int)v + (unsigned int)a.stream_id,
                          (unsigned int)(a.stream_id >> 32)), key);

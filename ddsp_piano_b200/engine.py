@@ -229,7 +229,7 @@ class Engine:
                 float(decay_exponent), int(decay_start), self.stream()))
         return out
 
-    # -- peer-visible buffers and the fused timeline overlap-add (sharding.PeerTimeline) ----------
+    # -- peer-visible buffers (sharding.SpanChain) --------------------------------------------------
     def peer_alloc(self, nbytes):
         """cudaMalloc + CUDA IPC handle: (device pointer, 64-byte handle)."""
         import ctypes
@@ -254,18 +254,80 @@ class Engine:
         with torch.cuda.device(self.device):
             self.check(self.lib.b200ddsp_peer_free(self.handle, ptr))
 
-    def timeline_overlap_add(self, wet_full, dry, out_ptr, peer_head_ptr, S, N, L):
-        wet_full = self.tensor(wet_full, 'wet_full', 2)
-        if tuple(wet_full.shape) != (S, N + L - 1):
-            raise ValueError(f'wet_full is {tuple(wet_full.shape)}, expected {(S, N + L - 1)}')
-        dry_ptr = 0
-        if dry is not None:
-            dry = self.tensor(dry, 'dry', 2)
-            dry_ptr = dry.data_ptr()
+    # -- spans of a timeline (sharding.SpanChain builds the links) ----------------------------------
+    def _span_voices(self, voices, reverb_ir, host):
+        arr, keep, (P, B, F, H, S, M, _), any_noise = self._voice_array(voices, host=host)
+        ir, L = None, 0
+        if reverb_ir is not None:
+            ir = self._impulse_response(reverb_ir, B, host=host)
+            L = ir.shape[1]
+        return arr, keep, (P, B, F, H, S, M, L), any_noise, ir
+
+    def forward_span(self, voices, span, seed=0):
+        """Additive + noise of one span of B timelines (``span``: a ``_lib.Span``; control tensors cover
+        the span's INPUT frames) -> dry [B, n_out_frames * U]."""
+        arr, keep, (P, B, F, H, S, M, _), _, _ = self._span_voices(voices, None, host=False)
+        ws = self.workspace(self.lib.b200ddsp_workspace_bytes(self.handle, P, B, F, H, S, M, 0))
+        dry = torch.empty([B, span.n_out_frames * self.upsampling], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            self.check(self.lib.b200ddsp_timeline_overlap_add(
-                self.handle, wet_full.data_ptr(), dry_ptr, out_ptr, peer_head_ptr or 0, S, N, L,
-                self.stream()))
+            self.check(self.lib.b200ddsp_forward_span(
+                self.handle, arr, P, dry.data_ptr(), B, F, H, S, M, seed, ctypes.byref(span),
+                ws.data_ptr(), ws.numel(), self.stream()))
+        return dry
+
+    def forward_timeline(self, voices, reverb_ir, span, seg_frames, tail=None, seed=0, want_dry=True):
+        """The span forward + the reverb of the timeline (segment convolutions, overlap-add, tail
+        hand-off through ``tail``: a ``_lib.Link`` or None).  HOST control tensors take the staged
+        entry point and come back as pinned host tensors (see forward_polyphonic_host).
+        Returns (dry or None, wet), each [B, n_out_frames * U]."""
+        f0_0 = voices[0]['f0_hz']
+        host = not (isinstance(f0_0, torch.Tensor) and f0_0.device.type == 'cuda')
+        arr, keep, (P, B, F, H, S, M, L), any_noise, ir = self._span_voices(voices, reverb_ir, host=host)
+        N = span.n_out_frames * self.upsampling
+        key = ('timeline', host, P, B, F, H, S, M, L, span.n_out_frames, seg_frames, any_noise)
+        nbytes = self._ws_sizes.get(key)
+        if nbytes is None:
+            nbytes = self._ws_sizes[key] = self.lib.b200ddsp_timeline_workspace_bytes(
+                self.handle, P, B, F, H, S, M, L, span.n_out_frames, seg_frames, int(host), int(any_noise))
+        if nbytes == 0:
+            raise ValueError('forward_timeline: bad shapes')
+        ws = self.workspace(nbytes)
+        if host:
+            bufs = self._host_out.get((B, N))
+            if bufs is None:
+                bufs = self._host_out[(B, N)] = (torch.empty([B, N], dtype=torch.float32).pin_memory(),
+                                                 torch.empty([B, N], dtype=torch.float32).pin_memory())
+            dry, wet = (bufs[0] if want_dry else None), bufs[1]
+            self._keep_alive = (keep, ir)
+            fn = self.lib.b200ddsp_forward_timeline_host
+        else:
+            dry = torch.empty([B, N], dtype=torch.float32, device=self.device) if want_dry else None
+            wet = torch.empty([B, N], dtype=torch.float32, device=self.device)
+            fn = self.lib.b200ddsp_forward_timeline
+        with torch.cuda.device(self.device):
+            self.check(fn(self.handle, arr, P, ir.data_ptr(), dry.data_ptr() if dry is not None else None,
+                          wet.data_ptr(), B, F, H, S, M, L, seg_frames, seed, ctypes.byref(span),
+                          ctypes.byref(tail) if tail is not None else None, ws.data_ptr(), ws.numel(),
+                          self.stream()))
+        return dry, wet
+
+    def timeline_reverb(self, dry, ir, n_seg, tail=None):
+        """Reverb of a dry span [B, n_seg * N] with the timelines' impulse responses [B, L] (segment
+        convolutions + overlap-add + tail hand-off); the reverb stage of forward_timeline alone."""
+        dry = self.tensor(dry, 'dry', 2)
+        B = dry.shape[0]
+        ir = self._impulse_response(ir, B, host=False)
+        L = ir.shape[1]
+        if dry.shape[1] % n_seg:
+            raise ValueError(f'span of {dry.shape[1]} samples is not {n_seg} equal segments')
+        N = dry.shape[1] // n_seg
+        ws = self.workspace(self.lib.b200ddsp_timeline_reverb_workspace_bytes(self.handle, B, n_seg, N, L))
+        out = torch.empty_like(dry)
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_timeline_reverb(
+                self.handle, dry.data_ptr(), ir.data_ptr(), out.data_ptr(), B, n_seg, N, L,
+                ctypes.byref(tail) if tail is not None else None, ws.data_ptr(), ws.numel(), self.stream()))
+        return out
 
     def note_release(self, conditioning, release_frames):
         """NoteRelease over conditioning [rows, F, 2] (pitch column) or active pitch [rows, F, 1]

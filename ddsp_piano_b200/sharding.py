@@ -12,13 +12,11 @@ Two regimes:
   neighbour exchange (``send`` to rank+1 / ``recv`` from rank-1) of an ``L-1``-sample carry that
   is added to the head of the receiving rank's timeline -- :func:`timeline_reverb`.
 
-A third piece, :func:`chain_carry`, is the rank-to-rank protocol for oscillator phase continuity
-across segments (the carried state is specified in DESIGN.md section 6; the kernels do not take a
-phase seed yet).
-
-The functions are backend-agnostic (``torch.distributed`` with NCCL on GPUs, gloo in the CPU
-tests); the convolution itself is injected (``conv_full``), on the GPU it is
-``Engine.reverb_full`` (hand-written FFT convolution, 'valid'-padded).
+On the GPUs both exchanges of a timeline -- the oscillators' phase state and the reverb tail -- happen
+INSIDE the kernels of ``b200ddsp_forward_timeline`` through NVLink peer memory; :class:`SpanChain` owns
+the inboxes and counters.  :func:`timeline_reverb` and :func:`chain_carry` are the same two protocols
+written with ``torch.distributed`` send/recv: the host-side model of the chain, exercised with the gloo
+backend on CPU (``tests/test_sharding_gloo.py``); the convolution / the span computation is injected.
 """
 import torch
 import torch.distributed as dist
@@ -105,68 +103,120 @@ def chain_carry(finish, carry_like, rank, world, group=None):
     if rank > 0:
         dist.recv(carry_in, src=rank - 1, group=group)
     result, carry_out = finish(carry_in)
+    bad = carry_out.shape != carry_like.shape or carry_out.dtype != carry_like.dtype
     if rank + 1 < world:
-        if carry_out.shape != carry_like.shape or carry_out.dtype != carry_like.dtype:
-            raise ValueError(f'carry changed from {tuple(carry_like.shape)} {carry_like.dtype} to '
-                             f'{tuple(carry_out.shape)} {carry_out.dtype}')
-        dist.send(carry_out.contiguous(), dst=rank + 1, group=group)
+        # the successor is blocked in recv: it always gets a message (NaNs if this rank's carry is
+        # unusable, so that the failure travels down the chain instead of hanging it)
+        dist.send(torch.full_like(carry_like, float('nan')) if bad else carry_out.contiguous(),
+                  dst=rank + 1, group=group)
+    if bad:
+        raise ValueError(f'carry changed from {tuple(carry_like.shape)} {carry_like.dtype} to '
+                         f'{tuple(carry_out.shape)} {carry_out.dtype}')
     return result
 
 
 class _DeviceBuffer:
     """A raw device allocation as a ``__cuda_array_interface__`` object (for torch.as_tensor)."""
 
-    def __init__(self, ptr, n_floats):
-        self.__cuda_array_interface__ = {'shape': (n_floats,), 'typestr': '<f4', 'data': (ptr, False),
+    def __init__(self, ptr, n, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (ptr, False),
                                          'version': 2}
 
 
-class PeerTimeline:
-    """The GPU form of :func:`timeline_reverb`: ONE kernel does the local overlap-add and adds the
-    carry straight into the successor's output buffer over NVLink peer memory
-    (``csrc/timeline.cuh``) -- no send/recv, no staging buffer, no separate add.
+def local_link(seed=None, carry=None, epoch=1):
+    """A hand-off inside ONE process and stream (spans of a timeline synthesised one after the other on
+    the same GPU): the payloads are ordinary device tensors, stream order is the synchronisation."""
+    from . import _lib
+    return _lib.Link(seed=seed.data_ptr() if seed is not None else None,
+                     carry=carry.data_ptr() if carry is not None else None, epoch=epoch)
 
-    Every rank owns a peer-visible output buffer [S * N] (``b200ddsp_peer_alloc``); the CUDA IPC
-    handles are exchanged once, here, through ``torch.distributed`` and rank r maps the buffer of
-    rank r + 1.  Per call: zero the head of the own buffer, barrier, launch, barrier."""
 
-    def __init__(self, engine, n_segments, n_samples, ir_length, rank, world, group=None):
-        self.eng, self.S, self.N, self.L = engine, n_segments, n_samples, ir_length
-        self.rank, self.world, self.group = rank, world, group
-        if ir_length - 1 > n_segments * n_samples:
-            raise ValueError(f'reverb tail ({ir_length - 1} samples) is longer than the rank\'s span '
-                             f'({n_segments} segments x {n_samples})')
-        self.ptr, handle = engine.peer_alloc(n_segments * n_samples * 4)
-        self.out = torch.as_tensor(_DeviceBuffer(self.ptr, n_segments * n_samples), device=engine.device)
+class SpanChain:
+    """Rank r's place in a chain of spans of one timeline (BASELINE config 4): the inboxes and counters
+    of the two stream-ordered hand-offs -- oscillator phase state and reverb tail -- that
+    ``b200ddsp_forward_timeline`` performs INSIDE its kernels over NVLink peer memory (``csrc/link.cuh``,
+    ``csrc/timeline.cuh``).  Nothing here runs per step except building two small structs: no barrier,
+    no NCCL call on the data path (``torch.distributed`` is used once, to exchange the CUDA IPC handles).
+
+    Mailbox layout (one peer-visible allocation per rank, zero-filled):
+    8 x u64 counters [phase ready, phase ack, tail ready, tail ack, phase scratch x 2, tail scratch x 2],
+    then 2 phase slots of ``n_phase`` floats, then 2 tail slots of ``n_tail`` floats."""
+
+    COUNTER_BYTES = 256
+
+    def __init__(self, engine, n_phase, n_tail, rank=0, world=1, group=None):
+        if world > 1 and dist.get_backend(group) != 'nccl':
+            raise ValueError('SpanChain hands state over through CUDA peer memory: it needs the NCCL '
+                             'process group of one node (use timeline_reverb / chain_carry on CPU groups)')
+        self.eng, self.rank, self.world, self.group = engine, rank, world, group
+        self.n_phase, self.n_tail = int(n_phase), int(n_tail)
+        al = lambda x: (x + 255) // 256 * 256
+        self.phase_off = self.COUNTER_BYTES
+        self.phase_slot = al(4 * self.n_phase)
+        self.tail_off = self.phase_off + 2 * self.phase_slot
+        self.tail_slot = al(4 * self.n_tail)
+        nbytes = self.tail_off + 2 * self.tail_slot
+        self.ptr, handle = engine.peer_alloc(nbytes)
+        self.counters = torch.as_tensor(_DeviceBuffer(self.ptr, 8, '<i8'), device=engine.device)
         handles = [None] * world
         if world > 1:
             dist.all_gather_object(handles, handle, group=group)
-        self.peer_head = engine.peer_open(handles[rank + 1]) if rank + 1 < world else 0
+        self.prev = engine.peer_open(handles[rank - 1]) if rank > 0 else 0
+        self.next = engine.peer_open(handles[rank + 1]) if rank + 1 < world else 0
+        self.epoch = 0
+        if world > 1:
+            dist.barrier(group=group)
 
-    def reverb(self, dry, ir, add_dry=True):
-        """dry [S, N] (this rank's consecutive segments), ir [L] -> wet [S, N], a view of the
-        peer-visible buffer (valid until the next call)."""
-        S, N, L = self.S, self.N, self.L
-        if tuple(dry.shape) != (S, N) or tuple(ir.shape) != (L,):
-            raise ValueError(f'expected dry {(S, N)} and ir {(L,)}, got {tuple(dry.shape)}, {tuple(ir.shape)}')
-        wet_full = self.eng.reverb_full(dry, ir[None, :].expand(S, L).contiguous())
-        self.out[:L - 1].zero_()
-        if self.world > 1:
-            dist.barrier(group=self.group)           # every head is zero before anyone adds into it
-        self.eng.timeline_overlap_add(wet_full, dry if add_dry else None, self.ptr, self.peer_head, S, N, L)
-        if self.world > 1:
-            dist.barrier(group=self.group)           # every carry has landed
-        return self.out.view(S, N)
+    def links(self):
+        """Advance the call counter and return (phase link, tail link) for this call."""
+        from . import _lib
+        self.epoch += 1
+        e, slot = self.epoch, self.epoch & 1
+
+        def link(ready, ack, scratch, off, slot_bytes):
+            lk = _lib.Link(epoch=e, scratch=self.ptr + 8 * scratch)
+            if self.prev:
+                lk.seed = self.ptr + off + slot * slot_bytes
+                lk.seed_ready = self.ptr + 8 * ready
+                lk.seed_ack = self.prev + 8 * ack
+            if self.next:
+                lk.carry = self.next + off + slot * slot_bytes
+                lk.carry_ready = self.next + 8 * ready
+                lk.carry_ack = self.ptr + 8 * ack
+            return lk
+
+        return (link(0, 1, 4, self.phase_off, self.phase_slot),
+                link(2, 3, 6, self.tail_off, self.tail_slot))
+
+    def check(self):
+        """Raise if a wait inside a kernel timed out (a peer never delivered).  Synchronises."""
+        c = self.counters.cpu().tolist()
+        if c[5] or c[7]:
+            raise RuntimeError(f'rank {self.rank}: span hand-off timed out (phase {c[5]:#x}, tail {c[7]:#x}); '
+                               f'counters {c[:4]} at epoch {self.epoch}')
 
     def close(self):
+        torch.cuda.synchronize(self.eng.device)
         if self.world > 1:
             dist.barrier(group=self.group)
-        if self.peer_head:
-            self.eng.peer_close(self.peer_head)
-            self.peer_head = 0
+        for attr in ('prev', 'next'):
+            if getattr(self, attr):
+                self.eng.peer_close(getattr(self, attr))
+                setattr(self, attr, 0)
         if self.world > 1:
             dist.barrier(group=self.group)
         if self.ptr:
-            self.out = None
+            self.counters = None
             self.eng.peer_free(self.ptr)
             self.ptr = 0
+
+
+def span_of(rank, world, frames_per_rank):
+    """(in_first_frame, out_first_frame, n_input_frames) of rank ``rank``'s span when every rank
+    synthesises ``frames_per_rank`` frames of a timeline of ``world * frames_per_rank``: one frame of
+    halo on either side except at the two ends of the timeline."""
+    total = world * frames_per_rank
+    out0 = rank * frames_per_rank
+    in0 = max(out0 - 1, 0)
+    in1 = min(out0 + frames_per_rank + 1, total)
+    return in0, out0, in1 - in0

@@ -181,20 +181,96 @@ int b200ddsp_surrogate_signal(b200ddsp_handle* h, const float* amplitudes, const
                               const float* harmonic_shifts, const float* f0_hz, float* out, int B, int F,
                               int H, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Timeline reverb across GPUs (the reference has no multi-GPU synthesis, its segment
- * pipeline -- synthesize_midi_file.py / data_pipeline.py -- treats every segment alone).  A rank holds S
- * consecutive segments of N samples; wet_full [S, N + L - 1] is b200ddsp_reverb_full of them.  One
- * launch overlap-adds them into out [S * N] (+ dry when given) and adds the L - 1 samples that spill past
- * the span directly into the head of the NEXT rank's out buffer through peer memory (peer_head = that
- * buffer mapped with b200ddsp_peer_open; NULL on the last rank).  Protocol: every rank zeroes
- * out[0 .. L-1), all ranks synchronise, every rank launches, all ranks synchronise.  Buffers that a
- * peer writes must come from b200ddsp_peer_alloc (plain cudaMalloc + CUDA IPC handle, 64 bytes). */
+/* Peer-visible device buffers for the hand-off between the spans of a timeline (below): plain
+ * cudaMalloc (zero-filled) + a CUDA IPC handle (64 bytes) that another process on the same node maps
+ * with b200ddsp_peer_open (cudaIpcOpenMemHandle, peer access over NVLink). */
 int b200ddsp_peer_alloc(b200ddsp_handle* h, size_t bytes, void** dev_ptr, unsigned char* ipc_handle64);
 int b200ddsp_peer_free(b200ddsp_handle* h, void* dev_ptr);
 int b200ddsp_peer_open(b200ddsp_handle* h, const unsigned char* ipc_handle64, void** peer_ptr);
 int b200ddsp_peer_close(b200ddsp_handle* h, void* peer_ptr);
-int b200ddsp_timeline_overlap_add(b200ddsp_handle* h, const float* wet_full, const float* dry, float* out,
-                                  float* peer_head, int S, int N, int L, void* stream);
+
+/* ---- one timeline cut into spans (BASELINE config 4) -----------------------------------
+ * The reference synthesises a whole piece in ONE pass (synthesize_midi_file.py:52-54,73: %duration is
+ * rebound to the piece), so the float32 phase of every oscillator (core.angular_cumsum,
+ * modules/inharm_synth.py:73-75), both resamplers (:117-119) and the noise FIR
+ * (modules/filtered_noise_synth.py:41) run THROUGH every 3 s boundary, and the legacy bilinear
+ * coordinate float(i) * float(F / N) is taken on the GLOBAL sample index.  A span call synthesises
+ * frames [out_first_frame, out_first_frame + n_out_frames) of such a timeline, bit for bit what the
+ * whole-timeline call produces for those samples, from
+ *   - control tensors that cover input frames [in_first_frame, in_first_frame + F) with at least one
+ *     frame of halo on either side of the output frames (none is needed where the span touches the
+ *     start / the end of the timeline: the reference zero-pads the noise there and holds the last
+ *     frame, core.resample add_endpoint);
+ *   - the phase state at the span's first sample: per (voice, timeline, substring, partial) the float32
+ *     running sum of the chunk-end phases mod 2 pi that angular_cumsum accumulates over the chunks
+ *     before the span (zeros at the start of the timeline).  out_first_frame * U must be a multiple of
+ *     the 1000-sample chunk.  The call returns the same state at the span's end.
+ * Across GPUs the state travels rank to rank in timeline order (float32 addition is not associative,
+ * so this is a chain, not a tree), and so do the L - 1 samples of reverb tail that spill into the next
+ * span.  Both hand-offs are stream-ordered through peer memory: the producing kernel stores the
+ * payload into the successor's inbox (NVLink P2P) and then raises a counter there; the consuming
+ * kernel spins on that counter.  No host synchronisation, no NCCL call on the data path. */
+
+/* One rank's end of such a hand-off.  Counters are 64-bit, only grow, and carry the call number
+ * `epoch` (1, 2, ...).  Inboxes are double buffered by the caller (slot = epoch & 1); the producer
+ * waits for ack >= epoch - 2 before it overwrites a slot.  Any pointer may be NULL: no predecessor
+ * (seed = zeros) / no successor / payload already in place (same-process use). */
+typedef struct {
+  const float* seed;                /* LOCAL inbox slot the predecessor wrote for this epoch */
+  unsigned long long* seed_ready;   /* LOCAL counter: >= epoch once `seed` is complete */
+  unsigned long long* seed_ack;     /* PEER counter (predecessor's): set to epoch once `seed` was read */
+  float* carry;                     /* PEER inbox slot of the successor for this epoch (or local memory) */
+  unsigned long long* carry_ready;  /* PEER counter (successor's seed_ready) */
+  unsigned long long* carry_ack;    /* LOCAL counter the successor acknowledges into */
+  unsigned long long epoch;
+  unsigned long long* scratch;      /* LOCAL, 2 words, zero-initialised once: CTA arrival counter + error
+                                       word (non-zero after a wait timed out, ~4 s) */
+} b200ddsp_link;
+
+typedef struct {
+  long long in_first_frame;    /* global index of input frame 0 of the control tensors */
+  long long out_first_frame;   /* global index of the first synthesised frame */
+  int n_out_frames;            /* frames synthesised: dry_out is [B, n_out_frames * U] */
+  long long total_frames;      /* frames of the whole timeline */
+  b200ddsp_link phase;         /* payload [P, B, S, H] float32 */
+} b200ddsp_span;
+
+/* b200ddsp_forward_polyphonic for one span of B timelines: voices[v] tensors are [B, F, C] over the
+ * INPUT frames; an injected noise tensor is [B, F * U] over the same frames.  No reverb node (see
+ * b200ddsp_forward_timeline).  Fast additive path only (U % 8 == 0, H <= 128, inference = 1).
+ * Workspace: b200ddsp_workspace_bytes(h, P, B, F, H, S, M, 0). */
+int b200ddsp_forward_span(b200ddsp_handle* h, const b200ddsp_voice* voices, int P, float* dry_out, int B,
+                          int F, int H, int S, int M, uint64_t seed, const b200ddsp_span* span,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* The span forward followed by the reverb of the timeline (ddsp.effects.Reverb on the WHOLE piece,
+ * configs/dafx22.gin:99-100): the dry span is convolved segment by segment (seg_frames frames each,
+ * padding='valid', one FFT block per segment) with the timeline's impulse response reverb_ir [B, L];
+ * ONE kernel then overlap-adds the segments, adds the dry signal (add_dry) and the predecessor's tail
+ * (`tail` link, payload [B, L - 1]) and hands the L - 1 samples that spill past the span to the
+ * successor.  dry_out / wet_out [B, n_out_frames * U] (dry_out may be NULL).  n_out_frames must be a
+ * multiple of seg_frames and L - 1 <= n_out_frames * U.
+ * Workspace: b200ddsp_timeline_workspace_bytes(). */
+int b200ddsp_forward_timeline(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
+                              const float* reverb_ir, float* dry_out, float* wet_out, int B, int F, int H,
+                              int S, int M, int L, int seg_frames, uint64_t seed,
+                              const b200ddsp_span* span, const b200ddsp_link* tail, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* The same from HOST control tensors / into HOST audio (see b200ddsp_forward_polyphonic_host). */
+int b200ddsp_forward_timeline_host(b200ddsp_handle* h, const b200ddsp_voice* voices_host, int P,
+                                   const float* reverb_ir_host, float* dry_out_host, float* wet_out_host,
+                                   int B, int F, int H, int S, int M, int L, int seg_frames, uint64_t seed,
+                                   const b200ddsp_span* span, const b200ddsp_link* tail, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+size_t b200ddsp_timeline_workspace_bytes(const b200ddsp_handle* h, int P, int B, int F, int H, int S, int M,
+                                         int L, int n_out_frames, int seg_frames, int host_inputs,
+                                         int with_noise);
+
+/* The reverb stage of b200ddsp_forward_timeline alone: dry [B, n_seg * N] device -> out. */
+int b200ddsp_timeline_reverb(b200ddsp_handle* h, const float* dry, const float* reverb_ir, float* out,
+                             int B, int n_seg, int N, int L, const b200ddsp_link* tail, void* workspace,
+                             size_t workspace_bytes, void* stream);
+size_t b200ddsp_timeline_reverb_workspace_bytes(const b200ddsp_handle* h, int B, int n_seg, int N, int L);
 
 /* NoteRelease -- modules/sub_modules.py:1174-1188 (tfkl.RNN over F0ProcessorCell, :1114-1171): holds
  * each voice's last played MIDI note for `release_frames` (= release_duration * frame_rate; the

@@ -63,6 +63,20 @@ def test_struct_layouts_match_the_header():
     vfields = re.findall(r'const float\*\s+([a-z_0-9]+)\s*;', voice)
     assert vfields == [f[0] for f in _lib.Voice._fields_]
     assert ctypes.sizeof(_lib.Voice) == 6 * ctypes.sizeof(ctypes.c_void_p)
+    def body(name):
+        end = text.index('} ' + name + ';')
+        return text[text.rindex('typedef struct {', 0, end) + len('typedef struct {'):end]
+
+    link = body('b200ddsp_link')
+    link = re.sub(r'/\*.*?\*/', '', link, flags=re.S)
+    lfields = re.findall(r'\b(?:const float\*|float\*|unsigned long long\*?)\s+([a-z_0-9]+)\s*;', link)
+    assert lfields == [f[0] for f in _lib.Link._fields_]
+    assert ctypes.sizeof(_lib.Link) == 8 * 8
+    span = body('b200ddsp_span')
+    span = re.sub(r'/\*.*?\*/', '', span, flags=re.S)
+    sfields = re.findall(r'\b(?:long long|int|b200ddsp_link)\s+([a-z_0-9]+)\s*;', span)
+    assert sfields == [f[0] for f in _lib.Span._fields_]
+    assert ctypes.sizeof(_lib.Span) == 4 * 8 + ctypes.sizeof(_lib.Link)
 
 
 def test_create_fails_loudly_without_a_gpu(lib_path):

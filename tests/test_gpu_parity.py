@@ -470,54 +470,6 @@ def test_reverb_full_and_timeline(dp, dev):
     assert rel_err(wet, want) < TIGHT
 
 
-def test_timeline_overlap_add_kernel_single_rank(dp, dev):
-    """csrc/timeline.cuh on one rank (no successor): overlap-add of the 'valid' convolutions ==
-    reverb of the concatenated timeline; with a fake 'successor' buffer on the same device the
-    carry lands in its head, added to what that buffer's own launch put there."""
-    from ddsp_piano_b200 import sharding
-    from ddsp_piano_b200.processors import _DEFAULT_CFG
-    eng = dp.get_engine(dev, **{**_DEFAULT_CFG, 'sample_rate': 24000})
-    S, N, L = 3, 2400, 5000                                # tail covers two successors
-    rng = np.random.default_rng(5)
-    dry = (rng.standard_normal([S, N]) * 0.1).astype(np.float32)
-    ir = (rng.standard_normal([L]) * np.exp(-6 * np.arange(L) / L) * 1e-2).astype(np.float32)
-    peer = sharding.PeerTimeline(eng, S, N, L, 0, 1)
-    wet = peer.reverb(cu(dry, dev), cu(ir, dev)).clone()
-    h = ir.astype(np.float64).copy()
-    h[0] = 0
-    x = dry.astype(np.float64).reshape(-1)
-    full = np.convolve(x, h)
-    want = (full[:x.size] + x).reshape(S, N)
-    assert rel_err(wet, want) < TIGHT
-    # the carry, into a second peer-visible buffer that already holds its own head
-    other = sharding.PeerTimeline(eng, S, N, L, 0, 1)
-    other.out.zero_()
-    other.out[:L - 1] += 1.0
-    wet_full = eng.reverb_full(cu(dry, dev), cu(ir, dev)[None, :].expand(S, L).contiguous())
-    peer.out[:L - 1].zero_()
-    eng.timeline_overlap_add(wet_full, None, peer.ptr, other.ptr, S, N, L)
-    torch.cuda.synchronize()
-    carry = other.out[:L - 1].cpu().numpy() - 1.0
-    assert np.max(np.abs(carry - full[x.size:x.size + L - 1])) / np.max(np.abs(want)) < TIGHT
-    peer.close()
-    other.close()
-
-
-def test_timeline_reverb_two_gpus_nccl():
-    """BASELINE config 4's exchange step on real GPUs (skipped on a single-GPU box)."""
-    import subprocess
-    import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    proc = subprocess.run(
-        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-         '--master-addr', '127.0.0.1', '--master-port', '29517',
-         os.path.join(root, 'tests', 'multi_gpu_timeline.py')],
-        capture_output=True, text=True, timeout=600)
-    assert proc.returncode == 0 and 'TIMELINE_OK' in proc.stdout, proc.stdout + proc.stderr
-
-
 def test_dag_stress_shapes_vs_oracle(dp, dev):
     """BASELINE configs[4] shapes (48 kHz, H = 128 -> 4 partial groups, M = 96, U = 192) at a
     size the oracle finishes in seconds; fused forward vs oracle."""
