@@ -175,6 +175,8 @@ def load():
     lib.b200ddsp_workspace_bytes_host.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci]
     lib.b200ddsp_midi_roll_to_conditioning.restype = ci
     lib.b200ddsp_midi_roll_to_conditioning.argtypes = [vp, ci, ci, ci, ctypes.c_float, vp, vp]
+    lib.b200ddsp_measure_fma_rate.restype = ci
+    lib.b200ddsp_measure_fma_rate.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
     lib.b200ddsp_launch_count.restype = u64
     lib.b200ddsp_launch_count.argtypes = [vp]
     lib.b200ddsp_set_profiling.restype = ci
@@ -195,7 +197,7 @@ EXPORTS = ['b200ddsp_version', 'b200ddsp_last_error', 'b200ddsp_create', 'b200dd
            'b200ddsp_fdn_workspace_bytes',
            'b200ddsp_forward_polyphonic', 'b200ddsp_forward_polyphonic_host',
            'b200ddsp_workspace_bytes_host', 'b200ddsp_midi_roll_to_conditioning',
-           'b200ddsp_launch_count', 'b200ddsp_set_profiling',
+           'b200ddsp_launch_count', 'b200ddsp_measure_fma_rate', 'b200ddsp_set_profiling',
            'b200ddsp_last_stage_ms']
 CONV_MASK_IR0, CONV_ADD_DRY, CONV_FULL = 1, 2, 4
 STAGES = ['controls', 'phase_ends', 'phase_scan', 'oscillators', 'noise', 'reverb', 'mix']

@@ -25,6 +25,7 @@
 #include "reverb.cuh"
 #include "control_rate.cuh"
 #include "timeline.cuh"
+#include "ubench.cuh"
 
 using namespace b200ddsp;
 
@@ -2150,6 +2151,42 @@ extern "C" int b200ddsp_peer_open(b200ddsp_handle* h, const unsigned char* ipc_h
 extern "C" int b200ddsp_peer_close(b200ddsp_handle* h, void* peer_ptr) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
   if (peer_ptr) CUDA_TRY(h, cudaIpcCloseMemHandle(peer_ptr));
+  return B200DDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measured FP32 peak (bench.py's roofline denominator)
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200ddsp_measure_fma_rate(b200ddsp_handle* h, int packed, double* lane_ops_per_s,
+                                         void* stream) {
+  if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (!lane_ops_per_s) return fail(h, B200DDSP_BAD_ARGUMENT, "null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ctas = h->n_sms, threads = 1024, iters = 1 << 15;   // 8 warps per scheduler, ~1 ms
+  float* out = nullptr;
+  CUDA_TRY(h, cudaMalloc(&out, (size_t)ctas * threads * sizeof(float)));   // not on the synthesis path
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {   // first repetition warms the clocks
+    cudaEventRecord(e0, st);
+    if (packed) fma_rate_kernel<true><<<ctas, threads, 0, st>>>(out, 0.999f, iters);
+    else fma_rate_kernel<false><<<ctas, threads, 0, st>>>(out, 0.999f, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  const cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess || best <= 0.f)
+    return fail(h, B200DDSP_CUDA_ERROR, "fma_rate_kernel: %s", cudaGetErrorString(e));
+  h->launches += 4;
+  *lane_ops_per_s = (double)ctas * threads * iters * kUbenchChains * 2.0 / (best * 1e-3);
   return B200DDSP_OK;
 }
 

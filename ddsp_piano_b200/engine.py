@@ -101,6 +101,14 @@ class Engine:
     def set_profiling(self, enable):
         self.check(self.lib.b200ddsp_set_profiling(self.handle, int(bool(enable))))
 
+    def measure_fma_rate(self, packed=True):
+        """FMA-pipe lane-operations per second this GPU sustains right now (bench.py's FP32 peak)."""
+        v = ctypes.c_double()
+        with torch.cuda.device(self.device):
+            self.check(self.lib.b200ddsp_measure_fma_rate(self.handle, int(packed), ctypes.byref(v),
+                                                          self.stream()))
+        return float(v.value)
+
     def last_stage_ms(self):
         """Device time of each stage of the most recent call (needs set_profiling(True))."""
         ms = (ctypes.c_float * len(_lib.STAGES))()

@@ -444,7 +444,7 @@ class ProcessorGroup:
                     ir_key=ir_key)
 
     # -- execution ------------------------------------------------------------------------
-    def _run_fused(self, outputs):
+    def _run_fused(self, outputs, timeline=None):
         plan = self._plan
         additive, noise, reverb = plan['additive'], plan['noise'], plan['reverb']
         voices = []
@@ -465,7 +465,13 @@ class ProcessorGroup:
         eng = get_engine(dev, **cfg)
         ir = nested_lookup(plan['ir_key'], outputs) if reverb is not None else None
         seed = (noise.seed + 0x9E3779B97F4A7C15 * noise.next_stream_id(len(voices))) & (2 ** 64 - 1)
-        if on_host:
+        if timeline is not None:
+            # one span of a timeline (sharding.SpanChain): the features cover the span's input frames
+            if reverb is None:
+                raise ValueError('a timeline call needs the reverb node (its tail is what crosses spans)')
+            dry, wet = eng.forward_timeline(voices, ir, timeline['span'], timeline['seg_frames'],
+                                            tail=timeline.get('tail'), seed=seed)
+        elif on_host:
             # HOST features (numpy / CPU tensors): staged copies overlap the kernels; the signals
             # come back as pinned host tensors, valid after torch.cuda.current_stream().synchronize()
             dry, wet = eng.forward_polyphonic_host(voices, reverb_ir=ir, seed=seed)
@@ -479,10 +485,12 @@ class ProcessorGroup:
         outputs['out'] = last
         return outputs
 
-    def get_controls(self, inputs, **kwargs):
+    def get_controls(self, inputs, timeline=None, **kwargs):
         outputs = inputs
         if self._plan is not None:
-            return self._run_fused(outputs)
+            return self._run_fused(outputs, timeline)
+        if timeline is not None:
+            raise ValueError('timeline calls run through the fused polyphonic DAG only')
         module_outputs = None
         for module_key, input_keys in self.dag:
             module = self._modules[module_key]
@@ -495,8 +503,12 @@ class ProcessorGroup:
     def get_signal(self, outputs):
         return outputs['out']['signal']
 
-    def __call__(self, inputs, return_outputs_dict=False, **kwargs):
-        controls = self.get_controls(inputs, **kwargs)
+    def __call__(self, inputs, return_outputs_dict=False, timeline=None, **kwargs):
+        """``timeline`` (no counterpart in the reference, which runs a piece in one pass): a dict
+        ``{'span': _lib.Span, 'seg_frames': int, 'tail': _lib.Link or None}`` makes this call ONE SPAN of
+        a longer timeline -- ``inputs`` then cover the span's input frames (one halo frame either side)
+        and the signals its output frames; see ``sharding.SpanChain`` and DESIGN.md section 6."""
+        controls = self.get_controls(inputs, timeline=timeline, **kwargs)
         signal = self.get_signal(controls)
         if return_outputs_dict:
             return dict(signal=signal, controls=controls)

@@ -353,6 +353,13 @@ size_t b200ddsp_workspace_bytes_host(const b200ddsp_handle* h, int P, int B, int
 int b200ddsp_midi_roll_to_conditioning(const float* roll, int n_frames, int n_pitches, int n_synths,
                                        float first_pitch, float* conditioning, float* polyphony);
 
+/* Measured FP32 peak for the roofline of the oscillator bank (which is bound by the FMA pipe, not by
+ * HBM): runs independent FFMA2 (packed != 0) or scalar FFMA chains on every SM for about a
+ * millisecond and returns the achieved FMA-pipe lane-operations per second (one FFMA2 = 2 lane
+ * operations; multiply by 2 for FLOP/s).  Timed with CUDA events on `stream`; synchronises it;
+ * allocates and frees its own 600 KB -- a measurement, not part of the synthesis path. */
+int b200ddsp_measure_fma_rate(b200ddsp_handle* h, int packed, double* lane_ops_per_s, void* stream);
+
 /* Number of kernel launches enqueued by this handle since creation (bench.py's
  * gpu_launches claim is read from here). */
 uint64_t b200ddsp_launch_count(const b200ddsp_handle* h);

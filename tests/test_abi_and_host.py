@@ -317,7 +317,12 @@ def test_bench_live_chain_samples_matches_brute_force():
                 t1 = min(N, t0 + 1000) - 1
                 nh = live[t0 // U:min(29, t1 // U + 1) + 1].max()
                 total += int(nh) * 32 * (t1 + 1 - t0)
-    assert bench.live_chain_samples(w, x) == total
+    synth, phase = bench.live_chain_samples(w, f0[..., 0], x['inharm_coef'][..., 0])
+    assert synth == total
+    # the phase pass follows a half-group through chunk c only if a LATER chunk sounds; a span that hands
+    # its state on follows every half-group (3 for H = 40) through every chunk
+    assert 0 < phase < synth
+    assert bench.live_chain_samples(w, f0[..., 0], x['inharm_coef'][..., 0], carry_all=True)[1] == 4 * 3 * 32 * N
     assert bench.bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3)   # never raises without a GPU
 
 
