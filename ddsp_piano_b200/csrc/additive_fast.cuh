@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(128) additive_alive_chunks_kernel(
 }
 
 enum { kAmpSilent = 0, kAmpNoCheck = 1, kAmpCheck = 2 };
+// Synthesis units are SUB-chunks: the phase pass stores the in-chunk accumulator at every kSubLen-th
+// sample, so pass 2 can enter a chunk at those points with bit-identical state.  A 1000-sample chunk
+// becomes 4 units (256 + 256 + 256 + 232): four times as many, four times shorter work items -- the
+// tail of the stage and the single-wave buckets shrink accordingly (a 1000-sample unit held its warp
+// for ~0.2 ms whatever else the GPU had to do).
+constexpr int kSubLen = 256;    // multiple of the 8-sample phase body and of kWrapEvery
 constexpr int kOscUnroll = 4;   // samples per unrolled body of the synthesis pass
 
 // cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
@@ -346,31 +352,45 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
   }
 }
 
-// One (row, substring pair, chunk) on one warp, half-warp layout.  ENDS_ONLY: phase chain only,
-// writes the chunk end phases; otherwise writes the audio of the chunk to `row_out`.
+// One (row, substring pair, chunk) on one warp, half-warp layout.  ENDS_ONLY: phase chain only over the
+// whole chunk, writes the accumulator at the sub-unit boundaries and the chunk end phases; otherwise
+// sub-unit q of the chunk: writes its audio to `row_out` (the chunk's base).
 template <int NC, int LW, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
-                                            int c, int lane, const float* win, float* row_out) {
+                                            int c, int q, int lane, const float* win, float* row_out) {
   const int t0 = c * a.chunk;
-  const int t1 = min(a.N, t0 + a.chunk);
+  const int tc1 = min(a.N, t0 + a.chunk);              // end of the chunk
+  const int ts = ENDS_ONLY ? t0 : t0 + q * kSubLen;    // first / one-past-last sample of this unit
+  const int t1 = (ENDS_ONLY || a.n_sub == 1) ? tc1 : min(tc1, ts + kSubLen);
   const int l = lane & (LW - 1), s = s0 + lane / LW;   // LW = 16: two substrings on the half-warps
   OscStateH<NC> st;
-  int k = t0 / a.U;
-  int r = t0 - k * a.U;
+  int k = ts / a.U;
+  int r = ts - k * a.U;
   k += a.koff;                                         // input frame (spans carry halo frames in front)
   bool steady;
   int amp_mode;
   enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
+  const size_t osc_chunk = ((size_t)row * a.S + s) * a.n_chunks + c;
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     st.ph[j] = 0.f;
     st.off[j] = 0.f;
     const int h = l + LW * j;
-    if (!ENDS_ONLY && (c > 0 || a.seeded) && h < a.H)
-      st.off[j] = a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h];
+    if (!ENDS_ONLY && h < a.H) {
+      if (c > 0 || a.seeded) st.off[j] = a.offsets[osc_chunk * a.H + h];
+      if (q > 0) st.ph[j] = a.mids[(osc_chunk * (a.n_sub - 1) + (q - 1)) * a.H + h];
+    }
   }
-  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk and frame lengths are multiples of 8
-  for (int t = t0; t < t1; t += STEP, r += STEP) {
+  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk, frame and sub-unit lengths are multiples of 8
+  for (int t = ts; t < t1; t += STEP, r += STEP) {
+    if (ENDS_ONLY && a.n_sub > 1 && t > t0 && ((t - t0) & (kSubLen - 1)) == 0) {
+      const int qq = (t - t0) / kSubLen - 1;           // state at the start of sub-unit qq + 1
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int h = l + LW * j;
+        if (h < a.H) a.mids[(osc_chunk * (a.n_sub - 1) + qq) * a.H + h] = st.ph[j];
+      }
+    }
     if (r == a.U) {
       r = 0;
       ++k;
@@ -411,7 +431,7 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     for (int j = 0; j < NC; ++j) {
       const int h = l + LW * j;
       if (h < a.H)
-        a.offsets[(((size_t)row * a.S + s) * a.n_chunks + c) * a.H + h] = floormod_two_pi(st.ph[j]);
+        a.offsets[osc_chunk * a.H + h] = floormod_two_pi(st.ph[j]);
     }
   }
 }
@@ -423,14 +443,14 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
 // register budget of the kernel, to what the configured H needs).
 template <int SP, bool ENDS_ONLY, bool PLAIN, int CMAX = 8>
 __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const float* fa_lerp, int nh,
-                                                   int row, int s0, int c, int lane, const float* win,
-                                                   float* row_out) {
+                                                   int row, int s0, int c, int q, int lane,
+                                                   const float* win, float* row_out) {
   constexpr int LW = (SP == 2) ? 16 : 32;
   const int chains = (SP == 2) ? nh : (nh + 1) / 2;
 #define B200DDSP_CHAIN_CASE(N)                                                                   \
   if constexpr (CMAX >= N) {                                                                     \
     if (chains == N || (N == CMAX && chains > N)) {                                              \
-      osc_chunk_h<N, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, lane, win, row_out);          \
+      osc_chunk_h<N, LW, ENDS_ONLY, PLAIN>(a, fa_lerp, row, s0, c, q, lane, win, row_out);       \
       return;                                                                                    \
     }                                                                                            \
   }
@@ -478,7 +498,7 @@ __device__ __forceinline__ int list_append_slot(int* counter, bool active, int k
 __global__ void __launch_bounds__(256) additive_plan_kernel(
     const unsigned char* __restrict__ synth_na, const unsigned char* __restrict__ ends_na,
     AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks, int B,
-    const PlanGroups groups, int carry_all) {
+    const PlanGroups groups, int carry_all, int n_sub) {
   // lists: [kPlanSlots][kMaxGroups][n_units]
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = i < n_units;
@@ -496,8 +516,14 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
     const int pos = list_append_slot(ns > 0 ? &plan->count[slot][ns - 1] : nullptr, ns > 0, key);
     if (ns > 0) lists[(size_t)key * n_units + pos] = i;
   }
-  const int ne = in_range ? ends_na[i] : 0;
-  const bool ends = ne > 0 && (c < n_chunks - 1 || carry_all);
+  // pass 1 follows a half-group through chunk c if a later chunk needs its end phase (ends_na) or if
+  // pass 2 enters this chunk at a sub-unit boundary (n_sub > 1: it needs the accumulator there)
+  int ne = in_range ? ends_na[i] : 0;
+  bool ends = ne > 0 && (c < n_chunks - 1 || carry_all);
+  if (n_sub > 1 && ns > 0) {
+    ne = ends ? max(ne, ns) : ns;
+    ends = true;
+  }
   {
     const int key = ne - 1;
     const int pos = list_append_slot(ends ? &plan->count[0][ne - 1] : nullptr, ends, key);
@@ -522,13 +548,15 @@ __global__ void __launch_bounds__(kAddThreads, 3) additive_fast_kernel(const Add
   }
   const int kind = fa.slot;
   const int sets = a.S / SP;
+  const int n_sub = ENDS_ONLY ? 1 : a.n_sub;
+  const int per_unit = sets * n_sub;               // items per listed unit: (set, sub-unit)
   const int n_units = a.P * a.B * a.n_chunks;
   int bucket_end[kMaxGroups];   // cumulative item counts, heaviest bucket first
   {
     int acc = 0;
 #pragma unroll
     for (int i = 0; i < kMaxGroups; ++i) {
-      acc += fa.plan->count[kind][kMaxGroups - 1 - i] * sets;
+      acc += fa.plan->count[kind][kMaxGroups - 1 - i] * per_unit;
       bucket_end[i] = acc;
     }
   }
@@ -543,14 +571,15 @@ __global__ void __launch_bounds__(kAddThreads, 3) additive_fast_kernel(const Add
       if (item >= bucket_end[i]) { bi = i + 1; begin = bucket_end[i]; }
     const int na = kMaxGroups - bi;   // live half-groups of the bucket
     const int local = item - begin;
-    const int unit = fa.lists[(size_t)(kind * kMaxGroups + na - 1) * n_units + local / sets];
-    const int set = local - (local / sets) * sets;
+    const int unit = fa.lists[(size_t)(kind * kMaxGroups + na - 1) * n_units + local / per_unit];
+    const int rem = local - (local / per_unit) * per_unit;
+    const int set = rem / n_sub, q = rem - set * n_sub;
     const int row = unit / a.n_chunks;
     const int c = unit - row * a.n_chunks;
     const int v = row / a.B, b = row - v * a.B;
     float* out = ENDS_ONLY ? nullptr
                            : a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-    osc_chunk_dispatch<SP, ENDS_ONLY, PLAIN>(a, fa.lerp, na, row, set * SP, c, lane, win, out);
+    osc_chunk_dispatch<SP, ENDS_ONLY, PLAIN>(a, fa.lerp, na, row, set * SP, c, q, lane, win, out);
   }
 }
 
@@ -602,21 +631,23 @@ additive_synth_kernel(const AdditiveFastArgs fa) {
   float* win = smem;                                   // [U] rising half of hann(2U)
   const int lane = threadIdx.x & 31;
   const int sets = a.S / SP;
-  const int n_items = fa.plan->count[fa.slot][NH - 1] * sets;
+  const int per_unit = sets * a.n_sub;                           // items per listed unit: (set, sub-unit)
+  const int n_items = fa.plan->count[fa.slot][NH - 1] * per_unit;
   if ((int)blockIdx.x * kSynthWarps >= n_items) return;          // whole CTA has nothing to do
   for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];
   __syncthreads();
   const int item = blockIdx.x * kSynthWarps + (threadIdx.x >> 5);
   if (item >= n_items) return;
   const int n_units = a.P * a.B * a.n_chunks;
-  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NH - 1) * n_units + item / sets];
-  const int set = item - (item / sets) * sets;
+  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NH - 1) * n_units + item / per_unit];
+  const int rem = item - (item / per_unit) * per_unit;
+  const int set = rem / a.n_sub, q = rem - set * a.n_sub;        // the sub-units of a chunk share a CTA
   const int row = unit / a.n_chunks;
   const int c = unit - row * a.n_chunks;
   const int v = row / a.B, b = row - v * a.B;
   float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, lane, win, out);
-  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, lane, win, out);
+  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, out);
+  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, q, lane, win, out);
 }
 
 }  // namespace b200ddsp

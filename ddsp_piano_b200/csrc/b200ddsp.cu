@@ -49,6 +49,10 @@ struct b200ddsp_handle {
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_mags[4] = {}, ev_ir = nullptr, ev_enter = nullptr, ev_small = nullptr;
   bool profiling = false;
+  bool trace = false;
+  std::vector<cudaEvent_t> trace_ev;      // [0] = entry of the call
+  std::vector<std::string> trace_what;
+  size_t trace_n = 0;
   cudaEvent_t ev_begin[B200DDSP_N_STAGES] = {};
   cudaEvent_t ev_end[B200DDSP_N_STAGES] = {};
   bool ev_used[B200DDSP_N_STAGES] = {};
@@ -73,6 +77,18 @@ struct StageTimer {
 
 static void reset_stage_flags(b200ddsp_handle* h) {
   for (int i = 0; i < B200DDSP_N_STAGES; ++i) h->ev_used[i] = false;
+}
+
+static void trace_launch(b200ddsp_handle* h, const char* what, cudaStream_t stream) {
+  if (!h->trace || !h->profiling || h->trace_n >= h->trace_ev.size()) return;
+  char tag[96];
+  const char* name = stream == h->noise_stream ? "noise" : stream == h->hd_stream ? "side" :
+                     stream == h->copy_stream ? "copy" : "main";
+  for (int i = 0; i < kMaxGroups - 1; ++i)
+    if (stream == h->aux_stream[i]) name = "aux";
+  snprintf(tag, sizeof tag, "%-5s %s", name, what);
+  cudaEventRecord(h->trace_ev[h->trace_n], stream);
+  h->trace_what[h->trace_n++] = tag;
 }
 
 static thread_local char g_create_err[512] = {0};
@@ -100,6 +116,14 @@ static int fail(b200ddsp_handle* h, int code, const char* fmt, ...) {
       return fail(h, B200DDSP_CUDA_ERROR, "launch of %s failed: %s", what,                   \
                   cudaGetErrorString(e_));                                                   \
     (h)->launches++;                                                                         \
+  } while (0)
+
+// Developer trace (B200DDSP_TRACE=1 + profiling on): an event after every launch of the forward path;
+// b200ddsp_last_stage_ms prints when each launch COMPLETED relative to the call's entry, by stream.
+#define CHECK_LAUNCH_ON(h, what, stream)                                                     \
+  do {                                                                                       \
+    CHECK_LAUNCH(h, what);                                                                   \
+    trace_launch(h, what, stream);                                                           \
   } while (0)
 
 // tuning knobs for experiments (not part of the ABI)
@@ -245,6 +269,12 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   if (!h) return fail(nullptr, B200DDSP_CUDA_ERROR, "out of host memory");
   h->cfg = *cfg;
   h->device = dev;
+  if (getenv("B200DDSP_TRACE")) {
+    h->trace = true;
+    h->trace_ev.resize(256);
+    h->trace_what.resize(256);
+    for (auto& e : h->trace_ev) cudaEventCreate(&e);
+  }
   h->n_sms = prop.multiProcessorCount;
   h->U = (int)((double)cfg->sample_rate / (double)cfg->frame_rate);   // inharm_synth.py:163-165
   h->fast_div = verify_fast_division((float)cfg->sample_rate);
@@ -322,6 +352,18 @@ extern "C" int b200ddsp_last_stage_ms(b200ddsp_handle* h, float* ms) {
     CUDA_TRY(h, cudaEventSynchronize(h->ev_end[i]));
     CUDA_TRY(h, cudaEventElapsedTime(&ms[i], h->ev_begin[i], h->ev_end[i]));
   }
+  if (h->trace && h->trace_n > 1) {
+    static int dumps = 0;
+    if (dumps++ < env_int("B200DDSP_TRACE", 1)) {
+      for (size_t i = 1; i < h->trace_n; ++i) {
+        float t = 0.f;
+        cudaEventSynchronize(h->trace_ev[i]);
+        cudaEventElapsedTime(&t, h->trace_ev[0], h->trace_ev[i]);
+        fprintf(stderr, "trace %8.1f us  %s\n", t * 1e3f, h->trace_what[i].c_str());
+      }
+      fprintf(stderr, "trace ----\n");
+    }
+  }
   return B200DDSP_OK;
 }
 
@@ -390,9 +432,19 @@ static int voice_groups_for(int P, int B, int n_chunks) {
 
 static int substrings_per_pass(int S) { return (S % 2 == 0) ? 2 : 1; }
 
+// Synthesis units per chunk on the fast additive path (additive_fast.cuh, kSubLen); the plain cumsum of
+// inference=0 has no phase pass that could record the state inside its single chunk.
+static int sub_units_for(const b200ddsp_handle* h, int N) {
+  if (!h->cfg.inference) return 1;
+  const int n = (chunk_for(h, N) + kSubLen - 1) / kSubLen;
+  const int forced = env_int("B200DDSP_SUB_UNITS", 0);   // 1 = whole-chunk units (A/B timing)
+  return forced == 1 ? 1 : n;
+}
+
 // Device buffers of the additive synth for R = P*B rows (byte offsets into a workspace).
 struct AdditiveLayout {
   size_t offsets;    // float [R*S, n_chunks, H]   chunk end phases, then chunk offsets
+  size_t mids;       // float [R*S, n_chunks, n_sub - 1, H]  phase accumulator at the sub-unit boundaries
   size_t na_frame;   // u8 [R, F]                  live partial groups per frame
   size_t synth_na;   // u8 [R, n_chunks]           live partial groups per chunk
   size_t ends_na;    // u8 [R, n_chunks]           groups whose end phase a later chunk needs
@@ -419,6 +471,8 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
   size_t o = at;
   auto take = [&](size_t bytes) { size_t p = o; o += align_up(bytes); return p; };
   a.offsets = take(R * S * n_chunks * H * 4);
+  const size_t n_sub = (size_t)sub_units_for(h, (int)N);
+  a.mids = take(R * S * n_chunks * (n_sub > 1 ? n_sub - 1 : 1) * H * 4);
   a.na_frame = take(R * F);
   a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
@@ -671,11 +725,13 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
   a.decays = decays; a.decay_time = decay_time;
   a.offsets = (float*)(base + lay.offsets);
+  a.mids = (float*)(base + lay.mids);
   a.out = r->partials;
   a.window = h->d_window;
   a.B = B; a.P = P; a.F = F; a.H = H; a.S = S; a.U = U; a.N = N;
   a.chunk = chunk_for(h, N);
   a.n_chunks = r->n_chunks;
+  a.n_sub = r->fast ? sub_units_for(h, N) : 1;
   a.voices_per_group = (P + r->G - 1) / r->G;
   a.koff = span ? span->koff : 0;
   a.seeded = (span && span->seeded) ? 1 : 0;
@@ -776,32 +832,32 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       if (!na_frame_ready) {
         additive_alive_frames_kernel<<<(R * r.F + 7) / 8, 256, 0, st>>>(a.amp, a.hd, r.na_frame,
                                                                         R * r.F, r.H);
-        CHECK_LAUNCH(h, "additive_alive_frames_kernel");
+        CHECK_LAUNCH_ON(h, "additive_alive_frames_kernel", st);
       }
       additive_lerp_kernel<<<(a.N + 255) / 256, 256, 0, st>>>((float*)r.fa.lerp, a.N, a.U, a.scale,
                                                                r.span ? r.span->tg0 : 0);
-      CHECK_LAUNCH(h, "additive_lerp_kernel");
+      CHECK_LAUNCH_ON(h, "additive_lerp_kernel", st);
       additive_alive_chunks_kernel<<<R, 128, (size_t)r.n_chunks, st>>>(
           r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks, a.koff,
           carry ? (r.H + 15) / 16 : 0);
-      CHECK_LAUNCH(h, "additive_alive_chunks_kernel");
+      CHECK_LAUNCH_ON(h, "additive_alive_chunks_kernel", st);
       CUDA_TRY(h, cudaMemsetAsync(r.fa.plan, 0, sizeof(AdditivePlan), st));
       const int n_units = R * r.n_chunks;
       additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(
           r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, n_units, r.n_chunks, r.B, r.groups,
-          carry ? 1 : 0);
-      CHECK_LAUNCH(h, "additive_plan_kernel");
+          carry ? 1 : 0, a.n_sub);
+      CHECK_LAUNCH_ON(h, "additive_plan_kernel", st);
     }
     if (small_kernels_done) {
       CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
       small_kernels_done = nullptr;
     }
-    if (r.n_chunks > 1 || carry) {
+    if (r.n_chunks > 1 || carry || a.n_sub > 1) {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
       AdditiveFastArgs fa = r.fa;
       fa.slot = 0;
       launch_additive_fast(fa, true, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), 0, st);
-      CHECK_LAUNCH(h, "additive_fast_kernel<ends>");
+      CHECK_LAUNCH_ON(h, "additive_fast_kernel<ends>", st);
     }
     if (r.n_chunks > 1 || carry || (r.span && r.span->seeded)) {
       OffsetsArgs oa{};
@@ -811,7 +867,7 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       oa.carry_all = carry ? 1 : 0;
       if (r.span) oa.link = r.span->phase;
       additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
-      CHECK_LAUNCH(h, "additive_offsets_kernel");
+      CHECK_LAUNCH_ON(h, "additive_offsets_kernel", st);
     }
     return B200DDSP_OK;
   }
@@ -819,14 +875,14 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
     {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
       launch_additive_generic(a, true, dim3(r.n_chunks - 1, r.B, r.G), st);
-      CHECK_LAUNCH(h, "additive_kernel<ends>");
+      CHECK_LAUNCH_ON(h, "additive_kernel<ends>", st);
     }
     StageTimer tm(h, B200DDSP_STAGE_PHASE_SCAN, st);
     OffsetsArgs oa{};
     oa.offsets = a.offsets;
     oa.n_osc_rows = R * r.S; oa.n_chunks = r.n_chunks; oa.H = r.H; oa.S = r.S;
     additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
-    CHECK_LAUNCH(h, "additive_offsets_kernel");
+    CHECK_LAUNCH_ON(h, "additive_offsets_kernel", st);
   }
   if (small_kernels_done) CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
   return B200DDSP_OK;
@@ -843,7 +899,7 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
     // one kernel per bucket (number of live 16-partial half-groups), heaviest on the caller's
     // stream, the others on auxiliary streams so that the buckets overlap; grids are sized for the
     // largest possible bucket, surplus CTAs exit at once
-    const long long max_items = (long long)Pg * r.B * r.n_chunks * r.sets;
+    const long long max_items = (long long)Pg * r.B * r.n_chunks * r.sets * r.a.n_sub;
     const int grid = (int)((max_items + kSynthWarps - 1) / kSynthWarps);
     const int n_buckets = (r.H + 15) / 16;
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
@@ -871,7 +927,11 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
         case 7: launch_synth_bucket<7>(fa, plain, grid, smem, s); break;
         default: launch_synth_bucket<8>(fa, plain, grid, smem, s); break;
       }
-      CHECK_LAUNCH(h, "additive_synth_kernel");
+      {
+        char what[40];
+        snprintf(what, sizeof what, "additive_synth_kernel<%d>", nh);
+        CHECK_LAUNCH_ON(h, what, s);
+      }
     }
     int aux = 0;
     for (int si = 1; si < kMaxGroups; ++si) {
@@ -896,7 +956,7 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
   a.voices_per_group = (Pg + G - 1) / G;
   a.out = r.partials + (size_t)(r.groups.n_groups == 1 ? 0 : g) * r.B * r.a.N;
   launch_additive_generic(a, false, dim3(r.n_chunks, r.B, G), st);
-  CHECK_LAUNCH(h, "additive_kernel<synth>");
+  CHECK_LAUNCH_ON(h, "additive_kernel<synth>", st);
   return B200DDSP_OK;
 }
 
@@ -1028,7 +1088,7 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
     t.bias = h->cfg.noise_initial_bias;
     dim3 grid((B * F + kTapsTileF - 1) / kTapsTileF, (M - 1 + kTapsTileD - 1) / kTapsTileD, v1 - v0);
     noise_taps_kernel<<<grid, 256, 0, st>>>(t, sub);
-    CHECK_LAUNCH(h, "noise_taps_kernel");
+    CHECK_LAUNCH_ON(h, "noise_taps_kernel", st);
   }
   NoiseArgs a{};
   a.taps = taps;
@@ -1048,9 +1108,10 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   const size_t smem = (size_t)L.total_floats * sizeof(float);
   if (smem > 227 * 1024)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise tile needs %zu bytes of shared memory", smem);
-  // warps split the U/8 blocks of a frame: one block per thread up to 16 warps, else 2..4
+  // warps split the U/8 blocks of a frame: one block per thread up to 12 warps, else 2..4 per thread
+  // on up to 16 warps
   const int n_blocks = U / 8;
-  const int nb = (n_blocks + 15) / 16;
+  const int nb = n_blocks <= 12 ? 1 : (n_blocks <= 32 ? 2 : (n_blocks + 15) / 16);
   const int warps = (n_blocks + nb - 1) / nb;
   dim3 grid((F_out + kNoiseFrames - 1) / kNoiseFrames, B, n_slices);
   auto launch = [&](auto kernel) -> cudaError_t {
@@ -1068,7 +1129,7 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   }
   if (e != cudaSuccess)
     return fail(h, B200DDSP_CUDA_ERROR, "noise_fir_kernel attribute: %s", cudaGetErrorString(e));
-  CHECK_LAUNCH(h, "noise_fir_kernel");
+  CHECK_LAUNCH_ON(h, "noise_fir_kernel", st);
   return B200DDSP_OK;
 }
 
@@ -1092,7 +1153,7 @@ static int run_mix(b200ddsp_handle* h, const float* noise_part, int n_noise, con
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "mixer needs N %% 4 == 0 (N=%d)", N);
   StageTimer tm(h, B200DDSP_STAGE_MIX, st);
   mix_kernel<<<dim3((N / 4 + 255) / 256, B), 256, 0, st>>>(m);
-  CHECK_LAUNCH(h, "mix_kernel");
+  CHECK_LAUNCH_ON(h, "mix_kernel", st);
   return B200DDSP_OK;
 }
 
@@ -1240,14 +1301,14 @@ static int run_reverb_ir_phase(b200ddsp_handle* h, const float* ir, int B, int N
   const std::vector<int> radices = fft_radices(n);
   const int pairs = (B + 1) / 2;
   fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
-  CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  CHECK_LAUNCH_ON(h, "fft_twiddle_kernel", st);
   float4* scales = reinterpret_cast<float4*>(tw + n);
   unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);
   CUDA_TRY(h, cudaMemsetAsync(maxima, 0, (size_t)B * 8, st));
   reverb_maxima1_kernel<<<dim3(32, B), 256, 0, st>>>(ir, maxima, L, 1, 1);
-  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_maxima1_kernel", st);
   reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);   // audio part still 1
-  CHECK_LAUNCH(h, "reverb_scales_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_scales_kernel", st);
   float2* src = nullptr;
   float2* dst = buf_a;
   int Ns = 1;
@@ -1255,7 +1316,7 @@ static int run_reverb_ir_phase(b200ddsp_handle* h, const float* ir, int B, int N
     const StoreComplex sto{dst, n};
     if (i == 0) launch_fft_pass(radices[i], LoadRealPair{ir, scales, L, 1, B, 1}, sto, tw, n, Ns, pairs, st);
     else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, pairs, st);
-    CHECK_LAUNCH(h, "fft_pass_kernel<ir>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<ir>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == buf_a) ? buf_b : buf_a;
@@ -1276,9 +1337,9 @@ static int run_reverb_audio_phase(b200ddsp_handle* h, const float* audio, const 
   float4* scales = reinterpret_cast<float4*>(tw + n);
   unsigned int* maxima = reinterpret_cast<unsigned int*>(scales + B);
   reverb_maxima1_kernel<<<dim3(32, B), 256, 0, st>>>(audio, maxima, N, 0, 0);
-  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_maxima1_kernel", st);
   reverb_scales_kernel<<<(B + 63) / 64, 64, 0, st>>>(maxima, scales, B);
-  CHECK_LAUNCH(h, "reverb_scales_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_scales_kernel", st);
   float2* wa = buf_a + (size_t)pairs * n;   // rows [pairs, 2 pairs) of both buffers
   float2* wb = buf_b + (size_t)pairs * n;
   float2* src = nullptr;
@@ -1288,7 +1349,7 @@ static int run_reverb_audio_phase(b200ddsp_handle* h, const float* audio, const 
     const StoreComplex sto{dst, n};
     if (i == 0) launch_fft_pass(radices[i], LoadRealPair{audio, scales, N, 0, B, 0}, sto, tw, n, Ns, pairs, st);
     else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, tw, n, Ns, pairs, st);
-    CHECK_LAUNCH(h, "fft_pass_kernel<forward>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<forward>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == wa) ? wb : wa;
@@ -1296,7 +1357,7 @@ static int run_reverb_audio_phase(b200ddsp_handle* h, const float* audio, const 
   {
     dim3 grid((n / 2 + 1 + 255) / 256, pairs);
     reverb_spectrum_split_kernel<<<grid, 256, 0, st>>>(src, ir_spectra, dst, n);
-    CHECK_LAUNCH(h, "reverb_spectrum_split_kernel");
+    CHECK_LAUNCH_ON(h, "reverb_spectrum_split_kernel", st);
     src = dst;
     dst = (dst == wa) ? wb : wa;
   }
@@ -1309,7 +1370,7 @@ static int run_reverb_audio_phase(b200ddsp_handle* h, const float* audio, const 
     } else {
       launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, tw, n, Ns, pairs, st);
     }
-    CHECK_LAUNCH(h, "fft_pass_kernel<inverse>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<inverse>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == wa) ? wb : wa;
@@ -1427,13 +1488,13 @@ static int timeline_reverb_ir_phase(b200ddsp_handle* h, const TimelineReverbPlan
   const int n = p.nfft, rows = p.B * p.n_seg;
   const std::vector<int> radices = fft_radices(n);
   fft_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.tw, n);
-  CHECK_LAUNCH(h, "fft_twiddle_kernel");
+  CHECK_LAUNCH_ON(h, "fft_twiddle_kernel", st);
   CUDA_TRY(h, cudaMemsetAsync(p.maxima, 0, (size_t)(rows + p.B) * 8, st));
   unsigned int* max_ir = p.maxima + 2 * rows;
   reverb_maxima1_kernel<<<dim3(32, p.B), 256, 0, st>>>(p.ir, max_ir, p.L, 1, 1);
-  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_maxima1_kernel", st);
   timeline_scales_kernel<<<(rows + 63) / 64, 64, 0, st>>>(nullptr, max_ir, p.scales, p.ir_scales, rows, p.n_seg);
-  CHECK_LAUNCH(h, "timeline_scales_kernel");
+  CHECK_LAUNCH_ON(h, "timeline_scales_kernel", st);
   float2* src = nullptr;
   float2* dst = p.buf_a;
   int Ns = 1;
@@ -1441,7 +1502,7 @@ static int timeline_reverb_ir_phase(b200ddsp_handle* h, const TimelineReverbPlan
     const StoreComplex sto{dst, n};
     if (i == 0) launch_fft_pass(radices[i], LoadRealSingle{p.ir, p.ir_scales, p.L, 1}, sto, p.tw, n, Ns, p.B, st);
     else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, p.tw, n, Ns, p.B, st);
-    CHECK_LAUNCH(h, "fft_pass_kernel<ir>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<ir>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == p.buf_a) ? p.buf_b : p.buf_a;
@@ -1457,10 +1518,10 @@ static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbP
   const std::vector<int> radices = fft_radices(n);
   const int n_pass = (int)radices.size();
   reverb_maxima1_kernel<<<dim3(32, rows), 256, 0, st>>>(dry, p.maxima, p.N, 0, 0);
-  CHECK_LAUNCH(h, "reverb_maxima1_kernel");
+  CHECK_LAUNCH_ON(h, "reverb_maxima1_kernel", st);
   timeline_scales_kernel<<<(rows + 63) / 64, 64, 0, st>>>(p.maxima, p.maxima + 2 * rows, p.scales, nullptr, rows,
                                                           p.n_seg);
-  CHECK_LAUNCH(h, "timeline_scales_kernel");
+  CHECK_LAUNCH_ON(h, "timeline_scales_kernel", st);
   float2* wa = p.buf_a + (size_t)p.B * n;
   float2* wb = p.buf_b + (size_t)p.B * n;
   float2* src = nullptr;
@@ -1470,7 +1531,7 @@ static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbP
     const StoreComplex sto{dst, n};
     if (i == 0) launch_fft_pass(radices[i], LoadRealPair{dry, p.scales, p.N, 0, rows, 0}, sto, p.tw, n, Ns, pairs, st);
     else launch_fft_pass(radices[i], LoadComplex{src, n}, sto, p.tw, n, Ns, pairs, st);
-    CHECK_LAUNCH(h, "fft_pass_kernel<forward>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<forward>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == wa) ? wb : wa;
@@ -1478,7 +1539,7 @@ static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbP
   {
     dim3 grid((n / 2 + 1 + 255) / 256, pairs);
     timeline_spectrum_kernel<<<grid, 256, 0, st>>>(src, p.ir_spectra, dst, n, rows, p.n_seg);
-    CHECK_LAUNCH(h, "timeline_spectrum_kernel");
+    CHECK_LAUNCH_ON(h, "timeline_spectrum_kernel", st);
     src = dst;
     dst = (dst == wa) ? wb : wa;
   }
@@ -1492,7 +1553,7 @@ static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbP
     } else {
       launch_fft_pass(radices[i], ld, StoreComplex{dst, n}, p.tw, n, Ns, pairs, st);
     }
-    CHECK_LAUNCH(h, "fft_pass_kernel<inverse>");
+    CHECK_LAUNCH_ON(h, "fft_pass_kernel<inverse>", st);
     Ns *= radices[i];
     src = dst;
     dst = (dst == wa) ? wb : wa;
@@ -1509,7 +1570,7 @@ static int timeline_reverb_audio_phase(b200ddsp_handle* h, const TimelineReverbP
   ta.head_ctas = (tail + 255) / 256;
   ta.link = p.tail;
   timeline_tail_kernel<<<dim3(ta.tail_ctas + ta.body_ctas + ta.head_ctas, p.B), 256, 0, st>>>(ta);
-  CHECK_LAUNCH(h, "timeline_tail_kernel");
+  CHECK_LAUNCH_ON(h, "timeline_tail_kernel", st);
   return B200DDSP_OK;
 }
 
@@ -1644,6 +1705,8 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     cp.f0_in[v] = vc.f0_hz;
   }
   reset_stage_flags(h);
+  h->trace_n = 0;
+  trace_launch(h, "entry", st);
   AdditiveRun run;
   if (int rc = additive_begin(h, &run, amp, hd, shifts, f0, base, w.add, P, B, F, H, S, w.groups, nullptr,
                               nullptr, span))
@@ -1701,7 +1764,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     AdditiveControlsArgs ga = ca;
     ga.hd_out = hd + (size_t)v0 * B * F * H;
     launch_additive_hd(ga, gp, Pg, h->hd_stream);
-    CHECK_LAUNCH(h, "additive_hd_kernel");
+    CHECK_LAUNCH_ON(h, "additive_hd_kernel", h->hd_stream);
     CUDA_TRY(h, cudaEventRecord(h->ev_hd_done[g], h->hd_stream));
   }
   // the impulse responses are known now, the dry signal only at the very end: their spectra are
@@ -1726,7 +1789,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   {
     StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
     launch_additive_prep(ca, cp, P, st);
-    CHECK_LAUNCH(h, "additive_prep_kernel");
+    CHECK_LAUNCH_ON(h, "additive_prep_kernel", st);
   }
   // the noise joins once the small latency-bound kernels of the phase pass are behind us (the
   // event is recorded after the work lists are built): it then shares the SMs with the long

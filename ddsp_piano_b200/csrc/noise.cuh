@@ -19,7 +19,7 @@
 //                      is register accumulation.  Lanes are FRAMES (shared-memory pitches = 4 mod
 //                      32 make the frame-strided 128-bit accesses conflict free); a thread owns 8
 //                      consecutive outputs of its frame and slides a 15-tap register window over
-//                      the taps: 4 LDS.128 per 64 FMAs.
+//                      the taps; two voices at a time in packed float32x2 (8 LDS.128 per 64 FFMA2).
 //  mix_kernel          dry = sum of the noise slices + the additive partial signals.
 #pragma once
 #include "common.cuh"
@@ -132,22 +132,27 @@ __host__ __device__ inline int pitch_4mod32(int n) {   // smallest p >= n with p
   return n + ((4 - n) % 32 + 32) % 32;
 }
 
+// Two voices are filtered at once: their taps and noise samples are staged INTERLEAVED in shared
+// memory -- (c_v0[k], c_v1[k]), (x_v0[j], x_v1[j]) -- so that every multiply-accumulate of the FIR is a
+// packed FFMA2 (sm_100) on naturally aligned register pairs: half the issue slots of the scalar form,
+// which was issue-bound (85 % issue-active at 59 % of the FMA pipe, profiles/r01_prof11_noise_summary.txt).
+// The two halves of an accumulator pair are added at the end (they belong to the same output sample).
 struct NoiseSmemLayout {
   int n_in;       // input frames held: kNoiseFrames + halo_before + halo_after
-  int pitch_x;    // >= U,  = 4 (mod 32)
-  int pitch_c;    // >= Lir + 2*kTapPad + 4,  = 4 (mod 32)
-  int tap_shift;  // 0..3: makes the register-window loads 16-byte aligned
+  int pitch_x;    // float2 per row, >= U;                 2 * pitch_x = 4 (mod 32) words
+  int pitch_c;    // float2 per row, >= Lir + 2*kTapPad + 2; 2 * pitch_c = 4 (mod 32) words
+  int tap_shift;  // 0..1: makes the register-window loads 16-byte aligned
   int off_x, off_c, total_floats;
   __host__ __device__ NoiseSmemLayout(int M, int U, int hb, int ha) {
     const int lir = 2 * (M - 1);
     const int start = (lir - 1) / 2 - 1;
     n_in = kNoiseFrames + hb + ha;
-    pitch_x = pitch_4mod32(U);
-    pitch_c = pitch_4mod32(lir + 2 * kTapPad + 4);
-    tap_shift = ((7 - start) % 4 + 4) % 4;
+    pitch_x = pitch_4mod32(2 * U) / 2;
+    pitch_c = pitch_4mod32(2 * (lir + 2 * kTapPad + 2)) / 2;
+    tap_shift = (kTapPad + start - 7) & 1;
     off_x = 0;
-    off_c = n_in * pitch_x;
-    total_floats = off_c + n_in * pitch_c;
+    off_c = 2 * n_in * pitch_x;
+    total_floats = off_c + 2 * n_in * pitch_c;
   }
 };
 
@@ -172,18 +177,42 @@ __device__ __forceinline__ float uniform_pm1(unsigned int bits) {
   return __fmaf_rn(u, 2.0f, -1.0f);
 }
 
-__device__ __forceinline__ void load4(float* dst, const float* src) {
+__device__ __forceinline__ void load2x2(float2* dst, const float2* src) {   // 16 bytes = two pairs
   const float4 v = *reinterpret_cast<const float4*>(src);
-  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  dst[0] = make_float2(v.x, v.y);
+  dst[1] = make_float2(v.z, v.w);
+}
+
+// 8 inputs x[0..7] (both voices) into 8 outputs: acc[q] += x[u] * w[7 - u + q], w = lo[0..7] | hi[0..7].
+__device__ __forceinline__ void fir_step8(float2 (&acc)[8], const float2 (&lo)[8], const float2 (&hi)[8],
+                                          const float2* xrow) {
+#pragma unroll
+  for (int h4 = 0; h4 < 2; ++h4) {                       // inputs in two halves: 8 registers instead of 16
+    float2 x[4];
+    load2x2(x, xrow + 4 * h4);
+    load2x2(x + 2, xrow + 4 * h4 + 2);
+#pragma unroll
+    for (int u4 = 0; u4 < 4; ++u4) {
+      const int u = 4 * h4 + u4;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = 7 - u + q;
+        acc[q] = __ffma2_rn(x[u4], i < 8 ? lo[i] : hi[i - 8], acc[q]);
+      }
+    }
+  }
 }
 
 // NB = 8-sample blocks per thread: blocks warp, warp + W, ... of the thread's frame.
+// NB = 1 (U <= 96): at most 12 warps and 85 registers, so that two CTAs share an SM and one stages
+// its next voice pair while the other filters.
 template <int NB>
-__global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
+__global__ void __launch_bounds__(NB == 1 ? 384 : 512, NB == 1 ? 2 : 1)
+noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
   extern __shared__ __align__(16) float smem[];
   const NoiseSmemLayout L(a.M, a.U, a.halo_before, a.halo_after);
-  float* xs = smem + L.off_x;     // [n_in][pitch_x]  noise samples by input frame
-  float* cs = smem + L.off_c;     // [n_in][pitch_c]  zero-padded taps by input frame
+  float2* xs = reinterpret_cast<float2*>(smem + L.off_x);     // [n_in][pitch_x]  noise of (voice 0, voice 1)
+  float2* cs = reinterpret_cast<float2*>(smem + L.off_c);     // [n_in][pitch_c]  zero-padded taps of both
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
   const int b = blockIdx.y;
@@ -198,55 +227,67 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   const int v_lo = a.v_begin + (int)(((long long)n_v * blockIdx.z) / gridDim.z);
   const int v_hi = a.v_begin + (int)(((long long)n_v * (blockIdx.z + 1)) / gridDim.z);
 
-  float acc[NB][8];
+  float2 acc[NB][8];
 #pragma unroll
   for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
+    for (int q = 0; q < 8; ++q) acc[i][q] = make_float2(0.f, 0.f);
   // taps outside [1, Lir-1] stay zero for the whole kernel
-  for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += n_threads) cs[i] = 0.f;
+  for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += n_threads) cs[i] = make_float2(0.f, 0.f);
 
-  for (int v = v_lo; v < v_hi; ++v) {
-    __syncthreads();   // previous voice's FIR is done with xs/cs (and the zero fill is visible)
-    // ---- stage this voice's taps and noise for the held input frames ----------------------
-    const float* taps = a.taps + ((size_t)v * a.B + b) * a.F * a.tap_pitch;
-    for (int i = threadIdx.x; i < L.n_in * (M - 1); i += n_threads) {
-      const int fi = i / (M - 1), d = i - fi * (M - 1);
+  for (int v = v_lo; v < v_hi; v += 2) {
+    __syncthreads();   // previous pair's FIR is done with xs/cs (and the zero fill is visible)
+    // ---- stage the pair's taps and noise for the held input frames: a warp per frame, both voices
+    //      in one 8-byte (taps) / 32-byte (noise) store -- no bank conflicts, no integer division
+    const bool have1 = v + 1 < v_hi;                   // odd voice count: the second half is silence
+    const float* taps0 = a.taps + ((size_t)v * a.B + b) * a.F * a.tap_pitch;
+    const float* taps1 = a.taps + ((size_t)(have1 ? v + 1 : v) * a.B + b) * a.F * a.tap_pitch;
+    const float* nz0 = vp.noise[v];
+    const float* nz1 = have1 ? vp.noise[v + 1] : nullptr;
+    if (nz0 != nullptr) nz0 += (size_t)b * a.F * U;
+    if (nz1 != nullptr) nz1 += (size_t)b * a.F * U;
+    const uint2 key = make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32));
+    for (int fi = warp; fi < L.n_in; fi += n_warps) {
       const int k = k_first + fi;
-      const float c = (k >= 0 && k < a.F) ? __ldg(taps + (size_t)k * a.tap_pitch + d) : 0.f;
-      float* row = cs + fi * L.pitch_c + tap0;
-      row[M - 1 + d] = c;
-      if (d > 0) row[M - 1 - d] = c;                   // linear phase: symmetric about tap M-1
-    }
-    const float* nz = vp.noise[v];
-    if (nz != nullptr) {
-      nz += (size_t)b * a.F * U;
-      for (int i = threadIdx.x; i < L.n_in * U; i += n_threads) {
-        const int fi = i / U, j = i - fi * U;
-        const int k = k_first + fi;
-        xs[fi * L.pitch_x + j] = (k >= 0 && k < a.F) ? __ldg(nz + (size_t)k * U + j) : 0.f;
-      }
-    } else {
-      // counter = (sample index / 4, clip, voice + stream, stream >> 32), key = seed
-      const uint2 key = make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32));
-      for (int i = threadIdx.x; i < L.n_in * U / 4; i += n_threads) {
-        const int fi = (i * 4) / U, j = i * 4 - fi * U;
-        const int k = k_first + fi;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k >= 0 && k < a.F) {
-          const unsigned int blk = (unsigned int)((a.sample0 + (size_t)k * U + j) >> 2);
-          const uint4 bits = philox4x32_10(
-              make_uint4(blk, (unsigned int)b, (unsigned int)v + (unsigned int)a.stream_id,
-                         (unsigned int)(a.stream_id >> 32)), key);
-          r = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z),
-                          uniform_pm1(bits.w));
+      const bool in = k >= 0 && k < a.F;
+      float2* crow = cs + fi * L.pitch_c + tap0;
+      for (int d = lane; d < M - 1; d += 32) {
+        float2 c = make_float2(0.f, 0.f);
+        if (in) {
+          c.x = __ldg(taps0 + (size_t)k * a.tap_pitch + d);
+          if (have1) c.y = __ldg(taps1 + (size_t)k * a.tap_pitch + d);
         }
-        *reinterpret_cast<float4*>(xs + fi * L.pitch_x + j) = r;
+        crow[M - 1 + d] = c;
+        if (d > 0) crow[M - 1 - d] = c;                // linear phase: symmetric about tap M-1
+      }
+      float2* xrow = xs + fi * L.pitch_x;
+      for (int j = 4 * lane; j < U; j += 128) {        // 4 samples of both voices per thread
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (in) {
+          // Philox counter = (global sample index / 4, clip, voice + stream, stream >> 32), key = seed
+          const unsigned int blk = (unsigned int)((a.sample0 + (size_t)k * U + j) >> 2);
+          if (nz0 != nullptr) {
+            r0 = __ldg(reinterpret_cast<const float4*>(nz0 + (size_t)k * U + j));
+          } else {
+            const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)v + (unsigned int)a.stream_id,
+                                                        (unsigned int)(a.stream_id >> 32)), key);
+            r0 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
+          }
+          if (nz1 != nullptr) {
+            r1 = __ldg(reinterpret_cast<const float4*>(nz1 + (size_t)k * U + j));
+          } else if (have1) {
+            const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)(v + 1) + (unsigned int)a.stream_id,
+                                                        (unsigned int)(a.stream_id >> 32)), key);
+            r1 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
+          }
+        }
+        *reinterpret_cast<float4*>(xrow + j) = make_float4(r0.x, r1.x, r0.y, r1.y);
+        *reinterpret_cast<float4*>(xrow + j + 2) = make_float4(r0.z, r1.z, r0.w, r1.w);
       }
     }
     __syncthreads();
 
-    // ---- FIR.  lane = output frame, warp walks its 8-sample blocks -------------------------
+    // ---- FIR.  lane = output frame, warp walks its 8-sample blocks -------------------------------
     const int fo = lane;                               // output frame within the tile
 #pragma unroll
     for (int ib = 0; ib < NB; ++ib) {
@@ -261,31 +302,34 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
         const int d_hi = e_hi / U;                       // e_hi >= 0
         for (int d = d_lo; d <= d_hi; ++d) {
           const int fi = fo + a.halo_before + d;         // held input frame index
-          const float* xrow = xs + fi * L.pitch_x;
-          const float* crow = cs + fi * L.pitch_c + tap0;
+          const float2* xrow = xs + fi * L.pitch_x;
+          const float2* crow = cs + fi * L.pitch_c + tap0;
           // 8-aligned input range (U % 8 == 0); taps outside [1, Lir-1] read the zero padding
           const int j_lo = max(0, e_lo - d * U) & ~7;
           const int j_hi = min(U - 1, e_hi - d * U) | 7;
           // tap of output q for input j+u: m0 - u + q with m0 = i0 + start - (d*U + j);
-          // m0 = start (mod 8), so crow + m0 - 7 is 16-byte aligned by the choice of tap_shift
+          // tap0 + m0 - 7 is even by the choice of tap_shift: 16-byte aligned pairs
           int m0 = i0 + start - (d * U + j_lo);
-          float w[16];                                   // taps m0-7 .. m0+8 (the last is unused)
+          // register window of 16 taps m0-7 .. m0+8 in two banks of 8: after 8 inputs the low bank
+          // becomes the high one and the other bank is reloaded -- the loop is unrolled by two so that
+          // the banks swap NAMES instead of contents (the moves of a shifting window ran on the FMA pipe)
+          float2 wa[8], wb[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) load4(w + i, crow + m0 - 7 + i);
-          for (int j = j_lo; j <= j_hi; j += 8) {
-            float x[8];
-            load4(x, xrow + j);
-            load4(x + 4, xrow + j + 4);
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[ib][q] = __fmaf_rn(x[u], w[7 - u + q], acc[ib][q]);
+          for (int i = 0; i < 8; i += 2) {
+            load2x2(wa + i, crow + m0 - 7 + i);
+            load2x2(wb + i, crow + m0 + 1 + i);
+          }
+          for (int j = j_lo; j <= j_hi; j += 16) {
+            fir_step8(acc[ib], wa, wb, xrow + j);
+            if (j + 8 > j_hi) break;
             m0 -= 8;
-            if (j + 8 <= j_hi) {
 #pragma unroll
-              for (int i = 0; i < 7; ++i) w[8 + i] = w[i];
-              load4(w, crow + m0 - 7);
-              load4(w + 4, crow + m0 - 3);
+            for (int i = 0; i < 8; i += 2) load2x2(wb + i, crow + m0 - 7 + i);
+            fir_step8(acc[ib], wb, wa, xrow + j + 8);
+            m0 -= 8;
+            if (j + 16 <= j_hi) {
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) load2x2(wa + i, crow + m0 - 7 + i);
             }
           }
         }
@@ -295,21 +339,24 @@ __global__ void __launch_bounds__(512) noise_fir_kernel(const NoiseArgs a, const
   __syncthreads();
 
   // ---- through shared memory (for coalescing) to the slice's noise signal -------------------
-  float* os = xs;   // [kNoiseFrames][pitch_x], reuses the noise tile
+  float* os = smem;   // [kNoiseFrames][U + 4], reuses the noise tile
+  const int pitch_o = U + 4;
 #pragma unroll
   for (int ib = 0; ib < NB; ++ib) {
     const int blk = warp + ib * n_warps;
     if (blk < n_blocks) {
-      float* o = os + lane * L.pitch_x + blk * 8;
-      *reinterpret_cast<float4*>(o) = make_float4(acc[ib][0], acc[ib][1], acc[ib][2], acc[ib][3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[ib][4], acc[ib][5], acc[ib][6], acc[ib][7]);
+      float* o = os + lane * pitch_o + blk * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[ib][0].x + acc[ib][0].y, acc[ib][1].x + acc[ib][1].y,
+                                                  acc[ib][2].x + acc[ib][2].y, acc[ib][3].x + acc[ib][3].y);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[ib][4].x + acc[ib][4].y, acc[ib][5].x + acc[ib][5].y,
+                                                      acc[ib][6].x + acc[ib][6].y, acc[ib][7].x + acc[ib][7].y);
     }
   }
   __syncthreads();
   const int t_tile = f_tile * U;
   const int len = min(kNoiseFrames * U, a.N - t_tile);
   float* out = a.out + ((size_t)(a.slice0 + blockIdx.z) * a.B + b) * a.N + t_tile;
-  for (int i = threadIdx.x; i < len; i += n_threads) out[i] = os[(i / U) * L.pitch_x + (i % U)];
+  for (int i = threadIdx.x; i < len; i += n_threads) out[i] = os[(i / U) * pitch_o + (i % U)];
 }
 
 // ---- mix ---------------------------------------------------------------------------------------
