@@ -86,10 +86,29 @@ def _shape(msg):
     return dims
 
 
+def latest_checkpoint(path):
+    """A checkpoint DIRECTORY (the reference's ``--ckpt`` default, ``model_weights/v2/``) resolves to the
+    prefix its ``checkpoint`` state file names (what ``tf.train.latest_checkpoint`` returns); a prefix
+    is returned unchanged."""
+    import os
+    import re
+    if not os.path.isdir(path):
+        return path
+    state = os.path.join(path, 'checkpoint')
+    if not os.path.exists(state):
+        raise FileNotFoundError(f'{path} is a directory without a "checkpoint" state file')
+    m = re.search(r'^model_checkpoint_path:\s*"([^"]+)"', open(state).read(), flags=re.M)
+    if not m:
+        raise ValueError(f'{state} names no model_checkpoint_path')
+    name = m.group(1)
+    return name if os.path.isabs(name) else os.path.join(path, name)
+
+
 class Checkpoint:
     """``Checkpoint(prefix)`` with ``prefix`` like ``.../model_weights/dafx22/ckpt-0``."""
 
     def __init__(self, prefix):
+        prefix = latest_checkpoint(prefix)
         self.prefix = prefix
         with open(prefix + '.index', 'rb') as f:
             buf = f.read()

@@ -187,9 +187,9 @@ def read_midi(path):
                 if key in open_notes:
                     close = [(s, v) for s, v in open_notes[key] if s != tick]
                     keep = [(s, v) for s, v in open_notes[key] if s == tick]
-                    dest = instrument(program[channel], channel, track, True)[0]
-                    for s, v in close:
-                        dest.append([seconds(s), seconds(tick), d1, v])
+                    for s, v in close:      # pretty_midi looks the instrument up per closed note only
+                        instrument(program[channel], channel, track, True)[0].append(
+                            [seconds(s), seconds(tick), d1, v])
                     if close and keep:
                         open_notes[key] = keep
                     else:

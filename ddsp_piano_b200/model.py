@@ -304,9 +304,15 @@ class PianoModel:
 
 
 def dafx22_model(checkpoint_prefix, device='cuda', sample_rate=16000, frame_rate=250, n_synths=16,
-                 inference=True, norm_axes='time_channels', seed=0):
+                 inference=True, norm_axes='time_channels', seed=0, reverb_decay_mask=False):
     """The model ``configs/dafx22.gin`` builds, restored from the shipped weights
-    (``model_weights/dafx22/ckpt-0``; 16 kHz, 96 partials, 64 noise bands, 1.5 s reverb)."""
+    (``model_weights/dafx22/ckpt-0``; 16 kHz, 96 partials, 64 noise bands, 1.5 s reverb).
+
+    ``inference`` is the gin macro ``%inference`` that ``synthesize_midi_file.py:53`` sets: in
+    ``dafx22.gin`` it reaches ``inharm_synth.MultiInharmonic`` only (angular cumsum).  The gin never
+    binds ``MultiInstrumentReverb.inference`` (constructor default False, sub_modules.py:300-337), so
+    the reference's dafx22 audio uses the learnt impulse response UNMASKED; ``reverb_decay_mask=True``
+    opts into the exponential decay mask of sub_modules.py:339-349."""
     device = torch.device(device)
     if isinstance(checkpoint_prefix, (Checkpoint, NpzWeights)):
         ck = checkpoint_prefix
@@ -346,7 +352,7 @@ def dafx22_model(checkpoint_prefix, device='cuda', sample_rate=16000, frame_rate
                                              'slopes_modifier', 'offsets_modifier'))),
         detuner=Detuner(dense('detuner/layer')),
         reverb_model=MultiInstrumentReverb(t('reverb_model/reverb_dict/layer_with_weights-0/embeddings'),
-                                           sample_rate=sample_rate, inference=inference),
+                                           sample_rate=sample_rate, inference=reverb_decay_mask),
         processor_group=ProcessorGroup(dag=dag), device=device)
 
 

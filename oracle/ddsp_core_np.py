@@ -74,8 +74,11 @@ def hann_window(window_length, dtype=np.float32):
     dt = np.dtype(dtype).type
     if window_length == 1:
         return np.ones([1], dtype=dt)
+    # tf.signal window_ops._raised_cosine_window: n = window_length + periodic * even - 1, so a periodic
+    # window of EVEN length divides by window_length and one of ODD length by window_length - 1 (the
+    # periodic flag has no effect there: hann(257)[k] = 0.5 - 0.5 cos(2 pi k / 256))
     even = 1 - window_length % 2
-    n = dt(window_length + 1 - even)
+    n = dt(window_length + even - 1)
     count = np.arange(window_length).astype(dt)
     cos_arg = dt(2 * np.pi) * count / n
     return (dt(0.5) - dt(0.5) * np.cos(cos_arg)).astype(dt)

@@ -336,3 +336,16 @@ def test_bench_config1_key_never_raises():
         assert {'dafx22', 'maestro_v2', 'what'} <= set(out) and out['dafx22']['rtf'] > 50
     else:
         assert set(out) == {'error'}
+
+
+def test_checkpoint_directory_resolves_to_its_latest_prefix(tmp_path):
+    """The reference's --ckpt default is a DIRECTORY (model_weights/v2/): the reader resolves it through
+    the `checkpoint` state file like tf.train.latest_checkpoint; a prefix passes through unchanged."""
+    from ddsp_piano_b200.checkpoint import latest_checkpoint
+    (tmp_path / 'checkpoint').write_text('model_checkpoint_path: "ckpt-225000"\nall_model_checkpoint_paths: "ckpt-225000"\n')
+    assert latest_checkpoint(str(tmp_path)) == str(tmp_path / 'ckpt-225000')
+    assert latest_checkpoint(str(tmp_path / 'ckpt-7')) == str(tmp_path / 'ckpt-7')
+    empty = tmp_path / 'empty'
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        latest_checkpoint(str(empty))

@@ -585,22 +585,37 @@ def _forward_full(dp, dev, w, x, noises, voices=None, reverb=True):
     return out['controls']['add']['signal'], out['signal']
 
 
-def test_full_size_parity_on_one_clip(dp, dev, full_size):
-    """The whole batch runs on the GPU at full size; clip 5 is checked against the oracle (clips
-    are independent, so the oracle only needs that clip's controls: ~15 s of CPU)."""
+def test_full_size_parity_on_four_clips(dp, dev, full_size):
+    """The whole batch runs on the GPU at full size; clips 0, 5, 10 and 15 are checked against the oracle
+    (clips are independent: the oracle needs those clips' controls only; its 64 (voice, clip) units run
+    on the host cores in parallel)."""
+    from _oracle_pool import polyphonic_forward_clips
     w, x, noises = full_size
     dry, wet = _forward_full(dp, dev, w, x, noises)
     assert dry.shape == (16, 72000) and wet.shape == (16, 72000)
     assert bool(torch.isfinite(wet).all())
-    b = 5
-    feats_np = {f'{k}_{v}': x[k][v][b:b + 1] for k in ('amplitudes', 'harmonic_distribution',
-                                                        'inharm_coef', 'f0_hz', 'magnitudes')
-                for v in range(w['P'])}
-    feats_np['reverb_ir'] = x['reverb_ir'][b:b + 1]
-    want = ref.polyphonic_forward(feats_np, n_synths=w['P'], sample_rate=w['sr'],
-                                  noise_by_voice=[n[b:b + 1] for n in noises])
-    assert rel_err(dry[b:b + 1], want['dry']) < TIGHT
-    assert rel_err(wet[b:b + 1], want['signal']) < TIGHT
+    want = polyphonic_forward_clips(x, noises, [0, 5, 10, 15], w['sr'])
+    for b, (want_dry, want_wet) in want.items():
+        assert rel_err(dry[b], want_dry) < TIGHT, b
+        assert rel_err(wet[b], want_wet) < TIGHT, b
+
+
+def test_stress_full_size_parity_on_one_clip(dp, dev):
+    """BASELINE configs[4] at FULL size on the GPU (48 kHz, 32 voices, 128 partials -> every bucket of
+    live half-groups up to 8, 144 chunks per clip, 96 noise bands -> 190-tap FIR, 144 000-tap reverb ->
+    2^19-point FFT); clip 7 against the oracle."""
+    import bench
+    from _oracle_pool import polyphonic_forward_clips
+    w = bench.WORKLOADS['stress']
+    x = bench.synthetic_inputs(w, seed=3)
+    rng = np.random.default_rng(48)
+    U = w['sr'] // 250
+    noises = [rng.uniform(-1, 1, [w['B'], w['F'] * U]).astype(np.float32) for _ in range(w['P'])]
+    dry, wet = _forward_full(dp, dev, w, x, noises)
+    assert dry.shape == (16, 144000) and bool(torch.isfinite(wet).all())
+    (want_dry, want_wet), = polyphonic_forward_clips(x, noises, [7], w['sr']).values()
+    assert rel_err(dry[7], want_dry) < TIGHT
+    assert rel_err(wet[7], want_wet) < TIGHT
 
 
 def test_full_size_properties(dp, dev, full_size):

@@ -172,6 +172,23 @@ def test_dafx22_midi_to_audio(weights):
     assert abs(peak_hz - 440.0) < 3.0, peak_hz
 
 
+@pytest.mark.gpu
+def test_dafx22_reverb_ir_is_the_unmasked_checkpoint_row(weights):
+    """configs/dafx22.gin binds %inference to MultiInharmonic only (dafx22.gin:108-110); its
+    MultiInstrumentReverb keeps the constructor default inference=False, so the reference convolves with
+    the learnt impulse response as stored -- no exponential decay mask (sub_modules.py:339-365)."""
+    import torch
+    import ddsp_piano_b200 as dp
+    row = weights.tensor('model/reverb_model/reverb_dict/layer_with_weights-0/embeddings/.ATTRIBUTES/VARIABLE_VALUE')
+    pm = torch.tensor([[1], [0]], dtype=torch.int64, device='cuda:0')      # the fixture keeps two of the ten rows
+    model = dp.dafx22_model(weights, device='cuda:0', inference=True)
+    ir = model.reverb_model(pm)
+    np.testing.assert_array_equal(ir.cpu().numpy(), row[[1, 0]])
+    masked = dp.dafx22_model(weights, device='cuda:0', inference=True, reverb_decay_mask=True).reverb_model(pm)
+    np.testing.assert_array_equal(masked[:, :16000].cpu().numpy(), row[[1, 0], :16000])
+    assert float((masked[:, 16001:] - ir[:, 16001:]).abs().max()) > 0
+
+
 # ---- maestro-v2.gin (the script default) --------------------------------------------------------
 
 V2_WEIGHTS = os.path.join(HERE, 'golden', 'v2_weights.npz')

@@ -107,6 +107,18 @@ def test_kat2_window_upsampling_is_partition_of_unity():
     assert np.max(np.abs(y - want)) < 1e-14
 
 
+def test_hann_window_of_odd_length_is_symmetric():
+    """tf.signal.hann_window(periodic=True) divides by window_length + even - 1: an odd-length window is
+    the symmetric one (latent in the configured shapes -- noise IRs of 126 / 190 taps and the 2U resampling
+    window are even -- but a cropped IR, window_size < 2 (M - 1) with window_size = 257, would use it)."""
+    k = np.arange(257)
+    np.testing.assert_allclose(core.hann_window(257, np.float64), 0.5 - 0.5 * np.cos(2 * np.pi * k / 256), atol=1e-15)
+    w = core.hann_window(257, np.float32)
+    assert abs(float(w[128]) - 1.0) < 1e-6 and abs(float(w[0])) < 1e-7 and abs(float(w[256])) < 1e-6
+    k = np.arange(64)
+    np.testing.assert_allclose(core.hann_window(64, np.float64), 0.5 - 0.5 * np.cos(2 * np.pi * k / 64), atol=1e-15)
+
+
 def test_kat3_partials_above_nyquist_are_silent():
     sr = 16000
     B, F, H = 1, 4, 8
