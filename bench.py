@@ -385,6 +385,9 @@ class GpuBench:
         self.dp = dp
         self.numa_node = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
         self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # > 126 MB L2
+        # the write leaves the L2 full of DIRTY lines whose write-back would be charged to the first
+        # kernels of the timed step; reading a second buffer afterwards leaves it cold and clean
+        self.flush_read = torch.zeros_like(self.flush) if os.environ.get('B200DDSP_FLUSH_READ', '1') != '0' else None
 
     def barrier(self):
         if self.world > 1:
@@ -400,6 +403,8 @@ class GpuBench:
         self.barrier()
         for i in range(steps):
             self.flush.zero_()
+            if self.flush_read is not None:
+                self.flush_read.sum()
             evs[i][0].record()
             fn()
             evs[i][1].record()
@@ -660,7 +665,8 @@ def run_gpu(args, workload):
                        'samples_per_segment': w['F'] * (w['sr'] // 250), 'reverb_taps': w['L'],
                        'sample_rate': w['sr'], 'noise': 'in-kernel Philox',
                        'phase': 'bit-faithful float32 angular_cumsum',
-                       'l2': 'flushed (256 MB write) between timed steps',
+                       'l2': 'flushed between timed steps: 256 MB written, then 256 MB of another buffer read (cold '
+                             'and clean: no write-back of the flush itself inside the timed step)',
                        'sharding': ('contiguous spans of one timeline over ranks; phase state '
                                     f'({w["P"] * w["S"] * w["H"] * 4} B) and reverb tail ({(w["L"] - 1) * 4} B) handed '
                                     'to the successor inside the kernels over NVLink peer memory (stream-ordered, '

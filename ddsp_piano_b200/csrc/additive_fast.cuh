@@ -237,6 +237,15 @@ __device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, in
 // less than pi per sample, so with the turns of up to three samples ago the argument x - n 2 pi
 // (still exact: one FMA) lies in [-pi, 4 pi), where the hardware cosine is as accurate as on
 // [-pi, pi] to within 1.5e-6 rad.  Saves 1.5 of 13 FMA-pipe cycles per oscillator-sample.
+// The unfused product (bottom - top) * lerp as ONE packed instruction: fma(g, lerp, +0) rounds g * lerp
+// exactly once like the multiply (the two differ only in the sign of a zero product, which the following
+// F + m erases because partial frequencies are positive), but -- unlike mul.rn.f32x2, or fma with -0
+// which ptxas first rewrites to a multiply -- ptxas may not contract it into the add that follows:
+// +0 is not the additive identity of IEEE arithmetic (-0 + +0 = +0).  One issue slot instead of two.
+#ifndef B200DDSP_LERP_FMA
+#define B200DDSP_LERP_FMA 1
+#endif
+constexpr bool kLerpProductAsFma = B200DDSP_LERP_FMA != 0;
 constexpr int kWrapEvery = 4;   // measured: 1 -> 2 -> 4 = 1.157 -> 1.111 -> 1.088 ms for the stage, error 4e-7 -> 9e-7
 
 // UNROLL consecutive samples (inside one control frame) of every chain of the lane.
@@ -277,7 +286,9 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
         om = make_float2(st.g[c0], st.g[c1]);
       } else {
         // top + (bottom - top) * lerp, product and sum rounded separately (scalar products: see above)
-        const float2 m = make_float2(__fmul_rn(st.g[c0], fr[j]), __fmul_rn(st.g[c1], fr[j]));
+        float2 m;
+        if (kLerpProductAsFma) m = __ffma2_rn(make_float2(st.g[c0], st.g[c1]), splat2(fr[j]), make_float2(0.f, 0.f));
+        else m = make_float2(__fmul_rn(st.g[c0], fr[j]), __fmul_rn(st.g[c1], fr[j]));
         f = __fadd2_rn(make_float2(st.F[c0], st.F[c1]), m);
         const float2 x = __fmul2_rn(f, two_pi2);                               // :69
         om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));                // :70, see div_sr
@@ -312,7 +323,9 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
       if (STEADY) {
         om = splat2(st.g[L]);
       } else {
-        const float2 m = make_float2(__fmul_rn(st.g[L], fr[j]), __fmul_rn(st.g[L], fr[j + 1]));
+        float2 m;
+        if (kLerpProductAsFma) m = __ffma2_rn(splat2(st.g[L]), make_float2(fr[j], fr[j + 1]), make_float2(0.f, 0.f));
+        else m = make_float2(__fmul_rn(st.g[L], fr[j]), __fmul_rn(st.g[L], fr[j + 1]));
         f = __fadd2_rn(splat2(st.F[L]), m);
         const float2 x = __fmul2_rn(f, two_pi2);
         om = __ffma2_rn(x, inv_sr2, __fmul2_rn(x, inv_sr_lo2));

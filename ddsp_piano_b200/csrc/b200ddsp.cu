@@ -412,7 +412,6 @@ static int fft_size_for(int N, int L) {
 
 constexpr int kNoiseSlices = 4;   // voice slices of the FIR stage (parallelism + overlap with copies)
 
-static int tap_pitch_for(int M) { return (M - 1 + 3) & ~3; }
 
 // ddsp.core.angular_cumsum wraps the phase every 1000 samples (inference=True); with
 // inference=False the reference uses one plain cumsum over the clip (inharm_synth.py:73-77):
@@ -487,7 +486,7 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
 // Voices are processed in `n_groups` consecutive groups (1 for device inputs; several for host
 // inputs, so that the H2D copies of one group overlap the kernels of the previous one).
 struct WorkspaceLayout {
-  size_t amp, hd, shifts, f0, taps, noise_part, tw, buf_a, buf_b, total;
+  size_t amp, hd, shifts, f0, noise_part, tw, buf_a, buf_b, total;
   AdditiveLayout add;
   PlanGroups groups;
   int n_chunks, nfft;
@@ -510,7 +509,6 @@ static WorkspaceLayout carve(const b200ddsp_handle* h, int P, int B, int F, int 
   w.hd = take(R * F * H * 4);
   w.shifts = take(R * F * H * 4);
   w.f0 = take(R * F * S * 4);
-  w.taps = take(R * F * (size_t)tap_pitch_for(M) * 4);
   w.noise_part = take((size_t)kNoiseSlices * B * N * 4);
   w.add = carve_additive(h, o, P, B, F, H, S);
   o = w.add.end;
@@ -1056,12 +1054,12 @@ extern "C" int b200ddsp_noise_controls(b200ddsp_handle* h, const float* magnitud
   return B200DDSP_OK;
 }
 
-// taps GEMM (+ fused get_controls scaling when scale_fn != 2) and FIR of voices [v0, v1), written
-// as `n_slices` noise signals starting at slice index `slice0` of noise_part [*, B, N].
-static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int scale_fn,
-                            const NoiseVoicePtrs& vp, int v0, int v1, int slice0, int n_slices,
-                            float* noise_part, int B, int F, int M, unsigned long long seed,
-                            unsigned long long stream_id, float* taps, cudaStream_t st,
+// The noise synth of voices [v0, v1) (get_controls scaling when scale_fn != 2, taps, noise, FIR: one
+// kernel, noise.cuh), written as `n_slices` noise signals starting at slice index `slice0` of
+// noise_part [*, B, N].  vp: magnitudes (and optional injected noise) of ALL voices.
+static int run_noise_voices(b200ddsp_handle* h, int scale_fn, const NoiseVoicePtrs& vp, int v0, int v1,
+                            int slice0, int n_slices, float* noise_part, int B, int F, int M,
+                            unsigned long long seed, unsigned long long stream_id, cudaStream_t st,
                             const SpanInfo* span = nullptr, long long in_first_frame = 0) {
   const int U = h->U;
   const int F_out = span ? span->F_out : F;
@@ -1073,25 +1071,8 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   if (U > 8 * 4 * 16)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "noise synth supports U <= 512 (U=%d)", U);
   StageTimer tm(h, B200DDSP_STAGE_NOISE, st);
-  const int tap_pitch = tap_pitch_for(M);
-  {
-    NoiseTapsArgs t{};
-    NoiseTapsPtrs sub{};
-    for (int v = v0; v < v1; ++v) sub.mags[v - v0] = mags.mags[v];
-    t.cmat_t = h->d_cmat_t;
-    t.taps = taps + (size_t)v0 * B * F * tap_pitch;
-    t.mags_out = nullptr;
-    t.frames_per_voice = B * F;
-    t.M = M;
-    t.tap_pitch = tap_pitch;
-    t.scale_fn = scale_fn;
-    t.bias = h->cfg.noise_initial_bias;
-    dim3 grid((B * F + kTapsTileF - 1) / kTapsTileF, (M - 1 + kTapsTileD - 1) / kTapsTileD, v1 - v0);
-    noise_taps_kernel<<<grid, 256, 0, st>>>(t, sub);
-    CHECK_LAUNCH_ON(h, "noise_taps_kernel", st);
-  }
   NoiseArgs a{};
-  a.taps = taps;
+  a.cmat_t = h->d_cmat_t;
   a.out = noise_part;
   a.v_begin = v0;
   a.v_end = v1;
@@ -1099,11 +1080,16 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   a.B = B; a.F = F; a.M = M; a.U = U; a.N = F_out * U;
   a.koff = span ? span->koff : 0;
   a.sample0 = (unsigned long long)in_first_frame * (unsigned long long)U;
-  a.tap_pitch = tap_pitch;
   a.halo_before = (M + U - 1) / U;
   a.halo_after = (U + M - 5) / U;
+  a.scale_fn = scale_fn;
+  a.bias = h->cfg.noise_initial_bias;
   a.seed = seed;
   a.stream_id = stream_id;
+  // bulk asynchronous copies need 16-byte aligned rows: M % 4 == 0 and aligned tensors (the ABI asks for
+  // 16-byte alignment; a misaligned view falls back to ordinary loads instead of faulting)
+  a.bulk = (M % 4 == 0) && env_int("B200DDSP_NOISE_BULK", 1);
+  for (int v = v0; v < v1; ++v) a.bulk = a.bulk && aligned16(vp.mags[v]);
   const NoiseSmemLayout L(M, U, a.halo_before, a.halo_after);
   const size_t smem = (size_t)L.total_floats * sizeof(float);
   if (smem > 227 * 1024)
@@ -1122,14 +1108,14 @@ static int run_noise_voices(b200ddsp_handle* h, const NoiseTapsPtrs& mags, int s
   };
   cudaError_t e = cudaSuccess;
   switch (nb) {
-    case 1: e = launch(noise_fir_kernel<1>); break;
-    case 2: e = launch(noise_fir_kernel<2>); break;
-    case 3: e = launch(noise_fir_kernel<3>); break;
-    default: e = launch(noise_fir_kernel<4>); break;
+    case 1: e = launch(noise_synth_kernel<1>); break;
+    case 2: e = launch(noise_synth_kernel<2>); break;
+    case 3: e = launch(noise_synth_kernel<3>); break;
+    default: e = launch(noise_synth_kernel<4>); break;
   }
   if (e != cudaSuccess)
-    return fail(h, B200DDSP_CUDA_ERROR, "noise_fir_kernel attribute: %s", cudaGetErrorString(e));
-  CHECK_LAUNCH_ON(h, "noise_fir_kernel", st);
+    return fail(h, B200DDSP_CUDA_ERROR, "noise_synth_kernel attribute: %s", cudaGetErrorString(e));
+  CHECK_LAUNCH_ON(h, "noise_synth_kernel", st);
   return B200DDSP_OK;
 }
 
@@ -1159,7 +1145,8 @@ static int run_mix(b200ddsp_handle* h, const float* noise_part, int n_noise, con
 
 extern "C" size_t b200ddsp_noise_workspace_bytes(const b200ddsp_handle* h, int B, int F, int M) {
   if (!h || B < 1 || F < 1 || M < 2) return 0;
-  return align_up((size_t)B * F * tap_pitch_for(M) * 4) + align_up((size_t)B * F * h->U * 4);
+  (void)M;
+  return align_up((size_t)B * F * h->U * 4);
 }
 
 extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes, const float* noise,
@@ -1173,15 +1160,13 @@ extern "C" int b200ddsp_noise_signal(b200ddsp_handle* h, const float* magnitudes
     return fail(h, B200DDSP_WORKSPACE_TOO_SMALL, "noise_signal needs %zu workspace bytes, got %zu", need,
                 workspace_bytes);
   if (!aligned16(workspace)) return fail(h, B200DDSP_BAD_ALIGN, "workspace must be 16-byte aligned");
-  NoiseTapsPtrs mp{};
-  mp.mags[0] = magnitudes;
   NoiseVoicePtrs vp{};
+  vp.mags[0] = magnitudes;
   vp.noise[0] = noise;
   reset_stage_flags(h);
-  float* taps = (float*)workspace;
-  float* part = (float*)((char*)workspace + align_up((size_t)B * F * tap_pitch_for(M) * 4));
-  if (int rc = run_noise_voices(h, mp, B200DDSP_SCALE_NONE, vp, 0, 1, 0, 1, part, B, F, M, seed,
-                                stream_id, taps, (cudaStream_t)stream))
+  float* part = (float*)workspace;
+  if (int rc = run_noise_voices(h, B200DDSP_SCALE_NONE, vp, 0, 1, 0, 1, part, B, F, M, seed, stream_id,
+                                (cudaStream_t)stream))
     return rc;
   return run_mix(h, part, 1, nullptr, out, B, F * h->U, accumulate, (cudaStream_t)stream);
 }
@@ -1688,16 +1673,14 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   float* hd = (float*)(base + w.hd);
   float* shifts = (float*)(base + w.shifts);
   float* f0 = (float*)(base + w.f0);
-  float* taps = (float*)(base + w.taps);
 
   NoiseVoicePtrs vp{};
-  NoiseTapsPtrs mp{};
   AdditiveControlsPtrs cp{};
   for (int v = 0; v < P; ++v) {
     const b200ddsp_voice& vc = voices[v];
     if (!vc.amplitudes || !vc.harmonic_distribution || !vc.inharm_coef || !vc.f0_hz || !vc.magnitudes)
       return fail(h, B200DDSP_BAD_ARGUMENT, "voice %d has a null control tensor", v);
-    mp.mags[v] = vc.magnitudes;
+    vp.mags[v] = vc.magnitudes;
     vp.noise[v] = vc.noise;
     cp.amp_in[v] = vc.amplitudes;
     cp.hd_in[v] = vc.harmonic_distribution;
@@ -1729,8 +1712,8 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
       const int v0 = P * hf / halves, v1 = P * (hf + 1) / halves;
       const int s0 = n_slices * hf / halves, s1 = n_slices * (hf + 1) / halves;
       if (sync) CUDA_TRY(h, cudaStreamWaitEvent(ns, sync->mags_ready[hf], 0));
-      if (int rc = run_noise_voices(h, mp, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B,
-                                    F, M, seed, 0, taps, ns, span, in_first_frame))
+      if (int rc = run_noise_voices(h, h->cfg.noise_scale_fn, vp, v0, v1, s0, s1 - s0, noise_part, B,
+                                    F, M, seed, 0, ns, span, in_first_frame))
         return rc;
     }
     return B200DDSP_OK;

@@ -7,124 +7,54 @@
 // overlap-adds at hop U; the result is cropped at start = (Lir-1)/2 - 1.  In the time domain
 //   z[n] = sum_{m=1}^{Lir-1} x[n-m] * c_{frame(n-m)}[m],     noise_out[t] = z[t + start].
 // With Lir = 126 (190 at M = 96) taps the direct form costs fewer flops than three FFTs per
-// frame, needs no transposes, and is exact, so that is what runs here, in two kernels:
+// frame, needs no transposes, and is exact, so that is what runs here, in ONE kernel:
 //
-//  noise_taps_kernel   c_k = Cmat x scale_fn(m_k + bias): the inverse real DFT and the window
-//                      folded into one [M x M-1] matrix (built once in create()); the filter is
-//                      symmetric about tap M-1 so only taps M-1 .. 2M-3 are computed and
-//                      stored.  A register-tiled FP32 GEMM over all frames of all voices; the
-//                      magnitudes' get_controls scaling is fused into the operand load.
-//  noise_fir_kernel    CTA = (tile of 32 output frames, clip, voice slice); it loops over the
-//                      voices of its slice, so most of the MultiAdd node (inharm_synth.py:296-309)
-//                      is register accumulation.  Lanes are FRAMES (shared-memory pitches = 4 mod
-//                      32 make the frame-strided 128-bit accesses conflict free); a thread owns 8
-//                      consecutive outputs of its frame and slides a 15-tap register window over
-//                      the taps; two voices at a time in packed float32x2 (8 LDS.128 per 64 FFMA2).
+//  noise_synth_kernel  CTA = (tile of 32 output frames, clip, voice slice); it loops over the voices
+//                      of its slice two at a time, so most of the MultiAdd node
+//                      (inharm_synth.py:296-309) is register accumulation.  Per voice pair:
+//    load     the raw magnitudes of the tile's frames (+ halo) are contiguous in the caller's
+//             [B, F, M] tensors: ONE bulk asynchronous copy per voice (cp.async.bulk, the 1-D form of
+//             TMA) lands them in shared memory and signals an mbarrier.  The copy for the NEXT pair
+//             is issued as soon as this pair's magnitudes have been consumed, so it flies under the
+//             taps / noise / FIR phases below;
+//    scale    FilteredNoise.get_controls, scale_fn(m + bias), both voices interleaved (m_v0, m_v1);
+//    taps     c_k = Cmat x m_k: the inverse real DFT and the window folded into one [M x M-1] matrix
+//             (built once in create()); the filter is symmetric about tap M-1, so only taps
+//             M-1 .. 2M-3 are computed and mirrored into shared memory;
+//    noise    Philox4x32-10 (or the injected tensor of the parity tests), interleaved like the taps;
+//    FIR      lanes are FRAMES (shared-memory pitches = 4 mod 32 words make the frame-strided 128-bit
+//             accesses conflict free); a thread owns 8 consecutive outputs of its frame and slides a
+//             16-tap register window over the taps.  Every multiply-accumulate is a packed FFMA2
+//             (sm_100) over the two voices: half the issue slots of the scalar form, which was
+//             issue-bound.
 //  mix_kernel          dry = sum of the noise slices + the additive partial signals.
 #pragma once
 #include "common.cuh"
 
 namespace b200ddsp {
 
-// ---- taps GEMM ------------------------------------------------------------------------------
-constexpr int kTapsTileF = 64;   // frames per CTA
-constexpr int kTapsTileD = 64;   // taps per CTA
-constexpr int kTapsTileK = 32;   // bands per shared-memory stage
-
-struct NoiseTapsPtrs {
-  const float* mags[B200DDSP_MAX_VOICES_INTERNAL];   // [B, F, M] raw or scaled magnitudes per voice
-};
-
-struct NoiseTapsArgs {
-  const float* cmat_t;   // [M][M-1]
-  float* taps;           // [P*B*F][tap_pitch]: taps M-1 .. 2M-3 of every frame
-  float* mags_out;       // [P*B*F][M] scaled magnitudes (get_controls output) or nullptr
-  int frames_per_voice;  // B * F
-  int M, tap_pitch;
-  int scale_fn;          // b200ddsp_scale_fn to apply on load; 2 = magnitudes are already scaled
-  float bias;
-};
-
-__global__ void __launch_bounds__(256) noise_taps_kernel(const NoiseTapsArgs a,
-                                                         const NoiseTapsPtrs vp) {
-  __shared__ float As[kTapsTileF][kTapsTileK + 1];
-  __shared__ __align__(16) float Cs[kTapsTileK][kTapsTileD];
-  const int v = blockIdx.z;
-  const int f0 = blockIdx.x * kTapsTileF;   // frame within the voice
-  const int d0 = blockIdx.y * kTapsTileD;
-  const int nd = a.M - 1;
-  const int tid = threadIdx.x;
-  const int tf = tid >> 4, td = tid & 15;   // 16 x 16 threads, 4 x 4 outputs each
-  const float* mags = vp.mags[v];
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < a.M; k0 += kTapsTileK) {
-    // A tile: 64 frames x 32 bands, scaled on the way in
-    for (int i = tid; i < kTapsTileF * kTapsTileK; i += 256) {
-      const int fr = i / kTapsTileK, kk = i - fr * kTapsTileK;
-      const int f = f0 + fr, k = k0 + kk;
-      float x = 0.f;
-      if (f < a.frames_per_voice && k < a.M) {
-        x = __ldg(mags + (size_t)f * a.M + k);
-        if (a.scale_fn != 2) x = apply_scale_fn(__fadd_rn(x, a.bias), a.scale_fn);
-        if (a.mags_out != nullptr && blockIdx.y == 0)
-          a.mags_out[((size_t)v * a.frames_per_voice + f) * a.M + k] = x;
-      }
-      As[fr][kk] = x;
-    }
-    for (int i = tid; i < kTapsTileK * kTapsTileD; i += 256) {
-      const int kk = i / kTapsTileD, dd = i - kk * kTapsTileD;
-      const int k = k0 + kk, d = d0 + dd;
-      Cs[kk][dd] = (k < a.M && d < nd) ? __ldg(a.cmat_t + (size_t)k * nd + d) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < kTapsTileK; ++kk) {
-      const float4 c4 = *reinterpret_cast<const float4*>(&Cs[kk][td * 4]);
-      const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float av = As[tf * 4 + i][kk];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av, cv[j], acc[i][j]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int f = f0 + tf * 4 + i;
-    if (f >= a.frames_per_voice) continue;
-    float* dst = a.taps + ((size_t)v * a.frames_per_voice + f) * a.tap_pitch + d0 + td * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (d0 + td * 4 + j < a.tap_pitch) dst[j] = acc[i][j];
-  }
-}
-
-// ---- FIR ---------------------------------------------------------------------------------------
 constexpr int kNoiseFrames = 32;   // output frames per CTA (= lanes)
 constexpr int kTapPad = 16;        // zero taps either side of c_k (8-aligned input blocks + the
                                    // 16-tap register window overhang by up to 14 taps)
 
 struct NoiseVoicePtrs {
-  const float* noise[B200DDSP_MAX_VOICES_INTERNAL];   // [B, N] or nullptr (Philox)
+  const float* mags[B200DDSP_MAX_VOICES_INTERNAL];    // [B, F, M] raw (or already scaled) magnitudes
+  const float* noise[B200DDSP_MAX_VOICES_INTERNAL];   // [B, F * U] or nullptr (Philox)
 };
 
 struct NoiseArgs {
-  const float* taps;     // [P*B*F][tap_pitch] from noise_taps_kernel
+  const float* cmat_t;   // [M][M-1] taps matrix
   float* out;            // [n_slices, B, N] noise of each voice slice
   int v_begin, v_end;    // voices handled by this launch, split evenly over gridDim.z slices
   int slice0;            // index of the launch's first slice in `out`
-  int B, F, M, U, N, tap_pitch;  // F = input frames (rows of `taps`, frames of an injected noise tensor),
-                                 // N = output samples
+  int B, F, M, U, N;     // F = input frames (rows of the magnitudes, frames of an injected noise tensor),
+                         // N = output samples
   int koff;                      // input frame of output frame 0 (spans of a timeline: halo in front)
   unsigned long long sample0;    // global sample index of input frame 0 (Philox counter base)
   int halo_before, halo_after;   // input halo in FRAMES either side of the tile
+  int scale_fn;          // b200ddsp_scale_fn applied to the magnitudes; 2 = already scaled
+  float bias;
+  int bulk;              // magnitudes rows are 16-byte aligned (M % 4 == 0): bulk asynchronous copies
   unsigned long long seed, stream_id;
 };
 
@@ -132,17 +62,19 @@ __host__ __device__ inline int pitch_4mod32(int n) {   // smallest p >= n with p
   return n + ((4 - n) % 32 + 32) % 32;
 }
 
-// Two voices are filtered at once: their taps and noise samples are staged INTERLEAVED in shared
-// memory -- (c_v0[k], c_v1[k]), (x_v0[j], x_v1[j]) -- so that every multiply-accumulate of the FIR is a
-// packed FFMA2 (sm_100) on naturally aligned register pairs: half the issue slots of the scalar form,
-// which was issue-bound (85 % issue-active at 59 % of the FMA pipe, profiles/r01_prof11_noise_summary.txt).
-// The two halves of an accumulator pair are added at the end (they belong to the same output sample).
+// Shared memory of one CTA (floats).  Taps and noise of the two voices are INTERLEAVED --
+// (c_v0[k], c_v1[k]), (x_v0[j], x_v1[j]) -- so that the FIR's operands are naturally aligned pairs.
 struct NoiseSmemLayout {
   int n_in;       // input frames held: kNoiseFrames + halo_before + halo_after
-  int pitch_x;    // float2 per row, >= U;                 2 * pitch_x = 4 (mod 32) words
+  int pitch_x;    // float2 per row, >= U;                   2 * pitch_x = 4 (mod 32) words
   int pitch_c;    // float2 per row, >= Lir + 2*kTapPad + 2; 2 * pitch_c = 4 (mod 32) words
   int tap_shift;  // 0..1: makes the register-window loads 16-byte aligned
-  int off_x, off_c, total_floats;
+  int off_raw;    // [2][n_in][M] raw magnitudes of the voice pair (bulk-copy destination)
+  int off_m;      // [n_in][M] float2 scaled magnitudes
+  int off_x;      // [n_in][pitch_x] float2 noise
+  int off_c;      // [n_in][pitch_c] float2 taps
+  int off_bar;    // mbarrier (8 bytes)
+  int total_floats;
   __host__ __device__ NoiseSmemLayout(int M, int U, int hb, int ha) {
     const int lir = 2 * (M - 1);
     const int start = (lir - 1) / 2 - 1;
@@ -150,11 +82,46 @@ struct NoiseSmemLayout {
     pitch_x = pitch_4mod32(2 * U) / 2;
     pitch_c = pitch_4mod32(2 * (lir + 2 * kTapPad + 2)) / 2;
     tap_shift = (kTapPad + start - 7) & 1;
-    off_x = 0;
-    off_c = 2 * n_in * pitch_x;
-    total_floats = off_c + 2 * n_in * pitch_c;
+    off_raw = 0;
+    off_m = (2 * n_in * M + 31) & ~31;
+    off_x = off_m + ((2 * n_in * M + 31) & ~31);
+    off_c = off_x + ((2 * n_in * pitch_x + 31) & ~31);
+    off_bar = off_c + 2 * n_in * pitch_c;
+    total_floats = off_bar + 4;
   }
 };
+
+// ---- asynchronous bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) -----------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) {
+  return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned int bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // Philox4x32-10 (Salmon et al. 2011), the generator family TF's random ops use.  The
 // reference draws unseeded noise (filtered_noise_synth.py:39-40), so only the distribution
@@ -204,15 +171,17 @@ __device__ __forceinline__ void fir_step8(float2 (&acc)[8], const float2 (&lo)[8
 }
 
 // NB = 8-sample blocks per thread: blocks warp, warp + W, ... of the thread's frame.
-// NB = 1 (U <= 96): at most 12 warps and 85 registers, so that two CTAs share an SM and one stages
-// its next voice pair while the other filters.
+// NB = 1 (U <= 96): at most 12 warps and 85 registers, so that two CTAs share an SM.
 template <int NB>
 __global__ void __launch_bounds__(NB == 1 ? 384 : 512, NB == 1 ? 2 : 1)
-noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
+noise_synth_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
   extern __shared__ __align__(16) float smem[];
   const NoiseSmemLayout L(a.M, a.U, a.halo_before, a.halo_after);
-  float2* xs = reinterpret_cast<float2*>(smem + L.off_x);     // [n_in][pitch_x]  noise of (voice 0, voice 1)
+  float* raw = smem + L.off_raw;                              // [2][n_in][M]
+  float2* ms = reinterpret_cast<float2*>(smem + L.off_m);     // [n_in][M]  scaled magnitudes of both voices
+  float2* xs = reinterpret_cast<float2*>(smem + L.off_x);     // [n_in][pitch_x]  noise of both voices
   float2* cs = reinterpret_cast<float2*>(smem + L.off_c);     // [n_in][pitch_c]  zero-padded taps of both
+  void* bar = smem + L.off_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_threads = blockDim.x, n_warps = blockDim.x >> 5;
   const int b = blockIdx.y;
@@ -222,10 +191,22 @@ noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
   const int start = (lir - 1) / 2 - 1;                 // crop_and_compensate_delay
   const int n_blocks = U / 8;
   const int tap0 = kTapPad + L.tap_shift;              // position of tap 0 inside a taps row
+  // frames of the held range that exist: [k_lo, k_hi)
+  const int k_lo = max(k_first, 0), k_hi = min(k_first + L.n_in, a.F);
   // this CTA's voices
   const int n_v = a.v_end - a.v_begin;
   const int v_lo = a.v_begin + (int)(((long long)n_v * blockIdx.z) / gridDim.z);
   const int v_hi = a.v_begin + (int)(((long long)n_v * (blockIdx.z + 1)) / gridDim.z);
+
+  // one elected thread starts the copies of a voice pair and tells the mbarrier how many bytes to expect
+  auto start_loads = [&](int v) {
+    const unsigned int bytes = (unsigned int)(k_hi - k_lo) * M * 4u;
+    const int nv = (v + 1 < v_hi) ? 2 : 1;
+    mbar_expect_tx(bar, bytes * nv);
+    for (int e = 0; e < nv; ++e)
+      bulk_load(raw + (e * L.n_in + (k_lo - k_first)) * M, vp.mags[v + e] + ((size_t)b * a.F + k_lo) * M, bytes, bar);
+  };
+  if (a.bulk && threadIdx.x == 0) mbar_init(bar, 1);
 
   float2 acc[NB][8];
 #pragma unroll
@@ -234,58 +215,129 @@ noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
     for (int q = 0; q < 8; ++q) acc[i][q] = make_float2(0.f, 0.f);
   // taps outside [1, Lir-1] stay zero for the whole kernel
   for (int i = threadIdx.x; i < L.n_in * L.pitch_c; i += n_threads) cs[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  if (a.bulk && threadIdx.x == 0 && v_lo < v_hi && k_hi > k_lo) start_loads(v_lo);
 
+  unsigned int parity = 0;
   for (int v = v_lo; v < v_hi; v += 2) {
-    __syncthreads();   // previous pair's FIR is done with xs/cs (and the zero fill is visible)
-    // ---- stage the pair's taps and noise for the held input frames: a warp per frame, both voices
-    //      in one 8-byte (taps) / 32-byte (noise) store -- no bank conflicts, no integer division
     const bool have1 = v + 1 < v_hi;                   // odd voice count: the second half is silence
-    const float* taps0 = a.taps + ((size_t)v * a.B + b) * a.F * a.tap_pitch;
-    const float* taps1 = a.taps + ((size_t)(have1 ? v + 1 : v) * a.B + b) * a.F * a.tap_pitch;
-    const float* nz0 = vp.noise[v];
-    const float* nz1 = have1 ? vp.noise[v + 1] : nullptr;
-    if (nz0 != nullptr) nz0 += (size_t)b * a.F * U;
-    if (nz1 != nullptr) nz1 += (size_t)b * a.F * U;
-    const uint2 key = make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32));
-    for (int fi = warp; fi < L.n_in; fi += n_warps) {
-      const int k = k_first + fi;
-      const bool in = k >= 0 && k < a.F;
-      float2* crow = cs + fi * L.pitch_c + tap0;
-      for (int d = lane; d < M - 1; d += 32) {
-        float2 c = make_float2(0.f, 0.f);
-        if (in) {
-          c.x = __ldg(taps0 + (size_t)k * a.tap_pitch + d);
-          if (have1) c.y = __ldg(taps1 + (size_t)k * a.tap_pitch + d);
-        }
-        crow[M - 1 + d] = c;
-        if (d > 0) crow[M - 1 - d] = c;                // linear phase: symmetric about tap M-1
-      }
-      float2* xrow = xs + fi * L.pitch_x;
-      for (int j = 4 * lane; j < U; j += 128) {        // 4 samples of both voices per thread
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        if (in) {
-          // Philox counter = (global sample index / 4, clip, voice + stream, stream >> 32), key = seed
-          const unsigned int blk = (unsigned int)((a.sample0 + (size_t)k * U + j) >> 2);
-          if (nz0 != nullptr) {
-            r0 = __ldg(reinterpret_cast<const float4*>(nz0 + (size_t)k * U + j));
-          } else {
-            const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)v + (unsigned int)a.stream_id,
-                                                        (unsigned int)(a.stream_id >> 32)), key);
-            r0 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
+    // ---- noise of the pair for the held input frames (needs nothing from the magnitudes: it runs while
+    //      their copy is in flight): a warp per frame, 4 samples of both voices per thread
+    {
+      const float* nz0 = vp.noise[v];
+      const float* nz1 = have1 ? vp.noise[v + 1] : nullptr;
+      if (nz0 != nullptr) nz0 += (size_t)b * a.F * U;
+      if (nz1 != nullptr) nz1 += (size_t)b * a.F * U;
+      const uint2 key = make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32));
+      for (int fi = warp; fi < L.n_in; fi += n_warps) {
+        const int k = k_first + fi;
+        const bool in = k >= k_lo && k < k_hi;
+        float2* xrow = xs + fi * L.pitch_x;
+        for (int j = 4 * lane; j < U; j += 128) {
+          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+          if (in) {
+            // Philox counter = (global sample index / 4, clip, voice + stream, stream >> 32), key = seed
+            const unsigned int blk = (unsigned int)((a.sample0 + (size_t)k * U + j) >> 2);
+            if (nz0 != nullptr) {
+              r0 = __ldg(reinterpret_cast<const float4*>(nz0 + (size_t)k * U + j));
+            } else {
+              const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)v + (unsigned int)a.stream_id,
+                                                          (unsigned int)(a.stream_id >> 32)), key);
+              r0 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
+            }
+            if (nz1 != nullptr) {
+              r1 = __ldg(reinterpret_cast<const float4*>(nz1 + (size_t)k * U + j));
+            } else if (have1) {
+              const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)(v + 1) + (unsigned int)a.stream_id,
+                                                          (unsigned int)(a.stream_id >> 32)), key);
+              r1 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
+            }
           }
-          if (nz1 != nullptr) {
-            r1 = __ldg(reinterpret_cast<const float4*>(nz1 + (size_t)k * U + j));
-          } else if (have1) {
-            const uint4 bits = philox4x32_10(make_uint4(blk, (unsigned int)b, (unsigned int)(v + 1) + (unsigned int)a.stream_id,
-                                                        (unsigned int)(a.stream_id >> 32)), key);
-            r1 = make_float4(uniform_pm1(bits.x), uniform_pm1(bits.y), uniform_pm1(bits.z), uniform_pm1(bits.w));
-          }
+          *reinterpret_cast<float4*>(xrow + j) = make_float4(r0.x, r1.x, r0.y, r1.y);
+          *reinterpret_cast<float4*>(xrow + j + 2) = make_float4(r0.z, r1.z, r0.w, r1.w);
         }
-        *reinterpret_cast<float4*>(xrow + j) = make_float4(r0.x, r1.x, r0.y, r1.y);
-        *reinterpret_cast<float4*>(xrow + j + 2) = make_float4(r0.z, r1.z, r0.w, r1.w);
       }
     }
-    __syncthreads();
+    // ---- magnitudes of the pair in shared memory ---------------------------------------------------
+    if (a.bulk) {
+      if (k_hi > k_lo) mbar_wait(bar, parity);
+      parity ^= 1u;
+    } else {
+      for (int e = 0; e < (have1 ? 2 : 1); ++e)
+        for (int i = threadIdx.x; i < (k_hi - k_lo) * M; i += n_threads)
+          raw[(e * L.n_in + (k_lo - k_first)) * M + i] = __ldg(vp.mags[v + e] + ((size_t)b * a.F + k_lo) * M + i);
+      __syncthreads();
+    }
+    // ---- scale (FilteredNoise.get_controls), interleave the two voices: a warp per frame ------------
+    for (int fi = warp; fi < L.n_in; fi += n_warps) {
+      const int k = k_first + fi;
+      const bool in = k >= k_lo && k < k_hi;
+      for (int j = lane; j < M; j += 32) {
+        float2 m = make_float2(0.f, 0.f);
+        if (in) {
+          m.x = raw[fi * M + j];
+          if (have1) m.y = raw[(L.n_in + fi) * M + j];
+          if (a.scale_fn != 2) {
+            m.x = apply_scale_fn(__fadd_rn(m.x, a.bias), a.scale_fn);
+            if (have1) m.y = apply_scale_fn(__fadd_rn(m.y, a.bias), a.scale_fn);
+          }
+        }
+        ms[fi * M + j] = m;
+      }
+    }
+    __syncthreads();   // scaled magnitudes complete; the raw buffer is free again
+    if (a.bulk && threadIdx.x == 0 && v + 2 < v_hi && k_hi > k_lo) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async writes
+      start_loads(v + 2);
+    }
+    // ---- taps: c[fi][d] = sum_k Cmat[k][d] * m[fi][k] for both voices.  Thread = (tap d, frame group g):
+    //      it owns tap d of frames g, g + G, .., 6 at a time; per pair of bands it reads 2 matrix entries
+    //      (coalesced over d, L1 resident) and one 16-byte broadcast per frame for 12 FFMA2.
+    {
+      const int nd = M - 1;
+      const int dcols = min((nd + 31) & ~31, n_threads);   // taps per pass, whole warps
+      const int G = n_threads / dcols;                 // frame groups
+      const int g = threadIdx.x / dcols;
+      for (int d = threadIdx.x % dcols; d < nd && g < G; d += dcols) {
+        const float* cd = a.cmat_t + d;
+        for (int f0 = g; f0 < L.n_in; f0 += 6 * G) {
+          int off[6];                                  // row offsets; frames past the end repeat the last one
+#pragma unroll
+          for (int i = 0; i < 6; ++i) off[i] = min(f0 + i * G, L.n_in - 1) * M;
+          float2 c6[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) c6[i] = make_float2(0.f, 0.f);
+          if ((M & 1) == 0) {
+#pragma unroll 4
+            for (int k = 0; k < M; k += 2) {
+              const float ca = __ldg(cd + (size_t)k * nd), cb = __ldg(cd + (size_t)(k + 1) * nd);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const float4 m4 = *reinterpret_cast<const float4*>(ms + off[i] + k);
+                c6[i] = __ffma2_rn(make_float2(ca, ca), make_float2(m4.x, m4.y), c6[i]);
+                c6[i] = __ffma2_rn(make_float2(cb, cb), make_float2(m4.z, m4.w), c6[i]);
+              }
+            }
+          } else {
+            for (int k = 0; k < M; ++k) {
+              const float ca = __ldg(cd + (size_t)k * nd);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) c6[i] = __ffma2_rn(make_float2(ca, ca), ms[off[i] + k], c6[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int fi = f0 + i * G;
+            if (fi < L.n_in) {
+              float2* row = cs + fi * L.pitch_c + tap0;
+              row[M - 1 + d] = c6[i];
+              if (d > 0) row[M - 1 - d] = c6[i];       // linear phase: symmetric about tap M-1
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // taps and noise tile complete
 
     // ---- FIR.  lane = output frame, warp walks its 8-sample blocks -------------------------------
     const int fo = lane;                               // output frame within the tile
@@ -335,11 +387,11 @@ noise_fir_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
         }
       }
     }
+    __syncthreads();   // the FIR is done with the noise tile and the taps
   }
-  __syncthreads();
 
   // ---- through shared memory (for coalescing) to the slice's noise signal -------------------
-  float* os = smem;   // [kNoiseFrames][U + 4], reuses the noise tile
+  float* os = reinterpret_cast<float*>(xs);   // [kNoiseFrames][U + 4], reuses the noise tile
   const int pitch_o = U + 4;
 #pragma unroll
   for (int ib = 0; ib < NB; ++ib) {
