@@ -421,10 +421,11 @@ class GpuBench:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def group(self, w):
+    def group(self, w, fast_phase=False):
         dp = self.dp
         sr, P, L = w['sr'], w['P'], w['L']
-        additive = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='additive')
+        additive = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='additive',
+                                      fast_phase=fast_phase)
         noise = dp.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, name='noise', seed=1234)
         reverb = dp.Reverb(trainable=False) if L else None
         group = dp.ProcessorGroup(dag=dp.polyphonic_dag(
@@ -445,7 +446,7 @@ class GpuBench:
         return f
 
 
-def measure_clips(gb, w, steps, warmup, held=False, e2e=True):
+def measure_clips(gb, w, steps, warmup, held=False, e2e=True, fast_phase=False):
     """Independent clips sharded over ranks (no collective on the data path)."""
     torch = gb.torch
     P, L, B, F = w['P'], w['L'], w['B'], w['F']
@@ -453,7 +454,7 @@ def measure_clips(gb, w, steps, warmup, held=False, e2e=True):
     x_np = synthetic_inputs(w, seed=gb.rank, held_notes=held)
     host = {k: torch.from_numpy(v).pin_memory() for k, v in x_np.items()}
     resident = {k: v.to(gb.dev) for k, v in host.items()}
-    group, eng = gb.group(w)
+    group, eng = gb.group(w, fast_phase)
     eng.set_profiling(True)
     # the per-voice views exist once (Parallelizer.unparallelize hands them out the same way);
     # every step passes a fresh shallow copy of the dict because ProcessorGroup extends it
@@ -632,6 +633,12 @@ def run_gpu(args, workload):
             extras['held_notes_variant'] = dict(brief(dict(mh, steps=steps)), what=(
                 'same workload, inharm_coef constant per (voice, clip) as in the reference model: partial '
                 'frequencies are constant between frames'))
+        if workload == 'full':
+            mf = measure_clips(gb, w, steps, 3, e2e=False, fast_phase=True)
+            extras['fast_phase_variant'] = dict(brief(dict(mf, steps=steps)), what=(
+                'same workload with b200ddsp_config.fast_phase = 1 (opt-in): closed-form double-precision unit start '
+                'phases instead of the bit-faithful phase pass; within 1e-3 of the exact signal model but NOT within '
+                '1e-4 of the reference (profiles/r02_fast_phase_error_table.txt) -- never the headline'))
         if workload == 'full' and gb.world == 1:
             for name in ('dry', 'stress', 'timeline'):
                 wx = WORKLOADS[name]
@@ -639,6 +646,7 @@ def run_gpu(args, workload):
                 extras[name] = dict(brief(dict(mx, steps=xsteps)), workload=wx['name'], steps=xsteps)
                 if name == 'timeline':
                     extras[name]['roofline_fp32'] = roofline_of(gb, wx, mx, fma_peak, clocks, name)['fp32']
+        extras['e2e_from_conditioning'] = from_conditioning_line(gb)
         if workload == 'timeline' and gb.world > 1:
             # continuity with round 1's scaling series: independent clips, no exchange at all
             mc = measure_clips(gb, WORKLOADS['full'], xsteps, 3)
@@ -677,7 +685,9 @@ def run_gpu(args, workload):
                     'd2h_bytes_per_step': m['d2h'], 'ms_per_step': m['e2e_ms'],
                     'h2d_GBps_if_copy_bound': m['h2d'] / (m['e2e_ms'] * 1e-3) / 1e9,
                     'note': 'bounded by the host-to-device copy of the control tensors over PCIe; the kernels run '
-                            'under the copies (DESIGN.md section 5)'},
+                            'under the copies (DESIGN.md section 5).  Host ceiling measured with no kernels running '
+                            '(scripts/h2d_ceiling.py, profiles/r02_h2d_ceiling_n*.json): 55.5 GB/s per rank alone, '
+                            '29.3 with 4 ranks copying, 23.4 with 8 (one host, 237 GB/s aggregate)'},
             'gpu_launches': m['launches'], 'clocks': clocks,
             'roofline': roofline_of(gb, w, m, fma_peak, clocks, workload),
         }
@@ -695,6 +705,49 @@ def run_gpu(args, workload):
     if gb.world > 1:
         gb.dist.barrier()
         gb.dist.destroy_process_group()
+
+
+def from_conditioning_line(gb, steps=10):
+    """`e2e_from_conditioning`: what the reference pipeline actually moves to the device is the MIDI
+    conditioning, not the control tensors (piano_model.py:146-164): batch 16 x 3 s of polyphonic
+    conditioning [16, 750, 16, 2] + pedals (1.7 MB, pinned host memory) -> control-rate graph (dafx22.gin with
+    the shipped weights, its native 16 kHz / H96 / M64 / 1.5 s IR) -> the synthesis kernels -> audio back on
+    the host, all inside CUDA events.  Random notes: 4 of the 16 channels sound at any time."""
+    try:
+        torch = gb.torch
+        B, F, P, sr = 16, 750, 16, 16000
+        rng = np.random.default_rng(5 + gb.rank)
+        cond = np.zeros([B, F, P, 2], np.float32)
+        for b in range(B):
+            for v in range(4):
+                t = 0
+                while t < F - 40:
+                    n = int(rng.integers(40, 200))
+                    cond[b, t:t + n - 10, v, 0] = rng.integers(36, 96)
+                    cond[b, t, v, 1] = rng.uniform(0.3, 1.0)
+                    t += n
+        host = {'conditioning': torch.from_numpy(cond).pin_memory(),
+                'pedal': torch.zeros([B, F, 4]).pin_memory(),
+                'piano_model': torch.zeros([B, 1], dtype=torch.int64).pin_memory()}
+        model = gb.dp.dafx22_model(os.path.join(ROOT, 'tests', 'golden', 'dafx22_weights.npz'), device=gb.dev,
+                                   sample_rate=sr, inference=True)
+        out_host = torch.empty([B, F * (sr // 250)], dtype=torch.float32).pin_memory()
+
+        def step():
+            feats = {k: v.to(gb.dev, non_blocking=True) for k, v in host.items()}
+            out = model(feats)
+            out_host.copy_(model.get_audio_from_outputs(out), non_blocking=True)
+
+        for _ in range(3):
+            step()
+        ms = gb.reduce_max(gb.timed(step, steps)) / steps
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        return {'value': gb.world * B * F / 250.0 / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out_host.numel() * 4, 'steps': steps,
+                'what': 'MIDI conditioning (pinned host) -> dafx22 control-rate graph (shipped weights, 16 kHz) -> '
+                        'synthesis kernels -> audio on the host; batch 16 x 3 s per GPU, 4 sounding voices of 16'}
+    except Exception as e:                               # noqa: BLE001 (informational key)
+        return {'error': f'{type(e).__name__}: {e}'}
 
 
 def config1_line():

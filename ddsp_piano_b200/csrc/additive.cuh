@@ -38,8 +38,10 @@ struct AdditiveArgs {
   const float* f0;      // [R, F, S]
   float* offsets;       // [R*S, n_chunks, H]: chunk end phases (pass 1), then chunk offsets (scan)
   float* mids;          // [R*S, n_chunks, n_sub - 1, H]: in-chunk phase accumulator at samples kSubLen, 2 kSubLen,
-                        // ... of every chunk (fast path, pass 1), so that pass 2 can start inside a chunk
+                        // ... of every chunk (fast path, pass 1), so that pass 2 can start inside a chunk;
+                        // fast_phase: [R*S, n_chunks, n_sub, H] phase (mod 2 pi) at the start of every unit
   int n_sub;            // synthesis units per chunk (fast path): ceil(chunk / kSubLen), or 1
+  int fast_phase;       // unit start phases come from the closed form (additive_closed_phase_kernel)
   const float* decays;      // [R, F, H] or nullptr: SurrogateAdditive (surrogate_synth.py:78-97), generic
   const float* decay_time;  // [R, F]                kernel only: amplitude *= |decay|^(decay_time U + r)
   float* out;           // [G, B, N]

@@ -390,8 +390,12 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     st.off[j] = 0.f;
     const int h = l + LW * j;
     if (!ENDS_ONLY && h < a.H) {
-      if (c > 0 || a.seeded) st.off[j] = a.offsets[osc_chunk * a.H + h];
-      if (q > 0) st.ph[j] = a.mids[(osc_chunk * (a.n_sub - 1) + (q - 1)) * a.H + h];
+      if (a.fast_phase) {
+        st.off[j] = a.mids[(osc_chunk * a.n_sub + q) * a.H + h];
+      } else {
+        if (c > 0 || a.seeded) st.off[j] = a.offsets[osc_chunk * a.H + h];
+        if (q > 0) st.ph[j] = a.mids[(osc_chunk * (a.n_sub - 1) + (q - 1)) * a.H + h];
+      }
     }
   }
   constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk, frame and sub-unit lengths are multiples of 8
@@ -470,6 +474,124 @@ __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const 
   B200DDSP_CHAIN_CASE(1) B200DDSP_CHAIN_CASE(2) B200DDSP_CHAIN_CASE(3) B200DDSP_CHAIN_CASE(4)
   B200DDSP_CHAIN_CASE(5) B200DDSP_CHAIN_CASE(6) B200DDSP_CHAIN_CASE(7) B200DDSP_CHAIN_CASE(8)
 #undef B200DDSP_CHAIN_CASE
+}
+
+// ---- fast_phase: closed-form unit start phases ---------------------------------------------------
+// b200ddsp_config.fast_phase = 1 trades the bit-faithful float32 phase for speed: instead of following the
+// reference's 1000 sequential float32 adds per chunk (pass 1) and its float32 sum of chunk ends (scan),
+// the phase at the start of every synthesis unit is evaluated in double precision from the frame-rate
+// controls.  The signal model stays the reference's -- partial frequencies move along ITS legacy
+// bilinear coordinates, lerp[t] of additive_lerp_kernel -- so within frame k
+//   sum_{r < n} (F_k + g_k lerp[kU + r]) = n F_k + g_k sum_{r < n} lerp[kU + r],   g_k = F_{k+1} - F_k,
+// with the lerp sums taken once per call (additive_lerp_sums_kernel: one per frame, one per unit start).
+// One thread per oscillator then walks the frames (a few double operations each: microseconds for the
+// whole batch against 0.4 ms for pass 1).  Inside a unit (<= 256 samples) pass 2 still accumulates in
+// float32 from that start.  What is removed is the rounding noise of the reference's float32 running sum
+// (up to ~1e-3 rad per chunk in the highest partials, more over a clip), so the output is NOT within
+// 1e-4 of the reference: opt-in, validated against the oracle's float64-accumulation variant
+// (oracle/ddsp_piano_np.py::additive_signal_exact_sum).
+__global__ void __launch_bounds__(128) additive_lerp_sums_kernel(const float* __restrict__ lerp,
+                                                                 double* __restrict__ frame_sum,   // [F_out]
+                                                                 double* __restrict__ unit_sum,    // [n_chunks * n_sub]
+                                                                 int N, int U, int chunk, int n_chunks, int n_sub) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_frames = N / U, n_units = n_chunks * n_sub;
+  if (i < n_frames) {
+    double acc = 0.0;
+    for (int r = 0; r < U; ++r) acc += (double)lerp[i * U + r];
+    frame_sum[i] = acc;
+  } else if (i < n_frames + n_units) {
+    const int u = i - n_frames, c = u / n_sub, q = u - c * n_sub;
+    const long long ts = (long long)c * chunk + (long long)q * kSubLen;
+    double acc = 0.0;
+    if (ts < N) {
+      const int k = (int)(ts / U), n = (int)(ts - (long long)k * U);
+      for (int r = 0; r < n; ++r) acc += (double)lerp[k * U + r];
+    }
+    unit_sum[u] = acc;
+  }
+}
+
+// CTA = (oscillator row rs, block of 32 partials); lane = partial, warp = one of 8 time segments of the
+// clip.  Phase A: every warp sums the turns of its segment's frames; a prefix over the 8 segment totals
+// gives each warp its start; phase B: the warps walk their segments again and write the unit start phases.
+// Eight times the parallelism of one thread per oscillator for twice the (coalesced, 8-deep batched) loads.
+constexpr int kClosedSegs = 8;
+constexpr int kClosedBatch = 8;
+
+__global__ void __launch_bounds__(kClosedSegs * 32) additive_closed_phase_kernel(
+    const AdditiveArgs a, const double* __restrict__ frame_sum, const double* __restrict__ unit_sum) {
+  __shared__ double seg_turns[kClosedSegs][32];
+  const int hb = (a.H + 31) / 32;
+  const int rs = blockIdx.x / hb, h = (blockIdx.x - rs * hb) * 32 + (threadIdx.x & 31);
+  const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = rs / a.S, s = rs - row * a.S;
+  const int n_frames = a.N / a.U;                       // frames synthesised
+  const int per = (n_frames + kClosedSegs - 1) / kClosedSegs;
+  const int k_lo = seg * per, k_hi = min(n_frames, k_lo + per);
+  const double inv_sr = 1.0 / (double)a.sr;
+  const float nf = (float)(h + 1);
+  const bool live = h < a.H;
+  const float* f0p = a.f0 + (size_t)row * a.F * a.S + s;
+  const float* shp = a.shifts + (size_t)row * a.F * a.H + (live ? h : 0);
+  auto freq = [&](int k) {                              // frame-rate partial frequency, float32 like the kernels
+    k = min(k + a.koff, a.F - 1);
+    return __fmul_rn(__fmul_rn(__ldg(f0p + (size_t)k * a.S), nf), __fadd_rn(1.0f, __ldg(shp + (size_t)k * a.H)));
+  };
+  float* dst = a.mids + (size_t)rs * a.n_chunks * a.n_sub * a.H + (live ? h : 0);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    double turns = 0.0;                                 // phase / 2 pi before the first sample of frame k
+    if (pass == 1) {
+      for (int j = 0; j < seg; ++j) turns += seg_turns[j][lane];
+      turns -= floor(turns);
+    }
+    // next unit start at or after the segment's first sample
+    long long ts = 0;
+    int c = 0, q = 0;
+    if (pass == 1) {
+      const long long t_lo = (long long)k_lo * a.U;
+      c = (int)(t_lo / a.chunk);
+      q = (int)((t_lo - (long long)c * a.chunk + kSubLen - 1) / kSubLen);
+      if (q >= a.n_sub || (long long)c * a.chunk + (long long)q * kSubLen >= min((long long)a.N, (long long)(c + 1) * a.chunk)) {
+        q = 0;
+        ++c;
+      }
+      ts = (long long)c * a.chunk + (long long)q * kSubLen;
+    }
+    for (int k0 = k_lo; k0 < k_hi; k0 += kClosedBatch) {
+      float Fb[kClosedBatch + 1];
+#pragma unroll
+      for (int i = 0; i <= kClosedBatch; ++i) Fb[i] = freq(min(k0 + i, n_frames + 1));
+#pragma unroll
+      for (int i = 0; i < kClosedBatch; ++i) {
+        const int k = k0 + i;
+        if (k < k_hi) {
+          const double g = (double)__fadd_rn(Fb[i + 1], -Fb[i]), F = (double)Fb[i];
+          if (pass == 1) {
+            const long long t_end = (long long)(k + 1) * a.U;
+            while (c < a.n_chunks && ts < t_end) {      // unit starts inside this frame
+              const double n = (double)(ts - (long long)k * a.U);
+              const double at = turns + (n * F + g * unit_sum[c * a.n_sub + q]) * inv_sr;
+              if (live) dst[((size_t)c * a.n_sub + q) * a.H] = (float)((at - floor(at)) * 6.283185307179586);
+              const long long chunk_end = min((long long)a.N, (long long)(c + 1) * a.chunk);
+              if (++q == a.n_sub || (long long)c * a.chunk + (long long)q * kSubLen >= chunk_end) {
+                q = 0;
+                ++c;
+              }
+              ts = (long long)c * a.chunk + (long long)q * kSubLen;
+            }
+          }
+          turns += ((double)a.U * F + g * frame_sum[k]) * inv_sr;
+          turns -= floor(turns);
+        }
+      }
+    }
+    if (pass == 0) {
+      seg_turns[seg][lane] = turns;
+      __syncthreads();
+    }
+  }
 }
 
 // ---- work lists ------------------------------------------------------------------------------

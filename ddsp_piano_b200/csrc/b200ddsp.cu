@@ -241,8 +241,12 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   if (cfg->sample_rate <= 0 || cfg->frame_rate <= 0 || cfg->sample_rate < cfg->frame_rate)
     return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "bad sample_rate/frame_rate %d/%d",
                 cfg->sample_rate, cfg->frame_rate);
-  if (cfg->fast_phase != 0)
-    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "fast_phase is not implemented");
+  if (cfg->fast_phase != 0 && cfg->fast_phase != 1)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "fast_phase must be 0 or 1");
+  if (cfg->fast_phase && !cfg->inference)
+    return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG,
+                "fast_phase replaces the chunked angular_cumsum of inference=1; with inference=0 the "
+                "reference's single plain cumsum has no chunk structure to start from");
   for (int fn : {cfg->additive_scale_fn, cfg->noise_scale_fn})
     if (fn < 0 || fn > 2) return fail(nullptr, B200DDSP_UNSUPPORTED_CONFIG, "bad scale_fn %d", fn);
   const int M = cfg->n_noise_bands;
@@ -448,6 +452,7 @@ struct AdditiveLayout {
   size_t synth_na;   // u8 [R, n_chunks]           live partial groups per chunk
   size_t ends_na;    // u8 [R, n_chunks]           groups whose end phase a later chunk needs
   size_t lerp;       // float [N]                  legacy-bilinear lerp weight per sample
+  size_t lerp_sums;  // double [F + n_chunks * n_sub]  fast_phase: lerp sums per frame / up to every unit start
   size_t plan;       // AdditivePlan
   size_t lists;      // int [kPlanSlots][kMaxGroups][R * n_chunks]
   size_t partials;   // float [n_partials, B, N]   partial signals for the mixer
@@ -471,11 +476,12 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
   auto take = [&](size_t bytes) { size_t p = o; o += align_up(bytes); return p; };
   a.offsets = take(R * S * n_chunks * H * 4);
   const size_t n_sub = (size_t)sub_units_for(h, (int)N);
-  a.mids = take(R * S * n_chunks * (n_sub > 1 ? n_sub - 1 : 1) * H * 4);
+  a.mids = take(R * S * n_chunks * n_sub * H * 4);   // n_sub - 1 per chunk, n_sub with fast_phase
   a.na_frame = take(R * F);
   a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
   a.lerp = take(N * 4);
+  a.lerp_sums = take(((size_t)F + n_chunks * n_sub) * 8);
   a.plan = take(sizeof(AdditivePlan));
   a.lists = take((size_t)kPlanSlots * kMaxGroups * R * n_chunks * 4);
   a.partials = take(max_partials(P, S) * B * N * 4);
@@ -675,6 +681,7 @@ struct AdditiveRun {
   unsigned char *na_frame, *synth_na, *ends_na;
   PlanGroups groups;
   float* partials;
+  double* frame_sum;
   const SpanInfo* span;
 };
 
@@ -694,6 +701,13 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "spans of a timeline are implemented on the fast additive path only (U %% 8 == 0, "
                 "H <= 128, uniform resize coordinates); got U=%d H=%d", U, H);
+  if (span && h->cfg.fast_phase)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "spans of a timeline carry the reference's float32 phase state: not available with fast_phase");
+  if (h->cfg.fast_phase && !r->fast)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
+                "fast_phase is implemented on the fast additive path only (U %% 8 == 0, H <= 128); got U=%d H=%d",
+                U, H);
   if (span && !h->cfg.inference)
     return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
                 "spans of a timeline need inference=1: the plain cumsum of training mode carries an "
@@ -718,6 +732,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   r->synth_na = (unsigned char*)(base + lay.synth_na);
   r->ends_na = (unsigned char*)(base + lay.ends_na);
   r->partials = (float*)(base + lay.partials);
+  r->frame_sum = (double*)(base + lay.lerp_sums);
   AdditiveArgs& a = r->a;
   a = AdditiveArgs{};
   a.amp = amp; a.hd = hd; a.shifts = shifts; a.f0 = f0;
@@ -730,6 +745,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.chunk = chunk_for(h, N);
   a.n_chunks = r->n_chunks;
   a.n_sub = r->fast ? sub_units_for(h, N) : 1;
+  a.fast_phase = h->cfg.fast_phase ? 1 : 0;
   a.voices_per_group = (P + r->G - 1) / r->G;
   a.koff = span ? span->koff : 0;
   a.seeded = (span && span->seeded) ? 1 : 0;
@@ -849,6 +865,18 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
     if (small_kernels_done) {
       CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
       small_kernels_done = nullptr;
+    }
+    if (a.fast_phase) {   // closed-form unit start phases instead of pass 1 + scan
+      StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
+      const int n_osc = R * r.S * r.H, n_frames = a.N / a.U, n_units = r.n_chunks * a.n_sub;
+      additive_lerp_sums_kernel<<<(n_frames + n_units + 127) / 128, 128, 0, st>>>(
+          r.fa.lerp, r.frame_sum, r.frame_sum + n_frames, a.N, a.U, a.chunk, r.n_chunks, a.n_sub);
+      CHECK_LAUNCH_ON(h, "additive_lerp_sums_kernel", st);
+      (void)n_osc;
+      additive_closed_phase_kernel<<<R * r.S * ((r.H + 31) / 32), kClosedSegs * 32, 0, st>>>(a, r.frame_sum,
+                                                                                            r.frame_sum + n_frames);
+      CHECK_LAUNCH_ON(h, "additive_closed_phase_kernel", st);
+      return B200DDSP_OK;
     }
     if (r.n_chunks > 1 || carry || a.n_sub > 1) {
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);

@@ -94,11 +94,16 @@ class Processor:
 
 
 class InHarmonic(Processor):
-    """modules/inharm_synth.py:130-244: bank of inharmonic cosine oscillators."""
+    """modules/inharm_synth.py:130-244: bank of inharmonic cosine oscillators.
+
+    ``fast_phase`` (not in the reference): start every 256-sample unit from a closed-form double-precision
+    phase instead of reproducing the reference's float32 ``angular_cumsum`` bit for bit -- about 20 % less
+    time per forward, output within ~3e-4 of the exact (float64) synthesis but NOT within 1e-4 of the
+    reference, whose own float32 phase drifts (``b200ddsp_config.fast_phase``)."""
 
     def __init__(self, frame_rate=250, sample_rate=16000, min_frequency=20,
                  scale_fn=exp_sigmoid, normalize_after_nyquist_cut=True,
-                 normalize_below_nyquist=True, inference=False, name='inharmonic'):
+                 normalize_below_nyquist=True, inference=False, name='inharmonic', fast_phase=False):
         self.frame_rate = frame_rate
         self.sample_rate = sample_rate
         self.min_frequency = min_frequency
@@ -106,6 +111,7 @@ class InHarmonic(Processor):
         self.scale_fn = scale_fn
         self.normalize_below_nyquist = normalize_below_nyquist
         self.inference = inference
+        self.fast_phase = fast_phase
         super().__init__(name=name)
 
     @property
@@ -118,7 +124,7 @@ class InHarmonic(Processor):
                     additive_scale_fn=scale_fn_id(self.scale_fn),
                     normalize_after_nyquist_cut=int(bool(self.normalize_after_nyquist_cut)),
                     normalize_below_nyquist=int(bool(self.normalize_below_nyquist)),
-                    inference=int(bool(self.inference)))
+                    inference=int(bool(self.inference)), fast_phase=int(bool(self.fast_phase)))
 
     def _engine(self, *tensors):
         return get_engine(_device_of(*tensors), **{**_DEFAULT_CFG, **self.engine_config()})

@@ -73,10 +73,15 @@ typedef struct {
   int reverb_add_dry;              /* effects.Reverb add_dry (default 1) */
   int n_noise_bands;               /* M: the FIR window / cosine tables are built for this M */
   int fast_phase;                  /* 0 (default): bit-faithful float32 phase accumulation in the
-                                      reference's summation order.  1: closed-form fixed-point
-                                      phase (more accurate than the reference, but differs from it
-                                      by up to ~1e-3 rad in high partials).  Not yet implemented:
-                                      must be 0. */
+                                      reference's summation order (two passes over the phase chain).
+                                      1: the phase at the start of every 256-sample synthesis unit is
+                                      evaluated in closed form in double precision from the frame-rate
+                                      controls (no phase pass, ~20 % less time per forward); closer to
+                                      the exact phase than the reference's float32 cumsum and
+                                      therefore up to ~1e-2 rad away from it in the highest partials:
+                                      NOT within 1e-4 of the reference, validated against the float64
+                                      oracle instead (tests/test_gpu_parity.py).
+                                      inference = 1, fast additive path, whole clips only. */
 } b200ddsp_config;
 
 typedef struct b200ddsp_handle b200ddsp_handle;

@@ -120,6 +120,50 @@ def additive_signal(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, *
     return audio
 
 
+def additive_signal_exact_sum(amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, *,
+                              sample_rate, frame_rate=250, rounded_omega=False):
+    """The reference's signal model in EXACT arithmetic -- ground truth for ``fast_phase`` (SURVEY 7 'hard
+    parts': a fast mode validated against a float64 oracle).  Envelopes come from the float32 controls along
+    the reference's own resampling (legacy bilinear coordinates float32(i) * float32(F / N), window
+    cross-fade); then the angular frequency (F_k + g_k lerp) 2 pi / sr, its running sum, the cosines and the
+    sum over partials are evaluated in float64.  What the reference adds on top of this model is float32
+    rounding: of every omega (systematic for a held partial: the same rounded value is added thousands of
+    times) and of the running sum itself (angular_cumsum); ``rounded_omega=True`` keeps the first kind
+    (the float32 omegas of modules/inharm_synth.py:69-70, summed exactly) to tell the two apart.
+    additive_signal on float64 INPUTS is a third thing: it also resamples along float64 coordinates."""
+    amplitudes = core.tf_float32(amplitudes).astype(np.float32)
+    harmonic_distribution = core.tf_float32(harmonic_distribution).astype(np.float32)
+    harmonic_shifts = core.tf_float32(harmonic_shifts).astype(np.float32)
+    f0_hz = core.tf_float32(f0_hz).astype(np.float32)
+    dt = np.float32
+    n_frames = f0_hz.shape[1]
+    upsampling = int(sample_rate / frame_rate)
+    n_samples = upsampling * n_frames
+    n_harm = harmonic_distribution.shape[-1]
+    # legacy bilinear coordinates (core._resize_bilinear_legacy), float32 like the reference
+    pos = np.arange(n_samples).astype(dt) * (dt(n_frames) / dt(n_samples))
+    lower = np.floor(pos).astype(np.int64)
+    upper = np.minimum(np.ceil(pos).astype(np.int64), n_frames - 1)
+    lerp = (pos - np.floor(pos)).astype(dt)
+    audio = None
+    for s in range(f0_hz.shape[-1]):
+        partial_hz = core.get_harmonic_frequencies(f0_hz[..., s:s + 1], n_harm) * (dt(1.0) + harmonic_shifts)
+        partial_amp = amplitudes * harmonic_distribution
+        freq_env = core.resample(partial_hz, n_samples)                               # float32: the Nyquist mask
+        amp_env = core.resample(partial_amp, n_samples, method='window')
+        amp_env = core.remove_above_nyquist(freq_env, amp_env, sample_rate)
+        if rounded_omega:
+            omega = ((freq_env * dt(2.0 * np.pi)) / dt(float(sample_rate))).astype(np.float64)
+        else:
+            top, bottom = partial_hz[:, lower, :], partial_hz[:, upper, :]
+            slope = (bottom - top).astype(np.float64)                                  # float32 difference, like the resize
+            omega = (top.astype(np.float64) + slope * lerp[None, :, None].astype(np.float64)) * (2.0 * np.pi / sample_rate)
+        phase = np.mod(np.cumsum(omega, axis=1), 2.0 * np.pi)
+        y = np.sum(amp_env.astype(np.float64) * np.cos(phase), axis=-1)
+        audio = y if audio is None else audio + y
+    return audio
+
+
 def surrogate_controls(amplitudes, decays, decay_time, harmonic_distribution, inharm_coef, f0_hz, *,
                        sample_rate, min_frequency=20, scale_fn=SCALE_EXP_SIGMOID,
                        normalize_harm_distribution=True, normalize_below_nyquist=True):

@@ -187,6 +187,28 @@ def test_surrogate_additive_golden(dp, dev, golden_dir, name):
         dp.SurrogateAdditive(sample_rate=int(g['sample_rate']), inference=False)(*args)
 
 
+@pytest.mark.parametrize('sr,F,B,H,S', [(24000, 750, 2, 96, 2), (48000, 250, 1, 128, 2), (24000, 300, 2, 128, 1)])
+def test_fast_phase_against_the_exact_model(dp, dev, sr, F, B, H, S):
+    """b200ddsp_config.fast_phase = 1 (closed-form double-precision unit start phases, no phase pass) against
+    the reference's signal model evaluated in exact arithmetic (oracle additive_signal_exact_sum): within
+    1e-3 -- while the reference's own float32 output sits percent away from that model (rounding noise of
+    its float32 omegas and running sum), which is also why the fast mode cannot be within 1e-4 of the
+    REFERENCE and stays opt-in.  The default mode is pinned to the reference at 2e-5 on the same inputs."""
+    x = voice_inputs(np.random.default_rng(sr + H + 1), B, F, H, S, 8)
+    ctl = ref.additive_controls(x['amplitudes'], x['harmonic_distribution'], x['inharm_coef'], x['f0_hz'],
+                                sample_rate=sr)
+    ideal = ref.additive_signal_exact_sum(**ctl, sample_rate=sr)
+    ref32 = ref.additive_signal(**ctl, sample_rate=sr, inference=True)
+    args = [cu(ctl[k], dev) for k in ('amplitudes', 'harmonic_distribution', 'harmonic_shifts', 'f0_hz')]
+    fast = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, fast_phase=True, name='a').get_signal(*args)
+    faithful = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='a').get_signal(*args)
+    assert rel_err(fast, ideal) < 1e-3
+    assert rel_err(faithful, ref32) < TIGHT
+    assert rel_err(ref32, ideal) > 3 * rel_err(fast, ideal)       # the fast mode is the closer one to the model
+    with pytest.raises(ValueError, match='fast_phase'):
+        dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=False, fast_phase=True, name='a').get_signal(*args)
+
+
 def test_additive_known_answers(dp, dev):
     """SURVEY 8c KATs 2-4, 6 on the CUDA path."""
     sr, F, H = 24000, 30, 8
