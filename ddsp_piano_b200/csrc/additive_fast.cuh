@@ -488,8 +488,8 @@ __device__ __forceinline__ void osc_chunk_dispatch(const AdditiveArgs& a, const 
 // whole batch against 0.4 ms for pass 1).  Inside a unit (<= 256 samples) pass 2 still accumulates in
 // float32 from that start.  What is removed is the rounding noise of the reference's float32 running sum
 // (up to ~1e-3 rad per chunk in the highest partials, more over a clip), so the output is NOT within
-// 1e-4 of the reference: opt-in, validated against the oracle's float64-accumulation variant
-// (oracle/ddsp_piano_np.py::additive_signal_exact_sum).
+// 1e-4 of the reference: opt-in, validated against the same signal model evaluated in float64
+// (tests/test_gpu_parity.py::test_fast_phase_against_the_exact_model, profiles/r02_fast_phase_error_table.txt).
 __global__ void __launch_bounds__(128) additive_lerp_sums_kernel(const float* __restrict__ lerp,
                                                                  double* __restrict__ frame_sum,   // [F_out]
                                                                  double* __restrict__ unit_sum,    // [n_chunks * n_sub]

@@ -79,8 +79,8 @@ typedef struct {
                                       controls (no phase pass, ~20 % less time per forward); closer to
                                       the exact phase than the reference's float32 cumsum and
                                       therefore up to ~1e-2 rad away from it in the highest partials:
-                                      NOT within 1e-4 of the reference, validated against the float64
-                                      oracle instead (tests/test_gpu_parity.py).
+                                      NOT within 1e-4 of the reference, validated against the same signal
+                                      model in float64 instead (tests/test_gpu_parity.py).
                                       inference = 1, fast additive path, whole clips only. */
 } b200ddsp_config;
 
