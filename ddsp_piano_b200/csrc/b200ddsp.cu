@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <map>
+#include <type_traits>
 #include <new>
 #include <string>
 #include <utility>
@@ -1208,6 +1209,22 @@ static void launch_fft_pass(int R, const Loader& ld, const Storer& st, const flo
                             int batches, cudaStream_t s) {
   if (R == 64) {
     dim3 grid64(n / 64 / kFft64J, batches);
+    if constexpr (std::is_same<Loader, LoadComplex>::value) {
+      static const int bulk = env_int("B200DDSP_FFT_BULK", 0);
+      if (bulk == 2) {   // persistent, two-stage pipeline
+        static const int per_sm = env_int("B200DDSP_FFT_PIPE_CTAS", 6);
+        const int tiles = n / 64 / kFft64J * batches;
+        const int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
+        if (Ns < 16) fft_pass64_pipelined_kernel<Storer, true><<<grid, kFft64Threads, 0, s>>>(ld.src, st, tw, n, Ns, batches);
+        else fft_pass64_pipelined_kernel<Storer, false><<<grid, kFft64Threads, 0, s>>>(ld.src, st, tw, n, Ns, batches);
+        return;
+      }
+      if (bulk) {
+        if (Ns < 16) fft_pass64_kernel<Loader, Storer, true, true><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
+        else fft_pass64_kernel<Loader, Storer, false, true><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
+        return;
+      }
+    }
     if (Ns < 16) fft_pass64_kernel<Loader, Storer, true><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
     else fft_pass64_kernel<Loader, Storer, false><<<grid64, kFft64Threads, 0, s>>>(ld, st, tw, n, Ns);
     return;

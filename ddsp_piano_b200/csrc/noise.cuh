@@ -91,38 +91,6 @@ struct NoiseSmemLayout {
   }
 };
 
-// ---- asynchronous bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) -----------------------------------
-__device__ __forceinline__ unsigned int smem_u32(const void* p) {
-  return (unsigned int)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(void* bar, unsigned int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, unsigned int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned int bytes, void* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // Philox4x32-10 (Salmon et al. 2011), the generator family TF's random ops use.  The
 // reference draws unseeded noise (filtered_noise_synth.py:39-40), so only the distribution
 // matters: uniform on [-1, 1) with 23 random mantissa bits, like tf.random.uniform.

@@ -292,11 +292,17 @@ __global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const Loader ld, 
 constexpr int kFft64J = 16;
 constexpr int kFft64Threads = kFft64J * 8;
 
-template <class Loader, class Storer, bool SMALL_NS>
+// BULK (complex source only): the CTA's tile -- 64 runs of 16 consecutive points, one per residue r --
+// is staged in shared memory by 64 bulk asynchronous copies of 128 bytes (cp.async.bulk, the 1-D form of
+// TMA; one per thread of the first two warps) that complete on an mbarrier, instead of 8 strided 8-byte
+// loads per thread.  A/B against the plain loads: DESIGN.md 4.3 (B200DDSP_FFT_BULK).
+template <class Loader, class Storer, bool SMALL_NS, bool BULK = false>
 __global__ void __launch_bounds__(kFft64Threads) fft_pass64_kernel(const Loader ld, const Storer st,
                                                                   const float2* __restrict__ tw,
                                                                   int n, int Ns) {
   __shared__ float2 S[kFft64J * 65];
+  __shared__ __align__(128) float2 T[BULK ? 64 * kFft64J : 1];
+  __shared__ __align__(8) unsigned long long bar;
   const int jj = threadIdx.x & (kFft64J - 1);
   const int a = threadIdx.x >> 4;                 // stage 1: residue of r mod 8; stage 2: c
   const int batch = blockIdx.y;
@@ -304,8 +310,23 @@ __global__ void __launch_bounds__(kFft64Threads) fft_pass64_kernel(const Loader 
   const int j = blockIdx.x * kFft64J + jj;        // n >= 1024: every j is valid
   const int k = j & (Ns - 1);
   float2 v[8];
+  if constexpr (BULK) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_expect_tx(&bar, 64 * kFft64J * (unsigned int)sizeof(float2));
+    }
+    __syncthreads();
+    if (threadIdx.x < 64)
+      bulk_load(&T[threadIdx.x * kFft64J], ld.src + (size_t)batch * n + (size_t)blockIdx.x * kFft64J +
+                                               (size_t)threadIdx.x * stride,
+                kFft64J * (unsigned int)sizeof(float2), &bar);
+    mbar_wait(&bar, 0);
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = ld(batch, j + (a + 8 * m) * stride);
+    for (int m = 0; m < 8; ++m) v[m] = T[(a + 8 * m) * kFft64J + jj];
+  } else {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = ld(batch, j + (a + 8 * m) * stride);
+  }
   if (Ns > 1) {
     const int step = k * (stride / Ns);           // k * n / (Ns * 64)
 #pragma unroll
@@ -348,6 +369,98 @@ __global__ void __launch_bounds__(kFft64Threads) fft_pass64_kernel(const Loader 
       const int jg = j0 + jl;
       st(batch, (jg - kk) * 64 + kk + q * Ns, S[jl * 65 + q]);
     }
+  }
+}
+
+// The same pass as a PERSISTENT kernel with a two-stage bulk-asynchronous pipeline (complex source only):
+// a CTA walks tiles (batch, 16 consecutive butterflies) with stride gridDim.x; while it transforms tile i
+// out of stage i & 1, the 64 bulk copies of tile i + 1 (128 bytes each, cp.async.bulk -> UBLKCP) fill the
+// other stage and complete on that stage's mbarrier.  The global-load latency that the one-shot kernel
+// covers with occupancy alone (stalls: long_scoreboard + lg_throttle) is hidden behind the butterflies.
+template <class Storer, bool SMALL_NS>
+__global__ void __launch_bounds__(kFft64Threads) fft_pass64_pipelined_kernel(const float2* __restrict__ src,
+                                                                            const Storer st,
+                                                                            const float2* __restrict__ tw,
+                                                                            int n, int Ns, int batches) {
+  __shared__ float2 S[kFft64J * 65];
+  __shared__ __align__(128) float2 T[2][64 * kFft64J];
+  __shared__ __align__(8) unsigned long long bar[2];
+  const int jj = threadIdx.x & (kFft64J - 1);
+  const int a = threadIdx.x >> 4;                 // stage 1: residue of r mod 8; stage 2: c
+  const int stride = n >> 6;                      // n / 64
+  const int tiles_per_batch = stride / kFft64J;
+  const int n_tiles = tiles_per_batch * batches;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int stage) {         // threads 0..63: one 128-byte run each
+    const int batch = tile / tiles_per_batch, jb = tile - batch * tiles_per_batch;
+    if (threadIdx.x == 0) mbar_expect_tx(&bar[stage], 64 * kFft64J * (unsigned int)sizeof(float2));
+    // the expect_tx of thread 0 and the copies of the other threads may reach the barrier in any order: the
+    // phase cannot complete before the arrival that carries the expected byte count
+    if (threadIdx.x < 64)
+      bulk_load(&T[stage][threadIdx.x * kFft64J],
+                src + (size_t)batch * n + (size_t)jb * kFft64J + (size_t)threadIdx.x * stride,
+                kFft64J * (unsigned int)sizeof(float2), &bar[stage]);
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) issue(tile, 0);
+  unsigned int parity[2] = {0u, 0u};
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) issue(next, stage ^ 1);   // stage ^ 1 was released by the barrier that ended tile it - 1
+    mbar_wait(&bar[stage], parity[stage]);
+    parity[stage] ^= 1u;
+    const int batch = tile / tiles_per_batch;
+    const int j = (tile - batch * tiles_per_batch) * kFft64J + jj;
+    const int k = j & (Ns - 1);
+    float2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = T[stage][(a + 8 * m) * kFft64J + jj];
+    if (Ns > 1) {
+      const int step = k * (stride / Ns);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int r = a + 8 * m;
+        if (r > 0) v[m] = cmul(v[m], __ldg(tw + r * step));
+      }
+    }
+    dft<8>(v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float2 x = v[c];
+      if (a * c > 0) x = cmul(x, __ldg(tw + (a * c) * stride));
+      S[jj * 65 + c * 8 + a] = x;
+    }
+    __syncthreads();
+    const int c = a;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = S[jj * 65 + c * 8 + i];
+    dft<8>(v);
+    if (!SMALL_NS) {
+      const int base = (j - k) * 64 + k;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) st(batch, base + (c + 8 * d) * Ns, v[d]);
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int d = 0; d < 8; ++d) S[jj * 65 + c + 8 * d] = v[d];
+      __syncthreads();
+      const int j0 = (tile - batch * tiles_per_batch) * kFft64J;
+      for (int e = threadIdx.x; e < kFft64J * 64; e += kFft64Threads) {
+        const int kk = e & (Ns - 1);
+        const int q = (e / Ns) & 63;
+        const int jb = e / (Ns * 64);
+        const int jl = jb * Ns + kk;
+        const int jg = j0 + jl;
+        st(batch, (jg - kk) * 64 + kk + q * Ns, S[jl * 65 + q]);
+      }
+    }
+    __syncthreads();   // S and T[stage] are free again (generic reads done before the next async writes)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
 }
 
