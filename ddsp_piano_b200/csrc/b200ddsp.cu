@@ -2309,8 +2309,9 @@ static int launch_gru(b200ddsp_handle* h, const float* x_proj, const float* w_hh
   int RB = 2;
   while (RB < rb_max && (int64_t)((rows + RB - 1) / RB) * CL > h->n_sms) RB *= 2;
   const int groups = (rows + RB - 1) / RB;
-  const size_t smem = (size_t)(3 * UC * (u + 16) + 2 * RB * u) * sizeof(float);
-  auto kernel = gru_recurrence_kernel<UC, CL>;
+  const size_t smem = (size_t)(3 * UC * (u + 16) + 2 * RB * u) * sizeof(float) + 16;   // + two mbarriers
+  static const int async_exchange = env_int("B200DDSP_GRU_ASYNC", 1);
+  auto kernel = (CL > 1 && async_exchange) ? gru_recurrence_kernel<UC, CL, true> : gru_recurrence_kernel<UC, CL, false>;
   CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CL));

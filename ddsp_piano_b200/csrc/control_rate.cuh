@@ -56,7 +56,25 @@ __global__ void __launch_bounds__(128) note_release_kernel(const float* __restri
 // Thread = (row pair p, unit j, quarter q of the k range): 4 adjacent lanes split the dot products
 // (float4 reads, k interleaved by 16 so that a quarter-warp reads 2 x 64 contiguous bytes on disjoint
 // banks: row stride u + 16 floats), reduce with two shuffles, lanes q = 0, 1 finish rows 2p, 2p + 1.
-template <int UC, int CL>
+// ASYNC (CL > 1): the new state travels with st.async.shared::cluster ... mbarrier::complete_tx::bytes into an
+// mbarrier of the DESTINATION CTA, which every CTA arms with the bytes it expects per frame and waits on:
+// no cluster barrier and no GPU-scope fence in the frame loop (cluster.sync() compiles to MEMBAR.ALL.GPU +
+// UCGABAR arrive/wait).  Measured in isolation (scripts/ubench/cluster_exchange.cu,
+// profiles/r02_ubench_cluster_exchange.txt): 793 -> 410 cycles per frame.  Why no barrier is needed: a CTA can
+// only write frame t + 1's state into a peer's buffer after it has received ALL of frame t's state, which the
+// peer sends after it has finished reading that very buffer.
+__device__ __forceinline__ unsigned int map_shared_u32(unsigned int addr, unsigned int rank) {
+  unsigned int r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(unsigned int remote_addr, float v, unsigned int remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+
+template <int UC, int CL, bool ASYNC = false>
 __global__ void __launch_bounds__(UC * 32 > 1024 ? 1024 : UC * 32, 1)
 gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gates (r, z, n), bias b_i included
                       const float* __restrict__ w_hh,     // [3u, u]        torch weight_hh layout
@@ -68,6 +86,7 @@ gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gate
   extern __shared__ __align__(16) float gru_smem[];
   float* Ws = gru_smem;                                   // [3][UC][WS]
   float* hs = gru_smem + 3 * UC * WS;                     // [2][RB][u]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(hs + 2 * RB * u);   // [2] (ASYNC)
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
@@ -100,21 +119,29 @@ gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gate
     const int c = q + 4 * i;
     remote[i] = c >= CL ? nullptr : (CL > 1 ? cluster.map_shared_rank(hs, c) : hs);
   }
-  if (CL > 1) cluster.sync(); else __syncthreads();       // weights and zero state in place everywhere
+  if (ASYNC && tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
+  if (CL > 1) cluster.sync(); else __syncthreads();       // weights, zero state and barriers in place everywhere
+  const unsigned int hs_u32 = smem_u32(hs), bars_u32 = smem_u32(bars);
 
   const float4* wr = reinterpret_cast<const float4*>(Ws + (0 * UC + jl) * WS) + q;
   const float4* wz = reinterpret_cast<const float4*>(Ws + (1 * UC + jl) * WS) + q;
   const float4* wn = reinterpret_cast<const float4*>(Ws + (2 * UC + jl) * WS) + q;
   const unsigned base_lane = (tid & 31) & ~3u;
 
+  float xr_n = 0.f, xz_n = 0.f, xn_n = 0.f;               // input projections, fetched one frame ahead
+  if (owner) { xr_n = __ldg(xp); xz_n = __ldg(xp + u); xn_n = __ldg(xp + 2 * u); }
   for (int t = 0; t < F; ++t) {
     const int cur = t & 1;
-    float xr = 0.f, xz = 0.f, xn = 0.f;
-    if (owner) {                                          // in flight under the dot products
-      xr = __ldg(xp + (size_t)t * 3 * u);
-      xz = __ldg(xp + (size_t)t * 3 * u + u);
-      xn = __ldg(xp + (size_t)t * 3 * u + 2 * u);
+    const float xr = xr_n, xz = xz_n, xn = xn_n;
+    if (owner && t + 1 < F) {                             // in flight under this frame's dot products and exchange
+      xr_n = __ldg(xp + (size_t)(t + 1) * 3 * u);
+      xz_n = __ldg(xp + (size_t)(t + 1) * 3 * u + u);
+      xn_n = __ldg(xp + (size_t)(t + 1) * 3 * u + 2 * u);
     }
+    if (ASYNC && tid == 0) mbar_expect_tx(&bars[cur ^ 1], (unsigned int)(RB * u * sizeof(float)));
     const float4* ha = reinterpret_cast<const float4*>(hs + (cur * RB + 2 * p) * u) + q;
     const float4* hb = ha + u / 4;
     float ar0 = 0.f, az0 = 0.f, an0 = 0.f, ar1 = 0.f, az1 = 0.f, an1 = 0.f;
@@ -138,6 +165,9 @@ gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gate
       az1 += __shfl_xor_sync(0xffffffffu, az1, o); an1 += __shfl_xor_sync(0xffffffffu, an1, o);
     }
     const float sr = q == 0 ? ar0 : ar1, sz = q == 0 ? az0 : az1, sn = q == 0 ? an0 : an1;
+    // precise expf / tanhf / IEEE division on purpose: with the hardware approximations (__expf, __fdividef:
+    // 3e-7 per gate) the frame loses ~150 cycles but the controls of a 750-frame clip drift past 1e-4 of the
+    // restatement (the recurrence amplifies per-frame rounding; measured, round 2)
     const float r = 1.f / (1.f + expf(-(xr + sr + b_r)));
     const float z = 1.f / (1.f + expf(-(xz + sz + b_z)));
     const float n = tanhf(xn + r * (sn + b_n));
@@ -147,11 +177,25 @@ gru_recurrence_kernel(const float* __restrict__ x_proj,   // [rows, F, 3u]  gate
     // both rows of the pair to all four lanes, then out to the cluster
     const float va = __shfl_sync(0xffffffffu, h_new, base_lane), vb = __shfl_sync(0xffffffffu, h_new, base_lane + 1);
     const int at = ((cur ^ 1) * RB + 2 * p) * u + j;
+    if (ASYNC) {
 #pragma unroll
-    for (int i = 0; i < NR; ++i)
-      if (remote[i] != nullptr) { remote[i][at] = va; remote[i][at + u] = vb; }
-    if (CL > 1) cluster.sync(); else __syncthreads();
+      for (int i = 0; i < NR; ++i) {
+        const unsigned int c = q + 4 * i;
+        if (c < CL) {
+          const unsigned int bar = map_shared_u32(bars_u32 + 8u * (cur ^ 1), c);
+          st_async_f32(map_shared_u32(hs_u32 + 4u * at, c), va, bar);
+          st_async_f32(map_shared_u32(hs_u32 + 4u * (at + u), c), vb, bar);
+        }
+      }
+      mbar_wait(&bars[cur ^ 1], (unsigned int)((t >> 1) & 1));   // each barrier is used every other frame
+    } else {
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (remote[i] != nullptr) { remote[i][at] = va; remote[i][at + u] = vb; }
+      if (CL > 1) cluster.sync(); else __syncthreads();
+    }
   }
+  if (ASYNC) cluster.sync();                              // nobody leaves while peers may still write
 }
 
 }  // namespace b200ddsp
