@@ -134,6 +134,30 @@ __device__ __forceinline__ float cos_large(float x) {
   return __cosf((float)fma(-n, 6.283185307179586, xd));
 }
 
+// Cross-lane reduction of the synthesis pass through shared memory.  Every 4-sample group leaves 4 partial
+// sums per lane; summing them over the 32 lanes with a shuffle butterfly costs 6 SHFL + 6 FSEL + 10 FADD and a
+// 16-byte store per group.  Instead each lane parks its 4 values in a per-warp tile [32 lanes][kRedPitch]
+// (one STS.128; pitch 36 = 4 mod 32 words: conflict free) and after 8 groups lane s adds column s over the
+// 32 rows (conflict free, fixed order -> bitwise reproducible) and stores one coalesced 128-byte run.
+constexpr int kRedPitch = 36;
+constexpr int kRedTileFloats = 32 * kRedPitch;          // per warp
+
+__device__ __forceinline__ void flush_tile(const float* tile, int lane, int n, float* dst) {
+  __syncwarp();
+  if (lane < n) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int L = 0; L < 32; L += 4) {
+      s0 += tile[(L + 0) * kRedPitch + lane];
+      s1 += tile[(L + 1) * kRedPitch + lane];
+      s2 += tile[(L + 2) * kRedPitch + lane];
+      s3 += tile[(L + 3) * kRedPitch + lane];
+    }
+    dst[lane] = (s0 + s1) + (s2 + s3);
+  }
+  __syncwarp();
+}
+
 // 32 lanes x 4 values -> every lane returns the sum over lanes of y[lane & 3].
 __device__ __forceinline__ float transpose_reduce4(float (&y)[4], int lane) {
 #pragma unroll
@@ -370,7 +394,8 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
 // sub-unit q of the chunk: writes its audio to `row_out` (the chunk's base).
 template <int NC, int LW, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
-                                            int c, int q, int lane, const float* win, float* row_out) {
+                                            int c, int q, int lane, const float* win, float* row_out,
+                                            float* tile = nullptr) {
   const int t0 = c * a.chunk;
   const int tc1 = min(a.N, t0 + a.chunk);              // end of the chunk
   const int ts = ENDS_ONLY ? t0 : t0 + q * kSubLen;    // first / one-past-last sample of this unit
@@ -430,7 +455,6 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     if (ENDS_ONLY || amp_mode == kAmpSilent) {
       if (steady) osc_group_h<NC, true, kAmpSilent, STEP, false>(a, st, w, fr, y);
       else osc_group_h<NC, false, kAmpSilent, STEP, false>(a, st, w, fr, y);
-      if (!ENDS_ONLY && lane < kOscUnroll) row_out[t - t0 + lane] = 0.f;
     } else if constexpr (!ENDS_ONLY) {
       if (amp_mode == kAmpNoCheck) {
         if (steady) osc_group_h<NC, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
@@ -439,8 +463,13 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
         if (steady) osc_group_h<NC, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
         else osc_group_h<NC, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
       }
-      const float v = transpose_reduce4(y, lane);
-      if (lane < kOscUnroll) row_out[t - t0 + lane] = v;
+    }
+    if constexpr (!ENDS_ONLY) {
+      // park the group's partial sums (zeros for a silent group); every 8th group, and at the unit's end,
+      // the warp adds the tile's columns and writes up to 32 samples
+      const int gi = ((t - ts) >> 2) & 7;
+      *reinterpret_cast<float4*>(tile + lane * kRedPitch + 4 * gi) = make_float4(y[0], y[1], y[2], y[3]);
+      if (gi == 7 || t + kOscUnroll >= t1) flush_tile(tile, lane, 4 * (gi + 1), row_out + (t - t0) - 4 * gi);
     }
   }
   if (ENDS_ONLY) {
@@ -673,14 +702,10 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
 // result independent of the scheduling order.
 template <int SP, bool ENDS_ONLY, bool PLAIN = false>
 __global__ void __launch_bounds__(kAddThreads, 3) additive_fast_kernel(const AdditiveFastArgs fa) {
+  static_assert(ENDS_ONLY, "the persistent kernel is the phase pass; synthesis runs per bucket (additive_synth_kernel)");
   const AdditiveArgs& a = fa.a;
-  extern __shared__ __align__(16) float smem[];
-  float* win = smem;                                   // [2U]
+  const float* win = nullptr;
   const int lane = threadIdx.x & 31;
-  if (!ENDS_ONLY) {
-    for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];   // rising half
-    __syncthreads();
-  }
   const int kind = fa.slot;
   const int sets = a.S / SP;
   const int n_sub = ENDS_ONLY ? 1 : a.n_sub;
@@ -764,6 +789,7 @@ additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [U] rising half of hann(2U)
+  float* tile = smem + ((a.U + 3) & ~3) + (threadIdx.x >> 5) * kRedTileFloats;   // reduction tile of this warp
   const int lane = threadIdx.x & 31;
   const int sets = a.S / SP;
   const int per_unit = sets * a.n_sub;                           // items per listed unit: (set, sub-unit)
@@ -781,8 +807,8 @@ additive_synth_kernel(const AdditiveFastArgs fa) {
   const int c = unit - row * a.n_chunks;
   const int v = row / a.B, b = row - v * a.B;
   float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, out);
-  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, q, lane, win, out);
+  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, out, tile);
+  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, q, lane, win, out, tile);
 }
 
 }  // namespace b200ddsp

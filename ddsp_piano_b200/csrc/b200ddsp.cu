@@ -41,6 +41,8 @@ struct b200ddsp_handle {
   std::map<std::pair<int, int>, bool> uniform_lerp;   // (F, N) -> floor(float(t)*scale) == t/U
   unsigned long long launches = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of the host-input entry point
+  cudaStream_t d2h_stream = nullptr;    // the dry signal goes home while the reverb still runs
+  cudaEvent_t ev_dry_ready = nullptr, ev_dry_home = nullptr;
   cudaStream_t aux_stream[kMaxGroups - 1] = {};   // the synthesis buckets run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {};
   cudaStream_t noise_stream = nullptr;  // the noise synth runs beside the oscillator bank
@@ -312,6 +314,9 @@ extern "C" int b200ddsp_create(const b200ddsp_config* cfg, b200ddsp_handle** out
   }
   {
     bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_dry_ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_dry_home, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kMaxGroups - 1 && ok; ++i) {
       ok = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -377,6 +382,9 @@ extern "C" int b200ddsp_destroy(b200ddsp_handle* h) {
   if (h->d_window) cudaFree(h->d_window);
   if (h->d_cmat_t) cudaFree(h->d_cmat_t);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->ev_dry_ready) cudaEventDestroy(h->ev_dry_ready);
+  if (h->ev_dry_home) cudaEventDestroy(h->ev_dry_home);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->noise_stream) cudaStreamDestroy(h->noise_stream);
   if (h->ev_noise_fork) cudaEventDestroy(h->ev_noise_fork);
@@ -800,20 +808,10 @@ static void launch_additive_generic(const AdditiveArgs& a, bool ends_only, dim3 
   }
 }
 
-static void launch_additive_fast(const AdditiveFastArgs& fa, bool ends_only, int grid, size_t smem,
-                                 cudaStream_t st, bool plain_cumsum = false) {
-  if (plain_cumsum) {   // inference=False: one chunk per clip, no phase pass, exact cos reduction
-    if (fa.sp == 2) additive_fast_kernel<2, false, true><<<grid, kAddThreads, smem, st>>>(fa);
-    else additive_fast_kernel<1, false, true><<<grid, kAddThreads, smem, st>>>(fa);
-    return;
-  }
-  if (fa.sp == 2) {
-    if (ends_only) additive_fast_kernel<2, true><<<grid, kAddThreads, 0, st>>>(fa);
-    else additive_fast_kernel<2, false><<<grid, kAddThreads, smem, st>>>(fa);
-  } else {
-    if (ends_only) additive_fast_kernel<1, true><<<grid, kAddThreads, 0, st>>>(fa);
-    else additive_fast_kernel<1, false><<<grid, kAddThreads, smem, st>>>(fa);
-  }
+// the phase pass: persistent kernel, every warp pulls (unit, substring set) items until the list is empty
+static void launch_additive_ends(const AdditiveFastArgs& fa, int grid, cudaStream_t st) {
+  if (fa.sp == 2) additive_fast_kernel<2, true><<<grid, kAddThreads, 0, st>>>(fa);
+  else additive_fast_kernel<1, true><<<grid, kAddThreads, 0, st>>>(fa);
 }
 
 template <int NH>
@@ -883,7 +881,7 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       StageTimer tm(h, B200DDSP_STAGE_PHASE_ENDS, st);
       AdditiveFastArgs fa = r.fa;
       fa.slot = 0;
-      launch_additive_fast(fa, true, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), 0, st);
+      launch_additive_ends(fa, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), st);
       CHECK_LAUNCH_ON(h, "additive_fast_kernel<ends>", st);
     }
     if (r.n_chunks > 1 || carry || (r.span && r.span->seeded)) {
@@ -921,7 +919,8 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
   if (r.fast) {
     AdditiveFastArgs fa = r.fa;
     fa.slot = 1 + g;
-    const size_t smem = (size_t)r.a.U * sizeof(float);
+    // Hann half-window + one reduction tile per warp
+    const size_t smem = (size_t)(((r.a.U + 3) & ~3) + kSynthWarps * kRedTileFloats) * sizeof(float);
     const bool plain = !h->cfg.inference;
     // one kernel per bucket (number of live 16-partial half-groups), heaviest on the caller's
     // stream, the others on auxiliary streams so that the buckets overlap; grids are sized for the
@@ -1702,6 +1701,7 @@ extern "C" int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, cons
 static int noise_parts(int P) { return P < kNoiseSlices ? 1 : kNoiseSlices; }
 
 struct ForwardSync {
+  float* dry_host;                              // where the dry signal goes as soon as it is mixed (or nullptr)
   cudaEvent_t small_ready;                      // amplitudes, inharm_coef, f0_hz of all voices
   cudaEvent_t group_ready[kMaxVoiceGroups];     // harmonic_distribution of voice group g
   cudaEvent_t mags_ready[4];                    // magnitudes of voice part p (noise_parts(P) parts)
@@ -1841,6 +1841,12 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_noise_join, 0));
   }
   if (int rc = run_mix(h, noise_part, n_slices, &mix, dry_out, B, N, 0, st)) return rc;
+  if (sync && sync->dry_host) {   // host-input path: the dry signal travels home under the reverb
+    CUDA_TRY(h, cudaEventRecord(h->ev_dry_ready, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_dry_ready, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(sync->dry_host, dry_out, (size_t)B * N * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_dry_home, h->d2h_stream));
+  }
   if (tl) {
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ir_spectra, 0));
     return timeline_reverb_audio_phase(h, *tl, dry_out, wet_out, st);
@@ -2121,6 +2127,7 @@ static int forward_host_impl(b200ddsp_handle* h, const b200ddsp_voice* voices_ho
   CUDA_TRY(h, cudaEventRecord(h->ev_enter, st));
   CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_enter, 0));
   ForwardSync sync{};
+  sync.dry_host = dry_out_host;
   // small tensors of every voice first: they are all the phase pass needs
   CUDA_TRY(h, copy_runs(0, P, BF, [&](int v) { return voices_host[v].amplitudes; },
                         [&](int v) { return dev[v].amplitudes; }));
@@ -2171,8 +2178,7 @@ static int forward_host_impl(b200ddsp_handle* h, const b200ddsp_voice* voices_ho
                                    w, &sync, st)) {
     return rc;
   }
-  if (dry_out_host)
-    CUDA_TRY(h, cudaMemcpyAsync(dry_out_host, dry_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  if (dry_out_host) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_dry_home, 0));   // copied under the reverb (forward_core)
   if (wet_out_host)
     CUDA_TRY(h, cudaMemcpyAsync(wet_out_host, wet_dev, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
   return B200DDSP_OK;
