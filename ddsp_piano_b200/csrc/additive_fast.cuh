@@ -37,7 +37,12 @@ struct AdditivePlan;
 struct AdditiveFastArgs {
   AdditiveArgs a;                  // a.out: [P * sets, B, N] partial signals
   AdditivePlan* plan;              // bucket counts + work counters
-  const int* lists;                // [kPlanSlots][kMaxGroups][R * n_chunks] units by slot and bucket
+  const int* lists;                // [kPlanSlots][kMaxGroups][R * n_chunks] units by slot and bucket: slot 0 (phase
+                                   // pass) a flat list of units; synthesis slots: rows grouped by chunk, entry
+                                   // c * R + j = row of the j-th unit of chunk c
+  const int* chunk_count;          // [kPlanSlots][kMaxGroups][n_chunks]      units per (slot, bucket, chunk)
+  const int* chunk_first;          // [kPlanSlots][kMaxGroups][n_chunks + 1]  first work item of chunk c (prefix of
+                                   // ceil(count / units per warp)), written by additive_plan_items_kernel
   const float* lerp;               // [N] legacy-bilinear lerp weight of every sample (additive_lerp_kernel)
   int slot;                        // work list to drain: 0 = phase ends (all voices),
                                    // 1 + g = synthesis of voice group g
@@ -125,6 +130,10 @@ enum { kAmpSilent = 0, kAmpNoCheck = 1, kAmpCheck = 2 };
 // for ~0.2 ms whatever else the GPU had to do).
 constexpr int kSubLen = 256;    // multiple of the 8-sample phase body and of kWrapEvery
 constexpr int kOscUnroll = 4;   // samples per unrolled body of the synthesis pass
+#ifndef B200DDSP_SYNTH_STEP
+#define B200DDSP_SYNTH_STEP 4
+#endif
+constexpr int kSynthStep = B200DDSP_SYNTH_STEP;   // samples per loop trip of the synthesis pass (4 or 8)
 
 // cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
 // reduce modulo the true 2 pi in double precision, then the hardware cosine.
@@ -133,6 +142,12 @@ __device__ __forceinline__ float cos_large(float x) {
   const double n = rint(xd * 0.15915494309189535);
   return __cosf((float)fma(-n, 6.283185307179586, xd));
 }
+
+// Rows and outputs of the units that share a warp in the synthesis pass (osc_chunk_h, LW < 16); row < 0: none.
+struct WarpUnits {
+  int row[4];
+  float* out[4];
+};
 
 // Cross-lane reduction of the synthesis pass through shared memory.  Every 4-sample group leaves 4 partial
 // sums per lane; summing them over the 32 lanes with a shuffle butterfly costs 6 SHFL + 6 FSEL + 10 FADD and a
@@ -154,6 +169,29 @@ __device__ __forceinline__ void flush_tile(const float* tile, int lane, int n, f
       s3 += tile[(L + 3) * kRedPitch + lane];
     }
     dst[lane] = (s0 + s1) + (s2 + s3);
+  }
+  __syncwarp();
+}
+
+// The same for UPW units sharing the warp: rows [u * 32 / UPW, (u + 1) * 32 / UPW) belong to unit u.
+template <int UPW>
+__device__ __forceinline__ void flush_tile_units(const float* tile, int lane, int n, const WarpUnits& units,
+                                                 int at) {
+  constexpr int RU = 32 / UPW;                            // rows per unit (8 or 16)
+  __syncwarp();
+  if (lane < n) {
+#pragma unroll
+    for (int u = 0; u < UPW; ++u) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int L = 0; L < RU; L += 4) {
+        s0 += tile[(u * RU + L + 0) * kRedPitch + lane];
+        s1 += tile[(u * RU + L + 1) * kRedPitch + lane];
+        s2 += tile[(u * RU + L + 2) * kRedPitch + lane];
+        s3 += tile[(u * RU + L + 3) * kRedPitch + lane];
+      }
+      if (units.out[u] != nullptr) units.out[u][at + lane] = (s0 + s1) + (s2 + s3);
+    }
   }
   __syncwarp();
 }
@@ -207,9 +245,9 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 template <int NC, int LW, bool WITH_AMP>
 __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int s, int k, int l,
-                                             float (&F)[NC], float (&A)[NC]) {
+                                             float (&F)[NC], float (&A)[NC], bool muted = false) {
   const size_t base = ((size_t)row * a.F + k) * a.H;
-  const float amp = WITH_AMP ? __ldg(a.amp + (size_t)row * a.F + k) : 0.f;
+  const float amp = (WITH_AMP && !muted) ? __ldg(a.amp + (size_t)row * a.F + k) : 0.f;
   const float f0 = __ldg(a.f0 + ((size_t)row * a.F + k) * a.S + s);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
@@ -228,10 +266,11 @@ __device__ __forceinline__ void load_frame_h(const AdditiveArgs& a, int row, int
 // every frame boundary: one extra L1 hit per 96 samples buys 3 NC registers of carried state).
 template <int NC, int LW, bool WITH_AMP>
 __device__ __forceinline__ void enter_frame_h(const AdditiveArgs& a, int row, int s, int k, int l,
-                                              OscStateH<NC>& st, bool& steady, int& amp_mode) {
+                                              OscStateH<NC>& st, bool& steady, int& amp_mode,
+                                              bool muted = false) {
   float Fn[NC], An[NC];
-  load_frame_h<NC, LW, WITH_AMP>(a, row, s, k, l, st.F, st.A);
-  load_frame_h<NC, LW, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l, Fn, An);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, k, l, st.F, st.A, muted);
+  load_frame_h<NC, LW, WITH_AMP>(a, row, s, min(k + 1, a.F - 1), l, Fn, An, muted);
   bool all_steady = true, any_live = false, any_risky = false;
   // f stays within [min(F, Fn), max(F, Fn) * (1 + 2^-22)] over the frame (one rounding in
   // bottom - top, one in the product, one in the sum), hence the margin
@@ -392,22 +431,36 @@ __device__ __forceinline__ void osc_group_h(const AdditiveArgs& a, OscStateH<NC>
 // One (row, substring pair, chunk) on one warp, half-warp layout.  ENDS_ONLY: phase chain only over the
 // whole chunk, writes the accumulator at the sub-unit boundaries and the chunk end phases; otherwise
 // sub-unit q of the chunk: writes its audio to `row_out` (the chunk's base).
+// LW = 8 / LW = 4 (synthesis pass, S even, few live half-groups): TWO / FOUR units of the same chunk share
+// the warp -- unit u on lanes [u * 2 LW, (u + 1) * 2 LW), its two substrings on the halves of that range,
+// chain j = partial LW j + (lane & (LW - 1)).  The per-sample work that does not depend on the oscillator
+// (loop, lerp and window loads, variant dispatch, reduction) is shared by 2 / 4 times as many chains, and a
+// lane carries 2 NH / 4 NH chains instead of NH: buckets of 16 or 32 live partials stop being one or two
+// dependent chains per lane under a fixed per-sample overhead.  `units`: row and output of every unit of
+// the warp (row < 0: none).
 template <int NC, int LW, bool ENDS_ONLY, bool PLAIN>
 __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* fa_lerp, int row, int s0,
                                             int c, int q, int lane, const float* win, float* row_out,
-                                            float* tile = nullptr) {
+                                            float* tile = nullptr, const WarpUnits* units = nullptr) {
   const int t0 = c * a.chunk;
   const int tc1 = min(a.N, t0 + a.chunk);              // end of the chunk
   const int ts = ENDS_ONLY ? t0 : t0 + q * kSubLen;    // first / one-past-last sample of this unit
   const int t1 = (ENDS_ONLY || a.n_sub == 1) ? tc1 : min(tc1, ts + kSubLen);
-  const int l = lane & (LW - 1), s = s0 + lane / LW;   // LW = 16: two substrings on the half-warps
+  const int l = lane & (LW - 1);
+  const int s = (LW < 16) ? s0 + ((lane / LW) & 1) : s0 + lane / LW;   // LW = 16: two substrings on the half-warps
+  bool muted = false;                                  // lanes of a missing unit
+  if constexpr (LW < 16) {
+    const int r_u = units->row[lane / (2 * LW)];
+    muted = r_u < 0;
+    row = muted ? units->row[0] : r_u;
+  }
   OscStateH<NC> st;
   int k = ts / a.U;
   int r = ts - k * a.U;
   k += a.koff;                                         // input frame (spans carry halo frames in front)
   bool steady;
   int amp_mode;
-  enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
+  enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode, muted);
   const size_t osc_chunk = ((size_t)row * a.S + s) * a.n_chunks + c;
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
@@ -423,7 +476,9 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
       }
     }
   }
-  constexpr int STEP = ENDS_ONLY ? 8 : kOscUnroll;   // chunk, frame and sub-unit lengths are multiples of 8
+  // samples per loop trip: 8 (chunk, frame and sub-unit lengths are multiples of 8).  The synthesis pass runs
+  // its 4-sample body kSynthStep / 4 times per trip: frame check, lerp load and variant dispatch once per trip
+  constexpr int STEP = ENDS_ONLY ? 8 : kSynthStep;
   for (int t = ts; t < t1; t += STEP, r += STEP) {
     if (ENDS_ONLY && a.n_sub > 1 && t > t0 && ((t - t0) & (kSubLen - 1)) == 0) {
       const int qq = (t - t0) / kSubLen - 1;           // state at the start of sub-unit qq + 1
@@ -436,9 +491,9 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
     if (r == a.U) {
       r = 0;
       ++k;
-      enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode);
+      enter_frame_h<NC, LW, !ENDS_ONLY>(a, row, s, k, l, st, steady, amp_mode, muted);
     }
-    // legacy-bilinear lerp weights of the group's samples (table built by additive_lerp_kernel);
+    // legacy-bilinear lerp weights of the trip's samples (table built by additive_lerp_kernel);
     // steady frames (held notes) never touch the table.  Fetching one group ahead was measured
     // and does not pay: the other resident warps already cover the L1 latency.
     float fr[STEP];
@@ -448,28 +503,50 @@ __device__ __forceinline__ void osc_chunk_h(const AdditiveArgs& a, const float* 
       if (!steady) l4 = __ldg(reinterpret_cast<const float4*>(fa_lerp + t) + j4);
       fr[4 * j4] = l4.x; fr[4 * j4 + 1] = l4.y; fr[4 * j4 + 2] = l4.z; fr[4 * j4 + 3] = l4.w;
     }
-    float y[kOscUnroll];
-#pragma unroll
-    for (int i = 0; i < kOscUnroll; ++i) y[i] = 0.f;
     const float* w = win + r;
-    if (ENDS_ONLY || amp_mode == kAmpSilent) {
+    if constexpr (ENDS_ONLY) {
+      float y[kOscUnroll] = {0.f, 0.f, 0.f, 0.f};
       if (steady) osc_group_h<NC, true, kAmpSilent, STEP, false>(a, st, w, fr, y);
       else osc_group_h<NC, false, kAmpSilent, STEP, false>(a, st, w, fr, y);
-    } else if constexpr (!ENDS_ONLY) {
-      if (amp_mode == kAmpNoCheck) {
-        if (steady) osc_group_h<NC, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-        else osc_group_h<NC, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+    } else {
+      constexpr int NG = STEP / kOscUnroll;            // 4-sample groups per trip
+      float y[NG][kOscUnroll];
+      float f4[NG][kOscUnroll];
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int i = 0; i < kOscUnroll; ++i) { y[g][i] = 0.f; f4[g][i] = fr[4 * g + i]; }
+      if (amp_mode == kAmpSilent) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (steady) osc_group_h<NC, true, kAmpSilent, kOscUnroll, false>(a, st, w + 4 * g, f4[g], y[g]);
+          else osc_group_h<NC, false, kAmpSilent, kOscUnroll, false>(a, st, w + 4 * g, f4[g], y[g]);
+        }
+      } else if (amp_mode == kAmpNoCheck) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (steady) osc_group_h<NC, true, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w + 4 * g, f4[g], y[g]);
+          else osc_group_h<NC, false, kAmpNoCheck, kOscUnroll, PLAIN>(a, st, w + 4 * g, f4[g], y[g]);
+        }
       } else {
-        if (steady) osc_group_h<NC, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
-        else osc_group_h<NC, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w, fr, y);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (steady) osc_group_h<NC, true, kAmpCheck, kOscUnroll, PLAIN>(a, st, w + 4 * g, f4[g], y[g]);
+          else osc_group_h<NC, false, kAmpCheck, kOscUnroll, PLAIN>(a, st, w + 4 * g, f4[g], y[g]);
+        }
       }
-    }
-    if constexpr (!ENDS_ONLY) {
-      // park the group's partial sums (zeros for a silent group); every 8th group, and at the unit's end,
-      // the warp adds the tile's columns and writes up to 32 samples
-      const int gi = ((t - ts) >> 2) & 7;
-      *reinterpret_cast<float4*>(tile + lane * kRedPitch + 4 * gi) = make_float4(y[0], y[1], y[2], y[3]);
-      if (gi == 7 || t + kOscUnroll >= t1) flush_tile(tile, lane, 4 * (gi + 1), row_out + (t - t0) - 4 * gi);
+      // park the trip's partial sums (zeros for a silent one); every 32 samples, and at the unit's end, the
+      // warp adds the tile's columns and writes up to 32 samples
+      const int gi = ((t - ts) >> 2) & 7;              // first 4-sample group of the trip inside its 32-sample block
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        *reinterpret_cast<float4*>(tile + lane * kRedPitch + 4 * (gi + g)) =
+            make_float4(y[g][0], y[g][1], y[g][2], y[g][3]);
+      if (gi + NG == 8 || t + STEP >= t1) {
+        const int at = (t - t0) - 4 * gi;
+        if constexpr (LW < 16) flush_tile_units<16 / LW>(tile, lane, 4 * (gi + NG), *units, at);
+        else flush_tile(tile, lane, 4 * (gi + NG), row_out + at);
+      }
     }
   }
   if (ENDS_ONLY) {
@@ -659,26 +736,29 @@ __device__ __forceinline__ int list_append_slot(int* counter, bool active, int k
   return pos;
 }
 
+// Units per warp in the synthesis pass: buckets of few live half-groups run four (one half-group) or two
+// (two or three) units of the same chunk on one warp (osc_chunk_h, LW = 4 / 8).
+__host__ __device__ constexpr int synth_pack(int nh, int sp, bool plain) {
+  return (sp != 2 || plain) ? 1 : nh == 1 ? 4 : nh <= 3 ? 2 : 1;
+}
+
 __global__ void __launch_bounds__(256) additive_plan_kernel(
     const unsigned char* __restrict__ synth_na, const unsigned char* __restrict__ ends_na,
-    AdditivePlan* plan, int* __restrict__ lists, int n_units, int n_chunks, int B,
-    const PlanGroups groups, int carry_all, int n_sub) {
-  // lists: [kPlanSlots][kMaxGroups][n_units]
+    AdditivePlan* plan, int* __restrict__ lists, int* __restrict__ chunk_count, int n_units, int n_chunks,
+    int B, const PlanGroups groups, int carry_all, int n_sub) {
+  // lists: [kPlanSlots][kMaxGroups][n_units]; chunk_count: [kPlanSlots][kMaxGroups][n_chunks], zeroed
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = i < n_units;
   const int row = in_range ? i / n_chunks : 0, c = in_range ? i - row * n_chunks : 0;
   const int ns = in_range ? synth_na[i] : 0;
-  int slot = 0;
-  if (ns > 0) {
+  const int R = n_units / n_chunks;
+  if (ns > 0) {   // synthesis: rows grouped by chunk (threads of a warp have consecutive chunks: no contention)
     const int v = row / B;
     int g = 0;
     while (g + 1 < groups.n_groups && v >= groups.first_voice[g + 1]) ++g;
-    slot = 1 + g;
-  }
-  {
-    const int key = slot * kMaxGroups + ns - 1;
-    const int pos = list_append_slot(ns > 0 ? &plan->count[slot][ns - 1] : nullptr, ns > 0, key);
-    if (ns > 0) lists[(size_t)key * n_units + pos] = i;
+    const int key = (1 + g) * kMaxGroups + ns - 1;
+    const int j = atomicAdd(chunk_count + (size_t)key * n_chunks + c, 1);
+    lists[(size_t)key * n_units + (size_t)c * R + j] = row;
   }
   // pass 1 follows a half-group through chunk c if a later chunk needs its end phase (ends_na) or if
   // pass 2 enters this chunk at a sub-unit boundary (n_sub > 1: it needs the accumulator there)
@@ -692,6 +772,39 @@ __global__ void __launch_bounds__(256) additive_plan_kernel(
     const int key = ne - 1;
     const int pos = list_append_slot(ends ? &plan->count[0][ne - 1] : nullptr, ends, key);
     if (ends) lists[(size_t)key * n_units + pos] = i;
+  }
+}
+
+// Work items of the synthesis pass: chunk c of (slot, bucket) contributes ceil(count / pack) items; one
+// warp per (slot, bucket) scans the chunks and leaves the first item of every chunk in chunk_first and the
+// total in plan->count.  The order of the rows inside a chunk follows the atomics of the plan kernel; every
+// unit's output is computed independently of its partner, so the result does not depend on it.
+__global__ void __launch_bounds__(32) additive_plan_items_kernel(const int* __restrict__ chunk_count,
+                                                                 int* __restrict__ chunk_first,
+                                                                 AdditivePlan* plan, int n_chunks, int sp,
+                                                                 int plain) {
+  const int key = kMaxGroups + blockIdx.x;               // slots 1 .. kPlanSlots - 1
+  const int slot = key / kMaxGroups, b = key - slot * kMaxGroups;
+  const int pack = synth_pack(b + 1, sp, plain != 0);
+  const int lane = threadIdx.x;
+  const int* cnt = chunk_count + (size_t)key * n_chunks;
+  int* first = chunk_first + (size_t)key * (n_chunks + 1);
+  int base = 0;
+  for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+    const int c = c0 + lane;
+    const int items = c < n_chunks ? (cnt[c] + pack - 1) / pack : 0;
+    int incl = items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (c < n_chunks) first[c] = base + incl - items;
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    first[n_chunks] = base;
+    plan->count[slot][b] = base;
   }
 }
 
@@ -784,31 +897,57 @@ __host__ __device__ constexpr int synth_min_ctas(int chains) {
 }
 
 template <int NH, int SP, bool PLAIN>
-__global__ void __launch_bounds__(kSynthWarps * 32, synth_min_ctas(SP == 2 ? NH : (NH + 1) / 2) * 4 / kSynthWarps)
+__global__ void __launch_bounds__(kSynthWarps * 32,
+                                  synth_min_ctas(SP == 2 ? NH * synth_pack(NH, SP, PLAIN) : (NH + 1) / 2) * 4 / kSynthWarps)
 additive_synth_kernel(const AdditiveFastArgs fa) {
   const AdditiveArgs& a = fa.a;
   extern __shared__ __align__(16) float smem[];
   float* win = smem;                                   // [U] rising half of hann(2U)
   float* tile = smem + ((a.U + 3) & ~3) + (threadIdx.x >> 5) * kRedTileFloats;   // reduction tile of this warp
   const int lane = threadIdx.x & 31;
+  constexpr int PACK = synth_pack(NH, SP, PLAIN);                // units per warp
   const int sets = a.S / SP;
-  const int per_unit = sets * a.n_sub;                           // items per listed unit: (set, sub-unit)
-  const int n_items = fa.plan->count[fa.slot][NH - 1] * per_unit;
-  if ((int)blockIdx.x * kSynthWarps >= n_items) return;          // whole CTA has nothing to do
+  const int per_item = sets * a.n_sub;                           // warps per work item: (set, sub-unit)
+  const int n_warp_items = fa.plan->count[fa.slot][NH - 1] * per_item;
+  if ((int)blockIdx.x * kSynthWarps >= n_warp_items) return;     // whole CTA has nothing to do
   for (int i = threadIdx.x; i < a.U; i += blockDim.x) win[i] = a.window[i];
   __syncthreads();
-  const int item = blockIdx.x * kSynthWarps + (threadIdx.x >> 5);
-  if (item >= n_items) return;
-  const int n_units = a.P * a.B * a.n_chunks;
-  const int unit = fa.lists[(size_t)(fa.slot * kMaxGroups + NH - 1) * n_units + item / per_unit];
-  const int rem = item - (item / per_unit) * per_unit;
+  const int wi = blockIdx.x * kSynthWarps + (threadIdx.x >> 5);
+  if (wi >= n_warp_items) return;
+  const int item = wi / per_item, rem = wi - item * per_item;
   const int set = rem / a.n_sub, q = rem - set * a.n_sub;        // the sub-units of a chunk share a CTA
-  const int row = unit / a.n_chunks;
-  const int c = unit - row * a.n_chunks;
-  const int v = row / a.B, b = row - v * a.B;
-  float* out = a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
-  if constexpr (SP == 2) osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, out, tile);
-  else osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, q, lane, win, out, tile);
+  // chunk of the item: first[c] <= item < first[c + 1]
+  const int key = fa.slot * kMaxGroups + NH - 1;
+  const int* first = fa.chunk_first + (size_t)key * (a.n_chunks + 1);
+  int lo = 0, hi = a.n_chunks;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(first + mid) <= item) lo = mid; else hi = mid;
+  }
+  const int c = lo;
+  const int R = a.P * a.B, n_units = R * a.n_chunks;
+  const int j0 = (item - __ldg(first + c)) * PACK;
+  const int* rows = fa.lists + (size_t)key * n_units + (size_t)c * R;
+  const int row = rows[j0];
+  auto out_of = [&](int r) {
+    const int v = r / a.B, b = r - v * a.B;
+    return a.out + (((size_t)v * sets + set) * a.B + b) * a.N + (size_t)c * a.chunk;
+  };
+  if constexpr (SP == 2 && PACK > 1) {
+    const int n_here = __ldg(fa.chunk_count + (size_t)key * a.n_chunks + c);
+    WarpUnits units;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      units.row[u] = (u < PACK && j0 + u < n_here) ? rows[j0 + u] : -1;
+      units.out[u] = units.row[u] >= 0 ? out_of(units.row[u]) : nullptr;
+    }
+    osc_chunk_h<PACK * NH, 16 / PACK, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, nullptr, tile,
+                                                    &units);
+  } else if constexpr (SP == 2) {
+    osc_chunk_h<NH, 16, false, PLAIN>(a, fa.lerp, row, set * SP, c, q, lane, win, out_of(row), tile);
+  } else {
+    osc_chunk_h<(NH + 1) / 2, 32, false, PLAIN>(a, fa.lerp, row, set, c, q, lane, win, out_of(row), tile);
+  }
 }
 
 }  // namespace b200ddsp

@@ -464,6 +464,8 @@ struct AdditiveLayout {
   size_t lerp_sums;  // double [F + n_chunks * n_sub]  fast_phase: lerp sums per frame / up to every unit start
   size_t plan;       // AdditivePlan
   size_t lists;      // int [kPlanSlots][kMaxGroups][R * n_chunks]
+  size_t chunk_count; // int [kPlanSlots][kMaxGroups][n_chunks]      units per (slot, bucket, chunk)
+  size_t chunk_first; // int [kPlanSlots][kMaxGroups][n_chunks + 1]  first work item of every chunk
   size_t partials;   // float [n_partials, B, N]   partial signals for the mixer
   size_t end;
 };
@@ -491,8 +493,11 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
   a.ends_na = take(R * n_chunks);
   a.lerp = take(N * 4);
   a.lerp_sums = take(((size_t)F + n_chunks * n_sub) * 8);
-  a.plan = take(sizeof(AdditivePlan));
+  // plan and per-chunk unit counts are contiguous: one memset clears both
+  a.plan = take(align_up(sizeof(AdditivePlan)) + (size_t)kPlanSlots * kMaxGroups * n_chunks * 4);
+  a.chunk_count = a.plan + align_up(sizeof(AdditivePlan));
   a.lists = take((size_t)kPlanSlots * kMaxGroups * R * n_chunks * 4);
+  a.chunk_first = take((size_t)kPlanSlots * kMaxGroups * (n_chunks + 1) * 4);
   a.partials = take(max_partials(P, S) * B * N * 4);
   a.end = o;
   return a;
@@ -768,6 +773,8 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   r->fa.a = a;
   r->fa.plan = (AdditivePlan*)(base + lay.plan);
   r->fa.lists = (int*)(base + lay.lists);
+  r->fa.chunk_count = (int*)(base + lay.chunk_count);
+  r->fa.chunk_first = (int*)(base + lay.chunk_first);
   r->fa.lerp = (float*)(base + lay.lerp);
   r->fa.sp = substrings_per_pass(S);
   const size_t smem = (size_t)(((2 * U + 31) & ~31) + kAddWarps * kMaxChunk) * sizeof(float);
@@ -854,12 +861,16 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
           r.na_frame, r.synth_na, r.ends_na, r.F, a.U, a.N, a.chunk, r.n_chunks, a.koff,
           carry ? (r.H + 15) / 16 : 0);
       CHECK_LAUNCH_ON(h, "additive_alive_chunks_kernel", st);
-      CUDA_TRY(h, cudaMemsetAsync(r.fa.plan, 0, sizeof(AdditivePlan), st));
+      CUDA_TRY(h, cudaMemsetAsync(r.fa.plan, 0, align_up(sizeof(AdditivePlan)) +
+                                                    (size_t)kPlanSlots * kMaxGroups * r.n_chunks * 4, st));
       const int n_units = R * r.n_chunks;
       additive_plan_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(
-          r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, n_units, r.n_chunks, r.B, r.groups,
-          carry ? 1 : 0, a.n_sub);
+          r.synth_na, r.ends_na, r.fa.plan, (int*)r.fa.lists, (int*)r.fa.chunk_count, n_units, r.n_chunks, r.B,
+          r.groups, carry ? 1 : 0, a.n_sub);
       CHECK_LAUNCH_ON(h, "additive_plan_kernel", st);
+      additive_plan_items_kernel<<<(kPlanSlots - 1) * kMaxGroups, 32, 0, st>>>(
+          r.fa.chunk_count, (int*)r.fa.chunk_first, r.fa.plan, r.n_chunks, r.fa.sp, h->cfg.inference ? 0 : 1);
+      CHECK_LAUNCH_ON(h, "additive_plan_items_kernel", st);
     }
     if (small_kernels_done) {
       CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
