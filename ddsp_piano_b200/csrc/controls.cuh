@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
         sum += d[j];
       }
     }
-    if (!a.normalize_after) {                                        // :194-198
+    if (a.normalize_after == 0) {                                    // :194-198
       sum = warp_sum(sum);
       const float den = (sum == 0.f) ? 1e-7f : sum;
 #pragma unroll
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
         sum += d[j];
       }
     }
-    if (a.normalize_after) {                                         // :210-214
+    if (a.normalize_after == 1) {                                    // :210-214 (2: never normalised)
       sum = warp_sum(sum);
       const float den = (sum == 0.f) ? 1e-7f : sum;
 #pragma unroll

@@ -150,9 +150,13 @@ class SurrogateAdditive(InHarmonic):
         super().__init__(frame_rate=frame_rate, sample_rate=sample_rate, min_frequency=min_frequency,
                          scale_fn=scale_fn, normalize_after_nyquist_cut=True,
                          normalize_below_nyquist=normalize_below_nyquist, inference=inference, name=name)
-        if not normalize_harm_distribution:
-            raise ValueError('SurrogateAdditive(normalize_harm_distribution=False) is not implemented')
         self.normalize_harm_distribution = normalize_harm_distribution
+
+    def engine_config(self):
+        cfg = super().engine_config()
+        if not self.normalize_harm_distribution:               # surrogate_synth.py:183-187 skipped
+            cfg['normalize_after_nyquist_cut'] = 2
+        return cfg
 
     def get_controls(self, amplitudes, decays, decay_time, harmonic_distribution, inharm_coef, f0_hz):
         eng = self._engine(amplitudes, f0_hz)

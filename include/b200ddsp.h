@@ -62,7 +62,9 @@ typedef struct {
   int frame_rate;                  /* Hz, 250 */
   float min_frequency;             /* 20: voices with f0 <= this are muted (inharm_synth.py:207-208) */
   int additive_scale_fn;           /* b200ddsp_scale_fn */
-  int normalize_after_nyquist_cut; /* inharm_synth.py:210-214 (default 1) */
+  int normalize_after_nyquist_cut; /* inharm_synth.py:210-214 (default 1); 0: normalise BEFORE the cut instead
+                                      (:194-198); 2: never (SurrogateAdditive(normalize_harm_distribution=
+                                      False), modules/surrogate_synth.py:183-187) */
   int normalize_below_nyquist;     /* inharm_synth.py:200-208 (default 1) */
   int inference;                   /* 1: ddsp angular_cumsum (chunks of 1000); 0: plain cumsum over the
                                       clip (inharm_synth.py:73-77), one serial float32 chain per

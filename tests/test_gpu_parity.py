@@ -185,6 +185,17 @@ def test_surrogate_additive_golden(dp, dev, golden_dir, name):
     assert rel_err(plain, want) < TIGHT
     with pytest.raises(ValueError):
         dp.SurrogateAdditive(sample_rate=int(g['sample_rate']), inference=False)(*args)
+    # normalize_harm_distribution=False (surrogate_synth.py:183-187 skipped): against the oracle
+    raw = {k: g['in_' + k] for k in ('amplitudes', 'decays', 'decay_time', 'harmonic_distribution', 'inharm_coef',
+                                     'f0_hz')}
+    want_ctl = ref.surrogate_controls(**raw, sample_rate=int(g['sample_rate']), normalize_harm_distribution=False)
+    want_sig = ref.surrogate_signal(**want_ctl, sample_rate=int(g['sample_rate']), inference=True)
+    free = dp.SurrogateAdditive(frame_rate=250, sample_rate=int(g['sample_rate']), inference=True,
+                                normalize_harm_distribution=False, name='inharmonic')
+    out2 = free(*args, return_outputs_dict=True)
+    assert rel_err(out2['controls']['harmonic_distribution'], want_ctl['harmonic_distribution']) < 2e-6
+    assert float(out2['controls']['harmonic_distribution'].sum(-1).max()) > 1.5      # really not normalised
+    assert rel_err(out2['signal'], want_sig) < TIGHT
 
 
 @pytest.mark.parametrize('sr,F,B,H,S', [(24000, 750, 2, 96, 2), (48000, 250, 1, 128, 2), (24000, 300, 2, 128, 1)])
