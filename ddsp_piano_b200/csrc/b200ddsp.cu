@@ -158,10 +158,12 @@ static std::vector<float> hann_periodic(int n) {
 //        = hann[i]/Lir * ( m_0 + (-1)^(i+M-1) m_{M-1} + 2 sum_{j=1}^{M-2} (-1)^j m_j cos(2 pi j i / Lir) )
 // (ddsp.core.frequency_impulse_response + apply_window_to_impulse_response, window_size >= Lir).
 // window_size < Lir would crop the IR; the reference never configures that (window_size = 257).
+static int cmat_pitch_for(int M) { return (M - 1 + 7) & ~7; }   // rows padded for 16-byte loads
+
 static std::vector<float> noise_ir_matrix_t(int M) {
-  const int lir = 2 * (M - 1), nd = M - 1;
+  const int lir = 2 * (M - 1), nd = M - 1, pitch = cmat_pitch_for(M);
   std::vector<float> hann = hann_periodic(lir);
-  std::vector<float> c((size_t)M * nd);
+  std::vector<float> c((size_t)M * pitch, 0.f);
   for (int d = 0; d < nd; ++d) {
     const int i = M - 1 + d;
     const double wgt = (double)hann[i] / (double)lir;
@@ -175,7 +177,7 @@ static std::vector<float> noise_ir_matrix_t(int M) {
         const long long ji = ((long long)j * i) % lir;
         coef = 2.0 * ((j & 1) ? -1.0 : 1.0) * cos(2.0 * M_PI * (double)ji / (double)lir);
       }
-      c[(size_t)j * nd + d] = (float)(wgt * coef);
+      c[(size_t)j * pitch + d] = (float)(wgt * coef);
     }
   }
   return c;
@@ -1112,6 +1114,7 @@ static int run_noise_voices(b200ddsp_handle* h, int scale_fn, const NoiseVoicePt
   StageTimer tm(h, B200DDSP_STAGE_NOISE, st);
   NoiseArgs a{};
   a.cmat_t = h->d_cmat_t;
+  a.cmat_pitch = cmat_pitch_for(M);
   a.out = noise_part;
   a.v_begin = v0;
   a.v_end = v1;

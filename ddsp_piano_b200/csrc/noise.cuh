@@ -20,7 +20,7 @@
 //    scale    FilteredNoise.get_controls, scale_fn(m + bias), both voices interleaved (m_v0, m_v1);
 //    taps     c_k = Cmat x m_k: the inverse real DFT and the window folded into one [M x M-1] matrix
 //             (built once in create()); the filter is symmetric about tap M-1, so only taps
-//             M-1 .. 2M-3 are computed and mirrored into shared memory;
+//             M-1 .. 2M-3 are computed and mirrored into shared memory; thread = 4 frames x 4 taps;
 //    noise    Philox4x32-10 (or the injected tensor of the parity tests), interleaved like the taps;
 //    FIR      lanes are FRAMES (shared-memory pitches = 4 mod 32 words make the frame-strided 128-bit
 //             accesses conflict free); a thread owns 8 consecutive outputs of its frame and slides a
@@ -43,7 +43,8 @@ struct NoiseVoicePtrs {
 };
 
 struct NoiseArgs {
-  const float* cmat_t;   // [M][M-1] taps matrix
+  const float* cmat_t;   // [M][cmat_pitch] taps matrix, rows padded to a multiple of 8 with zeros
+  int cmat_pitch;
   float* out;            // [n_slices, B, N] noise of each voice slice
   int v_begin, v_end;    // voices handled by this launch, split evenly over gridDim.z slices
   int slice0;            // index of the launch's first slice in `out`
@@ -68,9 +69,10 @@ struct NoiseSmemLayout {
   int n_in;       // input frames held: kNoiseFrames + halo_before + halo_after
   int pitch_x;    // float2 per row, >= U;                   2 * pitch_x = 4 (mod 32) words
   int pitch_c;    // float2 per row, >= Lir + 2*kTapPad + 2; 2 * pitch_c = 4 (mod 32) words
+  int pitch_f;    // frames per band row of the scaled magnitudes: n_in rounded up to 4
   int tap_shift;  // 0..1: makes the register-window loads 16-byte aligned
   int off_raw;    // [2][n_in][M] raw magnitudes of the voice pair (bulk-copy destination)
-  int off_m;      // [n_in][M] float2 scaled magnitudes
+  int off_m;      // [M][pitch_f] float2 scaled magnitudes, band-major: 4 frames of a band = 32 contiguous bytes
   int off_x;      // [n_in][pitch_x] float2 noise
   int off_c;      // [n_in][pitch_c] float2 taps
   int off_bar;    // mbarrier (8 bytes)
@@ -84,7 +86,8 @@ struct NoiseSmemLayout {
     tap_shift = (kTapPad + start - 7) & 1;
     off_raw = 0;
     off_m = (2 * n_in * M + 31) & ~31;
-    off_x = off_m + ((2 * n_in * M + 31) & ~31);
+    pitch_f = (n_in + 3) & ~3;
+    off_x = off_m + ((2 * M * pitch_f + 31) & ~31);
     off_c = off_x + ((2 * n_in * pitch_x + 31) & ~31);
     off_bar = off_c + 2 * n_in * pitch_c;
     total_floats = off_bar + 4;
@@ -146,7 +149,7 @@ noise_synth_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
   extern __shared__ __align__(16) float smem[];
   const NoiseSmemLayout L(a.M, a.U, a.halo_before, a.halo_after);
   float* raw = smem + L.off_raw;                              // [2][n_in][M]
-  float2* ms = reinterpret_cast<float2*>(smem + L.off_m);     // [n_in][M]  scaled magnitudes of both voices
+  float2* ms = reinterpret_cast<float2*>(smem + L.off_m);     // [M][pitch_f]  scaled magnitudes of both voices
   float2* xs = reinterpret_cast<float2*>(smem + L.off_x);     // [n_in][pitch_x]  noise of both voices
   float2* cs = reinterpret_cast<float2*>(smem + L.off_c);     // [n_in][pitch_c]  zero-padded taps of both
   void* bar = smem + L.off_bar;
@@ -236,72 +239,101 @@ noise_synth_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
           raw[(e * L.n_in + (k_lo - k_first)) * M + i] = __ldg(vp.mags[v + e] + ((size_t)b * a.F + k_lo) * M + i);
       __syncthreads();
     }
-    // ---- scale (FilteredNoise.get_controls), interleave the two voices: a warp per frame ------------
-    for (int fi = warp; fi < L.n_in; fi += n_warps) {
+    // ---- scale (FilteredNoise.get_controls), interleave the two voices, transpose to band-major:
+    //      consecutive lanes take consecutive frames (reads at stride M words, M odd: no bank conflict)
+    for (int i = threadIdx.x; i < M * L.pitch_f; i += n_threads) {
+      const int j = i / L.pitch_f, fi = i - j * L.pitch_f;
       const int k = k_first + fi;
-      const bool in = k >= k_lo && k < k_hi;
-      for (int j = lane; j < M; j += 32) {
-        float2 m = make_float2(0.f, 0.f);
-        if (in) {
-          m.x = raw[fi * M + j];
-          if (have1) m.y = raw[(L.n_in + fi) * M + j];
-          if (a.scale_fn != 2) {
-            m.x = apply_scale_fn(__fadd_rn(m.x, a.bias), a.scale_fn);
-            if (have1) m.y = apply_scale_fn(__fadd_rn(m.y, a.bias), a.scale_fn);
-          }
+      float2 m = make_float2(0.f, 0.f);
+      if (fi < L.n_in && k >= k_lo && k < k_hi) {
+        m.x = raw[fi * M + j];
+        if (have1) m.y = raw[(L.n_in + fi) * M + j];
+        if (a.scale_fn != 2) {
+          m.x = apply_scale_fn(__fadd_rn(m.x, a.bias), a.scale_fn);
+          if (have1) m.y = apply_scale_fn(__fadd_rn(m.y, a.bias), a.scale_fn);
         }
-        ms[fi * M + j] = m;
       }
+      ms[i] = m;
     }
     __syncthreads();   // scaled magnitudes complete; the raw buffer is free again
     if (a.bulk && threadIdx.x == 0 && v + 2 < v_hi && k_hi > k_lo) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async writes
       start_loads(v + 2);
     }
-    // ---- taps: c[fi][d] = sum_k Cmat[k][d] * m[fi][k] for both voices.  Thread = (tap d, frame group g):
-    //      it owns tap d of frames g, g + G, .., 6 at a time; per pair of bands it reads 2 matrix entries
-    //      (coalesced over d, L1 resident) and one 16-byte broadcast per frame for 12 FFMA2.
+    // ---- taps: c[fi][d] = sum_k Cmat[k][d] * m[fi][k] for both voices.  Thread = 4 frames x 4 taps
+    //      (16 FFMA2 per band); per band it reads its 4 frames' magnitude pairs (32 contiguous bytes, shared by
+    //      the half warp) and 4 matrix entries (16 bytes of the padded, L1-resident table): 4 shared-memory/L1
+    //      wavefronts per 32 issue cycles of FFMA2.  The first version (a thread per tap over 6 frames) needed 4
+    //      wavefronts per 12 cycles on every one of the 4 schedulers -- more than the one L1 data path delivers
+    //      -- and spent 40 % of the kernel here.  Operands of band k+1 are loaded under the FMAs of band k.
     {
-      const int nd = M - 1;
-      const int dcols = min((nd + 31) & ~31, n_threads);   // taps per pass, whole warps
-      const int G = n_threads / dcols;                 // frame groups
-      const int g = threadIdx.x / dcols;
-      for (int d = threadIdx.x % dcols; d < nd && g < G; d += dcols) {
-        const float* cd = a.cmat_t + d;
-        for (int f0 = g; f0 < L.n_in; f0 += 6 * G) {
-          int off[6];                                  // row offsets; frames past the end repeat the last one
+      const int nd = M - 1, tgs = a.cmat_pitch / 4, fgs = L.n_in / 4, mstep = L.pitch_f / 2;
+      const int n_tiles = tgs * fgs;
+      for (int w = threadIdx.x; w < n_tiles; w += n_threads) {
+        const int fg = w / tgs, tg = w - fg * tgs;
+        const float4* mcol = reinterpret_cast<const float4*>(ms + 4 * fg);
+        const float4* ccol = reinterpret_cast<const float4*>(a.cmat_t) + tg;
+        float2 acc[4][4];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) off[i] = min(f0 + i * G, L.n_in - 1) * M;
-          float2 c6[6];
+        for (int f = 0; f < 4; ++f)
 #pragma unroll
-          for (int i = 0; i < 6; ++i) c6[i] = make_float2(0.f, 0.f);
-          if ((M & 1) == 0) {
-#pragma unroll 4
-            for (int k = 0; k < M; k += 2) {
-              const float ca = __ldg(cd + (size_t)k * nd), cb = __ldg(cd + (size_t)(k + 1) * nd);
+          for (int t = 0; t < 4; ++t) acc[f][t] = make_float2(0.f, 0.f);
+        auto band = [&](const float4& p01, const float4& p23, const float4& pc) {
+          const float2 mf[4] = {make_float2(p01.x, p01.y), make_float2(p01.z, p01.w),
+                                make_float2(p23.x, p23.y), make_float2(p23.z, p23.w)};
+          const float ct[4] = {pc.x, pc.y, pc.z, pc.w};
 #pragma unroll
-              for (int i = 0; i < 6; ++i) {
-                const float4 m4 = *reinterpret_cast<const float4*>(ms + off[i] + k);
-                c6[i] = __ffma2_rn(make_float2(ca, ca), make_float2(m4.x, m4.y), c6[i]);
-                c6[i] = __ffma2_rn(make_float2(cb, cb), make_float2(m4.z, m4.w), c6[i]);
-              }
-            }
-          } else {
-            for (int k = 0; k < M; ++k) {
-              const float ca = __ldg(cd + (size_t)k * nd);
+          for (int f = 0; f < 4; ++f)
 #pragma unroll
-              for (int i = 0; i < 6; ++i) c6[i] = __ffma2_rn(make_float2(ca, ca), ms[off[i] + k], c6[i]);
+            for (int t = 0; t < 4; ++t) acc[f][t] = __ffma2_rn(make_float2(ct[t], ct[t]), mf[f], acc[f][t]);
+        };
+        float4 a01 = mcol[0], a23 = mcol[1], ac = __ldg(ccol);      // two operand sets, rotated by name
+        int k = 0;
+#pragma unroll 1
+        for (; k + 2 <= M; k += 2) {
+          const float4 b01 = mcol[mstep], b23 = mcol[mstep + 1], bc = __ldg(ccol + tgs);
+          band(a01, a23, ac);
+          mcol += 2 * mstep;
+          ccol += 2 * tgs;
+          if (k + 2 < M) {
+            a01 = mcol[0];
+            a23 = mcol[1];
+            ac = __ldg(ccol);
+          }
+          band(b01, b23, bc);
+        }
+        if (k < M) band(a01, a23, ac);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          float2* row = cs + (4 * fg + f) * L.pitch_c + tap0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int d = 4 * tg + t;
+            if (d < nd) {
+              row[M - 1 + d] = acc[f][t];
+              if (d > 0) row[M - 1 - d] = acc[f][t];       // linear phase: symmetric about tap M-1
             }
           }
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int fi = f0 + i * G;
-            if (fi < L.n_in) {
-              float2* row = cs + fi * L.pitch_c + tap0;
-              row[M - 1 + d] = c6[i];
-              if (d > 0) row[M - 1 - d] = c6[i];       // linear phase: symmetric about tap M-1
-            }
-          }
+        }
+      }
+      // the n_in % 4 frames left over (the halo makes n_in = 34): one output per thread, on the warps after
+      // the tiles' so that each scheduler gets one tile warp and one of these
+      const int f_rest = 4 * fgs, n_rest = (L.n_in - f_rest) * a.cmat_pitch;
+      const int t0 = ((n_tiles + 31) & ~31) % n_threads;
+      for (int w = (threadIdx.x - t0 + n_threads) % n_threads; w < n_rest; w += n_threads) {
+        const int fr = w / a.cmat_pitch, d = w - fr * a.cmat_pitch;
+        const float2* mcol = ms + f_rest + fr;
+        const float* ccol = a.cmat_t + d;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 5
+        for (int k = 0; k < M; ++k) {
+          const float c = __ldg(ccol + k * a.cmat_pitch);
+          acc = __ffma2_rn(make_float2(c, c), mcol[k * L.pitch_f], acc);
+        }
+        if (d < nd) {
+          float2* row = cs + (f_rest + fr) * L.pitch_c + tap0;
+          row[M - 1 + d] = acc;
+          if (d > 0) row[M - 1 - d] = acc;
         }
       }
     }
