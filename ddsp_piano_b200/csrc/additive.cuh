@@ -52,6 +52,7 @@ struct AdditiveArgs {
   int koff;             // input frame of output sample 0 (spans: halo frames in front; else 0)
   int seeded;           // chunk 0 has an offset too (a span that continues a timeline)
   int accumulate;       // out += (only honoured when gridDim.z == 1)
+  int plain;            // generic kernel, inference = 0: one plain cumsum over the clip (chunk = N), no wrap
   float scale;          // float32(F) / float32(N)
   float nyquist;        // float32(sr / 2)
   float sr;             // float32(sr)
@@ -240,8 +241,9 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
                 float amp = __fmaf_rn(cur.A[q], w1, __fmul_rn(nxt.A[q], w0));
                 if (surrogate) amp = __fmul_rn(amp, powf(D[q], __fadd_rn(T0, (float)(r + j))));
                 amp = (f >= a.nyquist) ? 0.f : amp;                    // :65-67
-                const float p = wrap_to_pi(__fadd_rn(ph[q], off[q]));
-                y[gi * G + j] = __fmaf_rn(amp, __cosf(p), y[gi * G + j]);   // :80-83
+                const float cv = a.plain ? cos_large(ph[q])                     // tf.cos(tf.cumsum), :76-77
+                                         : __cosf(wrap_to_pi(__fadd_rn(ph[q], off[q])));
+                y[gi * G + j] = __fmaf_rn(amp, cv, y[gi * G + j]);              // :80-83
               }
             }
             tf += 1.0f;
@@ -252,7 +254,13 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
       }
       if (!ENDS_ONLY) {
         const float ysum = transpose_reduce32(y, lane);
-        rows[warp * kMaxChunk + pos + lane] += ysum;   // pos + lane < kMaxChunk always
+        if (a.plain) {
+          // one "chunk" = the whole clip: no staging row; the (voice, substring) warps add straight into the
+          // zeroed output (float atomics: the order of the voices is not fixed in this mode)
+          if (t0 + pos + lane < t1) atomicAdd(a.out + ((size_t)g * a.B + b) * a.N + t0 + pos + lane, ysum);
+        } else {
+          rows[warp * kMaxChunk + pos + lane] += ysum;   // pos + lane < kMaxChunk always
+        }
       }
       pos += 32;
     }
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
     }
   }
 
-  if (!ENDS_ONLY) {
+  if (!ENDS_ONLY && !a.plain) {
     __syncthreads();
     float* out = a.out + ((size_t)g * a.B + b) * a.N + t0;
     const int len = t1 - t0;

@@ -135,14 +135,6 @@ constexpr int kOscUnroll = 4;   // samples per unrolled body of the synthesis pa
 #endif
 constexpr int kSynthStep = B200DDSP_SYNTH_STEP;   // samples per loop trip of the synthesis pass (4 or 8)
 
-// cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
-// reduce modulo the true 2 pi in double precision, then the hardware cosine.
-__device__ __forceinline__ float cos_large(float x) {
-  const double xd = (double)x;
-  const double n = rint(xd * 0.15915494309189535);
-  return __cosf((float)fma(-n, 6.283185307179586, xd));
-}
-
 // Rows and outputs of the units that share a warp in the synthesis pass (osc_chunk_h, LW < 16); row < 0: none.
 struct WarpUnits {
   int row[4];

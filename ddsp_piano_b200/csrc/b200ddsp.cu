@@ -733,10 +733,6 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
                 "legacy-bilinear source frame departs from t/U by more than one frame (F=%d N=%d)",
                 F, N);
   r->n_chunks = n_chunks_for(h, N);
-  if (!r->fast && !h->cfg.inference)
-    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
-                "inference=0 (plain cumsum) is implemented on the fast additive path only "
-                "(U %% 8 == 0, H <= 128); got U=%d H=%d", U, H);
   if (r->n_chunks > 12 * 1024)
     return fail(h, B200DDSP_BAD_SHAPE, "timeline of %d chunks is too long for one call", r->n_chunks);
   r->P = P; r->B = B; r->F = F; r->H = H; r->S = S;
@@ -766,6 +762,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   a.koff = span ? span->koff : 0;
   a.seeded = (span && span->seeded) ? 1 : 0;
   a.accumulate = 0;
+  a.plain = (!r->fast && !h->cfg.inference) ? 1 : 0;
   a.scale = (float)F_all / (float)N_all;
   a.nyquist = (float)(h->cfg.sample_rate / 2.0);
   a.sr = (float)h->cfg.sample_rate;
@@ -994,6 +991,8 @@ static int additive_synth_group(b200ddsp_handle* h, AdditiveRun& r, int g, cudaS
   const int G = (r.groups.n_groups == 1) ? r.G : 1;
   a.voices_per_group = (Pg + G - 1) / G;
   a.out = r.partials + (size_t)(r.groups.n_groups == 1 ? 0 : g) * r.B * r.a.N;
+  if (a.plain && !a.accumulate)   // the plain-cumsum kernel adds into its output (additive.cuh)
+    CUDA_TRY(h, cudaMemsetAsync(a.out, 0, (size_t)G * r.B * r.a.N * sizeof(float), st));
   launch_additive_generic(a, false, dim3(r.n_chunks, r.B, G), st);
   CHECK_LAUNCH_ON(h, "additive_kernel<synth>", st);
   return B200DDSP_OK;
@@ -1063,9 +1062,6 @@ extern "C" int b200ddsp_surrogate_signal(b200ddsp_handle* h, const float* amplit
                                          void* stream) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
   if (!decays || !decay_time) return fail(h, B200DDSP_BAD_ARGUMENT, "null decay tensor");
-  if (!h->cfg.inference)
-    return fail(h, B200DDSP_UNSUPPORTED_CONFIG,
-                "SurrogateAdditive is implemented for inference=1 (angular cumsum) only");
   return additive_signal_impl(h, amplitudes, harmonic_distribution, harmonic_shifts, f0_hz, decays,
                               decay_time, out, B, F, H, 1, 0, workspace, workspace_bytes, stream);
 }

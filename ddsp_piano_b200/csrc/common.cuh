@@ -35,6 +35,14 @@ __device__ __forceinline__ float floormod_two_pi(float x) {
   return (m != 0.f && m < 0.f) ? __fadd_rn(m, kTwoPi) : m;
 }
 
+// cos of a float32 phase of any magnitude (inference=False: the plain cumsum reaches 1e5 rad):
+// reduce modulo the true 2 pi in double precision, then the hardware cosine.
+__device__ __forceinline__ float cos_large(float x) {
+  const double xd = (double)x;
+  const double n = rint(xd * 0.15915494309189535);
+  return __cosf((float)fma(-n, 6.283185307179586, xd));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -141,8 +141,8 @@ class InHarmonic(Processor):
 class SurrogateAdditive(InHarmonic):
     """modules/surrogate_synth.py:107-214 (configs/surrogate.gin): the inharmonic bank of one string
     with exponentially decaying partial amplitudes, ``|decays| ** (decay_time * U + r)`` per sample
-    (B. Hayes, sinusoidal frequency estimation by gradient descent).  Forward only, ``inference=True``
-    (angular cumsum); it runs on the generic oscillator kernel."""
+    (B. Hayes, sinusoidal frequency estimation by gradient descent).  Forward only (both cumsum modes of
+    ``inference``); it runs on the generic oscillator kernel."""
 
     def __init__(self, frame_rate=250, sample_rate=16000, min_frequency=20,
                  normalize_harm_distribution=True, scale_fn=exp_sigmoid, normalize_below_nyquist=True,

@@ -68,7 +68,7 @@ typedef struct {
   int normalize_below_nyquist;     /* inharm_synth.py:200-208 (default 1) */
   int inference;                   /* 1: ddsp angular_cumsum (chunks of 1000); 0: plain cumsum over the
                                       clip (inharm_synth.py:73-77), one serial float32 chain per
-                                      oscillator -- fast additive path only (U % 8 == 0, H <= 128) */
+                                      oscillator (whole clips only, no spans) */
   int noise_scale_fn;              /* b200ddsp_scale_fn (FilteredNoise.scale_fn) */
   float noise_initial_bias;        /* -5.0 */
   int noise_window_size;           /* 257 */
@@ -180,7 +180,7 @@ int b200ddsp_ir_decay_mask(b200ddsp_handle* h, const float* ir, float* out, int 
  * b200ddsp_additive_controls with S = 1 (no pre-normalisation) for amplitudes / harmonic_distribution /
  * harmonic_shifts, plus b200ddsp_surrogate_decays (clip to [1e-5, 1], 1 above Nyquist, :163-171);
  * get_signal = b200ddsp_surrogate_signal (decays [B, F, H], decay_time [B, F, 1]; workspace of
- * b200ddsp_additive_workspace_bytes(h, B, F, H, 1)).  inference = 1 only. */
+ * b200ddsp_additive_workspace_bytes(h, B, F, H, 1)).  Both inference modes (:212). */
 int b200ddsp_surrogate_decays(b200ddsp_handle* h, const float* decays, const float* inharm_coef,
                               const float* f0_hz, float* decays_out, int B, int F, int H, void* stream);
 int b200ddsp_surrogate_signal(b200ddsp_handle* h, const float* amplitudes, const float* decays,

@@ -183,8 +183,13 @@ def test_surrogate_additive_golden(dp, dev, golden_dir, name):
                                g['ctl_harmonic_shifts'], g['ctl_f0_hz'],
                                sample_rate=int(g['sample_rate']), inference=True)
     assert rel_err(plain, want) < TIGHT
-    with pytest.raises(ValueError):
-        dp.SurrogateAdditive(sample_rate=int(g['sample_rate']), inference=False)(*args)
+    # inference=False (the class default, surrogate_synth.py:122,212): tf.cumsum instead of angular_cumsum
+    want_tr = ref.surrogate_signal(**{k[4:]: g[k] for k in ('ctl_amplitudes', 'ctl_decays', 'ctl_decay_time',
+                                                            'ctl_harmonic_distribution', 'ctl_harmonic_shifts',
+                                                            'ctl_f0_hz')},
+                                   sample_rate=int(g['sample_rate']), inference=False)
+    got_tr = dp.SurrogateAdditive(frame_rate=250, sample_rate=int(g['sample_rate']), inference=False)(*args)
+    assert rel_err(got_tr, want_tr) < TIGHT
     # normalize_harm_distribution=False (surrogate_synth.py:183-187 skipped): against the oracle
     raw = {k: g['in_' + k] for k in ('amplitudes', 'decays', 'decay_time', 'harmonic_distribution', 'inharm_coef',
                                      'f0_hz')}
@@ -554,6 +559,23 @@ def test_additive_training_mode_vs_oracle_long(dp, dev):
         cu(x['amplitudes'], dev), cu(x['harmonic_distribution'], dev),
         cu(x['inharm_coef'], dev), cu(x['f0_hz'], dev))
     assert rel_err(other, want) > 1e-3
+
+
+@pytest.mark.parametrize('sr,F,B,H,S', [(25000, 250, 2, 64, 2),      # U = 100: generic kernel (U % 8 != 0)
+                                        (32000, 125, 1, 192, 1)])     # H > 128: generic kernel
+def test_additive_training_mode_on_the_generic_kernel(dp, dev, sr, F, B, H, S):
+    """inference=False (inharm_synth.py:76-77) on shapes the fast path does not take: one plain cumsum over
+    the clip in the generic kernel, phases up to 1e5 rad."""
+    x = voice_inputs(np.random.default_rng(sr + F), B, F, H, S, 8)
+    ctl = ref.additive_controls(x['amplitudes'], x['harmonic_distribution'], x['inharm_coef'], x['f0_hz'],
+                                sample_rate=sr)
+    want = ref.additive_signal(**ctl, sample_rate=sr, inference=False)
+    args = [cu(x[k], dev) for k in ('amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz')]
+    got = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=False, name='additive')(*args)
+    assert rel_err(got, want) < TIGHT
+    other = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, name='additive')(*args)
+    assert rel_err(other, want) > 1e-3                       # the knob really changes the algorithm
+    assert rel_err(other, ref.additive_signal(**ctl, sample_rate=sr, inference=True)) < TIGHT
 
 
 def test_config1_shapes_four_notes_real_ir(dp, dev, golden_dir):
