@@ -162,7 +162,7 @@ def load():
     lib.b200ddsp_fft_convolve.restype = ci
     lib.b200ddsp_fft_convolve.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     lib.b200ddsp_fdn_ir.restype = ci
-    lib.b200ddsp_fdn_ir.argtypes = [vp] + [vp] * 7 + [ci, c_float_p, ctypes.c_float, vp, ci, vp, sz, vp]
+    lib.b200ddsp_fdn_ir.argtypes = [vp] + [vp] * 7 + [ci, c_float_p, ci, ctypes.c_float, vp, ci, vp, sz, vp]
     lib.b200ddsp_fdn_workspace_bytes.restype = sz
     lib.b200ddsp_fdn_workspace_bytes.argtypes = [vp, ctypes.c_float, ci]
     lib.b200ddsp_forward_polyphonic.restype = ci

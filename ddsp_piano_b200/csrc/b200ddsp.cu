@@ -1664,9 +1664,14 @@ extern "C" int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, cons
                                const float* gain_allpass, const float* delays_allpass,
                                const float* time_rev_0_sec, const float* alpha_tone,
                                const float* early_ir, int E, const float* delay_values,
-                               float sampling_rate, float* ir_out, int B, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int delay_lines, float sampling_rate, float* ir_out, int B,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return B200DDSP_BAD_ARGUMENT;
+  if (delay_lines != 6 && delay_lines != 8)
+    return fail(h, B200DDSP_UNSUPPORTED_CONFIG, "delay_lines=%d: the network is built for 8 lines "
+                "(fdn_reverb.py:30) or 6 (configs/ENSTDkCl-*.gin)", delay_lines);
+  if (delay_lines != 8 && !delay_values)
+    return fail(h, B200DDSP_BAD_ARGUMENT, "delay_values are required when delay_lines != 8");
   if (!input_gain || !output_gain || !gain_allpass || !delays_allpass || !time_rev_0_sec || !alpha_tone ||
       !ir_out || (E > 0 && !early_ir))
     return fail(h, B200DDSP_BAD_ARGUMENT, "null tensor pointer");
@@ -1688,11 +1693,12 @@ extern "C" int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, cons
   a.early_ir = early_ir;
   a.H = (float2*)workspace;
   a.ir = ir_out;
-  for (int d = 0; d < kFdnLines; ++d) a.delay_values[d] = delay_values ? delay_values[d] : kDefaultDelays[d];
+  for (int d = 0; d < delay_lines; ++d) a.delay_values[d] = delay_values ? delay_values[d] : kDefaultDelays[d];
   a.sampling_rate = sampling_rate;
   a.n = n; a.E = E < n ? E : n; a.B = B;
   cudaStream_t st = (cudaStream_t)stream;
-  fdn_transfer_kernel<<<dim3((n / 2 + 1 + 127) / 128, B), 128, 0, st>>>(a);
+  if (delay_lines == 8) fdn_transfer_kernel<8><<<dim3((n / 2 + 1 + 127) / 128, B), 128, 0, st>>>(a);
+  else fdn_transfer_kernel<6><<<dim3((n / 2 + 1 + 127) / 128, B), 128, 0, st>>>(a);
   CHECK_LAUNCH(h, "fdn_transfer_kernel");
   fdn_irfft_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(a);
   CHECK_LAUNCH(h, "fdn_irfft_kernel");

@@ -5,7 +5,7 @@
 // The network (8 delay lines, Householder mixing, one-pole reverberation-time control, four
 // Schroeder allpasses per line) is sampled on n/2+1 frequencies, n = 2 * sampling_rate:
 //     H[k] = c^T D_k (I - F_k D_k)^-1 b ,      late_ir = irfft(H) ,      ir = early_ir + late_ir
-// fdn_transfer_kernel  one thread per (frequency bin, batch row): builds the 8x8 complex system
+// fdn_transfer_kernel  one thread per (frequency bin, batch row): builds the lines x lines complex system
 //                      in float32 complex arithmetic and solves it by Gaussian elimination with
 //                      partial pivoting.  Phase angles are formed exactly as the reference forms
 //                      them -- float32 w_k = (2pi * k) / n, float32 product w_k * delay -- because
@@ -19,14 +19,14 @@
 
 namespace b200ddsp {
 
-constexpr int kFdnLines = 8;
+constexpr int kFdnLines = 8;        // at most; the kernel is instantiated for 6 (configs/ENSTDkCl-*.gin) and 8
 constexpr int kFdnAllpass = 4;
 
 struct FdnArgs {
-  const float* input_gain;      // [B, 8]
-  const float* output_gain;     // [B, 8]
-  const float* gain_allpass;    // [B, 8, 4]
-  const float* delays_allpass;  // [B, 8, 4]
+  const float* input_gain;      // [B, lines]
+  const float* output_gain;     // [B, lines]
+  const float* gain_allpass;    // [B, lines, 4]
+  const float* delays_allpass;  // [B, lines, 4]
   const float* time_rev_0_sec;  // [B]
   const float* alpha_tone;      // [B]
   const float* early_ir;        // [B, E]
@@ -50,6 +50,7 @@ __device__ __forceinline__ float2 c_expi(float theta) {   // exp(i theta), accur
   return make_float2(c, s);
 }
 
+template <int NL>
 __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
   const int nb = a.n / 2 + 1;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,9 +62,9 @@ __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
   const float t0 = a.time_rev_0_sec[b];
   const float at0 = __fmul_rn(a.alpha_tone[b], t0);
 
-  float2 D[kFdnLines], lowpass[kFdnLines], allpass[kFdnLines];
+  float2 D[NL], lowpass[NL], allpass[NL];
 #pragma unroll
-  for (int d = 0; d < kFdnLines; ++d) {
+  for (int d = 0; d < NL; ++d) {
     const float dv = a.delay_values[d];
     const float whole = floorf(dv);
     // integer delay + first-order allpass interpolation of the fractional part   (:241-262)
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
     float2 ap = make_float2(1.f, 0.f);
 #pragma unroll
     for (int j = 0; j < kFdnAllpass; ++j) {
-      const float da = a.delays_allpass[((size_t)b * kFdnLines + d) * kFdnAllpass + j];
-      const float ga = a.gain_allpass[((size_t)b * kFdnLines + d) * kFdnAllpass + j];
+      const float da = a.delays_allpass[((size_t)b * NL + d) * kFdnAllpass + j];
+      const float ga = a.gain_allpass[((size_t)b * NL + d) * kFdnAllpass + j];
       sum_ap += da;
       const float2 zdel = c_expi(__fmul_rn(wk, da));                        // :298
       ap = c_mul(ap, c_div(make_float2(1.0f + ga * zdel.x, ga * zdel.y),
@@ -94,29 +95,29 @@ __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
     lowpass[d] = c_div(make_float2(g, 0.f), make_float2(1.0f - p * zinv.x + 1e-8f, -p * zinv.y));
   }
   // M = I - F D,  F = diag(lowpass) (0.5 * 11^T - I) diag(allpass);  augmented with b   (:310-330)
-  float2 M[kFdnLines][kFdnLines + 1];
+  float2 M[NL][NL + 1];
 #pragma unroll
-  for (int i = 0; i < kFdnLines; ++i) {
+  for (int i = 0; i < NL; ++i) {
 #pragma unroll
-    for (int j = 0; j < kFdnLines; ++j) {
+    for (int j = 0; j < NL; ++j) {
       const float mix = (i == j) ? -0.5f : 0.5f;
       const float2 f = c_mul(c_mul(lowpass[i], make_float2(mix, 0.f)), allpass[j]);
       const float2 fd = c_mul(f, D[j]);
       M[i][j] = make_float2((i == j ? 1.0f : 0.0f) - fd.x, -fd.y);
     }
-    M[i][kFdnLines] = make_float2(a.input_gain[(size_t)b * kFdnLines + i], 0.f);
+    M[i][NL] = make_float2(a.input_gain[(size_t)b * NL + i], 0.f);
   }
   // Gaussian elimination with partial pivoting (row swaps done by value: fully unrolled, no
   // dynamic indexing)
 #pragma unroll
-  for (int c = 0; c < kFdnLines; ++c) {
+  for (int c = 0; c < NL; ++c) {
 #pragma unroll
-    for (int r = c + 1; r < kFdnLines; ++r) {
+    for (int r = c + 1; r < NL; ++r) {
       const float mc = M[c][c].x * M[c][c].x + M[c][c].y * M[c][c].y;
       const float mr = M[r][c].x * M[r][c].x + M[r][c].y * M[r][c].y;
       if (mr > mc) {
 #pragma unroll
-        for (int j = c; j <= kFdnLines; ++j) {
+        for (int j = c; j <= NL; ++j) {
           const float2 t = M[c][j];
           M[c][j] = M[r][j];
           M[r][j] = t;
@@ -125,21 +126,21 @@ __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
     }
     const float2 inv = c_div(make_float2(1.f, 0.f), M[c][c]);
 #pragma unroll
-    for (int r = c + 1; r < kFdnLines; ++r) {
+    for (int r = c + 1; r < NL; ++r) {
       const float2 f = c_mul(M[r][c], inv);
 #pragma unroll
-      for (int j = c + 1; j <= kFdnLines; ++j) {
+      for (int j = c + 1; j <= NL; ++j) {
         const float2 t = c_mul(f, M[c][j]);
         M[r][j] = make_float2(M[r][j].x - t.x, M[r][j].y - t.y);
       }
     }
   }
-  float2 x[kFdnLines];
+  float2 x[NL];
 #pragma unroll
-  for (int i = kFdnLines - 1; i >= 0; --i) {
-    float2 s = M[i][kFdnLines];
+  for (int i = NL - 1; i >= 0; --i) {
+    float2 s = M[i][NL];
 #pragma unroll
-    for (int j = i + 1; j < kFdnLines; ++j) {
+    for (int j = i + 1; j < NL; ++j) {
       const float2 t = c_mul(M[i][j], x[j]);
       s = make_float2(s.x - t.x, s.y - t.y);
     }
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(128) fdn_transfer_kernel(const FdnArgs a) {
   // H = c^T D x      (:322-334)
   float2 Hk = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < kFdnLines; ++i) {
+  for (int i = 0; i < NL; ++i) {
     const float2 t = c_mul(D[i], x[i]);
-    const float c = a.output_gain[(size_t)b * kFdnLines + i];
+    const float c = a.output_gain[(size_t)b * NL + i];
     Hk.x += c * t.x;
     Hk.y += c * t.y;
   }

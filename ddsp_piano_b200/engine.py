@@ -370,17 +370,20 @@ class Engine:
 
     def fdn_ir(self, input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
                alpha_tone, early_ir, sampling_rate, delay_values=None):
-        """FeedbackDelayNetwork.get_ir for a batch of parameter rows -> [B, int(2 * sampling_rate)]."""
+        """FeedbackDelayNetwork.get_ir for a batch of parameter rows -> [B, int(2 * sampling_rate)].
+        The number of delay lines D (8, or 6 as in configs/ENSTDkCl-*.gin) is the last axis of
+        ``input_gain``."""
         ig = self.tensor(input_gain, 'input_gain')
         batched = ig.dim() == 2
         B = ig.shape[0] if batched else 1
+        D = int(ig.shape[-1])
         def prep(x, name, shape):
             x = self.tensor(x, name).reshape(shape)
             return x if x.is_contiguous() else x.contiguous()
-        ig = prep(ig, 'input_gain', [B, 8])
-        og = prep(output_gain, 'output_gain', [B, 8])
-        ga = prep(gain_allpass, 'gain_allpass', [B, 8, 4])
-        da = prep(delays_allpass, 'delays_allpass', [B, 8, 4])
+        ig = prep(ig, 'input_gain', [B, D])
+        og = prep(output_gain, 'output_gain', [B, D])
+        ga = prep(gain_allpass, 'gain_allpass', [B, D, 4])
+        da = prep(delays_allpass, 'delays_allpass', [B, D, 4])
         t0 = prep(time_rev_0_sec, 'time_rev_0_sec', [B])
         al = prep(alpha_tone, 'alpha_tone', [B])
         er = self.tensor(early_ir, 'early_ir')
@@ -390,15 +393,15 @@ class Engine:
         dv = None
         if delay_values is not None:
             vals = [float(v) for v in torch.as_tensor(delay_values).reshape(-1).tolist()]
-            if len(vals) != 8:
-                raise ValueError('the CUDA path implements the reference\'s fixed 8 delay lines')
-            dv = (ctypes.c_float * 8)(*vals)
+            if len(vals) != D:
+                raise ValueError(f'{len(vals)} delay values for {D} delay lines')
+            dv = (ctypes.c_float * D)(*vals)
         ws = self.workspace(self.lib.b200ddsp_fdn_workspace_bytes(self.handle, float(sampling_rate), B))
         out = torch.empty([B, n], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self.check(self.lib.b200ddsp_fdn_ir(
                 self.handle, ig.data_ptr(), og.data_ptr(), ga.data_ptr(), da.data_ptr(), t0.data_ptr(),
-                al.data_ptr(), er.data_ptr(), E, dv, float(sampling_rate), out.data_ptr(), B,
+                al.data_ptr(), er.data_ptr(), E, dv, D, float(sampling_rate), out.data_ptr(), B,
                 ws.data_ptr(), ws.numel(), self.stream()))
         return out if batched else out[0]
 

@@ -317,50 +317,94 @@ class MultiInstrumentReverb:
 
 
 class FeedbackDelayNetwork(Processor):
-    """modules/fdn_reverb.py:20-410 with ``trainable=False``: frequency-sampled feedback delay
-    network (8 delay lines, Householder mixing, one-pole reverberation-time control, 4 allpasses
-    per line, FIR early reflections).  ``get_ir`` is what
-    ``MultiInstrumentFeedbackDelayReverb`` (modules/sub_modules.py:368-446, the reverb model of
-    configs/maestro-v2.gin) calls to produce ``reverb_ir``; as a DAG processor
-    (configs/ENSTDkCl-*.gin) ``get_signal`` convolves the dry audio with that IR."""
+    """modules/fdn_reverb.py:20-410: frequency-sampled feedback delay network (Householder mixing,
+    one-pole reverberation-time control, 4 allpasses per line, FIR early reflections).  ``get_ir`` is
+    what ``MultiInstrumentFeedbackDelayReverb`` (modules/sub_modules.py:368-446, the reverb model of
+    configs/maestro-v2.gin) calls to produce ``reverb_ir``; as a DAG processor (configs/ENSTDkCl-*.gin)
+    ``get_signal`` convolves the dry audio with that IR.
+
+    ``trainable=False`` (8 lines, fdn_reverb.py:95-97): the parameters are inputs of ``get_controls``.
+    ``trainable=True`` (:121-174, the ENSTDkCl gins with 6 lines and trainable delays): the processor owns
+    them -- ``self.parameters``, drawn like the reference's initialisers or set with
+    :meth:`load_parameters` from a checkpoint -- and ``get_controls(audio_dry)`` needs nothing else.
+    Forward only: nothing here computes gradients."""
+
+    PARAMETERS = ('input_gain', 'output_gain', 'gain_allpass', 'delays_allpass', 'time_rev_0_sec',
+                  'alpha_tone', 'early_ir')
 
     def __init__(self, trainable=False, name='DelayNetwork', sampling_rate=16000.0, delay_lines=8,
                  delay_values=None, delays_allpass=None, early_ir_length=200, early_reflections=6,
-                 time_control_bands=6, delay_trainable=False):
+                 time_control_bands=6, delay_trainable=False, seed=0):
         super().__init__(name=name, trainable=trainable)
-        if trainable:
-            raise ValueError('FeedbackDelayNetwork(trainable=True) owns tf.Variables in the reference; '
-                             'the hot path implements the trainable=False form (parameters are inputs)')
-        if delay_lines != 8:
-            raise ValueError('the reference fixes the network to 8 delay lines')
         self.sampling_rate = float(sampling_rate)
         self.freq_points = int(2 * self.sampling_rate)
         self.delay_values = delay_values
         self.delays_allpass = delays_allpass
         self.early_ir_length = early_ir_length
         self.delay_lines = delay_lines
+        self.delay_trainable = delay_trainable
+        self.parameters = None
+        self._seed = seed
+        self.build()
 
     def __len__(self):
         return self.delay_lines
 
     def build(self, input_shape=None):
-        """The reference fills in its fixed delay values here (fdn_reverb.py:93-97)."""
-        if self.delay_values is None:
+        """fdn_reverb.py:92-175: fixed delay values unless they are trainable; the variables of the
+        trainable form, from the reference's initialisers (normal(0.25, 0.1) gains, normal(400, 60) delays,
+        normal(2, 0.5) >= 0 reverberation time, normal(0, 0.1) early response and tone)."""
+        if self.delay_values is None and not (self.trainable and self.delay_trainable):
             self.delay_values = [233., 311., 421., 461., 587., 613., 789., 891.]
+            self.delay_lines = len(self.delay_values)
+        if self.delay_lines not in (6, 8):
+            raise ValueError(f'delay_lines={self.delay_lines}: the kernels are built for 8 lines '
+                             '(fdn_reverb.py:30) or 6 (configs/ENSTDkCl-*.gin)')
+        if self.trainable and self.parameters is None:
+            g = torch.Generator().manual_seed(self._seed)
+            D = self.delay_lines
+            normal = lambda mean, std, *shape: torch.normal(mean, std, size=shape, generator=g)
+            self.parameters = {
+                'early_ir': normal(0.0, 0.1, self.early_ir_length),
+                'input_gain': normal(0.25, 0.1, D), 'output_gain': normal(0.25, 0.1, D),
+                'time_rev_0_sec': normal(2.0, 0.5, 1).clamp_min(0.0), 'alpha_tone': normal(0.0, 0.1, 1),
+                'delays_allpass': normal(400.0, 60.0, D, 4), 'gain_allpass': normal(0.25, 0.1, D, 4)}
+            if self.delay_trainable and self.delay_values is None:
+                self.parameters['delay_values'] = normal(400.0, 60.0, D)
+
+    def load_parameters(self, values):
+        """Set the variables of the trainable form (raw values: ``alpha_tone`` BEFORE its sigmoid, like the
+        reference's variable ``_alpha_tone``)."""
+        if not self.trainable:
+            raise ValueError('only FeedbackDelayNetwork(trainable=True) owns parameters')
+        for k, v in values.items():
+            if k not in self.parameters and k != 'delay_values':
+                raise KeyError(k)
+            self.parameters[k] = torch.as_tensor(v, dtype=torch.float32).reshape(
+                self.parameters[k].shape if k in self.parameters else [self.delay_lines])
 
     def _engine(self, *tensors):
         return get_engine(_device_of(*tensors), **_DEFAULT_CFG)
 
     def get_ir(self, input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
-               alpha_tone, early_ir):
-        return self._engine(input_gain, early_ir).fdn_ir(
-            input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec, alpha_tone,
-            early_ir, self.sampling_rate, self.delay_values)
+               alpha_tone, early_ir, device=None):
+        delays = self.delay_values
+        if self.trainable and self.parameters.get('delay_values') is not None:
+            delays = self.parameters['delay_values']
+        eng = get_engine(device, **_DEFAULT_CFG) if device is not None else self._engine(input_gain, early_ir)
+        return eng.fdn_ir(input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec, alpha_tone,
+                          early_ir, self.sampling_rate, delays)
 
     def get_controls(self, audio_dry=None, input_gain=None, output_gain=None, gain_allpass=None,
                      delays_allpass=None, time_rev_0_sec=None, alpha_tone=None, early_ir=None):
-        ir = self.get_ir(input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
-                         alpha_tone, early_ir)
+        if self.trainable:                                              # fdn_reverb.py:382-391
+            dev = _device_of(audio_dry)
+            p = {k: self.parameters[k].to(dev) for k in self.PARAMETERS}
+            p['alpha_tone'] = torch.sigmoid(p['alpha_tone'])
+            ir = self.get_ir(**p, device=dev)
+        else:
+            ir = self.get_ir(input_gain, output_gain, gain_allpass, delays_allpass, time_rev_0_sec,
+                             alpha_tone, early_ir)
         return {'audio': audio_dry, 'ir': ir}
 
     def get_signal(self, audio, ir):
@@ -444,9 +488,18 @@ class ProcessorGroup:
         if has_reverb:
             r = dag[-1]
             reverb = self._modules[r[0]]
-            if not isinstance(reverb, Reverb) or len(r[1]) != 2 or r[1][0] != sum_name + '/signal':
+            if r[1][0] != sum_name + '/signal':
                 return None
-            ir_key = r[1][1]
+            if isinstance(reverb, FeedbackDelayNetwork):
+                # configs/ENSTDkCl-*.gin:99-100: the network itself closes the DAG (its parameters are its
+                # own, or -- trainable=False -- 7 more feature keys)
+                if len(r[1]) != (1 if reverb.trainable else 8):
+                    return None
+                ir_key = list(r[1][1:])
+            elif isinstance(reverb, Reverb) and len(r[1]) == 2:
+                ir_key = r[1][1]
+            else:
+                return None
         if int(additive.sample_rate) != int(noise.sample_rate) or \
                 int(additive.frame_rate) != int(noise.frame_rate):
             return None
@@ -467,14 +520,26 @@ class ProcessorGroup:
                            'magnitudes': get(mag_key), 'noise': noise.pop_noise()})
         M = voices[0]['magnitudes'].shape[-1]
         cfg = {**_DEFAULT_CFG, **additive.engine_config(), **noise.engine_config(M)}
-        if reverb is not None:
+        fdn_tail = isinstance(reverb, FeedbackDelayNetwork)
+        if reverb is not None and not fdn_tail:
             cfg.update(reverb.engine_config())
         f0_0 = voices[0]['f0_hz']
         on_host = not (isinstance(f0_0, torch.Tensor) and f0_0.device.type == 'cuda')
         dev = torch.device('cuda', torch.cuda.current_device()) if on_host else f0_0.device
         eng = get_engine(dev, **cfg)
-        ir = nested_lookup(plan['ir_key'], outputs) if reverb is not None else None
+        ir = nested_lookup(plan['ir_key'], outputs) if reverb is not None and not fdn_tail else None
         seed = (noise.seed + 0x9E3779B97F4A7C15 * noise.next_stream_id(len(voices))) & (2 ** 64 - 1)
+        if fdn_tail:
+            # additive + noise + sums fused as above; the network's own two steps close the DAG:
+            # get_controls (the impulse response, two kernels) and get_signal (FFT convolution, no dry path)
+            if timeline is not None or on_host:
+                raise ValueError('a DAG closed by FeedbackDelayNetwork takes whole clips of device tensors')
+            dry, _ = eng.forward_polyphonic(voices, reverb_ir=None, seed=seed)
+            ctl = reverb.get_controls(dry, *[nested_lookup(k, outputs) for k in plan['ir_key']])
+            outputs[plan['add'].name] = {'signal': dry, 'controls': {}}
+            outputs[reverb.name] = {'signal': reverb.get_signal(ctl['audio'], ctl['ir']), 'controls': ctl}
+            outputs['out'] = outputs[reverb.name]
+            return outputs
         if timeline is not None:
             # one span of a timeline (sharding.SpanChain): the features cover the span's input frames
             if reverb is None:

@@ -311,18 +311,19 @@ int b200ddsp_fft_convolve(b200ddsp_handle* h, const float* audio, const float* i
                           void* stream);
 
 /* FeedbackDelayNetwork.get_ir -- modules/fdn_reverb.py:339-360 over get_late_ir :178-337: the
- * impulse response of the 8-line feedback delay network that modules/sub_modules.py:368-446
- * (MultiInstrumentFeedbackDelayReverb, configs/maestro-v2.gin:118-122) feeds to effects.Reverb.
- * All parameters are device tensors, one row per batch element: input_gain, output_gain [B,8],
- * gain_allpass, delays_allpass [B,8,4], time_rev_0_sec, alpha_tone [B], early_ir [B,E].
- * delay_values: HOST array of 8 delay-line lengths, or NULL for the reference's fixed values
- * (fdn_reverb.py:96).  ir_out [B, n], n = (int)(2 * sampling_rate).  workspace >=
- * b200ddsp_fdn_workspace_bytes(). */
+ * impulse response of the feedback delay network that modules/sub_modules.py:368-446
+ * (MultiInstrumentFeedbackDelayReverb, configs/maestro-v2.gin:118-122) feeds to effects.Reverb, and
+ * that configs/ENSTDkCl-*.gin:99-100,118-122 put at the end of the DAG itself.  delay_lines = D: 8
+ * (fdn_reverb.py:30) or 6 (ENSTDkCl gins).  All parameters are device tensors, one row per batch
+ * element: input_gain, output_gain [B,D], gain_allpass, delays_allpass [B,D,4], time_rev_0_sec,
+ * alpha_tone [B], early_ir [B,E].  delay_values: HOST array of D delay-line lengths, or NULL (D = 8
+ * only) for the reference's fixed values (fdn_reverb.py:96).  ir_out [B, n], n = (int)(2 *
+ * sampling_rate).  workspace >= b200ddsp_fdn_workspace_bytes(). */
 int b200ddsp_fdn_ir(b200ddsp_handle* h, const float* input_gain, const float* output_gain,
                     const float* gain_allpass, const float* delays_allpass,
                     const float* time_rev_0_sec, const float* alpha_tone, const float* early_ir, int E,
-                    const float* delay_values, float sampling_rate, float* ir_out, int B,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    const float* delay_values, int delay_lines, float sampling_rate, float* ir_out,
+                    int B, void* workspace, size_t workspace_bytes, void* stream);
 size_t b200ddsp_fdn_workspace_bytes(const b200ddsp_handle* h, float sampling_rate, int B);
 
 /* The whole DAG of modules/polyphonic_dag.py:21-42 as wired by configs/dafx22.gin:91-100,

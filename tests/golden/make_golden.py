@@ -218,6 +218,44 @@ def make_fdn():
         print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
 
 
+def make_fdn6():
+    """tests/golden/fdn6_sr4000.npz: the 6-line network of configs/ENSTDkCl-*.gin:118-122 -- the reference's
+    modules/fdn_reverb.py executed over the stand-in with 6 delay values / gains / allpass rows (its
+    variables' shapes, drawn from its initialisers, fdn_reverb.py:121-174), then used as the DAG's last
+    processor: get_controls(audio_dry) -> get_signal.
+
+        python -c "import sys; sys.path.insert(0, 'tests/golden'); import make_golden as m; m.make_fdn6()"
+    """
+    load_reference_modules()
+    spec = importlib.util.spec_from_file_location(
+        'ddsp_piano.modules.fdn_reverb', os.path.join(REF, 'ddsp_piano', 'modules', 'fdn_reverb.py'))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['ddsp_piano.modules.fdn_reverb'] = mod
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(20240117)
+    sr, n_audio, D = 4000.0, 3000, 6
+    delay_values = rng.normal(400, 60, D).astype(np.float32)           # "Delay values" (delay_trainable)
+    fdn = mod.FeedbackDelayNetwork(trainable=False, sampling_rate=sr, delay_lines=D, delay_values=delay_values)
+    fdn.build(None)
+    assert tuple(fdn.mixing_matrix.shape) == (D, D)
+    p = dict(
+        input_gain=rng.normal(0.25, 0.1, D).astype(np.float32),
+        output_gain=rng.normal(0.25, 0.1, D).astype(np.float32),
+        gain_allpass=rng.normal(0.25, 0.1, [D, 4]).astype(np.float32),
+        delays_allpass=rng.normal(400, 60, [D, 4]).astype(np.float32),
+        time_rev_0_sec=np.maximum(rng.normal(2, 0.5, [1]), 0).astype(np.float32),
+        alpha_tone=(1 / (1 + np.exp(-rng.normal(0, 0.1, [1])))).astype(np.float32),
+        early_ir=rng.normal(0, 0.1, [200]).astype(np.float32))
+    audio = (rng.standard_normal([2, n_audio]) * 0.1).astype(np.float32)
+    ctl = fdn.get_controls(audio_dry=audio, **{k: v.copy() for k, v in p.items()})
+    ir = ctl['ir']
+    assert ir.dtype == np.float32 and ir.shape == (int(2 * sr),)
+    sig = fdn.get_signal(ctl['audio'], ir)
+    path = os.path.join(HERE, 'fdn6_sr4000.npz')
+    np.savez_compressed(path, sampling_rate=sr, audio=audio, ir=ir, signal=sig, delay_values=delay_values, **p)
+    print(f'fdn6_sr4000: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
 def make_checkpoint_fixtures():
     """Small fixtures cut from the SHIPPED checkpoints with ddsp_piano_b200/checkpoint.py (no TF):
     * dafx22_ckpt-0.index         -- verbatim copy of model_weights/dafx22/ckpt-0.index (2.5 KB), for

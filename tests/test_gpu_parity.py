@@ -823,7 +823,76 @@ def test_fdn_full_size_vs_oracle_and_into_reverb(dp, dev):
     want = ref.reverb_signal(audio.cpu().numpy(), ir.cpu().numpy())
     assert rel_err(wet, want) < TIGHT
     with pytest.raises(ValueError):
-        dp.FeedbackDelayNetwork(trainable=True)
+        dp.FeedbackDelayNetwork(trainable=True, delay_trainable=True, delay_lines=5)
+
+
+def test_fdn_six_lines_golden(dp, dev, golden_dir):
+    """configs/ENSTDkCl-*.gin:118-122: 6 delay lines with their own (trainable) delay values; vector made by
+    executing the reference's module (make_golden.py::make_fdn6)."""
+    g = load(golden_dir, 'fdn6_sr4000')
+    fdn = dp.FeedbackDelayNetwork(trainable=False, sampling_rate=float(g['sampling_rate']), delay_lines=6,
+                                  delay_values=g['delay_values'])
+    out = fdn(cu(g['audio'], dev), *[cu(g[k], dev) for k in FDN_KEYS], return_outputs_dict=True)
+    assert out['controls']['ir'].shape == g['ir'].shape
+    assert rel_err(out['controls']['ir'], g['ir']) < TIGHT
+    assert rel_err(out['signal'], g['signal']) < TIGHT
+    # the trainable form owns the same numbers (alpha_tone before its sigmoid)
+    own = dp.FeedbackDelayNetwork(trainable=True, delay_trainable=True, delay_lines=6,
+                                  sampling_rate=float(g['sampling_rate']))
+    assert own.parameters['input_gain'].shape == (6,) and own.parameters['delay_values'].shape == (6,)
+    vals = {k: g[k] for k in FDN_KEYS}
+    vals['alpha_tone'] = np.log(g['alpha_tone'] / (1 - g['alpha_tone']))
+    own.load_parameters({**vals, 'delay_values': g['delay_values']})
+    assert rel_err(own(cu(g['audio'], dev)), g['signal']) < TIGHT
+
+
+def test_dag_closed_by_the_delay_network(dp, dev):
+    """configs/ENSTDkCl-32kHz.gin:91-122: polyphonic_dag(reverb=FeedbackDelayNetwork(trainable=True,
+    delay_lines=6), reverb_controls=[]), exp_tanh scaling, normalisation before the Nyquist cut.  The
+    fused plan (one call for additive + noise + sums, then the network's two steps) against the oracle
+    and against the node-by-node walk of the same DAG."""
+    from oracle import fdn_np
+    sr, F, B, H, S, M, P = 32000, 50, 2, 96, 2, 64, 3
+    U = sr // 250
+    rng = np.random.default_rng(32)
+    feats, noises = {}, []
+    for v in range(P):
+        x = voice_inputs(rng, B, F, H, S, M)
+        for k, val in x.items():
+            feats[f'{k}_{v}'] = val
+        noises.append(rng.uniform(-1, 1, [B, F * U]).astype(np.float32))
+
+    def build(fused):
+        additive = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, scale_fn=dp.exp_tanh,
+                                      normalize_after_nyquist_cut=False, name='additive')
+        noise = dp.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, scale_fn=dp.exp_tanh, name='noise')
+        fdn = dp.FeedbackDelayNetwork(trainable=True, delay_trainable=True, delay_lines=6, sampling_rate=sr,
+                                      seed=5)
+        dag = dp.polyphonic_dag(additive=additive, noise=noise, reverb=fdn,
+                                additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+                                noise_controls=['magnitudes'], reverb_controls=[], n_synths=P)
+        for n in noises:
+            noise.push_noise(cu(n, dev))
+        return dp.ProcessorGroup(dag=dag, fused=fused), fdn
+
+    group, fdn = build(True)
+    assert group._plan is not None and group._plan['reverb'] is fdn
+    out = group({k: cu(v, dev) for k, v in feats.items()}, return_outputs_dict=True)
+    walk, _ = build(False)
+    out_walk = walk({k: cu(v, dev) for k, v in feats.items()}, return_outputs_dict=True)
+
+    want = ref.polyphonic_forward(feats, n_synths=P, sample_rate=sr, noise_by_voice=noises,
+                                  scale_fn=ref.SCALE_EXP_TANH, noise_scale_fn=ref.SCALE_EXP_TANH,
+                                  normalize_after_nyquist_cut=False, reverb=False)
+    p = {k: v.numpy() for k, v in fdn.parameters.items()}
+    ir = fdn_np.fdn_ir(p['input_gain'], p['output_gain'], p['gain_allpass'], p['delays_allpass'],
+                       p['time_rev_0_sec'], 1 / (1 + np.exp(-p['alpha_tone'])), p['early_ir'],
+                       sampling_rate=float(sr), delay_values=p['delay_values'])
+    wet = fdn_np.fdn_signal(want['dry'], ir)
+    assert rel_err(out['controls']['add']['signal'], want['dry']) < TIGHT
+    assert rel_err(out['controls']['DelayNetwork']['controls']['ir'], ir) < TIGHT
+    assert rel_err(out['signal'], wet) < TIGHT
+    assert rel_err(out_walk['signal'], wet) < TIGHT
 
 
 def test_fdn_shipped_v2_parameters(dp, dev, golden_dir):

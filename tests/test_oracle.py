@@ -271,6 +271,20 @@ def test_fdn_restatement_matches_reference_python(golden_dir, name):
     assert np.max(np.abs(ir[-200:])) < 0.2 * np.max(np.abs(ir))
 
 
+def test_fdn_restatement_six_lines(golden_dir):
+    """The 6-line network of configs/ENSTDkCl-*.gin:118-122 (trainable delays): restatement vs the
+    reference's code executed over the stand-in (tests/golden/make_golden.py::make_fdn6)."""
+    from oracle import fdn_np
+    g = load(golden_dir, 'fdn6_sr4000')
+    keys = ('input_gain', 'output_gain', 'gain_allpass', 'delays_allpass', 'time_rev_0_sec',
+            'alpha_tone', 'early_ir')
+    assert g['input_gain'].shape == (6,) and g['delay_values'].shape == (6,)
+    ir = fdn_np.fdn_ir(*[g[k] for k in keys], sampling_rate=float(g['sampling_rate']),
+                       delay_values=g['delay_values'])
+    assert np.max(np.abs(ir - g['ir'])) <= 2e-6 * np.max(np.abs(g['ir']))
+    np.testing.assert_array_equal(fdn_np.fdn_signal(g['audio'], g['ir']), g['signal'])
+
+
 @pytest.mark.parametrize('name', ['surrogate_16k', 'surrogate_24k_h40'])
 def test_surrogate_restatement_matches_reference_execution(golden_dir, name):
     """SurrogateAdditive (surrogate_synth.py), goldens from tests/golden/make_golden_surrogate.py:
