@@ -846,6 +846,40 @@ def test_fdn_six_lines_golden(dp, dev, golden_dir):
     assert rel_err(own(cu(g['audio'], dev)), g['signal']) < TIGHT
 
 
+def test_dag_of_multi_instruments_gin(dp, dev):
+    """configs/multi_instruments.gin:84-109: exp_tanh scaling, normalisation before the Nyquist cut and
+    effects.Reverb(add_dry=False) fed by reverb_ir -- the fused plan (device and host features) vs the oracle."""
+    sr, F, B, H, S, M, P, L = 16000, 60, 2, 96, 2, 64, 3, 3000
+    U = sr // 250
+    rng = np.random.default_rng(107)
+    feats, noises = {}, []
+    for v in range(P):
+        for k, val in voice_inputs(rng, B, F, H, S, M).items():
+            feats[f'{k}_{v}'] = val
+        noises.append(rng.uniform(-1, 1, [B, F * U]).astype(np.float32))
+    feats['reverb_ir'] = (rng.standard_normal([B, L]) * np.exp(-6 * np.arange(L) / L) * 1e-2).astype(np.float32)
+    want = ref.polyphonic_forward(feats, n_synths=P, sample_rate=sr, noise_by_voice=noises, add_dry=False,
+                                  scale_fn=ref.SCALE_EXP_TANH, noise_scale_fn=ref.SCALE_EXP_TANH,
+                                  normalize_after_nyquist_cut=False)
+    additive = dp.MultiInharmonic(frame_rate=250, sample_rate=sr, inference=True, scale_fn=dp.exp_tanh,
+                                  normalize_after_nyquist_cut=False, name='additive')
+    noise = dp.DynamicSizeFilteredNoise(frame_rate=250, sample_rate=sr, scale_fn=dp.exp_tanh, name='noise')
+    dag = dp.polyphonic_dag(additive=additive, noise=noise, reverb=dp.Reverb(trainable=False, add_dry=False),
+                            additive_controls=['amplitudes', 'harmonic_distribution', 'inharm_coef', 'f0_hz'],
+                            noise_controls=['magnitudes'], reverb_controls=['reverb_ir'], n_synths=P)
+    group = dp.ProcessorGroup(dag=dag)
+    assert group._plan is not None
+    for host in (False, True):
+        for n in noises:
+            noise.push_noise(torch.from_numpy(n) if host else cu(n, dev))
+        x = {k: (torch.from_numpy(v) if host else cu(v, dev)) for k, v in feats.items()}
+        out = group(x, return_outputs_dict=True)
+        torch.cuda.synchronize()
+        assert rel_err(out['controls']['add']['signal'], want['dry']) < TIGHT
+        assert rel_err(out['signal'], want['signal']) < TIGHT
+    assert rel_err(want['signal'], want['dry']) > 0.5            # really no dry path in the output
+
+
 def test_dag_closed_by_the_delay_network(dp, dev):
     """configs/ENSTDkCl-32kHz.gin:91-122: polyphonic_dag(reverb=FeedbackDelayNetwork(trainable=True,
     delay_lines=6), reverb_controls=[]), exp_tanh scaling, normalisation before the Nyquist cut.  The
