@@ -840,8 +840,11 @@ static int persistent_grid(const b200ddsp_handle* h, long long max_items, int ct
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// small_kernels_done / ends_done: optional events recorded after the work lists are built / after the
+// phase pass proper, in front of the scan.
 static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame_ready,
-                               cudaStream_t st, cudaEvent_t small_kernels_done = nullptr) {
+                               cudaStream_t st, cudaEvent_t small_kernels_done = nullptr,
+                               cudaEvent_t ends_done = nullptr) {
   const AdditiveArgs& a = r.a;
   const int R = r.P * r.B;
   const bool carry = r.span && r.span->carry;
@@ -894,7 +897,13 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       launch_additive_ends(fa, persistent_grid(h, (long long)R * r.n_chunks * r.sets, 4), st);
       CHECK_LAUNCH_ON(h, "additive_fast_kernel<ends>", st);
     }
+    if (ends_done) CUDA_TRY(h, cudaEventRecord(ends_done, st));
     if (r.n_chunks > 1 || carry || (r.span && r.span->seeded)) {
+      if (r.span && r.span->phase.seed && r.span->phase.seed_ready) {
+        // the predecessor's state may still be on its way: hold the stream, not the SMs (link.cuh)
+        link_gate_kernel<<<1, 32, 0, st>>>(r.span->phase.seed_ready, r.span->phase.epoch, r.span->phase.scratch);
+        CHECK_LAUNCH_ON(h, "link_gate_kernel", st);
+      }
       OffsetsArgs oa{};
       oa.offsets = a.offsets;
       oa.ends_na = r.ends_na;
@@ -1779,7 +1788,13 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     }
     return B200DDSP_OK;
   };
-  static const int noise_mode = env_int("B200DDSP_NOISE_STREAM", 1);   // 0 after the oscillators, 1 from the start, 2 after the work lists, 3 after the phase pass (measured: 1 and 2 equal, 0 is 2 % slower)
+  // 0 after the oscillators, 1 from the start, 2 after the work lists, 3 after the scan, 4 after the phase
+  // pass in front of the scan (measured on whole clips: 1 and 2 equal, 0 is 2 % slower).  A span that takes
+  // its phase state from a PEER waits for it in front of the scan -- the later in the chain, the longer --
+  // so there the noise synth is started at that point (4) and runs under the wait.
+  static const int noise_env = env_int("B200DDSP_NOISE_STREAM", -1);
+  const bool waits_for_peer = span && span->phase.seed && span->phase.seed_ready;
+  const int noise_mode = noise_env >= 0 ? noise_env : (waits_for_peer && run.fast ? 4 : 1);
   const bool noise_beside = noise_mode != 0;
   auto fork_noise = [&](bool record) -> int {
     if (record) CUDA_TRY(h, cudaEventRecord(h->ev_noise_fork, st));
@@ -1838,10 +1853,11 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   // the noise joins once the small latency-bound kernels of the phase pass are behind us (the
   // event is recorded after the work lists are built): it then shares the SMs with the long
   // phase and oscillator kernels only
-  if (int rc = additive_phase_pass(h, run, run.fast, st, noise_mode == 2 ? h->ev_noise_fork : nullptr))
+  if (int rc = additive_phase_pass(h, run, run.fast, st, noise_mode == 2 ? h->ev_noise_fork : nullptr,
+                                   noise_mode == 4 ? h->ev_noise_fork : nullptr))
     return rc;
   if (noise_mode >= 2)
-    if (int rc = fork_noise(noise_mode != 2)) return rc;
+    if (int rc = fork_noise(noise_mode == 3)) return rc;
 
   // 2. per voice group: the oscillator bank -> partial signals (its harmonic distribution was
   //    prepared on the side stream, see below)

@@ -50,6 +50,14 @@ __device__ __forceinline__ void link_wait(const unsigned long long* counter, uns
   }
 }
 
+// One thread on the stream instead of a grid of waiting CTAs: launched in front of a kernel that reads an
+// inbox, it holds the STREAM until the peer's payload has arrived and leaves the SMs to whatever runs on the
+// other streams meanwhile (a grid that spins in its CTAs keeps every thread slot of the GPU occupied).
+__global__ void __launch_bounds__(32) link_gate_kernel(const unsigned long long* counter, unsigned long long want,
+                                                       unsigned long long* scratch) {
+  if (threadIdx.x == 0) link_wait(counter, want, scratch);
+}
+
 // Called by every CTA (all threads) after its last store of a payload / last read of an inbox: the
 // CTA that arrives last raises the counters.  `n_ctas` CTAs take part.
 __device__ __forceinline__ void link_arrive(const Link& lk, unsigned int n_ctas, bool wrote_carry,
