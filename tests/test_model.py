@@ -258,6 +258,23 @@ def test_v2_controls_match_the_oracle_on_gpu(v2_weights):
 
 
 @pytest.mark.gpu
+def test_v2_reverb_ir_is_cached_for_frozen_weights(v2_weights):
+    """inference=True: the network's response is computed once per set of instrument ids; inference=False
+    evaluates it on every call like the reference (sub_modules.py:413-446)."""
+    import ddsp_piano_b200 as dp
+    cond, pedal, pm = midi_clip(B=2, T=50, seed=6)
+    x = {'conditioning': cond, 'pedal': pedal, 'piano_model': pm}
+    model = dp.maestro_v2_model(v2_weights, device='cuda:0')
+    a = model.compute_controls(x)['reverb_ir']
+    b = model.compute_controls(x)['reverb_ir']
+    assert b is a and len(model.reverb_model.ir_cache) == 1
+    fresh = dp.maestro_v2_model(v2_weights, device='cuda:0', inference=False)
+    c = fresh.compute_controls(x)['reverb_ir']
+    d = fresh.compute_controls(x)['reverb_ir']
+    assert d is not c and torch.equal(c, d) and torch.equal(a, c) and not fresh.reverb_model.ir_cache
+
+
+@pytest.mark.gpu
 def test_v2_midi_to_audio(v2_weights):
     """The reference's default model (maestro-v2.gin, 24 kHz, one string per note, FDN reverb) from
     MIDI conditioning to audio: a sustained A4 peaks at its (slightly stretched) 440 Hz."""
