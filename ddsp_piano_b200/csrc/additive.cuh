@@ -293,24 +293,30 @@ __global__ void __launch_bounds__(kAddThreads) additive_kernel(const AdditiveArg
 // not associative and the reference's order is part of its output), so: one CTA per (row, substring,
 // block of 32 partials); all threads stage a tile of chunk ends in shared memory (coalesced: 32
 // consecutive partials per chunk), ONE warp walks the tile adding sequentially, all threads store the
-// wrapped offsets.  A 1152-chunk span costs the same few microseconds as a 72-chunk clip.
+// wrapped offsets.
 // ends_na (optional): 16-partial half-groups >= ends_na[row, c] were not computed for chunk c and count
 // as 0 (no later chunk reads their offset).
 // Spans of a timeline (b200ddsp_span): the sum starts from the predecessor's state `link.seed` instead
 // of 0 and its final value (including the LAST chunk's end, carry_all) goes to `link.carry` -- which
 // may be the successor GPU's inbox; see link.cuh for the hand-off.
-constexpr int kOffTile = 128;   // chunks per shared-memory tile
+constexpr int kOffTileMax = 1536;   // chunks per shared-memory tile at most (33 floats each: 198 KB)
 
 struct OffsetsArgs {
   float* offsets;                 // [n_osc_rows, n_chunks, H]
   const unsigned char* ends_na;   // [n_osc_rows / S, n_chunks] or nullptr
   int n_osc_rows, n_chunks, H, S;
   int carry_all;                  // the last chunk's end phase is part of the sum (a carry is wanted)
+  int tile_chunks;                // chunks per tile: min(n_chunks, kOffTileMax); dynamic smem = 33 floats each
   Link link;                      // payload [n_osc_rows, H]
 };
 
-__global__ void __launch_bounds__(256) additive_offsets_kernel(const OffsetsArgs a) {
-  __shared__ float tile[kOffTile][33];
+// The tile holds as many chunks as fit (a config-4 span of 1152 chunks is ONE tile): all loads of the tile are
+// in flight together, one warp then adds through it, and -- what the next rank of a chain is waiting for --
+// the carry leaves and its flag is raised BEFORE the wrapped offsets are written back.
+__global__ void __launch_bounds__(512) additive_offsets_kernel(const OffsetsArgs a) {
+  extern __shared__ float off_tile[];                  // [tile_chunks][33] floats, then [tile_chunks] bytes
+  unsigned char* na_s = reinterpret_cast<unsigned char*>(off_tile + (size_t)a.tile_chunks * 33);
+  const int n_warps = blockDim.x >> 5;                 // 8, or 16 for long spans (more loads in flight)
   const int hb = (a.H + 31) / 32;
   const int rs = blockIdx.x / hb, h0 = (blockIdx.x - rs * hb) * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,39 +327,47 @@ __global__ void __launch_bounds__(256) additive_offsets_kernel(const OffsetsArgs
   const Link& lk = a.link;
   float cum = 0.f;
   if (lk.seed != nullptr) {
-    if (threadIdx.x == 0) link_wait(lk.seed_ready, lk.epoch, lk.scratch);
+    if (threadIdx.x == 0) link_wait(lk.seed_ready, lk.epoch, lk.scratch);   // (a gate kernel has waited already)
     __syncthreads();
     if (warp == 0 && h < a.H) cum = ld_inbox(lk.seed + (size_t)rs * a.H + h);
   }
   const int last_end = a.carry_all ? a.n_chunks : a.n_chunks - 1;   // chunks whose end phase counts
-  for (int c0 = 0; c0 < a.n_chunks; c0 += kOffTile) {
-    const int nc = min(kOffTile, a.n_chunks - c0);
-    for (int j = warp; j < nc; j += 8) {
+  bool arrived = false;
+  for (int c0 = 0; c0 < a.n_chunks; c0 += a.tile_chunks) {
+    const int nc = min(a.tile_chunks, a.n_chunks - c0);
+    for (int j = threadIdx.x; j < nc; j += blockDim.x) na_s[j] = na ? na[c0 + j] : (unsigned char)255;
+    __syncthreads();
+#pragma unroll 16
+    for (int j = warp; j < nc; j += n_warps) {
       const int c = c0 + j;
-      const bool have = (h < a.H) && (c < last_end) && (na == nullptr || group < (int)na[c]);
-      tile[j][lane] = have ? p[(size_t)c * a.H] : 0.f;
+      const bool have = (h < a.H) && (c < last_end) && (group < (int)na_s[j]);
+      off_tile[j * 33 + lane] = have ? p[(size_t)c * a.H] : 0.f;
     }
     __syncthreads();
     if (warp == 0) {
 #pragma unroll 8
       for (int j = 0; j < nc; ++j) {
-        const float e = tile[j][lane];
-        tile[j][lane] = cum;             // offset of chunk c0 + j, unwrapped
+        const float e = off_tile[j * 33 + lane];
+        off_tile[j * 33 + lane] = cum;   // offset of chunk c0 + j, unwrapped
         cum = __fadd_rn(cum, e);
       }
     }
+    if (c0 + nc >= a.n_chunks) {         // last tile: hand the state on first
+      if (lk.carry != nullptr) {
+        if (threadIdx.x == 0 && lk.carry_ack != nullptr && lk.epoch > 2)
+          link_wait(lk.carry_ack, lk.epoch - 2, lk.scratch);
+        __syncthreads();
+        if (warp == 0 && h < a.H) lk.carry[(size_t)rs * a.H + h] = cum;
+      }
+      link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr);
+      arrived = true;
+    }
     __syncthreads();
-    for (int j = warp; j < nc; j += 8)
-      if (h < a.H) p[(size_t)(c0 + j) * a.H] = floormod_two_pi(tile[j][lane]);
+    for (int j = warp; j < nc; j += n_warps)
+      if (h < a.H) p[(size_t)(c0 + j) * a.H] = floormod_two_pi(off_tile[j * 33 + lane]);
     __syncthreads();
   }
-  if (lk.carry != nullptr) {
-    if (threadIdx.x == 0 && lk.carry_ack != nullptr && lk.epoch > 2)
-      link_wait(lk.carry_ack, lk.epoch - 2, lk.scratch);
-    __syncthreads();
-    if (warp == 0 && h < a.H) lk.carry[(size_t)rs * a.H + h] = cum;
-  }
-  link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr);
+  if (!arrived) link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr);   // n_chunks == 0
 }
 
 }  // namespace b200ddsp

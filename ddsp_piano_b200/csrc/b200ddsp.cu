@@ -45,6 +45,7 @@ struct b200ddsp_handle {
   cudaEvent_t ev_dry_ready = nullptr, ev_dry_home = nullptr;
   cudaStream_t aux_stream[kMaxGroups - 1] = {};   // the synthesis buckets run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {};
+  bool offsets_smem_opted_in = false;
   cudaStream_t noise_stream = nullptr;  // the noise synth runs beside the oscillator bank
   cudaEvent_t ev_noise_fork = nullptr, ev_noise_join = nullptr;
   cudaStream_t hd_stream = nullptr;     // harmonic_distribution controls run beside the phase pass
@@ -840,6 +841,19 @@ static int persistent_grid(const b200ddsp_handle* h, long long max_items, int ct
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// chunk end phases -> chunk offsets: the whole span in one shared-memory tile when it fits (additive.cuh)
+static void launch_offsets(b200ddsp_handle* h, OffsetsArgs& oa, cudaStream_t st) {
+  oa.tile_chunks = oa.n_chunks < kOffTileMax ? (oa.n_chunks > 0 ? oa.n_chunks : 1) : kOffTileMax;
+  const size_t smem = (size_t)oa.tile_chunks * (33 * sizeof(float) + 1);
+  if (!h->offsets_smem_opted_in) {   // per handle = per device
+    cudaFuncSetAttribute(additive_offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)kOffTileMax * (33 * sizeof(float) + 1)));
+    h->offsets_smem_opted_in = true;
+  }
+  const int threads = oa.n_chunks > 128 ? 512 : 256;
+  additive_offsets_kernel<<<oa.n_osc_rows * ((oa.H + 31) / 32), threads, smem, st>>>(oa);
+}
+
 // small_kernels_done / ends_done: optional events recorded after the work lists are built / after the
 // phase pass proper, in front of the scan.
 static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame_ready,
@@ -910,7 +924,7 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
       oa.n_osc_rows = R * r.S; oa.n_chunks = r.n_chunks; oa.H = r.H; oa.S = r.S;
       oa.carry_all = carry ? 1 : 0;
       if (r.span) oa.link = r.span->phase;
-      additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
+      launch_offsets(h, oa, st);
       CHECK_LAUNCH_ON(h, "additive_offsets_kernel", st);
     }
     return B200DDSP_OK;
@@ -925,7 +939,7 @@ static int additive_phase_pass(b200ddsp_handle* h, AdditiveRun& r, bool na_frame
     OffsetsArgs oa{};
     oa.offsets = a.offsets;
     oa.n_osc_rows = R * r.S; oa.n_chunks = r.n_chunks; oa.H = r.H; oa.S = r.S;
-    additive_offsets_kernel<<<R * r.S * ((r.H + 31) / 32), 256, 0, st>>>(oa);
+    launch_offsets(h, oa, st);
     CHECK_LAUNCH_ON(h, "additive_offsets_kernel", st);
   }
   if (small_kernels_done) CUDA_TRY(h, cudaEventRecord(small_kernels_done, st));
