@@ -337,11 +337,21 @@ __global__ void __launch_bounds__(512) additive_offsets_kernel(const OffsetsArgs
     const int nc = min(a.tile_chunks, a.n_chunks - c0);
     for (int j = threadIdx.x; j < nc; j += blockDim.x) na_s[j] = na ? na[c0 + j] : (unsigned char)255;
     __syncthreads();
-#pragma unroll 16
-    for (int j = warp; j < nc; j += n_warps) {
-      const int c = c0 + j;
-      const bool have = (h < a.H) && (c < last_end) && (group < (int)na_s[j]);
-      off_tile[j * 33 + lane] = have ? p[(size_t)c * a.H] : 0.f;
+    // 16 rows per warp and round, every load unconditional (clamped to a valid address; what does not count is
+    // replaced by 0 afterwards) so that all 16 are in flight before the first is stored
+    const float* p_safe = a.offsets + (size_t)rs * a.n_chunks * a.H + min(h, a.H - 1);
+    for (int j0 = warp; j0 < nc; j0 += 16 * n_warps) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = p_safe[(size_t)(c0 + min(j0 + u * n_warps, nc - 1)) * a.H];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int j = j0 + u * n_warps;
+        if (j < nc) {
+          const bool have = (h < a.H) && (c0 + j < last_end) && (group < (int)na_s[j]);
+          off_tile[j * 33 + lane] = have ? v[u] : 0.f;
+        }
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(512) additive_offsets_kernel(const OffsetsArgs
         __syncthreads();
         if (warp == 0 && h < a.H) lk.carry[(size_t)rs * a.H + h] = cum;
       }
-      link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr);
+      link_arrive(lk, gridDim.x, lk.carry != nullptr, lk.seed != nullptr, warp == 0);
       arrived = true;
     }
     __syncthreads();

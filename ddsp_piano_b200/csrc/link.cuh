@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(32) link_gate_kernel(const unsigned long long*
 
 // Called by every CTA (all threads) after its last store of a payload / last read of an inbox: the
 // CTA that arrives last raises the counters.  `n_ctas` CTAs take part.
+// `i_wrote`: this thread stored part of the payload (only those threads pay for the system-scope fence).
 __device__ __forceinline__ void link_arrive(const Link& lk, unsigned int n_ctas, bool wrote_carry,
-                                            bool read_seed) {
-  if (lk.scratch == nullptr) return;
-  __threadfence_system();   // this thread's payload stores are visible system-wide
+                                            bool read_seed, bool i_wrote = true) {
+  if (lk.scratch == nullptr || !(wrote_carry || read_seed)) return;   // nothing to signal (uniform over the grid)
+  if (wrote_carry && i_wrote) __threadfence_system();   // this thread's payload stores are visible system-wide
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long prev = atomicAdd(lk.scratch, 1ull);

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) timeline_tail_kernel(const TimelineTailAr
       a.out[(size_t)b * span + t] = acc;
     }
   }
-  link_arrive(lk, n_ctas, produce, consume);
+  link_arrive(lk, n_ctas, produce, consume, region == 0);
 }
 
 }  // namespace b200ddsp
