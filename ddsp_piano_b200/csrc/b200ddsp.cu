@@ -461,6 +461,7 @@ struct AdditiveLayout {
   size_t offsets;    // float [R*S, n_chunks, H]   chunk end phases, then chunk offsets
   size_t mids;       // float [R*S, n_chunks, n_sub - 1, H]  phase accumulator at the sub-unit boundaries
   size_t na_frame;   // u8 [R, F]                  live partial groups per frame
+  size_t cut_index;  // u16 [R, F]                 partials below Nyquist per frame (prep kernel -> hd kernel)
   size_t synth_na;   // u8 [R, n_chunks]           live partial groups per chunk
   size_t ends_na;    // u8 [R, n_chunks]           groups whose end phase a later chunk needs
   size_t lerp;       // float [N]                  legacy-bilinear lerp weight per sample
@@ -492,6 +493,7 @@ static AdditiveLayout carve_additive(const b200ddsp_handle* h, size_t at, int P,
   const size_t n_sub = (size_t)sub_units_for(h, (int)N);
   a.mids = take(R * S * n_chunks * n_sub * H * 4);   // n_sub - 1 per chunk, n_sub with fast_phase
   a.na_frame = take(R * F);
+  a.cut_index = take(R * F * 2);
   a.synth_na = take(R * n_chunks);
   a.ends_na = take(R * n_chunks);
   a.lerp = take(N * 4);
@@ -696,6 +698,7 @@ struct AdditiveRun {
   bool fast;
   int sets, n_chunks, P, B, F, H, S, G;
   unsigned char *na_frame, *synth_na, *ends_na;
+  unsigned short* cut_index;
   PlanGroups groups;
   float* partials;
   double* frame_sum;
@@ -742,6 +745,7 @@ static int additive_begin(b200ddsp_handle* h, AdditiveRun* r, const float* amp, 
   // generic path: voice groups inside one launch (only when the forward itself is not grouped)
   r->G = (groups.n_groups == 1) ? voice_groups_for(P, B, r->n_chunks) : 1;
   r->na_frame = (unsigned char*)(base + lay.na_frame);
+  r->cut_index = (unsigned short*)(base + lay.cut_index);
   r->synth_na = (unsigned char*)(base + lay.synth_na);
   r->ends_na = (unsigned char*)(base + lay.ends_na);
   r->partials = (float*)(base + lay.partials);
@@ -1781,6 +1785,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   AdditiveControlsArgs ca = controls_args(h, B * F, H, S);
   ca.amp_out = amp; ca.hd_out = hd; ca.shifts_out = shifts; ca.f0_out = f0;
   ca.na_frame = run.fast ? run.na_frame : nullptr;
+  ca.cut_index = run.cut_index;
 
   // 3. noise of every voice -> noise slices; FilteredNoise.get_controls is fused into the taps
   //    GEMM's operand load.  It depends on the magnitudes only, so it is enqueued on its own stream
@@ -1820,9 +1825,19 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
   if (noise_mode == 1)
     if (int rc = fork_noise(true)) return rc;
 
+  // 1. everything that does not need harmonic_distribution: amplitudes, inharmonic shifts,
+  //    liveness, then the phase pass of ALL voices (chunk end phases -> chunk offsets)
+  if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->small_ready, 0));
+  {
+    StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
+    launch_additive_prep(ca, cp, P, st);
+    CHECK_LAUNCH_ON(h, "additive_prep_kernel", st);
+  }
+
   // harmonic_distribution (scale, Nyquist cut, normalise: an HBM stream over 147 MB) needs nothing
   // from the phase pass, which is bound by the FP32 pipe: it runs beside it on its own stream, one
-  // launch per voice group as the group's copy arrives
+  // launch per voice group as the group's copy arrives.  It starts after the prep kernel, which leaves it the
+  // index of the first partial above Nyquist per frame (96 square roots per frame it need not repeat).
   CUDA_TRY(h, cudaEventRecord(h->ev_hd_fork, st));
   CUDA_TRY(h, cudaStreamWaitEvent(h->hd_stream, h->ev_hd_fork, 0));
   for (int g = 0; g < w.groups.n_groups; ++g) {
@@ -1836,6 +1851,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     }
     AdditiveControlsArgs ga = ca;
     ga.hd_out = hd + (size_t)v0 * B * F * H;
+    if (ga.cut_index) ga.cut_index += (size_t)v0 * B * F;
     launch_additive_hd(ga, gp, Pg, h->hd_stream);
     CHECK_LAUNCH_ON(h, "additive_hd_kernel", h->hd_stream);
     CUDA_TRY(h, cudaEventRecord(h->ev_hd_done[g], h->hd_stream));
@@ -1856,14 +1872,7 @@ static int forward_core(b200ddsp_handle* h, const b200ddsp_voice* voices, int P,
     CUDA_TRY(h, cudaEventRecord(h->ev_ir_spectra, h->hd_stream));
   }
 
-  // 1. everything that does not need harmonic_distribution: amplitudes, inharmonic shifts,
-  //    liveness, then the phase pass of ALL voices (chunk end phases -> chunk offsets)
-  if (sync) CUDA_TRY(h, cudaStreamWaitEvent(st, sync->small_ready, 0));
-  {
-    StageTimer tm(h, B200DDSP_STAGE_CONTROLS, st);
-    launch_additive_prep(ca, cp, P, st);
-    CHECK_LAUNCH_ON(h, "additive_prep_kernel", st);
-  }
+  // (the phase pass of ALL voices follows: chunk end phases -> chunk offsets)
   // the noise joins once the small latency-bound kernels of the phase pass are behind us (the
   // event is recorded after the work lists are built): it then shares the SMs with the long
   // phase and oscillator kernels only

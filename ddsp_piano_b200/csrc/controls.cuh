@@ -19,6 +19,9 @@ struct AdditiveControlsArgs {
   float* f0_out;           // [P*B, F, S] copy (get_controls returns f0_hz unchanged), or nullptr
   unsigned char* na_frame; // [P*B, F] number of leading 16-partial half-groups that can sound
                            // (additive_fast.cuh), or nullptr
+  unsigned short* cut_index;  // [P*B, F] number of partials below Nyquist = index of the first one the cut of
+                              // get_controls removes: written by the prep kernel, read by the hd kernel
+                              // (which otherwise recomputes every partial's frequency), or nullptr
   int n_frames_voice;      // B * F
   int H, S;
   float nyquist, min_frequency;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(256) additive_prep_kernel(const AdditiveContro
     const float amp_final = __fdiv_rn(amp, (float)a.S);             // :269
     if (a.f0_out != nullptr && lane < a.S)
       a.f0_out[rf * a.S + lane] = __ldg(p.f0_in[v] + (size_t)vf * a.S + lane);
-    int na = 0;
+    int na = 0, n_below = 0;
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
       const int h = lane + 32 * j;
@@ -83,10 +86,14 @@ __global__ void __launch_bounds__(256) additive_prep_kernel(const AdditiveContro
       }
       const unsigned m = __ballot_sync(0xffffffffu, can_sound);
       if (m) na = (m >> 16) ? 2 * j + 2 : 2 * j + 1;
+      // every operation of fi is monotonic in h (f0 > 0; for f0 <= 0 nothing is ever cut), so the partials
+      // below Nyquist are the first n_below ones (without the cut: all H of them)
+      n_below += __popc(m);
     }
     if (lane == 0) {
       a.amp_out[rf] = amp_final;
       if (a.na_frame != nullptr) a.na_frame[rf] = (unsigned char)(amp_final != 0.f ? na : 0);
+      if (a.cut_index != nullptr) a.cut_index[rf] = (unsigned short)n_below;
     }
   }
 }
@@ -120,23 +127,30 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
     float d[HP];
     bool cut[HP];
     float sum = 0.f;
+    const int n_below = (a.cut_index != nullptr) ? (int)a.cut_index[rf] : -1;   // from the prep kernel
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
       const int h = lane + 32 * j;
       d[j] = 0.f;
       cut[j] = false;
       if (h < a.H) {
-        const float fi = __fmul_rn(__fmul_rn(f0, (float)(h + 1)), inharm_factor(h, binh));
-        cut[j] = fi >= a.nyquist;
+        if (n_below >= 0) {
+          cut[j] = h >= n_below;
+        } else {
+          const float fi = __fmul_rn(__fmul_rn(f0, (float)(h + 1)), inharm_factor(h, binh));
+          cut[j] = fi >= a.nyquist;
+        }
         d[j] = apply_scale_fn(raw[e][j], a.scale_fn);               // :184-186
         sum += d[j];
       }
     }
+    // safe_divide by the frame's sum: one IEEE reciprocal per frame and a multiply per partial (within an ulp
+    // of the quotient; these are amplitudes, not phases: nothing accumulates)
     if (a.normalize_after == 0) {                                    // :194-198
       sum = warp_sum(sum);
-      const float den = (sum == 0.f) ? 1e-7f : sum;
+      const float inv = __frcp_rn((sum == 0.f) ? 1e-7f : sum);
 #pragma unroll
-      for (int j = 0; j < HP; ++j) d[j] = __fdiv_rn(d[j], den);
+      for (int j = 0; j < HP; ++j) d[j] = __fmul_rn(d[j], inv);
     }
     if (a.normalize_below) {                                         // :200-205
       sum = 0.f;
@@ -148,9 +162,9 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
     }
     if (a.normalize_after == 1) {                                    // :210-214 (2: never normalised)
       sum = warp_sum(sum);
-      const float den = (sum == 0.f) ? 1e-7f : sum;
+      const float inv = __frcp_rn((sum == 0.f) ? 1e-7f : sum);
 #pragma unroll
-      for (int j = 0; j < HP; ++j) d[j] = __fdiv_rn(d[j], den);
+      for (int j = 0; j < HP; ++j) d[j] = __fmul_rn(d[j], inv);
     }
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
