@@ -847,7 +847,9 @@ static int persistent_grid(const b200ddsp_handle* h, long long max_items, int ct
 
 // chunk end phases -> chunk offsets: the whole span in one shared-memory tile when it fits (additive.cuh)
 static void launch_offsets(b200ddsp_handle* h, OffsetsArgs& oa, cudaStream_t st) {
-  oa.tile_chunks = oa.n_chunks < kOffTileMax ? (oa.n_chunks > 0 ? oa.n_chunks : 1) : kOffTileMax;
+  int cap = env_int("B200DDSP_OFFSETS_TILE", kOffTileMax);   // tests force several tiles on short clips
+  cap = cap < 1 ? 1 : (cap > kOffTileMax ? kOffTileMax : cap);
+  oa.tile_chunks = oa.n_chunks < cap ? (oa.n_chunks > 0 ? oa.n_chunks : 1) : cap;
   const size_t smem = (size_t)oa.tile_chunks * (33 * sizeof(float) + 1);
   if (!h->offsets_smem_opted_in) {   // per handle = per device
     cudaFuncSetAttribute(additive_offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -64,6 +64,27 @@ def run_spans(dp, eng, voices, bounds, total, U, dev, P, B, S, H, seed=0):
     return torch.cat(pieces, dim=1), carries
 
 
+def test_offset_scan_in_several_tiles(dp, dev, monkeypatch):
+    """The chunk-offset scan keeps a whole span in one shared-memory tile when it fits (1536 chunks); longer
+    spans go through it tile by tile.  Forced here with tiles of 7 chunks on a 36-chunk clip and on spans with
+    a carried phase state: same bits."""
+    sr, H, S, M, P, B = 24000, 96, 2, 64, 3, 2
+    U = sr // 250
+    bounds = [(0, 125), (125, 375)]
+    total = bounds[-1][1]
+    voices = timeline_inputs(21, P, B, total, H, S, M, U, with_noise=False)
+    eng = engine_for(dp, dev, sr, M)
+    whole, _ = eng.forward_polyphonic(slice_voices(voices, 0, total, U, dev), seed=9)
+    spans, carries = run_spans(dp, eng, voices, bounds, total, U, dev, P, B, S, H, seed=9)
+    monkeypatch.setenv('B200DDSP_OFFSETS_TILE', '7')
+    whole7, _ = eng.forward_polyphonic(slice_voices(voices, 0, total, U, dev), seed=9)
+    spans7, carries7 = run_spans(dp, eng, voices, bounds, total, U, dev, P, B, S, H, seed=9)
+    torch.cuda.synchronize()
+    assert torch.equal(whole7, whole) and torch.equal(spans7, spans) and torch.equal(spans, whole)
+    for a, b in zip(carries, carries7):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('sr,H,S,M,bounds', [
     (24000, 96, 2, 64, [(0, 375), (375, 1000), (1000, 1500)]),     # BASELINE shapes, unequal spans
     (24000, 128, 1, 96, [(0, 125), (125, 250), (250, 500)]),       # v2 shapes: one string, 190-tap noise FIR
