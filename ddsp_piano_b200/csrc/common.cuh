@@ -54,13 +54,38 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   exp_tanh(x)    = 2 * (0.5 (tanh x + 1))^ln(10) + 1e-7, and 0.5 (tanh x + 1) = sigmoid(2x)
 // evaluated with the hardware exp2/log2 approximations: relative error below 1e-6, against a
 // parity budget of 1e-4 on the audio (amplitudes are not accumulated, unlike the phase).
+// One MUFU each: the flush-to-zero forms need no range scaling around the instruction, and nothing here
+// depends on a subnormal (e^-z underflows to 0 where sigmoid is 1 to within 1e-38; the result has 1e-7 added).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// The same function with its mode decided once, outside the per-element loop: no branch per element.
+struct ScaleFn {
+  float c;        // -log2(e) for exp_sigmoid, twice that for exp_tanh (the doubling is exact)
+  bool identity;
+  __device__ __forceinline__ explicit ScaleFn(int fn)
+      : c(fn == 1 ? -2.0f * 1.4426950408889634f : -1.4426950408889634f), identity(fn == 2) {}
+  __device__ __forceinline__ float operator()(float x) const {
+    const float l = lg2_ftz(1.0f + ex2_ftz(x * c));
+    const float y = ex2_ftz(__fmaf_rn(-2.302585092994046f, l, 1.0f)) + 1e-7f;
+    return identity ? x : y;
+  }
+};
+
 __device__ __forceinline__ float apply_scale_fn(float x, int fn) {
   if (fn == 2) return x;
   const float kLog2e = 1.4426950408889634f, kLn10 = 2.302585092994046f;
   const float z = (fn == 1) ? 2.0f * x : x;
-  const float t = exp2f(-z * kLog2e);              // e^-z, +inf for very negative z
-  const float l = __log2f(1.0f + t);               // -log2(sigmoid(z))
-  return exp2f(__fmaf_rn(-kLn10, l, 1.0f)) + 1e-7f;
+  const float t = ex2_ftz(-z * kLog2e);            // e^-z, +inf for very negative z
+  const float l = lg2_ftz(1.0f + t);               // -log2(sigmoid(z))
+  return ex2_ftz(__fmaf_rn(-kLn10, l, 1.0f)) + 1e-7f;
 }
 
 // ---- asynchronous bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) -----------------------------------

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
   if (vf0 >= a.n_frames_voice) return;
   const int v = blockIdx.y;
   float raw[kFramesPerWarp][HP], f0s[kFramesPerWarp], inh[kFramesPerWarp];
+  const ScaleFn scale(a.scale_fn);
 #pragma unroll
   for (int e = 0; e < kFramesPerWarp; ++e) {
     const int vf = min(vf0 + e, a.n_frames_voice - 1);
@@ -127,20 +128,27 @@ __global__ void __launch_bounds__(256) additive_hd_kernel(const AdditiveControls
     float d[HP];
     bool cut[HP];
     float sum = 0.f;
-    const int n_below = (a.cut_index != nullptr) ? (int)a.cut_index[rf] : -1;   // from the prep kernel
+    // partials below Nyquist = the first n_below (their frequencies are monotonic in h, see the prep kernel,
+    // which leaves the count in cut_index; without it the warp counts them here)
+    int n_below = 0;
+    if (a.cut_index != nullptr) {
+      n_below = (int)a.cut_index[rf];
+    } else {
+#pragma unroll
+      for (int j = 0; j < HP; ++j) {
+        const int h = lane + 32 * j;
+        bool below = false;
+        if (h < a.H) below = !(__fmul_rn(__fmul_rn(f0, (float)(h + 1)), inharm_factor(h, binh)) >= a.nyquist);
+        n_below += __popc(__ballot_sync(0xffffffffu, below));
+      }
+    }
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
       const int h = lane + 32 * j;
       d[j] = 0.f;
-      cut[j] = false;
+      cut[j] = h >= n_below;
       if (h < a.H) {
-        if (n_below >= 0) {
-          cut[j] = h >= n_below;
-        } else {
-          const float fi = __fmul_rn(__fmul_rn(f0, (float)(h + 1)), inharm_factor(h, binh));
-          cut[j] = fi >= a.nyquist;
-        }
-        d[j] = apply_scale_fn(raw[e][j], a.scale_fn);               // :184-186
+        d[j] = scale(raw[e][j]);                                    // :184-186
         sum += d[j];
       }
     }
