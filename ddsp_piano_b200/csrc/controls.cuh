@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(256) additive_prep_kernel(const AdditiveContro
     const float binh = fmaxf(inh[e], 0.f);                          // :183
     float amp = apply_scale_fn(amps[e], a.scale_fn);                // :184-186
     if (a.normalize_below) amp = __fmul_rn(amp, (f0 > a.min_frequency) ? 1.0f : 0.0f);   // :207-208
-    const float amp_final = __fdiv_rn(amp, (float)a.S);             // :269
+    // :269; by a power of two the division is a multiplication by its (exact) reciprocal
+    const float amp_final = ((a.S & (a.S - 1)) == 0)
+                                ? __fmul_rn(amp, __int_as_float(0x3f800000 - ((31 - __clz(a.S)) << 23)))
+                                : __fdiv_rn(amp, (float)a.S);
     if (a.f0_out != nullptr && lane < a.S)
       a.f0_out[rf * a.S + lane] = __ldg(p.f0_in[v] + (size_t)vf * a.S + lane);
     int na = 0, n_below = 0;

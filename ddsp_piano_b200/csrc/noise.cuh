@@ -241,6 +241,7 @@ noise_synth_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
     }
     // ---- scale (FilteredNoise.get_controls), interleave the two voices, transpose to band-major:
     //      consecutive lanes take consecutive frames (reads at stride M words, M odd: no bank conflict)
+    const ScaleFn scale(a.scale_fn);
     for (int i = threadIdx.x; i < M * L.pitch_f; i += n_threads) {
       const int j = i / L.pitch_f, fi = i - j * L.pitch_f;
       const int k = k_first + fi;
@@ -249,8 +250,8 @@ noise_synth_kernel(const NoiseArgs a, const NoiseVoicePtrs vp) {
         m.x = raw[fi * M + j];
         if (have1) m.y = raw[(L.n_in + fi) * M + j];
         if (a.scale_fn != 2) {
-          m.x = apply_scale_fn(__fadd_rn(m.x, a.bias), a.scale_fn);
-          if (have1) m.y = apply_scale_fn(__fadd_rn(m.y, a.bias), a.scale_fn);
+          m.x = scale(__fadd_rn(m.x, a.bias));
+          if (have1) m.y = scale(__fadd_rn(m.y, a.bias));
         }
       }
       ms[i] = m;
