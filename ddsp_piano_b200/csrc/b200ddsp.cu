@@ -2369,18 +2369,11 @@ static int launch_gru(b200ddsp_handle* h, const float* x_proj, const float* w_hh
   // rows per cluster: as few as keeps every cluster resident at once (the frame loop is latency-bound,
   // so small groups on many SMs win), at most what 1024 threads hold (4 lanes per unit and row pair)
   const int rb_max = 2 * (1024 / (4 * UC)) < 16 ? 2 * (1024 / (4 * UC)) : 16;
-  int RB = 2;
-  while (RB < rb_max && (int64_t)((rows + RB - 1) / RB) * CL > h->n_sms) RB *= 2;
-  const int groups = (rows + RB - 1) / RB;
-  const size_t smem = (size_t)(3 * UC * (u + 16) + 2 * RB * u) * sizeof(float) + 16;   // + two mbarriers
   static const int async_exchange = env_int("B200DDSP_GRU_ASYNC", 1);
   auto kernel = (CL > 1 && async_exchange) ? gru_recurrence_kernel<UC, CL, true> : gru_recurrence_kernel<UC, CL, false>;
-  CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto smem_for = [&](int rb) { return (size_t)(3 * UC * (u + 16) + 2 * rb * u) * sizeof(float) + 16; };   // + two mbarriers
+  CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(rb_max)));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(groups * CL));
-  cfg.blockDim = dim3((unsigned)(UC * (RB / 2) * 4));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
@@ -2388,6 +2381,34 @@ static int launch_gru(b200ddsp_handle* h, const float* x_proj, const float* w_hh
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cfg.stream = st;
+  // How many clusters of a given shape the GPU holds at once (several small CTAs share an SM) is the driver's
+  // to say; B200DDSP_GRU_RB forces a group size for A/B timing.
+  static const int forced_rb = env_int("B200DDSP_GRU_RB", 0);
+  static int cached_rows = -1, cached_rb = 0;   // the occupancy queries cost host time: once per row count
+  int RB = rb_max;
+  if (cached_rows == rows) RB = cached_rb;
+  else for (int rb = 2; rb <= rb_max; rb *= 2) {
+    const int groups_rb = (rows + rb - 1) / rb;
+    cfg.gridDim = dim3((unsigned)(groups_rb * CL));
+    cfg.blockDim = dim3((unsigned)(UC * (rb / 2) * 4));
+    cfg.dynamicSmemBytes = smem_for(rb);
+    int resident = 0;
+    if (cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      resident = h->n_sms / CL;
+    }
+    if (forced_rb == rb || (forced_rb == 0 && groups_rb <= resident)) {
+      RB = rb;
+      break;
+    }
+  }
+  cached_rows = rows;
+  cached_rb = RB;
+  const int groups = (rows + RB - 1) / RB;
+  cfg.gridDim = dim3((unsigned)(groups * CL));
+  cfg.blockDim = dim3((unsigned)(UC * (RB / 2) * 4));
+  cfg.dynamicSmemBytes = smem_for(RB);
   CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kernel, x_proj, w_hh, b_hh, out, rows, F, RB));
   CHECK_LAUNCH(h, "gru_recurrence_kernel");
   return B200DDSP_OK;
