@@ -343,7 +343,11 @@ __global__ void __launch_bounds__(512) additive_offsets_kernel(const OffsetsArgs
     for (int j0 = warp; j0 < nc; j0 += 16 * n_warps) {
       float v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = p_safe[(size_t)(c0 + min(j0 + u * n_warps, nc - 1)) * a.H];
+      for (int u = 0; u < 16; ++u) {
+        const int j = j0 + u * n_warps;
+        v[u] = 0.f;
+        if (j < nc) v[u] = p_safe[(size_t)(c0 + j) * a.H];      // predicated, not branched: still 16 in flight
+      }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int j = j0 + u * n_warps;
